@@ -1,0 +1,141 @@
+/* ovvc_b200.h -- C ABI of the B200-native reconstruction backend for OpenVVC.
+ *
+ * This is the drop-in boundary for OpenVVC's rcn_* hot path (struct RCNFunctions,
+ * libovvc/rcn_structures.h:499-694).  Plain C, plain pointers and sizes: it is what a
+ * `rcn_init_functions_cuda()` added next to rcn_init_*_functions_avx2 (libovvc/rcn.c:242-254) binds to;
+ * INTEGRATION.md shows that binding.  The CPU keeps CABAC / coding-tree parsing; each entry point below
+ * replaces one coarse reference slot (named in its comment) and works on whole pictures that live in
+ * HBM.  Every function returns 0 or a negative OVGPU_E* code; there is NO CPU fallback -- if the CUDA
+ * device or kernel image is unusable the call fails.
+ *
+ * Pictures are planar 4:2:0, one uint16_t per sample (OVSample at BITDEPTH=10, libovvc/bitdepth.h:38).
+ * Host-side planes use the OVFrame convention: data[3] + linesize[3] in BYTES (libovvc/ovframe.h:84-93).
+ */
+#ifndef OVVC_B200_H
+#define OVVC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVGPU_EINVAL   (-22)   /* bad argument                                             */
+#define OVGPU_ENOMEM   (-12)   /* host or device allocation failed                         */
+#define OVGPU_ECUDA    (-5)    /* CUDA runtime / launch error (see ovgpu_last_error)       */
+#define OVGPU_ENODEV   (-19)   /* no usable sm_100 device                                  */
+
+typedef struct OVGPUCtx OVGPUCtx;          /* one per GPU / decoder thread: stream + scratch   */
+typedef struct OVGPUPicture OVGPUPicture;  /* device-resident picture (3 planes)               */
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+/* cuda_stream: a cudaStream_t to launch on (e.g. the caller's stream), or NULL to create a private one. */
+int  ovgpu_ctx_create(OVGPUCtx **ctx, int device, void *cuda_stream);
+void ovgpu_ctx_destroy(OVGPUCtx *ctx);
+int  ovgpu_ctx_sync(OVGPUCtx *ctx);
+const char *ovgpu_last_error(const OVGPUCtx *ctx);
+/* number of kernels this context launched since creation (bench.py's "gpu_launches") */
+uint64_t ovgpu_launch_count(const OVGPUCtx *ctx);
+/* per-stage device timing with CUDA events on the context's stream */
+enum OVGPUStage { OVGPU_STAGE_ALF_LUMA = 0, OVGPU_STAGE_ALF_CHROMA, OVGPU_STAGE_SAO, OVGPU_STAGE_DBF_V,
+                  OVGPU_STAGE_DBF_H, OVGPU_STAGE_MC, OVGPU_STAGE_RESIDUAL, OVGPU_STAGE_INTRA,
+                  OVGPU_STAGE_LMCS, OVGPU_NB_STAGES };
+int  ovgpu_profile_enable(OVGPUCtx *ctx, int on);
+/* accumulated milliseconds and launch count for a stage since the last reset (syncs the stream) */
+int  ovgpu_profile_get(OVGPUCtx *ctx, int stage, double *ms, uint64_t *launches);
+int  ovgpu_profile_reset(OVGPUCtx *ctx);
+/* write `bytes` of device scratch (> L2) so the next timed launch starts cold; bench.py uses it */
+int  ovgpu_flush_l2(OVGPUCtx *ctx);
+
+/* ---- pictures  (replaces the ov_mallocz'ed planes of ovframepool_request_planes, ovframepool.c:194) --- */
+int  ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **pic);
+/* wrap caller-owned device memory (e.g. a torch tensor that NCCL broadcasts) */
+int  ovgpu_picture_wrap(OVGPUCtx *ctx, int width, int height, int bitdepth,
+                        void *const dev_planes[3], const size_t pitch_bytes[3], OVGPUPicture **pic);
+void ovgpu_picture_destroy(OVGPUPicture *pic);
+int  ovgpu_picture_upload(OVGPUCtx *ctx, OVGPUPicture *pic, const void *const data[3], const size_t linesize[3]);
+int  ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const data[3], const size_t linesize[3]);
+int  ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pitch_bytes[3]);
+int  ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src);
+
+/* ---- ALF / CC-ALF  (replaces alf.rcn_alf_filter_line, rcn_alf.c:1285, for all CTU lines of a picture,
+ *                     and alf.rcn_alf_reconstruct_coeff_APS, rcn_alf.c:264) ------------------------------ */
+#define OVGPU_ALF_NUM_SETS 24
+#define OVGPU_ALF_SET_SIZE (4 * 25 * 13)
+
+/* Byte-identical to the reference's RCNALF (rcn_alf.h:60-66) followed by the CC-ALF coefficients the
+ * reference reads from the APS (OVALFData.alf_cc_mapped_coeff, nvcl_structures.h:668). */
+typedef struct OVGPUAlfTables {
+    int16_t luma_coeff[OVGPU_ALF_NUM_SETS][OVGPU_ALF_SET_SIZE];
+    int16_t luma_clip [OVGPU_ALF_NUM_SETS][OVGPU_ALF_SET_SIZE];
+    int16_t chroma_coeff[8][7];
+    int16_t chroma_clip [8][7];
+    int16_t cc_coeff[2][4][8];
+} OVGPUAlfTables;
+
+/* Byte-identical to ALFParamsCtu (dec_structures.h:277-283). */
+typedef struct OVGPUAlfCtu {
+    uint8_t ctb_alf_flag;     /* bit2 luma, bit1 cb, bit0 cr */
+    uint8_t ctb_alf_idx;
+    uint8_t cb_alternative;
+    uint8_t cr_alternative;
+} OVGPUAlfCtu;
+
+/* APS fields rcn_alf_reconstruct_coeff_APS reads (OVALFData, nvcl_structures.h:649-669) */
+typedef struct OVGPUAlfAps {
+    uint8_t luma_clip_flag;
+    uint8_t num_luma_filters;
+    uint8_t luma_coeff_delta_idx[25];
+    int16_t luma_coeff[25][13];
+    int16_t luma_clip_idx[25][13];
+    uint8_t chroma_clip_flag;
+    uint8_t num_chroma_alts;
+    int16_t chroma_coeff[8][7];
+    int16_t chroma_clip_idx[8][7];
+} OVGPUAlfAps;
+
+/* Host-side table construction (tiny, runs once per slice on the CPU like the reference's). */
+int ovgpu_alf_reconstruct_coeff_aps(OVGPUAlfTables *tab, const OVGPUAlfAps *luma_aps, int nb_luma_aps,
+                                    const OVGPUAlfAps *chroma_aps, int bitdepth);
+
+typedef struct OVGPUAlfParams OVGPUAlfParams;   /* pinned staging + device copy of one picture's ALF state */
+int  ovgpu_alf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUAlfParams **p);
+void ovgpu_alf_params_destroy(OVGPUAlfParams *p);
+/* cc_idx[c]: ALFInfo.ctb_cc_alf_filter_idx[c] (ctudec.h:207), one byte per CTU, may be NULL when disabled */
+int  ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTables *tab,
+                             const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
+                             int cc_cb_enabled, int cc_cr_enabled);
+/* dst = ALF(src): src is the post-SAO picture; dst must be a different picture. Asynchronous. */
+int  ovgpu_alf_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUAlfParams *p);
+/* Whole call with HOST buffers: H2D of planes + params, ALF, D2H into dst planes, then stream sync. */
+int  ovgpu_alf_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t dst_linesize[3],
+                          const void *const src_data[3], const size_t src_linesize[3],
+                          int width, int height, int log2_ctu_s, int bitdepth,
+                          const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
+                          int cc_cb_enabled, int cc_cr_enabled);
+
+/* ---- SAO  (replaces sao.rcn_sao_first_pix_rows + sao.rcn_sao_filter_line, rcn_sao.c:190-293) ---------- */
+/* Compact form of SAOParamsCtu (dec_structures.h:263-274): the fields rcn_sao.c actually reads. */
+typedef struct OVGPUSaoCtu {
+    int16_t offset_val[3][5];
+    uint8_t band_position[3];
+    uint8_t eo_class[3];
+    uint8_t type_idx[3];      /* 0 off, 1 band, 2 edge */
+    uint8_t pad;
+} OVGPUSaoCtu;
+
+typedef struct OVGPUSaoParams OVGPUSaoParams;
+int  ovgpu_sao_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUSaoParams **p);
+void ovgpu_sao_params_destroy(OVGPUSaoParams *p);
+int  ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu *ctu);
+/* dst = SAO(src): src is the deblocked picture; dst must be a different picture. Asynchronous. */
+int  ovgpu_sao_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUSaoParams *p);
+int  ovgpu_sao_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t dst_linesize[3],
+                          const void *const src_data[3], const size_t src_linesize[3],
+                          int width, int height, int log2_ctu_s, int bitdepth, const OVGPUSaoCtu *ctu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVVC_B200_H */

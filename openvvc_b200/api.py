@@ -1,0 +1,250 @@
+"""Thin ctypes binding of the C ABI in include/ovvc_b200.h (libovvc_b200.so).
+
+This is what tests and bench.py call; it adds nothing to the data path.  There is no CPU fallback:
+if the library is missing it is built (nvcc), and if no sm_100 GPU is present Ctx() raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libovvc_b200.so")
+
+vp = C.c_void_p
+szp = C.POINTER(C.c_size_t)
+
+
+class AlfTables(C.Structure):
+    """OVGPUAlfTables: RCNALF (rcn_alf.h:60-66) + CC-ALF coefficients."""
+    _fields_ = [("luma_coeff", C.c_int16 * (24 * 1300)), ("luma_clip", C.c_int16 * (24 * 1300)),
+                ("chroma_coeff", C.c_int16 * (8 * 7)), ("chroma_clip", C.c_int16 * (8 * 7)),
+                ("cc_coeff", C.c_int16 * (2 * 4 * 8))]
+
+    def np(self, name):
+        shape = {"luma_coeff": (24, 4, 25, 13), "luma_clip": (24, 4, 25, 13),
+                 "chroma_coeff": (8, 7), "chroma_clip": (8, 7), "cc_coeff": (2, 4, 8)}[name]
+        return np.ctypeslib.as_array(getattr(self, name)).reshape(shape)
+
+
+class AlfAps(C.Structure):
+    """OVGPUAlfAps: the OVALFData fields rcn_alf_reconstruct_coeff_APS reads."""
+    _fields_ = [("luma_clip_flag", C.c_uint8), ("num_luma_filters", C.c_uint8),
+                ("luma_coeff_delta_idx", C.c_uint8 * 25),
+                ("luma_coeff", C.c_int16 * (25 * 13)), ("luma_clip_idx", C.c_int16 * (25 * 13)),
+                ("chroma_clip_flag", C.c_uint8), ("num_chroma_alts", C.c_uint8),
+                ("chroma_coeff", C.c_int16 * (8 * 7)), ("chroma_clip_idx", C.c_int16 * (8 * 7))]
+
+    @classmethod
+    def from_dict(cls, d):
+        a = cls()
+        a.luma_clip_flag = int(d["luma_clip_flag"])
+        a.num_luma_filters = int(d["num_luma_filters"])
+        a.luma_coeff_delta_idx[:] = [int(v) for v in d["luma_coeff_delta_idx"]]
+        a.luma_coeff[:] = np.asarray(d["luma_coeff"], dtype=np.int16).reshape(-1).tolist()
+        a.luma_clip_idx[:] = np.asarray(d["luma_clip_idx"], dtype=np.int16).reshape(-1).tolist()
+        a.chroma_clip_flag = int(d["chroma_clip_flag"])
+        a.num_chroma_alts = int(d["num_chroma_alts"])
+        a.chroma_coeff[:] = np.asarray(d["chroma_coeff"], dtype=np.int16).reshape(-1).tolist()
+        a.chroma_clip_idx[:] = np.asarray(d["chroma_clip_idx"], dtype=np.int16).reshape(-1).tolist()
+        return a
+
+
+ALF_CTU = np.dtype([("ctb_alf_flag", np.uint8), ("ctb_alf_idx", np.uint8),
+                    ("cb_alternative", np.uint8), ("cr_alternative", np.uint8)])
+SAO_CTU = np.dtype([("offset_val", np.int16, (3, 5)), ("band_position", np.uint8, 3),
+                    ("eo_class", np.uint8, 3), ("type_idx", np.uint8, 3), ("pad", np.uint8)])
+
+STAGES = {"alf_luma": 0, "alf_chroma": 1, "sao": 2, "dbf_v": 3, "dbf_h": 4, "mc": 5, "residual": 6,
+          "intra": 7, "lmcs": 8}
+
+_lib = None
+
+
+def lib():
+    """Load (building if needed) libovvc_b200.so. Raises if it cannot be built/loaded."""
+    global _lib
+    if _lib is None:
+        _build.build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ovgpu_last_error.restype = C.c_char_p
+        _lib.ovgpu_launch_count.restype = C.c_uint64
+    return _lib
+
+
+class OVGPUError(RuntimeError):
+    pass
+
+
+def _check(ctx, ret, what):
+    if ret != 0:
+        msg = lib().ovgpu_last_error(ctx).decode() if ctx else ""
+        raise OVGPUError("%s failed: %d %s" % (what, ret, msg))
+
+
+def _host_planes(planes):
+    data = (vp * 3)(*[p.ctypes.data for p in planes])
+    ls = (C.c_size_t * 3)(*[p.strides[0] for p in planes])
+    return data, ls
+
+
+def alf_tables_from_aps(luma_aps, chroma_aps, bitdepth=10):
+    """ovgpu_alf_reconstruct_coeff_aps: host-side table build (rcn_alf.c:264)."""
+    t = AlfTables()
+    arr = (AlfAps * max(1, len(luma_aps)))(*[AlfAps.from_dict(d) for d in luma_aps])
+    ca = AlfAps.from_dict(chroma_aps) if chroma_aps is not None else None
+    ret = lib().ovgpu_alf_reconstruct_coeff_aps(C.byref(t), arr, len(luma_aps),
+                                                C.byref(ca) if ca is not None else None, bitdepth)
+    _check(None, ret, "ovgpu_alf_reconstruct_coeff_aps")
+    return t
+
+
+def alf_ctu_array(ctu):
+    n = len(ctu["flag"])
+    a = np.zeros(n, dtype=ALF_CTU)
+    a["ctb_alf_flag"] = ctu["flag"]; a["ctb_alf_idx"] = ctu["idx"]
+    a["cb_alternative"] = ctu["cb_alt"]; a["cr_alternative"] = ctu["cr_alt"]
+    return a
+
+
+class Ctx:
+    def __init__(self, device=0, stream=None):
+        self.h = vp()
+        ret = lib().ovgpu_ctx_create(C.byref(self.h), device, vp(stream) if stream else None)
+        if ret != 0:
+            raise OVGPUError("ovgpu_ctx_create failed: %d (no usable sm_100 GPU?)" % ret)
+
+    def close(self):
+        if self.h:
+            lib().ovgpu_ctx_destroy(self.h)
+            self.h = vp()
+
+    def sync(self):
+        _check(self.h, lib().ovgpu_ctx_sync(self.h), "sync")
+
+    def launch_count(self):
+        return int(lib().ovgpu_launch_count(self.h))
+
+    def profile(self, on):
+        lib().ovgpu_profile_enable(self.h, int(on))
+
+    def profile_reset(self):
+        lib().ovgpu_profile_reset(self.h)
+
+    def profile_get(self, stage):
+        ms = C.c_double(); n = C.c_uint64()
+        _check(self.h, lib().ovgpu_profile_get(self.h, STAGES[stage], C.byref(ms), C.byref(n)), "profile_get")
+        return ms.value, n.value
+
+    def flush_l2(self):
+        _check(self.h, lib().ovgpu_flush_l2(self.h), "flush_l2")
+
+    # ---- pictures
+    def picture(self, w, h, bitdepth=10):
+        return Picture(self, w, h, bitdepth)
+
+    def wrap_picture(self, w, h, dev_ptrs, pitches, bitdepth=10):
+        return Picture(self, w, h, bitdepth, dev_ptrs, pitches)
+
+    # ---- host-buffer (end-to-end) calls
+    def alf_frame_host(self, planes, tables, ctu, cc_idx, cc_en=(1, 1), log2_ctu=7, bitdepth=10, out=None):
+        h, w = planes[0].shape
+        out = out or [np.empty_like(p) for p in planes]
+        sd, sl = _host_planes(planes); dd, dl = _host_planes(out)
+        ctu = np.ascontiguousarray(ctu, dtype=ALF_CTU)
+        keep = [np.ascontiguousarray(c, dtype=np.uint8) for c in cc_idx]
+        cc = (vp * 2)(keep[0].ctypes.data, keep[1].ctypes.data)
+        ret = lib().ovgpu_alf_frame_host(self.h, dd, dl, sd, sl, w, h, log2_ctu, bitdepth, C.byref(tables),
+                                         vp(ctu.ctypes.data), cc, int(cc_en[0]), int(cc_en[1]))
+        _check(self.h, ret, "ovgpu_alf_frame_host")
+        return out
+
+    def sao_frame_host(self, planes, sao_ctu, log2_ctu=7, bitdepth=10, out=None):
+        h, w = planes[0].shape
+        out = out or [np.empty_like(p) for p in planes]
+        sd, sl = _host_planes(planes); dd, dl = _host_planes(out)
+        sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SAO_CTU)
+        ret = lib().ovgpu_sao_frame_host(self.h, dd, dl, sd, sl, w, h, log2_ctu, bitdepth, vp(sao_ctu.ctypes.data))
+        _check(self.h, ret, "ovgpu_sao_frame_host")
+        return out
+
+
+class Picture:
+    def __init__(self, ctx, w, h, bitdepth=10, dev_ptrs=None, pitches=None):
+        self.ctx, self.w, self.h, self.bitdepth = ctx, w, h, bitdepth
+        self.p = vp()
+        if dev_ptrs is None:
+            ret = lib().ovgpu_picture_create(ctx.h, w, h, bitdepth, C.byref(self.p))
+        else:
+            ptrs = (vp * 3)(*dev_ptrs)
+            pit = (C.c_size_t * 3)(*pitches)
+            ret = lib().ovgpu_picture_wrap(ctx.h, w, h, bitdepth, ptrs, pit, C.byref(self.p))
+        _check(ctx.h, ret, "picture create/wrap")
+
+    def upload(self, planes):
+        d, l = _host_planes(planes)
+        _check(self.ctx.h, lib().ovgpu_picture_upload(self.ctx.h, self.p, d, l), "picture_upload")
+
+    def download(self, out=None):
+        shapes = [(self.h, self.w), (self.h // 2, self.w // 2), (self.h // 2, self.w // 2)]
+        out = out or [np.empty(s, dtype=np.uint16) for s in shapes]
+        d, l = _host_planes(out)
+        _check(self.ctx.h, lib().ovgpu_picture_download(self.ctx.h, self.p, d, l), "picture_download")
+        self.ctx.sync()
+        return out
+
+    def planes(self):
+        ptrs = (vp * 3)(); pit = (C.c_size_t * 3)()
+        lib().ovgpu_picture_planes(self.p, ptrs, pit)
+        return [int(x or 0) for x in ptrs], [int(x) for x in pit]
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_picture_destroy(self.p)
+            self.p = vp()
+
+
+class AlfParams:
+    def __init__(self, ctx, w, h, log2_ctu=7):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_alf_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "alf_params_create")
+        self._keep = None
+
+    def upload(self, tables, ctu, cc_idx, cc_en=(1, 1)):
+        ctu = np.ascontiguousarray(ctu, dtype=ALF_CTU)
+        keep = [np.ascontiguousarray(c, dtype=np.uint8) for c in cc_idx]
+        cc = (vp * 2)(keep[0].ctypes.data, keep[1].ctypes.data)
+        self._keep = (tables, ctu, keep)
+        _check(self.ctx.h, lib().ovgpu_alf_params_upload(self.ctx.h, self.p, C.byref(tables), vp(ctu.ctypes.data), cc,
+                                                         int(cc_en[0]), int(cc_en[1])), "alf_params_upload")
+
+    def run(self, dst, src):
+        _check(self.ctx.h, lib().ovgpu_alf_picture(self.ctx.h, dst.p, src.p, self.p), "alf_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_alf_params_destroy(self.p)
+            self.p = vp()
+
+
+class SaoParams:
+    def __init__(self, ctx, w, h, log2_ctu=7):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_sao_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "sao_params_create")
+
+    def upload(self, sao_ctu):
+        sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SAO_CTU)
+        self._keep = sao_ctu
+        _check(self.ctx.h, lib().ovgpu_sao_params_upload(self.ctx.h, self.p, vp(sao_ctu.ctypes.data)), "sao_params_upload")
+
+    def run(self, dst, src):
+        _check(self.ctx.h, lib().ovgpu_sao_picture(self.ctx.h, dst.p, src.p, self.p), "sao_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_sao_params_destroy(self.p)
+            self.p = vp()

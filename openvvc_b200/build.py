@@ -1,0 +1,62 @@
+"""Builds openvvc_b200/libovvc_b200.so (the C-ABI library of include/ovvc_b200.h) for sm_100a, in-tree.
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+import glob
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libovvc_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+         "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--use_fast_math", "-Xptxas", "-v"]
+
+
+def _sources():
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(CSRC, "*")) + [os.path.join(HERE, "..", "include", "ovvc_b200.h"), __file__]):
+        if os.path.isfile(f):
+            h.update(open(f, "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force=False, verbose=False):
+    stamp_file = LIB + ".stamp"
+    stamp = _stamp()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return LIB
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in _sources():
+        obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([NVCC] + FLAGS + ["-c", src, "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append("== %s\n%s" % (os.path.basename(src), out))
+        if p.returncode:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError("nvcc failed on %s" % src)
+    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"], check=True)
+    open(stamp_file, "w").write(stamp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,105 @@
+// common.cuh -- shared host/device definitions of the B200 rcn backend (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/ovvc_b200.h"
+
+struct OVGPUCtx {
+    int device;
+    cudaStream_t stream;
+    int own_stream;
+    int num_sms;
+    uint64_t launches;
+    char err[256];
+    // profiling: events bracket each stage launch when enabled
+    int profile;
+    struct StageProf {
+        double ms;
+        uint64_t n;
+    } prof[OVGPU_NB_STAGES];
+    static const int MAX_PENDING = 256;
+    struct Pending { cudaEvent_t a, b; int stage; } pending[MAX_PENDING];
+    int nb_pending;
+    cudaEvent_t ev_pool[2 * MAX_PENDING];
+    int ev_pool_init;
+    // scratch used to flush L2 between timed iterations
+    void *flush_buf;
+    size_t flush_bytes;
+};
+
+struct OVGPUPicture {
+    int width, height, bitdepth;
+    uint16_t *plane[3];
+    size_t pitch[3];      // bytes
+    int owned;            // planes allocated by us (single allocation based at plane[0])
+    void *base;
+    int device;
+};
+
+// Plane view passed by value to kernels: pitch in SAMPLES.
+struct PlaneView {
+    uint16_t *p;
+    int pitch;   // samples
+    int w, h;
+};
+
+static inline PlaneView plane_view(const OVGPUPicture *pic, int c)
+{
+    PlaneView v;
+    v.p = pic->plane[c];
+    v.pitch = (int)(pic->pitch[c] / sizeof(uint16_t));
+    v.w = c ? pic->width >> 1 : pic->width;
+    v.h = c ? pic->height >> 1 : pic->height;
+    return v;
+}
+
+int ovgpu_set_error(OVGPUCtx *ctx, int code, const char *fmt, ...);
+
+#define OVGPU_CUDA_CHECK(ctx, call)                                                          \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return ovgpu_set_error((ctx), OVGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__,   \
+                                   #call, cudaGetErrorString(e__));                          \
+    } while (0)
+
+// Stage bracket: counts the launch and, when profiling, records events around it.
+struct StageScope {
+    OVGPUCtx *ctx;
+    int slot;
+    StageScope(OVGPUCtx *c, int stage, int nb_kernels);
+    ~StageScope();
+};
+
+#define OVGPU_CEIL_DIV(a, b) (((a) + (b) - 1) / (b))
+
+// ---- device helpers ------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// 16-byte streaming loads/stores: pictures are touched once per pass, keep them out of L1
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void *p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_u4(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(void *p, uint2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+#endif

@@ -1,0 +1,227 @@
+// ctx.cu -- context, picture memory and profiling plumbing of the B200 rcn backend.
+//
+// Replaces, on the device side, the plane allocation of the reference's frame pool
+// (libovvc/ovframepool.c:194-231 -> mempool.c:73-86): pictures live in HBM with 256-byte aligned
+// pitches so that every row start is aligned for 128-bit vector access; host frames keep the OVFrame
+// convention (data[3], linesize[3] in bytes, libovvc/ovframe.h:84-93).
+#include "common.cuh"
+#include <stdarg.h>
+#include <stdlib.h>
+
+int ovgpu_set_error(OVGPUCtx *ctx, int code, const char *fmt, ...)
+{
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+StageScope::StageScope(OVGPUCtx *c, int stage, int nb_kernels) : ctx(c), slot(-1)
+{
+    ctx->launches += nb_kernels;
+    if (!ctx->profile) return;
+    if (!ctx->ev_pool_init) {
+        for (int i = 0; i < 2 * OVGPUCtx::MAX_PENDING; i++) cudaEventCreate(&ctx->ev_pool[i]);
+        ctx->ev_pool_init = 1;
+    }
+    if (ctx->nb_pending == OVGPUCtx::MAX_PENDING) {
+        double ms; uint64_t n;
+        ovgpu_profile_get(ctx, 0, &ms, &n);   // drains pending events
+    }
+    slot = ctx->nb_pending++;
+    ctx->pending[slot].a = ctx->ev_pool[2 * slot];
+    ctx->pending[slot].b = ctx->ev_pool[2 * slot + 1];
+    ctx->pending[slot].stage = stage;
+    cudaEventRecord(ctx->pending[slot].a, ctx->stream);
+}
+
+StageScope::~StageScope()
+{
+    if (slot >= 0) cudaEventRecord(ctx->pending[slot].b, ctx->stream);
+}
+
+extern "C" {
+
+int ovgpu_ctx_create(OVGPUCtx **out, int device, void *cuda_stream)
+{
+    if (!out) return OVGPU_EINVAL;
+    *out = NULL;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return OVGPU_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return OVGPU_ENODEV;
+    if (prop.major != 10) return OVGPU_ENODEV;   // kernels are built for sm_100a only
+    OVGPUCtx *ctx = (OVGPUCtx *)calloc(1, sizeof(*ctx));
+    if (!ctx) return OVGPU_ENOMEM;
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess) { free(ctx); return OVGPU_ECUDA; }
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+    } else {
+        if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { free(ctx); return OVGPU_ECUDA; }
+        ctx->own_stream = 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+void ovgpu_ctx_destroy(OVGPUCtx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_pool_init)
+        for (int i = 0; i < 2 * OVGPUCtx::MAX_PENDING; i++) cudaEventDestroy(ctx->ev_pool[i]);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    free(ctx);
+}
+
+int ovgpu_ctx_sync(OVGPUCtx *ctx)
+{
+    if (!ctx) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+const char *ovgpu_last_error(const OVGPUCtx *ctx) { return ctx ? ctx->err : "no context"; }
+uint64_t ovgpu_launch_count(const OVGPUCtx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ovgpu_profile_enable(OVGPUCtx *ctx, int on)
+{
+    if (!ctx) return OVGPU_EINVAL;
+    ctx->profile = on;
+    return 0;
+}
+
+int ovgpu_profile_get(OVGPUCtx *ctx, int stage, double *ms, uint64_t *launches)
+{
+    if (!ctx || stage < 0 || stage >= OVGPU_NB_STAGES) return OVGPU_EINVAL;
+    if (ctx->nb_pending) {
+        OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < ctx->nb_pending; i++) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ctx->pending[i].a, ctx->pending[i].b);
+            ctx->prof[ctx->pending[i].stage].ms += t;
+            ctx->prof[ctx->pending[i].stage].n += 1;
+        }
+        ctx->nb_pending = 0;
+    }
+    if (ms) *ms = ctx->prof[stage].ms;
+    if (launches) *launches = ctx->prof[stage].n;
+    return 0;
+}
+
+int ovgpu_profile_reset(OVGPUCtx *ctx)
+{
+    if (!ctx) return OVGPU_EINVAL;
+    double ms; uint64_t n;
+    ovgpu_profile_get(ctx, 0, &ms, &n);
+    memset(ctx->prof, 0, sizeof(ctx->prof));
+    return 0;
+}
+
+int ovgpu_flush_l2(OVGPUCtx *ctx)
+{
+    if (!ctx) return OVGPU_EINVAL;
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;   // 2x the 126 MB L2
+        OVGPU_CUDA_CHECK(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    OVGPU_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->flush_buf, 0x5a, ctx->flush_bytes, ctx->stream));
+    return 0;
+}
+
+// ---- pictures ---------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **out)
+{
+    if (!ctx || !out || width <= 0 || height <= 0 || (width & 7) || (height & 7)) return OVGPU_EINVAL;
+    if (bitdepth != 10 && bitdepth != 8) return OVGPU_EINVAL;
+    OVGPUPicture *pic = (OVGPUPicture *)calloc(1, sizeof(*pic));
+    if (!pic) return OVGPU_ENOMEM;
+    pic->width = width; pic->height = height; pic->bitdepth = bitdepth; pic->device = ctx->device;
+    pic->pitch[0] = align_up((size_t)width * 2, 256);
+    pic->pitch[1] = pic->pitch[2] = align_up((size_t)(width >> 1) * 2, 256);
+    size_t s0 = pic->pitch[0] * height, s1 = pic->pitch[1] * (height >> 1);
+    cudaError_t e = cudaMalloc(&pic->base, s0 + 2 * s1);
+    if (e != cudaSuccess) { free(pic); return ovgpu_set_error(ctx, OVGPU_ENOMEM, "cudaMalloc picture: %s", cudaGetErrorString(e)); }
+    pic->plane[0] = (uint16_t *)pic->base;
+    pic->plane[1] = (uint16_t *)((char *)pic->base + s0);
+    pic->plane[2] = (uint16_t *)((char *)pic->base + s0 + s1);
+    pic->owned = 1;
+    *out = pic;
+    return 0;
+}
+
+int ovgpu_picture_wrap(OVGPUCtx *ctx, int width, int height, int bitdepth,
+                       void *const dev_planes[3], const size_t pitch_bytes[3], OVGPUPicture **out)
+{
+    if (!ctx || !out || !dev_planes || !pitch_bytes || (width & 7) || (height & 7)) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++)
+        if (!dev_planes[c] || ((uintptr_t)dev_planes[c] & 15) || (pitch_bytes[c] & 15)) return OVGPU_EINVAL;
+    OVGPUPicture *pic = (OVGPUPicture *)calloc(1, sizeof(*pic));
+    if (!pic) return OVGPU_ENOMEM;
+    pic->width = width; pic->height = height; pic->bitdepth = bitdepth; pic->device = ctx->device;
+    for (int c = 0; c < 3; c++) { pic->plane[c] = (uint16_t *)dev_planes[c]; pic->pitch[c] = pitch_bytes[c]; }
+    *out = pic;
+    return 0;
+}
+
+void ovgpu_picture_destroy(OVGPUPicture *pic)
+{
+    if (!pic) return;
+    if (pic->owned) { cudaSetDevice(pic->device); cudaFree(pic->base); }
+    free(pic);
+}
+
+int ovgpu_picture_upload(OVGPUCtx *ctx, OVGPUPicture *pic, const void *const data[3], const size_t linesize[3])
+{
+    if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++) {
+        int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(pic->plane[c], pic->pitch[c], data[c], linesize[c],
+                                                (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+int ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const data[3], const size_t linesize[3])
+{
+    if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++) {
+        int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(data[c], linesize[c], pic->plane[c], pic->pitch[c],
+                                                (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return 0;
+}
+
+int ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pitch_bytes[3])
+{
+    if (!pic) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++) {
+        if (dev_planes) dev_planes[c] = pic->plane[c];
+        if (pitch_bytes) pitch_bytes[c] = pic->pitch[c];
+    }
+    return 0;
+}
+
+int ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src)
+{
+    if (!ctx || !dst || !src || dst->width != src->width || dst->height != src->height) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++) {
+        int w = c ? src->width >> 1 : src->width, h = c ? src->height >> 1 : src->height;
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst->plane[c], dst->pitch[c], src->plane[c], src->pitch[c],
+                                                (size_t)w * 2, h, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+} // extern "C"

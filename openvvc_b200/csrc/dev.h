@@ -1,0 +1,161 @@
+// dev.h -- device-code portability layer.
+//
+// Kernels are written as structs with phase functions (phase0 .. phaseN-1, separated by a CTA barrier)
+// over an explicit (tid, block index) so the SAME source compiles two ways:
+//   * nvcc, sm_100a: ovd_kernel<K> below is the __global__ entry; intrinsics map to the native
+//     Blackwell packed-16-bit instructions (VIADDMNMX.S16x2, VIMNMX.S16x2, VIADD.16x2, IDP.2A, PRMT);
+//   * g++ with -DOVGPU_HOST_EMU (tests/emu only): phases run in a serial loop over the CTA's threads and
+//     intrinsics are bit-exact C models. This is a TEST harness used to check kernel logic against the
+//     oracle on machines without a GPU; the product library never contains or calls it.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#ifdef OVGPU_HOST_EMU
+#include <stdlib.h>
+#include <vector>
+#define OVD static inline
+#define OVD_CONST static const
+struct ovd_dim3 { unsigned x, y, z; ovd_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+#else
+#include <cuda_runtime.h>
+#define OVD static __device__ __forceinline__
+#define OVD_CONST __device__ const
+typedef dim3 ovd_dim3;
+#endif
+
+// ---- packed 2 x int16 arithmetic -------------------------------------------------------------------------
+#ifdef OVGPU_HOST_EMU
+static inline int16_t ovd__lo(uint32_t v) { return (int16_t)(v & 0xffff); }
+static inline int16_t ovd__hi(uint32_t v) { return (int16_t)(v >> 16); }
+static inline uint32_t ovd__pk(int lo, int hi) { return (uint32_t)(uint16_t)lo | ((uint32_t)(uint16_t)hi << 16); }
+static inline int ovd__mn(int a, int b) { return a < b ? a : b; }
+static inline int ovd__mx(int a, int b) { return a > b ? a : b; }
+// per half: min((int16)(a+b), c)   (the add wraps to 16 bit like the hardware)
+OVD uint32_t ovd_viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{ return ovd__pk(ovd__mn((int16_t)(ovd__lo(a) + ovd__lo(b)), ovd__lo(c)), ovd__mn((int16_t)(ovd__hi(a) + ovd__hi(b)), ovd__hi(c))); }
+OVD uint32_t ovd_vmax_s16x2(uint32_t a, uint32_t b)
+{ return ovd__pk(ovd__mx(ovd__lo(a), ovd__lo(b)), ovd__mx(ovd__hi(a), ovd__hi(b))); }
+OVD uint32_t ovd_vmin_s16x2(uint32_t a, uint32_t b)
+{ return ovd__pk(ovd__mn(ovd__lo(a), ovd__lo(b)), ovd__mn(ovd__hi(a), ovd__hi(b))); }
+OVD uint32_t ovd_vadd_16x2(uint32_t a, uint32_t b)
+{ return ovd__pk(ovd__lo(a) + ovd__lo(b), ovd__hi(a) + ovd__hi(b)); }
+OVD uint32_t ovd_vsub_16x2(uint32_t a, uint32_t b)
+{ return ovd__pk(ovd__lo(a) - ovd__lo(b), ovd__hi(a) - ovd__hi(b)); }
+// a = 2 x s16, b = 4 x s8: LO: a.lo*b0 + a.hi*b1 + c ; HI: a.lo*b2 + a.hi*b3 + c
+OVD int ovd_dp2a_lo(uint32_t a, uint32_t b, int c)
+{ return c + ovd__lo(a) * (int8_t)(b & 0xff) + ovd__hi(a) * (int8_t)((b >> 8) & 0xff); }
+OVD int ovd_dp2a_hi(uint32_t a, uint32_t b, int c)
+{ return c + ovd__lo(a) * (int8_t)((b >> 16) & 0xff) + ovd__hi(a) * (int8_t)((b >> 24) & 0xff); }
+OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s)
+{
+    uint64_t v = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        uint32_t sel = (s >> (4 * i)) & 0xf;
+        uint32_t b = (uint32_t)(v >> (8 * (sel & 7))) & 0xff;
+        if (sel & 8) b = (b & 0x80) ? 0xff : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+OVD int ovd_sad(int a, int b, int c) { return c + (a > b ? a - b : b - a); }
+OVD int ovd_min(int a, int b) { return a < b ? a : b; }
+OVD int ovd_max(int a, int b) { return a > b ? a : b; }
+OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+#else
+OVD uint32_t ovd_viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
+OVD uint32_t ovd_vmax_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+OVD uint32_t ovd_vmin_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
+OVD uint32_t ovd_vadd_16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+OVD uint32_t ovd_vsub_16x2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+OVD int ovd_dp2a_lo(uint32_t a, uint32_t b, int c) { return __dp2a_lo((int)a, (int)b, c); }
+OVD int ovd_dp2a_hi(uint32_t a, uint32_t b, int c) { return __dp2a_hi((int)a, (int)b, c); }
+OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
+OVD int ovd_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }
+OVD int ovd_min(int a, int b) { return min(a, b); }
+OVD int ovd_max(int a, int b) { return max(a, b); }
+OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return min(a, b); }
+#endif
+
+OVD int ovd_clamp(int v, int lo, int hi) { return ovd_min(ovd_max(v, lo), hi); }
+
+// ---- global memory access ----------------------------------------------------------------------------------
+struct ovd_u2 { uint32_t x, y; };
+struct ovd_u4 { uint32_t x, y, z, w; };
+
+#ifdef OVGPU_HOST_EMU
+OVD ovd_u2 ovd_ld8(const void *p) { ovd_u2 r; memcpy(&r, p, 8); return r; }
+OVD ovd_u4 ovd_ld16(const void *p) { ovd_u4 r; memcpy(&r, p, 16); return r; }
+OVD void ovd_st8(void *p, ovd_u2 v) { memcpy(p, &v, 8); }
+OVD void ovd_st16(void *p, ovd_u4 v) { memcpy(p, &v, 16); }
+#else
+// streaming (touch-once) accesses: bypass L1 allocation
+OVD ovd_u2 ovd_ld8(const void *p)
+{
+    ovd_u2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+OVD ovd_u4 ovd_ld16(const void *p)
+{
+    ovd_u4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+OVD void ovd_st8(void *p, ovd_u2 v)
+{
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+OVD void ovd_st16(void *p, ovd_u4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+#endif
+
+// ---- kernel entry / emulation driver -----------------------------------------------------------------------
+// A kernel struct K provides:  Args, State, THREADS, MIN_BLOCKS, PHASES and
+//   static void phase<P>(const Args&, unsigned char *smem, State&, int tid, int bx, int by, int bz)
+#ifndef OVGPU_HOST_EMU
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const typename K::Args a)
+{
+    extern __shared__ __align__(16) unsigned char ovd_smem[];
+    typename K::State st;
+    const int tid = threadIdx.x, bx = blockIdx.x, by = blockIdx.y, bz = blockIdx.z;
+    K::template phase<0>(a, ovd_smem, st, tid, bx, by, bz);
+    if (K::PHASES > 1) { __syncthreads(); K::template phase<1>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 2) { __syncthreads(); K::template phase<2>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 3) { __syncthreads(); K::template phase<3>(a, ovd_smem, st, tid, bx, by, bz); }
+}
+
+template <class K>
+static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_t smem, cudaStream_t s)
+{
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    ovd_kernel<K><<<grid, K::THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+#else
+template <class K>
+static inline void ovd_emulate(const typename K::Args &a, ovd_dim3 grid, size_t smem_bytes)
+{
+    std::vector<typename K::State> st(K::THREADS);
+    std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
+    for (unsigned bz = 0; bz < grid.z; bz++)
+        for (unsigned by = 0; by < grid.y; by++)
+            for (unsigned bx = 0; bx < grid.x; bx++) {
+                unsigned char *sm = (unsigned char *)smem.data();
+                memset(sm, 0xcd, smem_bytes);   // poison: catches reads of unwritten shared memory
+                for (int t = 0; t < K::THREADS; t++) K::template phase<0>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 1) for (int t = 0; t < K::THREADS; t++) K::template phase<1>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 2) for (int t = 0; t < K::THREADS; t++) K::template phase<2>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 3) for (int t = 0; t < K::THREADS; t++) K::template phase<3>(a, sm, st[t], t, bx, by, bz);
+            }
+}
+#endif

@@ -1,0 +1,96 @@
+/* oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Plain-C restatement ("port") of OpenVVC's rcn_* reconstruction hot path, written from scratch at
+ * whole-picture granularity (the reference works CTU by CTU with saved rows/columns; the results are
+ * the same because both implement the VVC decoding order DBF-V -> DBF-H -> SAO -> ALF).
+ * Every function cites the reference file:line it restates.  The port is pinned by differential tests
+ * against the compiled, unmodified reference (oracle/_ref, built by oracle/Makefile) and by the golden
+ * fixtures under tests/golden/ that were generated from that reference build.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * liboracle.so.  The product path (openvvc_b200/) never does.
+ *
+ * All samples are 10-bit (or 8-bit) values stored in uint16_t, planar 4:2:0, strides in SAMPLES.
+ */
+#ifndef OVO_ORACLE_H
+#define OVO_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- ALF ------------------------------------------------------------------------------------------- */
+#define OVO_ALF_NUM_SETS      24   /* 16 fixed + 8 APS   (rcn_alf.h:48-51)                  */
+#define OVO_ALF_SET_SIZE      (4 * 25 * 13) /* transposes x classes x coeffs (rcn_alf.h:62)  */
+
+/* Same content as the reference's RCNALF (rcn_alf.h:60-66) plus the CC-ALF coefficients that the reference
+ * reads straight from the APS (rcn_alf.c:1414).  The same struct is the product's table format
+ * (include/ovvc_b200.h, OVGPUAlfTables) -- keep them identical. */
+typedef struct OVOAlfTables {
+    int16_t luma_coeff[OVO_ALF_NUM_SETS][OVO_ALF_SET_SIZE];
+    int16_t luma_clip [OVO_ALF_NUM_SETS][OVO_ALF_SET_SIZE];   /* clip VALUES (1024/32/8/2 at 10 bit) */
+    int16_t chroma_coeff[8][7];
+    int16_t chroma_clip [8][7];
+    int16_t cc_coeff[2][4][8];                                /* [cb,cr][filt_idx-1][7 used]        */
+} OVOAlfTables;
+
+/* Per-CTU parameters, raster order, one byte each (ALFParamsCtu dec_structures.h:277-283 and
+ * ALFInfo.ctb_cc_alf_filter_idx ctudec.h:207). */
+typedef struct OVOAlfCtuParams {
+    const uint8_t *ctb_alf_flag;   /* bit2 luma, bit1 cb, bit0 cr */
+    const uint8_t *ctb_alf_idx;    /* 0..23 luma filter set       */
+    const uint8_t *cb_alternative;
+    const uint8_t *cr_alternative;
+    const uint8_t *cc_idx_cb;      /* 0 = off, 1..4               */
+    const uint8_t *cc_idx_cr;
+    uint8_t cc_cb_enabled, cc_cr_enabled;
+} OVOAlfCtuParams;
+
+/* APS description used to (re)build tables: mirrors the fields of OVALFData that
+ * rcn_alf_reconstruct_coeff_APS reads (nvcl_structures.h:649-669, rcn_alf.c:196-281). */
+typedef struct OVOAlfAps {
+    uint8_t luma_clip_flag;
+    uint8_t num_luma_filters;                 /* alf_luma_num_filters_signalled_minus1 + 1 */
+    uint8_t luma_coeff_delta_idx[25];
+    int16_t luma_coeff[25][13];
+    int16_t luma_clip_idx[25][13];
+    uint8_t chroma_clip_flag;
+    uint8_t num_chroma_alts;                  /* alf_chroma_num_alt_filters_minus1 + 1     */
+    int16_t chroma_coeff[8][7];
+    int16_t chroma_clip_idx[8][7];
+} OVOAlfAps;
+
+void ovo_alf_build_tables(OVOAlfTables *t, const OVOAlfAps *luma_aps, int nb_luma_aps,
+                          const OVOAlfAps *chroma_aps, int bitdepth);
+
+/* Whole-picture ALF (+CC-ALF). src = post-SAO picture, dst = output (must not alias src). */
+void ovo_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
+                     const uint16_t *const src[3], const int src_stride[3],
+                     int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                     const OVOAlfTables *tab, const OVOAlfCtuParams *ctu);
+
+/* Classification only (class | transpose<<5 per 4x4 block, raster over the picture's 4x4 grid). */
+void ovo_alf_classify_picture(uint8_t *cls, const uint16_t *src, int stride,
+                              int pic_w, int pic_h, int log2_ctu_s, int bitdepth);
+
+/* ---- SAO ------------------------------------------------------------------------------------------- */
+/* Compact per-CTU SAO parameters (SAOParamsCtu dec_structures.h:263-274). */
+typedef struct OVOSaoCtu {
+    int16_t offset_val[3][5];
+    uint8_t band_position[3];
+    uint8_t eo_class[3];
+    uint8_t type_idx[3];       /* 0 off, 1 band, 2 edge */
+    uint8_t pad;
+} OVOSaoCtu;
+
+void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
+                     const uint16_t *const src[3], const int src_stride[3],
+                     int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                     const OVOSaoCtu *ctu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

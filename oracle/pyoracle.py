@@ -1,0 +1,164 @@
+"""ctypes bindings for the oracle -- TEST INFRASTRUCTURE ONLY.
+
+Two checkers live behind this module:
+
+* ``port``  -- oracle/liboracle.so, our plain-C restatement of the reference algorithms (oracle/port_*.c);
+* ``ref``   -- oracle/_ref/libovref_harness.so, a driver around the UNMODIFIED OpenVVC reference compiled
+  from /root/reference by oracle/Makefile (prebuilt files travel to the GPU box; sources never do).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+The product package (openvvc_b200) must never import it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SRC = "/root/reference"
+
+u16p = C.POINTER(C.c_uint16)
+u8p = C.POINTER(C.c_uint8)
+
+
+class AlfTables(C.Structure):
+    """OVOAlfTables (oracle.h) == OVGPUAlfTables (include/ovvc_b200.h) == RCNALF + cc coeffs."""
+    _fields_ = [("luma_coeff", C.c_int16 * (24 * 1300)),
+                ("luma_clip", C.c_int16 * (24 * 1300)),
+                ("chroma_coeff", C.c_int16 * (8 * 7)),
+                ("chroma_clip", C.c_int16 * (8 * 7)),
+                ("cc_coeff", C.c_int16 * (2 * 4 * 8))]
+
+    def np(self, name):
+        shape = {"luma_coeff": (24, 4, 25, 13), "luma_clip": (24, 4, 25, 13),
+                 "chroma_coeff": (8, 7), "chroma_clip": (8, 7), "cc_coeff": (2, 4, 8)}[name]
+        return np.ctypeslib.as_array(getattr(self, name)).reshape(shape)
+
+
+class AlfCtuParams(C.Structure):
+    _fields_ = [("ctb_alf_flag", u8p), ("ctb_alf_idx", u8p), ("cb_alternative", u8p),
+                ("cr_alternative", u8p), ("cc_idx_cb", u8p), ("cc_idx_cr", u8p),
+                ("cc_cb_enabled", C.c_uint8), ("cc_cr_enabled", C.c_uint8)]
+
+
+class AlfAps(C.Structure):
+    _fields_ = [("luma_clip_flag", C.c_uint8), ("num_luma_filters", C.c_uint8),
+                ("luma_coeff_delta_idx", C.c_uint8 * 25),
+                ("luma_coeff", C.c_int16 * (25 * 13)), ("luma_clip_idx", C.c_int16 * (25 * 13)),
+                ("chroma_clip_flag", C.c_uint8), ("num_chroma_alts", C.c_uint8),
+                ("chroma_coeff", C.c_int16 * (8 * 7)), ("chroma_clip_idx", C.c_int16 * (8 * 7))]
+
+
+SaoCtu = np.dtype([("offset_val", np.int16, (3, 5)), ("band_position", np.uint8, 3),
+                   ("eo_class", np.uint8, 3), ("type_idx", np.uint8, 3), ("pad", np.uint8)])
+assert SaoCtu.itemsize == 40
+
+
+def build(ref=True):
+    """(Re)build liboracle.so and, when /root/reference is present, oracle/_ref."""
+    subprocess.run(["make", "-s", "-C", HERE, "port"], check=True)
+    if ref and os.path.isdir(os.path.join(REF_SRC, "libovvc")):
+        subprocess.run(["make", "-s", "-j8", "-C", HERE, "ref"], check=True)
+
+
+_port = None
+_ref = None
+
+
+def port():
+    global _port
+    if _port is None:
+        path = os.path.join(HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        _port = C.CDLL(path)
+    return _port
+
+
+def ref_available():
+    return os.path.exists(os.path.join(HERE, "_ref", "libovref_harness.so"))
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(HERE, "_ref", "libovref_harness.so"))
+    return _ref
+
+
+def _planes_arg(planes):
+    arr = (u16p * 3)(*[p.ctypes.data_as(u16p) for p in planes])
+    strides = (C.c_int * 3)(*[p.strides[0] // 2 for p in planes])
+    return arr, strides
+
+
+def _ctu_params(ctu):
+    """ctu: dict of uint8 arrays (flag, idx, cb_alt, cr_alt, cc_cb, cc_cr) + cc enables."""
+    keep = [np.ascontiguousarray(ctu[k], dtype=np.uint8) for k in
+            ("flag", "idx", "cb_alt", "cr_alt", "cc_cb", "cc_cr")]
+    p = AlfCtuParams(*[a.ctypes.data_as(u8p) for a in keep],
+                     int(ctu.get("cc_cb_enabled", 1)), int(ctu.get("cc_cr_enabled", 1)))
+    return p, keep
+
+
+def make_aps(d):
+    a = AlfAps()
+    a.luma_clip_flag = int(d["luma_clip_flag"])
+    a.num_luma_filters = int(d["num_luma_filters"])
+    a.luma_coeff_delta_idx[:] = [int(v) for v in d["luma_coeff_delta_idx"]]
+    a.luma_coeff[:] = np.asarray(d["luma_coeff"], dtype=np.int16).reshape(-1).tolist()
+    a.luma_clip_idx[:] = np.asarray(d["luma_clip_idx"], dtype=np.int16).reshape(-1).tolist()
+    a.chroma_clip_flag = int(d["chroma_clip_flag"])
+    a.num_chroma_alts = int(d["num_chroma_alts"])
+    a.chroma_coeff[:] = np.asarray(d["chroma_coeff"], dtype=np.int16).reshape(-1).tolist()
+    a.chroma_clip_idx[:] = np.asarray(d["chroma_clip_idx"], dtype=np.int16).reshape(-1).tolist()
+    return a
+
+
+def alf_build_tables(luma_aps, chroma_aps, bitdepth=10, impl="port"):
+    t = AlfTables()
+    arr = (AlfAps * max(1, len(luma_aps)))(*[make_aps(d) for d in luma_aps])
+    ca = make_aps(chroma_aps) if chroma_aps is not None else None
+    fn = port().ovo_alf_build_tables if impl == "port" else ref().ovref_alf_build_tables
+    fn(C.byref(t), arr, len(luma_aps), C.byref(ca) if ca is not None else None, bitdepth)
+    return t
+
+
+def alf_picture(planes, tables, ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1):
+    """planes: 3 contiguous uint16 arrays (post-SAO). Returns the 3 filtered planes."""
+    h, w = planes[0].shape
+    p, keep = _ctu_params(ctu)
+    if impl == "port":
+        out = [np.empty_like(pl) for pl in planes]
+        src, ss = _planes_arg(planes)
+        dst, ds = _planes_arg(out)
+        port().ovo_alf_picture(dst, ds, src, ss, w, h, log2_ctu, bitdepth, C.byref(tables), C.byref(p))
+        return out
+    out = [pl.copy() for pl in planes]
+    dst, ds = _planes_arg(out)
+    ref().ovref_alf_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(tables), C.byref(p))
+    return out
+
+
+def alf_classify(luma, log2_ctu=7, bitdepth=10):
+    h, w = luma.shape
+    cls = np.zeros((h // 4, w // 4), dtype=np.uint8)
+    port().ovo_alf_classify_picture(cls.ctypes.data_as(u8p), luma.ctypes.data_as(u16p),
+                                    luma.strides[0] // 2, w, h, log2_ctu, bitdepth)
+    return cls
+
+
+def sao_picture(planes, sao_ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1):
+    h, w = planes[0].shape
+    sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SaoCtu)
+    if impl == "port":
+        out = [np.empty_like(pl) for pl in planes]
+        src, ss = _planes_arg(planes)
+        dst, ds = _planes_arg(out)
+        port().ovo_sao_picture(dst, ds, src, ss, w, h, log2_ctu, bitdepth, sao_ctu.ctypes.data_as(C.c_void_p))
+        return out
+    out = [pl.copy() for pl in planes]
+    dst, ds = _planes_arg(out)
+    ref().ovref_sao_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, sao_ctu.ctypes.data_as(C.c_void_p))
+    return out

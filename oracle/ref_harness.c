@@ -1,0 +1,230 @@
+/* oracle/ref_harness.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Thin driver around the UNMODIFIED OpenVVC reference (linked as oracle/_ref/libovvc_ref.so): it builds
+ * the minimum decoder state each reference entry point reads, then calls the
+ * reference's own function through its RCNFunctions table.  No reference code is restated here; the
+ * arithmetic all runs inside the reference.  Compiled by oracle/Makefile with -I/root/reference/libovvc
+ * into oracle/_ref/libovref_harness.so (git-ignored, travels to the GPU box as a prebuilt file).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+
+#include "ovdefs.h"
+#include "ovframe.h"
+#include "ctudec.h"
+#include "dec_structures.h"
+#include "nvcl_structures.h"
+#include "rcn.h"
+#include "rcn_alf.h"
+#include "rcn_structures.h"
+
+#include "oracle.h"
+
+/* C-only init functions of the 10-bit template (rcn.c:151-178) used to force the scalar path */
+void rcn_init_alf_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_sao_functions_10(struct RCNFunctions *rcn_func);
+
+int ovref_harness_version(void) { return 2; }
+
+typedef struct HarnessCtx {
+    OVCTUDec *ctudec;
+    OVPartInfo part;
+    OVFrame frame;
+} HarnessCtx;
+
+static HarnessCtx *
+harness_open(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s,
+             int bitdepth, int simd)
+{
+    HarnessCtx *h = calloc(1, sizeof(*h));
+    if (ctudec_init(&h->ctudec) < 0) { free(h); return NULL; }
+    OVCTUDec *c = h->ctudec;
+
+    memset(&h->part, 0, sizeof(h->part));
+    h->part.log2_ctu_s    = log2_ctu_s;
+    h->part.log2_min_cb_s = 2;
+    c->part_ctx = &h->part;
+    c->rcn_ctx.ctudec = c;
+    c->pic_w = pic_w;
+    c->pic_h = pic_h;
+
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 0, bitdepth);
+    if (!simd && bitdepth == 10) {
+        rcn_init_alf_functions_10(&c->rcn_funcs);
+        rcn_init_sao_functions_10(&c->rcn_funcs);
+    }
+
+    for (int i = 0; i < 3; i++) {
+        h->frame.data[i]     = planes[i];
+        h->frame.linesize[i] = (size_t)stride[i] * sizeof(uint16_t);
+    }
+    h->frame.width  = pic_w;
+    h->frame.height = pic_h;
+    c->rcn_ctx.frame_start = &h->frame;
+
+    int nb_ctu_w = (pic_w + (1 << log2_ctu_s) - 1) >> log2_ctu_s;
+    /* margin 3 as in slicedec.c:1319-1320 */
+    c->rcn_funcs.rcn_alloc_filter_buffers(&c->rcn_ctx, nb_ctu_w, 3, log2_ctu_s);
+    return h;
+}
+
+static void
+harness_close(HarnessCtx *h)
+{
+    OVCTUDec *c = h->ctudec;
+    /* the in-loop parameter arrays belong to the caller */
+    c->alf_info.ctb_alf_params = NULL;
+    c->alf_info.ctb_cc_alf_filter_idx[0] = NULL;
+    c->alf_info.ctb_cc_alf_filter_idx[1] = NULL;
+    c->sao_info.sao_params = NULL;
+    c->rcn_funcs.rcn_buff_uninit(&c->rcn_ctx);
+    free(c);
+    free(h);
+}
+
+static void
+aps_to_ref(OVALFData *d, const OVOAlfAps *a)
+{
+    memset(d, 0, sizeof(*d));
+    d->alf_luma_clip_flag = a->luma_clip_flag;
+    d->alf_luma_num_filters_signalled_minus1 = a->num_luma_filters - 1;
+    memcpy(d->alf_luma_coeff_delta_idx, a->luma_coeff_delta_idx, 25);
+    memcpy(d->alf_luma_coeff, a->luma_coeff, sizeof(d->alf_luma_coeff));
+    memcpy(d->alf_luma_clip_idx, a->luma_clip_idx, sizeof(d->alf_luma_clip_idx));
+    d->alf_chroma_clip_flag = a->chroma_clip_flag;
+    d->alf_chroma_num_alt_filters_minus1 = a->num_chroma_alts - 1;
+    memcpy(d->alf_chroma_coeff, a->chroma_coeff, sizeof(d->alf_chroma_coeff));
+    memcpy(d->alf_chroma_clip_idx, a->chroma_clip_idx, sizeof(d->alf_chroma_clip_idx));
+}
+
+/* Runs the reference's alf.rcn_alf_reconstruct_coeff_APS (rcn_alf.c:264) and copies RCNALF out. */
+void
+ovref_alf_build_tables(OVOAlfTables *t, const OVOAlfAps *luma_aps, int nb_luma_aps,
+                       const OVOAlfAps *chroma_aps, int bitdepth)
+{
+    OVCTUDec *c;
+    OVALFData *d = calloc(9, sizeof(*d));
+    ctudec_init(&c);
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 0, bitdepth);
+    c->alf_info.num_alf_aps_ids_luma = nb_luma_aps;
+    for (int i = 0; i < nb_luma_aps; i++) {
+        aps_to_ref(&d[i], &luma_aps[i]);
+        c->alf_info.aps_alf_data[i] = &d[i];
+    }
+    if (chroma_aps) {
+        aps_to_ref(&d[8], chroma_aps);
+        c->alf_info.aps_alf_data_c = &d[8];
+    }
+    c->rcn_funcs.alf.rcn_alf_reconstruct_coeff_APS(&c->alf_info.rcn_alf, c, 1, chroma_aps != NULL);
+    memcpy(t->luma_coeff, c->alf_info.rcn_alf.filter_coeff_dec, sizeof(t->luma_coeff));
+    memcpy(t->luma_clip,  c->alf_info.rcn_alf.filter_clip_dec,  sizeof(t->luma_clip));
+    memcpy(t->chroma_coeff, c->alf_info.rcn_alf.chroma_coeff_final, sizeof(t->chroma_coeff));
+    memcpy(t->chroma_clip,  c->alf_info.rcn_alf.chroma_clip_final,  sizeof(t->chroma_clip));
+    free(c);
+    free(d);
+}
+
+/* In-place whole-picture ALF through alf.rcn_alf_filter_line (rcn_alf.c:1285), rows in decode order. */
+void
+ovref_alf_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h,
+                  int log2_ctu_s, int bitdepth, int simd,
+                  const OVOAlfTables *tab, const OVOAlfCtuParams *p)
+{
+    HarnessCtx *h = harness_open(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd);
+    OVCTUDec *c = h->ctudec;
+    struct ALFInfo *ai = &c->alf_info;
+    int ctu_s = 1 << log2_ctu_s;
+    int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s;
+    int nb_h = (pic_h + ctu_s - 1) >> log2_ctu_s;
+    int n = nb_w * nb_h;
+    ALFParamsCtu *params = calloc(n, sizeof(*params));
+    OVALFData cc[2];
+    memset(cc, 0, sizeof(cc));
+
+    memcpy(ai->rcn_alf.filter_coeff_dec, tab->luma_coeff, sizeof(tab->luma_coeff));
+    memcpy(ai->rcn_alf.filter_clip_dec,  tab->luma_clip,  sizeof(tab->luma_clip));
+    memcpy(ai->rcn_alf.chroma_coeff_final, tab->chroma_coeff, sizeof(tab->chroma_coeff));
+    memcpy(ai->rcn_alf.chroma_clip_final,  tab->chroma_clip,  sizeof(tab->chroma_clip));
+    memcpy(cc[0].alf_cc_mapped_coeff[0], tab->cc_coeff[0], sizeof(tab->cc_coeff[0]));
+    memcpy(cc[1].alf_cc_mapped_coeff[1], tab->cc_coeff[1], sizeof(tab->cc_coeff[1]));
+
+    for (int i = 0; i < n; i++) {
+        params[i].ctb_alf_flag   = p->ctb_alf_flag[i];
+        params[i].ctb_alf_idx    = p->ctb_alf_idx[i];
+        params[i].cb_alternative = p->cb_alternative[i];
+        params[i].cr_alternative = p->cr_alternative[i];
+    }
+    ai->alf_luma_enabled_flag = 1;
+    ai->alf_cb_enabled_flag = 1;
+    ai->alf_cr_enabled_flag = 1;
+    ai->cc_alf_cb_enabled_flag = p->cc_cb_enabled;
+    ai->cc_alf_cr_enabled_flag = p->cc_cr_enabled;
+    ai->aps_cc_alf_data_cb = &cc[0];
+    ai->aps_cc_alf_data_cr = &cc[1];
+    ai->ctb_alf_params = params;
+    ai->ctb_cc_alf_filter_idx[0] = (uint8_t *)p->cc_idx_cb;
+    ai->ctb_cc_alf_filter_idx[1] = (uint8_t *)p->cc_idx_cr;
+
+    struct RectEntryInfo e;
+    memset(&e, 0, sizeof(e));
+    e.nb_ctu_w = nb_w;
+    e.nb_ctu_h = nb_h;
+    e.nb_ctu_rect = n;
+    e.nb_ctb_pic_w = nb_w;
+
+    for (int row = 0; row < nb_h; row++)
+        c->rcn_funcs.alf.rcn_alf_filter_line(c, &e, row);
+
+    harness_close(h);
+    free(params);
+}
+
+/* In-place whole-picture SAO following the call order of decode_ctu_line's tail (slicedec.c:934-956). */
+void
+ovref_sao_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h,
+                  int log2_ctu_s, int bitdepth, int simd, const OVOSaoCtu *p)
+{
+    HarnessCtx *h = harness_open(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd);
+    OVCTUDec *c = h->ctudec;
+    int ctu_s = 1 << log2_ctu_s;
+    int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s;
+    int nb_h = (pic_h + ctu_s - 1) >> log2_ctu_s;
+    int n = nb_w * nb_h;
+    SAOParamsCtu *params = calloc(n, sizeof(*params));
+
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            memcpy(params[i].offset_val[k], p[i].offset_val[k], sizeof(params[i].offset_val[k]));
+            params[i].band_position[k] = p[i].band_position[k];
+            params[i].eo_class[k]      = p[i].eo_class[k];
+            params[i].type_idx[k]      = p[i].type_idx[k];
+        }
+    c->sao_info.sao_luma_flag = 1;
+    c->sao_info.sao_chroma_flag = 1;
+    c->sao_info.chroma_format_idc = 1;
+    c->sao_info.sao_params = params;
+
+    struct RectEntryInfo e;
+    memset(&e, 0, sizeof(e));
+    e.nb_ctu_w = nb_w;
+    e.nb_ctu_h = nb_h;
+    e.nb_ctu_rect = n;
+    e.nb_ctb_pic_w = nb_w;
+
+    const struct SAOFunctions *sao = &c->rcn_funcs.sao;
+    for (int row = 0; row < nb_h; row++) {
+        if (row == 0) {
+            sao->rcn_sao_first_pix_rows(c, &e, 0);
+            if (nb_h == 1) sao->rcn_sao_filter_line(c, &e, 0);
+        } else if (row == nb_h - 1) {
+            sao->rcn_sao_filter_line(c, &e, row - 1);
+            sao->rcn_sao_filter_line(c, &e, row);
+        } else {
+            sao->rcn_sao_filter_line(c, &e, row - 1);
+        }
+    }
+
+    harness_close(h);
+    free(params);
+}

@@ -1,0 +1,70 @@
+// tests/emu/emu.cpp -- TEST HARNESS ONLY: runs the product's kernel source (openvvc_b200/csrc/*_kernels.h)
+// on the CPU through the serial CTA emulation of csrc/dev.h (-DOVGPU_HOST_EMU), so kernel logic can be
+// checked against the oracle on a machine without a GPU.  Never linked into libovvc_b200.so.
+#include <vector>
+#include "../../openvvc_b200/csrc/alf_host.h"
+#include "../../openvvc_b200/csrc/sao_kernels.h"
+
+extern "C" {
+
+int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
+                    const uint16_t *const src[3], const int src_stride[3],
+                    int w, int h, int log2_ctu, int bitdepth,
+                    const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
+                    int cc_cb_enabled, int cc_cr_enabled)
+{
+    AlfGeom g = alf_geom(w, h, log2_ctu);
+    int n = g.nb_ctu_w * g.nb_ctu_h;
+    std::vector<uint32_t> ltab((size_t)OVGPU_ALF_NUM_SETS * ALF_TAB_SET_WORDS + 4);
+    // 16-byte align like cudaMalloc would
+    uint32_t *lt = ltab.data();
+    while ((uintptr_t)lt & 15) lt++;
+    int wide = alf_pack_luma_tab(lt, tab);
+    std::vector<AlfCtuDev> dctu(n);
+    alf_pack_ctu(dctu.data(), n, ctu, cc_idx);
+    ovd_dim3 grid(g.nb_ctu_w * g.l_tx, g.nb_ctu_h * g.l_ty, 1);
+    if (wide) {
+        typedef AlfLumaK<true> K;
+        K::Args a = { src[0], dst[0], src_stride[0], dst_stride[0], w, h, log2_ctu, bitdepth,
+                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data() };
+        ovd_emulate<K>(a, grid, K::SMEM_BYTES);
+    } else {
+        typedef AlfLumaK<false> K;
+        K::Args a = { src[0], dst[0], src_stride[0], dst_stride[0], w, h, log2_ctu, bitdepth,
+                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data() };
+        ovd_emulate<K>(a, grid, K::SMEM_BYTES);
+    }
+    {
+        typedef AlfChromaK K;
+        K::Args a;
+        a.src[0] = src[1]; a.src[1] = src[2]; a.dst[0] = dst[1]; a.dst[1] = dst[2];
+        a.luma = src[0];
+        a.src_pitch = src_stride[1]; a.dst_pitch = dst_stride[1]; a.luma_pitch = src_stride[0];
+        a.pic_w = w; a.pic_h = h; a.log2_ctu = log2_ctu; a.bitdepth = bitdepth;
+        a.tw = g.c_tw; a.th = g.c_th; a.tiles_x_per_ctu = g.c_tx; a.tiles_y_per_ctu = g.c_ty; a.nb_ctu_w = g.nb_ctu_w;
+        a.cc_enabled[0] = cc_cb_enabled && cc_idx && cc_idx[0];
+        a.cc_enabled[1] = cc_cr_enabled && cc_idx && cc_idx[1];
+        a.ctu = dctu.data();
+        alf_pack_chroma_tab(&a.tab, tab);
+        ovd_emulate<K>(a, ovd_dim3(g.nb_ctu_w * g.c_tx, g.nb_ctu_h * g.c_ty, 2), K::SMEM_BYTES);
+    }
+    return wide;
+}
+
+int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
+                    const uint16_t *const src[3], const int src_stride[3],
+                    int w, int h, int log2_ctu, int bitdepth, const OVGPUSaoCtu *ctu)
+{
+    SaoK::Args a;
+    int ctu_s = 1 << log2_ctu;
+    for (int c = 0; c < 3; c++) {
+        a.src[c] = src[c]; a.dst[c] = dst[c]; a.src_pitch[c] = src_stride[c]; a.dst_pitch[c] = dst_stride[c];
+    }
+    a.pic_w = w; a.pic_h = h; a.log2_ctu = log2_ctu; a.bitdepth = bitdepth;
+    a.nb_ctu_w = (w + ctu_s - 1) >> log2_ctu; a.nb_ctu_h = (h + ctu_s - 1) >> log2_ctu;
+    a.ctu = (const SaoCtuDev *)ctu;
+    ovd_emulate<SaoK>(a, ovd_dim3((w + SaoK::BX * 8 - 1) / (SaoK::BX * 8), (h + SaoK::BY - 1) / SaoK::BY, 3), 0);
+    return 0;
+}
+
+}
