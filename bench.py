@@ -171,7 +171,11 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream shared by torch events and the C-ABI context, so that
+    # torch.cuda.Event timing brackets exactly the kernels the library launches
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = api.Ctx(local, stream.cuda_stream)
 
     P = args.pics
