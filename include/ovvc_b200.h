@@ -135,6 +135,66 @@ int  ovgpu_sao_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t d
                           const void *const src_data[3], const size_t src_linesize[3],
                           int width, int height, int log2_ctu_s, int bitdepth, const OVGPUSaoCtu *ctu);
 
+/* ---- LMCS  (replaces rcn_init_lmcs, lmcs_reshape_forward/backward; rcn_lmcs.c:274-361) ------------------ */
+typedef struct OVGPULmcsData {        /* OVLMCSData (nvcl_structures.h:671-680) */
+    uint8_t lmcs_min_bin_idx;
+    uint8_t lmcs_delta_max_bin_idx;
+    uint8_t lmcs_delta_cw_prec_minus1;
+    uint16_t lmcs_delta_abs_cw[16];
+    uint8_t lmcs_delta_sign_cw_flag[16];
+    uint8_t lmcs_delta_abs_crs;
+    uint8_t lmcs_delta_sign_crs_flag;
+} OVGPULmcsData;
+
+typedef struct OVGPULmcsLuts {        /* struct LMCSLUTs (rcn_lmcs.c:77-82) at 10 bit */
+    uint16_t fwd_lut[1024];
+    uint16_t bwd_lut[1024];
+    uint16_t wnd_bnd[17];
+} OVGPULmcsLuts;
+
+/* host-side LUT construction (rcn_init_lmcs, rcn_lmcs.c:345) */
+int  ovgpu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *data, int bitdepth);
+typedef struct OVGPULmcs OVGPULmcs;   /* device copy of the LUTs of one slice */
+int  ovgpu_lmcs_create(OVGPUCtx *ctx, OVGPULmcs **l);
+void ovgpu_lmcs_destroy(OVGPULmcs *l);
+int  ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts);
+/* luma plane of pic <- bwd_lut[luma] (forward != 0: fwd_lut); the reference does this per CTU after
+ * rcn_write_ctu_to_frame (slicedec.c:745-750). In place. */
+int  ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *l, int forward);
+
+/* ---- Motion compensation  (replaces rcn_mcp, rcn_mcp_b, rcn_mcp_b_l, rcn_mcp_b_c; rcn_inter.c:2750-2966) - */
+#define OVGPU_MC_LUMA      1   /* rcn_mcp_b_l (or rcn_mcp_b with both bits)            */
+#define OVGPU_MC_CHROMA    2   /* rcn_mcp_b_c                                           */
+#define OVGPU_MC_HPEL_AMVR 4   /* inter_ctx->prec_amvr == MV_PRECISION_HALF             */
+
+/* One recorded call; x0/y0 are picture-absolute luma samples ((ctb_x << log2_ctu_s) + x0 in the reference). */
+typedef struct OVGPUMcCmd {
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h;
+    uint8_t inter_dir;            /* 1 = L0, 2 = L1, 3 = bi                              */
+    uint8_t flags;
+    int8_t  ref_idx0, ref_idx1;
+    uint8_t bcw_idx_plus1;        /* OVMV.bcw_idx_plus1 of mv0 (ctudec.h:281-289)        */
+    uint8_t tool;                 /* 0 = plain translational                             */
+    int32_t mv0_x, mv0_y, mv1_x, mv1_y;   /* 1/16 luma sample                            */
+    uint32_t aux;
+} OVGPUMcCmd;
+
+/* Reference picture lists of the current slice: inter_ctx->rpl0/rpl1 (ctudec.h:349-350) and their POCs. */
+typedef struct OVGPUMcRefs {
+    const OVGPUPicture *rpl[2][16];
+    int32_t poc[2][16];
+} OVGPUMcRefs;
+
+typedef struct OVGPUMcBatch OVGPUMcBatch;   /* pinned staging + device copy of one picture's PU list */
+int  ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBatch **b);
+void ovgpu_mc_batch_destroy(OVGPUMcBatch *b);
+/* splits the PUs into <=16x16 work items on the host and copies both lists to the device (async) */
+int  ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds);
+/* writes the prediction of every command into dst; lmcs may be NULL (no forward reshape). Asynchronous. */
+int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
+                      const OVGPULmcs *lmcs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -230,6 +230,102 @@ class AlfParams:
             self.p = vp()
 
 
+MC_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), ("log2_h", np.uint8),
+                   ("inter_dir", np.uint8), ("flags", np.uint8), ("ref_idx0", np.int8), ("ref_idx1", np.int8),
+                   ("bcw_idx_plus1", np.uint8), ("tool", np.uint8),
+                   ("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32),
+                   ("aux", np.uint32)])
+
+
+class McRefs(C.Structure):
+    """OVGPUMcRefs: inter_ctx->rpl0/rpl1 as device pictures + POCs."""
+    _fields_ = [("rpl", vp * 16 * 2), ("poc", C.c_int32 * 16 * 2)]
+
+
+class LmcsData(C.Structure):
+    _fields_ = [("lmcs_min_bin_idx", C.c_uint8), ("lmcs_delta_max_bin_idx", C.c_uint8),
+                ("lmcs_delta_cw_prec_minus1", C.c_uint8), ("lmcs_delta_abs_cw", C.c_uint16 * 16),
+                ("lmcs_delta_sign_cw_flag", C.c_uint8 * 16), ("lmcs_delta_abs_crs", C.c_uint8),
+                ("lmcs_delta_sign_crs_flag", C.c_uint8)]
+
+    @classmethod
+    def from_dict(cls, d):
+        x = cls()
+        x.lmcs_min_bin_idx = int(d["min_bin_idx"]); x.lmcs_delta_max_bin_idx = int(d["delta_max_bin_idx"])
+        x.lmcs_delta_abs_cw[:] = [int(v) for v in d["delta_abs_cw"]]
+        x.lmcs_delta_sign_cw_flag[:] = [int(v) for v in d["delta_sign_cw"]]
+        x.lmcs_delta_abs_crs = int(d["delta_abs_crs"]); x.lmcs_delta_sign_crs_flag = int(d["delta_sign_crs"])
+        return x
+
+
+class LmcsLuts(C.Structure):
+    _fields_ = [("fwd_lut", C.c_uint16 * 1024), ("bwd_lut", C.c_uint16 * 1024), ("wnd_bnd", C.c_uint16 * 17)]
+
+    def np(self, name):
+        return np.ctypeslib.as_array(getattr(self, name))
+
+
+def lmcs_build_luts(d, bitdepth=10):
+    luts = LmcsLuts()
+    data = LmcsData.from_dict(d)
+    _check(None, lib().ovgpu_lmcs_build_luts(C.byref(luts), C.byref(data), bitdepth), "ovgpu_lmcs_build_luts")
+    return luts
+
+
+class Lmcs:
+    def __init__(self, ctx, luts=None):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_lmcs_create(ctx.h, C.byref(self.p)), "lmcs_create")
+        if luts is not None:
+            self.upload(luts)
+
+    def upload(self, luts):
+        self._keep = luts
+        _check(self.ctx.h, lib().ovgpu_lmcs_upload(self.ctx.h, self.p, C.byref(luts)), "lmcs_upload")
+
+    def reshape(self, pic, forward=False):
+        _check(self.ctx.h, lib().ovgpu_lmcs_reshape_picture(self.ctx.h, pic.p, self.p, int(forward)), "lmcs_reshape_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_lmcs_destroy(self.p)
+            self.p = vp()
+
+
+class McBatch:
+    """One picture's PU list on the device (ovgpu_mc_batch_*)."""
+
+    def __init__(self, ctx, max_cmds, max_items):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_mc_batch_create(ctx.h, int(max_cmds), int(max_items), C.byref(self.p)), "mc_batch_create")
+
+    def upload(self, cmds):
+        cmds = np.ascontiguousarray(cmds, dtype=MC_CMD)
+        self._keep = cmds
+        _check(self.ctx.h, lib().ovgpu_mc_batch_upload(self.ctx.h, self.p, vp(cmds.ctypes.data), len(cmds)), "mc_batch_upload")
+
+    def run(self, dst, ref_lists, pocs, lmcs=None):
+        """ref_lists: [rpl0, rpl1] lists of Picture; pocs likewise."""
+        r = McRefs()
+        for l in range(2):
+            for i, pic in enumerate(ref_lists[l]):
+                r.rpl[l][i] = pic.p
+                r.poc[l][i] = int(pocs[l][i])
+        _check(self.ctx.h, lib().ovgpu_mc_picture(self.ctx.h, dst.p, C.byref(r), self.p, lmcs.p if lmcs else None), "mc_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_mc_batch_destroy(self.p)
+            self.p = vp()
+
+
+def mc_nb_items(cmds):
+    w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))
+    return int((((w + 15) >> 4) * ((h + 15) >> 4)).sum())
+
+
 class SaoParams:
     def __init__(self, ctx, w, h, log2_ctu=7):
         self.ctx = ctx

@@ -1,0 +1,157 @@
+// mc.cu -- C-ABI entry points of motion compensation and LMCS (kernels in mc_kernels.h / mc_host.h).
+// Replaces rcn_mcp, rcn_mcp_b, rcn_mcp_b_l, rcn_mcp_b_c (libovvc/rcn_inter.c:2750-2966) for all PUs of a picture,
+// rcn_init_lmcs and lmcs_reshape_forward/backward (libovvc/rcn_lmcs.c).
+#include "common.cuh"
+#include "mc_host.h"
+#include <stdlib.h>
+
+static_assert(sizeof(McCmdDev) == sizeof(OVGPUMcCmd) && sizeof(McCmdDev) == 32, "MC command layout");
+
+struct OVGPUMcBatch {
+    int max_cmds, max_items, nb_cmds, nb_items, device;
+    McCmdDev *h_cmds, *d_cmds;
+    McItemDev *h_items, *d_items;
+};
+
+struct OVGPULmcs {
+    OVGPULmcsLuts *h_luts, *d_luts;
+    int device;
+};
+
+extern "C" {
+
+int ovgpu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *data, int bitdepth)
+{
+    if (!luts || !data || (bitdepth != 10 && bitdepth != 8)) return OVGPU_EINVAL;
+    if (data->lmcs_min_bin_idx > 15 || data->lmcs_delta_max_bin_idx > 15) return OVGPU_EINVAL;
+    lmcs_build_luts_host(luts, data, bitdepth);
+    return 0;
+}
+
+int ovgpu_lmcs_create(OVGPUCtx *ctx, OVGPULmcs **out)
+{
+    if (!ctx || !out) return OVGPU_EINVAL;
+    OVGPULmcs *l = (OVGPULmcs *)calloc(1, sizeof(*l));
+    if (!l) return OVGPU_ENOMEM;
+    l->device = ctx->device;
+    if (cudaMallocHost(&l->h_luts, sizeof(OVGPULmcsLuts)) != cudaSuccess ||
+        cudaMalloc(&l->d_luts, sizeof(OVGPULmcsLuts)) != cudaSuccess) {
+        ovgpu_lmcs_destroy(l);
+        return ovgpu_set_error(ctx, OVGPU_ENOMEM, "LMCS buffers");
+    }
+    *out = l;
+    return 0;
+}
+
+void ovgpu_lmcs_destroy(OVGPULmcs *l)
+{
+    if (!l) return;
+    cudaSetDevice(l->device);
+    if (l->h_luts) cudaFreeHost(l->h_luts);
+    if (l->d_luts) cudaFree(l->d_luts);
+    free(l);
+}
+
+int ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts)
+{
+    if (!ctx || !l || !luts) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(l->h_luts, luts, sizeof(*luts));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(l->d_luts, l->h_luts, sizeof(*luts), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *l, int forward)
+{
+    if (!ctx || !pic || !l) return OVGPU_EINVAL;
+    StageScope scope(ctx, OVGPU_STAGE_LMCS, 1);
+    PlaneView v = plane_view(pic, 0);
+    LmcsReshapeK::Args a = { v.p, v.pitch, v.w, v.h, pic->bitdepth, forward ? l->d_luts->fwd_lut : l->d_luts->bwd_lut };
+    dim3 grid(OVGPU_CEIL_DIV(v.w, 256), OVGPU_CEIL_DIV(v.h, 8), 1);
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<LmcsReshapeK>(a, grid, 0, ctx->stream));
+    return 0;
+}
+
+int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBatch **out)
+{
+    if (!ctx || !out || max_cmds <= 0 || max_items < max_cmds) return OVGPU_EINVAL;
+    OVGPUMcBatch *b = (OVGPUMcBatch *)calloc(1, sizeof(*b));
+    if (!b) return OVGPU_ENOMEM;
+    b->max_cmds = max_cmds; b->max_items = max_items; b->device = ctx->device;
+    if (cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMallocHost(&b->h_items, sizeof(McItemDev) * max_items) != cudaSuccess ||
+        cudaMalloc(&b->d_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMalloc(&b->d_items, sizeof(McItemDev) * max_items) != cudaSuccess) {
+        ovgpu_mc_batch_destroy(b);
+        return ovgpu_set_error(ctx, OVGPU_ENOMEM, "MC batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = b;
+    return 0;
+}
+
+void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->h_cmds) cudaFreeHost(b->h_cmds);
+    if (b->h_items) cudaFreeHost(b->h_items);
+    if (b->d_cmds) cudaFree(b->d_cmds);
+    if (b->d_items) cudaFree(b->d_items);
+    free(b);
+}
+
+int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds)
+{
+    if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds) return OVGPU_EINVAL;
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVGPUMcCmd *c = &cmds[i];
+        if (c->log2_w < 2 || c->log2_w > 7 || c->log2_h < 2 || c->log2_h > 7 || c->inter_dir < 1 || c->inter_dir > 3 ||
+            c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->tool != 0)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d malformed", i);
+    }
+    int n_items = mc_count_items(cmds, nb_cmds);
+    if (n_items > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch needs %d items (max %d)", n_items, b->max_items);
+    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(b->h_cmds, cmds, sizeof(McCmdDev) * nb_cmds);
+    b->nb_cmds = nb_cmds;
+    b->nb_items = mc_build_items(b->h_items, cmds, nb_cmds);
+    if (nb_cmds) {
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(McItemDev) * b->nb_items, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return 0;
+}
+
+int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
+                     const OVGPULmcs *lmcs)
+{
+    if (!ctx || !dst || !refs || !b) return OVGPU_EINVAL;
+    if (!b->nb_items) return 0;
+    McK::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { PlaneView v = plane_view(dst, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
+    a.pic_w = dst->width; a.pic_h = dst->height; a.bitdepth = dst->bitdepth;
+    a.cmds = b->d_cmds; a.items = b->d_items; a.nb_items = b->nb_items;
+    a.lmcs_fwd = lmcs ? lmcs->d_luts->fwd_lut : NULL;
+    // every reference a command names must be present and of the picture's size
+    for (int i = 0; i < b->nb_cmds; i++) {
+        const McCmdDev *c = &b->h_cmds[i];
+        if (((c->inter_dir & 1) && !refs->rpl[0][c->ref_idx0]) || ((c->inter_dir & 2) && !refs->rpl[1][c->ref_idx1]))
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d references a missing picture", i);
+    }
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++) {
+            const OVGPUPicture *p = refs->rpl[l][i];
+            a.refs.poc[l][i] = refs->poc[l][i];
+            if (!p) continue;
+            if (p->width != dst->width || p->height != dst->height)
+                return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture size differs (RPR is not supported)");
+            for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = p->plane[c]; a.refs.pitch[l][i][c] = (int)(p->pitch[c] / 2); }
+        }
+    StageScope scope(ctx, OVGPU_STAGE_MC, 1);
+    dim3 grid(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1);
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, grid, McK::SMEM_BYTES, ctx->stream));
+    return 0;
+}
+
+} // extern "C"

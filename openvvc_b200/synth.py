@@ -112,3 +112,90 @@ def sao_params(w, h, seed=1002, log2_ctu=7, sao_dtype=None):
         ov = np.where((t == 2)[:, None], edge, ov)
         p["offset_val"][:, c, :] = ov
     return p
+
+
+# ---- inter prediction -----------------------------------------------------------------------------------
+MC_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), ("log2_h", np.uint8),
+                   ("inter_dir", np.uint8), ("flags", np.uint8), ("ref_idx0", np.int8), ("ref_idx1", np.int8),
+                   ("bcw_idx_plus1", np.uint8), ("tool", np.uint8),
+                   ("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32),
+                   ("aux", np.uint32)])
+
+
+def partition(w, h, rng, log2_ctu=7, min_log2=2, max_log2=7, p_split=0.55):
+    """Random QTBT-like partition of the picture into power-of-two blocks (x, y, log2_w, log2_h) that lie
+    inside the picture.  Blocks never straddle a CTU; picture dimensions must be multiples of 8."""
+    out = []
+    ctu = 1 << log2_ctu
+
+    def rec(x, y, lw, lh):
+        bw, bh = 1 << lw, 1 << lh
+        if x >= w or y >= h:
+            return
+        must = x + bw > w or y + bh > h or lw > max_log2 or lh > max_log2
+        can_h = lw > min_log2
+        can_v = lh > min_log2
+        if must or ((can_h or can_v) and rng.random() < p_split):
+            if must:
+                sh = x + bw > w or lw > max_log2
+                sv = y + bh > h or lh > max_log2
+            else:
+                mode = rng.integers(0, 3)
+                sh = can_h and mode != 1
+                sv = can_v and mode != 0
+                if not sh and not sv:
+                    sh, sv = can_h, can_v
+            nlw, nlh = lw - (1 if sh else 0), lh - (1 if sv else 0)
+            for dy in range(2 if sv else 1):
+                for dx in range(2 if sh else 1):
+                    rec(x + (dx << nlw), y + (dy << nlh), nlw, nlh)
+        else:
+            out.append((x, y, lw, lh))
+
+    for cy in range(0, h, ctu):
+        for cx in range(0, w, ctu):
+            rec(cx, cy, log2_ctu, log2_ctu)
+    return out
+
+
+def mc_commands(w, h, seed=1004, log2_ctu=7, n_refs=2, p_bi=0.7, mv_range=64, min_log2=3):
+    """PU list for one inter picture (seed 1004): random partition, MVs with an integer part in
+    +-mv_range samples (some pointing outside the picture so border replication is exercised), uniformly
+    random 1/16 fractions, 70 % bi-prediction, 5 % BCW != default, 5 % half-pel AMVR."""
+    rng = np.random.default_rng(seed)
+    blocks = partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(7, log2_ctu))
+    cmds = np.zeros(len(blocks), dtype=MC_CMD)
+    for i, (x, y, lw, lh) in enumerate(blocks):
+        c = cmds[i]
+        c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
+        bi = rng.random() < p_bi and not (lw + lh < 6)       # bi-prediction needs >= 8x8
+        c["inter_dir"] = 3 if bi else int(rng.integers(1, 3))
+        # half-pel AMVR (not on 4x4 blocks: those only exist as affine sub-blocks, where it cannot be signalled)
+        c["flags"] = 3 | (4 if (rng.random() < 0.05 and lw + lh > 4) else 0)
+        c["ref_idx0"] = rng.integers(0, n_refs); c["ref_idx1"] = rng.integers(0, n_refs)
+        if bi and rng.random() < 0.05:
+            c["bcw_idx_plus1"] = int(rng.choice([1, 2, 4, 5]))
+        kind = rng.random()
+        for k in ("mv0", "mv1"):
+            if kind < 0.1:        # far outside: exercises clip_mv and full border replication
+                mx = int(rng.integers(-(w + 200), w + 200)) * 16; my = int(rng.integers(-(h + 200), h + 200)) * 16
+            else:
+                mx = int(rng.integers(-mv_range * 16, mv_range * 16 + 1)); my = int(rng.integers(-mv_range * 16, mv_range * 16 + 1))
+                if rng.random() < 0.25:
+                    mx &= ~15
+                if rng.random() < 0.25:
+                    my &= ~15
+            if c["flags"] & 4:    # half-pel AMVR: MVs are multiples of 8
+                mx &= ~7; my &= ~7
+            c[k + "_x"], c[k + "_y"] = mx, my
+        if bi and rng.random() < 0.03:   # identical motion -> falls back to uni-prediction from list 1
+            c["mv1_x"], c["mv1_y"] = c["mv0_x"], c["mv0_y"]
+    return cmds
+
+
+def lmcs_data(seed=1007):
+    rng = np.random.default_rng(seed)
+    min_idx = int(rng.integers(0, 4)); dmax = int(rng.integers(0, 4))
+    return dict(min_bin_idx=min_idx, delta_max_bin_idx=dmax,
+                delta_abs_cw=rng.integers(0, 24, size=16), delta_sign_cw=rng.integers(0, 2, size=16),
+                delta_abs_crs=int(rng.integers(0, 8)), delta_sign_crs=int(rng.integers(0, 2)))

@@ -90,6 +90,54 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                      int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                      const OVOSaoCtu *ctu);
 
+/* ---- Motion compensation ---------------------------------------------------------------------------- */
+/* One command = one call of rcn_mcp_b / rcn_mcp_b_l / rcn_mcp_b_c / rcn_mcp (rcn_inter.c:2750-2966) with
+ * picture-absolute luma coordinates.  Identical to OVGPUMcCmd (include/ovvc_b200.h). */
+#define OVO_MC_LUMA      1
+#define OVO_MC_CHROMA    2
+#define OVO_MC_HPEL_AMVR 4      /* inter_ctx->prec_amvr == MV_PRECISION_HALF (rcn_inter.c:572) */
+typedef struct OVOMcCmd {
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h;
+    uint8_t inter_dir;          /* 1 L0, 2 L1, 3 bi */
+    uint8_t flags;
+    int8_t  ref_idx0, ref_idx1;
+    uint8_t bcw_idx_plus1;
+    uint8_t tool;               /* 0 plain (others reserved for BDOF/DMVR/PROF commands) */
+    int32_t mv0_x, mv0_y, mv1_x, mv1_y;   /* 1/16 luma sample */
+    uint32_t aux;
+} OVOMcCmd;
+
+typedef struct OVOMcRefs {
+    const uint16_t *plane[2][16][3];   /* [list][ref_idx][component] */
+    int stride[2][16][3];              /* samples */
+    int32_t poc[2][16];
+} OVOMcRefs;
+
+/* lmcs_fwd_lut: 1<<bitdepth entries or NULL (rcn_lmcs_reshape_forward, rcn_lmcs.c:287) */
+void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                    const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut);
+
+/* ---- LMCS ------------------------------------------------------------------------------------------- */
+typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */
+    uint8_t lmcs_min_bin_idx;
+    uint8_t lmcs_delta_max_bin_idx;
+    uint8_t lmcs_delta_cw_prec_minus1;
+    uint16_t lmcs_delta_abs_cw[16];
+    uint8_t lmcs_delta_sign_cw_flag[16];
+    uint8_t lmcs_delta_abs_crs;
+    uint8_t lmcs_delta_sign_crs_flag;
+} OVOLmcsData;
+
+typedef struct OVOLmcsLuts {          /* struct LMCSLUTs, rcn_lmcs.c:77-82 (10-bit: 1024 entries) */
+    uint16_t fwd_lut[1024];
+    uint16_t bwd_lut[1024];
+    uint16_t wnd_bnd[17];
+} OVOLmcsLuts;
+
+void ovo_lmcs_build_luts(OVOLmcsLuts *luts, const OVOLmcsData *data, int bitdepth);
+void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uint16_t *lut, int bitdepth);
+
 #ifdef __cplusplus
 }
 #endif

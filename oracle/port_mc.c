@@ -1,0 +1,217 @@
+/* oracle/port_mc.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Restatement of OpenVVC's translational motion compensation: dispatch (rcn_mcp_b & co,
+ * libovvc/rcn_inter.c:2750-2966), MV clipping / fractional split / reference addressing
+ * (rcn_inter.c:96-108, 521-602, 1392-1476, 1479-1554, 1822-1900), border replication
+ * (emulate_block_border :148-225 == clamped coordinates) and the separable interpolation kernels
+ * (libovvc/rcn_mc.c:381-1098 luma, :1100-1376 chroma, :1380-1608 BCW-weighted).
+ * Plus the LMCS LUTs (libovvc/rcn_lmcs.c:84-187) because every luma inter prediction is forward-reshaped
+ * inside the MC routines (rcn_inter.c:599, 1552).
+ */
+#include "oracle.h"
+#include <string.h>
+
+static inline int clipi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* VVC luma 1/16-sample filters; row 15 = the half-sample filter selected by AMVR half-pel (rcn_mc.c:103-123) */
+static const int8_t mc_filt_l[16][8] = {
+    {  0, 1,  -3, 63,  4,  -2,  1,  0 }, { -1, 2,  -5, 62,  8,  -3,  1,  0 }, { -1, 3,  -8, 60, 13,  -4,  1,  0 },
+    { -1, 4, -10, 58, 17,  -5,  1,  0 }, { -1, 4, -11, 52, 26,  -8,  3, -1 }, { -1, 3,  -9, 47, 31, -10,  4, -1 },
+    { -1, 4, -11, 45, 34, -10,  4, -1 }, { -1, 4, -11, 40, 40, -11,  4, -1 }, { -1, 4, -10, 34, 45, -11,  4, -1 },
+    { -1, 4, -10, 31, 47,  -9,  3, -1 }, { -1, 3,  -8, 26, 52, -11,  4, -1 }, {  0, 1,  -5, 17, 58, -10,  4, -1 },
+    {  0, 1,  -4, 13, 60,  -8,  3, -1 }, {  0, 1,  -3,  8, 62,  -5,  2, -1 }, {  0, 1,  -2,  4, 63,  -3,  1,  0 },
+    {  0, 3,   9, 20, 20,   9,  3,  0 } };
+/* 6-tap variant used for 4x4 (affine sub-)blocks (rcn_mc.c:125-142) */
+static const int8_t mc_filt_l4[15][8] = {
+    { 0, 1,  -3, 63,  4,  -2, 1, 0 }, { 0, 1,  -5, 62,  8,  -3, 1, 0 }, { 0, 2,  -8, 60, 13,  -4, 1, 0 },
+    { 0, 3, -10, 58, 17,  -5, 1, 0 }, { 0, 3, -11, 52, 26,  -8, 2, 0 }, { 0, 2,  -9, 47, 31, -10, 3, 0 },
+    { 0, 3, -11, 45, 34, -10, 3, 0 }, { 0, 3, -11, 40, 40, -11, 3, 0 }, { 0, 3, -10, 34, 45, -11, 3, 0 },
+    { 0, 3, -10, 31, 47,  -9, 2, 0 }, { 0, 2,  -8, 26, 52, -11, 3, 0 }, { 0, 1,  -5, 17, 58, -10, 3, 0 },
+    { 0, 1,  -4, 13, 60,  -8, 2, 0 }, { 0, 1,  -3,  8, 62,  -5, 1, 0 }, { 0, 1,  -2,  4, 63,  -3, 1, 0 } };
+/* chroma 1/32-sample filters (rcn_mc.c:67-101) */
+static const int8_t mc_filt_c[31][4] = {
+    { -1, 63,  2,  0 }, { -2, 62,  4,  0 }, { -2, 60,  7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+    { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 },
+    { -6, 49, 24, -3 }, { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 },
+    { -4, 36, 36, -4 }, { -4, 33, 39, -4 }, { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 },
+    { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 }, { -2, 16, 54, -4 }, { -2, 15, 55, -4 },
+    { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1,  7, 60, -2 }, {  0,  4, 62, -2 },
+    {  0,  2, 63, -1 } };
+static const int8_t bcw_w[5] = { -2, 3, 4, 5, 10 };   /* rcn_inter.c:89 */
+
+typedef struct { const uint16_t *p; int stride, w, h; } RefPlane;
+
+static inline int rpx(const RefPlane *r, int x, int y)
+{   /* emulate_block_border (rcn_inter.c:148-225): samples outside the picture repeat the border */
+    return r->p[(size_t)clipi(y, 0, r->h - 1) * r->stride + clipi(x, 0, r->w - 1)];
+}
+
+/* 14-bit intermediate prediction of one block (put_vvc_pel_pixels / qpel_h / qpel_v / qpel_hv and the
+ * epel equivalents, rcn_mc.c:401-419, 901-997, 1208-1300).  ntaps = 8 luma / 4 chroma; fx, fy = filters or NULL. */
+static void pred14(int16_t *dst, int dst_stride, const RefPlane *r, int x_int, int y_int, int w, int h,
+                   const int8_t *fx, const int8_t *fy, int ntaps, int bitdepth)
+{
+    int before = ntaps / 2 - 1;
+    int sh1 = bitdepth - 8;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int v;
+            if (!fx && !fy) {
+                v = rpx(r, x_int + x, y_int + y) << (14 - bitdepth);
+            } else if (fx && !fy) {
+                int s = 0;
+                for (int k = 0; k < ntaps; k++) s += fx[k] * rpx(r, x_int + x + k - before, y_int + y);
+                v = s >> sh1;
+            } else if (!fx && fy) {
+                int s = 0;
+                for (int k = 0; k < ntaps; k++) s += fy[k] * rpx(r, x_int + x, y_int + y + k - before);
+                v = s >> sh1;
+            } else {
+                int s2 = 0;
+                for (int j = 0; j < ntaps; j++) {
+                    int s = 0;
+                    for (int k = 0; k < ntaps; k++)
+                        s += fx[k] * rpx(r, x_int + x + k - before, y_int + y + j - before);
+                    s2 += fy[j] * (int16_t)(s >> sh1);     /* tmp[] is int16_t, rcn_mc.c:506,515 */
+                }
+                v = s2 >> 6;
+            }
+            dst[y * dst_stride + x] = (int16_t)v;
+        }
+}
+
+typedef struct { int x, y; } MV;
+
+static MV clip_mv(int pos_x, int pos_y, int pic_w, int pic_h, int pb_w, int pb_h, MV mv)
+{   /* rcn_inter.c:96-108 */
+    int x_max = (pic_w + 2 - pos_x) << 4, y_max = (pic_h + 2 - pos_y) << 4;
+    int x_min = -((pb_w + 3 + pos_x) << 4), y_min = -((pb_h + 3 + pos_y) << 4);
+    mv.x = clipi(mv.x, x_min, x_max);
+    mv.y = clipi(mv.y, y_min, y_max);
+    return mv;
+}
+
+/* prediction of one component of one PU from one reference into a 14-bit buffer */
+static void pu_pred14(int16_t *buf, const OVOMcRefs *refs, int list, int ref_idx, int comp,
+                      int pic_w, int pic_h, const OVOMcCmd *c, MV mv, int bitdepth)
+{
+    int pu_w = 1 << c->log2_w, pu_h = 1 << c->log2_h;
+    mv = clip_mv(c->x0, c->y0, pic_w, pic_h, pu_w, pu_h, mv);
+    if (comp == 0) {
+        RefPlane r = { refs->plane[list][ref_idx][0], refs->stride[list][ref_idx][0], pic_w, pic_h };
+        int px = mv.x & 15, py = mv.y & 15;
+        int small = (pu_w == 4 && pu_h == 4);                                              /* rcn_mc.c:457 */
+        /* half-pel AMVR never coexists with 4x4 (affine) blocks in a conforming stream; the reference would
+         * index ov_mc_filters_4[15] out of bounds there, so the combination is left undefined/ignored */
+        if ((c->flags & OVO_MC_HPEL_AMVR) && !small) { if (px == 8) px = 16; if (py == 8) py = 16; }   /* rcn_inter.c:572-577 */
+        const int8_t *fx = px ? (small ? mc_filt_l4[px - 1] : mc_filt_l[px - 1]) : NULL;
+        const int8_t *fy = py ? (small ? mc_filt_l4[py - 1] : mc_filt_l[py - 1]) : NULL;
+        pred14(buf, 128, &r, c->x0 + (mv.x >> 4), c->y0 + (mv.y >> 4), pu_w, pu_h, fx, fy, 8, bitdepth);
+    } else {
+        RefPlane r = { refs->plane[list][ref_idx][comp], refs->stride[list][ref_idx][comp], pic_w >> 1, pic_h >> 1 };
+        int px = mv.x & 31, py = mv.y & 31;
+        pred14(buf, 128, &r, (c->x0 >> 1) + (mv.x >> 5), (c->y0 >> 1) + (mv.y >> 5), pu_w >> 1, pu_h >> 1,
+               px ? mc_filt_c[px - 1] : NULL, py ? mc_filt_c[py - 1] : NULL, 4, bitdepth);
+    }
+}
+
+void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                    const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut)
+{
+    static int16_t p0[128 * 128], p1[128 * 128];
+    int maxv = (1 << bitdepth) - 1;
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVOMcCmd *c = &cmds[i];
+        MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
+        /* check_identical_motion, rcn_inter.c:256-267 (POCs compared as uint16_t) */
+        int identical = c->inter_dir == 3 &&
+                        (uint16_t)refs->poc[0][c->ref_idx0] == (uint16_t)refs->poc[1][c->ref_idx1] &&
+                        mv0.x == mv1.x && mv0.y == mv1.y;
+        int bi = c->inter_dir == 3 && !identical;
+        int uni_list = (c->inter_dir & 2 || identical) ? 1 : 0;          /* rcn_inter.c:2795-2812 */
+        for (int comp = 0; comp < 3; comp++) {
+            if (comp == 0 && !(c->flags & OVO_MC_LUMA)) continue;
+            if (comp != 0 && !(c->flags & OVO_MC_CHROMA)) continue;
+            int sh = comp ? 1 : 0;
+            int w = (1 << c->log2_w) >> sh, h = (1 << c->log2_h) >> sh;
+            uint16_t *d = dst[comp] + (size_t)(c->y0 >> sh) * dst_stride[comp] + (c->x0 >> sh);
+            if (bi) {
+                pu_pred14(p0, refs, 0, c->ref_idx0, comp, pic_w, pic_h, c, mv0, bitdepth);
+                pu_pred14(p1, refs, 1, c->ref_idx1, comp, pic_w, pic_h, c, mv1, bitdepth);
+                int def = (c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3);   /* rcn_inter.c:587 */
+                int w1 = def ? 0 : bcw_w[c->bcw_idx_plus1 - 1], w0 = 8 - w1;
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) {
+                        int a = p0[y * 128 + x], b = p1[y * 128 + x], v;
+                        if (def) v = (a + b + (1 << (14 - bitdepth))) >> (15 - bitdepth);   /* rcn_mc.c:433-439 */
+                        else     v = (b * w1 + a * w0 + (1 << (16 - bitdepth))) >> (17 - bitdepth);   /* rcn_mc.c:1520-1526 */
+                        d[(size_t)y * dst_stride[comp] + x] = (uint16_t)clipi(v, 0, maxv);
+                    }
+            } else {
+                MV mv = uni_list ? mv1 : mv0;
+                int ref_idx = uni_list ? c->ref_idx1 : c->ref_idx0;
+                pu_pred14(p0, refs, uni_list, ref_idx, comp, pic_w, pic_h, c, mv, bitdepth);
+                int shift = 14 - bitdepth, off = 1 << (shift - 1);       /* rcn_mc.c:458-465 */
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++)
+                        d[(size_t)y * dst_stride[comp] + x] = (uint16_t)clipi((p0[y * 128 + x] + off) >> shift, 0, maxv);
+            }
+            if (comp == 0 && lmcs_fwd_lut)                                /* rcn_inter.c:599, 1552 */
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) {
+                        uint16_t *q = &d[(size_t)y * dst_stride[0] + x];
+                        *q = lmcs_fwd_lut[*q & maxv];
+                    }
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * LMCS look-up tables (rcn_lmcs.c:84-187, 189-203)
+ * ------------------------------------------------------------------------------------------------- */
+void ovo_lmcs_build_luts(OVOLmcsLuts *luts, const OVOLmcsData *data, int bitdepth)
+{
+    const int nb_wnd = 16, prec = 11, rnd = 1 << (prec - 1);
+    int rng = 1 << bitdepth, log2_wnd = bitdepth - 4, smp_wnd = rng >> 4;
+    int min_idx = data->lmcs_min_bin_idx, max_idx_p1 = nb_wnd - data->lmcs_delta_max_bin_idx;
+    int cw_delta[16] = { 0 };
+    uint16_t fwd_step[16] = { 0 }, bwd_step[16] = { 0 }, bnd[17] = { 0 };
+    int maxv = rng - 1;
+
+    for (int i = min_idx; i < max_idx_p1; i++)
+        cw_delta[i] = data->lmcs_delta_sign_cw_flag[i] ? -data->lmcs_delta_abs_cw[i] : data->lmcs_delta_abs_cw[i];
+    for (int i = min_idx; i < max_idx_p1; i++) {          /* compute_windows_scale_steps */
+        int wnd_sz = smp_wnd + (int16_t)cw_delta[i];
+        if (wnd_sz) {
+            fwd_step[i] = (uint16_t)(((wnd_sz << prec) + (1 << (log2_wnd - 1))) >> log2_wnd);
+            bwd_step[i] = (uint16_t)((smp_wnd << prec) / wnd_sz);
+        }
+        bnd[i + 1] = (uint16_t)(bnd[i] + wnd_sz);
+    }
+    for (int i = max_idx_p1; i < nb_wnd; i++) bnd[i + 1] = bnd[i];
+
+    for (int val = 0; val < rng; val++) {                 /* derive_forward_lut */
+        int idx = val >> log2_wnd;
+        int nb_step = val - (idx << log2_wnd);
+        int v = (int16_t)bnd[idx] + (((int32_t)fwd_step[idx] * nb_step + rnd) >> prec);
+        luts->fwd_lut[val] = (uint16_t)clipi(v, 0, maxv);
+    }
+    for (int val = 0; val < rng; val++) {                 /* derive_backward_lut + get_bwd_idx */
+        int i = min_idx;
+        for (; i < max_idx_p1; i++)
+            if (val < bnd[i + 1]) break;
+        int idx = i < nb_wnd - 1 ? i : nb_wnd - 1;
+        int nb_step = val - bnd[idx];
+        int v = (idx << log2_wnd) + (((int32_t)bwd_step[idx] * nb_step + rnd) >> prec);
+        luts->bwd_lut[val] = (uint16_t)clipi(v, 0, maxv);
+    }
+    memcpy(luts->wnd_bnd, bnd, sizeof(bnd));
+}
+
+void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uint16_t *lut, int bitdepth)
+{   /* rcn_lmcs_reshape_luma_blk_lut, rcn_lmcs.c:274-284 */
+    int msk = (1 << bitdepth) - 1;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            plane[(size_t)y * stride + x] = lut[plane[(size_t)y * stride + x] & msk];
+}

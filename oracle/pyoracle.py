@@ -162,3 +162,77 @@ def sao_picture(planes, sao_ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1):
     dst, ds = _planes_arg(out)
     ref().ovref_sao_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, sao_ctu.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ---- motion compensation / LMCS -------------------------------------------------------------------------
+McCmd = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), ("log2_h", np.uint8),
+                  ("inter_dir", np.uint8), ("flags", np.uint8), ("ref_idx0", np.int8), ("ref_idx1", np.int8),
+                  ("bcw_idx_plus1", np.uint8), ("tool", np.uint8),
+                  ("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32),
+                  ("aux", np.uint32)])
+assert McCmd.itemsize == 32
+
+
+class McRefs(C.Structure):
+    _fields_ = [("plane", u16p * 3 * 16 * 2), ("stride", C.c_int * 3 * 16 * 2), ("poc", C.c_int32 * 16 * 2)]
+
+
+class LmcsData(C.Structure):
+    _fields_ = [("lmcs_min_bin_idx", C.c_uint8), ("lmcs_delta_max_bin_idx", C.c_uint8),
+                ("lmcs_delta_cw_prec_minus1", C.c_uint8), ("lmcs_delta_abs_cw", C.c_uint16 * 16),
+                ("lmcs_delta_sign_cw_flag", C.c_uint8 * 16), ("lmcs_delta_abs_crs", C.c_uint8),
+                ("lmcs_delta_sign_crs_flag", C.c_uint8)]
+
+
+class LmcsLuts(C.Structure):
+    _fields_ = [("fwd_lut", C.c_uint16 * 1024), ("bwd_lut", C.c_uint16 * 1024), ("wnd_bnd", C.c_uint16 * 17)]
+
+    def np(self, name):
+        return np.ctypeslib.as_array(getattr(self, name))
+
+
+def make_lmcs_data(d):
+    x = LmcsData()
+    x.lmcs_min_bin_idx = int(d["min_bin_idx"]); x.lmcs_delta_max_bin_idx = int(d["delta_max_bin_idx"])
+    x.lmcs_delta_cw_prec_minus1 = 0
+    x.lmcs_delta_abs_cw[:] = [int(v) for v in d["delta_abs_cw"]]
+    x.lmcs_delta_sign_cw_flag[:] = [int(v) for v in d["delta_sign_cw"]]
+    x.lmcs_delta_abs_crs = int(d["delta_abs_crs"]); x.lmcs_delta_sign_crs_flag = int(d["delta_sign_crs"])
+    return x
+
+
+def lmcs_build_luts(d, bitdepth=10, impl="port"):
+    luts = LmcsLuts()
+    data = make_lmcs_data(d)
+    fn = port().ovo_lmcs_build_luts if impl == "port" else ref().ovref_lmcs_build_luts
+    fn(C.byref(luts), C.byref(data), bitdepth)
+    return luts
+
+
+def make_mc_refs(ref_lists, pocs):
+    """ref_lists: [list0, list1], each a list of pictures (3 uint16 planes); pocs likewise."""
+    r = McRefs()
+    keep = []
+    for l in range(2):
+        for i, pic in enumerate(ref_lists[l]):
+            for c in range(3):
+                r.plane[l][i][c] = pic[c].ctypes.data_as(u16p)
+                r.stride[l][i][c] = pic[c].strides[0] // 2
+            r.poc[l][i] = int(pocs[l][i])
+            keep.append(pic)
+    return r, keep
+
+
+def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl="port", lmcs=None):
+    """Writes the predictions of all commands into dst_planes (in place) and returns them."""
+    h, w = dst_planes[0].shape
+    cmds = np.ascontiguousarray(cmds, dtype=McCmd)
+    refs, keep = make_mc_refs(ref_lists, pocs)
+    dst, ds = _planes_arg(dst_planes)
+    if impl == "port":
+        lut = lmcs.np("fwd_lut").ctypes.data_as(u16p) if lmcs is not None else None
+        port().ovo_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut)
+    else:
+        ref().ovref_mc_picture(dst, ds, w, h, log2_ctu, bitdepth, 1, C.byref(refs), cmds.ctypes.data_as(C.c_void_p),
+                               len(cmds), C.byref(lmcs) if lmcs is not None else None)
+    return dst_planes

@@ -228,3 +228,117 @@ ovref_sao_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int
     harness_close(h);
     free(params);
 }
+
+/* ===================================================================================================
+ * Motion compensation through the reference's coarse slots rcn_mcp_b / rcn_mcp_b_l / rcn_mcp_b_c
+ * (rcn_structures.h:650-676).  The destination OVBuffInfo points at the CTU origin inside the output
+ * picture so that the reference, which writes CTU-relative, lands on picture coordinates.
+ * =================================================================================================== */
+#include "ovdpb.h"
+#include "rcn_lmcs.h"
+
+static void harness_no_synchro(const OVPicture *const ref_pic, int a, int b, int c, int d) { (void)ref_pic; (void)a; (void)b; (void)c; (void)d; }
+
+void
+ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
+{
+    OVCTUDec *c;
+    OVLMCSData data;
+    ctudec_init(&c);
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 1, bitdepth);
+    memset(&data, 0, sizeof(data));
+    data.lmcs_min_bin_idx = d->lmcs_min_bin_idx;
+    data.lmcs_delta_max_bin_idx = d->lmcs_delta_max_bin_idx;
+    data.lmcs_delta_cw_prec_minus1 = d->lmcs_delta_cw_prec_minus1;
+    memcpy(data.lmcs_delta_abs_cw, d->lmcs_delta_abs_cw, sizeof(data.lmcs_delta_abs_cw));
+    memcpy(data.lmcs_delta_sign_cw_flag, d->lmcs_delta_sign_cw_flag, sizeof(data.lmcs_delta_sign_cw_flag));
+    data.lmcs_delta_abs_crs = d->lmcs_delta_abs_crs;
+    data.lmcs_delta_sign_crs_flag = d->lmcs_delta_sign_crs_flag;
+    c->rcn_funcs.rcn_init_lmcs(&c->lmcs_info, &data);
+    /* struct LMCSLUTs (rcn_lmcs.c:77-82) is private to the reference: fwd[1<<BD], bwd[1<<BD], bnd[17] */
+    memcpy(out, c->lmcs_info.luts, sizeof(*out));
+    free(c->lmcs_info.luts);
+    free(c);
+}
+
+void
+ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
+                 int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds,
+                 const OVOLmcsLuts *lmcs)
+{
+    OVCTUDec *c;
+    OVPartInfo part;
+    static OVPicture pics[2][16];
+    static OVFrame frames[2][16];
+    ctudec_init(&c);
+    memset(&part, 0, sizeof(part));
+    part.log2_ctu_s = log2_ctu_s;
+    part.log2_min_cb_s = 2;
+    c->part_ctx = &part;
+    c->rcn_ctx.ctudec = c;
+    c->pic_w = pic_w;
+    c->pic_h = pic_h;
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, lmcs != NULL, bitdepth);
+    (void)simd;
+    if (lmcs) {
+        c->lmcs_info.luts = malloc(sizeof(*lmcs));
+        memcpy(c->lmcs_info.luts, lmcs, sizeof(*lmcs));
+        c->lmcs_info.lmcs_enabled_flag = 1;
+    }
+    struct InterDRVCtx *ic = &c->drv_ctx.inter_ctx;
+    memset(pics, 0, sizeof(pics));
+    memset(frames, 0, sizeof(frames));
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++) {
+            if (!refs->plane[l][i][0]) continue;
+            OVFrame *f = &frames[l][i];
+            for (int k = 0; k < 3; k++) {
+                f->data[k] = (void *)refs->plane[l][i][k];
+                f->linesize[k] = (size_t)refs->stride[l][i][k] * sizeof(uint16_t);
+            }
+            f->width = pic_w; f->height = pic_h;
+            pics[l][i].frame = f;
+            pics[l][i].poc = refs->poc[l][i];
+            atomic_init(&pics[l][i].idx_function, 0);
+            pics[l][i].ovdpb_frame_synchro[0] = harness_no_synchro;
+            pics[l][i].ovdpb_frame_synchro[1] = harness_no_synchro;
+            if (l == 0) { ic->rpl0[i] = &pics[l][i]; ic->scale_fact_rpl0[i][0] = ic->scale_fact_rpl0[i][1] = 1 << 14; }
+            else        { ic->rpl1[i] = &pics[l][i]; ic->scale_fact_rpl1[i][0] = ic->scale_fact_rpl1[i][1] = 1 << 14; }
+        }
+
+    for (int n = 0; n < nb_cmds; n++) {
+        const OVOMcCmd *m = &cmds[n];
+        int ctu_s = 1 << log2_ctu_s;
+        c->ctb_x = m->x0 >> log2_ctu_s;
+        c->ctb_y = m->y0 >> log2_ctu_s;
+        int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
+        /* The reference writes into its CTU-local buffer (stride 324, rcn_ctu.c:558) and its SIMD kernels may
+         * store a few samples past a narrow block; give it the same kind of padded scratch and copy the PU out. */
+        enum { SCR_STRIDE = 384 };
+        static uint16_t scr[3][(128 + 8) * SCR_STRIDE];
+        struct OVBuffInfo b;
+        memset(&b, 0, sizeof(b));
+        b.stride = SCR_STRIDE;
+        b.stride_c = SCR_STRIDE;
+        b.y = scr[0]; b.cb = scr[1]; b.cr = scr[2];
+        OVMV mv0 = { .x = m->mv0_x, .y = m->mv0_y, .ref_idx = m->ref_idx0, .bcw_idx_plus1 = m->bcw_idx_plus1 };
+        OVMV mv1 = { .x = m->mv1_x, .y = m->mv1_y, .ref_idx = m->ref_idx1, .bcw_idx_plus1 = m->bcw_idx_plus1 };
+        ic->prec_amvr = (m->flags & OVO_MC_HPEL_AMVR) ? 3 /* MV_PRECISION_HALF, drv_utils.h:102 */ : 0;
+        if ((m->flags & 3) == 3)
+            c->rcn_funcs.rcn_mcp_b(c, b, ic, &part, mv0, mv1, x0, y0, m->log2_w, m->log2_h, m->inter_dir, m->ref_idx0, m->ref_idx1);
+        else if (m->flags & OVO_MC_LUMA)
+            c->rcn_funcs.rcn_mcp_b_l(c, b, ic, &part, mv0, mv1, x0, y0, m->log2_w, m->log2_h, m->inter_dir, m->ref_idx0, m->ref_idx1);
+        else if (m->flags & OVO_MC_CHROMA)
+            c->rcn_funcs.rcn_mcp_b_c(c, b, ic, &part, mv0, mv1, x0, y0, m->log2_w, m->log2_h, m->inter_dir, m->ref_idx0, m->ref_idx1);
+        for (int k = 0; k < 3; k++) {
+            int sh = k ? 1 : 0;
+            if ((k == 0 && !(m->flags & OVO_MC_LUMA)) || (k && !(m->flags & OVO_MC_CHROMA))) continue;
+            int bw = (1 << m->log2_w) >> sh, bh = (1 << m->log2_h) >> sh;
+            for (int y = 0; y < bh; y++)
+                memcpy(dst[k] + (size_t)((m->y0 >> sh) + y) * dst_stride[k] + (m->x0 >> sh),
+                       scr[k] + (size_t)((y0 >> sh) + y) * SCR_STRIDE + (x0 >> sh), bw * sizeof(uint16_t));
+        }
+    }
+    if (lmcs) free(c->lmcs_info.luts);
+    free(c);
+}

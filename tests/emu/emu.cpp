@@ -4,6 +4,7 @@
 #include <vector>
 #include "../../openvvc_b200/csrc/alf_host.h"
 #include "../../openvvc_b200/csrc/sao_kernels.h"
+#include "../../openvvc_b200/csrc/mc_host.h"
 
 extern "C" {
 
@@ -64,6 +65,47 @@ int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
     a.nb_ctu_w = (w + ctu_s - 1) >> log2_ctu; a.nb_ctu_h = (h + ctu_s - 1) >> log2_ctu;
     a.ctu = (const SaoCtuDev *)ctu;
     ovd_emulate<SaoK>(a, ovd_dim3((w + SaoK::BX * 8 - 1) / (SaoK::BX * 8), (h + SaoK::BY - 1) / SaoK::BY, 3), 0);
+    return 0;
+}
+
+// refs: plane pointers / strides (samples) / pocs laid out like OVOMcRefs ([list][ref][comp])
+struct EmuMcRefs {
+    const uint16_t *plane[2][16][3];
+    int stride[2][16][3];
+    int32_t poc[2][16];
+};
+
+int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h, int bitdepth,
+                   const EmuMcRefs *refs, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd)
+{
+    int n_items = mc_count_items(cmds, nb_cmds);
+    std::vector<McItemDev> items(n_items + 1);
+    mc_build_items(items.data(), cmds, nb_cmds);
+    McK::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
+    a.pic_w = w; a.pic_h = h; a.bitdepth = bitdepth;
+    a.cmds = (const McCmdDev *)cmds; a.items = items.data(); a.nb_items = n_items;
+    a.lmcs_fwd = lmcs_fwd;
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++) {
+            a.refs.poc[l][i] = refs->poc[l][i];
+            for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = refs->plane[l][i][c]; a.refs.pitch[l][i][c] = refs->stride[l][i][c]; }
+        }
+    ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
+    return n_items;
+}
+
+int emu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *d, int bitdepth)
+{
+    lmcs_build_luts_host(luts, d, bitdepth);
+    return 0;
+}
+
+int emu_lmcs_reshape(uint16_t *plane, int stride, int w, int h, int bitdepth, const uint16_t *lut)
+{
+    LmcsReshapeK::Args a = { plane, stride, w, h, bitdepth, lut };
+    ovd_emulate<LmcsReshapeK>(a, ovd_dim3((w + 255) / 256, (h + 7) / 8, 1), 0);
     return 0;
 }
 

@@ -1,0 +1,54 @@
+"""Test helpers for motion compensation / LMCS cases."""
+import ctypes as C
+
+import numpy as np
+
+from openvvc_b200 import synth
+
+
+def mc_case(po, w, h, seed, log2_ctu=7, lmcs=False, min_log2=3, n_refs=2):
+    refs0 = [synth.planes(w, h, seed + 10 + i) for i in range(n_refs)]
+    refs1 = [synth.planes(w, h, seed + 20 + i) for i in range(n_refs)]
+    pocs = [[8 * (i + 1) for i in range(n_refs)], [8 * (i + 2) for i in range(n_refs)]]   # poc0[1] == poc1[0]
+    cmds = synth.mc_commands(w, h, seed, log2_ctu, n_refs=n_refs, min_log2=min_log2).astype(po.McCmd)
+    luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
+    return refs0, refs1, pocs, cmds, luts
+
+
+def blank(w, h):
+    return [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
+
+
+def emu_mc(emu, po, w, h, refs0, refs1, pocs, cmds, luts, bitdepth=10):
+    out = blank(w, h)
+    refs, keep = po.make_mc_refs([refs0, refs1], pocs)
+    dst, ds = po._planes_arg(out)
+    lut = luts.np("fwd_lut").ctypes.data_as(po.u16p) if luts is not None else None
+    emu.emu_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut)
+    return out
+
+
+def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts):
+    from openvvc_b200 import api
+    dst = ctx.picture(w, h)
+    dst.upload(blank(w, h))
+    pics = [[], []]
+    for l, lst in enumerate((refs0, refs1)):
+        for planes in lst:
+            p = ctx.picture(w, h); p.upload(planes); pics[l].append(p)
+    batch = api.McBatch(ctx, len(cmds), api.mc_nb_items(cmds))
+    batch.upload(cmds.astype(api.MC_CMD))
+    lm = None
+    if luts is not None:
+        gl = api.LmcsLuts()
+        C.memmove(C.byref(gl), C.byref(luts), C.sizeof(gl))
+        lm = api.Lmcs(ctx, gl)
+    batch.run(dst, pics, pocs, lm)
+    out = dst.download()
+    batch.destroy(); dst.destroy()
+    if lm:
+        lm.destroy()
+    for lst in pics:
+        for p in lst:
+            p.destroy()
+    return out

@@ -1,0 +1,119 @@
+"""Motion compensation + LMCS: oracle port vs golden / compiled reference (CPU), kernel-source emulation vs
+oracle (CPU), and the sm_100a kernels through the C ABI vs oracle / golden (GPU)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import helpers_mc
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_golden.json")))
+IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], "_lmcs" if c["lmcs"] else "")
+
+
+def _case(po, c):
+    refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(po, c["w"], c["h"], c["seed"], c["log2_ctu"], c["lmcs"], c["min_log2"])
+    assert helpers.md5(cmds, *refs0[0], *refs1[-1]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return refs0, refs1, pocs, cmds, luts
+
+
+@pytest.mark.parametrize("c", GOLDEN, ids=IDS)
+def test_port_matches_golden(oracle, c):
+    refs0, refs1, pocs, cmds, luts = _case(oracle, c)
+    dst = helpers_mc.blank(c["w"], c["h"])
+    oracle.mc_picture(dst, [refs0, refs1], pocs, cmds, c["log2_ctu"], impl="port", lmcs=luts)
+    assert [helpers.md5(p) for p in dst] == c["md5"]
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs,min_log2", [(416, 240, 7, False, 3), (416, 240, 7, True, 2), (832, 480, 7, True, 3),
+                                                     (264, 136, 6, False, 2), (72, 40, 5, True, 2)])
+def test_port_vs_compiled_reference(oracle, w, h, log2, lmcs, min_log2):
+    po = oracle
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(po, w, h, 5 * w + h, log2, lmcs, min_log2)
+    a, b = helpers_mc.blank(w, h), helpers_mc.blank(w, h)
+    po.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts)
+    po.mc_picture(b, [refs0, refs1], pocs, cmds, log2, impl="ref", lmcs=luts)
+    helpers.assert_planes_equal(a, b, "MC port vs reference")
+
+
+def test_lmcs_luts_port_vs_reference_and_product(oracle):
+    from openvvc_b200 import api, synth
+    for seed in range(8):
+        d = synth.lmcs_data(900 + seed)
+        p = oracle.lmcs_build_luts(d, impl="port")
+        g = api.lmcs_build_luts(d)
+        for k in ("fwd_lut", "bwd_lut", "wnd_bnd"):
+            assert (p.np(k) == g.np(k)).all(), k
+            if oracle.ref_available():
+                assert (p.np(k) == oracle.lmcs_build_luts(d, impl="ref").np(k)).all(), k
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs,min_log2", [(416, 240, 7, False, 3), (416, 240, 7, True, 2), (256, 128, 6, False, 3),
+                                                     (136, 72, 5, True, 2), (832, 480, 7, False, 2)])
+def test_emulated_kernel_matches_oracle(oracle, emu, w, h, log2, lmcs, min_log2):
+    refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(oracle, w, h, 7 * w + h, log2, lmcs, min_log2)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts)
+    helpers.assert_planes_equal(helpers_mc.emu_mc(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts), a, "emulated MC kernel vs oracle")
+
+
+def test_emulated_lmcs_reshape(oracle, emu):
+    from openvvc_b200 import synth
+    luts = oracle.lmcs_build_luts(synth.lmcs_data(3))
+    pl = synth.planes(264, 136, 4)[0]
+    want = pl.copy()
+    oracle.port().ovo_lmcs_reshape_plane(want.ctypes.data_as(oracle.u16p), want.strides[0] // 2, 264, 136,
+                                         luts.np("bwd_lut").ctypes.data_as(oracle.u16p), 10)
+    got = pl.copy()
+    emu.emu_lmcs_reshape(got.ctypes.data_as(oracle.u16p), got.strides[0] // 2, 264, 136, 10, luts.np("bwd_lut").ctypes.data_as(oracle.u16p))
+    assert (got == want).all()
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", GOLDEN, ids=IDS)
+def test_gpu_matches_golden(oracle, gpu_ctx, c):
+    refs0, refs1, pocs, cmds, luts = _case(oracle, c)
+    out = helpers_mc.gpu_mc(gpu_ctx, c["w"], c["h"], refs0, refs1, pocs, cmds, luts)
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,lmcs,min_log2", [(416, 240, 7, False, 2), (264, 136, 6, True, 2), (1920, 1080, 7, True, 3)])
+def test_gpu_matches_oracle(oracle, gpu_ctx, w, h, log2, lmcs, min_log2):
+    refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(oracle, w, h, 9 * w + h, log2, lmcs, min_log2)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts), a, "CUDA MC vs oracle")
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
+    """BASELINE.json config 2 geometry (3840x2160): CUDA vs the compiled reference (SIMD table) when present."""
+    w, h = 3840, 2160
+    refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(oracle, w, h, 77, 7, True, 3)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="ref" if oracle.ref_available() else "port", lmcs=luts)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts), a, "CUDA MC vs reference at 4K")
+
+
+@pytest.mark.gpu
+def test_gpu_lmcs_backward_picture(oracle, gpu_ctx):
+    from openvvc_b200 import api, synth
+    w, h = 1920, 1080
+    luts = oracle.lmcs_build_luts(synth.lmcs_data(11))
+    planes = synth.planes(w, h, 12)
+    want = planes[0].copy()
+    oracle.port().ovo_lmcs_reshape_plane(want.ctypes.data_as(oracle.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(oracle.u16p), 10)
+    gl = api.LmcsLuts(); C.memmove(C.byref(gl), C.byref(luts), C.sizeof(gl))
+    lm = api.Lmcs(gpu_ctx, gl)
+    pic = gpu_ctx.picture(w, h); pic.upload(planes)
+    lm.reshape(pic, forward=False)
+    out = pic.download()
+    assert (out[0] == want).all() and (out[1] == planes[1]).all()
+    lm.destroy(); pic.destroy()
