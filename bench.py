@@ -3,12 +3,14 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 4k|8k]
 
-One "step" = one pass of the hot path over a batch of `pictures_per_step` synthetic pictures per GPU
+One "step" = one pass of the hot path over a batch of `pictures_per_step` synthetic inter pictures per GPU
 (frame-parallel sharding: every rank owns whole pictures); value = pictures/s over all
-ranks with inputs resident in HBM; e2e = the same through the host-buffer C-ABI calls (H2D of planes and
-parameters + D2H of the result inside the timed region).  Prints ONE JSON line on rank 0.
+ranks with inputs resident in HBM; e2e = the same through the host-buffer C-ABI calls (H2D of reference
+planes' worth of decoder state: PU lists + in-loop parameters, D2H of the output picture, inside the timed
+region).  Prints ONE JSON line on rank 0.
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -23,7 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["sao", "alf"]       # widened as §8 rows land; named in config.workload
+STAGES_IMPLEMENTED = ["mc(uni/bi/bcw)+lmcs_fwd", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
 def peaks():
@@ -70,38 +72,49 @@ class ClockSampler(threading.Thread):
 
 
 def make_workload(w, h, n_pics, seed0=5000):
-    """n_pics synthetic pictures with their SAO/ALF decoder state (SURVEY.md §8(d) generators)."""
-    import helpers
-    from oracle import pyoracle as po   # only for the table struct layout helper + cpu arms
+    """Shared reference pictures + n_pics synthetic inter pictures: PU list, SAO and ALF decoder state
+    (SURVEY.md §8(d) generators)."""
     from openvvc_b200 import api, synth
+    refs = [[synth.planes(w, h, seed0 + 900 + i) for i in range(2)], [synth.planes(w, h, seed0 + 950 + i) for i in range(2)]]
+    pocs = [[8, 16], [16, 24]]
+    lmcs = api.lmcs_build_luts(synth.lmcs_data(seed0))
     pics = []
     for i in range(n_pics):
-        planes = synth.planes(w, h, seed0 + i, "natural")
         ap = synth.alf_params(w, h, seed0 + 100 + i, 7)
         tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
-        pics.append(dict(planes=planes, tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao))
-    return pics
+        cmds = synth.mc_commands(w, h, seed0 + 300 + i, 7).astype(api.MC_CMD)
+        pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds))
+    return dict(refs=refs, pocs=pocs, lmcs=lmcs, pics=pics)
+
+
+def mc_dirs_per_sample(cmds):
+    area = (1 << cmds["log2_w"].astype(np.int64)) * (1 << cmds["log2_h"].astype(np.int64))
+    ident = (cmds["mv0_x"] == cmds["mv1_x"]) & (cmds["mv0_y"] == cmds["mv1_y"]) & (cmds["ref_idx0"] == 1) & (cmds["ref_idx1"] == 0)
+    nref = np.where((cmds["inter_dir"] == 3) & ~ident, 2, 1)
+    return float((area * nref).sum() / area.sum())
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_step(po, pics, threads):
-    """The reference's own CPU implementation (oracle/_ref, SSE4.1/AVX2 table) of the same stages, one picture
-    per host thread (the reference's frame parallelism, ovdec.h:47)."""
-    import ctypes as C
+def reference_step(po, wl, threads):
+    """The reference's own CPU implementation (oracle/_ref: rcn_mcp_b, rcn_sao_filter_line, rcn_alf_filter_line
+    through the SSE4.1/AVX2 function table) of the same stages, one picture per host thread (the reference's
+    frame parallelism, ovdec.h:47).  Falls back to the C port only if oracle/_ref was not built."""
+    impl = "ref" if po.ref_available() else "port"
+    h, w = wl["refs"][0][0][0].shape
+    luts = po.LmcsLuts()
+    C.memmove(C.byref(luts), C.byref(wl["lmcs"]), C.sizeof(luts))
 
     def one(p):
         t = po.AlfTables()
         C.memmove(C.byref(t), C.byref(p["tab"]), C.sizeof(t))
-        if po.ref_available():
-            s = po.sao_picture(p["planes"], p["sao"].astype(po.SaoCtu), 7, impl="ref", simd=1)
-            po.alf_picture(s, t, p["ctu"], 7, impl="ref", simd=1)
-        else:
-            s = po.sao_picture(p["planes"], p["sao"].astype(po.SaoCtu), 7, impl="port")
-            po.alf_picture(s, t, p["ctu"], 7, impl="port")
+        rec = [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
+        po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts)
+        s = po.sao_picture(rec, p["sao"].astype(po.SaoCtu), 7, impl=impl)
+        po.alf_picture(s, t, p["ctu"], 7, impl=impl)
 
-    ths = [threading.Thread(target=one, args=(p,)) for p in pics[:threads]]
+    ths = [threading.Thread(target=one, args=(p,)) for p in wl["pics"][:threads]]
     t0 = time.perf_counter()
     for t in ths:
         t.start()
@@ -116,13 +129,13 @@ def run_reference(args, w, h):
         return
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    pics = make_workload(w, h, min(cores, 8))
-    threads = len(pics)
+    wl = make_workload(w, h, min(cores, 8))
+    threads = len(wl["pics"])
     for _ in range(max(1, min(args.warmup, 1))):
-        reference_step(po, pics, threads)
+        reference_step(po, wl, threads)
     tot, n = 0.0, 0
     for _ in range(args.steps):
-        dt, k = reference_step(po, pics, threads)
+        dt, k = reference_step(po, wl, threads)
         tot += dt; n += k
     fps = n / tot
     kind = "reference" if po.ref_available() else "port"
@@ -137,10 +150,10 @@ def run_reference(args, w, h):
 
 
 def workload_config(w, h, pics_per_step):
-    return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA picture, rcn stages: %s (in-loop filters; "
-                        "remaining rcn stages not yet in the timed path)" % (w, h, "+".join(STAGES_IMPLEMENTED)),
+    return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
+                        "(residual/intra/DBF stages not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "parallelism": "frame-parallel, one picture stream per GPU",
-            "l2": "inputs larger than L2: %d pictures x (src+mid+dst) per step" % pics_per_step}
+            "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -179,24 +192,35 @@ def main():
     ctx = api.Ctx(local, stream.cuda_stream)
 
     P = args.pics
-    pics = make_workload(w, h, P, seed0=5000 + 1000 * rank)
+    wl = make_workload(w, h, P, seed0=5000 + 1000 * rank)
+    pics = wl["pics"]
     pbytes = w * h * 2 * 3 // 2
 
-    # device-resident state: per picture src (deblocked), mid (post-SAO), dst (post-ALF) + parameters
+    # device-resident state: reference pictures, per picture recon (prediction), mid (post-SAO), dst (post-ALF)
+    ref_pics = [[ctx.picture(w, h) for _ in lst] for lst in wl["refs"]]
+    for lst, src in zip(ref_pics, wl["refs"]):
+        for pic, planes in zip(lst, src):
+            pic.upload(planes)
+    lmcs = api.Lmcs(ctx, wl["lmcs"])
     dev = []
     for p in pics:
-        d = dict(src=ctx.picture(w, h), mid=ctx.picture(w, h), dst=ctx.picture(w, h),
-                 alf=api.AlfParams(ctx, w, h, 7), sao=api.SaoParams(ctx, w, h, 7))
-        d["src"].upload(p["planes"])
+        d = dict(rec=ctx.picture(w, h), mid=ctx.picture(w, h), dst=ctx.picture(w, h),
+                 alf=api.AlfParams(ctx, w, h, 7), sao=api.SaoParams(ctx, w, h, 7),
+                 mc=api.McBatch(ctx, len(p["cmds"]), api.mc_nb_items(p["cmds"])))
         d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
         d["sao"].upload(p["sao"])
+        d["mc"].upload(p["cmds"])
         dev.append(d)
     ctx.sync()
 
+    def run_stages(d):
+        d["mc"].run(d["rec"], ref_pics, wl["pocs"], lmcs)
+        d["sao"].run(d["mid"], d["rec"])
+        d["alf"].run(d["dst"], d["mid"])
+
     def step_device():
         for d in dev:
-            d["sao"].run(d["mid"], d["src"])
-            d["alf"].run(d["dst"], d["mid"])
+            run_stages(d)
 
     def barrier():
         if world > 1:
@@ -212,7 +236,6 @@ def main():
     time.sleep(0.3)
 
     # ---- value: device-resident throughput, CUDA events on the launching stream
-    ctx.profile(True); ctx.profile_reset()
     n0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -223,23 +246,27 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - n0
-    prof = {s: ctx.profile_get(s) for s in ("alf_luma", "alf_chroma", "sao")}
+
+    # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
+    stage_names = ("mc", "sao", "alf_luma", "alf_chroma")
+    ctx.profile(True); ctx.profile_reset()
+    for _ in range(max(2, min(args.steps, 5))):
+        step_device()
+    prof = {s: ctx.profile_get(s) for s in stage_names}
     ctx.profile(False)
 
-    # ---- e2e: host buffers (pinned), H2D planes + params, stages, D2H result, every step
-    pinned_in = [[torch.from_numpy(pl).pin_memory() for pl in p["planes"]] for p in pics]
-    pinned_out = [[torch.empty_like(t).pin_memory() for t in pin] for pin in pinned_in]
-    np_in = [[t.numpy() for t in pin] for pin in pinned_in]
+    # ---- e2e: host buffers (pinned), H2D decoder state, stages, D2H result, every step
+    pinned_out = [[torch.empty((hh, ww), dtype=torch.uint16).pin_memory() for (hh, ww) in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
+                  for _ in pics]
     np_out = [[t.numpy() for t in pin] for pin in pinned_out]
 
     def step_e2e():
         for i, d in enumerate(dev):
             p = pics[i]
-            d["src"].upload(np_in[i])
+            d["mc"].upload(p["cmds"])
             d["sao"].upload(p["sao"])
             d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
-            d["sao"].run(d["mid"], d["src"])
-            d["alf"].run(d["dst"], d["mid"])
+            run_stages(d)
             api._check(ctx.h, api.lib().ovgpu_picture_download(ctx.h, d["dst"].p, *api._host_planes(np_out[i])), "download")
         ctx.sync()
 
@@ -263,32 +290,40 @@ def main():
         fps = world * P * args.steps / (ms * 1e-3)
         e2e_fps = world * P * e2e_steps / e2e_s
         peak, peak_src = peaks()
-        luma_ms, luma_n = prof["alf_luma"]
-        luma_bytes = 2 * w * h * 2                       # read + write of the luma plane
-        achieved = luma_bytes / (luma_ms / luma_n * 1e-3) / 1e9 if luma_n else None
-        tab_bytes = 24 * 100 * 36 * 4 + 8 * (((w + 127) // 128) * ((h + 127) // 128))
-        sao_bytes = pics[0]["sao"].nbytes
+        dirs = float(np.mean([mc_dirs_per_sample(p["cmds"]) for p in pics]))
+        L, Cc = w * h * 2, w * h     # luma plane bytes, both chroma planes bytes
+        # algorithmic bytes per launch: MC (dirs+1)*P, SAO 2P, ALF luma 2L, ALF chroma 2C
+        alg = {"mc": (dirs + 1) * pbytes, "sao": 2 * pbytes, "alf_luma": 2 * L, "alf_chroma": 2 * Cc}
+        stages = {}
+        for s in stage_names:
+            t_ms, n = prof[s]
+            if n:
+                avg = t_ms / n
+                stages[s] = {"avg_launch_ms": avg, "algorithmic_bytes": alg[s], "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9,
+                             "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
+        top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
+        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",
                 "config": workload_config(w, h, P),
                 "gpu_launches": launches,
-                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": P * (pbytes + tab_bytes + sao_bytes),
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps},
-                "roofline": {"kernel": "AlfLumaK (classification + 7x7 luma ALF)", "bound": "hbm", "achieved": achieved,
-                             "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                             "frac": achieved / peak if achieved else None, "traffic": None,
-                             "algorithmic_bytes_per_launch": luma_bytes, "avg_launch_ms": luma_ms / luma_n if luma_n else None},
-                "stage_ms_per_picture": {s: (prof[s][0] / prof[s][1] if prof[s][1] else None) for s in prof},
+                "roofline": {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak,
+                             "peak_source": peak_src, "unit": "GB/s", "frac": stages[top]["frac"], "traffic": None,
+                             "algorithmic_bytes_per_launch": stages[top]["algorithmic_bytes"],
+                             "avg_launch_ms": stages[top]["avg_launch_ms"]},
+                "stages": stages, "mc_dirs_per_sample": dirs,
                 "clocks": clocks}
         # CPU baseline on the box's host cores (N=1 only): the compiled reference on a bounded sample
         if world == 1:
             from oracle import pyoracle as po
             cores = min(os.cpu_count() or 1, P)
-            reference_step(po, pics, cores)
+            reference_step(po, wl, cores)
             tot, n = 0.0, 0
             while tot < 10.0 and n < 64:
-                dt, k = reference_step(po, pics, cores)
+                dt, k = reference_step(po, wl, cores)
                 tot += dt; n += k
             line["cpu_baseline"] = {"value": n / tot, "unit": "frames/s", "cores": cores,
                                     "kind": "reference" if po.ref_available() else "port",

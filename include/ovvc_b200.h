@@ -195,6 +195,52 @@ int  ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmd
 int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                       const OVGPULmcs *lmcs);
 
+/* ---- Residual  (replaces tmp.rcn_tu_st / tmp.rcn_tu_c, rcn_transform_tree.c:1228-1390, and below them
+ *                 dequant_tb_4x4 (rcn_dequant.c:160), process_lfnst(_luma) (drv_lfnst.c:120), tr.func / tr.dc
+ *                 (rcn_transform.c:45-598) and ict.add / ict.ict (rcn_residuals.c:46-331)) ------------------------- */
+#define OVGPU_TU_IMPLICIT_MTS 1   /* luma TB of an intra, non-MIP CU while ctudec->mts_implicit (rcn_transform_tree.c:435) */
+#define OVGPU_TU_LFNST_L      2   /* TUInfo.lfnst_flag applies to the luma TB                                       */
+#define OVGPU_TU_LFNST_C      4   /* TUInfo.lfnst_flag applies to the chroma TBs (dual-tree chroma, rcn_tu_c)       */
+
+/* One recorded transform unit; x0/y0 picture-absolute luma samples, log2_w/h the luma size (chroma TBs are half).
+ * Per-TB arrays are indexed like TUInfo.tb_info (rcn_transform_tree.c:56-66): [0] Cb or joint CbCr, [1] Cr, [2] luma. */
+typedef struct OVGPUTuCmd {
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h;
+    uint8_t cbf_mask;             /* 0x10 luma, 0x08 joint CbCr, 0x02 Cb, 0x01 Cr                  */
+    uint8_t tr_skip_mask;
+    uint8_t cu_mts_flag, cu_mts_idx;
+    uint8_t flags;                /* OVGPU_TU_*                                                    */
+    uint8_t lfnst_idx;
+    uint8_t qp[4];                /* dequant_luma / cb / cr / joint_cb_cr .qp (ctudec.h:829-833)   */
+    uint8_t qp_ts[4];             /* dequant_*_skip.qp                                             */
+    uint16_t last_pos[3];
+    int16_t chroma_scale;         /* lmcs_info.lmcs_chroma_scale at call time (2048 = neutral)     */
+    uint8_t lfnst_mode_l;         /* ctudec->intra_mode (PLANAR for MIP CUs)                       */
+    uint8_t lfnst_mode_c;         /* chroma mode with DM / CCLM resolved to the collocated luma mode (drv_lfnst.c:97-104) */
+    uint16_t pad;
+    uint32_t coeff_off[3];        /* int16 offsets into the coefficient arena; data in the reference's buffer order:
+                                   * 4x4 sub-blocks of 16 contiguous values, min(32,w)/4 per row (rcn_dequant.c:243-253) */
+    uint32_t pad2;
+    uint64_t sig_sb_map[3];
+} OVGPUTuCmd;
+
+/* slice-level switches of the residual path */
+typedef struct OVGPUTuSlice {
+    uint8_t dep_quant;            /* ctudec->residual_coding_l == residual_coding_dpq              */
+    uint8_t sh_ts_disabled;       /* ctudec->sh_ts_disabled                                        */
+    uint8_t ict_type;             /* (ph_joint_cbcr_sign << 1) | chroma residual scaling (slicedec.c:1354-1359) */
+    uint8_t pad;
+} OVGPUTuSlice;
+
+typedef struct OVGPUTuBatch OVGPUTuBatch;   /* pinned staging + device copy of one picture's TU list and coefficients */
+int  ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPUTuBatch **b);
+void ovgpu_tu_batch_destroy(OVGPUTuBatch *b);
+int  ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds, int nb_cmds,
+                           const int16_t *coeffs, size_t nb_coeffs, const OVGPUTuSlice *slice);
+/* pic += residual of every TU (pic holds the prediction). Asynchronous. */
+int  ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -321,6 +321,36 @@ class McBatch:
             self.p = vp()
 
 
+class TuSlice(C.Structure):
+    _fields_ = [("dep_quant", C.c_uint8), ("sh_ts_disabled", C.c_uint8), ("ict_type", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class TuBatch:
+    """One picture's transform units + coefficient arena on the device (ovgpu_tu_batch_*)."""
+
+    def __init__(self, ctx, max_cmds, max_coeffs):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_tu_batch_create(ctx.h, int(max_cmds), C.c_size_t(int(max_coeffs)), C.byref(self.p)), "tu_batch_create")
+
+    def upload(self, cmds, coeffs, dep_quant=1, sh_ts_disabled=0, ict_type=0):
+        from .synth_tu import TU_CMD
+        cmds = np.ascontiguousarray(cmds, dtype=TU_CMD)
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.int16)
+        sl = TuSlice(int(dep_quant), int(sh_ts_disabled), int(ict_type), 0)
+        self._keep = (cmds, coeffs)
+        _check(self.ctx.h, lib().ovgpu_tu_batch_upload(self.ctx.h, self.p, vp(cmds.ctypes.data), len(cmds), vp(coeffs.ctypes.data),
+                                                       C.c_size_t(len(coeffs)), C.byref(sl)), "tu_batch_upload")
+
+    def run(self, pic):
+        _check(self.ctx.h, lib().ovgpu_residual_picture(self.ctx.h, pic.p, self.p), "residual_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_tu_batch_destroy(self.p)
+            self.p = vp()
+
+
 def mc_nb_items(cmds):
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))
     return int((((w + 15) >> 4) * ((h + 15) >> 4)).sum())

@@ -1,0 +1,106 @@
+// tr.cu -- C-ABI entry points of the residual path (kernels in tr_kernels.h, work lists in tr_host.h).
+// Replaces tmp.rcn_tu_st / tmp.rcn_tu_c (libovvc/rcn_transform_tree.c:1228-1390) for all TUs of a picture.
+#include "common.cuh"
+#include "tr_host.h"
+#include <stdlib.h>
+
+static_assert(sizeof(TuCmdDev) == sizeof(OVGPUTuCmd) && sizeof(TuCmdDev) == 72, "TU command layout");
+
+struct OVGPUTuBatch {
+    int max_cmds, nb_cmds, nb_small, nb_large, device;
+    size_t max_coeffs, nb_coeffs;
+    OVGPUTuSlice slice;
+    TuCmdDev *h_cmds, *d_cmds;
+    TbItemDev *h_items, *d_items;       // small items first, then large ones
+    int16_t *h_coeffs, *d_coeffs;
+};
+
+template <int GROUP>
+static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, const TbItemDev *items, int n)
+{
+    typedef TrK<GROUP> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { PlaneView v = plane_view(pic, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
+    a.bitdepth = pic->bitdepth;
+    a.cmds = b->d_cmds; a.items = items; a.nb_items = n; a.arena = b->d_coeffs;
+    a.dep_quant = b->slice.dep_quant; a.sh_ts_disabled = b->slice.sh_ts_disabled; a.ict_type = b->slice.ict_type;
+    return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, ctx->stream);
+}
+
+extern "C" {
+
+int ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPUTuBatch **out)
+{
+    if (!ctx || !out || max_cmds <= 0 || !max_coeffs) return OVGPU_EINVAL;
+    OVGPUTuBatch *b = (OVGPUTuBatch *)calloc(1, sizeof(*b));
+    if (!b) return OVGPU_ENOMEM;
+    b->max_cmds = max_cmds; b->max_coeffs = max_coeffs; b->device = ctx->device;
+    if (cudaMallocHost(&b->h_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMallocHost(&b->h_items, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
+        cudaMallocHost(&b->h_coeffs, sizeof(int16_t) * max_coeffs) != cudaSuccess ||
+        cudaMalloc(&b->d_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMalloc(&b->d_items, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
+        cudaMalloc(&b->d_coeffs, sizeof(int16_t) * max_coeffs) != cudaSuccess) {
+        ovgpu_tu_batch_destroy(b);
+        return ovgpu_set_error(ctx, OVGPU_ENOMEM, "TU batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = b;
+    return 0;
+}
+
+void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->h_cmds) cudaFreeHost(b->h_cmds);
+    if (b->h_items) cudaFreeHost(b->h_items);
+    if (b->h_coeffs) cudaFreeHost(b->h_coeffs);
+    if (b->d_cmds) cudaFree(b->d_cmds);
+    if (b->d_items) cudaFree(b->d_items);
+    if (b->d_coeffs) cudaFree(b->d_coeffs);
+    free(b);
+}
+
+int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds, int nb_cmds,
+                          const int16_t *coeffs, size_t nb_coeffs, const OVGPUTuSlice *slice)
+{
+    if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs ||
+        (nb_cmds && (!cmds || !coeffs)))
+        return OVGPU_EINVAL;
+    for (int i = 0; i < nb_cmds; i++)
+        if (tu_check_cmd(&cmds[i], nb_coeffs))
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d malformed", i);
+    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // staging buffers may still be in flight
+    b->slice = *slice;
+    b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
+    if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
+    memcpy(b->h_cmds, cmds, sizeof(TuCmdDev) * nb_cmds);
+    memcpy(b->h_coeffs, coeffs, sizeof(int16_t) * nb_coeffs);
+    tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
+    tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(TuCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * (b->nb_small + b->nb_large),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_coeffs, b->h_coeffs, sizeof(int16_t) * nb_coeffs, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b)
+{
+    if (!ctx || !pic || !b) return OVGPU_EINVAL;
+    if (pic->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "residual path is built for 10-bit pictures");
+    for (int i = 0; i < b->nb_cmds; i++) {
+        const TuCmdDev *c = &b->h_cmds[i];
+        if (c->x0 + (1 << c->log2_w) > pic->width || c->y0 + (1 << c->log2_h) > pic->height)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
+    }
+    const int nk = (b->nb_small > 0) + (b->nb_large > 0);
+    if (!nk) return 0;
+    StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, nk);
+    if (b->nb_small) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items, b->nb_small));
+    if (b->nb_large) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->nb_small, b->nb_large));
+    return 0;
+}
+
+} // extern "C"

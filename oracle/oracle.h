@@ -138,6 +138,37 @@ typedef struct OVOLmcsLuts {          /* struct LMCSLUTs, rcn_lmcs.c:77-82 (10-b
 void ovo_lmcs_build_luts(OVOLmcsLuts *luts, const OVOLmcsData *data, int bitdepth);
 void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uint16_t *lut, int bitdepth);
 
+/* ---- Residual: dequantisation, LFNST, inverse transform, residual add ------------------------------------- */
+/* One command = one tmp.rcn_tu_st (rcn_transform_tree.c:1228) or tmp.rcn_tu_c (:1349, dual-tree chroma) call;
+ * picture-absolute luma coordinates, luma-sized log2_w/h.  Identical to OVGPUTuCmd (include/ovvc_b200.h).
+ * Index order of the per-TB arrays follows TUInfo.tb_info: [0] Cb (or the joint Cb-Cr block), [1] Cr, [2] luma. */
+#define OVO_TU_IMPLICIT_MTS 1   /* luma: intra, non-MIP CU in a slice with mts_implicit (rcn_transform_tree.c:435) */
+#define OVO_TU_LFNST_L      2   /* TUInfo.lfnst_flag applies to the luma TB  (rcn_tu_st / rcn_tu_l)              */
+#define OVO_TU_LFNST_C      4   /* TUInfo.lfnst_flag applies to the chroma TBs (rcn_tu_c only)                    */
+typedef struct OVOTuCmd {
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h;      /* luma TU size */
+    uint8_t cbf_mask;            /* 0x10 luma, 0x08 joint CbCr, 0x02 Cb, 0x01 Cr */
+    uint8_t tr_skip_mask;        /* same bits */
+    uint8_t cu_mts_flag, cu_mts_idx;
+    uint8_t flags;               /* OVO_TU_* */
+    uint8_t lfnst_idx;           /* TUInfo.lfnst_idx: 0/1 selects the kernel of the set */
+    uint8_t qp[4];               /* dequant_luma / cb / cr / joint_cb_cr .qp (ctudec.h:829-833) */
+    uint8_t qp_ts[4];            /* the *_skip variants */
+    uint16_t last_pos[3];
+    int16_t chroma_scale;        /* lmcs_chroma_scale (2048 = neutral) */
+    uint8_t lfnst_mode_l;        /* intra mode LFNST derives its set from: ctudec->intra_mode, PLANAR for MIP   */
+    uint8_t lfnst_mode_c;        /* chroma: resolved mode (DM / CCLM replaced by the collocated luma mode)      */
+    uint16_t pad;
+    uint32_t coeff_off[3];       /* int16 offsets into the coefficient arena */
+    uint32_t pad2;
+    uint64_t sig_sb_map[3];
+} OVOTuCmd;
+
+void ovo_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                          const OVOTuCmd *cmds, int nb_cmds, const int16_t *arena,
+                          int dep_quant, int sh_ts_disabled, int ict_type);
+
 #ifdef __cplusplus
 }
 #endif

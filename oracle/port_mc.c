@@ -10,6 +10,7 @@
  */
 #include "oracle.h"
 #include <string.h>
+#include <stdlib.h>
 
 static inline int clipi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
@@ -118,7 +119,7 @@ static void pu_pred14(int16_t *buf, const OVOMcRefs *refs, int list, int ref_idx
 void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut)
 {
-    static int16_t p0[128 * 128], p1[128 * 128];
+    int16_t *p0 = malloc(2 * 128 * 128 * sizeof(int16_t)), *p1 = p0 + 128 * 128;   /* per call: thread-safe */
     int maxv = (1 << bitdepth) - 1;
     for (int i = 0; i < nb_cmds; i++) {
         const OVOMcCmd *c = &cmds[i];
@@ -164,6 +165,7 @@ void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, 
                     }
         }
     }
+    free(p0);
 }
 
 /* ---------------------------------------------------------------------------------------------------

@@ -268,8 +268,11 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
 {
     OVCTUDec *c;
     OVPartInfo part;
-    static OVPicture pics[2][16];
-    static OVFrame frames[2][16];
+    /* heap, not static: bench.py drives one picture per host thread */
+    OVPicture (*pics)[16] = calloc(2, sizeof(*pics));
+    OVFrame (*frames)[16] = calloc(2, sizeof(*frames));
+    enum { SCR_STRIDE = 384 };
+    uint16_t (*scr)[(128 + 8) * SCR_STRIDE] = calloc(3, sizeof(*scr));
     ctudec_init(&c);
     memset(&part, 0, sizeof(part));
     part.log2_ctu_s = log2_ctu_s;
@@ -286,8 +289,6 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
         c->lmcs_info.lmcs_enabled_flag = 1;
     }
     struct InterDRVCtx *ic = &c->drv_ctx.inter_ctx;
-    memset(pics, 0, sizeof(pics));
-    memset(frames, 0, sizeof(frames));
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
             if (!refs->plane[l][i][0]) continue;
@@ -314,8 +315,6 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
         int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
         /* The reference writes into its CTU-local buffer (stride 324, rcn_ctu.c:558) and its SIMD kernels may
          * store a few samples past a narrow block; give it the same kind of padded scratch and copy the PU out. */
-        enum { SCR_STRIDE = 384 };
-        static uint16_t scr[3][(128 + 8) * SCR_STRIDE];
         struct OVBuffInfo b;
         memset(&b, 0, sizeof(b));
         b.stride = SCR_STRIDE;
@@ -341,4 +340,5 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
     }
     if (lmcs) free(c->lmcs_info.luts);
     free(c);
+    free(pics); free(frames); free(scr);
 }

@@ -5,6 +5,21 @@
 #include "../../openvvc_b200/csrc/alf_host.h"
 #include "../../openvvc_b200/csrc/sao_kernels.h"
 #include "../../openvvc_b200/csrc/mc_host.h"
+#include "../../openvvc_b200/csrc/tr_host.h"
+
+template <int GROUP>
+static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,
+                          const TbItemDev *items, int n, const int16_t *arena, const OVGPUTuSlice *sl)
+{
+    typedef TrK<GROUP> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
+    a.bitdepth = bitdepth;
+    a.cmds = (const TuCmdDev *)cmds; a.items = items; a.nb_items = n; a.arena = arena;
+    a.dep_quant = sl->dep_quant; a.sh_ts_disabled = sl->sh_ts_disabled; a.ict_type = sl->ict_type;
+    ovd_emulate<K>(a, ovd_dim3((n + K::GROUPS - 1) / K::GROUPS, 1, 1), K::SMEM_BYTES);
+}
 
 extern "C" {
 
@@ -107,6 +122,20 @@ int emu_lmcs_reshape(uint16_t *plane, int stride, int w, int h, int bitdepth, co
     LmcsReshapeK::Args a = { plane, stride, w, h, bitdepth, lut };
     ovd_emulate<LmcsReshapeK>(a, ovd_dim3((w + 255) / 256, (h + 7) / 8, 1), 0);
     return 0;
+}
+
+int emu_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds, int nb_cmds,
+                         const int16_t *arena, size_t nb_coeffs, int dep_quant, int sh_ts_disabled, int ict_type)
+{
+    for (int i = 0; i < nb_cmds; i++) if (tu_check_cmd(&cmds[i], nb_coeffs)) return -(i + 1);
+    int ns, nl;
+    tu_build_items(NULL, NULL, &ns, &nl, cmds, nb_cmds);
+    std::vector<TbItemDev> items(ns + nl + 1);
+    tu_build_items(items.data(), items.data() + ns, &ns, &nl, cmds, nb_cmds);
+    OVGPUTuSlice sl = { (uint8_t)dep_quant, (uint8_t)sh_ts_disabled, (uint8_t)ict_type, 0 };
+    if (ns) emu_tr_launch<32>(dst, dst_stride, bitdepth, cmds, items.data(), ns, arena, &sl);
+    if (nl) emu_tr_launch<128>(dst, dst_stride, bitdepth, cmds, items.data() + ns, nl, arena, &sl);
+    return ns + nl;
 }
 
 }

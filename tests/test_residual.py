@@ -1,0 +1,124 @@
+"""Residual path (dequantisation, LFNST, DCT-2/DST-7/DCT-8, transform skip, residual add / joint CbCr / LMCS chroma
+scale): oracle port vs golden / compiled reference (CPU), kernel-source emulation vs oracle (CPU), and the sm_100a
+kernels through the C ABI vs oracle / golden (GPU).
+
+Arithmetic of record = the reference's scalar C templates.  Its SSE/AVX2 variants saturate asymmetrically where the
+C code clips symmetrically (dequantisation: -32768 vs -32767; LFNST: +32767 vs a wrapped +32768), so SIMD is only
+compared on `legal` coefficient levels -- the only ones a conforming stream can carry."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import helpers_tr
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tr_golden.json")))
+IDS = lambda c: "%dx%d_ict%d_tsd%d_dq%d" % (c["w"], c["h"], c["ict_type"], c["sh_ts_disabled"], c["dep_quant"])
+KW = lambda c: dict(dep_quant=c["dep_quant"], sh_ts_disabled=c["sh_ts_disabled"], ict_type=c["ict_type"])
+
+
+@pytest.fixture(scope="module")
+def pt(oracle):
+    from oracle import pyoracle_tr
+    return pyoracle_tr
+
+
+def _case(c):
+    planes, cmds, arena = helpers_tr.tr_case(c["w"], c["h"], c["seed"], c["log2_ctu"], c["ict_type"], c["sh_ts_disabled"],
+                                             c["dep_quant"], c["legal"])
+    assert helpers.md5(cmds, arena, *planes) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return planes, cmds, arena
+
+
+@pytest.mark.parametrize("c", GOLDEN, ids=IDS)
+def test_port_matches_golden(pt, c):
+    planes, cmds, arena = _case(c)
+    pt.residual_picture(planes, cmds, arena, c["log2_ctu"], impl="port", **KW(c))
+    assert [helpers.md5(p) for p in planes] == c["md5"]
+
+
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq", [(416, 240, 7, 0, 0, 1), (416, 240, 7, 3, 1, 0), (832, 480, 7, 1, 0, 1),
+                                                  (264, 136, 6, 2, 1, 1), (72, 40, 5, 1, 0, 0)])
+def test_port_vs_compiled_reference(oracle, pt, w, h, log2, ict, tsd, dq):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 5 * w + h, log2, ict, tsd, dq, legal=False, p_intra=0.35)
+    a = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    b = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="ref", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict, simd=0)
+    helpers.assert_planes_equal(a, b, "residual port vs reference (scalar C)")
+    assert sum(int((x != y).sum()) for x, y in zip(a, planes)) > 1000
+
+
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq", [(416, 240, 7, 1, 0, 1), (832, 480, 7, 2, 0, 1), (256, 128, 6, 0, 1, 0)])
+def test_port_vs_reference_simd_on_legal_levels(oracle, pt, w, h, log2, ict, tsd, dq):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 3 * w + h, log2, ict, tsd, dq, legal=True, p_intra=0.35)
+    a = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    b = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="ref", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict, simd=1)
+    helpers.assert_planes_equal(a, b, "residual port vs reference (SSE/AVX2 table)")
+
+
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq,legal", [(416, 240, 7, 0, 0, 1, False), (416, 240, 7, 3, 1, 0, False),
+                                                        (256, 128, 6, 1, 0, 1, True), (136, 72, 5, 2, 1, 1, False),
+                                                        (832, 480, 7, 1, 0, 0, False)])
+def test_emulated_kernel_matches_oracle(pt, emu, w, h, log2, ict, tsd, dq, legal):
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 7 * w + h, log2, ict, tsd, dq, legal, p_intra=0.35)
+    want = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    got = helpers_tr.emu_residual(emu, planes, cmds, arena, dq, tsd, ict)
+    helpers.assert_planes_equal(got, want, "emulated residual kernels vs oracle")
+
+
+def test_zero_residual_is_identity(pt, emu):
+    planes, cmds, arena = helpers_tr.tr_case(256, 128, 9, 7)
+    arena[:] = 0
+    got = helpers_tr.emu_residual(emu, planes, cmds, arena)
+    helpers.assert_planes_equal(got, planes, "all-zero coefficients")
+
+
+def test_emu_rejects_out_of_range_offsets(emu):
+    planes, cmds, arena = helpers_tr.tr_case(256, 128, 10, 7)
+    cmds = cmds.copy()
+    i = int(np.nonzero(cmds["cbf_mask"] & 0x10)[0][0])
+    cmds["coeff_off"][i][2] = len(arena)
+    with pytest.raises(AssertionError):
+        helpers_tr.emu_residual(emu, planes, cmds, arena)
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", GOLDEN, ids=IDS)
+def test_gpu_matches_golden(gpu_ctx, c):
+    planes, cmds, arena = _case(c)
+    out = helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena, **KW(c))
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq", [(416, 240, 7, 1, 0, 1), (264, 136, 6, 3, 1, 0), (1920, 1080, 7, 1, 0, 1)])
+def test_gpu_matches_oracle(pt, gpu_ctx, w, h, log2, ict, tsd, dq):
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 9 * w + h, log2, ict, tsd, dq, p_intra=0.35)
+    want = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    helpers.assert_planes_equal(helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena, dq, tsd, ict), want, "CUDA residual vs oracle")
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_4k_vs_reference(oracle, pt, gpu_ctx):
+    """BASELINE.json config 2 geometry (3840x2160): CUDA vs the compiled reference (scalar C) when present."""
+    w, h = 3840, 2160
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 78, 7, 1, 0, 1, legal=True, p_intra=0.1, min_log2=3)
+    want = pt.residual_picture([p.copy() for p in planes], cmds, arena, 7, impl="ref" if oracle.ref_available() else "port",
+                               dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=0)
+    helpers.assert_planes_equal(helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena, 1, 0, 1), want, "CUDA residual vs reference at 4K")
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_malformed_commands(gpu_ctx):
+    from openvvc_b200 import api
+    planes, cmds, arena = helpers_tr.tr_case(256, 128, 10, 7)
+    cmds = cmds.copy()
+    cmds["log2_w"][0] = 9
+    with pytest.raises(api.OVGPUError):
+        helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena)
