@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["mc(uni/bi/bcw)+lmcs_fwd", "sao", "alf+ccalf"]   # widened as §8 rows land
+STAGES_IMPLEMENTED = ["mc(uni/bi/bcw)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
 def peaks():
@@ -74,7 +74,7 @@ class ClockSampler(threading.Thread):
 def make_workload(w, h, n_pics, seed0=5000):
     """Shared reference pictures + n_pics synthetic inter pictures: PU list, SAO and ALF decoder state
     (SURVEY.md §8(d) generators)."""
-    from openvvc_b200 import api, synth
+    from openvvc_b200 import api, synth, synth_tu, synth_dbf
     refs = [[synth.planes(w, h, seed0 + 900 + i) for i in range(2)], [synth.planes(w, h, seed0 + 950 + i) for i in range(2)]]
     pocs = [[8, 16], [16, 24]]
     lmcs = api.lmcs_build_luts(synth.lmcs_data(seed0))
@@ -85,8 +85,29 @@ def make_workload(w, h, n_pics, seed0=5000):
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
         cmds = synth.mc_commands(w, h, seed0 + 300 + i, 7).astype(api.MC_CMD)
-        pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds))
+        tus, coeffs = synth_tu.tu_commands(w, h, seed0 + 400 + i, 7, ict_type=1, legal=True, p_intra=0.1, min_log2=3, p_cbf=0.4)
+        blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
+        dbf = synth_dbf.dbf_maps(w, h, blks, 7)
+        pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, tus=tus, coeffs=coeffs,
+                         dbf_blks=blks, dbf=dbf))
     return dict(refs=refs, pocs=pocs, lmcs=lmcs, pics=pics)
+
+
+def residual_bytes(tus):
+    """Algorithmic bytes of the residual stage: coded coefficient sub-blocks (32 B each) + read-modify-write of the
+    samples of every coded transform block."""
+    area = (1 << tus["log2_w"].astype(np.int64)) * (1 << tus["log2_h"].astype(np.int64))
+    cbf = tus["cbf_mask"]
+    luma = (cbf & 0x10) != 0
+    joint = (cbf & 0x08) != 0
+    n_c = np.where(joint, 2, ((cbf & 2) != 0).astype(np.int64) + ((cbf & 1) != 0))        # chroma planes touched
+    n_ctb = np.where(joint, 1, n_c)                                                       # chroma blocks coded
+    rmw = 4 * (area * luma + (area // 4) * n_c)
+    sb = np.zeros(len(tus), np.int64)
+    for k, used in ((2, luma), (0, n_ctb >= 1), (1, (n_ctb == 2))):
+        bits = np.array([bin(int(v)).count("1") for v in tus["sig_sb_map"][:, k]], np.int64)
+        sb += np.where(used, np.maximum(bits, 1), 0)
+    return float(rmw.sum() + 32 * sb.sum())
 
 
 def mc_dirs_per_sample(cmds):
@@ -101,6 +122,7 @@ def reference_step(po, wl, threads):
     """The reference's own CPU implementation (oracle/_ref: rcn_mcp_b, rcn_sao_filter_line, rcn_alf_filter_line
     through the SSE4.1/AVX2 function table) of the same stages, one picture per host thread (the reference's
     frame parallelism, ovdec.h:47).  Falls back to the C port only if oracle/_ref was not built."""
+    from oracle import pyoracle_tr as pt, pyoracle_df as pdf
     impl = "ref" if po.ref_available() else "port"
     h, w = wl["refs"][0][0][0].shape
     luts = po.LmcsLuts()
@@ -111,6 +133,12 @@ def reference_step(po, wl, threads):
         C.memmove(C.byref(t), C.byref(p["tab"]), C.sizeof(t))
         rec = [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
         po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts)
+        pt.residual_picture(rec, p["tus"], p["coeffs"], 7, impl=impl, dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=1)
+        po.port().ovo_lmcs_reshape_plane(rec[0].ctypes.data_as(po.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(po.u16p), 10)
+        if impl == "ref":
+            pdf.dbf_picture_ref(rec, p["dbf_blks"], 7, simd=1)
+        else:
+            pdf.dbf_picture_port(rec, p["dbf"])
         s = po.sao_picture(rec, p["sao"].astype(po.SaoCtu), 7, impl=impl)
         po.alf_picture(s, t, p["ctu"], 7, impl=impl)
 
@@ -151,7 +179,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(residual/intra/DBF stages not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(intra prediction and BDOF/DMVR/PROF not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "parallelism": "frame-parallel, one picture stream per GPU",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
@@ -206,15 +234,21 @@ def main():
     for p in pics:
         d = dict(rec=ctx.picture(w, h), mid=ctx.picture(w, h), dst=ctx.picture(w, h),
                  alf=api.AlfParams(ctx, w, h, 7), sao=api.SaoParams(ctx, w, h, 7),
-                 mc=api.McBatch(ctx, len(p["cmds"]), api.mc_nb_items(p["cmds"])))
+                 mc=api.McBatch(ctx, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
+                 tu=api.TuBatch(ctx, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(ctx, w, h, 7))
         d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
         d["sao"].upload(p["sao"])
         d["mc"].upload(p["cmds"])
+        d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
+        d["dbf"].upload(p["dbf"])
         dev.append(d)
     ctx.sync()
 
     def run_stages(d):
         d["mc"].run(d["rec"], ref_pics, wl["pocs"], lmcs)
+        d["tu"].run(d["rec"])
+        lmcs.reshape(d["rec"], forward=False)
+        d["dbf"].run(d["rec"])
         d["sao"].run(d["mid"], d["rec"])
         d["alf"].run(d["dst"], d["mid"])
 
@@ -248,7 +282,7 @@ def main():
     launches = ctx.launch_count() - n0
 
     # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
-    stage_names = ("mc", "sao", "alf_luma", "alf_chroma")
+    stage_names = ("mc", "residual", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
     ctx.profile(True); ctx.profile_reset()
     for _ in range(max(2, min(args.steps, 5))):
         step_device()
@@ -264,6 +298,8 @@ def main():
         for i, d in enumerate(dev):
             p = pics[i]
             d["mc"].upload(p["cmds"])
+            d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
+            d["dbf"].upload(p["dbf"])
             d["sao"].upload(p["sao"])
             d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
             run_stages(d)
@@ -293,7 +329,8 @@ def main():
         dirs = float(np.mean([mc_dirs_per_sample(p["cmds"]) for p in pics]))
         L, Cc = w * h * 2, w * h     # luma plane bytes, both chroma planes bytes
         # algorithmic bytes per launch: MC (dirs+1)*P, SAO 2P, ALF luma 2L, ALF chroma 2C
-        alg = {"mc": (dirs + 1) * pbytes, "sao": 2 * pbytes, "alf_luma": 2 * L, "alf_chroma": 2 * Cc}
+        alg = {"mc": (dirs + 1) * pbytes, "residual": float(np.mean([residual_bytes(p["tus"]) for p in pics])),
+               "lmcs": 2 * L, "dbf_v": 2 * pbytes, "dbf_h": 2 * pbytes, "sao": 2 * pbytes, "alf_luma": 2 * L, "alf_chroma": 2 * Cc}
         stages = {}
         for s in stage_names:
             t_ms, n = prof[s]
@@ -302,7 +339,7 @@ def main():
                 stages[s] = {"avg_launch_ms": avg, "algorithmic_bytes": alg[s], "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9,
                              "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
-        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
+        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",

@@ -241,6 +241,40 @@ int  ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmd
 /* pic += residual of every TU (pic holds the prediction). Asynchronous. */
 int  ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b);
 
+/* ---- Deblocking filter  (replaces df.rcn_dbf_ctu / df.rcn_dbf_truncated_ctu, rcn_df.c:2170-2228, for all CTUs) ---- */
+/* Picture-level form of what struct DBFInfo (ctudec.h:130-170) holds per CTU at rcn_dbf_ctu time, i.e. after the CPU
+ * side has run dbf_ctu_preproc_{h,v} (MV / reference mismatch -> bs1, rcn_df.c:1822-1874).  With n_u = CTU size / 4,
+ * w_u = width / 4, h_u = height / 4 (4x4 luma units):
+ *   ver[m][cy * (w_u + 1) + X]  bit j  <=>  vertical edge at unit column X (0..w_u), unit row cy * n_u + j
+ *   hor[m][cx * (h_u + 1) + Y]  bit j  <=>  horizontal edge at unit row Y (0..h_u), unit column cx * n_u + j
+ *   qp[c][Y * w_u + X]                      QP of the unit (qp_map_y / qp_map_cb / qp_map_cr)
+ * The recorder copies, for CTU (cx, cy) and local index i: ver[m][..cx * n_u + i] = <map>.ver[i] and
+ * hor[m][..cy * n_u + i] = <map>.hor[i] >> 2; map m is one of: */
+enum OVGPUDbfMap {
+    OVGPU_DBF_EDGE_TU = 0,   /* ctb_bound_ver / ctb_bound_hor [8 + i]        transform / coding block edges      */
+    OVGPU_DBF_EDGE_SB,       /* aff_edg_ver / aff_edg_hor [8 + i]            affine 8x8 sub-block edges          */
+    OVGPU_DBF_BS1,           /* bs1_map                                      coded residual or MV/ref mismatch   */
+    OVGPU_DBF_BS2,           /* bs2_map                                      intra / CIIP                        */
+    OVGPU_DBF_AFFINE,        /* affine_map [1 + i]: the unit at index i belongs to an affine CU                  */
+    OVGPU_DBF_EDGE_C,        /* ctb_bound_ver_c / ctb_bound_hor_c [8 + i]                                         */
+    OVGPU_DBF_BS1_CB, OVGPU_DBF_BS1_CR, OVGPU_DBF_BS2_C,
+    OVGPU_DBF_NB_MAPS
+};
+typedef struct OVGPUDbfMaps {
+    int32_t width, height, log2_ctu_s;
+    int16_t beta_offset, tc_offset;       /* DBFInfo.beta_offset / tc_offset */
+    const uint32_t *ver[OVGPU_DBF_NB_MAPS];
+    const uint32_t *hor[OVGPU_DBF_NB_MAPS];
+    const uint8_t *qp[3];
+} OVGPUDbfMaps;
+
+typedef struct OVGPUDbfParams OVGPUDbfParams;   /* pinned staging + device copy of one picture's deblocking maps */
+int  ovgpu_dbf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUDbfParams **p);
+void ovgpu_dbf_params_destroy(OVGPUDbfParams *p);
+int  ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps *maps);
+/* deblocks pic in place: all vertical edges, then all horizontal edges (luma and chroma). Asynchronous. */
+int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p);
+
 #ifdef __cplusplus
 }
 #endif

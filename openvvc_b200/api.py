@@ -351,6 +351,47 @@ class TuBatch:
             self.p = vp()
 
 
+class DbfMaps(C.Structure):
+    """OVGPUDbfMaps: picture-level deblocking maps (layout in include/ovvc_b200.h)."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("log2_ctu_s", C.c_int32),
+                ("beta_offset", C.c_int16), ("tc_offset", C.c_int16),
+                ("ver", C.POINTER(C.c_uint32) * 9), ("hor", C.POINTER(C.c_uint32) * 9), ("qp", C.POINTER(C.c_uint8) * 3)]
+
+    @classmethod
+    def from_dict(cls, m):
+        """m: dict from synth_dbf.dbf_maps -- ver [9][nch][w_u+1] u32, hor [9][ncw][h_u+1] u32, qp [3][h_u][w_u] u8"""
+        s = cls()
+        s.width, s.height, s.log2_ctu_s = m["width"], m["height"], m["log2_ctu"]
+        s.beta_offset, s.tc_offset = m["beta_offset"], m["tc_offset"]
+        for k in range(9):
+            s.ver[k] = m["ver"][k].ctypes.data_as(C.POINTER(C.c_uint32))
+            s.hor[k] = m["hor"][k].ctypes.data_as(C.POINTER(C.c_uint32))
+        for k in range(3):
+            s.qp[k] = m["qp"][k].ctypes.data_as(C.POINTER(C.c_uint8))
+        s._keep = m
+        return s
+
+
+class DbfParams:
+    def __init__(self, ctx, w, h, log2_ctu=7):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_dbf_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "dbf_params_create")
+
+    def upload(self, maps):
+        st = DbfMaps.from_dict(maps) if isinstance(maps, dict) else maps
+        self._keep = st
+        _check(self.ctx.h, lib().ovgpu_dbf_params_upload(self.ctx.h, self.p, C.byref(st)), "dbf_params_upload")
+
+    def run(self, pic):
+        _check(self.ctx.h, lib().ovgpu_dbf_picture(self.ctx.h, pic.p, self.p), "dbf_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_dbf_params_destroy(self.p)
+            self.p = vp()
+
+
 def mc_nb_items(cmds):
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))
     return int((((w + 15) >> 4) * ((h + 15) >> 4)).sum())

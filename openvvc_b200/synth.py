@@ -31,7 +31,7 @@ def _smooth(rng, shape, scale):
 
 
 def planes(w, h, seed, kind="natural", bitdepth=10):
-    """3 planar 4:2:0 uint16 planes. kind 'noise' = uniform; 'natural' = smooth field + sigma-4 noise
+    """3 planar 4:2:0 uint16 planes. kind 'noise' = uniform; 'blocky' = smooth + block steps; 'natural' = smooth field + sigma-4 noise
     (keeps DBF/ALF decisions non-degenerate)."""
     rng = np.random.default_rng(seed)
     maxv = (1 << bitdepth) - 1
@@ -39,6 +39,13 @@ def planes(w, h, seed, kind="natural", bitdepth=10):
     for (ph, pw) in plane_dims(w, h):
         if kind == "noise":
             p = rng.integers(0, maxv + 1, size=(ph, pw), dtype=np.uint16)
+        elif kind == "blocky":
+            # very smooth field + a DC step per 8x8 block and sigma-0.7 noise: what a coarsely quantised picture looks
+            # like before deblocking (reaches the strong and long deblocking filters)
+            f = _smooth(rng, (ph, pw), 48) * (maxv / 1023.0)
+            steps = rng.integers(-6, 7, size=((ph + 7) // 8, (pw + 7) // 8)).astype(np.float64)
+            f = f + np.kron(steps, np.ones((8, 8)))[:ph, :pw] + rng.normal(0, 0.7, size=(ph, pw))
+            p = np.clip(np.rint(f), 0, maxv).astype(np.uint16)
         else:
             f = _smooth(rng, (ph, pw), 16) * (maxv / 1023.0)
             f = f + rng.normal(0, 4, size=(ph, pw))

@@ -169,6 +169,32 @@ void ovo_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int p
                           const OVOTuCmd *cmds, int nb_cmds, const int16_t *arena,
                           int dep_quant, int sh_ts_disabled, int ict_type);
 
+/* ---- Deblocking filter ---------------------------------------------------------------------------------- */
+/* One block of the synthetic decoder state (openvvc_b200/synth_dbf.py: DBF_BLK) */
+typedef struct OVODbfBlk {
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h;
+    uint8_t flags;               /* 1 intra, 2 cbf luma, 4 cbf cb, 8 cbf cr, 16 MV/ref mismatch on its edges, 32 affine */
+    uint8_t qp_y, qp_cb, qp_cr;
+    uint16_t pad;
+} OVODbfBlk;
+
+/* Picture-level maps; identical to OVGPUDbfMaps (include/ovvc_b200.h). n_u = CTU size / 4, w_u = width / 4,
+ * h_u = height / 4.  ver[m][cy * (w_u + 1) + X]: bit j <=> unit row cy * n_u + j of vertical edge column X;
+ * hor[m][cx * (h_u + 1) + Y]: bit j <=> unit column cx * n_u + j of horizontal edge row Y; qp[c][Y * w_u + X]. */
+enum { OVO_DBF_EDGE_TU = 0, OVO_DBF_EDGE_SB, OVO_DBF_BS1, OVO_DBF_BS2, OVO_DBF_AFFINE, OVO_DBF_EDGE_C,
+       OVO_DBF_BS1_CB, OVO_DBF_BS1_CR, OVO_DBF_BS2_C, OVO_DBF_NB_MAPS };
+typedef struct OVODbfMaps {
+    int32_t width, height, log2_ctu_s;
+    int16_t beta_offset, tc_offset;
+    uint32_t *ver[OVO_DBF_NB_MAPS];
+    uint32_t *hor[OVO_DBF_NB_MAPS];
+    uint8_t *qp[3];
+} OVODbfMaps;
+
+/* in place on the picture: all vertical edges, then all horizontal edges, luma and chroma (rcn_df.c) */
+void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth, const OVODbfMaps *maps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include "../../openvvc_b200/csrc/sao_kernels.h"
 #include "../../openvvc_b200/csrc/mc_host.h"
 #include "../../openvvc_b200/csrc/tr_host.h"
+#include "../../openvvc_b200/csrc/dbf_kernels.h"
 
 template <int GROUP>
 static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,
@@ -136,6 +137,24 @@ int emu_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int bi
     if (ns) emu_tr_launch<32>(dst, dst_stride, bitdepth, cmds, items.data(), ns, arena, &sl);
     if (nl) emu_tr_launch<128>(dst, dst_stride, bitdepth, cmds, items.data() + ns, nl, arena, &sl);
     return ns + nl;
+}
+
+int emu_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth, const OVGPUDbfMaps *maps)
+{
+    DbfK<0>::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { a.plane[c] = planes[c]; a.pitch[c] = stride[c]; }
+    a.bitdepth = bitdepth;
+    for (int k = 0; k < DBF_NB_MAPS; k++) { a.m.ver[k] = maps->ver[k]; a.m.hor[k] = maps->hor[k]; }
+    for (int c = 0; c < 3; c++) a.m.qp[c] = maps->qp[c];
+    a.m.n_u = (1 << maps->log2_ctu_s) >> 2; a.m.w_u = maps->width >> 2; a.m.h_u = maps->height >> 2;
+    a.m.beta_offset = maps->beta_offset; a.m.tc_offset = maps->tc_offset;
+    ovd_dim3 grid((a.m.w_u + 31) / 32, (a.m.h_u + 7) / 8, 3);
+    ovd_emulate<DbfK<0> >(a, grid, 0);
+    DbfK<1>::Args b;
+    memcpy(&b, &a, sizeof(b));
+    ovd_emulate<DbfK<1> >(b, grid, 0);
+    return 0;
 }
 
 }
