@@ -238,6 +238,12 @@ int  ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPU
 void ovgpu_tu_batch_destroy(OVGPUTuBatch *b);
 int  ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds, int nb_cmds,
                            const int16_t *coeffs, size_t nb_coeffs, const OVGPUTuSlice *slice);
+/* Zero-copy staging (what the north-star recorder uses): _staging returns the batch's PINNED command / coefficient
+ * buffers (after the previous H2D copy out of them has completed) for the parser to write into directly; _commit
+ * validates the commands, builds the work lists and issues the asynchronous H2D copies.  upload = staging + memcpy +
+ * commit. */
+int  ovgpu_tu_batch_staging(OVGPUCtx *ctx, OVGPUTuBatch *b, OVGPUTuCmd **cmds, int16_t **coeffs);
+int  ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb_coeffs, const OVGPUTuSlice *slice);
 /* pic += residual of every TU (pic holds the prediction). Asynchronous. */
 int  ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b);
 
@@ -272,6 +278,10 @@ typedef struct OVGPUDbfParams OVGPUDbfParams;   /* pinned staging + device copy 
 int  ovgpu_dbf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUDbfParams **p);
 void ovgpu_dbf_params_destroy(OVGPUDbfParams *p);
 int  ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps *maps);
+/* zero-copy variant: _staging fills `maps` with pointers into the object's pinned buffer (writable by the caller),
+ * _commit issues the asynchronous H2D copy */
+int  ovgpu_dbf_params_staging(OVGPUCtx *ctx, OVGPUDbfParams *p, OVGPUDbfMaps *maps);
+int  ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, int tc_offset);
 /* deblocks pic in place: all vertical edges, then all horizontal edges (luma and chroma). Asynchronous. */
 int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p);
 

@@ -213,16 +213,16 @@ class AlfParams:
         _check(ctx.h, lib().ovgpu_alf_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "alf_params_create")
         self._keep = None
 
-    def upload(self, tables, ctu, cc_idx, cc_en=(1, 1)):
+    def upload(self, tables, ctu, cc_idx, cc_en=(1, 1), ctx=None):
         ctu = np.ascontiguousarray(ctu, dtype=ALF_CTU)
         keep = [np.ascontiguousarray(c, dtype=np.uint8) for c in cc_idx]
         cc = (vp * 2)(keep[0].ctypes.data, keep[1].ctypes.data)
         self._keep = (tables, ctu, keep)
-        _check(self.ctx.h, lib().ovgpu_alf_params_upload(self.ctx.h, self.p, C.byref(tables), vp(ctu.ctypes.data), cc,
+        _check((ctx or self.ctx).h, lib().ovgpu_alf_params_upload((ctx or self.ctx).h, self.p, C.byref(tables), vp(ctu.ctypes.data), cc,
                                                          int(cc_en[0]), int(cc_en[1])), "alf_params_upload")
 
-    def run(self, dst, src):
-        _check(self.ctx.h, lib().ovgpu_alf_picture(self.ctx.h, dst.p, src.p, self.p), "alf_picture")
+    def run(self, dst, src, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_alf_picture((ctx or self.ctx).h, dst.p, src.p, self.p), "alf_picture")
 
     def destroy(self):
         if self.p:
@@ -280,12 +280,12 @@ class Lmcs:
         if luts is not None:
             self.upload(luts)
 
-    def upload(self, luts):
+    def upload(self, luts, ctx=None):
         self._keep = luts
-        _check(self.ctx.h, lib().ovgpu_lmcs_upload(self.ctx.h, self.p, C.byref(luts)), "lmcs_upload")
+        _check((ctx or self.ctx).h, lib().ovgpu_lmcs_upload((ctx or self.ctx).h, self.p, C.byref(luts)), "lmcs_upload")
 
-    def reshape(self, pic, forward=False):
-        _check(self.ctx.h, lib().ovgpu_lmcs_reshape_picture(self.ctx.h, pic.p, self.p, int(forward)), "lmcs_reshape_picture")
+    def reshape(self, pic, forward=False, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_lmcs_reshape_picture((ctx or self.ctx).h, pic.p, self.p, int(forward)), "lmcs_reshape_picture")
 
     def destroy(self):
         if self.p:
@@ -301,19 +301,19 @@ class McBatch:
         self.p = vp()
         _check(ctx.h, lib().ovgpu_mc_batch_create(ctx.h, int(max_cmds), int(max_items), C.byref(self.p)), "mc_batch_create")
 
-    def upload(self, cmds):
+    def upload(self, cmds, ctx=None):
         cmds = np.ascontiguousarray(cmds, dtype=MC_CMD)
         self._keep = cmds
-        _check(self.ctx.h, lib().ovgpu_mc_batch_upload(self.ctx.h, self.p, vp(cmds.ctypes.data), len(cmds)), "mc_batch_upload")
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds)), "mc_batch_upload")
 
-    def run(self, dst, ref_lists, pocs, lmcs=None):
+    def run(self, dst, ref_lists, pocs, lmcs=None, ctx=None):
         """ref_lists: [rpl0, rpl1] lists of Picture; pocs likewise."""
         r = McRefs()
         for l in range(2):
             for i, pic in enumerate(ref_lists[l]):
                 r.rpl[l][i] = pic.p
                 r.poc[l][i] = int(pocs[l][i])
-        _check(self.ctx.h, lib().ovgpu_mc_picture(self.ctx.h, dst.p, C.byref(r), self.p, lmcs.p if lmcs else None), "mc_picture")
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_picture((ctx or self.ctx).h, dst.p, C.byref(r), self.p, lmcs.p if lmcs else None), "mc_picture")
 
     def destroy(self):
         if self.p:
@@ -331,19 +331,33 @@ class TuBatch:
     def __init__(self, ctx, max_cmds, max_coeffs):
         self.ctx = ctx
         self.p = vp()
+        self.max_cmds, self.max_coeffs = int(max_cmds), int(max_coeffs)
         _check(ctx.h, lib().ovgpu_tu_batch_create(ctx.h, int(max_cmds), C.c_size_t(int(max_coeffs)), C.byref(self.p)), "tu_batch_create")
 
-    def upload(self, cmds, coeffs, dep_quant=1, sh_ts_disabled=0, ict_type=0):
+    def staging(self, ctx=None):
+        """numpy views of the batch's PINNED command / coefficient buffers (ovgpu_tu_batch_staging)."""
+        from .synth_tu import TU_CMD
+        pc, pk = vp(), vp()
+        _check((ctx or self.ctx).h, lib().ovgpu_tu_batch_staging((ctx or self.ctx).h, self.p, C.byref(pc), C.byref(pk)), "tu_batch_staging")
+        cmds = np.frombuffer((C.c_uint8 * (TU_CMD.itemsize * self.max_cmds)).from_address(pc.value), dtype=TU_CMD)
+        coeffs = np.frombuffer((C.c_int16 * self.max_coeffs).from_address(pk.value), dtype=np.int16)
+        return cmds, coeffs
+
+    def commit(self, nb_cmds, nb_coeffs, dep_quant=1, sh_ts_disabled=0, ict_type=0, ctx=None):
+        sl = TuSlice(int(dep_quant), int(sh_ts_disabled), int(ict_type), 0)
+        _check((ctx or self.ctx).h, lib().ovgpu_tu_batch_commit((ctx or self.ctx).h, self.p, int(nb_cmds), C.c_size_t(int(nb_coeffs)), C.byref(sl)), "tu_batch_commit")
+
+    def upload(self, cmds, coeffs, dep_quant=1, sh_ts_disabled=0, ict_type=0, ctx=None):
         from .synth_tu import TU_CMD
         cmds = np.ascontiguousarray(cmds, dtype=TU_CMD)
         coeffs = np.ascontiguousarray(coeffs, dtype=np.int16)
         sl = TuSlice(int(dep_quant), int(sh_ts_disabled), int(ict_type), 0)
         self._keep = (cmds, coeffs)
-        _check(self.ctx.h, lib().ovgpu_tu_batch_upload(self.ctx.h, self.p, vp(cmds.ctypes.data), len(cmds), vp(coeffs.ctypes.data),
+        _check((ctx or self.ctx).h, lib().ovgpu_tu_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds), vp(coeffs.ctypes.data),
                                                        C.c_size_t(len(coeffs)), C.byref(sl)), "tu_batch_upload")
 
-    def run(self, pic):
-        _check(self.ctx.h, lib().ovgpu_residual_picture(self.ctx.h, pic.p, self.p), "residual_picture")
+    def run(self, pic, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_residual_picture((ctx or self.ctx).h, pic.p, self.p), "residual_picture")
 
     def destroy(self):
         if self.p:
@@ -378,13 +392,30 @@ class DbfParams:
         self.p = vp()
         _check(ctx.h, lib().ovgpu_dbf_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "dbf_params_create")
 
-    def upload(self, maps):
+    def upload(self, maps, ctx=None):
         st = DbfMaps.from_dict(maps) if isinstance(maps, dict) else maps
         self._keep = st
-        _check(self.ctx.h, lib().ovgpu_dbf_params_upload(self.ctx.h, self.p, C.byref(st)), "dbf_params_upload")
+        _check((ctx or self.ctx).h, lib().ovgpu_dbf_params_upload((ctx or self.ctx).h, self.p, C.byref(st)), "dbf_params_upload")
 
-    def run(self, pic):
-        _check(self.ctx.h, lib().ovgpu_dbf_picture(self.ctx.h, pic.p, self.p), "dbf_picture")
+    def staging(self, ctx=None):
+        """numpy views (ver [9][nch][w_u+1], hor [9][ncw][h_u+1], qp [3][h_u][w_u]) of the PINNED map buffer."""
+        st = DbfMaps()
+        _check((ctx or self.ctx).h, lib().ovgpu_dbf_params_staging((ctx or self.ctx).h, self.p, C.byref(st)), "dbf_params_staging")
+        n_u = (1 << st.log2_ctu_s) >> 2
+        w_u, h_u = st.width >> 2, st.height >> 2
+        ncw, nch = -(-w_u // n_u), -(-h_u // n_u)
+        u32 = lambda ptr, n: np.frombuffer((C.c_uint32 * n).from_address(C.addressof(ptr.contents)), dtype=np.uint32)
+        ver = [u32(st.ver[k], nch * (w_u + 1)).reshape(nch, w_u + 1) for k in range(9)]
+        hor = [u32(st.hor[k], ncw * (h_u + 1)).reshape(ncw, h_u + 1) for k in range(9)]
+        qp = [np.frombuffer((C.c_uint8 * (w_u * h_u)).from_address(C.addressof(st.qp[k].contents)), dtype=np.uint8).reshape(h_u, w_u)
+              for k in range(3)]
+        return dict(ver=ver, hor=hor, qp=qp)
+
+    def commit(self, beta_offset=0, tc_offset=0, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_dbf_params_commit((ctx or self.ctx).h, self.p, int(beta_offset), int(tc_offset)), "dbf_params_commit")
+
+    def run(self, pic, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_dbf_picture((ctx or self.ctx).h, pic.p, self.p), "dbf_picture")
 
     def destroy(self):
         if self.p:
@@ -403,13 +434,13 @@ class SaoParams:
         self.p = vp()
         _check(ctx.h, lib().ovgpu_sao_params_create(ctx.h, w, h, log2_ctu, C.byref(self.p)), "sao_params_create")
 
-    def upload(self, sao_ctu):
+    def upload(self, sao_ctu, ctx=None):
         sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SAO_CTU)
         self._keep = sao_ctu
-        _check(self.ctx.h, lib().ovgpu_sao_params_upload(self.ctx.h, self.p, vp(sao_ctu.ctypes.data)), "sao_params_upload")
+        _check((ctx or self.ctx).h, lib().ovgpu_sao_params_upload((ctx or self.ctx).h, self.p, vp(sao_ctu.ctypes.data)), "sao_params_upload")
 
-    def run(self, dst, src):
-        _check(self.ctx.h, lib().ovgpu_sao_picture(self.ctx.h, dst.p, src.p, self.p), "sao_picture")
+    def run(self, dst, src, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_sao_picture((ctx or self.ctx).h, dst.p, src.p, self.p), "sao_picture")
 
     def destroy(self):
         if self.p:

@@ -18,6 +18,7 @@ struct OVGPUAlfParams {
     AlfChromaTab chroma;
     int wide, cc_enabled[2];
     int device;
+    StagingFence fence;
 };
 
 // ---- fixed filters and APS expansion (host; same tables as the VVC spec / rcn_alf.c:61-155) -------------
@@ -154,6 +155,7 @@ void ovgpu_alf_params_destroy(OVGPUAlfParams *p)
     if (p->h_ctu) cudaFreeHost(p->h_ctu);
     if (p->d_tab) cudaFree(p->d_tab);
     if (p->d_ctu) cudaFree(p->d_ctu);
+    fence_destroy(&p->fence);
     free(p);
 }
 
@@ -162,8 +164,8 @@ int ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTabl
                             int cc_cb_enabled, int cc_cr_enabled)
 {
     if (!ctx || !p || !tab || !ctu) return OVGPU_EINVAL;
-    // the pinned staging buffers are reused: wait for the previous upload to be consumed
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    // the pinned staging buffers are reused: wait for the previous H2D copy out of them
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
     p->wide = alf_pack_luma_tab(p->h_tab, tab);
     alf_pack_chroma_tab(&p->chroma, tab);
     alf_pack_ctu(p->h_ctu, p->nb_ctu, ctu, cc_idx);
@@ -173,6 +175,7 @@ int ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTabl
                                           cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_ctu, p->h_ctu, sizeof(AlfCtuDev) * p->nb_ctu,
                                           cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&p->fence, ctx->stream));
     return 0;
 }
 

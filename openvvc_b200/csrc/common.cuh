@@ -75,6 +75,29 @@ struct StageScope {
 
 #define OVGPU_CEIL_DIV(a, b) (((a) + (b) - 1) / (b))
 
+// Fence on a pinned staging buffer: the host may rewrite the buffer only after the last H2D copy out of it has
+// completed.  Waiting on this event (instead of the whole stream) lets the CPU stage picture N+1 while the GPU
+// still works on picture N.
+struct StagingFence {
+    cudaEvent_t ev;
+    int pending;
+};
+static inline cudaError_t fence_wait(StagingFence *f)
+{
+    cudaError_t e = cudaSuccess;
+    if (f->pending) { e = cudaEventSynchronize(f->ev); f->pending = 0; }
+    return e;
+}
+static inline cudaError_t fence_mark(StagingFence *f, cudaStream_t s)
+{
+    cudaError_t e = cudaSuccess;
+    if (!f->ev) e = cudaEventCreateWithFlags(&f->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(f->ev, s);
+    f->pending = e == cudaSuccess;
+    return e;
+}
+static inline void fence_destroy(StagingFence *f) { if (f->ev) cudaEventDestroy(f->ev); f->ev = NULL; f->pending = 0; }
+
 // ---- device helpers ------------------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }

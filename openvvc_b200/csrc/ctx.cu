@@ -197,8 +197,11 @@ int ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const d
     if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
     for (int c = 0; c < 3; c++) {
         int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
-        OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(data[c], linesize[c], pic->plane[c], pic->pitch[c],
-                                                (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
+        if (linesize[c] == (size_t)w * 2 && pic->pitch[c] == (size_t)w * 2)      // contiguous on both sides: one flat copy
+            OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(data[c], pic->plane[c], (size_t)w * 2 * h, cudaMemcpyDeviceToHost, ctx->stream));
+        else
+            OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(data[c], linesize[c], pic->plane[c], pic->pitch[c],
+                                                    (size_t)w * 2, h, cudaMemcpyDeviceToHost, ctx->stream));
     }
     return 0;
 }

@@ -10,6 +10,7 @@ struct OVGPUDbfParams {
     size_t ver_words, hor_words, qp_bytes, total;    // per map / per component
     unsigned char *h_buf, *d_buf;
     int beta_offset, tc_offset, loaded;
+    StagingFence fence;
 };
 
 static size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
@@ -42,7 +43,31 @@ void ovgpu_dbf_params_destroy(OVGPUDbfParams *p)
     cudaSetDevice(p->device);
     if (p->h_buf) cudaFreeHost(p->h_buf);
     if (p->d_buf) cudaFree(p->d_buf);
+    fence_destroy(&p->fence);
     free(p);
+}
+
+int ovgpu_dbf_params_staging(OVGPUCtx *ctx, OVGPUDbfParams *p, OVGPUDbfMaps *maps)
+{
+    if (!ctx || !p || !maps) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
+    maps->width = p->width; maps->height = p->height; maps->log2_ctu_s = p->log2_ctu;
+    size_t off = 0;
+    for (int k = 0; k < DBF_NB_MAPS; k++) { maps->ver[k] = (const uint32_t *)(p->h_buf + off); off += align16(p->ver_words * 4); }
+    for (int k = 0; k < DBF_NB_MAPS; k++) { maps->hor[k] = (const uint32_t *)(p->h_buf + off); off += align16(p->hor_words * 4); }
+    for (int c = 0; c < 3; c++) { maps->qp[c] = p->h_buf + off; off += align16(p->qp_bytes); }
+    return 0;
+}
+
+int ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, int tc_offset)
+{
+    if (!ctx || !p) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
+    p->beta_offset = beta_offset; p->tc_offset = tc_offset;
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_buf, p->h_buf, p->total, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&p->fence, ctx->stream));
+    p->loaded = 1;
+    return 0;
 }
 
 int ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps *maps)
@@ -52,15 +77,15 @@ int ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "DBF maps geometry differs from the parameter object");
     for (int k = 0; k < DBF_NB_MAPS; k++) if (!maps->ver[k] || !maps->hor[k]) return OVGPU_EINVAL;
     for (int c = 0; c < 3; c++) if (!maps->qp[c]) return OVGPU_EINVAL;
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    size_t off = 0;
-    for (int k = 0; k < DBF_NB_MAPS; k++) { memcpy(p->h_buf + off, maps->ver[k], p->ver_words * 4); off += align16(p->ver_words * 4); }
-    for (int k = 0; k < DBF_NB_MAPS; k++) { memcpy(p->h_buf + off, maps->hor[k], p->hor_words * 4); off += align16(p->hor_words * 4); }
-    for (int c = 0; c < 3; c++) { memcpy(p->h_buf + off, maps->qp[c], p->qp_bytes); off += align16(p->qp_bytes); }
-    p->beta_offset = maps->beta_offset; p->tc_offset = maps->tc_offset;
-    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_buf, p->h_buf, p->total, cudaMemcpyHostToDevice, ctx->stream));
-    p->loaded = 1;
-    return 0;
+    OVGPUDbfMaps st;
+    int ret = ovgpu_dbf_params_staging(ctx, p, &st);
+    if (ret) return ret;
+    for (int k = 0; k < DBF_NB_MAPS; k++) {
+        memcpy((void *)st.ver[k], maps->ver[k], p->ver_words * 4);
+        memcpy((void *)st.hor[k], maps->hor[k], p->hor_words * 4);
+    }
+    for (int c = 0; c < 3; c++) memcpy((void *)st.qp[c], maps->qp[c], p->qp_bytes);
+    return ovgpu_dbf_params_commit(ctx, p, maps->beta_offset, maps->tc_offset);
 }
 
 int ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p)

@@ -40,7 +40,7 @@ struct DbfMapsDev {
 
 template <int HOR>
 struct DbfK {
-    static const int THREADS = 256, MIN_BLOCKS = 2, PHASES = 1;
+    static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 1;
     static const int BX = 32, BY = 8;     // lanes along x (units); 8 unit rows / edge rows per CTA
 
     struct Args {

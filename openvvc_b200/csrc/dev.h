@@ -47,7 +47,8 @@ OVD int ovd_dp2a_lo(uint32_t a, uint32_t b, int c)
 { return c + ovd__lo(a) * (int8_t)(b & 0xff) + ovd__hi(a) * (int8_t)((b >> 8) & 0xff); }
 OVD int ovd_dp2a_hi(uint32_t a, uint32_t b, int c)
 { return c + ovd__lo(a) * (int8_t)((b >> 16) & 0xff) + ovd__hi(a) * (int8_t)((b >> 24) & 0xff); }
-OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s)
+// PTX prmt.b32, default mode: nibble bits 0-2 select a byte of {y,x}, bit 3 replicates that byte's sign
+OVD uint32_t ovd_prmt(uint32_t x, uint32_t y, uint32_t s)
 {
     uint64_t v = ((uint64_t)y << 32) | x;
     uint32_t r = 0;
@@ -59,6 +60,8 @@ OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s)
     }
     return r;
 }
+// CUDA __byte_perm: 3-bit selectors only
+OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s) { return ovd_prmt(x, y, s & 0x7777u); }
 OVD int ovd_sad(int a, int b, int c) { return c + (a > b ? a - b : b - a); }
 OVD int ovd_min(int a, int b) { return a < b ? a : b; }
 OVD int ovd_max(int a, int b) { return a > b ? a : b; }
@@ -71,7 +74,14 @@ OVD uint32_t ovd_vadd_16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 OVD uint32_t ovd_vsub_16x2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
 OVD int ovd_dp2a_lo(uint32_t a, uint32_t b, int c) { return __dp2a_lo((int)a, (int)b, c); }
 OVD int ovd_dp2a_hi(uint32_t a, uint32_t b, int c) { return __dp2a_hi((int)a, (int)b, c); }
-OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }
+OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s) { return __byte_perm(x, y, s); }   // 3-bit selectors only
+// prmt.b32 default mode: selector nibble bit 3 replicates the sign of the selected byte (PRMT)
+OVD uint32_t ovd_prmt(uint32_t x, uint32_t y, uint32_t s)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(y), "r"(s));
+    return r;
+}
 OVD int ovd_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }
 OVD int ovd_min(int a, int b) { return min(a, b); }
 OVD int ovd_max(int a, int b) { return max(a, b); }
@@ -134,9 +144,15 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const ty
 template <class K>
 static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_t smem, cudaStream_t s)
 {
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+    static bool configured = false;          // per kernel instantiation
+    if (!configured) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        // ask for the largest shared-memory carve-out so that occupancy is bounded by registers, not by the L1 split
+        if (smem > 0) cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
     }
     ovd_kernel<K><<<grid, K::THREADS, smem, s>>>(a);
     return cudaGetLastError();

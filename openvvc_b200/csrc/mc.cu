@@ -11,11 +11,13 @@ struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
     McCmdDev *h_cmds, *d_cmds;
     McItemDev *h_items, *d_items;
+    StagingFence fence;
 };
 
 struct OVGPULmcs {
     OVGPULmcsLuts *h_luts, *d_luts;
     int device;
+    StagingFence fence;
 };
 
 extern "C" {
@@ -49,15 +51,17 @@ void ovgpu_lmcs_destroy(OVGPULmcs *l)
     cudaSetDevice(l->device);
     if (l->h_luts) cudaFreeHost(l->h_luts);
     if (l->d_luts) cudaFree(l->d_luts);
+    fence_destroy(&l->fence);
     free(l);
 }
 
 int ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts)
 {
     if (!ctx || !l || !luts) return OVGPU_EINVAL;
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&l->fence));
     memcpy(l->h_luts, luts, sizeof(*luts));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(l->d_luts, l->h_luts, sizeof(*luts), cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&l->fence, ctx->stream));
     return 0;
 }
 
@@ -97,6 +101,7 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
     if (b->h_items) cudaFreeHost(b->h_items);
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_items) cudaFree(b->d_items);
+    fence_destroy(&b->fence);
     free(b);
 }
 
@@ -111,13 +116,14 @@ int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds
     }
     int n_items = mc_count_items(cmds, nb_cmds);
     if (n_items > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch needs %d items (max %d)", n_items, b->max_items);
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     memcpy(b->h_cmds, cmds, sizeof(McCmdDev) * nb_cmds);
     b->nb_cmds = nb_cmds;
     b->nb_items = mc_build_items(b->h_items, cmds, nb_cmds);
     if (nb_cmds) {
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(McItemDev) * b->nb_items, cudaMemcpyHostToDevice, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
     }
     return 0;
 }

@@ -6,14 +6,20 @@
 // (emulate_block_border, rcn_inter.c:148-225), interpolation kernels libovvc/rcn_mc.c:381-1608, forward LMCS
 // reshape of the luma prediction (rcn_inter.c:599).
 //
-// One warp owns one work item = a <=16x16 luma block (+ its 8x8 Cb/Cr blocks) of one PU.  The reference
-// window of each used list is staged in shared memory as packed pairs of samples; the separable filter runs
-// as IDP.2A dot products: an output at an even window position takes 4 (luma) / 2 (chroma) two-tap products on
-// aligned pairs, an output at an odd position 5 / 3 products with a shifted coefficient packing, so no
-// realignment is needed.  Zero fractions use the identity filter {..,64,..}, which reproduces the reference's
-// pel / h / v / hv variants bit for bit (64*s >> (BD-8) == s << (14-BD); (64*t) >> 6 == t).
+// One warp owns one work item = a <=16x16 luma block (+ its 8x8 Cb/Cr blocks) of one PU.
+//   phase 0  the reference window of each used list is staged in shared memory as packed pairs of samples with
+//            8-byte loads (clamped per-sample loads only for windows that cross the picture border);
+//   phase 1  every lane owns one output COLUMN of one list (bi-prediction: lanes 0-15 list 0, 16-31 list 1; uni:
+//            the two half-warps split the rows): it runs the horizontal filter down the column, keeps the 14-bit
+//            intermediates packed in registers and applies the vertical filter to them, all as IDP.2A dot products
+//            on (sample pair) x (tap pair) -- an output whose first tap sits on an odd sample index uses the shifted
+//            tap packing of mc_tables.h, so no realignment is needed;
+//   phase 2  the two lists are combined (average / BCW), clipped, forward-LMCS'ed (luma) and stored.
+// Zero fractions use the identity filter {..,64,..}, which reproduces the reference's pel / h / v / hv variants bit
+// for bit (64*s >> (BD-8) == s << (14-BD); (64*t) >> 6 == t).
 #pragma once
 #include "dev.h"
+#include "mc_tables.h"
 
 #define MC_LUMA 1
 #define MC_CHROMA 2
@@ -39,45 +45,18 @@ struct McRefsDev {
     int poc[2][16];
 };
 
-// filter coefficient banks (constant memory on the device)
-OVD_CONST int8_t mc_filt_l_tab[17][8] = {
-    {  0, 0,   0, 64,  0,   0,  0,  0 },
-    {  0, 1,  -3, 63,  4,  -2,  1,  0 }, { -1, 2,  -5, 62,  8,  -3,  1,  0 }, { -1, 3,  -8, 60, 13,  -4,  1,  0 },
-    { -1, 4, -10, 58, 17,  -5,  1,  0 }, { -1, 4, -11, 52, 26,  -8,  3, -1 }, { -1, 3,  -9, 47, 31, -10,  4, -1 },
-    { -1, 4, -11, 45, 34, -10,  4, -1 }, { -1, 4, -11, 40, 40, -11,  4, -1 }, { -1, 4, -10, 34, 45, -11,  4, -1 },
-    { -1, 4, -10, 31, 47,  -9,  3, -1 }, { -1, 3,  -8, 26, 52, -11,  4, -1 }, {  0, 1,  -5, 17, 58, -10,  4, -1 },
-    {  0, 1,  -4, 13, 60,  -8,  3, -1 }, {  0, 1,  -3,  8, 62,  -5,  2, -1 }, {  0, 1,  -2,  4, 63,  -3,  1,  0 },
-    {  0, 3,   9, 20, 20,   9,  3,  0 } };
-OVD_CONST int8_t mc_filt_l4_tab[16][8] = {
-    { 0, 0,   0, 64,  0,   0, 0, 0 },
-    { 0, 1,  -3, 63,  4,  -2, 1, 0 }, { 0, 1,  -5, 62,  8,  -3, 1, 0 }, { 0, 2,  -8, 60, 13,  -4, 1, 0 },
-    { 0, 3, -10, 58, 17,  -5, 1, 0 }, { 0, 3, -11, 52, 26,  -8, 2, 0 }, { 0, 2,  -9, 47, 31, -10, 3, 0 },
-    { 0, 3, -11, 45, 34, -10, 3, 0 }, { 0, 3, -11, 40, 40, -11, 3, 0 }, { 0, 3, -10, 34, 45, -11, 3, 0 },
-    { 0, 3, -10, 31, 47,  -9, 2, 0 }, { 0, 2,  -8, 26, 52, -11, 3, 0 }, { 0, 1,  -5, 17, 58, -10, 3, 0 },
-    { 0, 1,  -4, 13, 60,  -8, 2, 0 }, { 0, 1,  -3,  8, 62,  -5, 1, 0 }, { 0, 1,  -2,  4, 63,  -3, 1, 0 } };
-OVD_CONST int8_t mc_filt_c_tab[32][4] = {
-    {  0, 64,  0,  0 },
-    { -1, 63,  2,  0 }, { -2, 62,  4,  0 }, { -2, 60,  7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
-    { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 },
-    { -6, 49, 24, -3 }, { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 },
-    { -4, 36, 36, -4 }, { -4, 33, 39, -4 }, { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 },
-    { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 }, { -2, 16, 54, -4 }, { -2, 15, 55, -4 },
-    { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1,  7, 60, -2 }, {  0,  4, 62, -2 },
-    {  0,  2, 63, -1 } };
-
 struct McK {
-    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 3;
+    static const int THREADS = 128, MIN_BLOCKS = 6, PHASES = 3;
     static const int WARPS = 4;
-    // per-warp shared memory (bytes)
-    static const int WIN_Y_WORDS = 12, WIN_Y_ROWS = 23;
-    static const int WIN_C_WORDS = 6, WIN_C_ROWS = 11;
-    static const int TMP_Y_COL = 26;       // int16 per column (23 rows, padded: 52 B keeps columns on distinct banks)
-    static const int TMP_C_COL = 12;
-    static const int SM_WIN_Y = 2 * WIN_Y_ROWS * WIN_Y_WORDS * 4;        // [ref][row][word]
-    static const int SM_WIN_C = 2 * 2 * WIN_C_ROWS * WIN_C_WORDS * 4;    // [ref][comp][row][word]
-    static const int SM_TMP_Y = 2 * 16 * TMP_Y_COL * 2;                  // [ref][col][row]
-    static const int SM_TMP_C = 2 * 2 * 8 * TMP_C_COL * 2;               // [ref][comp][col][row]
-    static const int SM_WARP = SM_WIN_Y + SM_WIN_C + SM_TMP_Y + SM_TMP_C;
+    // per-warp shared memory, 32-bit words
+    static const int WIN_Y_WORDS = 14, WIN_Y_ROWS = 23;      // 28 samples x (16 + 7) rows per list
+    static const int WIN_C_WORDS = 8, WIN_C_ROWS = 11;       // 16 samples x (8 + 3) rows per list and component
+    static const int SM_ITEM = 16;
+    static const int SM_WIN_Y = 2 * WIN_Y_ROWS * WIN_Y_WORDS;            // [list][row][word]
+    static const int SM_WIN_C = 2 * 2 * WIN_C_ROWS * WIN_C_WORDS;        // [list][comp][row][word]
+    static const int SM_EX_Y = 2 * 16 * 16 / 2;                          // [list][row][col] int16
+    static const int SM_EX_C = 2 * 2 * 8 * 8 / 2;                        // [list][comp][row][col] int16
+    static const int SM_WARP = (SM_ITEM + SM_WIN_Y + SM_WIN_C + SM_EX_Y + SM_EX_C) * 4;
     static const int SMEM_BYTES = WARPS * SM_WARP;
 
     struct Args {
@@ -150,28 +129,85 @@ struct McK {
         return (uint32_t)row[ovd_clamp(xa, 0, w - 1)] | ((uint32_t)row[ovd_clamp(xa + 1, 0, w - 1)] << 16);
     }
 
-    // coefficient packing: word j = bytes [c(2j), c(2j+1) | c(2j-1), c(2j)] (see file header)
-    OVD uint32_t coef_word(const int8_t *f, int ntaps, int j)
+    // horizontal filter at window row `wrow` (already offset to the lane's first word): NW IDP.2A.LO
+    template <int NW>
+    OVD int hfir(const uint32_t *wrow, const uint32_t *B)
     {
-        int c0 = 2 * j < ntaps ? f[2 * j] : 0, c1 = 2 * j + 1 < ntaps ? f[2 * j + 1] : 0;
-        int cm = (2 * j - 1 >= 0 && 2 * j - 1 < ntaps) ? f[2 * j - 1] : 0;
-        return (uint32_t)(uint8_t)c0 | ((uint32_t)(uint8_t)c1 << 8) | ((uint32_t)(uint8_t)cm << 16) | ((uint32_t)(uint8_t)c0 << 24);
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < NW; j++) acc = ovd_dp2a_lo(wrow[j], B[j], acc);
+        return acc;
+    }
+    OVD uint32_t pack2(int a, int b) { return (uint32_t)(uint16_t)(int16_t)a | ((uint32_t)b << 16); }
+
+    // One output column: horizontal filter over NOUT + NT - 1 window rows, vertical filter over the packed results.
+    // NT = 8 (luma, NW = 5 words) or 4 (chroma, NW = 3 words).  ex: this column of the exchange buffer, row stride exs.
+    // Fully unrolled and branch-free: NOUT is the block height (a power of two), chosen by a warp-uniform switch.
+    template <int NOUT, int NT, int NW>
+    OVD void column(const uint32_t *win, int row_words, const uint32_t *Bh, const uint32_t *Bv0, const uint32_t *Bv1,
+                    int sh1, int16_t *ex, int exs)
+    {
+        const int NR = NOUT + NT - 1, NP = (NR + 1) / 2;    // window rows, packed pairs of intermediates
+        uint32_t T[NP];
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            const int a = hfir<NW>(win + (2 * k) * row_words, Bh) >> sh1;
+            const int b = 2 * k + 1 < NR ? hfir<NW>(win + (2 * k + 1) * row_words, Bh) >> sh1 : 0;
+            T[k] = pack2(a, b);
+        }
+#pragma unroll
+        for (int y = 0; y < NOUT; y++) {
+            const int k = y >> 1;
+            int acc = 0;
+            if (y & 1) {
+#pragma unroll
+                for (int j = 0; j < NT / 2 + 1; j++) acc = ovd_dp2a_lo(T[k + j], Bv1[j], acc);
+            } else {
+#pragma unroll
+                for (int j = 0; j < NT / 2; j++) acc = ovd_dp2a_lo(T[k + j], Bv0[j], acc);
+            }
+            ex[y * exs] = (int16_t)(acc >> 6);
+        }
     }
 
-    // 8-tap (NW = 5 coefficient words) or 4-tap (NW = 3) filter at window sample index i over packed pairs W[]
-    template <int NW>
-    OVD int fir(const uint32_t *W, int i, const uint32_t *B)
+    // final sample from the two 14-bit predictions (rcn_mc.c put_*_uni / put_*_bi / put_weighted_*)
+    OVD int combine(int p0, int p1, int nref, int bcw, int w1, int bd, int maxv)
     {
-        const int q = i >> 1;
-        int acc = 0;
-        if (i & 1) {
+        int v;
+        if (nref == 1)  v = (p0 + (1 << (13 - bd))) >> (14 - bd);
+        else if (!bcw)  v = (p0 + p1 + (1 << (14 - bd))) >> (15 - bd);
+        else            v = (p1 * w1 + p0 * (8 - w1) + (1 << (16 - bd))) >> (17 - bd);
+        return ovd_clamp(v, 0, maxv);
+    }
+    // 8 horizontally adjacent final samples: two 16-byte reads of the exchange buffer, one 16-byte (or 8-byte) store
+    OVD void store_row8(const Args &a, int plane, const int16_t *e0, const int16_t *e1, uint16_t *d, int n, int nref, int bcw, int w1,
+                        int maxv, bool lut)
+    {
+        const ovd_u4 q0 = *(const ovd_u4 *)e0;
+        ovd_u4 q1; q1.x = q1.y = q1.z = q1.w = 0;
+        if (nref == 2) q1 = *(const ovd_u4 *)e1;
+        const uint32_t w0[4] = { q0.x, q0.y, q0.z, q0.w }, w1v[4] = { q1.x, q1.y, q1.z, q1.w };
+        uint32_t o[4];
+        (void)plane;
 #pragma unroll
-            for (int j = 0; j < NW; j++) acc = ovd_dp2a_hi(W[q + j], B[j], acc);
-        } else {
-#pragma unroll
-            for (int j = 0; j < NW - 1; j++) acc = ovd_dp2a_lo(W[q + j], B[j], acc);
+        for (int k = 0; k < 4; k++) {
+            int va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), nref, bcw, w1, a.bitdepth, maxv);
+            int vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), nref, bcw, w1, a.bitdepth, maxv);
+            if (lut) { va = a.lmcs_fwd[va]; vb = a.lmcs_fwd[vb]; }
+            o[k] = (uint32_t)va | ((uint32_t)vb << 16);
         }
-        return acc;
+        // block positions are multiples of 4 luma samples only (ternary splits): pick the widest aligned store
+        const unsigned al = (unsigned)(uintptr_t)d;
+        if (n >= 8 && !(al & 15)) { ovd_u4 r; r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3]; ovd_st16(d, r); }
+        else if (!(al & 7)) {
+            ovd_u2 r; r.x = o[0]; r.y = o[1]; ovd_st8(d, r);
+            if (n >= 8) { r.x = o[2]; r.y = o[3]; ovd_st8(d + 4, r); }
+        } else {
+            uint32_t *d32 = (uint32_t *)d;
+            d32[0] = o[0];
+            if (n >= 4) d32[1] = o[1];
+            if (n >= 8) { d32[2] = o[2]; d32[3] = o[3]; }
+        }
     }
 
     template <int P>
@@ -179,164 +215,154 @@ struct McK {
     {
         (void)st; (void)by; (void)bz;
         const int warp = tid >> 5, lane = tid & 31;
-        const Item it = load_item(a, bx * WARPS + warp);
-        if (!it.valid) return;
-        unsigned char *sm = smem + warp * SM_WARP;
-        uint32_t *win_y = (uint32_t *)sm;
-        uint32_t *win_c = (uint32_t *)(sm + SM_WIN_Y);
-        int16_t *tmp_y = (int16_t *)(sm + SM_WIN_Y + SM_WIN_C);
-        int16_t *tmp_c = (int16_t *)(sm + SM_WIN_Y + SM_WIN_C + SM_TMP_Y);
-        const int do_y = it.flags & MC_LUMA, do_c = it.flags & MC_CHROMA;
+        uint32_t *sm = (uint32_t *)(smem + warp * SM_WARP);
+        int *sit = (int *)sm;
+        uint32_t *win_y = sm + SM_ITEM;
+        uint32_t *win_c = win_y + SM_WIN_Y;
+        int16_t *ex_y = (int16_t *)(win_c + SM_WIN_C);
+        int16_t *ex_c = (int16_t *)(win_c + SM_WIN_C + SM_EX_Y);
         const int cw = a.pic_w >> 1, ch = a.pic_h >> 1;
 
         if (P == 0) {
-            // ---- stage reference windows -------------------------------------------------------------------
-            for (int r = 0; r < it.nref; r++) {
-                if (do_y) {
-                    const uint16_t *pl = a.refs.plane[it.list[r]][it.ridx[r]][0];
-                    const int pitch = a.refs.pitch[it.list[r]][it.ridx[r]][0];
-                    const int x_al = (it.bx + (it.mvx[r] >> 4) - 3) & ~1, y0 = it.by + (it.mvy[r] >> 4) - 3;
-                    for (int i = lane; i < WIN_Y_ROWS * WIN_Y_WORDS; i += 32) {
-                        int row = i / WIN_Y_WORDS, wd = i - row * WIN_Y_WORDS;
-                        win_y[(r * WIN_Y_ROWS + row) * WIN_Y_WORDS + wd] = load_pair(pl, pitch, a.pic_w, a.pic_h, x_al + 2 * wd, y0 + row);
+            const Item it = load_item(a, bx * WARPS + warp);
+            if (lane == 0) sit[0] = it.valid;
+            if (!it.valid) return;
+            const int do_y = it.flags & MC_LUMA, do_c = it.flags & MC_CHROMA;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (r >= it.nref) break;
+                // ---- luma window: 28 samples from a 4-sample aligned start, h + 7 rows
+                const int xs = it.bx + (it.mvx[r] >> 4) - 3, ys = it.by + (it.mvy[r] >> 4) - 3, x_al = xs & ~3;
+                const int xc = (it.bx >> 1) + (it.mvx[r] >> 5) - 1, yc = (it.by >> 1) + (it.mvy[r] >> 5) - 1, xc_al = xc & ~3;
+                if (lane == 0) {
+                    int px = it.mvx[r] & 15, py = it.mvy[r] & 15;
+                    if ((it.flags & MC_HPEL_AMVR) && !it.pu_small) { if (px == 8) px = 16; if (py == 8) py = 16; }   // rcn_inter.c:572-577
+                    if (it.pu_small) { px += 17; py += 17; }                                                       // 6-tap set, rcn_mc.c:457
+                    sit[8 + 4 * r] = (xs - x_al) | ((xc - xc_al) << 8);
+                    sit[9 + 4 * r] = px | (py << 8);
+                    sit[10 + 4 * r] = (it.mvx[r] & 31) | ((it.mvy[r] & 31) << 8);
+                }
+                // All global loads of a list are issued before the first shared-memory store so that they overlap
+                // (the windows are latency-, not bandwidth-bound).
+                const uint16_t *pl = a.refs.plane[it.list[r]][it.ridx[r]][0];
+                const int pitch = a.refs.pitch[it.list[r]][it.ridx[r]][0], nrows = it.h + 7;
+                uint32_t *w = win_y + r * WIN_Y_ROWS * WIN_Y_WORDS;
+                const int fast_y = do_y && x_al >= 0 && x_al + 2 * WIN_Y_WORDS <= a.pic_w && ys >= 0 && ys + nrows <= a.pic_h;
+                const int nrows_c = (it.h >> 1) + 3, comp = lane >> 4;
+                const uint16_t *plc = a.refs.plane[it.list[r]][it.ridx[r]][1 + comp];
+                const int pitch_c = a.refs.pitch[it.list[r]][it.ridx[r]][1 + comp];
+                uint32_t *wc = win_c + (r * 2 + comp) * WIN_C_ROWS * WIN_C_WORDS;
+                const int fast_c = do_c && xc_al >= 0 && xc_al + 2 * WIN_C_WORDS <= cw && yc >= 0 && yc + nrows_c <= ch;
+                ovd_u2 vy[6], vc[3];
+                const int cy = lane & 7, ry = lane >> 3, cc = lane & 3, rc = (lane >> 2) & 3;
+                if (fast_y && cy < 7) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                        if (ry + 4 * k < nrows) vy[k] = ovd_ld8(pl + (size_t)(ys + ry + 4 * k) * pitch + x_al + 4 * cy);
+                }
+                if (fast_c) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        if (rc + 4 * k < nrows_c) vc[k] = ovd_ld8(plc + (size_t)(yc + rc + 4 * k) * pitch_c + xc_al + 4 * cc);
+                }
+                if (fast_y && cy < 7) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                        if (ry + 4 * k < nrows) { w[(ry + 4 * k) * WIN_Y_WORDS + 2 * cy] = vy[k].x; w[(ry + 4 * k) * WIN_Y_WORDS + 2 * cy + 1] = vy[k].y; }
+                }
+                if (fast_c) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++)
+                        if (rc + 4 * k < nrows_c) { wc[(rc + 4 * k) * WIN_C_WORDS + 2 * cc] = vc[k].x; wc[(rc + 4 * k) * WIN_C_WORDS + 2 * cc + 1] = vc[k].y; }
+                }
+                if (do_y && !fast_y) {              // window crosses the picture border: clamped coordinates
+                    for (int i = lane; i < nrows * WIN_Y_WORDS; i += 32) {
+                        const int row = i / WIN_Y_WORDS, wd = i - row * WIN_Y_WORDS;
+                        w[i] = load_pair(pl, pitch, a.pic_w, a.pic_h, x_al + 2 * wd, ys + row);
                     }
                 }
-                if (do_c) {
-                    const int x_al = ((it.bx >> 1) + (it.mvx[r] >> 5) - 1) & ~1, y0 = (it.by >> 1) + (it.mvy[r] >> 5) - 1;
-                    for (int i = lane; i < 2 * WIN_C_ROWS * WIN_C_WORDS; i += 32) {
-                        int comp = i / (WIN_C_ROWS * WIN_C_WORDS), k = i - comp * (WIN_C_ROWS * WIN_C_WORDS);
-                        int row = k / WIN_C_WORDS, wd = k - row * WIN_C_WORDS;
-                        const uint16_t *pl = a.refs.plane[it.list[r]][it.ridx[r]][1 + comp];
-                        const int pitch = a.refs.pitch[it.list[r]][it.ridx[r]][1 + comp];
-                        win_c[((r * 2 + comp) * WIN_C_ROWS + row) * WIN_C_WORDS + wd] = load_pair(pl, pitch, cw, ch, x_al + 2 * wd, y0 + row);
+                if (do_c && !fast_c) {
+                    for (int i = lane & 15; i < nrows_c * WIN_C_WORDS; i += 16) {
+                        const int row = i / WIN_C_WORDS, wd = i - row * WIN_C_WORDS;
+                        wc[i] = load_pair(plc, pitch_c, cw, ch, xc_al + 2 * wd, yc + row);
                     }
                 }
+            }
+            if (lane == 0) {
+                sit[1] = it.bx; sit[2] = it.by; sit[3] = it.w; sit[4] = it.h; sit[5] = it.nref; sit[6] = it.flags; sit[7] = it.bcw;
             }
             return;
         }
 
-        const int sh1 = a.bitdepth - 8;
+        if (!sit[0]) return;
+        const int ibx = sit[1], iby = sit[2], iw = sit[3], ih = sit[4], nref = sit[5], flags = sit[6], bcw = sit[7];
+        const int do_y = flags & MC_LUMA, do_c = flags & MC_CHROMA;
+
         if (P == 1) {
-            // ---- horizontal pass: window rows -> column-major 14-bit intermediates ---------------------------
+            const int sh1 = a.bitdepth - 8, hi = lane >> 4, bi = nref == 2;
+            const int r = bi ? hi : 0;
+            const int offs = sit[8 + 4 * r], frl = sit[9 + 4 * r], frc = sit[10 + 4 * r];
             if (do_y) {
-                for (int task = lane; task < it.nref * WIN_Y_ROWS * 2; task += 32) {
-                    const int r = task / (WIN_Y_ROWS * 2), k = task - r * (WIN_Y_ROWS * 2);
-                    const int row = k >> 1, half = k & 1;
-                    int px = it.mvx[r] & 15;
-                    if ((it.flags & MC_HPEL_AMVR) && !it.pu_small && px == 8) px = 16;  // rcn_inter.c:572-577
-                    const int8_t *f = it.pu_small ? mc_filt_l4_tab[px] : mc_filt_l_tab[px];
-                    uint32_t B[5];
+                const int x = lane & 15, row0 = bi ? 0 : 8 * hi;
+                if (x < iw && row0 < ih) {
+                    const int o = (offs & 0xff) + x;
+                    uint32_t Bh[5], Bv0[4], Bv1[5];
 #pragma unroll
-                    for (int j = 0; j < 5; j++) B[j] = coef_word(f, 8, j);
-                    const int o = (it.bx + (it.mvx[r] >> 4) - 3) & 1;
-                    const uint32_t *wrow = win_y + (r * WIN_Y_ROWS + row) * WIN_Y_WORDS + 4 * half;
-                    uint32_t W[9];
+                    for (int j = 0; j < 5; j++) { Bh[j] = mc_cw_l[frl & 0xff][o & 1][j]; Bv1[j] = mc_cw_l[frl >> 8][1][j]; }
 #pragma unroll
-                    for (int j = 0; j < 9; j++) W[j] = wrow[(4 * half + j < WIN_Y_WORDS) ? j : 0];
-                    int16_t *tcol = tmp_y + (r * 16 + 8 * half) * TMP_Y_COL + row;
-                    // o is uniform for the warp: two fully unrolled variants keep W[] in registers
-                    if (o) {
-#pragma unroll
-                        for (int x = 0; x < 8; x++) tcol[x * TMP_Y_COL] = (int16_t)(fir<5>(W, x + 1, B) >> sh1);
+                    for (int j = 0; j < 4; j++) Bv0[j] = mc_cw_l[frl >> 8][0][j];
+                    const uint32_t *w = win_y + (r * WIN_Y_ROWS + row0) * WIN_Y_WORDS + (o >> 1);
+                    int16_t *ex = ex_y + (r * 16 + row0) * 16 + x;
+                    if (bi) {
+                        if (ih == 16)     column<16, 8, 5>(w, WIN_Y_WORDS, Bh, Bv0, Bv1, sh1, ex, 16);
+                        else if (ih == 8) column<8, 8, 5>(w, WIN_Y_WORDS, Bh, Bv0, Bv1, sh1, ex, 16);
+                        else              column<4, 8, 5>(w, WIN_Y_WORDS, Bh, Bv0, Bv1, sh1, ex, 16);
                     } else {
-#pragma unroll
-                        for (int x = 0; x < 8; x++) tcol[x * TMP_Y_COL] = (int16_t)(fir<5>(W, x, B) >> sh1);
+                        if (ih >= 8)      column<8, 8, 5>(w, WIN_Y_WORDS, Bh, Bv0, Bv1, sh1, ex, 16);
+                        else              column<4, 8, 5>(w, WIN_Y_WORDS, Bh, Bv0, Bv1, sh1, ex, 16);
                     }
                 }
             }
             if (do_c) {
-                for (int task = lane; task < it.nref * 2 * WIN_C_ROWS; task += 32) {
-                    const int rc = task / WIN_C_ROWS, row = task - rc * WIN_C_ROWS;     // rc = ref * 2 + comp
-                    const int r = rc >> 1;
-                    const int8_t *f = mc_filt_c_tab[it.mvx[r] & 31];
-                    uint32_t B[3];
+                const int x = lane & 7, comp = (lane >> 3) & 1, row0 = bi ? 0 : 4 * hi, hc = ih >> 1;
+                if (x < (iw >> 1) && row0 < hc) {
+                    const int o = (offs >> 8) + x;
+                    uint32_t Bh[3], Bv0[2], Bv1[3];
 #pragma unroll
-                    for (int j = 0; j < 3; j++) B[j] = coef_word(f, 4, j);
-                    const int o = ((it.bx >> 1) + (it.mvx[r] >> 5) - 1) & 1;
-                    const uint32_t *wrow = win_c + (rc * WIN_C_ROWS + row) * WIN_C_WORDS;
-                    uint32_t W[6];
+                    for (int j = 0; j < 3; j++) { Bh[j] = mc_cw_c[frc & 0xff][o & 1][j]; Bv1[j] = mc_cw_c[frc >> 8][1][j]; }
 #pragma unroll
-                    for (int j = 0; j < 6; j++) W[j] = wrow[j];
-                    int16_t *tcol = tmp_c + rc * 8 * TMP_C_COL + row;
-                    if (o) {
-#pragma unroll
-                        for (int x = 0; x < 8; x++) tcol[x * TMP_C_COL] = (int16_t)(fir<3>(W, x + 1, B) >> sh1);
+                    for (int j = 0; j < 2; j++) Bv0[j] = mc_cw_c[frc >> 8][0][j];
+                    const uint32_t *w = win_c + ((r * 2 + comp) * WIN_C_ROWS + row0) * WIN_C_WORDS + (o >> 1);
+                    int16_t *ex = ex_c + ((r * 2 + comp) * 8 + row0) * 8 + x;
+                    if (bi) {
+                        if (hc == 8)      column<8, 4, 3>(w, WIN_C_WORDS, Bh, Bv0, Bv1, sh1, ex, 8);
+                        else if (hc == 4) column<4, 4, 3>(w, WIN_C_WORDS, Bh, Bv0, Bv1, sh1, ex, 8);
+                        else              column<2, 4, 3>(w, WIN_C_WORDS, Bh, Bv0, Bv1, sh1, ex, 8);
                     } else {
-#pragma unroll
-                        for (int x = 0; x < 8; x++) tcol[x * TMP_C_COL] = (int16_t)(fir<3>(W, x, B) >> sh1);
+                        if (hc >= 4)      column<4, 4, 3>(w, WIN_C_WORDS, Bh, Bv0, Bv1, sh1, ex, 8);
+                        else              column<2, 4, 3>(w, WIN_C_WORDS, Bh, Bv0, Bv1, sh1, ex, 8);
                     }
                 }
             }
             return;
         }
 
-        // ---- vertical pass + combination + store --------------------------------------------------------------
+        // ---- combination + store ----------------------------------------------------------------------------------
         const int maxv = (1 << a.bitdepth) - 1;
-        const int w1 = it.bcw == 1 ? -2 : it.bcw == 2 ? 3 : it.bcw == 4 ? 5 : 10;           // rcn_inter.c:89
+        const int w1 = bcw == 1 ? -2 : bcw == 2 ? 3 : bcw == 4 ? 5 : 10;           // rcn_inter.c:89
         if (do_y) {
-            const int x = lane & 15, g = lane >> 4;
-            int p[2][8];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (r < it.nref) {
-                    int py = it.mvy[r] & 15;
-                    if ((it.flags & MC_HPEL_AMVR) && !it.pu_small && py == 8) py = 16;
-                    const int8_t *f = it.pu_small ? mc_filt_l4_tab[py] : mc_filt_l_tab[py];
-                    uint32_t B[5];
-#pragma unroll
-                    for (int j = 0; j < 5; j++) B[j] = coef_word(f, 8, j);
-                    const uint32_t *tw = (const uint32_t *)(tmp_y + (r * 16 + x) * TMP_Y_COL) + 4 * g;
-                    uint32_t W[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) W[j] = tw[j];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) p[r][k] = fir<5>(W, k, B) >> 6;
-                }
-            }
-            if (x < it.w) {
-#pragma unroll
-                for (int k = 0; k < 8; k++) {
-                    const int y = 8 * g + k;
-                    if (y >= it.h) continue;
-                    int v;
-                    if (it.nref == 1)   v = (p[0][k] + (1 << (13 - a.bitdepth))) >> (14 - a.bitdepth);
-                    else if (!it.bcw)   v = (p[0][k] + p[1][k] + (1 << (14 - a.bitdepth))) >> (15 - a.bitdepth);
-                    else                v = (p[1][k] * w1 + p[0][k] * (8 - w1) + (1 << (16 - a.bitdepth))) >> (17 - a.bitdepth);
-                    v = ovd_clamp(v, 0, maxv);
-                    if (a.lmcs_fwd) v = a.lmcs_fwd[v];
-                    a.dst[0][(size_t)(it.by + y) * a.dst_pitch[0] + it.bx + x] = (uint16_t)v;
-                }
-            }
+            // lane -> (row, 8-sample half): 16 rows x 2 halves
+            const int y = lane >> 1, x = (lane & 1) * 8;
+            if (y < ih && x < iw)
+                store_row8(a, 0, ex_y + y * 16 + x, ex_y + (16 + y) * 16 + x, a.dst[0] + (size_t)(iby + y) * a.dst_pitch[0] + ibx + x,
+                           iw - x, nref, bcw, w1, maxv, a.lmcs_fwd != 0);
         }
         if (do_c) {
-            const int x = lane & 7, comp = (lane >> 3) & 1, g = lane >> 4;
-            int p[2][4];
-#pragma unroll
-            for (int r = 0; r < 2; r++) {
-                if (r < it.nref) {
-                    const int8_t *f = mc_filt_c_tab[it.mvy[r] & 31];
-                    uint32_t B[3];
-#pragma unroll
-                    for (int j = 0; j < 3; j++) B[j] = coef_word(f, 4, j);
-                    const uint32_t *tw = (const uint32_t *)(tmp_c + ((r * 2 + comp) * 8 + x) * TMP_C_COL) + 2 * g;
-                    uint32_t W[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) W[j] = tw[j];
-#pragma unroll
-                    for (int k = 0; k < 4; k++) p[r][k] = fir<3>(W, k, B) >> 6;
-                }
-            }
-            if (x < (it.w >> 1)) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int y = 4 * g + k;
-                    if (y >= (it.h >> 1)) continue;
-                    int v;
-                    if (it.nref == 1)   v = (p[0][k] + (1 << (13 - a.bitdepth))) >> (14 - a.bitdepth);
-                    else if (!it.bcw)   v = (p[0][k] + p[1][k] + (1 << (14 - a.bitdepth))) >> (15 - a.bitdepth);
-                    else                v = (p[1][k] * w1 + p[0][k] * (8 - w1) + (1 << (16 - a.bitdepth))) >> (17 - a.bitdepth);
-                    a.dst[1 + comp][(size_t)((it.by >> 1) + y) * a.dst_pitch[1 + comp] + (it.bx >> 1) + x] = (uint16_t)ovd_clamp(v, 0, maxv);
-                }
+            // lanes 0-15 -> (component, row): 2 x 8 rows of <= 8 samples
+            const int comp = (lane >> 3) & 1, y = lane & 7;
+            if (lane < 16 && y < (ih >> 1)) {
+                uint16_t *d = (comp ? a.dst[2] : a.dst[1]) + (size_t)((iby >> 1) + y) * (comp ? a.dst_pitch[2] : a.dst_pitch[1]) + (ibx >> 1);
+                store_row8(a, 1, ex_c + (comp * 8 + y) * 8, ex_c + ((2 + comp) * 8 + y) * 8, d, iw >> 1, nref, bcw, w1, maxv, false);
             }
         }
     }

@@ -8,6 +8,7 @@ struct OVGPUSaoParams {
     int width, height, log2_ctu, nb_ctu_w, nb_ctu_h, nb_ctu;
     SaoCtuDev *h_ctu, *d_ctu;
     int device;
+    StagingFence fence;
 };
 
 static_assert(sizeof(SaoCtuDev) == sizeof(OVGPUSaoCtu), "SAO CTU parameter layout");
@@ -40,16 +41,24 @@ void ovgpu_sao_params_destroy(OVGPUSaoParams *p)
     cudaSetDevice(p->device);
     if (p->h_ctu) cudaFreeHost(p->h_ctu);
     if (p->d_ctu) cudaFree(p->d_ctu);
+    fence_destroy(&p->fence);
     free(p);
 }
 
 int ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu *ctu)
 {
     if (!ctx || !p || !ctu) return OVGPU_EINVAL;
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    // the kernel keeps the five offsets of a CTU as packed bytes (|offset| <= 31 at 10 bit, vcl_sao.c:69)
+    for (int i = 0; i < p->nb_ctu; i++)
+        for (int c = 0; c < 3; c++)
+            for (int k = 0; k < 5; k++)
+                if (ctu[i].offset_val[c][k] < -128 || ctu[i].offset_val[c][k] > 127)
+                    return ovgpu_set_error(ctx, OVGPU_EINVAL, "SAO offset of CTU %d out of range", i);
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
     memcpy(p->h_ctu, ctu, sizeof(SaoCtuDev) * p->nb_ctu);
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_ctu, p->h_ctu, sizeof(SaoCtuDev) * p->nb_ctu,
                                           cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&p->fence, ctx->stream));
     return 0;
 }
 

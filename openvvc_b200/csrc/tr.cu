@@ -13,6 +13,7 @@ struct OVGPUTuBatch {
     TuCmdDev *h_cmds, *d_cmds;
     TbItemDev *h_items, *d_items;       // small items first, then large ones
     int16_t *h_coeffs, *d_coeffs;
+    StagingFence fence;
 };
 
 template <int GROUP>
@@ -59,7 +60,38 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_items) cudaFree(b->d_items);
     if (b->d_coeffs) cudaFree(b->d_coeffs);
+    fence_destroy(&b->fence);
     free(b);
+}
+
+int ovgpu_tu_batch_staging(OVGPUCtx *ctx, OVGPUTuBatch *b, OVGPUTuCmd **cmds, int16_t **coeffs)
+{
+    if (!ctx || !b || !cmds || !coeffs) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));           // previous H2D copy out of the staging buffers
+    *cmds = (OVGPUTuCmd *)b->h_cmds;
+    *coeffs = b->h_coeffs;
+    return 0;
+}
+
+int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb_coeffs, const OVGPUTuSlice *slice)
+{
+    if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs) return OVGPU_EINVAL;
+    const OVGPUTuCmd *cmds = (const OVGPUTuCmd *)b->h_cmds;
+    for (int i = 0; i < nb_cmds; i++)
+        if (tu_check_cmd(&cmds[i], nb_coeffs))
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d malformed", i);
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    b->slice = *slice;
+    b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
+    if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
+    tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
+    tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(TuCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * (b->nb_small + b->nb_large),
+                                          cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_coeffs, b->h_coeffs, sizeof(int16_t) * nb_coeffs, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+    return 0;
 }
 
 int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds, int nb_cmds,
@@ -68,22 +100,11 @@ int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds
     if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs ||
         (nb_cmds && (!cmds || !coeffs)))
         return OVGPU_EINVAL;
-    for (int i = 0; i < nb_cmds; i++)
-        if (tu_check_cmd(&cmds[i], nb_coeffs))
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d malformed", i);
-    OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // staging buffers may still be in flight
-    b->slice = *slice;
-    b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
-    if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
-    memcpy(b->h_cmds, cmds, sizeof(TuCmdDev) * nb_cmds);
-    memcpy(b->h_coeffs, coeffs, sizeof(int16_t) * nb_coeffs);
-    tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
-    tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
-    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(TuCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
-    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * (b->nb_small + b->nb_large),
-                                          cudaMemcpyHostToDevice, ctx->stream));
-    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_coeffs, b->h_coeffs, sizeof(int16_t) * nb_coeffs, cudaMemcpyHostToDevice, ctx->stream));
-    return 0;
+    OVGPUTuCmd *hc; int16_t *hk;
+    int ret = ovgpu_tu_batch_staging(ctx, b, &hc, &hk);
+    if (ret) return ret;
+    if (nb_cmds) { memcpy(hc, cmds, sizeof(TuCmdDev) * nb_cmds); memcpy(hk, coeffs, sizeof(int16_t) * nb_coeffs); }
+    return ovgpu_tu_batch_commit(ctx, b, nb_cmds, nb_coeffs, slice);
 }
 
 int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b)

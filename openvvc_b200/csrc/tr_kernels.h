@@ -224,7 +224,9 @@ struct TrK {
                        int scale, int gt)
     {
         const int w = 1 << t.lw, n = 1 << (t.lw + t.lh), maxv = (1 << a.bitdepth) - 1;
-        uint16_t *base = a.dst[comp] + (size_t)t.py * a.dst_pitch[comp] + t.px;
+        // selects, not a.dst[comp]: dynamic indexing would copy the kernel parameter block to local memory
+        const int pitch = comp == 0 ? a.dst_pitch[0] : (comp == 1 ? a.dst_pitch[1] : a.dst_pitch[2]);
+        uint16_t *base = (comp == 0 ? a.dst[0] : (comp == 1 ? a.dst[1] : a.dst[2])) + (size_t)t.py * pitch + t.px;
         for (int o = gt; o < n; o += GROUP) {
             int v = t.mode == MODE_DC ? dcv : res[o];
             if (sub) v = -v;
@@ -235,7 +237,7 @@ struct TrK {
                 m = (ovd_min(m, maxv) * scale + (1 << 10)) >> 11;
                 v = ovd_clamp(sign ? -m : m, -(1 << 15), 1 << 15);
             }
-            uint16_t *p = base + (size_t)(o >> t.lw) * a.dst_pitch[comp] + (o & (w - 1));
+            uint16_t *p = base + (size_t)(o >> t.lw) * pitch + (o & (w - 1));
             *p = (uint16_t)ovd_clamp((int)*p + v, 0, maxv);
         }
     }
