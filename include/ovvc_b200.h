@@ -167,6 +167,16 @@ int  ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmc
 #define OVGPU_MC_CHROMA    2   /* rcn_mcp_b_c                                           */
 #define OVGPU_MC_HPEL_AMVR 4   /* inter_ctx->prec_amvr == MV_PRECISION_HALF             */
 
+#define OVGPU_MC_TOOL_PLAIN 0  /* rcn_mcp_b / rcn_mcp_b_l / rcn_mcp_b_c                                             */
+#define OVGPU_MC_TOOL_BDOF  1  /* rcn_bdof_mcp_l (rcn_inter.c:1137): one <=16x16 luma sub-block of a BDOF CU, as called
+                                * from vcl_coding_unit.c:2648-2672; bi-prediction, luma only                          */
+#define OVGPU_MC_TOOL_PROF  2  /* rcn_prof_mcp_b_l (rcn_inter.c:2865): one 4x4 luma sub-block of an affine CU, as called
+                                * from drv_affine_mvp.c:3355; aux = prof_dir (bits 0-1) | PROF table index << 8       */
+/* struct PROFInfo (rcn_inter.c:1128-1134): the 16 per-sample delta-MV scales of an affine CU and list */
+typedef struct OVGPUProfInfo {
+    int16_t dmv_scale_h_0[16], dmv_scale_v_0[16], dmv_scale_h_1[16], dmv_scale_v_1[16];
+} OVGPUProfInfo;
+
 /* One recorded call; x0/y0 are picture-absolute luma samples ((ctb_x << log2_ctu_s) + x0 in the reference). */
 typedef struct OVGPUMcCmd {
     int16_t x0, y0;
@@ -175,7 +185,7 @@ typedef struct OVGPUMcCmd {
     uint8_t flags;
     int8_t  ref_idx0, ref_idx1;
     uint8_t bcw_idx_plus1;        /* OVMV.bcw_idx_plus1 of mv0 (ctudec.h:281-289)        */
-    uint8_t tool;                 /* 0 = plain translational                             */
+    uint8_t tool;                 /* OVGPU_MC_TOOL_*                                     */
     int32_t mv0_x, mv0_y, mv1_x, mv1_y;   /* 1/16 luma sample                            */
     uint32_t aux;
 } OVGPUMcCmd;
@@ -191,6 +201,9 @@ int  ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBa
 void ovgpu_mc_batch_destroy(OVGPUMcBatch *b);
 /* splits the PUs into <=16x16 work items on the host and copies both lists to the device (async) */
 int  ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds);
+/* same, with the PROF table that OVGPU_MC_TOOL_PROF commands index (may be NULL when nb_prof == 0) */
+int  ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
+                            const OVGPUProfInfo *prof, int nb_prof);
 /* writes the prediction of every command into dst; lmcs may be NULL (no forward reshape). Asynchronous. */
 int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                       const OVGPULmcs *lmcs);

@@ -301,10 +301,14 @@ class McBatch:
         self.p = vp()
         _check(ctx.h, lib().ovgpu_mc_batch_create(ctx.h, int(max_cmds), int(max_items), C.byref(self.p)), "mc_batch_create")
 
-    def upload(self, cmds, ctx=None):
+    def upload(self, cmds, ctx=None, prof=None):
+        """prof: int16 [n][4][16] PROF table (OVGPUProfInfo) indexed by tool-2 commands"""
         cmds = np.ascontiguousarray(cmds, dtype=MC_CMD)
-        self._keep = cmds
-        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds)), "mc_batch_upload")
+        prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
+        self._keep = (cmds, prof)
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_upload2((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds),
+                                                                 vp(prof.ctypes.data) if prof is not None else None,
+                                                                 len(prof) if prof is not None else 0), "mc_batch_upload2")
 
     def run(self, dst, ref_lists, pocs, lmcs=None, ctx=None):
         """ref_lists: [rpl0, rpl1] lists of Picture; pocs likewise."""
@@ -424,8 +428,10 @@ class DbfParams:
 
 
 def mc_nb_items(cmds):
+    """work items a PU list expands to: <=16x16 blocks of plain commands + one per BDOF / PROF command"""
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))
-    return int((((w + 15) >> 4) * ((h + 15) >> 4)).sum())
+    n = ((w + 15) >> 4) * ((h + 15) >> 4)
+    return int(np.where(cmds["tool"] == 0, n, 1).sum())
 
 
 class SaoParams:

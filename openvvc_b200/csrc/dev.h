@@ -139,6 +139,8 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const ty
     if (K::PHASES > 1) { __syncthreads(); K::template phase<1>(a, ovd_smem, st, tid, bx, by, bz); }
     if (K::PHASES > 2) { __syncthreads(); K::template phase<2>(a, ovd_smem, st, tid, bx, by, bz); }
     if (K::PHASES > 3) { __syncthreads(); K::template phase<3>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 4) { __syncthreads(); K::template phase<4>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 5) { __syncthreads(); K::template phase<5>(a, ovd_smem, st, tid, bx, by, bz); }
 }
 
 template <class K>
@@ -172,6 +174,8 @@ static inline void ovd_emulate(const typename K::Args &a, ovd_dim3 grid, size_t 
                 if (K::PHASES > 1) for (int t = 0; t < K::THREADS; t++) K::template phase<1>(a, sm, st[t], t, bx, by, bz);
                 if (K::PHASES > 2) for (int t = 0; t < K::THREADS; t++) K::template phase<2>(a, sm, st[t], t, bx, by, bz);
                 if (K::PHASES > 3) for (int t = 0; t < K::THREADS; t++) K::template phase<3>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 4) for (int t = 0; t < K::THREADS; t++) K::template phase<4>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 5) for (int t = 0; t < K::THREADS; t++) K::template phase<5>(a, sm, st[t], t, bx, by, bz);
             }
 }
 #endif

@@ -9,10 +9,14 @@ static_assert(sizeof(McCmdDev) == sizeof(OVGPUMcCmd) && sizeof(McCmdDev) == 32, 
 
 struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
+    int nb_bdof, nb_prof_items, nb_prof;      // BDOF / PROF work items (appended to the item list), PROF table entries
     McCmdDev *h_cmds, *d_cmds;
-    McItemDev *h_items, *d_items;
+    McItemDev *h_items, *d_items;             // [plain items | BDOF items | PROF items]
+    ProfInfoDev *h_prof, *d_prof;             // max_cmds / 16 + 1 entries (one per affine CU of >= 16 sub-blocks)
+    int max_prof;
     StagingFence fence;
 };
+static_assert(sizeof(ProfInfoDev) == sizeof(OVGPUProfInfo), "PROF table layout");
 
 struct OVGPULmcs {
     OVGPULmcsLuts *h_luts, *d_luts;
@@ -82,7 +86,10 @@ int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBat
     OVGPUMcBatch *b = (OVGPUMcBatch *)calloc(1, sizeof(*b));
     if (!b) return OVGPU_ENOMEM;
     b->max_cmds = max_cmds; b->max_items = max_items; b->device = ctx->device;
-    if (cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
+    b->max_prof = max_cmds / 16 + 1;
+    if (cudaMallocHost(&b->h_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
+        cudaMalloc(&b->d_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
+        cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
         cudaMallocHost(&b->h_items, sizeof(McItemDev) * max_items) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
         cudaMalloc(&b->d_items, sizeof(McItemDev) * max_items) != cudaSuccess) {
@@ -101,28 +108,42 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
     if (b->h_items) cudaFreeHost(b->h_items);
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_items) cudaFree(b->d_items);
+    if (b->h_prof) cudaFreeHost(b->h_prof);
+    if (b->d_prof) cudaFree(b->d_prof);
     fence_destroy(&b->fence);
     free(b);
 }
 
 int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds)
 {
-    if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds) return OVGPU_EINVAL;
-    for (int i = 0; i < nb_cmds; i++) {
-        const OVGPUMcCmd *c = &cmds[i];
-        if (c->log2_w < 2 || c->log2_w > 7 || c->log2_h < 2 || c->log2_h > 7 || c->inter_dir < 1 || c->inter_dir > 3 ||
-            c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->tool != 0)
+    return ovgpu_mc_batch_upload2(ctx, b, cmds, nb_cmds, NULL, 0);
+}
+
+int ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
+                           const OVGPUProfInfo *prof, int nb_prof)
+{
+    if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0 || (nb_prof && !prof)) return OVGPU_EINVAL;
+    if (nb_prof > b->max_prof) return ovgpu_set_error(ctx, OVGPU_EINVAL, "PROF table too large (%d > %d)", nb_prof, b->max_prof);
+    for (int i = 0; i < nb_cmds; i++)
+        if (mc_check_cmd(&cmds[i], nb_prof))
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d malformed", i);
-    }
-    int n_items = mc_count_items(cmds, nb_cmds);
-    if (n_items > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch needs %d items (max %d)", n_items, b->max_items);
+    const int n_plain = mc_count_items(cmds, nb_cmds), n_bdof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_BDOF),
+              n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
+    if (n_plain + n_bdof + n_prof > b->max_items)
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch needs %d items (max %d)", n_plain + n_bdof + n_prof, b->max_items);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     memcpy(b->h_cmds, cmds, sizeof(McCmdDev) * nb_cmds);
-    b->nb_cmds = nb_cmds;
+    if (nb_prof) memcpy(b->h_prof, prof, sizeof(ProfInfoDev) * nb_prof);
+    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof;
     b->nb_items = mc_build_items(b->h_items, cmds, nb_cmds);
+    b->nb_bdof = mc_build_tool_items(b->h_items + b->nb_items, cmds, nb_cmds, OVGPU_MC_TOOL_BDOF);
+    b->nb_prof_items = mc_build_tool_items(b->h_items + b->nb_items + b->nb_bdof, cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
     if (nb_cmds) {
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
-        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(McItemDev) * b->nb_items, cudaMemcpyHostToDevice, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(McItemDev) * (b->nb_items + b->nb_bdof + b->nb_prof_items),
+                                              cudaMemcpyHostToDevice, ctx->stream));
+        if (nb_prof)
+            OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_prof, b->h_prof, sizeof(ProfInfoDev) * nb_prof, cudaMemcpyHostToDevice, ctx->stream));
         OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
     }
     return 0;
@@ -132,7 +153,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                      const OVGPULmcs *lmcs)
 {
     if (!ctx || !dst || !refs || !b) return OVGPU_EINVAL;
-    if (!b->nb_items) return 0;
+    if (!(b->nb_items + b->nb_bdof + b->nb_prof_items)) return 0;
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { PlaneView v = plane_view(dst, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
@@ -144,6 +165,8 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
         const McCmdDev *c = &b->h_cmds[i];
         if (((c->inter_dir & 1) && !refs->rpl[0][c->ref_idx0]) || ((c->inter_dir & 2) && !refs->rpl[1][c->ref_idx1]))
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d references a missing picture", i);
+        if (c->x0 + (1 << c->log2_w) > dst->width || c->y0 + (1 << c->log2_h) > dst->height)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d lies outside the picture", i);
     }
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
@@ -154,9 +177,20 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                 return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture size differs (RPR is not supported)");
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = p->plane[c]; a.refs.pitch[l][i][c] = (int)(p->pitch[c] / 2); }
         }
-    StageScope scope(ctx, OVGPU_STAGE_MC, 1);
-    dim3 grid(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1);
-    OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, grid, McK::SMEM_BYTES, ctx->stream));
+    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0));
+    if (b->nb_items)
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, ctx->stream));
+    if (b->nb_bdof) {
+        McK::Args t = a;
+        t.items = b->d_items + b->nb_items; t.nb_items = b->nb_bdof;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, ctx->stream));
+    }
+    if (b->nb_prof_items) {
+        ProfK::Args t;
+        t.mc = a; t.mc.items = b->d_items + b->nb_items + b->nb_bdof; t.mc.nb_items = b->nb_prof_items; t.prof = b->d_prof;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<ProfK>(t, dim3(OVGPU_CEIL_DIV(b->nb_prof_items, ProfK::WARPS * ProfK::SBS), 1, 1),
+                                                ProfK::SMEM_BYTES, ctx->stream));
+    }
     return 0;
 }
 

@@ -2,23 +2,61 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/ovvc_b200.h"
-#include "mc_kernels.h"
+#include "mc_tools_kernels.h"
 
-// number of <=16x16 work items of a PU list
+// number of <=16x16 work items of the plain (tool 0) commands of a PU list
 static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
 {
     int total = 0;
     for (int i = 0; i < n; i++) {
+        if (cmds[i].tool != 0) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         total += ((w + 15) >> 4) * ((h + 15) >> 4);
     }
     return total;
 }
 
+// BDOF / PROF commands are one work item each (BdofK: one warp per item, ProfK: four items per warp)
+static inline int mc_count_tool_items(const OVGPUMcCmd *cmds, int n, int tool)
+{
+    int total = 0;
+    for (int i = 0; i < n; i++) total += cmds[i].tool == tool;
+    return total;
+}
+
+static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, int n, int tool)
+{
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        if (cmds[i].tool != tool) continue;
+        items[k].cmd = (uint32_t)i; items[k].ox = items[k].oy = 0;
+        items[k].w = (uint8_t)(1 << cmds[i].log2_w); items[k].h = (uint8_t)(1 << cmds[i].log2_h);
+        k++;
+    }
+    return k;
+}
+
+// well-formedness of one command; nb_prof = entries of the PROF table
+static inline int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
+{
+    if (c->log2_w < 2 || c->log2_w > 7 || c->log2_h < 2 || c->log2_h > 7 || c->inter_dir < 1 || c->inter_dir > 3 ||
+        c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->x0 < 0 || c->y0 < 0)
+        return -1;
+    if (c->tool == OVGPU_MC_TOOL_PLAIN) return 0;
+    if (c->tool == OVGPU_MC_TOOL_BDOF)      /* rcn_bdof_mcp_l: bi-predicted luma sub-block of 8 or 16 samples a side */
+        return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 4 && c->log2_h >= 3 && c->log2_h <= 4 &&
+                (c->flags & 3) == OVGPU_MC_LUMA) ? 0 : -1;
+    if (c->tool == OVGPU_MC_TOOL_PROF)      /* rcn_prof_mcp_b_l: 4x4 luma sub-block, table entry must exist */
+        return (c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA && (int)(c->aux >> 8) < nb_prof &&
+                (c->inter_dir == 3 || (c->aux & 3) == c->inter_dir)) ? 0 : -1;
+    return -1;
+}
+
 static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n)
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
+        if (cmds[i].tool != 0) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         for (int oy = 0; oy < h; oy += 16)
             for (int ox = 0; ox < w; ox += 16) {

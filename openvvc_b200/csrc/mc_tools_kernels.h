@@ -1,0 +1,335 @@
+// mc_tools_kernels.h -- BDOF and PROF motion compensation (sm_100a; also compiled by tests/emu, see dev.h).
+//
+// Reference behaviour:
+//   BDOF  rcn_bdof_mcp_l (libovvc/rcn_inter.c:1137-1250): 14-bit predictions of both lists, a one-sample ring taken
+//         from the nearest integer reference samples (extend_bdof_buff, libovvc/rcn_prof_bdof.c:295-345), gradients
+//         (compute_prof_grad :153-171), replicated padding of gradients and predictions (extend_bdof_grad,
+//         rcn_inter.c:840-870), per 4x4 sub-block weights from the 6x6 neighbourhood (derive_bdof_weights :347-422) and
+//         the corrected average (rcn_apply_bdof_subblock :60-99, int16 cast before the clip), forward LMCS.
+//   PROF  rcn_prof_mcp_b_l -> rcn_prof_motion_compensation_b_l / rcn_prof_mcp_l (rcn_inter.c:2865-2919, 1253-1388,
+//         1632-1727): 4x4 affine sub-block with the 6-tap filters, integer-sample ring (extend_prof_buff :173-221),
+//         gradients, per-sample refinement clip(dh*gx + dv*gy, -8192, 8191) (rcn_prof :223-282), average / BCW / uni
+//         rounding, forward LMCS.
+//
+// BdofK: one warp per <=16x16 sub-block.  ProfK: one warp per FOUR 4x4 sub-blocks (lanes = sub-block x list x column
+// while filtering).  Both reuse the column-per-lane interpolation of mc_kernels.h.
+#pragma once
+#include "mc_kernels.h"
+
+#define MC_TOOL_BDOF 1
+#define MC_TOOL_PROF 2
+
+struct ProfInfoDev { int16_t dmv[4][16]; };       // == OVGPUProfInfo: dmv_scale_h_0, v_0, h_1, v_1
+
+// ---- shared helpers ----------------------------------------------------------------------------------------------
+struct McToolCommon {
+    // clip_mv (rcn_inter.c:96-108) of one MV for a block at (x0, y0) of size w x h
+    OVD void clip_mv(int pic_w, int pic_h, int x0, int y0, int w, int h, int &mvx, int &mvy)
+    {
+        mvx = ovd_clamp(mvx, -((w + 3 + x0) << 4), (pic_w + 2 - x0) << 4);
+        mvy = ovd_clamp(mvy, -((h + 3 + y0) << 4), (pic_h + 2 - y0) << 4);
+    }
+    // luma filter rows of mc_cw_l for a fraction (half-pel AMVR row 16, 6-tap set for 4x4 blocks)
+    OVD int filter_row(int frac, int hpel, int small)
+    {
+        if (hpel && !small && frac == 8) frac = 16;
+        return small ? frac + 17 : frac;
+    }
+};
+
+// =================================================================================================================
+struct BdofK {
+    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 5;
+    static const int WARPS = 4;
+    static const int WW = McK::WIN_Y_WORDS, WR = McK::WIN_Y_ROWS;
+    static const int SM_ITEM = 16, SM_WIN = 2 * WR * WW, SM_EX = 2 * 16 * 16 / 2, SM_G = 4 * 16 * 16 / 2, SM_PART = 16 * 2 * 5;
+    static const int SM_WARP = (SM_ITEM + SM_WIN + SM_EX + SM_G + SM_PART) * 4;
+    static const int SMEM_BYTES = WARPS * SM_WARP;
+    typedef McK::Args Args;
+    struct State { int dummy; };
+
+    OVD int floor_log2(unsigned v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
+
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        const int warp = tid >> 5, lane = tid & 31;
+        uint32_t *sm = (uint32_t *)(smem + warp * SM_WARP);
+        int *sit = (int *)sm;
+        uint32_t *win = sm + SM_ITEM;
+        int16_t *ex = (int16_t *)(win + SM_WIN);             // [list][16][16] 14-bit predictions
+        int16_t *G = ex + 2 * 256;                           // [gx0, gy0, gx1, gy1][16][16]
+        int *part = (int *)(G + 4 * 256);                    // [sub-block][half][5]
+        const int item = bx * WARPS + warp;
+
+        if (P == 0) {
+            if (lane == 0) sit[0] = item < a.nb_items;
+            if (item >= a.nb_items) return;
+            const McCmdDev c = a.cmds[a.items[item].cmd];
+            const int w = 1 << c.log2_w, h = 1 << c.log2_h, hpel = (c.flags & MC_HPEL_AMVR) != 0;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                int mvx = r ? c.mv1_x : c.mv0_x, mvy = r ? c.mv1_y : c.mv0_y;
+                McToolCommon::clip_mv(a.pic_w, a.pic_h, c.x0, c.y0, w, h, mvx, mvy);
+                const int ridx = r ? c.ref_idx1 : c.ref_idx0;
+                const uint16_t *pl = a.refs.plane[r][ridx][0];
+                const int pitch = a.refs.pitch[r][ridx][0], nrows = h + 7;
+                const int xs = c.x0 + (mvx >> 4) - 3, ys = c.y0 + (mvy >> 4) - 3, x_al = xs & ~3;
+                uint32_t *wv = win + r * WR * WW;
+                if (lane == 0) {
+                    const int px = mvx & 15, py = mvy & 15;
+                    sit[4 + 4 * r] = xs - x_al;
+                    sit[5 + 4 * r] = McToolCommon::filter_row(px, hpel, 0) | (McToolCommon::filter_row(py, hpel, 0) << 8);
+                    sit[6 + 4 * r] = ((px >> 3) != 0) | (((py >> 3) != 0) << 1);          // ring offsets ext_x / ext_y
+                }
+                if (x_al >= 0 && x_al + 2 * WW <= a.pic_w && ys >= 0 && ys + nrows <= a.pic_h) {
+                    const int cy = lane & 7, ry = lane >> 3;
+                    ovd_u2 v[6];
+                    if (cy < 7) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++)
+                            if (ry + 4 * k < nrows) v[k] = ovd_ld8(pl + (size_t)(ys + ry + 4 * k) * pitch + x_al + 4 * cy);
+#pragma unroll
+                        for (int k = 0; k < 6; k++)
+                            if (ry + 4 * k < nrows) { wv[(ry + 4 * k) * WW + 2 * cy] = v[k].x; wv[(ry + 4 * k) * WW + 2 * cy + 1] = v[k].y; }
+                    }
+                } else {
+                    for (int i = lane; i < nrows * WW; i += 32) {
+                        const int row = i / WW, wd = i - row * WW;
+                        wv[i] = McK::load_pair(pl, pitch, a.pic_w, a.pic_h, x_al + 2 * wd, ys + row);
+                    }
+                }
+            }
+            if (lane == 0) { sit[1] = c.x0; sit[2] = c.y0; sit[3] = w | (h << 8); }
+            return;
+        }
+        if (!sit[0]) return;
+        const int ibx = sit[1], iby = sit[2], iw = sit[3] & 0xff, ih = sit[3] >> 8;
+
+        if (P == 1) {
+            // 14-bit predictions of both lists: lanes 0-15 list 0, 16-31 list 1, one column each
+            const int r = lane >> 4, x = lane & 15, sh1 = a.bitdepth - 8;
+            if (x < iw) {
+                const int o = sit[4 + 4 * r] + x, frl = sit[5 + 4 * r];
+                uint32_t Bh[5], Bv0[4], Bv1[5];
+#pragma unroll
+                for (int j = 0; j < 5; j++) { Bh[j] = mc_cw_l[frl & 0xff][o & 1][j]; Bv1[j] = mc_cw_l[frl >> 8][1][j]; }
+#pragma unroll
+                for (int j = 0; j < 4; j++) Bv0[j] = mc_cw_l[frl >> 8][0][j];
+                const uint32_t *wv = win + r * WR * WW + (o >> 1);
+                int16_t *e = ex + r * 256 + x;
+                if (ih == 16) McK::column<16, 8, 5>(wv, WW, Bh, Bv0, Bv1, sh1, e, 16);
+                else          McK::column<8, 8, 5>(wv, WW, Bh, Bv0, Bv1, sh1, e, 16);
+            }
+            return;
+        }
+
+        // padded 14-bit prediction: interior from ex, ring = integer reference sample << (14 - BD)
+#define BDOF_PINT(r_, x_, y_) (((x_) >= 0 && (x_) < iw && (y_) >= 0 && (y_) < ih) ? (int)ex[(r_) * 256 + (y_) * 16 + (x_)] : ring_sample(a, win, sit, r_, x_, y_))
+        if (P == 2) {
+            // gradients of the interior (compute_prof_grad)
+            for (int i = lane; i < iw * ih; i += 32) {
+                const int x = i % iw, y = i / iw;
+#pragma unroll
+                for (int r = 0; r < 2; r++) {
+                    const int gx = ((BDOF_PINT(r, x + 1, y) - 8192) >> 6) - ((BDOF_PINT(r, x - 1, y) - 8192) >> 6);
+                    const int gy = ((BDOF_PINT(r, x, y + 1) - 8192) >> 6) - ((BDOF_PINT(r, x, y - 1) - 8192) >> 6);
+                    G[(2 * r) * 256 + y * 16 + x] = (int16_t)gx;
+                    G[(2 * r + 1) * 256 + y * 16 + x] = (int16_t)gy;
+                }
+            }
+            return;
+        }
+        if (P == 3) {
+            // partial sums of derive_bdof_weights: lane = (sub-block, half of the 6 rows); padded reads = clamped coordinates
+            const int sb = lane >> 1, half = lane & 1, nsx = iw >> 2, nsb = nsx * (ih >> 2);
+            if (sb < nsb) {
+                const int sx = (sb % nsx) * 4, sy = (sb / nsx) * 4;
+                int s_ax = 0, s_ay = 0, s_dx = 0, s_dy = 0, s_sign = 0;
+                for (int i = 3 * half; i < 3 * half + 3; i++) {
+                    const int y = ovd_clamp(sy + i - 1, 0, ih - 1);
+#pragma unroll
+                    for (int j = 0; j < 6; j++) {
+                        const int x = ovd_clamp(sx + j - 1, 0, iw - 1), o = y * 16 + x;
+                        const int ax = (G[o] + G[2 * 256 + o]) >> 1, ay = (G[256 + o] + G[3 * 256 + o]) >> 1;
+                        const int dr = ((ex[256 + o] - 8192) >> 4) - ((ex[o] - 8192) >> 4);
+                        s_ax += ax < 0 ? -ax : ax; s_ay += ay < 0 ? -ay : ay;
+                        s_sign += ay < 0 ? -ax : (ay == 0 ? 0 : ax);
+                        s_dx += ax < 0 ? -dr : (ax == 0 ? 0 : dr);
+                        s_dy += ay < 0 ? -dr : (ay == 0 ? 0 : dr);
+                    }
+                }
+                int *p = part + (sb * 2 + half) * 5;
+                p[0] = s_ax; p[1] = s_ay; p[2] = s_dx; p[3] = s_dy; p[4] = s_sign;
+            }
+            return;
+        }
+        if (P == 4) {
+            // weights of the two sub-blocks a lane's 8 samples fall in, corrected average, LMCS, store
+            const int y = lane >> 1, x0 = (lane & 1) * 8;
+            if (y >= ih || x0 >= iw) return;
+            const int nsx = iw >> 2, shift = 15 - a.bitdepth, off = 1 << (shift - 1), maxv = (1 << a.bitdepth) - 1;
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int sb = (y >> 2) * nsx + (x0 >> 2) + q;
+                const int *p0 = part + sb * 10, *p1 = p0 + 5;
+                const int s_ax = p0[0] + p1[0], s_ay = p0[1] + p1[1], s_dx = p0[2] + p1[2], s_dy = p0[3] + p1[3], s_sign = p0[4] + p1[4];
+                int wx = 0, wy = 0;
+                if (s_ax) wx = ovd_clamp((s_dx << 2) >> floor_log2((unsigned)s_ax), -15, 15);
+                if (s_ay) {
+                    int xo = 0;
+                    if (wx) { const int hi = s_sign >> 12, lo = s_sign & 4095; xo = (((wx * hi) << 12) + (wx * lo)) >> 1; }
+                    wy = ovd_clamp(((s_dy << 2) - xo) >> floor_log2((unsigned)s_ay), -15, 15);
+                }
+                int v[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = y * 16 + x0 + 4 * q + k;
+                    const int b = wx * (G[i] - G[2 * 256 + i]) + wy * (G[256 + i] - G[3 * 256 + i]);
+                    v[k] = ovd_clamp((int)(int16_t)((ex[i] + ex[256 + i] + b + off) >> shift), 0, maxv);
+                    if (a.lmcs_fwd) v[k] = a.lmcs_fwd[v[k]];
+                }
+                o[2 * q] = (uint32_t)v[0] | ((uint32_t)v[1] << 16); o[2 * q + 1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+            }
+            uint16_t *d = a.dst[0] + (size_t)(iby + y) * a.dst_pitch[0] + ibx + x0;
+            ovd_u2 r0, r1;                                                     // block positions are multiples of 4 samples
+            r0.x = o[0]; r0.y = o[1]; ovd_st8(d, r0);
+            r1.x = o[2]; r1.y = o[3]; ovd_st8(d + 4, r1);
+        }
+#undef BDOF_PINT
+    }
+
+    // integer reference sample of the ring at padded position (x, y) in -1..w / -1..h (extend_bdof_buff)
+    OVD int ring_sample(const Args &a, const uint32_t *win, const int *sit, int r, int x, int y)
+    {
+        const int ext = sit[6 + 4 * r];
+        const int col = sit[4 + 4 * r] + 3 + x + (ext & 1), row = 3 + y + (ext >> 1);
+        const uint32_t wd = win[(r * WR + row) * WW + (col >> 1)];
+        return (int)(int16_t)(((col & 1) ? wd >> 16 : wd & 0xffff) << (14 - a.bitdepth));
+    }
+};
+
+// =================================================================================================================
+struct ProfK {
+    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 4;
+    static const int WARPS = 4, SBS = 4;                     // 4 sub-blocks (commands) per warp
+    static const int WW = 8, WR = 11;                        // 16 samples x 11 rows per sub-block and list
+    static const int SM_ITEM = SBS * 16, SM_WIN = SBS * 2 * WR * WW, SM_EX = SBS * 2 * 16 / 2;
+    static const int SM_WARP = (SM_ITEM + SM_WIN + 2 * SM_EX) * 4;
+    static const int SMEM_BYTES = WARPS * SM_WARP;
+
+    struct Args {
+        McK::Args mc;
+        const ProfInfoDev *prof;
+    };
+    struct State { int dummy; };
+
+    template <int P>
+    OVD void phase(const Args &aa, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        const McK::Args &a = aa.mc;
+        const int warp = tid >> 5, lane = tid & 31;
+        uint32_t *sm = (uint32_t *)(smem + warp * SM_WARP);
+        int *sit = (int *)sm;                                // [sub-block][16]
+        uint32_t *win = sm + SM_ITEM;                        // [sub-block][list][row][word]
+        int16_t *ex = (int16_t *)(win + SM_WIN);             // [sub-block][list][4][4] 14-bit predictions
+        int16_t *ex2 = ex + SBS * 2 * 16;                    // refined predictions
+        const int sb = lane >> 3, item = (bx * WARPS + warp) * SBS + sb;
+        int *si = sit + sb * 16;
+
+        if (P == 0) {
+            const int r = (lane >> 2) & 1, cc = lane & 3;
+            if ((lane & 7) == 0) si[0] = item < a.nb_items;
+            if (item >= a.nb_items) return;
+            const McCmdDev c = a.cmds[a.items[item].cmd];
+            const int used = (c.inter_dir >> r) & 1;
+            int mvx = r ? c.mv1_x : c.mv0_x, mvy = r ? c.mv1_y : c.mv0_y;
+            McToolCommon::clip_mv(a.pic_w, a.pic_h, c.x0, c.y0, 4, 4, mvx, mvy);
+            const int xs = c.x0 + (mvx >> 4) - 3, ys = c.y0 + (mvy >> 4) - 3, x_al = xs & ~3;
+            if (cc == 0) {
+                const int px = mvx & 15, py = mvy & 15;
+                si[4 + 4 * r] = xs - x_al;
+                si[5 + 4 * r] = McToolCommon::filter_row(px, 0, 1) | (McToolCommon::filter_row(py, 0, 1) << 8);
+                si[6 + 4 * r] = ((px >> 3) != 0) | (((py >> 3) != 0) << 1);
+                if (r == 0) { si[1] = c.x0; si[2] = c.y0; si[3] = c.inter_dir | ((c.aux & 3) << 4) | (c.bcw_idx_plus1 << 8) | ((c.aux >> 8) << 12); }
+            }
+            if (!used) return;
+            const int ridx = r ? c.ref_idx1 : c.ref_idx0;
+            const uint16_t *pl = a.refs.plane[r][ridx][0];
+            const int pitch = a.refs.pitch[r][ridx][0];
+            uint32_t *wv = win + (sb * 2 + r) * WR * WW;
+            if (x_al >= 0 && x_al + 2 * WW <= a.pic_w && ys >= 0 && ys + WR <= a.pic_h) {
+                ovd_u2 v[WR];
+#pragma unroll
+                for (int k = 0; k < WR; k++) v[k] = ovd_ld8(pl + (size_t)(ys + k) * pitch + x_al + 4 * cc);
+#pragma unroll
+                for (int k = 0; k < WR; k++) { wv[k * WW + 2 * cc] = v[k].x; wv[k * WW + 2 * cc + 1] = v[k].y; }
+            } else {
+                for (int i = cc; i < WR * WW; i += 4) {
+                    const int row = i / WW, wd = i - row * WW;
+                    wv[i] = McK::load_pair(pl, pitch, a.pic_w, a.pic_h, x_al + 2 * wd, ys + row);
+                }
+            }
+            return;
+        }
+        if (!si[0]) return;
+        const int info = si[3], inter_dir = info & 3, prof_dir = (info >> 4) & 3, bcw_raw = (info >> 8) & 15, tab = info >> 12;
+
+        if (P == 1) {
+            // 4x4 prediction with the 6-tap set: lane = (sub-block, list, column)
+            const int r = (lane >> 2) & 1, x = lane & 3, sh1 = a.bitdepth - 8;
+            if (!((inter_dir >> r) & 1)) return;
+            const int o = si[4 + 4 * r] + x, frl = si[5 + 4 * r];
+            uint32_t Bh[5], Bv0[4], Bv1[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) { Bh[j] = mc_cw_l[frl & 0xff][o & 1][j]; Bv1[j] = mc_cw_l[frl >> 8][1][j]; }
+#pragma unroll
+            for (int j = 0; j < 4; j++) Bv0[j] = mc_cw_l[frl >> 8][0][j];
+            McK::column<4, 8, 5>(win + (sb * 2 + r) * WR * WW + (o >> 1), WW, Bh, Bv0, Bv1, sh1, ex + (sb * 2 + r) * 16 + x, 4);
+            return;
+        }
+        if (P == 2) {
+            // gradients + refinement: lane = (sub-block, list, row), 4 samples each
+            const int r = (lane >> 2) & 1, y = lane & 3;
+            if (!((inter_dir >> r) & 1)) return;
+            const int apply = inter_dir == 3 ? (prof_dir >> r) & 1 : 1;       // uni-prediction always refines (rcn_prof_mcp_l)
+            const int16_t *e = ex + (sb * 2 + r) * 16;
+            const int16_t *dh = aa.prof[tab].dmv[2 * r], *dv = aa.prof[tab].dmv[2 * r + 1];
+            const int ext = si[6 + 4 * r], c0 = si[4 + 4 * r] + 3 + (ext & 1), r0 = 3 + (ext >> 1), sh = 14 - a.bitdepth;
+            const uint32_t *wv = win + (sb * 2 + r) * WR * WW;
+#define PROF_RING(x_, y_) ((int)(int16_t)((((c0 + (x_)) & 1 ? wv[(r0 + (y_)) * WW + ((c0 + (x_)) >> 1)] >> 16 : wv[(r0 + (y_)) * WW + ((c0 + (x_)) >> 1)] & 0xffff)) << sh))
+#define PROF_PINT(x_, y_) (((x_) >= 0 && (x_) < 4 && (y_) >= 0 && (y_) < 4) ? (int)e[(y_) * 4 + (x_)] : PROF_RING(x_, y_))
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                int v = e[y * 4 + x];
+                if (apply) {
+                    const int gx = (int16_t)(((PROF_PINT(x + 1, y) - 8192) >> 6) - ((PROF_PINT(x - 1, y) - 8192) >> 6));
+                    const int gy = (int16_t)(((PROF_PINT(x, y + 1) - 8192) >> 6) - ((PROF_PINT(x, y - 1) - 8192) >> 6));
+                    v = (int16_t)(v + ovd_clamp(dh[4 * y + x] * gx + dv[4 * y + x] * gy, -8192, 8191));
+                }
+                ex2[(sb * 2 + r) * 16 + y * 4 + x] = (int16_t)v;
+            }
+#undef PROF_PINT
+#undef PROF_RING
+            return;
+        }
+        if (P == 3) {
+            // combine + LMCS + store: lane = (sub-block, row, half): 2 samples
+            const int y = (lane >> 1) & 3, x0 = (lane & 1) * 2, maxv = (1 << a.bitdepth) - 1;
+            const int bcw = (bcw_raw == 0 || bcw_raw == 3) ? 0 : bcw_raw;
+            const int w1 = bcw == 1 ? -2 : bcw == 2 ? 3 : bcw == 4 ? 5 : 10;
+            const int16_t *e0 = ex2 + (sb * 2 + (inter_dir == 2 ? 1 : 0)) * 16, *e1 = ex2 + (sb * 2 + 1) * 16;
+            int v[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const int i = y * 4 + x0 + k;
+                v[k] = McK::combine(e0[i], inter_dir == 3 ? e1[i] : 0, inter_dir == 3 ? 2 : 1, bcw, w1, a.bitdepth, maxv);
+                if (a.lmcs_fwd) v[k] = a.lmcs_fwd[v[k]];
+            }
+            *(uint32_t *)(a.dst[0] + (size_t)(si[2] + y) * a.dst_pitch[0] + si[1] + x0) = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+        }
+    }
+};

@@ -200,6 +200,82 @@ def mc_commands(w, h, seed=1004, log2_ctu=7, n_refs=2, p_bi=0.7, mv_range=64, mi
     return cmds
 
 
+MC_TOOL_PLAIN, MC_TOOL_BDOF, MC_TOOL_PROF = 0, 1, 2
+
+
+def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_log2=3, p_bdof=0.3, p_affine=0.2):
+    """PU list with BDOF and affine/PROF coding units mixed in (25 % of eligible bi blocks BDOF, 15 %
+    affine 4x4).  Returns (cmds, prof_table): BDOF CUs become <=16x16 luma sub-block commands (tool 1) + one chroma
+    command; affine CUs become 4x4 luma commands (tool 2 with PROF, or plain 6-tap) + 8x8-luma chroma commands with the
+    averaged MVs (drv_affine_mvp.c:3380-3410); prof_table[n] = (dmv_scale_h_0, v_0, h_1, v_1) of affine CU n."""
+    rng = np.random.default_rng(seed)
+    blocks = partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(7, log2_ctu))
+    out, prof = [], []
+
+    def new(x, y, lw, lh, inter_dir, flags, r0, r1, mv0, mv1, tool=0, bcw=0, aux=0):
+        c = np.zeros((), dtype=MC_CMD)
+        c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
+        c["inter_dir"], c["flags"], c["ref_idx0"], c["ref_idx1"], c["tool"], c["bcw_idx_plus1"], c["aux"] = inter_dir, flags, r0, r1, tool, bcw, aux
+        c["mv0_x"], c["mv0_y"], c["mv1_x"], c["mv1_y"] = mv0[0], mv0[1], mv1[0], mv1[1]
+        out.append(c)
+
+    def rmv(far=False):
+        if far:
+            return int(rng.integers(-(w + 100), w + 100)) * 16 + int(rng.integers(0, 16)), int(rng.integers(-(h + 100), h + 100)) * 16 + int(rng.integers(0, 16))
+        mx, my = int(rng.integers(-mv_range * 16, mv_range * 16 + 1)), int(rng.integers(-mv_range * 16, mv_range * 16 + 1))
+        if rng.random() < 0.2:
+            mx &= ~15
+        if rng.random() < 0.2:
+            my &= ~15
+        return mx, my
+
+    for (x, y, lw, lh) in blocks:
+        r0, r1 = int(rng.integers(0, n_refs)), int(rng.integers(0, n_refs))
+        far = rng.random() < 0.06
+        mv0, mv1 = rmv(far), rmv(far)
+        hpel = 4 if rng.random() < 0.05 else 0
+        if hpel:
+            mv0 = (mv0[0] & ~7, mv0[1] & ~7); mv1 = (mv1[0] & ~7, mv1[1] & ~7)
+        kind = rng.random()
+        if lw >= 3 and lh >= 3 and lw + lh >= 7 and kind < p_bdof:
+            # BDOF CU (vcl_coding_unit.c:2648-2672): luma per <= 16x16 sub-block, chroma for the whole CU
+            sw, sh = min(lw, 4), min(lh, 4)
+            for oy in range(0, 1 << lh, 1 << sh):
+                for ox in range(0, 1 << lw, 1 << sw):
+                    new(x + ox, y + oy, sw, sh, 3, 1 | hpel, r0, r1, mv0, mv1, tool=MC_TOOL_BDOF)
+            new(x, y, lw, lh, 3, 2 | hpel, r0, r1, mv0, mv1)
+        elif lw >= 4 and lh >= 4 and kind < p_bdof + p_affine:
+            # affine CU: one MV per 4x4 from a random 6-parameter model, PROF on the lists flagged in prof_dir
+            inter_dir = int(rng.choice([1, 2, 3]))
+            prof_dir = 0 if rng.random() < 0.25 else (inter_dir if rng.random() < 0.7 else int(rng.integers(1, 4)) & inter_dir)
+            if inter_dir != 3 and prof_dir:
+                prof_dir = inter_dir
+            bcw = int(rng.choice([1, 2, 4, 5])) if (inter_dir == 3 and rng.random() < 0.1) else 0
+            mdl = [(rmv(far), rng.integers(-6, 7, size=4)) for _ in range(2)]
+            prof.append(rng.integers(-32, 32, size=(4, 16)).astype(np.int16))
+            nw, nh = (1 << lw) >> 2, (1 << lh) >> 2
+            mvs = [[[(int(b[0] + a[0] * i + a[1] * j), int(b[1] + a[2] * i + a[3] * j)) for i in range(nw)] for j in range(nh)] for (b, a) in mdl]
+            for j in range(nh):
+                for i in range(nw):
+                    new(x + 4 * i, y + 4 * j, 2, 2, inter_dir, 1, r0, r1, mvs[0][j][i], mvs[1][j][i],
+                        tool=MC_TOOL_PROF if prof_dir else MC_TOOL_PLAIN, bcw=bcw, aux=(prof_dir | ((len(prof) - 1) << 8)) if prof_dir else 0)
+            for j in range(0, nh, 2):
+                for i in range(0, nw, 2):
+                    avg = []
+                    for l in range(2):
+                        ax = mvs[l][j][i][0] + mvs[l][j + 1][i + 1][0]; ay = mvs[l][j][i][1] + mvs[l][j + 1][i + 1][1]
+                        ax += ax < 0; ay += ay < 0
+                        avg.append((ax >> 1, ay >> 1))
+                    new(x + 4 * i, y + 4 * j, 3, 3, inter_dir, 2, r0, r1, avg[0], avg[1], bcw=bcw)
+        else:
+            bi = rng.random() < 0.7 and lw + lh >= 6
+            new(x, y, lw, lh, 3 if bi else int(rng.integers(1, 3)), 3 | hpel, r0, r1, mv0, mv1,
+                bcw=int(rng.choice([1, 2, 4, 5])) if (bi and rng.random() < 0.05) else 0)
+    cmds = np.array(out, dtype=MC_CMD)
+    prof_tab = np.stack(prof) if prof else np.zeros((1, 4, 16), np.int16)
+    return cmds, np.ascontiguousarray(prof_tab, dtype=np.int16)
+
+
 def lmcs_data(seed=1007):
     rng = np.random.default_rng(seed)
     min_idx = int(rng.integers(0, 4)); dmax = int(rng.integers(0, 4))

@@ -96,6 +96,13 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
 #define OVO_MC_LUMA      1
 #define OVO_MC_CHROMA    2
 #define OVO_MC_HPEL_AMVR 4      /* inter_ctx->prec_amvr == MV_PRECISION_HALF (rcn_inter.c:572) */
+#define OVO_MC_TOOL_PLAIN 0     /* rcn_mcp_b / rcn_mcp_b_l / rcn_mcp_b_c                                             */
+#define OVO_MC_TOOL_BDOF  1     /* rcn_bdof_mcp_l (rcn_inter.c:1137): one <= 16x16 luma sub-block, bi-prediction      */
+#define OVO_MC_TOOL_PROF  2     /* rcn_prof_mcp_b_l (rcn_inter.c:2865): one 4x4 affine luma sub-block;                 *
+                                 * aux = prof_dir (bits 0-1) | index into the PROF table << 8                          */
+typedef struct OVOProfInfo {    /* struct PROFInfo, rcn_inter.c:1128-1134 */
+    int16_t dmv_scale_h_0[16], dmv_scale_v_0[16], dmv_scale_h_1[16], dmv_scale_v_1[16];
+} OVOProfInfo;
 typedef struct OVOMcCmd {
     int16_t x0, y0;
     uint8_t log2_w, log2_h;
@@ -103,7 +110,7 @@ typedef struct OVOMcCmd {
     uint8_t flags;
     int8_t  ref_idx0, ref_idx1;
     uint8_t bcw_idx_plus1;
-    uint8_t tool;               /* 0 plain (others reserved for BDOF/DMVR/PROF commands) */
+    uint8_t tool;               /* OVO_MC_TOOL_*                                                          */
     int32_t mv0_x, mv0_y, mv1_x, mv1_y;   /* 1/16 luma sample */
     uint32_t aux;
 } OVOMcCmd;
@@ -117,6 +124,10 @@ typedef struct OVOMcRefs {
 /* lmcs_fwd_lut: 1<<bitdepth entries or NULL (rcn_lmcs_reshape_forward, rcn_lmcs.c:287) */
 void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut);
+/* same with the PROF table that tool-2 commands index */
+void ovo_mc_picture2(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
+                     const OVOProfInfo *prof_tab);
 
 /* ---- LMCS ------------------------------------------------------------------------------------------- */
 typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */

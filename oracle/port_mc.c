@@ -116,13 +116,158 @@ static void pu_pred14(int16_t *buf, const OVOMcRefs *refs, int list, int ref_idx
     }
 }
 
+/* ---------------------------------------------------------------------------------------------------
+ * BDOF (rcn_bdof_mcp_l, rcn_inter.c:1137-1250; libovvc/rcn_prof_bdof.c:60-99, 295-492) and PROF
+ * (rcn_prof_mcp_b_l / rcn_prof_motion_compensation_b_l / rcn_prof_mcp_l, rcn_inter.c:1253-1388, 1632-1727,
+ * 2865-2919; rcn_prof_bdof.c:101-282)
+ * ------------------------------------------------------------------------------------------------- */
+enum { PS = 20 };      /* stride of the padded 14-bit prediction / gradient blocks (<= 16 + 2) */
+
+/* 14-bit prediction of a w x h luma block into the interior of a padded block, plus the one-sample ring taken from
+ * the nearest INTEGER reference samples (extend_bdof_buff / extend_prof_buff, rcn_prof_bdof.c:295-345, 173-221) */
+static void padded_pred14(int16_t *P, const OVOMcRefs *refs, int list, int ref_idx, int pic_w, int pic_h,
+                          int x0, int y0, int w, int h, MV mv, int hpel, int bitdepth)
+{
+    RefPlane r = { refs->plane[list][ref_idx][0], refs->stride[list][ref_idx][0], pic_w, pic_h };
+    mv = clip_mv(x0, y0, pic_w, pic_h, w, h, mv);
+    int px = mv.x & 15, py = mv.y & 15, small = (w == 4 && h == 4);
+    if (hpel && !small) { if (px == 8) px = 16; if (py == 8) py = 16; }
+    const int8_t *fx = px ? (small ? mc_filt_l4[px - 1] : mc_filt_l[px - 1]) : NULL;
+    const int8_t *fy = py ? (small ? mc_filt_l4[py - 1] : mc_filt_l[py - 1]) : NULL;
+    int xi = x0 + (mv.x >> 4), yi = y0 + (mv.y >> 4);
+    pred14(P + PS + 1, PS, &r, xi, yi, w, h, fx, fy, 8, bitdepth);
+    int ex = (px >> 3) != 0, ey = (py >> 3) != 0, sh = 14 - bitdepth;
+    for (int i = 0; i < w + 2; i++) {
+        P[i] = (int16_t)(rpx(&r, xi - 1 + i + ex, yi - 1 + ey) << sh);
+        P[(h + 1) * PS + i] = (int16_t)(rpx(&r, xi - 1 + i + ex, yi + h + ey) << sh);
+    }
+    for (int j = 0; j < h; j++) {
+        P[(j + 1) * PS] = (int16_t)(rpx(&r, xi - 1 + ex, yi + j + ey) << sh);
+        P[(j + 1) * PS + w + 1] = (int16_t)(rpx(&r, xi + w + ex, yi + j + ey) << sh);
+    }
+}
+
+/* compute_prof_grad, rcn_prof_bdof.c:153-171: gradients of the interior from the padded block */
+static void pad_grad(int16_t *gx, int16_t *gy, const int16_t *P, int w, int h)
+{
+    for (int y = 1; y <= h; y++)
+        for (int x = 1; x <= w; x++) {
+            gy[y * PS + x] = (int16_t)(((P[(y + 1) * PS + x] - 8192) >> 6) - ((P[(y - 1) * PS + x] - 8192) >> 6));
+            gx[y * PS + x] = (int16_t)(((P[y * PS + x + 1] - 8192) >> 6) - ((P[y * PS + x - 1] - 8192) >> 6));
+        }
+}
+
+/* extend_bdof_grad, rcn_inter.c:840-870: ring = nearest interior sample (columns first, then whole rows) */
+static void pad_replicate(int16_t *B, int w, int h)
+{
+    for (int y = 1; y <= h; y++) { B[y * PS] = B[y * PS + 1]; B[y * PS + w + 1] = B[y * PS + w]; }
+    for (int x = 0; x < w + 2; x++) { B[x] = B[PS + x]; B[(h + 1) * PS + x] = B[h * PS + x]; }
+}
+
+static int floor_log2u(unsigned v) { int n = -1; while (v) { v >>= 1; n++; } return n; }
+
+static void bdof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVOMcCmd *c, int pic_w, int pic_h, int bitdepth)
+{
+    int w = 1 << c->log2_w, h = 1 << c->log2_h, maxv = (1 << bitdepth) - 1;
+    int16_t P0[PS * PS], P1[PS * PS], gx0[PS * PS], gy0[PS * PS], gx1[PS * PS], gy1[PS * PS];
+    MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
+    int hpel = (c->flags & OVO_MC_HPEL_AMVR) != 0;
+    padded_pred14(P0, refs, 0, c->ref_idx0, pic_w, pic_h, c->x0, c->y0, w, h, mv0, hpel, bitdepth);
+    padded_pred14(P1, refs, 1, c->ref_idx1, pic_w, pic_h, c->x0, c->y0, w, h, mv1, hpel, bitdepth);
+    pad_grad(gx0, gy0, P0, w, h); pad_grad(gx1, gy1, P1, w, h);
+    pad_replicate(gx0, w, h); pad_replicate(gy0, w, h); pad_replicate(gx1, w, h); pad_replicate(gy1, w, h);
+    pad_replicate(P0, w, h); pad_replicate(P1, w, h);          /* "reference padding overwrite", rcn_inter.c:1233-1235 */
+    int shift = 15 - bitdepth, off = 1 << (shift - 1);
+    for (int sy = 0; sy < h; sy += 4)
+        for (int sx = 0; sx < w; sx += 4) {
+            /* derive_bdof_weights over the 6x6 neighbourhood, rcn_prof_bdof.c:347-422 */
+            int sum_ax = 0, sum_ay = 0, sum_dx = 0, sum_dy = 0, sum_sign = 0, wx = 0, wy = 0;
+            for (int i = 0; i < 6; i++)
+                for (int j = 0; j < 6; j++) {
+                    int o = (sy + i) * PS + sx + j;
+                    int ax = (gx0[o] + gx1[o]) >> 1, ay = (gy0[o] + gy1[o]) >> 1;
+                    int dr = ((P1[o] - 8192) >> 4) - ((P0[o] - 8192) >> 4);
+                    sum_ax += abs(ax); sum_ay += abs(ay);
+                    sum_sign += ay < 0 ? -ax : (ay == 0 ? 0 : ax);
+                    sum_dx += ax < 0 ? -dr : (ax == 0 ? 0 : dr);
+                    sum_dy += ay < 0 ? -dr : (ay == 0 ? 0 : dr);
+                }
+            if (sum_ax) wx = clipi((sum_dx << 2) >> floor_log2u(sum_ax), -15, 15);
+            if (sum_ay) {
+                int xo = 0;
+                if (wx) { int hi = sum_sign >> 12, lo = sum_sign & 4095; xo = (((wx * hi) << 12) + (wx * lo)) >> 1; }
+                wy = clipi(((sum_dy << 2) - xo) >> floor_log2u(sum_ay), -15, 15);
+            }
+            for (int y = 0; y < 4; y++)                         /* rcn_apply_bdof_subblock, :60-99 */
+                for (int x = 0; x < 4; x++) {
+                    int o = (sy + y + 1) * PS + sx + x + 1;
+                    int b = wx * (gx0[o] - gx1[o]) + wy * (gy0[o] - gy1[o]);
+                    int16_t v = (int16_t)((P0[o] + P1[o] + b + off) >> shift);
+                    d[(size_t)(sy + y) * stride + sx + x] = (uint16_t)clipi(v, 0, maxv);
+                }
+        }
+}
+
+static void prof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVOMcCmd *c, const OVOProfInfo *pi,
+                       int pic_w, int pic_h, int bitdepth)
+{
+    int maxv = (1 << bitdepth) - 1, prof_dir = c->aux & 3, hpel = (c->flags & OVO_MC_HPEL_AMVR) != 0;
+    int16_t val[2][16];
+    for (int l = 0; l < 2; l++) {
+        if (!(c->inter_dir & (1 << l))) continue;
+        int16_t P[PS * PS], gx[PS * PS], gy[PS * PS];
+        MV mv = l ? (MV){ c->mv1_x, c->mv1_y } : (MV){ c->mv0_x, c->mv0_y };
+        padded_pred14(P, refs, l, l ? c->ref_idx1 : c->ref_idx0, pic_w, pic_h, c->x0, c->y0, 4, 4, mv, hpel, bitdepth);
+        pad_grad(gx, gy, P, 4, 4);
+        const int16_t *dh = l ? pi->dmv_scale_h_1 : pi->dmv_scale_h_0, *dv = l ? pi->dmv_scale_v_1 : pi->dmv_scale_v_0;
+        int apply = c->inter_dir == 3 ? (prof_dir >> l) & 1 : 1;     /* uni-prediction always refines (rcn_prof_mcp_l) */
+        for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 4; x++) {
+                int o = (y + 1) * PS + x + 1, v = P[o];
+                if (apply) v = (int16_t)(v + clipi(dh[4 * y + x] * gx[o] + dv[4 * y + x] * gy[o], -8192, 8191));   /* rcn_prof, :223-282 */
+                val[l][4 * y + x] = (int16_t)v;
+            }
+    }
+    int def = (c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3), w1 = def ? 0 : bcw_w[c->bcw_idx_plus1 - 1];
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++) {
+            int v, k = 4 * y + x;
+            if (c->inter_dir == 3) {
+                if (def) v = (val[0][k] + val[1][k] + (1 << (14 - bitdepth))) >> (15 - bitdepth);      /* tmp_prof_mrg, :101-123 */
+                else     v = (val[1][k] * w1 + val[0][k] * (8 - w1) + (1 << (16 - bitdepth))) >> (17 - bitdepth);
+            } else {
+                v = (int16_t)((val[c->inter_dir == 2][k] + (1 << (13 - bitdepth))) >> (14 - bitdepth));
+            }
+            d[(size_t)y * stride + x] = (uint16_t)clipi(v, 0, maxv);
+        }
+}
+
 void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut)
+{
+    ovo_mc_picture2(dst, dst_stride, pic_w, pic_h, bitdepth, refs, cmds, nb_cmds, lmcs_fwd_lut, NULL);
+}
+
+void ovo_mc_picture2(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
+                     const OVOProfInfo *prof_tab)
 {
     int16_t *p0 = malloc(2 * 128 * 128 * sizeof(int16_t)), *p1 = p0 + 128 * 128;   /* per call: thread-safe */
     int maxv = (1 << bitdepth) - 1;
     for (int i = 0; i < nb_cmds; i++) {
         const OVOMcCmd *c = &cmds[i];
+        if (c->tool == OVO_MC_TOOL_BDOF || c->tool == OVO_MC_TOOL_PROF) {
+            uint16_t *d = dst[0] + (size_t)c->y0 * dst_stride[0] + c->x0;
+            if (c->tool == OVO_MC_TOOL_BDOF) bdof_block(d, dst_stride[0], refs, c, pic_w, pic_h, bitdepth);
+            else prof_block(d, dst_stride[0], refs, c, &prof_tab[c->aux >> 8], pic_w, pic_h, bitdepth);
+            if (lmcs_fwd_lut)
+                for (int y = 0; y < (1 << c->log2_h); y++)
+                    for (int x = 0; x < (1 << c->log2_w); x++) {
+                        uint16_t *q = &d[(size_t)y * dst_stride[0] + x];
+                        *q = lmcs_fwd_lut[*q & maxv];
+                    }
+            continue;
+        }
         MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
         /* check_identical_motion, rcn_inter.c:256-267 (POCs compared as uint16_t) */
         int identical = c->inter_dir == 3 &&

@@ -223,16 +223,19 @@ def make_mc_refs(ref_lists, pocs):
     return r, keep
 
 
-def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl="port", lmcs=None):
-    """Writes the predictions of all commands into dst_planes (in place) and returns them."""
+def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl="port", lmcs=None, prof=None, simd=1):
+    """Writes the predictions of all commands into dst_planes (in place) and returns them.
+    prof: int16 array [n][4][16] (struct PROFInfo: dmv_scale_h_0, v_0, h_1, v_1) indexed by tool-2 commands."""
     h, w = dst_planes[0].shape
     cmds = np.ascontiguousarray(cmds, dtype=McCmd)
     refs, keep = make_mc_refs(ref_lists, pocs)
     dst, ds = _planes_arg(dst_planes)
+    prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
+    pp = prof.ctypes.data_as(C.c_void_p) if prof is not None else None
     if impl == "port":
         lut = lmcs.np("fwd_lut").ctypes.data_as(u16p) if lmcs is not None else None
-        port().ovo_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut)
+        port().ovo_mc_picture2(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut, pp)
     else:
-        ref().ovref_mc_picture(dst, ds, w, h, log2_ctu, bitdepth, 1, C.byref(refs), cmds.ctypes.data_as(C.c_void_p),
-                               len(cmds), C.byref(lmcs) if lmcs is not None else None)
+        ref().ovref_mc_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(refs), cmds.ctypes.data_as(C.c_void_p),
+                               len(cmds), pp, C.byref(lmcs) if lmcs is not None else None)
     return dst_planes

@@ -237,6 +237,11 @@ ovref_sao_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int
 #include "ovdpb.h"
 #include "rcn_lmcs.h"
 
+void rcn_init_mc_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_prof_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_bdof_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_dmvr_functions_10(struct RCNFunctions *rcn_func);
+
 static void harness_no_synchro(const OVPicture *const ref_pic, int a, int b, int c, int d) { (void)ref_pic; (void)a; (void)b; (void)c; (void)d; }
 
 void
@@ -263,7 +268,7 @@ ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
 
 void
 ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
-                 int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds,
+                 int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const OVOProfInfo *prof_tab,
                  const OVOLmcsLuts *lmcs)
 {
     OVCTUDec *c;
@@ -282,7 +287,12 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
     c->pic_w = pic_w;
     c->pic_h = pic_h;
     rcn_init_functions(&c->rcn_funcs, 0, 1, 0, lmcs != NULL, bitdepth);
-    (void)simd;
+    if (!simd && bitdepth == 10) {      /* scalar C templates = arithmetic of record */
+        rcn_init_mc_functions_10(&c->rcn_funcs);
+        rcn_init_prof_functions_10(&c->rcn_funcs);
+        rcn_init_bdof_functions_10(&c->rcn_funcs);
+        rcn_init_dmvr_functions_10(&c->rcn_funcs);
+    }
     if (lmcs) {
         c->lmcs_info.luts = malloc(sizeof(*lmcs));
         memcpy(c->lmcs_info.luts, lmcs, sizeof(*lmcs));
@@ -323,7 +333,12 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
         OVMV mv0 = { .x = m->mv0_x, .y = m->mv0_y, .ref_idx = m->ref_idx0, .bcw_idx_plus1 = m->bcw_idx_plus1 };
         OVMV mv1 = { .x = m->mv1_x, .y = m->mv1_y, .ref_idx = m->ref_idx1, .bcw_idx_plus1 = m->bcw_idx_plus1 };
         ic->prec_amvr = (m->flags & OVO_MC_HPEL_AMVR) ? 3 /* MV_PRECISION_HALF, drv_utils.h:102 */ : 0;
-        if ((m->flags & 3) == 3)
+        if (m->tool == OVO_MC_TOOL_BDOF)
+            c->rcn_funcs.rcn_bdof_mcp_l(c, b, x0, y0, m->log2_w, m->log2_h, mv0, mv1, m->ref_idx0, m->ref_idx1);
+        else if (m->tool == OVO_MC_TOOL_PROF)      /* struct PROFInfo (rcn_inter.c:1128) has OVOProfInfo's layout */
+            c->rcn_funcs.rcn_prof_mcp_b_l(c, b, ic, &part, mv0, mv1, x0, y0, 2, 2, m->inter_dir, m->ref_idx0, m->ref_idx1,
+                                          m->aux & 3, (const void *)&prof_tab[m->aux >> 8]);
+        else if ((m->flags & 3) == 3)
             c->rcn_funcs.rcn_mcp_b(c, b, ic, &part, mv0, mv1, x0, y0, m->log2_w, m->log2_h, m->inter_dir, m->ref_idx0, m->ref_idx1);
         else if (m->flags & OVO_MC_LUMA)
             c->rcn_funcs.rcn_mcp_b_l(c, b, ic, &part, mv0, mv1, x0, y0, m->log2_w, m->log2_h, m->inter_dir, m->ref_idx0, m->ref_idx1);

@@ -92,11 +92,16 @@ struct EmuMcRefs {
 };
 
 int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h, int bitdepth,
-                   const EmuMcRefs *refs, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd)
+                   const EmuMcRefs *refs, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd,
+                   const OVGPUProfInfo *prof, int nb_prof)
 {
-    int n_items = mc_count_items(cmds, nb_cmds);
-    std::vector<McItemDev> items(n_items + 1);
+    for (int i = 0; i < nb_cmds; i++) if (mc_check_cmd(&cmds[i], nb_prof)) return -(i + 1);
+    int n_items = mc_count_items(cmds, nb_cmds), n_bdof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_BDOF),
+        n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
+    std::vector<McItemDev> items(n_items + n_bdof + n_prof + 1);
     mc_build_items(items.data(), cmds, nb_cmds);
+    mc_build_tool_items(items.data() + n_items, cmds, nb_cmds, OVGPU_MC_TOOL_BDOF);
+    mc_build_tool_items(items.data() + n_items + n_bdof, cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
@@ -108,8 +113,18 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
             a.refs.poc[l][i] = refs->poc[l][i];
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = refs->plane[l][i][c]; a.refs.pitch[l][i][c] = refs->stride[l][i][c]; }
         }
-    ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
-    return n_items;
+    if (n_items) ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
+    if (n_bdof) {
+        McK::Args t = a;
+        t.items = items.data() + n_items; t.nb_items = n_bdof;
+        ovd_emulate<BdofK>(t, ovd_dim3((n_bdof + BdofK::WARPS - 1) / BdofK::WARPS, 1, 1), BdofK::SMEM_BYTES);
+    }
+    if (n_prof) {
+        ProfK::Args t;
+        t.mc = a; t.mc.items = items.data() + n_items + n_bdof; t.mc.nb_items = n_prof; t.prof = (const ProfInfoDev *)prof;
+        ovd_emulate<ProfK>(t, ovd_dim3((n_prof + ProfK::WARPS * ProfK::SBS - 1) / (ProfK::WARPS * ProfK::SBS), 1, 1), ProfK::SMEM_BYTES);
+    }
+    return n_items + n_bdof + n_prof;
 }
 
 int emu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *d, int bitdepth)

@@ -19,16 +19,29 @@ def blank(w, h):
     return [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
 
 
-def emu_mc(emu, po, w, h, refs0, refs1, pocs, cmds, luts, bitdepth=10):
+def mc_tools_case(po, w, h, seed, log2_ctu=7, lmcs=False, min_log2=3, n_refs=2):
+    """like mc_case, with BDOF and affine/PROF coding units mixed in; returns the PROF table as well"""
+    refs0 = [synth.planes(w, h, seed + 10 + i) for i in range(n_refs)]
+    refs1 = [synth.planes(w, h, seed + 20 + i) for i in range(n_refs)]
+    pocs = [[8 * (i + 1) for i in range(n_refs)], [8 * (i + 2) for i in range(n_refs)]]
+    cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, n_refs=n_refs, min_log2=min_log2)
+    luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
+    return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof
+
+
+def emu_mc(emu, po, w, h, refs0, refs1, pocs, cmds, luts, bitdepth=10, prof=None):
     out = blank(w, h)
     refs, keep = po.make_mc_refs([refs0, refs1], pocs)
     dst, ds = po._planes_arg(out)
     lut = luts.np("fwd_lut").ctypes.data_as(po.u16p) if luts is not None else None
-    emu.emu_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut)
+    prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
+    n = emu.emu_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut,
+                           prof.ctypes.data_as(C.c_void_p) if prof is not None else None, len(prof) if prof is not None else 0)
+    assert n >= 0, "emu rejected command %d" % (-n - 1)
     return out
 
 
-def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts):
+def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None):
     from openvvc_b200 import api
     dst = ctx.picture(w, h)
     dst.upload(blank(w, h))
@@ -37,7 +50,7 @@ def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts):
         for planes in lst:
             p = ctx.picture(w, h); p.upload(planes); pics[l].append(p)
     batch = api.McBatch(ctx, len(cmds), api.mc_nb_items(cmds))
-    batch.upload(cmds.astype(api.MC_CMD))
+    batch.upload(cmds.astype(api.MC_CMD), prof=prof)
     lm = None
     if luts is not None:
         gl = api.LmcsLuts()

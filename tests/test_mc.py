@@ -117,3 +117,78 @@ def test_gpu_lmcs_backward_picture(oracle, gpu_ctx):
     out = pic.download()
     assert (out[0] == want).all() and (out[1] == planes[1]).all()
     lm.destroy(); pic.destroy()
+
+
+# ================================================================================================ BDOF / PROF
+TOOLS_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_tools_golden.json")))
+
+
+def _tools_case(po, c):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(po, c["w"], c["h"], c["seed"], c["log2_ctu"], c["lmcs"], c["min_log2"])
+    assert helpers.md5(cmds, prof, *refs0[0], *refs1[-1]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return refs0, refs1, pocs, cmds, luts, prof
+
+
+@pytest.mark.parametrize("c", TOOLS_GOLDEN, ids=IDS)
+def test_tools_port_matches_golden(oracle, c):
+    refs0, refs1, pocs, cmds, luts, prof = _tools_case(oracle, c)
+    assert (cmds["tool"] == 1).sum() > 10 and (cmds["tool"] == 2).sum() > 10
+    dst = helpers_mc.blank(c["w"], c["h"])
+    oracle.mc_picture(dst, [refs0, refs1], pocs, cmds, c["log2_ctu"], impl="port", lmcs=luts, prof=prof)
+    assert [helpers.md5(p) for p in dst] == c["md5"]
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs", [(416, 240, 7, False), (416, 240, 7, True), (832, 480, 7, True), (264, 136, 6, False)])
+def test_tools_port_vs_compiled_reference(oracle, w, h, log2, lmcs):
+    """BDOF (rcn_bdof_mcp_l) and PROF (rcn_prof_mcp_b_l): port vs the reference's scalar C and its SSE/AVX2 table"""
+    po = oracle
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(po, w, h, 5 * w + h + 1, log2, lmcs)
+    a = helpers_mc.blank(w, h)
+    po.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts, prof=prof)
+    for simd in (0, 1):
+        b = helpers_mc.blank(w, h)
+        po.mc_picture(b, [refs0, refs1], pocs, cmds, log2, impl="ref", lmcs=luts, prof=prof, simd=simd)
+        helpers.assert_planes_equal(a, b, "MC tools port vs reference (simd=%d)" % simd)
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs", [(416, 240, 7, False), (416, 240, 7, True), (256, 128, 6, False), (832, 480, 7, True)])
+def test_tools_emulated_kernels_match_oracle(oracle, emu, w, h, log2, lmcs):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, w, h, 7 * w + h + 1, log2, lmcs)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts, prof=prof)
+    helpers.assert_planes_equal(helpers_mc.emu_mc(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts, prof=prof), a,
+                                "emulated MC/BDOF/PROF kernels vs oracle")
+
+
+def test_tools_malformed_commands_rejected(oracle, emu):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, 256, 128, 3, 7, False)
+    bad = cmds.copy()
+    i = int(np.nonzero(bad["tool"] == 2)[0][0])
+    bad["aux"][i] = (len(prof) << 8) | 1            # PROF table index out of range
+    with pytest.raises(AssertionError):
+        helpers_mc.emu_mc(emu, oracle, 256, 128, refs0, refs1, pocs, bad, luts, prof=prof)
+    bad = cmds.copy()
+    i = int(np.nonzero(bad["tool"] == 1)[0][0])
+    bad["inter_dir"][i] = 1                         # BDOF needs bi-prediction
+    with pytest.raises(AssertionError):
+        helpers_mc.emu_mc(emu, oracle, 256, 128, refs0, refs1, pocs, bad, luts, prof=prof)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", TOOLS_GOLDEN, ids=IDS)
+def test_tools_gpu_matches_golden(oracle, gpu_ctx, c):
+    refs0, refs1, pocs, cmds, luts, prof = _tools_case(oracle, c)
+    out = helpers_mc.gpu_mc(gpu_ctx, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, prof=prof)
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
+@pytest.mark.gpu
+def test_tools_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
+    """BASELINE.json config 4 flavour (affine + BDOF heavy inter) at 3840x2160: CUDA vs the compiled reference"""
+    w, h = 3840, 2160
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, w, h, 81, 7, True, 3)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="ref" if oracle.ref_available() else "port", lmcs=luts, prof=prof)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=prof), a, "CUDA MC tools vs reference at 4K")
