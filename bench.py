@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["mc(uni/bi/bcw)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
+STAGES_IMPLEMENTED = ["mc(uni/bi/bcw, bdof, affine 4x4 + prof)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
 def peaks():
@@ -84,11 +84,12 @@ def make_workload(w, h, n_pics, seed0=5000):
         tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
-        cmds = synth.mc_commands(w, h, seed0 + 300 + i, 7).astype(api.MC_CMD)
+        cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15)
+        cmds = cmds.astype(api.MC_CMD)
         tus, coeffs = synth_tu.tu_commands(w, h, seed0 + 400 + i, 7, ict_type=1, legal=True, p_intra=0.1, min_log2=3, p_cbf=0.4)
         blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
         dbf = synth_dbf.dbf_maps(w, h, blks, 7)
-        pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, tus=tus, coeffs=coeffs,
+        pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, prof=prof, tus=tus, coeffs=coeffs,
                          dbf_blks=blks, dbf=dbf))
     return dict(refs=refs, pocs=pocs, lmcs=lmcs, pics=pics)
 
@@ -111,10 +112,12 @@ def residual_bytes(tus):
 
 
 def mc_dirs_per_sample(cmds):
+    """average number of prediction directions per luma sample (the d of the (d + 1) * P MC floor)"""
+    luma = (cmds["flags"] & 1) != 0
     area = (1 << cmds["log2_w"].astype(np.int64)) * (1 << cmds["log2_h"].astype(np.int64))
-    ident = (cmds["mv0_x"] == cmds["mv1_x"]) & (cmds["mv0_y"] == cmds["mv1_y"]) & (cmds["ref_idx0"] == 1) & (cmds["ref_idx1"] == 0)
+    ident = (cmds["tool"] == 0) & (cmds["mv0_x"] == cmds["mv1_x"]) & (cmds["mv0_y"] == cmds["mv1_y"]) & (cmds["ref_idx0"] == 1) & (cmds["ref_idx1"] == 0)
     nref = np.where((cmds["inter_dir"] == 3) & ~ident, 2, 1)
-    return float((area * nref).sum() / area.sum())
+    return float((area * nref)[luma].sum() / area[luma].sum())
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
@@ -132,7 +135,7 @@ def reference_step(po, wl, threads):
         t = po.AlfTables()
         C.memmove(C.byref(t), C.byref(p["tab"]), C.sizeof(t))
         rec = [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
-        po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts)
+        po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts, prof=p["prof"])
         pt.residual_picture(rec, p["tus"], p["coeffs"], 7, impl=impl, dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=1)
         po.port().ovo_lmcs_reshape_plane(rec[0].ctypes.data_as(po.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(po.u16p), 10)
         if impl == "ref":
@@ -179,8 +182,8 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(intra prediction and BDOF/DMVR/PROF not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
-            "pictures_per_step": pics_per_step, "parallelism": "frame-parallel, one picture stream per GPU",
+                        "(intra prediction and DMVR not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+            "pictures_per_step": pics_per_step, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
 
@@ -226,7 +229,12 @@ def main():
     pbytes = w * h * 2 * 3 // 2
 
     # device-resident state: reference pictures, per picture recon (prediction), mid (post-SAO), dst (post-ALF)
-    ref_pics = [[ctx.picture(w, h) for _ in lst] for lst in wl["refs"]]
+    # The DPB copies live in flat torch tensors wrapped as pictures (ovgpu_picture_wrap) so that the owner of a finished
+    # picture can hand it to the other ranks with an NCCL broadcast (openvvc_b200/dist.py).
+    from openvvc_b200 import dist as ovdist
+    dev_name = "cuda:%d" % local
+    ref_shared = [[ovdist.SharedPicture(w, h, dev_name) for _ in lst] for lst in wl["refs"]]
+    ref_pics = [[ctx.wrap_picture(w, h, *sp.plane_ptrs()) for sp in lst] for lst in ref_shared]
     for lst, src in zip(ref_pics, wl["refs"]):
         for pic, planes in zip(lst, src):
             pic.upload(planes)
@@ -239,7 +247,7 @@ def main():
                  tu=api.TuBatch(ctx, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(ctx, w, h, 7))
         d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
         d["sao"].upload(p["sao"])
-        d["mc"].upload(p["cmds"])
+        d["mc"].upload(p["cmds"], prof=p["prof"])
         d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
         d["dbf"].upload(p["dbf"])
         dev.append(d)
@@ -253,9 +261,22 @@ def main():
         d["sao"].run(d["mid"], d["rec"])
         d["alf"].run(d["dst"], d["mid"])
 
+    step_no = [0]
+
+    def hand_off_reference():
+        """the newest reconstructed picture of this step's owner rank becomes a reference on every rank: device copy
+        into the owner's DPB slot, then ncclBroadcast of the 3 planes (P bytes) to the other ranks"""
+        k = step_no[0]
+        step_no[0] += 1
+        slot, owner = k % 4, k % world
+        if rank == owner:
+            api._check(ctx.h, api.lib().ovgpu_picture_copy(ctx.h, ref_pics[slot // 2][slot % 2].p, dev[0]["dst"].p), "picture_copy")
+        ovdist.publish_reference(ref_shared[slot // 2][slot % 2], owner, world)
+
     def step_device():
         for d in dev:
             run_stages(d)
+        hand_off_reference()
 
     def barrier():
         if world > 1:
@@ -302,6 +323,8 @@ def main():
                   for _ in pics]
     np_out = [[t.numpy() for t in pin] for pin in pinned_out]
     for p, d in zip(pics, dev):
+        mc_c, mc_p = d["mc"].staging()
+        mc_c[:len(p["cmds"])] = p["cmds"]; mc_p[:len(p["prof"])] = p["prof"]
         hc, hk = d["tu"].staging()
         hc[:len(p["tus"])] = p["tus"]; hk[:len(p["coeffs"])] = p["coeffs"]
         st = d["dbf"].staging()
@@ -313,7 +336,7 @@ def main():
     def step_e2e():
         for i, d in enumerate(dev):
             p, c = pics[i], e_ctx[i % n_ctx]
-            d["mc"].upload(p["cmds"], ctx=c)
+            d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c)
             d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c)
             d["dbf"].commit(0, 0, ctx=c)
             d["sao"].upload(p["sao"], ctx=c)
@@ -327,6 +350,7 @@ def main():
             api._check(c.h, api.lib().ovgpu_picture_download(c.h, d["dst"].p, *api._host_planes(np_out[i])), "download")
         for c in e_ctx:
             c.sync()
+        hand_off_reference()
 
     step_e2e()
     e2e_steps = max(2, min(args.steps, 5))
@@ -361,7 +385,7 @@ def main():
                 stages[s] = {"avg_launch_ms": avg, "algorithmic_bytes": alg[s], "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9,
                              "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
-        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
+        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",

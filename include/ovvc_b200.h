@@ -204,6 +204,10 @@ int  ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmd
 /* same, with the PROF table that OVGPU_MC_TOOL_PROF commands index (may be NULL when nb_prof == 0) */
 int  ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
                             const OVGPUProfInfo *prof, int nb_prof);
+/* Zero-copy staging: _staging returns the batch's PINNED command (and PROF table) buffers for the recorder to fill,
+ * _commit validates, builds the work lists in one pass and issues the asynchronous H2D copies. */
+int  ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof);
+int  ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_prof);
 /* writes the prediction of every command into dst; lmcs may be NULL (no forward reshape). Asynchronous. */
 int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                       const OVGPULmcs *lmcs);

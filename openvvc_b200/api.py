@@ -299,6 +299,7 @@ class McBatch:
     def __init__(self, ctx, max_cmds, max_items):
         self.ctx = ctx
         self.p = vp()
+        self.max_cmds = int(max_cmds)
         _check(ctx.h, lib().ovgpu_mc_batch_create(ctx.h, int(max_cmds), int(max_items), C.byref(self.p)), "mc_batch_create")
 
     def upload(self, cmds, ctx=None, prof=None):
@@ -309,6 +310,18 @@ class McBatch:
         _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_upload2((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds),
                                                                  vp(prof.ctypes.data) if prof is not None else None,
                                                                  len(prof) if prof is not None else 0), "mc_batch_upload2")
+
+    def staging(self, ctx=None):
+        """numpy views of the batch's PINNED command and PROF-table buffers (ovgpu_mc_batch_staging)"""
+        pc, pp = vp(), vp()
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_staging((ctx or self.ctx).h, self.p, C.byref(pc), C.byref(pp)), "mc_batch_staging")
+        cmds = np.frombuffer((C.c_uint8 * (MC_CMD.itemsize * self.max_cmds)).from_address(pc.value), dtype=MC_CMD)
+        n_prof = self.max_cmds // 16 + 1
+        prof = np.frombuffer((C.c_int16 * (64 * n_prof)).from_address(pp.value), dtype=np.int16).reshape(n_prof, 4, 16)
+        return cmds, prof
+
+    def commit(self, nb_cmds, nb_prof=0, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_commit((ctx or self.ctx).h, self.p, int(nb_cmds), int(nb_prof)), "mc_batch_commit")
 
     def run(self, dst, ref_lists, pocs, lmcs=None, ctx=None):
         """ref_lists: [rpl0, rpl1] lists of Picture; pocs likewise."""

@@ -160,14 +160,19 @@ static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_
     return cudaGetLastError();
 }
 #else
+// CTAs of a launch may run in any order on the GPU: tests run the emulation in both orders to catch kernels whose
+// result depends on it (e.g. a store that spills into a neighbouring block's samples)
+static int ovd_emu_reverse_blocks = 0;
 template <class K>
 static inline void ovd_emulate(const typename K::Args &a, ovd_dim3 grid, size_t smem_bytes)
 {
     std::vector<typename K::State> st(K::THREADS);
     std::vector<uint64_t> smem((smem_bytes + 7) / 8 + 2);
-    for (unsigned bz = 0; bz < grid.z; bz++)
-        for (unsigned by = 0; by < grid.y; by++)
-            for (unsigned bx = 0; bx < grid.x; bx++) {
+    for (unsigned bz_ = 0; bz_ < grid.z; bz_++)
+        for (unsigned by_ = 0; by_ < grid.y; by_++)
+            for (unsigned bx_ = 0; bx_ < grid.x; bx_++) {
+                const unsigned bx = ovd_emu_reverse_blocks ? grid.x - 1 - bx_ : bx_, by = ovd_emu_reverse_blocks ? grid.y - 1 - by_ : by_,
+                               bz = ovd_emu_reverse_blocks ? grid.z - 1 - bz_ : bz_;
                 unsigned char *sm = (unsigned char *)smem.data();
                 memset(sm, 0xcd, smem_bytes);   // poison: catches reads of unwritten shared memory
                 for (int t = 0; t < K::THREADS; t++) K::template phase<0>(a, sm, st[t], t, bx, by, bz);

@@ -11,7 +11,9 @@ struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
     int nb_bdof, nb_prof_items, nb_prof;      // BDOF / PROF work items (appended to the item list), PROF table entries
     McCmdDev *h_cmds, *d_cmds;
-    McItemDev *h_items, *d_items;             // [plain items | BDOF items | PROF items]
+    McItemDev *h_items, *d_items;             // three regions of max_items entries: plain | BDOF | PROF
+    int max_x, max_y;                         // furthest sample any command writes (checked against the picture at run time)
+    uint32_t used_refs[2];                    // reference indices the commands name, per list
     ProfInfoDev *h_prof, *d_prof;             // max_cmds / 16 + 1 entries (one per affine CU of >= 16 sub-blocks)
     int max_prof;
     StagingFence fence;
@@ -90,9 +92,9 @@ int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBat
     if (cudaMallocHost(&b->h_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMalloc(&b->d_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMallocHost(&b->h_items, sizeof(McItemDev) * max_items) != cudaSuccess ||
+        cudaMallocHost(&b->h_items, sizeof(McItemDev) * 3 * max_items) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMalloc(&b->d_items, sizeof(McItemDev) * max_items) != cudaSuccess) {
+        cudaMalloc(&b->d_items, sizeof(McItemDev) * 3 * max_items) != cudaSuccess) {
         ovgpu_mc_batch_destroy(b);
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "MC batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -119,34 +121,71 @@ int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds
     return ovgpu_mc_batch_upload2(ctx, b, cmds, nb_cmds, NULL, 0);
 }
 
-int ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
-                           const OVGPUProfInfo *prof, int nb_prof)
+int ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof)
 {
-    if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0 || (nb_prof && !prof)) return OVGPU_EINVAL;
+    if (!ctx || !b || !cmds) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));           // previous H2D copy out of the staging buffers
+    *cmds = (OVGPUMcCmd *)b->h_cmds;
+    if (prof) *prof = (OVGPUProfInfo *)b->h_prof;
+    return 0;
+}
+
+int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_prof)
+{
+    if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0) return OVGPU_EINVAL;
     if (nb_prof > b->max_prof) return ovgpu_set_error(ctx, OVGPU_EINVAL, "PROF table too large (%d > %d)", nb_prof, b->max_prof);
-    for (int i = 0; i < nb_cmds; i++)
-        if (mc_check_cmd(&cmds[i], nb_prof))
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d malformed", i);
-    const int n_plain = mc_count_items(cmds, nb_cmds), n_bdof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_BDOF),
-              n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
-    if (n_plain + n_bdof + n_prof > b->max_items)
-        return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch needs %d items (max %d)", n_plain + n_bdof + n_prof, b->max_items);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
-    memcpy(b->h_cmds, cmds, sizeof(McCmdDev) * nb_cmds);
-    if (nb_prof) memcpy(b->h_prof, prof, sizeof(ProfInfoDev) * nb_prof);
-    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof;
-    b->nb_items = mc_build_items(b->h_items, cmds, nb_cmds);
-    b->nb_bdof = mc_build_tool_items(b->h_items + b->nb_items, cmds, nb_cmds, OVGPU_MC_TOOL_BDOF);
-    b->nb_prof_items = mc_build_tool_items(b->h_items + b->nb_items + b->nb_bdof, cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
+    // one pass over the commands: validate, split into <=16x16 work items per kernel, note extents and references
+    const OVGPUMcCmd *cmds = (const OVGPUMcCmd *)b->h_cmds;
+    McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items;
+    int np = 0, nb = 0, nq = 0, max_x = 0, max_y = 0;
+    uint32_t used[2] = { 0, 0 };
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVGPUMcCmd *c = &cmds[i];
+        if (mc_check_cmd(c, nb_prof)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d malformed", i);
+        const int w = 1 << c->log2_w, h = 1 << c->log2_h;
+        if (c->x0 + w > max_x) max_x = c->x0 + w;
+        if (c->y0 + h > max_y) max_y = c->y0 + h;
+        if (c->inter_dir & 1) used[0] |= 1u << c->ref_idx0;
+        if (c->inter_dir & 2) used[1] |= 1u << c->ref_idx1;
+        if (c->tool == OVGPU_MC_TOOL_PLAIN) {
+            if (np + ((w + 15) >> 4) * ((h + 15) >> 4) > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch: too many work items");
+            for (int oy = 0; oy < h; oy += 16)
+                for (int ox = 0; ox < w; ox += 16) {
+                    McItemDev it = { (uint32_t)i, (uint8_t)ox, (uint8_t)oy, (uint8_t)(w - ox < 16 ? w - ox : 16), (uint8_t)(h - oy < 16 ? h - oy : 16) };
+                    ip[np++] = it;
+                }
+        } else {
+            McItemDev it = { (uint32_t)i, 0, 0, (uint8_t)w, (uint8_t)h };
+            if (c->tool == OVGPU_MC_TOOL_BDOF) { if (nb >= b->max_items) return OVGPU_EINVAL; ib[nb++] = it; }
+            else                               { if (nq >= b->max_items) return OVGPU_EINVAL; iq[nq++] = it; }
+        }
+    }
+    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq;
+    b->max_x = max_x; b->max_y = max_y; b->used_refs[0] = used[0]; b->used_refs[1] = used[1];
     if (nb_cmds) {
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
-        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(McItemDev) * (b->nb_items + b->nb_bdof + b->nb_prof_items),
-                                              cudaMemcpyHostToDevice, ctx->stream));
+        if (np) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, ip, sizeof(McItemDev) * np, cudaMemcpyHostToDevice, ctx->stream));
+        if (nb) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + b->max_items, ib, sizeof(McItemDev) * nb, cudaMemcpyHostToDevice, ctx->stream));
+        if (nq) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 2 * b->max_items, iq, sizeof(McItemDev) * nq, cudaMemcpyHostToDevice, ctx->stream));
         if (nb_prof)
             OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_prof, b->h_prof, sizeof(ProfInfoDev) * nb_prof, cudaMemcpyHostToDevice, ctx->stream));
         OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
     }
     return 0;
+}
+
+int ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
+                           const OVGPUProfInfo *prof, int nb_prof)
+{
+    if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0 || (nb_prof && !prof)) return OVGPU_EINVAL;
+    if (nb_prof > b->max_prof) return ovgpu_set_error(ctx, OVGPU_EINVAL, "PROF table too large (%d > %d)", nb_prof, b->max_prof);
+    OVGPUMcCmd *hc; OVGPUProfInfo *hp;
+    int ret = ovgpu_mc_batch_staging(ctx, b, &hc, &hp);
+    if (ret) return ret;
+    memcpy(hc, cmds, sizeof(McCmdDev) * nb_cmds);
+    if (nb_prof) memcpy(hp, prof, sizeof(ProfInfoDev) * nb_prof);
+    return ovgpu_mc_batch_commit(ctx, b, nb_cmds, nb_prof);
 }
 
 int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
@@ -160,14 +199,13 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
     a.pic_w = dst->width; a.pic_h = dst->height; a.bitdepth = dst->bitdepth;
     a.cmds = b->d_cmds; a.items = b->d_items; a.nb_items = b->nb_items;
     a.lmcs_fwd = lmcs ? lmcs->d_luts->fwd_lut : NULL;
-    // every reference a command names must be present and of the picture's size
-    for (int i = 0; i < b->nb_cmds; i++) {
-        const McCmdDev *c = &b->h_cmds[i];
-        if (((c->inter_dir & 1) && !refs->rpl[0][c->ref_idx0]) || ((c->inter_dir & 2) && !refs->rpl[1][c->ref_idx1]))
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d references a missing picture", i);
-        if (c->x0 + (1 << c->log2_w) > dst->width || c->y0 + (1 << c->log2_h) > dst->height)
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d lies outside the picture", i);
-    }
+    // every reference a command names must be present, and every command must lie inside the picture
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++)
+            if (((b->used_refs[l] >> i) & 1) && !refs->rpl[l][i])
+                return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC commands reference a missing picture (list %d, index %d)", l, i);
+    if (b->max_x > dst->width || b->max_y > dst->height)
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC commands lie outside the picture");
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
             const OVGPUPicture *p = refs->rpl[l][i];
@@ -182,12 +220,12 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
         OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, ctx->stream));
     if (b->nb_bdof) {
         McK::Args t = a;
-        t.items = b->d_items + b->nb_items; t.nb_items = b->nb_bdof;
+        t.items = b->d_items + b->max_items; t.nb_items = b->nb_bdof;
         OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, ctx->stream));
     }
     if (b->nb_prof_items) {
         ProfK::Args t;
-        t.mc = a; t.mc.items = b->d_items + b->nb_items + b->nb_bdof; t.mc.nb_items = b->nb_prof_items; t.prof = b->d_prof;
+        t.mc = a; t.mc.items = b->d_items + 2 * b->max_items; t.mc.nb_items = b->nb_prof_items; t.prof = b->d_prof;
         OVGPU_CUDA_CHECK(ctx, ovd_launch<ProfK>(t, dim3(OVGPU_CEIL_DIV(b->nb_prof_items, ProfK::WARPS * ProfK::SBS), 1, 1),
                                                 ProfK::SMEM_BYTES, ctx->stream));
     }

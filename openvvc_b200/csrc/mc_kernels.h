@@ -199,7 +199,7 @@ struct McK {
         // block positions are multiples of 4 luma samples only (ternary splits): pick the widest aligned store
         const unsigned al = (unsigned)(uintptr_t)d;
         if (n >= 8 && !(al & 15)) { ovd_u4 r; r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3]; ovd_st16(d, r); }
-        else if (!(al & 7)) {
+        else if (n >= 4 && !(al & 7)) {
             ovd_u2 r; r.x = o[0]; r.y = o[1]; ovd_st8(d, r);
             if (n >= 8) { r.x = o[2]; r.y = o[3]; ovd_st8(d + 4, r); }
         } else {

@@ -24,6 +24,8 @@ static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int b
 
 extern "C" {
 
+void emu_set_reverse_block_order(int on) { ovd_emu_reverse_blocks = on; }
+
 int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
                     const uint16_t *const src[3], const int src_stride[3],
                     int w, int h, int log2_ctu, int bitdepth,

@@ -25,3 +25,31 @@ def test_emulated_sao_matches_oracle(oracle, emu, w, h, log2, kind, wide):
     planes, sao = helpers.sao_case(oracle, w, h, 13 * w + h, log2, kind)
     ref = oracle.sao_picture(planes, sao, log2, impl="port")
     helpers.assert_planes_equal(helpers.emu_sao(emu, planes, sao, log2), ref, "emulated SAO kernel vs oracle")
+
+
+def test_results_do_not_depend_on_cta_order(oracle, emu):
+    """CTAs run in any order on the GPU; the serial emulation is repeated with the block order reversed so that a kernel
+    writing outside its own samples (hidden by the forward order) is caught on the CPU."""
+    import helpers_mc, helpers_tr, helpers_df
+    from oracle import pyoracle_tr as pt, pyoracle_df as pd
+    try:
+        emu.emu_set_reverse_block_order(1)
+        w, h = 416, 240
+        refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, w, h, 41, 7, True, 2)
+        a = helpers_mc.blank(w, h)
+        oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="port", lmcs=luts, prof=prof)
+        helpers.assert_planes_equal(helpers_mc.emu_mc(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts, prof=prof), a, "MC, reversed CTA order")
+        refs0, refs1, pocs, cmds, luts = helpers_mc.mc_case(oracle, w, h, 42, 7, False, 2)
+        a = helpers_mc.blank(w, h)
+        oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="port", lmcs=luts)
+        helpers.assert_planes_equal(helpers_mc.emu_mc(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts), a, "MC 4x4, reversed CTA order")
+        planes, tus, arena = helpers_tr.tr_case(w, h, 43, 7, 1, 0, 1, p_intra=0.3)
+        want = pt.residual_picture([p.copy() for p in planes], tus, arena, 7, impl="port", dep_quant=1, sh_ts_disabled=0, ict_type=1)
+        helpers.assert_planes_equal(helpers_tr.emu_residual(emu, planes, tus, arena, 1, 0, 1), want, "residual, reversed CTA order")
+        planes, blks, maps = helpers_df.dbf_case(w, h, 44, 7, "blocky")
+        want = pd.dbf_picture_port([p.copy() for p in planes], maps)
+        helpers.assert_planes_equal(helpers_df.emu_dbf(emu, planes, maps), want, "DBF, reversed CTA order")
+        planes, sao = helpers.sao_case(oracle, w, h, 45, 7)
+        helpers.assert_planes_equal(helpers.emu_sao(emu, planes, sao, 7), oracle.sao_picture(planes, sao, 7, impl="port"), "SAO, reversed CTA order")
+    finally:
+        emu.emu_set_reverse_block_order(0)
