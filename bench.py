@@ -204,6 +204,12 @@ def main():
         run_reference(args, w, h)
         return
 
+    # Libraries (NCCL prints its version banner) may write to stdout; the contract is ONE JSON line there, so route
+    # fd 1 to stderr for the duration of the run and keep the real stdout for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from openvvc_b200 import api
@@ -411,7 +417,8 @@ def main():
             line["cpu_baseline"] = {"value": n / tot, "unit": "frames/s", "cores": cores,
                                     "kind": "reference" if po.ref_available() else "port",
                                     "sample": "%d pictures (%d per round, one per host thread), same stages" % (n, cores)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
