@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["mc(uni/bi/bcw, bdof, affine 4x4 + prof)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
+STAGES_IMPLEMENTED = ["mc(uni/bi/bcw, bdof, dmvr, affine 4x4 + prof)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
 def peaks():
@@ -84,7 +84,7 @@ def make_workload(w, h, n_pics, seed0=5000):
         tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
-        cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15)
+        cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15)
         cmds = cmds.astype(api.MC_CMD)
         tus, coeffs = synth_tu.tu_commands(w, h, seed0 + 400 + i, 7, ict_type=1, legal=True, p_intra=0.1, min_log2=3, p_cbf=0.4)
         blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
@@ -182,7 +182,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(intra prediction and DMVR not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(intra prediction, CIIP and GPM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 

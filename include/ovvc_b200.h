@@ -172,6 +172,10 @@ int  ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmc
                                 * from vcl_coding_unit.c:2648-2672; bi-prediction, luma only                          */
 #define OVGPU_MC_TOOL_PROF  2  /* rcn_prof_mcp_b_l (rcn_inter.c:2865): one 4x4 luma sub-block of an affine CU, as called
                                 * from drv_affine_mvp.c:3355; aux = prof_dir (bits 0-1) | PROF table index << 8       */
+#define OVGPU_MC_TOOL_DMVR  3  /* rcn_dmvr_mv_refine (rcn_inter.c:873): one <=16x16 sub-block of a DMVR CU, luma AND chroma, as
+                                * called from vcl_coding_unit.c:2621; aux bit 0 = apply_bdof.  The refined MVs come back
+                                * through ovgpu_mc_batch_read_dmvr (the caller stores them for TMVP, :2628-2645).        */
+typedef struct OVGPUDmvrMv { int32_t mv0_x, mv0_y, mv1_x, mv1_y; } OVGPUDmvrMv;
 /* struct PROFInfo (rcn_inter.c:1128-1134): the 16 per-sample delta-MV scales of an affine CU and list */
 typedef struct OVGPUProfInfo {
     int16_t dmv_scale_h_0[16], dmv_scale_v_0[16], dmv_scale_h_1[16], dmv_scale_v_1[16];
@@ -208,6 +212,9 @@ int  ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cm
  * _commit validates, builds the work lists in one pass and issues the asynchronous H2D copies. */
 int  ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof);
 int  ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_prof);
+/* Refined MVs of the DMVR commands of the last ovgpu_mc_picture call on this batch, in command order: D2H copy into
+ * `out` (up to max entries) + stream sync; returns the number of DMVR commands or a negative error. */
+int  ovgpu_mc_batch_read_dmvr(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUDmvrMv *out, int max);
 /* writes the prediction of every command into dst; lmcs may be NULL (no forward reshape). Asynchronous. */
 int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                       const OVGPULmcs *lmcs);

@@ -237,6 +237,9 @@ MC_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), ("l
                    ("aux", np.uint32)])
 
 
+DMVR_MV = np.dtype([("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32)])
+
+
 class McRefs(C.Structure):
     """OVGPUMcRefs: inter_ctx->rpl0/rpl1 as device pictures + POCs."""
     _fields_ = [("rpl", vp * 16 * 2), ("poc", C.c_int32 * 16 * 2)]
@@ -319,6 +322,15 @@ class McBatch:
         n_prof = self.max_cmds // 16 + 1
         prof = np.frombuffer((C.c_int16 * (64 * n_prof)).from_address(pp.value), dtype=np.int16).reshape(n_prof, 4, 16)
         return cmds, prof
+
+    def read_dmvr(self, n, ctx=None):
+        """refined MVs (OVGPUDmvrMv) of the DMVR commands of the last run, in command order"""
+        out = np.zeros(n, dtype=DMVR_MV)
+        ret = lib().ovgpu_mc_batch_read_dmvr((ctx or self.ctx).h, self.p, vp(out.ctypes.data), int(n))
+        if ret < 0:
+            _check((ctx or self.ctx).h, ret, "mc_batch_read_dmvr")
+        assert ret == n, "batch holds %d DMVR commands, asked for %d" % (ret, n)
+        return out
 
     def commit(self, nb_cmds, nb_prof=0, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_commit((ctx or self.ctx).h, self.p, int(nb_cmds), int(nb_prof)), "mc_batch_commit")

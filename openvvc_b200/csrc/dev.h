@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const ty
     if (K::PHASES > 3) { __syncthreads(); K::template phase<3>(a, ovd_smem, st, tid, bx, by, bz); }
     if (K::PHASES > 4) { __syncthreads(); K::template phase<4>(a, ovd_smem, st, tid, bx, by, bz); }
     if (K::PHASES > 5) { __syncthreads(); K::template phase<5>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 6) { __syncthreads(); K::template phase<6>(a, ovd_smem, st, tid, bx, by, bz); }
+    if (K::PHASES > 7) { __syncthreads(); K::template phase<7>(a, ovd_smem, st, tid, bx, by, bz); }
 }
 
 template <class K>
@@ -181,6 +183,8 @@ static inline void ovd_emulate(const typename K::Args &a, ovd_dim3 grid, size_t 
                 if (K::PHASES > 3) for (int t = 0; t < K::THREADS; t++) K::template phase<3>(a, sm, st[t], t, bx, by, bz);
                 if (K::PHASES > 4) for (int t = 0; t < K::THREADS; t++) K::template phase<4>(a, sm, st[t], t, bx, by, bz);
                 if (K::PHASES > 5) for (int t = 0; t < K::THREADS; t++) K::template phase<5>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 6) for (int t = 0; t < K::THREADS; t++) K::template phase<6>(a, sm, st[t], t, bx, by, bz);
+                if (K::PHASES > 7) for (int t = 0; t < K::THREADS; t++) K::template phase<7>(a, sm, st[t], t, bx, by, bz);
             }
 }
 #endif

@@ -10,8 +10,10 @@ static_assert(sizeof(McCmdDev) == sizeof(OVGPUMcCmd) && sizeof(McCmdDev) == 32, 
 struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
     int nb_bdof, nb_prof_items, nb_prof;      // BDOF / PROF work items (appended to the item list), PROF table entries
+    int nb_dmvr;
+    DmvrMvDev *d_dmvr, *h_dmvr;               // refined MVs, one per DMVR item (device result + pinned read-back)
     McCmdDev *h_cmds, *d_cmds;
-    McItemDev *h_items, *d_items;             // three regions of max_items entries: plain | BDOF | PROF
+    McItemDev *h_items, *d_items;             // four regions of max_items entries: plain | BDOF | PROF | DMVR
     int max_x, max_y;                         // furthest sample any command writes (checked against the picture at run time)
     uint32_t used_refs[2];                    // reference indices the commands name, per list
     ProfInfoDev *h_prof, *d_prof;             // max_cmds / 16 + 1 entries (one per affine CU of >= 16 sub-blocks)
@@ -19,6 +21,7 @@ struct OVGPUMcBatch {
     StagingFence fence;
 };
 static_assert(sizeof(ProfInfoDev) == sizeof(OVGPUProfInfo), "PROF table layout");
+static_assert(sizeof(DmvrMvDev) == sizeof(OVGPUDmvrMv), "DMVR result layout");
 
 struct OVGPULmcs {
     OVGPULmcsLuts *h_luts, *d_luts;
@@ -92,9 +95,11 @@ int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBat
     if (cudaMallocHost(&b->h_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMalloc(&b->d_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMallocHost(&b->h_items, sizeof(McItemDev) * 3 * max_items) != cudaSuccess ||
+        cudaMallocHost(&b->h_items, sizeof(McItemDev) * 4 * max_items) != cudaSuccess ||
+        cudaMallocHost(&b->h_dmvr, sizeof(DmvrMvDev) * max_items) != cudaSuccess ||
+        cudaMalloc(&b->d_dmvr, sizeof(DmvrMvDev) * max_items) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMalloc(&b->d_items, sizeof(McItemDev) * 3 * max_items) != cudaSuccess) {
+        cudaMalloc(&b->d_items, sizeof(McItemDev) * 4 * max_items) != cudaSuccess) {
         ovgpu_mc_batch_destroy(b);
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "MC batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -110,6 +115,8 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
     if (b->h_items) cudaFreeHost(b->h_items);
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_items) cudaFree(b->d_items);
+    if (b->h_dmvr) cudaFreeHost(b->h_dmvr);
+    if (b->d_dmvr) cudaFree(b->d_dmvr);
     if (b->h_prof) cudaFreeHost(b->h_prof);
     if (b->d_prof) cudaFree(b->d_prof);
     fence_destroy(&b->fence);
@@ -137,8 +144,8 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     // one pass over the commands: validate, split into <=16x16 work items per kernel, note extents and references
     const OVGPUMcCmd *cmds = (const OVGPUMcCmd *)b->h_cmds;
-    McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items;
-    int np = 0, nb = 0, nq = 0, max_x = 0, max_y = 0;
+    McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items, *id = b->h_items + 3 * b->max_items;
+    int np = 0, nb = 0, nq = 0, nd = 0, max_x = 0, max_y = 0;
     uint32_t used[2] = { 0, 0 };
     for (int i = 0; i < nb_cmds; i++) {
         const OVGPUMcCmd *c = &cmds[i];
@@ -157,17 +164,19 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
                 }
         } else {
             McItemDev it = { (uint32_t)i, 0, 0, (uint8_t)w, (uint8_t)h };
-            if (c->tool == OVGPU_MC_TOOL_BDOF) { if (nb >= b->max_items) return OVGPU_EINVAL; ib[nb++] = it; }
-            else                               { if (nq >= b->max_items) return OVGPU_EINVAL; iq[nq++] = it; }
+            if (c->tool == OVGPU_MC_TOOL_BDOF)      { if (nb >= b->max_items) return OVGPU_EINVAL; ib[nb++] = it; }
+            else if (c->tool == OVGPU_MC_TOOL_DMVR) { if (nd >= b->max_items) return OVGPU_EINVAL; id[nd++] = it; }
+            else                                    { if (nq >= b->max_items) return OVGPU_EINVAL; iq[nq++] = it; }
         }
     }
-    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq;
+    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq; b->nb_dmvr = nd;
     b->max_x = max_x; b->max_y = max_y; b->used_refs[0] = used[0]; b->used_refs[1] = used[1];
     if (nb_cmds) {
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
         if (np) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, ip, sizeof(McItemDev) * np, cudaMemcpyHostToDevice, ctx->stream));
         if (nb) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + b->max_items, ib, sizeof(McItemDev) * nb, cudaMemcpyHostToDevice, ctx->stream));
         if (nq) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 2 * b->max_items, iq, sizeof(McItemDev) * nq, cudaMemcpyHostToDevice, ctx->stream));
+        if (nd) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 3 * b->max_items, id, sizeof(McItemDev) * nd, cudaMemcpyHostToDevice, ctx->stream));
         if (nb_prof)
             OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_prof, b->h_prof, sizeof(ProfInfoDev) * nb_prof, cudaMemcpyHostToDevice, ctx->stream));
         OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
@@ -192,7 +201,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                      const OVGPULmcs *lmcs)
 {
     if (!ctx || !dst || !refs || !b) return OVGPU_EINVAL;
-    if (!(b->nb_items + b->nb_bdof + b->nb_prof_items)) return 0;
+    if (!(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr)) return 0;
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { PlaneView v = plane_view(dst, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
@@ -215,13 +224,18 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                 return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture size differs (RPR is not supported)");
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = p->plane[c]; a.refs.pitch[l][i][c] = (int)(p->pitch[c] / 2); }
         }
-    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0));
+    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0));
     if (b->nb_items)
         OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, ctx->stream));
     if (b->nb_bdof) {
         McK::Args t = a;
         t.items = b->d_items + b->max_items; t.nb_items = b->nb_bdof;
         OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, ctx->stream));
+    }
+    if (b->nb_dmvr) {
+        DmvrK::Args t;
+        t.mc = a; t.mc.items = b->d_items + 3 * b->max_items; t.mc.nb_items = b->nb_dmvr; t.out = b->d_dmvr;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<DmvrK>(t, dim3(OVGPU_CEIL_DIV(b->nb_dmvr, DmvrK::WARPS), 1, 1), DmvrK::SMEM_BYTES, ctx->stream));
     }
     if (b->nb_prof_items) {
         ProfK::Args t;
@@ -230,6 +244,18 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                                                 ProfK::SMEM_BYTES, ctx->stream));
     }
     return 0;
+}
+
+int ovgpu_mc_batch_read_dmvr(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUDmvrMv *out, int max)
+{
+    if (!ctx || !b || (max > 0 && !out)) return OVGPU_EINVAL;
+    const int n = b->nb_dmvr < max ? b->nb_dmvr : max;
+    if (n > 0) {
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->h_dmvr, b->d_dmvr, sizeof(DmvrMvDev) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(out, b->h_dmvr, sizeof(DmvrMvDev) * n);
+    }
+    return b->nb_dmvr;
 }
 
 } // extern "C"

@@ -49,6 +49,9 @@ static inline int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
     if (c->tool == OVGPU_MC_TOOL_PROF)      /* rcn_prof_mcp_b_l: 4x4 luma sub-block, table entry must exist */
         return (c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA && (int)(c->aux >> 8) < nb_prof &&
                 (c->inter_dir == 3 || (c->aux & 3) == c->inter_dir)) ? 0 : -1;
+    if (c->tool == OVGPU_MC_TOOL_DMVR)      /* rcn_dmvr_mv_refine: bi-predicted 8/16-sample sub-block, luma and chroma, no BCW */
+        return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 4 && c->log2_h >= 3 && c->log2_h <= 4 &&
+                (c->flags & 3) == 3 && (c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3)) ? 0 : -1;
     return -1;
 }
 

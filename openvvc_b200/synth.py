@@ -200,10 +200,10 @@ def mc_commands(w, h, seed=1004, log2_ctu=7, n_refs=2, p_bi=0.7, mv_range=64, mi
     return cmds
 
 
-MC_TOOL_PLAIN, MC_TOOL_BDOF, MC_TOOL_PROF = 0, 1, 2
+MC_TOOL_PLAIN, MC_TOOL_BDOF, MC_TOOL_PROF, MC_TOOL_DMVR = 0, 1, 2, 3
 
 
-def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_log2=3, p_bdof=0.3, p_affine=0.2):
+def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_log2=3, p_bdof=0.3, p_affine=0.2, p_dmvr=0.0):
     """PU list with BDOF and affine/PROF coding units mixed in (25 % of eligible bi blocks BDOF, 15 %
     affine 4x4).  Returns (cmds, prof_table): BDOF CUs become <=16x16 luma sub-block commands (tool 1) + one chroma
     command; affine CUs become 4x4 luma commands (tool 2 with PROF, or plain 6-tap) + 8x8-luma chroma commands with the
@@ -237,7 +237,19 @@ def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_lo
         if hpel:
             mv0 = (mv0[0] & ~7, mv0[1] & ~7); mv1 = (mv1[0] & ~7, mv1[1] & ~7)
         kind = rng.random()
-        if lw >= 3 and lh >= 3 and lw + lh >= 7 and kind < p_bdof:
+        if lw >= 3 and lh >= 3 and lw + lh >= 7 and kind >= 1.0 - p_dmvr:
+            # DMVR CU (vcl_coding_unit.c:2600-2647): luma + chroma per <= 16x16 sub-block, the refinement starts from the
+            # CU's MVs for every sub-block; MVs of the two lists roughly mirrored like true bi-prediction
+            sw, sh = min(lw, 4), min(lh, 4)
+            if rng.random() < 0.7:
+                mv1 = (-mv0[0] + int(rng.integers(-40, 41)), -mv0[1] + int(rng.integers(-40, 41)))
+                if hpel:
+                    mv1 = (mv1[0] & ~7, mv1[1] & ~7)
+            bd = int(rng.random() < 0.6)
+            for oy in range(0, 1 << lh, 1 << sh):
+                for ox in range(0, 1 << lw, 1 << sw):
+                    new(x + ox, y + oy, sw, sh, 3, 3 | hpel, r0, r1, mv0, mv1, tool=MC_TOOL_DMVR, aux=bd)
+        elif lw >= 3 and lh >= 3 and lw + lh >= 7 and kind < p_bdof:
             # BDOF CU (vcl_coding_unit.c:2648-2672): luma per <= 16x16 sub-block, chroma for the whole CU
             sw, sh = min(lw, 4), min(lh, 4)
             for oy in range(0, 1 << lh, 1 << sh):

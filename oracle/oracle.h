@@ -100,6 +100,9 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
 #define OVO_MC_TOOL_BDOF  1     /* rcn_bdof_mcp_l (rcn_inter.c:1137): one <= 16x16 luma sub-block, bi-prediction      */
 #define OVO_MC_TOOL_PROF  2     /* rcn_prof_mcp_b_l (rcn_inter.c:2865): one 4x4 affine luma sub-block;                 *
                                  * aux = prof_dir (bits 0-1) | index into the PROF table << 8                          */
+#define OVO_MC_TOOL_DMVR  3     /* rcn_dmvr_mv_refine (rcn_inter.c:873): one <= 16x16 sub-block, luma AND chroma;          *
+                                 * aux bit 0 = apply_bdof.  The refined MVs are an OUTPUT (fed back to TMVP on the CPU).   */
+typedef struct OVODmvrMv { int32_t mv0_x, mv0_y, mv1_x, mv1_y; } OVODmvrMv;
 typedef struct OVOProfInfo {    /* struct PROFInfo, rcn_inter.c:1128-1134 */
     int16_t dmv_scale_h_0[16], dmv_scale_v_0[16], dmv_scale_h_1[16], dmv_scale_v_1[16];
 } OVOProfInfo;
@@ -128,6 +131,10 @@ void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, 
 void ovo_mc_picture2(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
                      const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
                      const OVOProfInfo *prof_tab);
+/* same, and the refined MVs of the DMVR commands (in command order) are written to dmvr_out (may be NULL) */
+void ovo_mc_picture3(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
+                     const OVOProfInfo *prof_tab, OVODmvrMv *dmvr_out);
 
 /* ---- LMCS ------------------------------------------------------------------------------------------- */
 typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */

@@ -166,14 +166,12 @@ static void pad_replicate(int16_t *B, int w, int h)
 
 static int floor_log2u(unsigned v) { int n = -1; while (v) { v >>= 1; n++; } return n; }
 
-static void bdof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVOMcCmd *c, int pic_w, int pic_h, int bitdepth)
+/* BDOF on two padded 14-bit predictions whose ring holds the integer reference samples (rcn_bdof_mcp_l tail,
+ * rcn_inter.c:1215-1244; also the BDOF branch of rcn_dmvr_mv_refine, :1018-1056) */
+static void bdof_core(uint16_t *d, int stride, int16_t *P0, int16_t *P1, int w, int h, int bitdepth)
 {
-    int w = 1 << c->log2_w, h = 1 << c->log2_h, maxv = (1 << bitdepth) - 1;
-    int16_t P0[PS * PS], P1[PS * PS], gx0[PS * PS], gy0[PS * PS], gx1[PS * PS], gy1[PS * PS];
-    MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
-    int hpel = (c->flags & OVO_MC_HPEL_AMVR) != 0;
-    padded_pred14(P0, refs, 0, c->ref_idx0, pic_w, pic_h, c->x0, c->y0, w, h, mv0, hpel, bitdepth);
-    padded_pred14(P1, refs, 1, c->ref_idx1, pic_w, pic_h, c->x0, c->y0, w, h, mv1, hpel, bitdepth);
+    int maxv = (1 << bitdepth) - 1;
+    int16_t gx0[PS * PS], gy0[PS * PS], gx1[PS * PS], gy1[PS * PS];
     pad_grad(gx0, gy0, P0, w, h); pad_grad(gx1, gy1, P1, w, h);
     pad_replicate(gx0, w, h); pad_replicate(gy0, w, h); pad_replicate(gx1, w, h); pad_replicate(gy1, w, h);
     pad_replicate(P0, w, h); pad_replicate(P1, w, h);          /* "reference padding overwrite", rcn_inter.c:1233-1235 */
@@ -206,6 +204,195 @@ static void bdof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVO
                     d[(size_t)(sy + y) * stride + sx + x] = (uint16_t)clipi(v, 0, maxv);
                 }
         }
+}
+
+static void bdof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVOMcCmd *c, int pic_w, int pic_h, int bitdepth)
+{
+    int w = 1 << c->log2_w, h = 1 << c->log2_h;
+    int16_t P0[PS * PS], P1[PS * PS];
+    MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
+    int hpel = (c->flags & OVO_MC_HPEL_AMVR) != 0;
+    padded_pred14(P0, refs, 0, c->ref_idx0, pic_w, pic_h, c->x0, c->y0, w, h, mv0, hpel, bitdepth);
+    padded_pred14(P1, refs, 1, c->ref_idx1, pic_w, pic_h, c->x0, c->y0, w, h, mv1, hpel, bitdepth);
+    bdof_core(d, stride, P0, P1, w, h, bitdepth);
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * DMVR (rcn_dmvr_mv_refine, rcn_inter.c:873-1126)
+ * ------------------------------------------------------------------------------------------------- */
+/* The DMVR reference window: the (w + 7) x (h + 7) samples around the block at the CLIPPED integer MV (picture
+ * borders replicated, derive_dmvr_ref_buf_y :432-471), itself extended by replication (padd_dmvr :354-378):
+ * sample at window coordinates (x, y), x in -5 .. w + 5 */
+typedef struct { RefPlane r; int bx, by, w, h, before, after; } DmvrWin;
+static inline int dwin(const DmvrWin *d, int x, int y)
+{
+    return rpx(&d->r, d->bx + clipi(x, -d->before, d->w + d->after), d->by + clipi(y, -d->before, d->h + d->after));
+}
+
+static int div_for_maxq7(int64_t num, int64_t den)
+{   /* rcn_inter.c:758-797 */
+    int sign = 0, q = 0;
+    if (num < 0) { sign = 1; num = -num; }
+    den <<= 3;
+    if (num >= den) { num -= den; q++; }
+    q <<= 1; den >>= 1;
+    if (num >= den) { num -= den; q++; }
+    q <<= 1;
+    if (num >= (den >> 1)) q++;
+    return sign ? -q : q;
+}
+
+static void dmvr_block(uint16_t *const dst[3], const int dst_stride[3], const OVOMcRefs *refs, const OVOMcCmd *c,
+                       int pic_w, int pic_h, int bitdepth, OVODmvrMv *out)
+{
+    int w = 1 << c->log2_w, h = 1 << c->log2_h, maxv = (1 << bitdepth) - 1;
+    MV mv[2] = { { c->mv0_x, c->mv0_y }, { c->mv1_x, c->mv1_y } }, org[2];
+    int ridx[2] = { c->ref_idx0, c->ref_idx1 };
+    DmvrWin win[2];
+    uint16_t bl[2][20 * 20];
+    org[0] = mv[0]; org[1] = mv[1];
+    for (int r = 0; r < 2; r++) {
+        MV mc = clip_mv(c->x0, c->y0, pic_w, pic_h, w, h, mv[r]);
+        win[r] = (DmvrWin){ { refs->plane[r][ridx[r]][0], refs->stride[r][ridx[r]][0], pic_w, pic_h },
+                            c->x0 + (mc.x >> 4), c->y0 + (mc.y >> 4), w, h, 3, 3 };
+        /* bilinear interpolation with two extra samples on every side (put_vvc_*_bilinear*, rcn_mc.c:789-897);
+         * the fraction comes from the UNCLIPPED MV (rcn_inter.c:911-915) */
+        int fx = mv[r].x & 15, fy = mv[r].y & 15;
+        for (int i = 0; i < h + 4; i++)
+            for (int j = 0; j < w + 4; j++) {
+                int x = j - 2, y = i - 2, v;
+                if (!fx && !fy) v = dwin(&win[r], x, y) << (10 - bitdepth);
+                else if (fx && !fy) v = ((16 - fx) * dwin(&win[r], x, y) + fx * dwin(&win[r], x + 1, y) + 8) >> 4;
+                else if (!fx && fy) v = ((16 - fy) * dwin(&win[r], x, y) + fy * dwin(&win[r], x, y + 1) + 8) >> 4;
+                else {
+                    int t0 = (int16_t)(((16 - fx) * dwin(&win[r], x, y) + fx * dwin(&win[r], x + 1, y) + 8) >> 4);
+                    int t1 = (int16_t)(((16 - fx) * dwin(&win[r], x, y + 1) + fx * dwin(&win[r], x + 1, y + 1) + 8) >> 4);
+                    v = ((16 - fy) * t0 + fy * t1 + 8) >> 4;
+                }
+                bl[r][i * 20 + j] = (uint16_t)v;
+            }
+    }
+    /* SAD on every other row (rcn_dmvr_sad_{8,16}, :615-665) */
+    uint64_t sad[25];
+    for (int idx = 0; idx < 25; idx++) {
+        int dx = idx % 5 - 2, dy = idx / 5 - 2;
+        uint64_t s = 0;
+        for (int i = 0; i < h; i += 2)
+            for (int j = 0; j < w; j++)
+                s += abs((int16_t)bl[0][(i + 2 + dy) * 20 + j + 2 + dx] - (int16_t)bl[1][(i + 2 - dy) * 20 + j + 2 - dx]);
+        sad[idx] = s;
+    }
+    uint64_t min_cost = sad[12] - (sad[12] >> 2);
+    if (min_cost >= (uint64_t)(w * h)) {
+        sad[12] = min_cost;
+        int best = 12;
+        uint64_t mc = (uint64_t)-1;
+        for (int idx = 0; idx < 25; idx++)                      /* dmvr_compute_sads_*, :700-706 */
+            if (sad[idx] < mc || (idx == 12 && sad[idx] <= mc)) { mc = sad[idx]; best = idx; }
+        int dh = (best % 5 - 2) << 4, dv = (best / 5 - 2) << 4;
+        min_cost = sad[best];
+        if (abs(dh) != 32 && abs(dv) != 32) {                   /* refine_mv, :799-833 */
+            const uint64_t *sb = &sad[best];
+            int64_t den_h = (int64_t)(sb[-1] + sb[1] - (sb[0] << 1)), den_v = (int64_t)(sb[-5] + sb[5] - (sb[0] << 1));
+            if (den_h) {
+                if (sb[-1] != sb[0] && sb[1] != sb[0]) dh += div_for_maxq7((int64_t)(sb[-1] << 4) - (int64_t)(sb[1] << 4), den_h);
+                else dh += sb[-1] == sb[0] ? -8 : 8;
+            }
+            if (den_v) {
+                if (sb[-5] != sb[0] && sb[5] != sb[0]) dv += div_for_maxq7((int64_t)((sb[-5] - sb[5]) << 4), den_v);
+                else dv += sb[-5] == sb[0] ? -8 : 8;
+            }
+        }
+        mv[0].x = clipi(mv[0].x + dh, -(1 << 17), (1 << 17) - 1); mv[0].y = clipi(mv[0].y + dv, -(1 << 17), (1 << 17) - 1);
+        mv[1].x = clipi(mv[1].x - dh, -(1 << 17), (1 << 17) - 1); mv[1].y = clipi(mv[1].y - dv, -(1 << 17), (1 << 17) - 1);
+    }
+    if (out) { out->mv0_x = mv[0].x; out->mv0_y = mv[0].y; out->mv1_x = mv[1].x; out->mv1_y = mv[1].y; }
+    int disable_bdof = (c->aux & 1) ? min_cost < (uint64_t)(2 * w * h) : 1;
+    /* final 8-tap prediction from the padded window, shifted by the integer part of the refinement */
+    int hpel = (c->flags & OVO_MC_HPEL_AMVR) != 0;
+    int16_t P[2][PS * PS];
+    for (int r = 0; r < 2; r++) {
+        int px = mv[r].x & 15, py = mv[r].y & 15;
+        if (hpel) { if (px == 8) px = 16; if (py == 8) py = 16; }
+        const int8_t *fx = px ? mc_filt_l[px - 1] : NULL, *fy = py ? mc_filt_l[py - 1] : NULL;
+        int ox = (mv[r].x >> 4) - (org[r].x >> 4), oy = (mv[r].y >> 4) - (org[r].y >> 4), sh1 = bitdepth - 8;
+        win[r].before = 5; win[r].after = 5;                 /* reads beyond +-3 / w+3 see the replicated border */
+        DmvrWin *d = &win[r];
+#define DW(x_, y_) rpx(&d->r, d->bx + clipi((x_), -3, d->w + 3), d->by + clipi((y_), -3, d->h + 3))
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int v, X = x + ox, Y = y + oy;
+                if (!fx && !fy) v = DW(X, Y) << (14 - bitdepth);
+                else if (fx && !fy) { int s = 0; for (int k = 0; k < 8; k++) s += fx[k] * DW(X + k - 3, Y); v = s >> sh1; }
+                else if (!fx && fy) { int s = 0; for (int k = 0; k < 8; k++) s += fy[k] * DW(X, Y + k - 3); v = s >> sh1; }
+                else {
+                    int s2 = 0;
+                    for (int j = 0; j < 8; j++) {
+                        int s = 0;
+                        for (int k = 0; k < 8; k++) s += fx[k] * DW(X + k - 3, Y + j - 3);
+                        s2 += fy[j] * (int16_t)(s >> sh1);
+                    }
+                    v = s2 >> 6;
+                }
+                P[r][(y + 1) * PS + x + 1] = (int16_t)v;
+            }
+        if (!disable_bdof) {                                  /* extend_bdof_buff on the shifted window */
+            int ex = (px >> 3) != 0, ey = (py >> 3) != 0, sh = 14 - bitdepth;
+            for (int i = 0; i < w + 2; i++) {
+                P[r][i] = (int16_t)(DW(ox - 1 + i + ex, oy - 1 + ey) << sh);
+                P[r][(h + 1) * PS + i] = (int16_t)(DW(ox - 1 + i + ex, oy + h + ey) << sh);
+            }
+            for (int j = 0; j < h; j++) {
+                P[r][(j + 1) * PS] = (int16_t)(DW(ox - 1 + ex, oy + j + ey) << sh);
+                P[r][(j + 1) * PS + w + 1] = (int16_t)(DW(ox + w + ex, oy + j + ey) << sh);
+            }
+        }
+#undef DW
+    }
+    uint16_t *dy = dst[0] + (size_t)c->y0 * dst_stride[0] + c->x0;
+    if (disable_bdof) {
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int o = (y + 1) * PS + x + 1;
+                dy[(size_t)y * dst_stride[0] + x] = (uint16_t)clipi((P[0][o] + P[1][o] + (1 << (14 - bitdepth))) >> (15 - bitdepth), 0, maxv);
+            }
+    } else bdof_core(dy, dst_stride[0], P[0], P[1], w, h, bitdepth);
+    /* chroma: window at the clipped ORIGINAL MV, fraction and integer shift from the refined MV (:1079-1124) */
+    int wc = w >> 1, hc = h >> 1;
+    for (int comp = 1; comp < 3; comp++) {
+        int16_t Pc[2][8 * 8];
+        for (int r = 0; r < 2; r++) {
+            MV mc = clip_mv(c->x0, c->y0, pic_w, pic_h, w, h, org[r]);
+            RefPlane rp = { refs->plane[r][ridx[r]][comp], refs->stride[r][ridx[r]][comp], pic_w >> 1, pic_h >> 1 };
+            int bx = (c->x0 >> 1) + (mc.x >> 5), by = (c->y0 >> 1) + (mc.y >> 5);
+            int px = mv[r].x & 31, py = mv[r].y & 31, sh1 = bitdepth - 8;
+            int ox = (mv[r].x >> 5) - (org[r].x >> 5), oy = (mv[r].y >> 5) - (org[r].y >> 5);
+            const int8_t *fx = px ? mc_filt_c[px - 1] : NULL, *fy = py ? mc_filt_c[py - 1] : NULL;
+#define DC(x_, y_) rpx(&rp, bx + clipi((x_), -1, wc + 1), by + clipi((y_), -1, hc + 1))
+            for (int y = 0; y < hc; y++)
+                for (int x = 0; x < wc; x++) {
+                    int v, X = x + ox, Y = y + oy;
+                    if (!fx && !fy) v = DC(X, Y) << (14 - bitdepth);
+                    else if (fx && !fy) { int s = 0; for (int k = 0; k < 4; k++) s += fx[k] * DC(X + k - 1, Y); v = s >> sh1; }
+                    else if (!fx && fy) { int s = 0; for (int k = 0; k < 4; k++) s += fy[k] * DC(X, Y + k - 1); v = s >> sh1; }
+                    else {
+                        int s2 = 0;
+                        for (int j = 0; j < 4; j++) {
+                            int s = 0;
+                            for (int k = 0; k < 4; k++) s += fx[k] * DC(X + k - 1, Y + j - 1);
+                            s2 += fy[j] * (int16_t)(s >> sh1);
+                        }
+                        v = s2 >> 6;
+                    }
+                    Pc[r][y * 8 + x] = (int16_t)v;
+                }
+#undef DC
+        }
+        uint16_t *dc = dst[comp] + (size_t)(c->y0 >> 1) * dst_stride[comp] + (c->x0 >> 1);
+        for (int y = 0; y < hc; y++)
+            for (int x = 0; x < wc; x++)
+                dc[(size_t)y * dst_stride[comp] + x] = (uint16_t)clipi((Pc[0][y * 8 + x] + Pc[1][y * 8 + x] + (1 << (14 - bitdepth))) >> (15 - bitdepth), 0, maxv);
+    }
 }
 
 static void prof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVOMcCmd *c, const OVOProfInfo *pi,
@@ -252,13 +439,22 @@ void ovo_mc_picture2(uint16_t *const dst[3], const int dst_stride[3], int pic_w,
                      const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
                      const OVOProfInfo *prof_tab)
 {
+    ovo_mc_picture3(dst, dst_stride, pic_w, pic_h, bitdepth, refs, cmds, nb_cmds, lmcs_fwd_lut, prof_tab, NULL);
+}
+
+void ovo_mc_picture3(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
+                     const OVOProfInfo *prof_tab, OVODmvrMv *dmvr_out)
+{
+    int nb_dmvr = 0;
     int16_t *p0 = malloc(2 * 128 * 128 * sizeof(int16_t)), *p1 = p0 + 128 * 128;   /* per call: thread-safe */
     int maxv = (1 << bitdepth) - 1;
     for (int i = 0; i < nb_cmds; i++) {
         const OVOMcCmd *c = &cmds[i];
-        if (c->tool == OVO_MC_TOOL_BDOF || c->tool == OVO_MC_TOOL_PROF) {
+        if (c->tool == OVO_MC_TOOL_BDOF || c->tool == OVO_MC_TOOL_PROF || c->tool == OVO_MC_TOOL_DMVR) {
             uint16_t *d = dst[0] + (size_t)c->y0 * dst_stride[0] + c->x0;
             if (c->tool == OVO_MC_TOOL_BDOF) bdof_block(d, dst_stride[0], refs, c, pic_w, pic_h, bitdepth);
+            else if (c->tool == OVO_MC_TOOL_DMVR) { dmvr_block(dst, dst_stride, refs, c, pic_w, pic_h, bitdepth, dmvr_out ? &dmvr_out[nb_dmvr] : NULL); nb_dmvr++; }
             else prof_block(d, dst_stride[0], refs, c, &prof_tab[c->aux >> 8], pic_w, pic_h, bitdepth);
             if (lmcs_fwd_lut)
                 for (int y = 0; y < (1 << c->log2_h); y++)

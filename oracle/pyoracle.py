@@ -223,7 +223,10 @@ def make_mc_refs(ref_lists, pocs):
     return r, keep
 
 
-def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl="port", lmcs=None, prof=None, simd=1):
+DmvrMv = np.dtype([("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32)])
+
+
+def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl="port", lmcs=None, prof=None, simd=1, dmvr_out=None):
     """Writes the predictions of all commands into dst_planes (in place) and returns them.
     prof: int16 array [n][4][16] (struct PROFInfo: dmv_scale_h_0, v_0, h_1, v_1) indexed by tool-2 commands."""
     h, w = dst_planes[0].shape
@@ -232,10 +235,12 @@ def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl=
     dst, ds = _planes_arg(dst_planes)
     prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
     pp = prof.ctypes.data_as(C.c_void_p) if prof is not None else None
+    # dmvr_out: DmvrMv array with one entry per tool-3 command (refined MVs, in command order)
+    po_ = dmvr_out.ctypes.data_as(C.c_void_p) if dmvr_out is not None else None
     if impl == "port":
         lut = lmcs.np("fwd_lut").ctypes.data_as(u16p) if lmcs is not None else None
-        port().ovo_mc_picture2(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut, pp)
+        port().ovo_mc_picture3(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut, pp, po_)
     else:
         ref().ovref_mc_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(refs), cmds.ctypes.data_as(C.c_void_p),
-                               len(cmds), pp, C.byref(lmcs) if lmcs is not None else None)
+                               len(cmds), pp, C.byref(lmcs) if lmcs is not None else None, po_)
     return dst_planes

@@ -269,7 +269,7 @@ ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
 void
 ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
                  int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const OVOProfInfo *prof_tab,
-                 const OVOLmcsLuts *lmcs)
+                 const OVOLmcsLuts *lmcs, OVODmvrMv *dmvr_out)
 {
     OVCTUDec *c;
     OVPartInfo part;
@@ -333,7 +333,10 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
         OVMV mv0 = { .x = m->mv0_x, .y = m->mv0_y, .ref_idx = m->ref_idx0, .bcw_idx_plus1 = m->bcw_idx_plus1 };
         OVMV mv1 = { .x = m->mv1_x, .y = m->mv1_y, .ref_idx = m->ref_idx1, .bcw_idx_plus1 = m->bcw_idx_plus1 };
         ic->prec_amvr = (m->flags & OVO_MC_HPEL_AMVR) ? 3 /* MV_PRECISION_HALF, drv_utils.h:102 */ : 0;
-        if (m->tool == OVO_MC_TOOL_BDOF)
+        if (m->tool == OVO_MC_TOOL_DMVR) {
+            c->rcn_funcs.rcn_dmvr_mv_refine(c, b, x0, y0, m->log2_w, m->log2_h, &mv0, &mv1, m->ref_idx0, m->ref_idx1, m->aux & 1);
+            if (dmvr_out) { dmvr_out->mv0_x = mv0.x; dmvr_out->mv0_y = mv0.y; dmvr_out->mv1_x = mv1.x; dmvr_out->mv1_y = mv1.y; dmvr_out++; }
+        } else if (m->tool == OVO_MC_TOOL_BDOF)
             c->rcn_funcs.rcn_bdof_mcp_l(c, b, x0, y0, m->log2_w, m->log2_h, mv0, mv1, m->ref_idx0, m->ref_idx1);
         else if (m->tool == OVO_MC_TOOL_PROF)      /* struct PROFInfo (rcn_inter.c:1128) has OVOProfInfo's layout */
             c->rcn_funcs.rcn_prof_mcp_b_l(c, b, ic, &part, mv0, mv1, x0, y0, 2, 2, m->inter_dir, m->ref_idx0, m->ref_idx1,

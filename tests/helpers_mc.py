@@ -29,19 +29,33 @@ def mc_tools_case(po, w, h, seed, log2_ctu=7, lmcs=False, min_log2=3, n_refs=2):
     return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof
 
 
-def emu_mc(emu, po, w, h, refs0, refs1, pocs, cmds, luts, bitdepth=10, prof=None):
+def emu_mc(emu, po, w, h, refs0, refs1, pocs, cmds, luts, bitdepth=10, prof=None, dmvr_out=None):
     out = blank(w, h)
     refs, keep = po.make_mc_refs([refs0, refs1], pocs)
     dst, ds = po._planes_arg(out)
     lut = luts.np("fwd_lut").ctypes.data_as(po.u16p) if luts is not None else None
     prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
     n = emu.emu_mc_picture(dst, ds, w, h, bitdepth, C.byref(refs), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut,
-                           prof.ctypes.data_as(C.c_void_p) if prof is not None else None, len(prof) if prof is not None else 0)
+                           prof.ctypes.data_as(C.c_void_p) if prof is not None else None, len(prof) if prof is not None else 0,
+                           dmvr_out.ctypes.data_as(C.c_void_p) if dmvr_out is not None else None)
     assert n >= 0, "emu rejected command %d" % (-n - 1)
     return out
 
 
-def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None):
+def mc_dmvr_case(po, w, h, seed, log2_ctu=7, lmcs=False, kind="natural"):
+    """PU list with DMVR / BDOF / affine CUs; list-1 references are shifted noisy copies of list 0 so that the SAD search
+    finds real minima.  Returns (refs0, refs1, pocs, cmds, luts, prof)."""
+    refs0 = [synth.planes(w, h, seed + 10 + i, kind) for i in range(2)]
+    rng = np.random.default_rng(seed)
+    refs1 = [[np.clip(np.roll(p, (int(rng.integers(-2, 3)), int(rng.integers(-2, 3))), axis=(0, 1)).astype(int) + rng.integers(-3, 4, size=p.shape),
+                      0, 1023).astype(np.uint16) for p in refs0[i]] for i in range(2)]
+    pocs = [[8, 16], [16, 24]]
+    cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, p_dmvr=0.4)
+    luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
+    return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof
+
+
+def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None, dmvr_out=None):
     from openvvc_b200 import api
     dst = ctx.picture(w, h)
     dst.upload(blank(w, h))
@@ -57,6 +71,8 @@ def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None):
         C.memmove(C.byref(gl), C.byref(luts), C.sizeof(gl))
         lm = api.Lmcs(ctx, gl)
     batch.run(dst, pics, pocs, lm)
+    if dmvr_out is not None:
+        dmvr_out[:] = batch.read_dmvr(len(dmvr_out))
     out = dst.download()
     batch.destroy(); dst.destroy()
     if lm:

@@ -192,3 +192,85 @@ def test_tools_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
     a = helpers_mc.blank(w, h)
     oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="ref" if oracle.ref_available() else "port", lmcs=luts, prof=prof)
     helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=prof), a, "CUDA MC tools vs reference at 4K")
+
+
+# ================================================================================================ DMVR
+DMVR_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_dmvr_golden.json")))
+DIDS = lambda c: "%dx%d_ctu%d_%s%s" % (c["w"], c["h"], 1 << c["log2_ctu"], c["kind"], "_lmcs" if c["lmcs"] else "")
+
+
+def _dmvr_case(po, c):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_dmvr_case(po, c["w"], c["h"], c["seed"], c["log2_ctu"], c["lmcs"], c["kind"])
+    assert helpers.md5(cmds, prof, *refs0[0], *refs1[-1]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return refs0, refs1, pocs, cmds, luts, prof, np.zeros(c["nb_dmvr"], oracle_dmvr_dtype(po))
+
+
+def oracle_dmvr_dtype(po):
+    return po.DmvrMv
+
+
+@pytest.mark.parametrize("c", DMVR_GOLDEN, ids=DIDS)
+def test_dmvr_port_matches_golden(oracle, c):
+    refs0, refs1, pocs, cmds, luts, prof, mvs = _dmvr_case(oracle, c)
+    dst = helpers_mc.blank(c["w"], c["h"])
+    oracle.mc_picture(dst, [refs0, refs1], pocs, cmds, c["log2_ctu"], impl="port", lmcs=luts, prof=prof, dmvr_out=mvs)
+    assert [helpers.md5(p) for p in dst] == c["md5"] and helpers.md5(mvs) == c["mv_md5"]
+    dm = cmds[cmds["tool"] == 3]
+    assert ((mvs["mv0_x"] != dm["mv0_x"]) | (mvs["mv0_y"] != dm["mv0_y"])).mean() > 0.3      # the search really moves MVs
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs,kind", [(416, 240, 7, False, "natural"), (416, 240, 7, True, "blocky"), (832, 480, 7, True, "natural"),
+                                                 (264, 136, 6, False, "natural")])
+def test_dmvr_port_vs_compiled_reference(oracle, w, h, log2, lmcs, kind):
+    """rcn_dmvr_mv_refine: pixels (luma + chroma) and refined MVs, port vs the reference's scalar C and SSE/AVX2 table"""
+    po = oracle
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_dmvr_case(po, w, h, 5 * w + h + 2, log2, lmcs, kind)
+    nd = int((cmds["tool"] == 3).sum())
+    ma = np.zeros(nd, po.DmvrMv)
+    a = helpers_mc.blank(w, h)
+    po.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts, prof=prof, dmvr_out=ma)
+    for simd in (0, 1):
+        mb = np.zeros(nd, po.DmvrMv)
+        b = helpers_mc.blank(w, h)
+        po.mc_picture(b, [refs0, refs1], pocs, cmds, log2, impl="ref", lmcs=luts, prof=prof, simd=simd, dmvr_out=mb)
+        helpers.assert_planes_equal(a, b, "DMVR port vs reference (simd=%d)" % simd)
+        assert (ma == mb).all(), "refined MVs differ (simd=%d)" % simd
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs,kind", [(416, 240, 7, False, "natural"), (416, 240, 7, True, "blocky"), (256, 128, 6, True, "natural"),
+                                                 (832, 480, 7, False, "natural")])
+def test_dmvr_emulated_kernel_matches_oracle(oracle, emu, w, h, log2, lmcs, kind):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_dmvr_case(oracle, w, h, 7 * w + h + 2, log2, lmcs, kind)
+    nd = int((cmds["tool"] == 3).sum())
+    ma, mb = np.zeros(nd, oracle.DmvrMv), np.zeros(nd, oracle.DmvrMv)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts, prof=prof, dmvr_out=ma)
+    b = helpers_mc.emu_mc(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts, prof=prof, dmvr_out=mb)
+    helpers.assert_planes_equal(b, a, "emulated DMVR kernel vs oracle")
+    assert (ma == mb).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", DMVR_GOLDEN, ids=DIDS)
+def test_dmvr_gpu_matches_golden(oracle, gpu_ctx, c):
+    from openvvc_b200 import api
+    refs0, refs1, pocs, cmds, luts, prof, _ = _dmvr_case(oracle, c)
+    mvs = np.zeros(c["nb_dmvr"], api.DMVR_MV)
+    out = helpers_mc.gpu_mc(gpu_ctx, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, prof=prof, dmvr_out=mvs)
+    assert [helpers.md5(p) for p in out] == c["md5"] and helpers.md5(mvs) == c["mv_md5"]
+
+
+@pytest.mark.gpu
+def test_dmvr_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
+    """BASELINE.json config 4 flavour (affine + BDOF + DMVR heavy inter) at 3840x2160: CUDA vs the compiled reference"""
+    from openvvc_b200 import api
+    w, h = 3840, 2160
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_dmvr_case(oracle, w, h, 83, 7, True)
+    nd = int((cmds["tool"] == 3).sum())
+    ma, mb = np.zeros(nd, oracle.DmvrMv), np.zeros(nd, api.DMVR_MV)
+    a = helpers_mc.blank(w, h)
+    oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="ref" if oracle.ref_available() else "port", lmcs=luts, prof=prof, dmvr_out=ma)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=prof, dmvr_out=mb), a, "CUDA DMVR vs reference at 4K")
+    assert helpers.md5(ma) == helpers.md5(mb)
