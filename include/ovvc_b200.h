@@ -309,6 +309,29 @@ int  ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, 
 /* deblocks pic in place: all vertical edges, then all horizontal edges (luma and chroma). Asynchronous. */
 int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p);
 
+/* ---- Intra prediction  (replaces the intra_pred slot: vvc_intra_pred, rcn_intra.c:484-560) ---------------------------- */
+/* One luma intra block (no ISP / MRL / MIP / BDPCM in this revision).  avail_cols / avail_rows are the two words the
+ * reference reads from its progress bit-field at call time: rcn_ctx.progress_field.vfield[x0 >> 2] and .hfield[y0 >> 2]
+ * (CTU-local x0 / y0; bit 0 = the unit in the neighbouring CTU line, bit 1 + u = 4x4 unit u, rcn_structures.h:81-85).
+ * They are decode-order information, so the recorder copies them; the samples come from the picture on the GPU. */
+typedef struct OVGPUIntraCmd {
+    int16_t x0, y0;               /* picture-absolute luma samples */
+    uint8_t log2_w, log2_h;
+    uint8_t mode;                 /* ctudec->intra_mode: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
+    uint8_t flags;                /* reserved */
+    uint64_t avail_cols, avail_rows;
+} OVGPUIntraCmd;
+
+typedef struct OVGPUIntraBatch OVGPUIntraBatch;
+int  ovgpu_intra_batch_create(OVGPUCtx *ctx, int max_cmds, OVGPUIntraBatch **b);
+void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b);
+/* cmds in decode order; the host sorts them into dependency levels (blocks of a level only read blocks of lower levels) */
+int  ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
+                              int pic_w, int pic_h, int log2_ctu_s);
+int  ovgpu_intra_batch_levels(const OVGPUIntraBatch *b);
+/* predicts every block into pic (one launch per dependency level); neighbours are read from pic. Asynchronous. */
+int  ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch *b);
+
 #ifdef __cplusplus
 }
 #endif

@@ -452,6 +452,33 @@ class DbfParams:
             self.p = vp()
 
 
+class IntraBatch:
+    """Luma intra blocks of one picture, sorted into dependency levels on the host (ovgpu_intra_batch_*)."""
+
+    def __init__(self, ctx, max_cmds):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_intra_batch_create(ctx.h, int(max_cmds), C.byref(self.p)), "intra_batch_create")
+
+    def upload(self, cmds, w, h, log2_ctu=7, ctx=None):
+        from .synth_intra import INTRA_CMD
+        cmds = np.ascontiguousarray(cmds, dtype=INTRA_CMD)
+        self._keep = cmds
+        _check((ctx or self.ctx).h, lib().ovgpu_intra_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds), w, h, log2_ctu),
+               "intra_batch_upload")
+
+    def levels(self):
+        return int(lib().ovgpu_intra_batch_levels(self.p))
+
+    def run(self, pic, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_intra_picture((ctx or self.ctx).h, pic.p, self.p), "intra_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_intra_batch_destroy(self.p)
+            self.p = vp()
+
+
 def mc_nb_items(cmds):
     """work items a PU list expands to: <=16x16 blocks of plain commands + one per BDOF / PROF command"""
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))

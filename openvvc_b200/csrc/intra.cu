@@ -1,0 +1,89 @@
+// intra.cu -- C-ABI entry points of luma intra prediction (kernel in intra_kernels.h, scheduling in intra_host.h).
+// Replaces the intra_pred slot (vvc_intra_pred, libovvc/rcn_intra.c:484) for the intra blocks of a picture.
+#include "common.cuh"
+#include "intra_host.h"
+#include <stdlib.h>
+
+static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 24, "intra command layout");
+
+struct OVGPUIntraBatch {
+    int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu;
+    IntraCmdDev *h_cmds, *d_cmds;
+    uint32_t *h_order, *d_order, *level_start;      // level_start: host only, max_cmds + 2 entries
+    StagingFence fence;
+};
+
+extern "C" {
+
+int ovgpu_intra_batch_create(OVGPUCtx *ctx, int max_cmds, OVGPUIntraBatch **out)
+{
+    if (!ctx || !out || max_cmds <= 0) return OVGPU_EINVAL;
+    OVGPUIntraBatch *b = (OVGPUIntraBatch *)calloc(1, sizeof(*b));
+    if (!b) return OVGPU_ENOMEM;
+    b->max_cmds = max_cmds; b->device = ctx->device;
+    b->level_start = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)max_cmds + 3));
+    if (!b->level_start ||
+        cudaMallocHost(&b->h_cmds, sizeof(IntraCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMallocHost(&b->h_order, sizeof(uint32_t) * max_cmds) != cudaSuccess ||
+        cudaMalloc(&b->d_cmds, sizeof(IntraCmdDev) * max_cmds) != cudaSuccess ||
+        cudaMalloc(&b->d_order, sizeof(uint32_t) * max_cmds) != cudaSuccess) {
+        ovgpu_intra_batch_destroy(b);
+        return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = b;
+    return 0;
+}
+
+void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->h_cmds) cudaFreeHost(b->h_cmds);
+    if (b->h_order) cudaFreeHost(b->h_order);
+    if (b->d_cmds) cudaFree(b->d_cmds);
+    if (b->d_order) cudaFree(b->d_order);
+    free(b->level_start);
+    fence_destroy(&b->fence);
+    free(b);
+}
+
+int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
+                             int pic_w, int pic_h, int log2_ctu_s)
+{
+    if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || (nb_cmds && !cmds) || log2_ctu_s < 5 || log2_ctu_s > 7 ||
+        pic_w <= 0 || pic_h <= 0 || (pic_w & 7) || (pic_h & 7))
+        return OVGPU_EINVAL;
+    for (int i = 0; i < nb_cmds; i++)
+        if (intra_check_cmd(&cmds[i], pic_w, pic_h)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->nb_levels = 0;
+    if (!nb_cmds) return 0;
+    memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
+    b->nb_levels = intra_build_levels(b->h_order, b->level_start, b->max_cmds, cmds, nb_cmds, pic_w, pic_h);
+    if (b->nb_levels < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_order, b->h_order, sizeof(uint32_t) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+    return 0;
+}
+
+int ovgpu_intra_batch_levels(const OVGPUIntraBatch *b) { return b ? b->nb_levels : OVGPU_EINVAL; }
+
+int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch *b)
+{
+    if (!ctx || !pic || !b) return OVGPU_EINVAL;
+    if (!b->nb_cmds) return 0;
+    if (pic->width != b->pic_w || pic->height != b->pic_h)
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
+    PlaneView v = plane_view(pic, 0);
+    StageScope scope(ctx, OVGPU_STAGE_INTRA, b->nb_levels);
+    for (int l = 0; l < b->nb_levels; l++) {
+        const int start = (int)b->level_start[l], n = (int)b->level_start[l + 1] - start;
+        if (n <= 0) continue;
+        IntraK::Args a = { v.p, v.pitch, b->log2_ctu, pic->bitdepth, b->d_cmds, b->d_order + start, n };
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), 1, 1), IntraK::SMEM_BYTES, ctx->stream));
+    }
+    return 0;
+}
+
+} // extern "C"

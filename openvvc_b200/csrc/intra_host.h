@@ -1,0 +1,54 @@
+// intra_host.h -- dependency levels of a picture's intra blocks, shared by intra.cu and tests/emu.
+#pragma once
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "../../include/ovvc_b200.h"
+#include "intra_kernels.h"
+
+static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
+{
+    if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->mode > 66 || c->x0 < 0 || c->y0 < 0) return -1;
+    if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;
+    return 0;
+}
+
+// level[i] = 1 + the highest level among earlier blocks that cover one of block i's reference samples (left column of
+// 2h + 1 and above row of 2w + 1 samples, on the 4x4 unit grid).  order[] = command indices sorted by level (stable),
+// level_start[l] .. level_start[l + 1] = the blocks of level l (0-based).  Returns the number of levels or -1.
+static inline int intra_build_levels(uint32_t *order, uint32_t *level_start, int max_levels, const OVGPUIntraCmd *cmds, int n,
+                                     int pic_w, int pic_h)
+{
+    const int w_u = pic_w >> 2, h_u = pic_h >> 2;
+    uint16_t *lvl_map = (uint16_t *)calloc((size_t)w_u * h_u, sizeof(uint16_t));
+    uint16_t *lvl = (uint16_t *)malloc(sizeof(uint16_t) * (n > 0 ? n : 1));
+    if (!lvl_map || !lvl) { free(lvl_map); free(lvl); return -1; }
+    int nb_levels = 0;
+    for (int i = 0; i < n; i++) {
+        const OVGPUIntraCmd *c = &cmds[i];
+        const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
+        int m = 0;
+        if (xu > 0)
+            for (int y = yu - 1; y < yu + 2 * nh && y < h_u; y++) if (y >= 0 && lvl_map[y * w_u + xu - 1] > m) m = lvl_map[y * w_u + xu - 1];
+        if (yu > 0)
+            for (int x = xu - 1; x < xu + 2 * nw && x < w_u; x++) if (x >= 0 && lvl_map[(yu - 1) * w_u + x] > m) m = lvl_map[(yu - 1) * w_u + x];
+        if (m + 1 > 65535 || m + 1 > max_levels) { free(lvl_map); free(lvl); return -1; }
+        lvl[i] = (uint16_t)(m + 1);
+        if (m + 1 > nb_levels) nb_levels = m + 1;
+        for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) lvl_map[y * w_u + x] = lvl[i];
+    }
+    // counting sort by level
+    memset(level_start, 0, sizeof(uint32_t) * (nb_levels + 2));
+    for (int i = 0; i < n; i++) level_start[lvl[i]]++;                 // counts at index level (1-based)
+    uint32_t acc = 0;
+    for (int l = 1; l <= nb_levels; l++) { uint32_t cnt = level_start[l]; level_start[l] = acc; acc += cnt; }
+    level_start[nb_levels + 1] = acc;
+    uint32_t *fill = (uint32_t *)malloc(sizeof(uint32_t) * (nb_levels + 2));
+    if (!fill) { free(lvl_map); free(lvl); return -1; }
+    memcpy(fill, level_start, sizeof(uint32_t) * (nb_levels + 2));
+    for (int i = 0; i < n; i++) order[fill[lvl[i]]++] = (uint32_t)i;
+    // shift to 0-based: level_start[l] for l in 0..nb_levels
+    for (int l = 0; l <= nb_levels; l++) level_start[l] = level_start[l + 1];
+    free(fill); free(lvl_map); free(lvl);
+    return nb_levels;
+}

@@ -1,0 +1,229 @@
+// intra_kernels.h -- luma intra prediction of a list of coding units (sm_100a; also compiled by tests/emu).
+//
+// Reference behaviour: vvc_intra_pred (libovvc/rcn_intra.c:484-560): reference sample fill with availability-driven
+// substitution (libovvc/rcn_fill_ref.c:71-145, 320-390), [1 2 1] reference filter (:47-68), planar / DC with PDPC
+// (libovvc/rcn_intra_dc_planar.c:151-236), wide-angle remapping and the angular dispatch (rcn_intra.c:55-481), angular
+// kernels with cubic / Gaussian 4-tap interpolation and PDPC (libovvc/rcn_intra_angular.c:102-930).
+//
+// Intra blocks depend on the RECONSTRUCTED samples of earlier blocks, so the host sorts the blocks of a picture into
+// dependency levels (a block's level = 1 + the highest level among the blocks its reference samples come from) and
+// launches one grid per level; inside a level every block is independent.  One warp per block: phase 0 builds the
+// two reference arrays in shared memory, phase 1 their filtered copies, phase 2 the negative-index extension, phase 3
+// predicts -- each lane computes samples straight from the arrays with closed-form per-sample expressions (the
+// horizontal class is the vertical class on swapped roles), so there is no transposition pass.
+#pragma once
+#include "dev.h"
+
+struct IntraCmdDev {          // == OVGPUIntraCmd
+    int16_t x0, y0;
+    uint8_t log2_w, log2_h, mode, flags;
+    uint64_t avail_cols, avail_rows;
+};
+
+OVD_CONST int16_t intra_angle_tab[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29,
+                                          32, 35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+OVD_CONST int16_t intra_inv_angle_tab[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170, 1024, 910, 819, 712, 630, 565,
+                                              512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
+OVD_CONST uint8_t intra_filter_thr[8] = { 24, 24, 24, 14, 2, 0, 0, 0 };
+OVD_CONST uint8_t intra_wide_shift[6] = { 0, 6, 10, 12, 14, 15 };
+OVD_CONST int8_t intra_cubic[32][4] = {
+    { 0, 64, 0, 0 }, { -1, 63, 2, 0 }, { -2, 62, 4, 0 }, { -2, 60, 7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+    { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 }, { -6, 49, 24, -3 },
+    { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 }, { -4, 36, 36, -4 }, { -4, 33, 39, -4 },
+    { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 }, { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 },
+    { -2, 16, 54, -4 }, { -2, 15, 55, -4 }, { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 },
+    { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
+
+struct IntraK {
+    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 4;
+    static const int WARPS = 4;
+    static const int REF_OFF = 64, REF_LEN = 64 + 2 * 64 + 8;        // 64 negative-extension slots + 2 * 64 + 1 + 4 samples
+    static const int SM_WARP = 4 * REF_LEN * 2;                      // abv, lft, filtered abv, filtered lft (uint16)
+    static const int SMEM_BYTES = WARPS * SM_WARP;
+
+    struct Args {
+        uint16_t *plane;
+        int pitch, log2_ctu, bitdepth;
+        const IntraCmdDev *cmds;
+        const uint32_t *order;      // command indices of this level
+        int nb;
+    };
+    struct State { int dummy; };
+
+    // everything the phases derive from the command (warp-uniform)
+    struct Blk {
+        int valid, x0, y0, lw, lh, mode;            // mode as signalled: 0 planar, 1 DC, 2..66 angular
+        int vert;                                    // angular: vertical class
+        int mlw, mlh;                                // block size as seen by the class (swapped for the horizontal class)
+        int mode_idx, a, angle, inv, frac, gauss, pdpc_scale, use_pdpc, filt_m, filt_s, ext;
+        uint64_t cols, rows;
+    };
+
+    OVD int floor_log2(unsigned v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
+    OVD int pdpc_w(int scale, int pos) { const int s = (pos << 1) >> scale; return s > 5 ? 0 : 32 >> s; }
+
+    OVD Blk load(const Args &a, int idx)
+    {
+        Blk b;
+        b.valid = idx < a.nb;
+        if (!b.valid) return b;
+        const IntraCmdDev &c = a.cmds[a.order[idx]];
+        b.x0 = c.x0; b.y0 = c.y0; b.lw = c.log2_w; b.lh = c.log2_h; b.cols = c.avail_cols; b.rows = c.avail_rows;
+        int mode = c.mode;
+        b.mode = mode;                                 // 0 planar, 1 DC, else angular (the remapped value lives in mode_idx)
+        b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
+        b.mode_idx = b.a = b.angle = b.inv = b.frac = b.gauss = b.pdpc_scale = b.use_pdpc = b.filt_m = b.filt_s = b.ext = 0;
+        if (mode > 1) {
+            const int d = b.lw - b.lh, ms = intra_wide_shift[d < 0 ? -d : d];                  // derive_wide_angular_mode
+            if (b.lw > b.lh && mode < 2 + ms) mode += 65;
+            else if (b.lh > b.lw && mode > 66 - ms) mode -= 65;
+            b.vert = mode >= 34;
+            b.mode_idx = b.vert ? mode - 50 : 18 - mode;
+            if (!b.vert) { b.mlw = b.lh; b.mlh = b.lw; }
+            b.a = b.mode_idx < 0 ? -b.mode_idx : b.mode_idx;
+            b.gauss = (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
+            if (b.a == 0) {
+                b.use_pdpc = b.gauss || b.mlh > 1;
+            } else if (b.mode_idx == 16) {
+                b.use_pdpc = b.gauss || b.mlh > 1;
+                b.pdpc_scale = ovd_min(2, b.mlh - 2);
+                b.filt_m = b.filt_s = b.gauss;
+            } else {
+                b.angle = intra_angle_tab[b.a]; b.inv = intra_inv_angle_tab[b.a];
+                b.frac = (b.angle & 31) != 0;
+                b.pdpc_scale = ovd_min(2, b.mlh - (floor_log2((unsigned)(3 * b.inv - 2)) - 8));
+                const int f = b.gauss && !b.frac;                                              // integer slope: filtered references
+                if (b.mode_idx < 0) { b.ext = 1; b.filt_m = b.filt_s = f; b.angle = -b.angle; }
+                else if (b.pdpc_scale < 0 || (!b.gauss && b.mlh < 2)) { b.filt_m = f; }
+                else { b.filt_m = b.filt_s = f; b.use_pdpc = 1; }
+            }
+        } else if (mode == 0) {
+            b.filt_m = b.filt_s = (b.lw + b.lh) > 5;                                           // planar: rcn_intra.c:531-538
+        }
+        return b;
+    }
+
+    // fill_ref_left_0 / fill_ref_above_0 (offset 0): one lane per sample
+    OVD void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane)
+    {
+        const int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1;
+        const uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask;
+        int nb_avl = 0;
+        for (uint64_t t = avl; t; t >>= 1) nb_avl++;                                           // 64 - clz
+        int pad = 1 << (bitdepth - 1);
+        if (!avl) {
+            const int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
+            const uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+            if (avl_o) pad = p[other_step];
+        } else if (nb_avl > 1) pad = p[(size_t)(4 * (nb_avl - 1)) * step];
+        else pad = p[0];                                                                       // only the corner unit: its sample
+        for (int i = lane; i < ref_len + 4; i += 32) {
+            int v = pad;
+            const int k = ovd_min(i, ref_len - 1);                                             // wide-angle padding repeats the last sample
+            if (avl) {
+                if (k == 0) v = (avl & 1) ? p[0] : p[step];
+                else if (1 + ((k - 1) >> 2) < nb_avl) v = p[(size_t)k * step];
+            }
+            ref[i] = (uint16_t)v;
+        }
+    }
+
+    // one sample of the vertical-class prediction at (x along the main reference, y across)
+    OVD int class_pixel(const Blk &b, const uint16_t *M, const uint16_t *S, int tl, int x, int y, int maxv)
+    {
+        const int W = 1 << b.mlw;
+        if (b.a == 0) {
+            if (!b.use_pdpc) return M[x + 1];
+            return ovd_clamp((pdpc_w((b.lw + b.lh - 2) >> 2, x) * (S[y + 1] - tl) + (M[x + 1] << 6) + 32) >> 6, 0, maxv);
+        }
+        if (b.mode_idx == 16) {
+            int v = M[x + y + 2];
+            if (b.use_pdpc && x < ovd_min(3 << b.pdpc_scale, W))
+                v = ovd_clamp(v + (((32 >> ((2 * x) >> b.pdpc_scale)) * (S[y + x + 2] - v) + 32) >> 6), 0, maxv);
+            return v;
+        }
+        const int delta = (y + 1) * b.angle, di = delta >> 5, df = delta & 31;
+        int v;
+        if (!b.frac) v = M[x + di + 1];
+        else {
+            const uint16_t *r = M + x + di;
+            if (b.gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
+            else v = ovd_clamp((r[0] * intra_cubic[df][0] + r[1] * intra_cubic[df][1] + r[2] * intra_cubic[df][2] + r[3] * intra_cubic[df][3] + 32) >> 6, 0, maxv);
+        }
+        if (b.use_pdpc && x < ovd_min(3 << b.pdpc_scale, W)) {
+            const int wL = 32 >> ((x << 1) >> b.pdpc_scale), left = S[y + ((256 + (x + 1) * b.inv) >> 9) + 1];
+            v = ovd_clamp(v + ((wL * (left - v) + 32) >> 6), 0, maxv);
+        }
+        return v;
+    }
+
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        const int warp = tid >> 5, lane = tid & 31;
+        const Blk b = load(a, bx * WARPS + warp);
+        if (!b.valid) return;
+        uint16_t *base = (uint16_t *)(smem + warp * SM_WARP);
+        uint16_t *abv = base + REF_OFF, *lft = base + REF_LEN + REF_OFF, *fabv = base + 2 * REF_LEN + REF_OFF, *flft = base + 3 * REF_LEN + REF_OFF;
+        const int w = 1 << b.lw, h = 1 << b.lh, maxv = (1 << a.bitdepth) - 1, cm = (1 << a.log2_ctu) - 1;
+        uint16_t *dst = a.plane + (size_t)b.y0 * a.pitch + b.x0;
+
+        if (P == 0) {
+            const uint16_t *corner = dst - a.pitch - 1;
+            fill_ref(lft, corner, a.pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane);
+            fill_ref(abv, corner, 1, a.pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane);
+            return;
+        }
+        if (P == 1) {
+            // filter_ref_samples over 2 * len samples of both arrays (the consumers read inside that range)
+            for (int i = lane; i <= 2 * w; i += 32)
+                fabv[i] = (uint16_t)(i == 0 ? (lft[1] + (abv[0] << 1) + abv[1] + 2) >> 2 : (i == 2 * w ? abv[i] : (abv[i + 1] + (abv[i] << 1) + abv[i - 1] + 2) >> 2));
+            for (int i = lane; i <= 2 * h; i += 32)
+                flft[i] = (uint16_t)(i == 0 ? (abv[1] + (lft[0] << 1) + lft[1] + 2) >> 2 : (i == 2 * h ? lft[i] : (lft[i + 1] + (lft[i] << 1) + lft[i - 1] + 2) >> 2));
+            return;
+        }
+        // roles of the arrays for the block's class
+        uint16_t *M = b.vert ? (b.filt_m ? fabv : abv) : (b.filt_m ? flft : lft);
+        const uint16_t *S = b.vert ? (b.filt_s ? flft : lft) : (b.filt_s ? fabv : abv);
+        if (P == 2) {
+            if (b.ext) {                                                    // rcn_intra.c:118-121
+                const int H = 1 << b.mlh;
+                for (int k = 1 + lane; k <= H; k += 32) M[-k] = S[ovd_min((256 + k * b.inv) >> 9, H)];
+            }
+            return;
+        }
+        if (P == 3) {
+            const int tl = abv[0];
+            if (b.mode == 0) {                                              // intra_planar_pdpc
+                const uint16_t *A = b.filt_m ? fabv : abv, *L = b.filt_m ? flft : lft;
+                const int ws = ovd_max(b.lw, 1), hs = ovd_max(b.lh, 1), scale = (b.lw + b.lh - 2) >> 2;
+                for (int o = lane; o < w * h; o += 32) {
+                    const int x = o & (w - 1), y = o >> b.lw;
+                    const int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
+                    const int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
+                    const int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
+                    dst[(size_t)y * a.pitch + x] = (uint16_t)ovd_clamp((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv);
+                }
+            } else if (b.mode == 1) {                                       // intra_dc_pdpc
+                const int shift = ovd_max(b.lw, b.lh) + (b.lw == b.lh), scale = (b.lw + b.lh - 2) >> 2;
+                int dc = 0;
+                if (b.lw >= b.lh) for (int i = 0; i < w; i++) dc += abv[1 + i];
+                if (b.lw <= b.lh) for (int i = 0; i < h; i++) dc += lft[1 + i];
+                dc = (dc + ((1 << shift) >> 1)) >> shift;
+                for (int o = lane; o < w * h; o += 32) {
+                    const int x = o & (w - 1), y = o >> b.lw;
+                    const int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
+                    dst[(size_t)y * a.pitch + x] = (uint16_t)ovd_clamp((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv);
+                }
+            } else {
+                for (int o = lane; o < w * h; o += 32) {
+                    const int x = o & (w - 1), y = o >> b.lw;
+                    const int v = b.vert ? class_pixel(b, M, S, tl, x, y, maxv) : class_pixel(b, M, S, tl, y, x, maxv);
+                    dst[(size_t)y * a.pitch + x] = (uint16_t)v;
+                }
+            }
+        }
+    }
+};

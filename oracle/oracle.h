@@ -213,6 +213,20 @@ typedef struct OVODbfMaps {
 /* in place on the picture: all vertical edges, then all horizontal edges, luma and chroma (rcn_df.c) */
 void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth, const OVODbfMaps *maps);
 
+/* ---- Intra prediction ------------------------------------------------------------------------------------ */
+/* One rcn_funcs.intra_pred call (vvc_intra_pred, rcn_intra.c:484-560): luma block, no ISP / MRL / MIP / BDPCM.
+ * avail_cols / avail_rows are progress_field.vfield[x0 >> 2] / .hfield[y0 >> 2] at call time (CTU-local, bit 0 = the
+ * unit of the neighbouring CTU line, bit 1 + u = 4x4 unit u): syntax-order information recorded on the CPU. */
+typedef struct OVOIntraCmd {
+    int16_t x0, y0;              /* picture-absolute */
+    uint8_t log2_w, log2_h;
+    uint8_t mode;                /* 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
+    uint8_t flags;
+    uint64_t avail_cols, avail_rows;
+} OVOIntraCmd;
+void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                       const OVOIntraCmd *cmds, int nb_cmds);
+
 #ifdef __cplusplus
 }
 #endif

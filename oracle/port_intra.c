@@ -1,0 +1,191 @@
+/* oracle/port_intra.c -- TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Restatement of OpenVVC's luma intra prediction: vvc_intra_pred (libovvc/rcn_intra.c:484-560) with the reference
+ * sample fill of libovvc/rcn_fill_ref.c (fill_ref_left_0 :71-145, fill_ref_above_0 :320-390, filter_ref_samples
+ * :47-68), planar / DC with PDPC (libovvc/rcn_intra_dc_planar.c:151-236), the angular dispatch (rcn_intra.c:55-481)
+ * and kernels (libovvc/rcn_intra_angular.c:102-930; angle tables libovvc/data_rcn_angular.c:37-60).
+ * The horizontal class is the vertical class on the transposed block with the roles of the two reference arrays
+ * swapped, which is how it is written here.
+ */
+#include "oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+static inline int clipi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static int floor_log2u(unsigned v) { int n = -1; while (v) { v >>= 1; n++; } return n; }
+
+static const int angle_table[32] = { 0, 1, 2, 3, 4, 6, 8, 10, 12, 14, 16, 18, 20, 23, 26, 29,
+                                     32, 35, 39, 45, 51, 57, 64, 73, 86, 102, 128, 171, 256, 341, 512, 1024 };
+static const int inv_angle_table[32] = { 0, 16384, 8192, 5461, 4096, 2731, 2048, 1638, 1365, 1170, 1024, 910, 819, 712, 630, 565,
+                                         512, 468, 420, 364, 321, 287, 256, 224, 191, 161, 128, 96, 64, 48, 32, 16 };
+static const uint8_t intra_filter_thr[8] = { 24, 24, 24, 14, 2, 0, 0, 0 };
+/* cubic interpolation taps = the chroma MC filter (rcn_intra_angular.c:43-77) */
+static const int8_t cubic[32][4] = {
+    { 0, 64, 0, 0 }, { -1, 63, 2, 0 }, { -2, 62, 4, 0 }, { -2, 60, 7, -1 }, { -2, 58, 10, -2 }, { -3, 57, 12, -2 },
+    { -4, 56, 14, -2 }, { -4, 55, 15, -2 }, { -4, 54, 16, -2 }, { -5, 53, 18, -2 }, { -6, 52, 20, -2 }, { -6, 49, 24, -3 },
+    { -6, 46, 28, -4 }, { -5, 44, 29, -4 }, { -4, 42, 30, -4 }, { -4, 39, 33, -4 }, { -4, 36, 36, -4 }, { -4, 33, 39, -4 },
+    { -4, 30, 42, -4 }, { -4, 29, 44, -5 }, { -4, 28, 46, -6 }, { -3, 24, 49, -6 }, { -2, 20, 52, -6 }, { -2, 18, 53, -5 },
+    { -2, 16, 54, -4 }, { -2, 15, 55, -4 }, { -2, 14, 56, -4 }, { -2, 12, 57, -3 }, { -2, 10, 58, -2 }, { -1, 7, 60, -2 },
+    { 0, 4, 62, -2 }, { 0, 2, 63, -1 } };
+
+static inline int pdpc_w(int scale, int pos) { int s = (pos << 1) >> scale; return s > 5 ? 0 : 32 >> s; }   /* vvc_pdpc_w[scale][pos] */
+
+enum { REF_OFF = 128, REF_LEN = 128 + 2 * 128 + 16 };
+
+/* fill_ref_left_0 / fill_ref_above_0 with offset 0: ref[0] = corner, ref[1 + i] = i-th neighbour, 2 * len + 1 samples + 4
+ * of wide-angle padding.  `step` walks along the neighbour line, `p` points at the corner sample. */
+static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                     uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth)
+{
+    int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1;
+    uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask, navl = avl ^ mask;
+    if (!navl) {
+        for (int i = 0; i < ref_len; i++) ref[i] = p[i * step];
+    } else if (avl) {
+        int nb_avl = 64 - __builtin_clzll(avl), i;
+        ref[0] = (avl & 1) ? p[0] : p[step];
+        for (i = 1; i < nb_avl; i++)
+            for (int k = 0; k < 4; k++) ref[1 + 4 * (i - 1) + k] = p[(1 + 4 * (i - 1) + k) * step];
+        uint16_t pad = ref[4 * (nb_avl - 1)];
+        for (; i < nb_units; i++)
+            for (int k = 0; k < 4; k++) ref[1 + 4 * (i - 1) + k] = pad;
+    } else {
+        int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
+        uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+        uint16_t pad = avl_o ? p[other_step] : (uint16_t)(1 << (bitdepth - 1));     /* first sample of the other line */
+        for (int i = 0; i < ref_len; i++) ref[i] = pad;
+    }
+    for (int i = 0; i < 4; i++) ref[ref_len + i] = ref[ref_len - 1];
+}
+
+/* filter_ref_samples, rcn_fill_ref.c:47-68 */
+static void filter_ref(uint16_t *dst, const uint16_t *src, const uint16_t *src2, int length)
+{
+    dst[0] = (uint16_t)((src2[1] + (src[0] << 1) + src[1] + 2) >> 2);
+    for (int i = 1; i < length; i++) dst[i] = (uint16_t)((src[i + 1] + (src[i] << 1) + src[i - 1] + 2) >> 2);
+    dst[length] = src[length];
+}
+
+/* vertical-class angular prediction of a W x H block (W along the main reference): out[y * W + x].
+ * M = main reference (M[0] corner, negative indices writable), S = side reference, tl = ref_above[0]. */
+static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv)
+{
+    int W = 1 << lw, H = 1 << lh, a = abs(mode_idx);
+    int gauss = (lw + lh) > 5 && a > intra_filter_thr[(lw + lh) >> 1];
+    uint16_t fM[REF_LEN], fS[REF_LEN];
+    if (a == 0) {                                                  /* pure vertical: intra_angular_ver(_pdpc) */
+        int pd = gauss || lh > 1, scale = (lw + lh - 2) >> 2;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+                out[y * W + x] = pd ? clipi((pdpc_w(scale, x) * (S[y + 1] - tl) + (M[x + 1] << 6) + 32) >> 6, 0, maxv) : M[x + 1];
+        return;
+    }
+    if (mode_idx == 16) {                                          /* pure diagonal: intra_angular_vdia(_pdpc) */
+        int pd = gauss || lh > 1, scale = imin(2, lh - 2);
+        if (gauss) {
+            filter_ref(fM + REF_OFF, M, S, 2 * W); filter_ref(fS + REF_OFF, S, M, 2 * H);
+            M = fM + REF_OFF; S = fS + REF_OFF;
+        }
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                int v = M[x + y + 2];
+                if (pd && x < imin(3 << scale, W)) v = clipi(v + (((32 >> ((2 * x) >> scale)) * (S[y + x + 2] - v) + 32) >> 6), 0, maxv);
+                out[y * W + x] = v;
+            }
+        return;
+    }
+    int angle = angle_table[a], inv = inv_angle_table[a], frac = (angle & 31) != 0;
+    int pdpc_scale = imin(2, lh - (floor_log2u(3 * inv - 2) - 8));
+    int use_pdpc = 0;
+    if (mode_idx < 0) {
+        if (gauss && !frac) {                                      /* integer slope: [1 2 1]-filtered references */
+            filter_ref(fM + REF_OFF, M, S, 2 * W); filter_ref(fS + REF_OFF, S, M, 2 * H);
+            M = fM + REF_OFF; S = fS + REF_OFF;
+        }
+        for (int k = -1, sum = 256; k >= -H; k--) { sum += inv; M[k] = S[imin(sum >> 9, H)]; }     /* rcn_intra.c:118-121 */
+        angle = -angle;
+    } else if (pdpc_scale < 0 || (!gauss && lh < 2)) {
+        if (gauss && !frac) { filter_ref(fM + REF_OFF, M, S, 2 * W); M = fM + REF_OFF; }
+    } else {
+        if (gauss && !frac) {
+            filter_ref(fM + REF_OFF, M, S, 2 * W); filter_ref(fS + REF_OFF, S, M, 2 * H);
+            M = fM + REF_OFF; S = fS + REF_OFF;
+        }
+        use_pdpc = 1;
+    }
+    for (int y = 0; y < H; y++) {
+        int delta = (y + 1) * angle, di = delta >> 5, df = delta & 31;
+        for (int x = 0; x < W; x++) {
+            int v;
+            if (!frac) v = M[x + di + 1];
+            else {
+                const uint16_t *r = M + x + di;
+                if (gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
+                else       v = clipi((r[0] * cubic[df][0] + r[1] * cubic[df][1] + r[2] * cubic[df][2] + r[3] * cubic[df][3] + 32) >> 6, 0, maxv);
+            }
+            if (use_pdpc && x < imin(3 << pdpc_scale, W)) {
+                int wL = 32 >> ((x << 1) >> pdpc_scale), left = S[y + ((256 + (x + 1) * inv) >> 9) + 1];
+                v = clipi(v + ((wL * (left - v) + 32) >> 6), 0, maxv);
+            }
+            out[y * W + x] = v;
+        }
+    }
+}
+
+static void intra_block(uint16_t *plane, int stride, int log2_ctu, int bitdepth, const OVOIntraCmd *c)
+{
+    int lw = c->log2_w, lh = c->log2_h, w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, cm = (1 << log2_ctu) - 1;
+    uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
+    uint16_t *dst = plane + (size_t)c->y0 * stride + c->x0;
+    const uint16_t *corner = dst - stride - 1;
+    fill_ref(lft, corner, stride, 1, lh, lw, c->avail_cols, c->avail_rows, c->y0 & cm, c->x0 & cm, bitdepth);
+    fill_ref(abv, corner, 1, stride, lw, lh, c->avail_rows, c->avail_cols, c->x0 & cm, c->y0 & cm, bitdepth);
+    int *out = malloc(sizeof(int) * w * h);
+    if (c->mode == 0) {                                            /* intra_planar_pdpc, rcn_intra_dc_planar.c:196-236 */
+        uint16_t fa[REF_LEN], fl[REF_LEN];
+        const uint16_t *A = abv, *L = lft;
+        if (lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
+        int ws = lw > 1 ? lw : 1, hs = lh > 1 ? lh : 1, scale = (lw + lh - 2) >> 2;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
+                int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
+                int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
+                out[y * w + x] = clipi((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv);
+            }
+    } else if (c->mode == 1) {                                     /* intra_dc_pdpc, :151-194 */
+        int shift = (lw > lh ? lw : lh) + (lw == lh), dc = 0, scale = (lw + lh - 2) >> 2;
+        if (lw >= lh) for (int i = 0; i < w; i++) dc += abv[1 + i];
+        if (lw <= lh) for (int i = 0; i < h; i++) dc += lft[1 + i];
+        dc = (dc + ((1 << shift) >> 1)) >> shift;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
+                out[y * w + x] = clipi((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv);
+            }
+    } else {
+        /* derive_wide_angular_mode, rcn_intra.c:55-66 */
+        static const uint8_t mode_shift_tab[6] = { 0, 6, 10, 12, 14, 15 };
+        int mode = c->mode, ms = mode_shift_tab[abs(lw - lh)];
+        if (lw > lh && mode < 2 + ms) mode += 65;
+        else if (lh > lw && mode > 66 - ms) mode -= 65;
+        if (mode >= 34) {
+            angular_class(out, abv, lft, abv[0], lw, lh, mode - 50, maxv);
+        } else {
+            int *t = malloc(sizeof(int) * w * h);
+            angular_class(t, lft, abv, abv[0], lh, lw, 18 - mode, maxv);
+            for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * w + x] = t[x * h + y];
+            free(t);
+        }
+    }
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[(size_t)y * stride + x] = (uint16_t)out[y * w + x];
+    free(out);
+}
+
+void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                       const OVOIntraCmd *cmds, int nb_cmds)
+{
+    (void)pic_w; (void)pic_h;
+    for (int i = 0; i < nb_cmds; i++) intra_block(planes[0], stride[0], log2_ctu_s, bitdepth, &cmds[i]);
+}

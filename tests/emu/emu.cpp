@@ -7,6 +7,7 @@
 #include "../../openvvc_b200/csrc/mc_host.h"
 #include "../../openvvc_b200/csrc/tr_host.h"
 #include "../../openvvc_b200/csrc/dbf_kernels.h"
+#include "../../openvvc_b200/csrc/intra_host.h"
 
 template <int GROUP>
 static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,
@@ -181,6 +182,20 @@ int emu_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth
     memcpy(&b, &a, sizeof(b));
     ovd_emulate<DbfK<1> >(b, grid, 0);
     return 0;
+}
+
+int emu_intra_picture(uint16_t *plane, int stride, int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
+{
+    for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
+    std::vector<uint32_t> order(n + 1), level_start(n + 3);
+    int nl = intra_build_levels(order.data(), level_start.data(), n + 1, cmds, n, w, h);
+    if (nl < 0) return -1000000;
+    for (int l = 0; l < nl; l++) {
+        int start = (int)level_start[l], cnt = (int)level_start[l + 1] - start;
+        IntraK::Args a = { plane, stride, log2_ctu, bitdepth, (const IntraCmdDev *)cmds, order.data() + start, cnt };
+        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, 1, 1), IntraK::SMEM_BYTES);
+    }
+    return nl;
 }
 
 }

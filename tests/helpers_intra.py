@@ -1,0 +1,35 @@
+"""Test helpers for intra prediction."""
+import ctypes as C
+
+import numpy as np
+
+from openvvc_b200 import synth, synth_intra
+
+
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural"):
+    """planes + intra commands in decode order with the availability words replayed from that order"""
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2), log2_ctu)
+    return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
+
+
+def emu_intra(emu, planes, cmds, log2_ctu=7, bitdepth=10):
+    out = [p.copy() for p in planes]
+    h, w = out[0].shape
+    nl = emu.emu_intra_picture(out[0].ctypes.data_as(C.c_void_p), out[0].strides[0] // 2, w, h, log2_ctu, bitdepth,
+                               cmds.ctypes.data_as(C.c_void_p), len(cmds))
+    assert nl >= 0, "emu rejected command %d" % (-nl - 1)
+    return out, nl
+
+
+def gpu_intra(ctx, planes, cmds, log2_ctu=7):
+    from openvvc_b200 import api
+    h, w = planes[0].shape
+    pic = ctx.picture(w, h)
+    pic.upload(planes)
+    b = api.IntraBatch(ctx, max(1, len(cmds)))
+    b.upload(cmds, w, h, log2_ctu)
+    nl = b.levels()
+    b.run(pic)
+    out = pic.download()
+    b.destroy(); pic.destroy()
+    return out, nl
