@@ -309,16 +309,22 @@ int  ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, 
 /* deblocks pic in place: all vertical edges, then all horizontal edges (luma and chroma). Asynchronous. */
 int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p);
 
-/* ---- Intra prediction  (replaces the intra_pred slot: vvc_intra_pred, rcn_intra.c:484-560) ---------------------------- */
-/* One luma intra block (no ISP / MRL / MIP / BDPCM in this revision).  avail_cols / avail_rows are the two words the
+/* ---- Intra prediction  (replaces the intra_pred slot: vvc_intra_pred, rcn_intra.c:484-560, and the intra_pred_c slot:
+ *      vvc_intra_pred_chroma, rcn_intra.c:1015-1182, planar / DC / angular modes) -------------------------------------- */
+/* One intra coding unit: a luma block and / or its 4:2:0 Cb + Cr blocks of half the size (no ISP / MRL / MIP / BDPCM /
+ * CCLM in this revision).  avail_cols / avail_rows are the two words the
  * reference reads from its progress bit-field at call time: rcn_ctx.progress_field.vfield[x0 >> 2] and .hfield[y0 >> 2]
  * (CTU-local x0 / y0; bit 0 = the unit in the neighbouring CTU line, bit 1 + u = 4x4 unit u, rcn_structures.h:81-85).
- * They are decode-order information, so the recorder copies them; the samples come from the picture on the GPU. */
+ * In a single tree progress_field_c holds the same words (rcn_tu_st marks both with the same rectangles), so the chroma
+ * blocks use them too.  They are decode-order information, so the recorder copies them; the samples come from the
+ * picture on the GPU. */
+#define OVGPU_INTRA_NO_LUMA 255   /* mode value: no luma block in this command */
+#define OVGPU_INTRA_CHROMA  0x80  /* flags bit: predict Cb and Cr with mode flags & 0x7f (0 planar, 1 DC, 2..66 angular; DM resolved) */
 typedef struct OVGPUIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
-    uint8_t log2_w, log2_h;
+    uint8_t log2_w, log2_h;       /* luma size */
     uint8_t mode;                 /* ctudec->intra_mode: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
-    uint8_t flags;                /* reserved */
+    uint8_t flags;                /* OVGPU_INTRA_CHROMA | chroma mode, or 0 */
     uint64_t avail_cols, avail_rows;
 } OVGPUIntraCmd;
 

@@ -1,5 +1,6 @@
-// intra.cu -- C-ABI entry points of luma intra prediction (kernel in intra_kernels.h, scheduling in intra_host.h).
-// Replaces the intra_pred slot (vvc_intra_pred, libovvc/rcn_intra.c:484) for the intra blocks of a picture.
+// intra.cu -- C-ABI entry points of luma + chroma intra prediction (kernel in intra_kernels.h, scheduling in intra_host.h).
+// Replaces the intra_pred / intra_pred_c slots (vvc_intra_pred, libovvc/rcn_intra.c:484; vvc_intra_pred_chroma, :1015)
+// for the intra blocks of a picture.
 #include "common.cuh"
 #include "intra_host.h"
 #include <stdlib.h>
@@ -7,7 +8,7 @@
 static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 24, "intra command layout");
 
 struct OVGPUIntraBatch {
-    int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu;
+    int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu, has_chroma;
     IntraCmdDev *h_cmds, *d_cmds;
     uint32_t *h_order, *d_order, *level_start;      // level_start: host only, max_cmds + 2 entries
     StagingFence fence;
@@ -59,6 +60,8 @@ int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntra
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->nb_levels = 0;
     if (!nb_cmds) return 0;
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
+    b->has_chroma = 0;
+    for (int i = 0; i < nb_cmds; i++) b->has_chroma |= cmds[i].flags & OVGPU_INTRA_CHROMA;
     b->nb_levels = intra_build_levels(b->h_order, b->level_start, b->max_cmds, cmds, nb_cmds, pic_w, pic_h);
     if (b->nb_levels < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
@@ -75,13 +78,13 @@ int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
     if (!b->nb_cmds) return 0;
     if (pic->width != b->pic_w || pic->height != b->pic_h)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
-    PlaneView v = plane_view(pic, 0);
+    PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);
     StageScope scope(ctx, OVGPU_STAGE_INTRA, b->nb_levels);
     for (int l = 0; l < b->nb_levels; l++) {
         const int start = (int)b->level_start[l], n = (int)b->level_start[l + 1] - start;
         if (n <= 0) continue;
-        IntraK::Args a = { v.p, v.pitch, b->log2_ctu, pic->bitdepth, b->d_cmds, b->d_order + start, n };
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), 1, 1), IntraK::SMEM_BYTES, ctx->stream));
+        IntraK::Args a = { { v0.p, v1.p, v2.p }, { v0.pitch, v1.pitch, v2.pitch }, b->log2_ctu, pic->bitdepth, b->d_cmds, b->d_order + start, n };
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), b->has_chroma ? 3 : 1, 1), IntraK::SMEM_BYTES, ctx->stream));
     }
     return 0;
 }

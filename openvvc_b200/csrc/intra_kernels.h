@@ -1,6 +1,10 @@
-// intra_kernels.h -- luma intra prediction of a list of coding units (sm_100a; also compiled by tests/emu).
+// intra_kernels.h -- luma + chroma intra prediction of a list of coding units (sm_100a; also compiled by tests/emu).
 //
-// Reference behaviour: vvc_intra_pred (libovvc/rcn_intra.c:484-560): reference sample fill with availability-driven
+// Chroma (vvc_intra_pred_chroma, libovvc/rcn_intra.c:1015-1182, planar / DC / angular, no CCLM): 2-sample availability
+// units (rcn_fill_ref.c:147-230, 392-480), no reference filtering, 2-tap linear interpolation (rcn_intra_angular.c:
+// 270-470), PDPC only when both sides are >= 4 samples.  Grid y = component (0 luma, 1 Cb, 2 Cr).
+//
+// Luma: vvc_intra_pred (libovvc/rcn_intra.c:484-560): reference sample fill with availability-driven
 // substitution (libovvc/rcn_fill_ref.c:71-145, 320-390), [1 2 1] reference filter (:47-68), planar / DC with PDPC
 // (libovvc/rcn_intra_dc_planar.c:151-236), wide-angle remapping and the angular dispatch (rcn_intra.c:55-481), angular
 // kernels with cubic / Gaussian 4-tap interpolation and PDPC (libovvc/rcn_intra_angular.c:102-930).
@@ -42,8 +46,8 @@ struct IntraK {
     static const int SMEM_BYTES = WARPS * SM_WARP;
 
     struct Args {
-        uint16_t *plane;
-        int pitch, log2_ctu, bitdepth;
+        uint16_t *plane[3];
+        int pitch[3], log2_ctu, bitdepth;
         const IntraCmdDev *cmds;
         const uint32_t *order;      // command indices of this level
         int nb;
@@ -52,7 +56,8 @@ struct IntraK {
 
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
-        int valid, x0, y0, lw, lh, mode;            // mode as signalled: 0 planar, 1 DC, 2..66 angular
+        int valid, chroma, pd;                       // pd: planar / DC use their PDPC variant
+        int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
         int mlw, mlh;                                // block size as seen by the class (swapped for the horizontal class)
         int mode_idx, a, angle, inv, frac, gauss, pdpc_scale, use_pdpc, filt_m, filt_s, ext;
@@ -62,14 +67,19 @@ struct IntraK {
     OVD int floor_log2(unsigned v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
     OVD int pdpc_w(int scale, int pos) { const int s = (pos << 1) >> scale; return s > 5 ? 0 : 32 >> s; }
 
-    OVD Blk load(const Args &a, int idx)
+    OVD Blk load(const Args &a, int idx, int comp)
     {
         Blk b;
         b.valid = idx < a.nb;
         if (!b.valid) return b;
         const IntraCmdDev &c = a.cmds[a.order[idx]];
-        b.x0 = c.x0; b.y0 = c.y0; b.lw = c.log2_w; b.lh = c.log2_h; b.cols = c.avail_cols; b.rows = c.avail_rows;
-        int mode = c.mode;
+        b.chroma = comp > 0;
+        b.valid = b.chroma ? (c.flags & 0x80) != 0 : c.mode != 255;
+        if (!b.valid) return b;
+        const int sh = b.chroma;
+        b.x0 = c.x0 >> sh; b.y0 = c.y0 >> sh; b.lw = c.log2_w - sh; b.lh = c.log2_h - sh; b.cols = c.avail_cols; b.rows = c.avail_rows;
+        b.pd = !b.chroma || (b.lw > 1 && b.lh > 1);
+        int mode = b.chroma ? (c.flags & 0x7f) : c.mode;
         b.mode = mode;                                 // 0 planar, 1 DC, else angular (the remapped value lives in mode_idx)
         b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
         b.mode_idx = b.a = b.angle = b.inv = b.frac = b.gauss = b.pdpc_scale = b.use_pdpc = b.filt_m = b.filt_s = b.ext = 0;
@@ -81,11 +91,11 @@ struct IntraK {
             b.mode_idx = b.vert ? mode - 50 : 18 - mode;
             if (!b.vert) { b.mlw = b.lh; b.mlh = b.lw; }
             b.a = b.mode_idx < 0 ? -b.mode_idx : b.mode_idx;
-            b.gauss = (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
+            b.gauss = !b.chroma && (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
             if (b.a == 0) {
-                b.use_pdpc = b.gauss || b.mlh > 1;
+                b.use_pdpc = b.chroma ? b.pd : (b.gauss || b.mlh > 1);
             } else if (b.mode_idx == 16) {
-                b.use_pdpc = b.gauss || b.mlh > 1;
+                b.use_pdpc = b.chroma ? b.pd : (b.gauss || b.mlh > 1);
                 b.pdpc_scale = ovd_min(2, b.mlh - 2);
                 b.filt_m = b.filt_s = b.gauss;
             } else {
@@ -94,36 +104,38 @@ struct IntraK {
                 b.pdpc_scale = ovd_min(2, b.mlh - (floor_log2((unsigned)(3 * b.inv - 2)) - 8));
                 const int f = b.gauss && !b.frac;                                              // integer slope: filtered references
                 if (b.mode_idx < 0) { b.ext = 1; b.filt_m = b.filt_s = f; b.angle = -b.angle; }
-                else if (b.pdpc_scale < 0 || (!b.gauss && b.mlh < 2)) { b.filt_m = f; }
+                else if (b.pdpc_scale < 0 || (!b.gauss && b.mlh < 2) || !b.pd) { b.filt_m = f; }
                 else { b.filt_m = b.filt_s = f; b.use_pdpc = 1; }
             }
         } else if (mode == 0) {
-            b.filt_m = b.filt_s = (b.lw + b.lh) > 5;                                           // planar: rcn_intra.c:531-538
+            b.filt_m = b.filt_s = !b.chroma && (b.lw + b.lh) > 5;                              // planar: rcn_intra.c:531-538
         }
         return b;
     }
 
     // fill_ref_left_0 / fill_ref_above_0 (offset 0): one lane per sample
     OVD void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
-                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane)
+                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int us, int left_chroma)
     {
-        const int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1;
-        const uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask;
+        // us = log2 of the availability unit in samples of this plane (2 luma, 1 chroma)
+        const int nb_units = ((1 << (log2_len + 1)) >> us) + 1, ref_len = (1 << (log2_len + 1)) + 1;
+        const uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> us)) & mask;
         int nb_avl = 0;
         for (uint64_t t = avl; t; t >>= 1) nb_avl++;                                           // 64 - clz
         int pad = 1 << (bitdepth - 1);
         if (!avl) {
-            const int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
-            const uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+            const int nb_units_o = ((1 << (log2_other + 1)) >> us) + 1;
+            const uint64_t avl_o = (other_map >> (other_pos >> us)) & ((1ull << (nb_units_o + 1)) - 1);
             if (avl_o) pad = p[other_step];
-        } else if (nb_avl > 1) pad = p[(size_t)(4 * (nb_avl - 1)) * step];
-        else pad = p[0];                                                                       // only the corner unit: its sample
+        } else if (nb_avl > 1) pad = p[(size_t)((nb_avl - 1) << us) * step];
+        else if (!left_chroma) pad = p[0];                                                     // only the corner unit: its sample
+        // (fill_ref_left_0_chroma keeps the mid value there, rcn_fill_ref.c:193-200)
         for (int i = lane; i < ref_len + 4; i += 32) {
             int v = pad;
             const int k = ovd_min(i, ref_len - 1);                                             // wide-angle padding repeats the last sample
             if (avl) {
                 if (k == 0) v = (avl & 1) ? p[0] : p[step];
-                else if (1 + ((k - 1) >> 2) < nb_avl) v = p[(size_t)k * step];
+                else if (1 + ((k - 1) >> us) < nb_avl) v = p[(size_t)k * step];
             }
             ref[i] = (uint16_t)v;
         }
@@ -148,7 +160,8 @@ struct IntraK {
         if (!b.frac) v = M[x + di + 1];
         else {
             const uint16_t *r = M + x + di;
-            if (b.gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
+            if (b.chroma) v = ovd_clamp(r[1] + ((df * (r[2] - r[1]) + 16) >> 5), 0, maxv);     // intra_angular_v_c
+            else if (b.gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
             else v = ovd_clamp((r[0] * intra_cubic[df][0] + r[1] * intra_cubic[df][1] + r[2] * intra_cubic[df][2] + r[3] * intra_cubic[df][3] + 32) >> 6, 0, maxv);
         }
         if (b.use_pdpc && x < ovd_min(3 << b.pdpc_scale, W)) {
@@ -161,19 +174,22 @@ struct IntraK {
     template <int P>
     OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
     {
-        (void)st; (void)by; (void)bz;
+        (void)st; (void)bz;
         const int warp = tid >> 5, lane = tid & 31;
-        const Blk b = load(a, bx * WARPS + warp);
+        const Blk b = load(a, bx * WARPS + warp, by);
         if (!b.valid) return;
+        uint16_t *plane = by == 0 ? a.plane[0] : (by == 1 ? a.plane[1] : a.plane[2]);
+        const int pitch = by == 0 ? a.pitch[0] : (by == 1 ? a.pitch[1] : a.pitch[2]);
         uint16_t *base = (uint16_t *)(smem + warp * SM_WARP);
         uint16_t *abv = base + REF_OFF, *lft = base + REF_LEN + REF_OFF, *fabv = base + 2 * REF_LEN + REF_OFF, *flft = base + 3 * REF_LEN + REF_OFF;
-        const int w = 1 << b.lw, h = 1 << b.lh, maxv = (1 << a.bitdepth) - 1, cm = (1 << a.log2_ctu) - 1;
-        uint16_t *dst = a.plane + (size_t)b.y0 * a.pitch + b.x0;
+        const int w = 1 << b.lw, h = 1 << b.lh, maxv = (1 << a.bitdepth) - 1, cm = (1 << (a.log2_ctu - b.chroma)) - 1;
+        const int us = 2 - b.chroma;
+        uint16_t *dst = plane + (size_t)b.y0 * pitch + b.x0;
 
         if (P == 0) {
-            const uint16_t *corner = dst - a.pitch - 1;
-            fill_ref(lft, corner, a.pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane);
-            fill_ref(abv, corner, 1, a.pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane);
+            const uint16_t *corner = dst - pitch - 1;
+            fill_ref(lft, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, us, b.chroma);
+            fill_ref(abv, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, us, 0);
             return;
         }
         if (P == 1) {
@@ -204,7 +220,7 @@ struct IntraK {
                     const int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
                     const int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
                     const int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
-                    dst[(size_t)y * a.pitch + x] = (uint16_t)ovd_clamp((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv);
+                    dst[(size_t)y * pitch + x] = (uint16_t)(b.pd ? ovd_clamp((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv) : v);
                 }
             } else if (b.mode == 1) {                                       // intra_dc_pdpc
                 const int shift = ovd_max(b.lw, b.lh) + (b.lw == b.lh), scale = (b.lw + b.lh - 2) >> 2;
@@ -215,13 +231,13 @@ struct IntraK {
                 for (int o = lane; o < w * h; o += 32) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
-                    dst[(size_t)y * a.pitch + x] = (uint16_t)ovd_clamp((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv);
+                    dst[(size_t)y * pitch + x] = (uint16_t)(b.pd ? ovd_clamp((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv) : dc);
                 }
             } else {
                 for (int o = lane; o < w * h; o += 32) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int v = b.vert ? class_pixel(b, M, S, tl, x, y, maxv) : class_pixel(b, M, S, tl, y, x, maxv);
-                    dst[(size_t)y * a.pitch + x] = (uint16_t)v;
+                    dst[(size_t)y * pitch + x] = (uint16_t)v;
                 }
             }
         }

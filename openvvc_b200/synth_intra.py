@@ -10,7 +10,10 @@ INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), 
 assert INTRA_CMD.itemsize == 24
 
 
-def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6):
+INTRA_NO_LUMA, INTRA_CHROMA = 255, 0x80
+
+
+def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False):
     rng = np.random.default_rng(seed)
     part = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
@@ -19,6 +22,11 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6):
         c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
         r = rng.random()
         c["mode"] = 0 if r < 0.15 else (1 if r < 0.3 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.4 else int(rng.integers(2, 67))))
+        if chroma:
+            # single tree: Cb / Cr blocks of half the size, mode = DM (the luma mode) or an explicit planar / DC / ver / hor / random
+            r = rng.random()
+            mc = int(c["mode"]) if r < 0.4 else (0 if r < 0.5 else (1 if r < 0.6 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.7 else int(rng.integers(2, 67)))))
+            c["flags"] = INTRA_CHROMA | mc
     return cmds
 
 

@@ -217,9 +217,12 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
 /* One rcn_funcs.intra_pred call (vvc_intra_pred, rcn_intra.c:484-560): luma block, no ISP / MRL / MIP / BDPCM.
  * avail_cols / avail_rows are progress_field.vfield[x0 >> 2] / .hfield[y0 >> 2] at call time (CTU-local, bit 0 = the
  * unit of the neighbouring CTU line, bit 1 + u = 4x4 unit u): syntax-order information recorded on the CPU. */
+#define OVO_INTRA_NO_LUMA 255    /* mode value: the command carries no luma block */
+#define OVO_INTRA_CHROMA  0x80   /* flags bit: Cb + Cr blocks of half the size are predicted (rcn_funcs.intra_pred_c) with mode  *
+                                  * flags & 0x7f (0 planar, 1 DC, 2..66 angular; DM already resolved; CCLM not supported)       */
 typedef struct OVOIntraCmd {
-    int16_t x0, y0;              /* picture-absolute */
-    uint8_t log2_w, log2_h;
+    int16_t x0, y0;              /* picture-absolute luma samples */
+    uint8_t log2_w, log2_h;      /* luma size */
     uint8_t mode;                /* 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
     uint8_t flags;
     uint64_t avail_cols, avail_rows;

@@ -35,24 +35,28 @@ enum { REF_OFF = 128, REF_LEN = 128 + 2 * 128 + 16 };
 
 /* fill_ref_left_0 / fill_ref_above_0 with offset 0: ref[0] = corner, ref[1 + i] = i-th neighbour, 2 * len + 1 samples + 4
  * of wide-angle padding.  `step` walks along the neighbour line, `p` points at the corner sample. */
+/* us = log2 of the availability unit in samples of this plane: 2 for luma, 1 for 4:2:0 chroma (fill_ref_*_0_chroma,
+ * rcn_fill_ref.c:147-230, 392-480).  left_chroma: fill_ref_left_0_chroma pads with the mid value when only the corner
+ * unit is available (its padding value is only updated inside the copy loop, :193-200). */
 static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
-                     uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth)
+                     uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int us, int left_chroma)
 {
-    int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1;
-    uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask, navl = avl ^ mask;
+    int un = 1 << us, nb_units = ((1 << (log2_len + 1)) >> us) + 1, ref_len = (1 << (log2_len + 1)) + 1;
+    uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> us)) & mask, navl = avl ^ mask;
     if (!navl) {
         for (int i = 0; i < ref_len; i++) ref[i] = p[i * step];
     } else if (avl) {
         int nb_avl = 64 - __builtin_clzll(avl), i;
         ref[0] = (avl & 1) ? p[0] : p[step];
         for (i = 1; i < nb_avl; i++)
-            for (int k = 0; k < 4; k++) ref[1 + 4 * (i - 1) + k] = p[(1 + 4 * (i - 1) + k) * step];
-        uint16_t pad = ref[4 * (nb_avl - 1)];
+            for (int k = 0; k < un; k++) ref[1 + un * (i - 1) + k] = p[(1 + un * (i - 1) + k) * step];
+        uint16_t pad = ref[un * (nb_avl - 1)];
+        if (left_chroma && nb_avl == 1) pad = (uint16_t)(1 << (bitdepth - 1));
         for (; i < nb_units; i++)
-            for (int k = 0; k < 4; k++) ref[1 + 4 * (i - 1) + k] = pad;
+            for (int k = 0; k < un; k++) ref[1 + un * (i - 1) + k] = pad;
     } else {
-        int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
-        uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+        int nb_units_o = ((1 << (log2_other + 1)) >> us) + 1;
+        uint64_t avl_o = (other_map >> (other_pos >> us)) & ((1ull << (nb_units_o + 1)) - 1);
         uint16_t pad = avl_o ? p[other_step] : (uint16_t)(1 << (bitdepth - 1));     /* first sample of the other line */
         for (int i = 0; i < ref_len; i++) ref[i] = pad;
     }
@@ -69,20 +73,21 @@ static void filter_ref(uint16_t *dst, const uint16_t *src, const uint16_t *src2,
 
 /* vertical-class angular prediction of a W x H block (W along the main reference): out[y * W + x].
  * M = main reference (M[0] corner, negative indices writable), S = side reference, tl = ref_above[0]. */
-static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv)
+static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv, int chroma)
 {
     int W = 1 << lw, H = 1 << lh, a = abs(mode_idx);
-    int gauss = (lw + lh) > 5 && a > intra_filter_thr[(lw + lh) >> 1];
+    int gauss = !chroma && (lw + lh) > 5 && a > intra_filter_thr[(lw + lh) >> 1];
     uint16_t fM[REF_LEN], fS[REF_LEN];
+    int cpd = lw > 1 && lh > 1;                                    /* chroma: PDPC only when both sides are >= 4 (rcn_intra.c:954-1008) */
     if (a == 0) {                                                  /* pure vertical: intra_angular_ver(_pdpc) */
-        int pd = gauss || lh > 1, scale = (lw + lh - 2) >> 2;
+        int pd = chroma ? cpd : (gauss || lh > 1), scale = (lw + lh - 2) >> 2;
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++)
                 out[y * W + x] = pd ? clipi((pdpc_w(scale, x) * (S[y + 1] - tl) + (M[x + 1] << 6) + 32) >> 6, 0, maxv) : M[x + 1];
         return;
     }
     if (mode_idx == 16) {                                          /* pure diagonal: intra_angular_vdia(_pdpc) */
-        int pd = gauss || lh > 1, scale = imin(2, lh - 2);
+        int pd = chroma ? cpd : (gauss || lh > 1), scale = imin(2, lh - 2);
         if (gauss) {
             filter_ref(fM + REF_OFF, M, S, 2 * W); filter_ref(fS + REF_OFF, S, M, 2 * H);
             M = fM + REF_OFF; S = fS + REF_OFF;
@@ -105,7 +110,7 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
         }
         for (int k = -1, sum = 256; k >= -H; k--) { sum += inv; M[k] = S[imin(sum >> 9, H)]; }     /* rcn_intra.c:118-121 */
         angle = -angle;
-    } else if (pdpc_scale < 0 || (!gauss && lh < 2)) {
+    } else if (pdpc_scale < 0 || (!gauss && lh < 2) || (chroma && !cpd)) {
         if (gauss && !frac) { filter_ref(fM + REF_OFF, M, S, 2 * W); M = fM + REF_OFF; }
     } else {
         if (gauss && !frac) {
@@ -121,7 +126,8 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
             if (!frac) v = M[x + di + 1];
             else {
                 const uint16_t *r = M + x + di;
-                if (gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
+                if (chroma) v = clipi(r[1] + ((df * (r[2] - r[1]) + 16) >> 5), 0, maxv);    /* intra_angular_v_c, rcn_intra_angular.c:270-294 */
+                else if (gauss) v = (r[0] * (16 - (df >> 1)) + r[1] * (32 - (df >> 1)) + r[2] * (16 + (df >> 1)) + r[3] * (df >> 1) + 32) >> 6;
                 else       v = clipi((r[0] * cubic[df][0] + r[1] * cubic[df][1] + r[2] * cubic[df][2] + r[3] * cubic[df][3] + 32) >> 6, 0, maxv);
             }
             if (use_pdpc && x < imin(3 << pdpc_scale, W)) {
@@ -133,28 +139,32 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
     }
 }
 
-static void intra_block(uint16_t *plane, int stride, int log2_ctu, int bitdepth, const OVOIntraCmd *c)
+/* one block of one plane; chroma: x0 / y0 / log2 sizes in chroma samples */
+static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int mode_in,
+                        uint64_t cols, uint64_t rows, int chroma)
 {
-    int lw = c->log2_w, lh = c->log2_h, w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, cm = (1 << log2_ctu) - 1;
+    int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, us = chroma ? 1 : 2;
     uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
-    uint16_t *dst = plane + (size_t)c->y0 * stride + c->x0;
+    uint16_t *dst = plane + (size_t)y0 * stride + x0;
     const uint16_t *corner = dst - stride - 1;
-    fill_ref(lft, corner, stride, 1, lh, lw, c->avail_cols, c->avail_rows, c->y0 & cm, c->x0 & cm, bitdepth);
-    fill_ref(abv, corner, 1, stride, lw, lh, c->avail_rows, c->avail_cols, c->x0 & cm, c->y0 & cm, bitdepth);
+    fill_ref(lft, corner, stride, 1, lh, lw, cols, rows, yl, xl, bitdepth, us, chroma);
+    fill_ref(abv, corner, 1, stride, lw, lh, rows, cols, xl, yl, bitdepth, us, 0);
     int *out = malloc(sizeof(int) * w * h);
-    if (c->mode == 0) {                                            /* intra_planar_pdpc, rcn_intra_dc_planar.c:196-236 */
+    int pd = chroma ? (lw > 1 && lh > 1) : 1;
+    if (mode_in == 0) {                                            /* intra_planar(_pdpc), rcn_intra_dc_planar.c:106-149, 196-236 */
         uint16_t fa[REF_LEN], fl[REF_LEN];
         const uint16_t *A = abv, *L = lft;
-        if (lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
+        if (!chroma && lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
         int ws = lw > 1 ? lw : 1, hs = lh > 1 ? lh : 1, scale = (lw + lh - 2) >> 2;
+        if (!pd) { ws = lw; hs = lh; }
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
                 int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
                 int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
                 int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
-                out[y * w + x] = clipi((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv);
+                out[y * w + x] = pd ? clipi((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv) : v;
             }
-    } else if (c->mode == 1) {                                     /* intra_dc_pdpc, :151-194 */
+    } else if (mode_in == 1) {                                     /* intra_dc(_pdpc), :64-104, 151-194 */
         int shift = (lw > lh ? lw : lh) + (lw == lh), dc = 0, scale = (lw + lh - 2) >> 2;
         if (lw >= lh) for (int i = 0; i < w; i++) dc += abv[1 + i];
         if (lw <= lh) for (int i = 0; i < h; i++) dc += lft[1 + i];
@@ -162,19 +172,19 @@ static void intra_block(uint16_t *plane, int stride, int log2_ctu, int bitdepth,
         for (int y = 0; y < h; y++)
             for (int x = 0; x < w; x++) {
                 int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
-                out[y * w + x] = clipi((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv);
+                out[y * w + x] = pd ? clipi((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv) : dc;
             }
     } else {
         /* derive_wide_angular_mode, rcn_intra.c:55-66 */
         static const uint8_t mode_shift_tab[6] = { 0, 6, 10, 12, 14, 15 };
-        int mode = c->mode, ms = mode_shift_tab[abs(lw - lh)];
+        int mode = mode_in, ms = mode_shift_tab[abs(lw - lh)];
         if (lw > lh && mode < 2 + ms) mode += 65;
         else if (lh > lw && mode > 66 - ms) mode -= 65;
         if (mode >= 34) {
-            angular_class(out, abv, lft, abv[0], lw, lh, mode - 50, maxv);
+            angular_class(out, abv, lft, abv[0], lw, lh, mode - 50, maxv, chroma);
         } else {
             int *t = malloc(sizeof(int) * w * h);
-            angular_class(t, lft, abv, abv[0], lh, lw, 18 - mode, maxv);
+            angular_class(t, lft, abv, abv[0], lh, lw, 18 - mode, maxv, chroma);
             for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * w + x] = t[x * h + y];
             free(t);
         }
@@ -186,6 +196,16 @@ static void intra_block(uint16_t *plane, int stride, int log2_ctu, int bitdepth,
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, int nb_cmds)
 {
+    int cm = (1 << log2_ctu_s) - 1;
     (void)pic_w; (void)pic_h;
-    for (int i = 0; i < nb_cmds; i++) intra_block(planes[0], stride[0], log2_ctu_s, bitdepth, &cmds[i]);
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVOIntraCmd *c = &cmds[i];
+        if (c->mode != OVO_INTRA_NO_LUMA)
+            intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, c->mode,
+                        c->avail_cols, c->avail_rows, 0);
+        if (c->flags & OVO_INTRA_CHROMA)           /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr, same availability */
+            for (int k = 1; k < 3; k++)
+                intra_block(planes[k], stride[k], bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1,
+                            c->log2_w - 1, c->log2_h - 1, c->flags & 0x7f, c->avail_cols, c->avail_rows, 1);
+    }
 }

@@ -71,13 +71,23 @@ ovref_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, i
             }
             c->rcn_ctx.ctu_buff.y = planes[0] + (size_t)(cy << log2_ctu_s) * stride[0] + (cx << log2_ctu_s);
             c->rcn_ctx.ctu_buff.stride = stride[0];
+            c->rcn_ctx.ctu_buff.cb = planes[1] + (size_t)(cy << (log2_ctu_s - 1)) * stride[1] + (cx << (log2_ctu_s - 1));
+            c->rcn_ctx.ctu_buff.cr = planes[2] + (size_t)(cy << (log2_ctu_s - 1)) * stride[2] + (cx << (log2_ctu_s - 1));
+            c->rcn_ctx.ctu_buff.stride_c = stride[1];
             while (n < nb_cmds && (cmds[n].x0 >> log2_ctu_s) == cx && (cmds[n].y0 >> log2_ctu_s) == cy) {
                 OVOIntraCmd *m = &cmds[n++];
                 int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
                 m->avail_cols = c->rcn_ctx.progress_field.vfield[x0 >> 2];
                 m->avail_rows = c->rcn_ctx.progress_field.hfield[y0 >> 2];
-                c->rcn_funcs.intra_pred(&c->rcn_ctx, &c->rcn_ctx.ctu_buff, m->mode, x0, y0, m->log2_w, m->log2_h, flg_pred_mode_flag);
+                if (m->mode != OVO_INTRA_NO_LUMA)
+                    c->rcn_funcs.intra_pred(&c->rcn_ctx, &c->rcn_ctx.ctu_buff, m->mode, x0, y0, m->log2_w, m->log2_h, flg_pred_mode_flag);
+                if (m->flags & OVO_INTRA_CHROMA) {
+                    /* single tree: the chroma field is updated with the same rectangles as the luma one (rcn_tu_st, :1275) */
+                    if (c->rcn_ctx.progress_field_c.vfield[x0 >> 2] != m->avail_cols || c->rcn_ctx.progress_field_c.hfield[y0 >> 2] != m->avail_rows) abort();
+                    c->rcn_funcs.intra_pred_c(&c->rcn_ctx, m->flags & 0x7f, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flg_pred_mode_flag);
+                }
                 ctu_field_set_rect_bitfield(&c->rcn_ctx.progress_field, x0 >> 2, y0 >> 2, (1 << m->log2_w) >> 2, (1 << m->log2_h) >> 2);
+                ctu_field_set_rect_bitfield(&c->rcn_ctx.progress_field_c, x0 >> 2, y0 >> 2, (1 << m->log2_w) >> 2, (1 << m->log2_h) >> 2);
             }
         }
     free(c);

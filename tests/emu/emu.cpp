@@ -184,7 +184,7 @@ int emu_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth
     return 0;
 }
 
-int emu_intra_picture(uint16_t *plane, int stride, int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
+int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
 {
     for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
     std::vector<uint32_t> order(n + 1), level_start(n + 3);
@@ -192,8 +192,9 @@ int emu_intra_picture(uint16_t *plane, int stride, int w, int h, int log2_ctu, i
     if (nl < 0) return -1000000;
     for (int l = 0; l < nl; l++) {
         int start = (int)level_start[l], cnt = (int)level_start[l + 1] - start;
-        IntraK::Args a = { plane, stride, log2_ctu, bitdepth, (const IntraCmdDev *)cmds, order.data() + start, cnt };
-        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, 1, 1), IntraK::SMEM_BYTES);
+        IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
+                           (const IntraCmdDev *)cmds, order.data() + start, cnt };
+        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, 3, 1), IntraK::SMEM_BYTES);
     }
     return nl;
 }

@@ -1,5 +1,5 @@
 """Generates tests/golden/intra_golden.json from the UNMODIFIED reference (oracle/_ref, scalar C): MD5 of the luma plane
-after rcn_funcs.intra_pred ran over seeded intra blocks in decode order, and of the availability words the reference's
+after rcn_funcs.intra_pred (and intra_pred_c for the chroma cases) ran over seeded intra blocks in decode order, and of the availability words the reference's
 progress bit-field held at each call.  Run in the build container:  python tests/golden/gen_golden_intra.py"""
 import json
 import os
@@ -13,19 +13,22 @@ from oracle import pyoracle as po, pyoracle_intra as pi  # noqa: E402
 import helpers  # noqa: E402
 import helpers_intra  # noqa: E402
 
-CASES = [(128, 128, 901, 7), (416, 240, 902, 7), (832, 480, 903, 7), (264, 136, 904, 6), (200, 120, 905, 5), (1920, 1080, 906, 7)]
+CASES = [(128, 128, 901, 7, 0), (416, 240, 902, 7, 0), (832, 480, 903, 7, 0), (264, 136, 904, 6, 0), (200, 120, 905, 5, 0), (1920, 1080, 906, 7, 0),
+         # luma + Cb / Cr (rcn_funcs.intra_pred_c): md5 over the three planes
+         (128, 128, 911, 7, 1), (416, 240, 912, 7, 1), (264, 136, 914, 6, 1), (200, 120, 915, 5, 1), (1920, 1080, 916, 7, 1)]
 
 
 def main():
     assert po.ref_available()
     out = []
-    for (w, h, seed, log2) in CASES:
-        planes, cmds = helpers_intra.intra_case(w, h, seed, log2)
+    for (w, h, seed, log2, chroma) in CASES:
+        planes, cmds = helpers_intra.intra_case(w, h, seed, log2, chroma=bool(chroma))
         inp = helpers.md5(cmds, planes[0])
         rc = cmds.copy()
         rc["avail_cols"] = 0; rc["avail_rows"] = 0
         pi.intra_picture(planes, rc, log2, impl="ref", simd=0)
-        out.append(dict(w=w, h=h, seed=seed, log2_ctu=log2, nb_cmds=len(cmds), input_md5=inp, md5=helpers.md5(planes[0]),
+        out.append(dict(w=w, h=h, seed=seed, log2_ctu=log2, chroma=chroma, nb_cmds=len(cmds), input_md5=inp,
+                        md5=helpers.md5(*planes) if chroma else helpers.md5(planes[0]),
                         avail_md5=helpers.md5(rc["avail_cols"], rc["avail_rows"])))
         print(out[-1])
     json.dump(out, open(os.path.join(HERE, "intra_golden.json"), "w"), indent=1)

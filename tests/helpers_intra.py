@@ -6,17 +6,18 @@ import numpy as np
 from openvvc_b200 import synth, synth_intra
 
 
-def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural"):
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False):
     """planes + intra commands in decode order with the availability words replayed from that order"""
-    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2), log2_ctu)
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma), log2_ctu)
     return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
 
 
 def emu_intra(emu, planes, cmds, log2_ctu=7, bitdepth=10):
     out = [p.copy() for p in planes]
     h, w = out[0].shape
-    nl = emu.emu_intra_picture(out[0].ctypes.data_as(C.c_void_p), out[0].strides[0] // 2, w, h, log2_ctu, bitdepth,
-                               cmds.ctypes.data_as(C.c_void_p), len(cmds))
+    ptrs = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
+    strides = (C.c_int * 3)(*[p.strides[0] // 2 for p in out])
+    nl = emu.emu_intra_picture(ptrs, strides, w, h, log2_ctu, bitdepth, cmds.ctypes.data_as(C.c_void_p), len(cmds))
     assert nl >= 0, "emu rejected command %d" % (-nl - 1)
     return out, nl
 

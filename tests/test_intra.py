@@ -1,4 +1,4 @@
-"""Luma intra prediction (reference fill, [1 2 1] filter, planar / DC / angular with PDPC, wide angles): oracle port vs
+"""Luma and chroma intra prediction (reference fill, [1 2 1] filter, planar / DC / angular with PDPC, wide angles): oracle port vs
 golden / compiled reference (CPU), availability replay vs the reference's progress bit-field, kernel-source emulation vs
 oracle incl. the dependency-level schedule (CPU), sm_100a kernel through the C ABI vs oracle / golden (GPU)."""
 import json
@@ -11,7 +11,7 @@ import helpers
 import helpers_intra
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "intra_golden.json")))
-IDS = lambda c: "%dx%d_ctu%d" % (c["w"], c["h"], 1 << c["log2_ctu"])
+IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], "_yuv" if c["chroma"] else "")
 
 
 @pytest.fixture(scope="module")
@@ -21,7 +21,7 @@ def pi(oracle):
 
 
 def _case(c):
-    planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"])
+    planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"], chroma=bool(c["chroma"]))
     assert helpers.md5(cmds, planes[0]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
     return planes, cmds
 
@@ -32,35 +32,41 @@ def test_port_matches_golden(pi, c):
     # our replay of the availability words == what the reference's bit-field held (golden from the reference run)
     assert helpers.md5(cmds["avail_cols"], cmds["avail_rows"]) == c["avail_md5"]
     pi.intra_picture(planes, cmds, c["log2_ctu"], impl="port")
-    assert helpers.md5(planes[0]) == c["md5"]
+    assert (helpers.md5(*planes) if c["chroma"] else helpers.md5(planes[0])) == c["md5"]
 
 
+@pytest.mark.parametrize("chroma", [False, True], ids=["y", "yuv"])
 @pytest.mark.parametrize("w,h,log2", [(128, 128, 7), (416, 240, 7), (832, 480, 7), (264, 136, 6), (72, 40, 5), (200, 120, 5)])
-def test_port_vs_compiled_reference(oracle, pi, w, h, log2):
+def test_port_vs_compiled_reference(oracle, pi, w, h, log2, chroma):
     """every mode class over random partitions incl. partial CTUs; scalar C and the SSE/AVX2 table"""
     if not oracle.ref_available():
         pytest.skip("oracle/_ref not built (no /root/reference here)")
-    planes, cmds = helpers_intra.intra_case(w, h, 5 * w + h, log2)
+    planes, cmds = helpers_intra.intra_case(w, h, 5 * w + h, log2, chroma=chroma)
     want = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
     for simd in (0, 1):
         rc = cmds.copy()
         rc["avail_cols"] = 0; rc["avail_rows"] = 0
         got = pi.intra_picture([p.copy() for p in planes], rc, log2, impl="ref", simd=simd)
         assert (rc["avail_cols"] == cmds["avail_cols"]).all() and (rc["avail_rows"] == cmds["avail_rows"]).all()
-        assert (got[0] == want[0]).all(), "intra port vs reference (simd=%d): %d samples differ" % (simd, (got[0] != want[0]).sum())
-    assert (want[0] != planes[0]).mean() > 0.9
+        for k in range(3):
+            assert (got[k] == want[k]).all(), "intra port vs reference (simd=%d, plane %d): %d samples differ" % (simd, k, (got[k] != want[k]).sum())
+    for k in range(3 if chroma else 1):
+        assert (want[k] != planes[k]).mean() > 0.9
+    if not chroma:
+        assert (want[1] == planes[1]).all() and (want[2] == planes[2]).all()
 
 
 def test_every_mode_and_shape_is_covered():
     _, cmds = helpers_intra.intra_case(832, 480, 4645, 7)
     assert set(cmds["mode"]) >= set(range(0, 67))
     shapes = set(zip(cmds["log2_w"], cmds["log2_h"]))
-    assert len(shapes) >= 20 and any(a - b >= 2 for a, b in shapes) and any(b - a >= 2 for a, b in shapes)      # wide angles both ways
+    assert len(shapes) >= 20 and any(int(a) - int(b) >= 2 for a, b in shapes) and any(int(b) - int(a) >= 2 for a, b in shapes)      # wide angles both ways
 
 
+@pytest.mark.parametrize("chroma", [False, True], ids=["y", "yuv"])
 @pytest.mark.parametrize("w,h,log2", [(128, 128, 7), (416, 240, 7), (264, 136, 6), (200, 120, 5), (832, 480, 7)])
-def test_emulated_kernel_matches_oracle(pi, emu, w, h, log2):
-    planes, cmds = helpers_intra.intra_case(w, h, 7 * w + h, log2)
+def test_emulated_kernel_matches_oracle(pi, emu, w, h, log2, chroma):
+    planes, cmds = helpers_intra.intra_case(w, h, 7 * w + h, log2, chroma=chroma)
     want = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
     for rev in (0, 1):          # CTAs of a level may run in any order
         emu.emu_set_reverse_block_order(rev)
@@ -68,7 +74,24 @@ def test_emulated_kernel_matches_oracle(pi, emu, w, h, log2):
             got, nl = helpers_intra.emu_intra(emu, planes, cmds, log2)
         finally:
             emu.emu_set_reverse_block_order(0)
-        assert (got[0] == want[0]).all() and 1 < nl <= len(cmds)
+        assert all((got[k] == want[k]).all() for k in range(3)) and 1 < nl <= len(cmds)
+
+
+def test_chroma_only_and_luma_only_commands(pi, emu):
+    """dual-tree style commands: luma-only, chroma-only and both in one list"""
+    planes, cmds = helpers_intra.intra_case(416, 240, 77, 7, chroma=True)
+    cmds = cmds.copy()
+    cmds["flags"][::3] = 0
+    cmds["mode"][1::3] = 255
+    want = pi.intra_picture([p.copy() for p in planes], cmds, 7, impl="port")
+    got, _ = helpers_intra.emu_intra(emu, planes, cmds, 7)
+    assert all((got[k] == want[k]).all() for k in range(3))
+    bad = cmds.copy(); bad["flags"][0] = 0; bad["mode"][0] = 255                  # neither
+    with pytest.raises(AssertionError):
+        helpers_intra.emu_intra(emu, planes, bad, 7)
+    bad = cmds.copy(); bad["flags"][0] = 0x80 | 67                                 # CCLM is not a mode of this revision
+    with pytest.raises(AssertionError):
+        helpers_intra.emu_intra(emu, planes, bad, 7)
 
 
 def test_emu_rejects_blocks_outside_the_picture(emu):
@@ -85,15 +108,19 @@ def test_emu_rejects_blocks_outside_the_picture(emu):
 def test_gpu_matches_golden(gpu_ctx, c):
     planes, cmds = _case(c)
     out, nl = helpers_intra.gpu_intra(gpu_ctx, planes, cmds, c["log2_ctu"])
-    assert helpers.md5(out[0]) == c["md5"]
-    assert (out[1] == planes[1]).all() and (out[2] == planes[2]).all()
+    if c["chroma"]:
+        assert helpers.md5(*out) == c["md5"]
+    else:
+        assert helpers.md5(out[0]) == c["md5"]
+        assert (out[1] == planes[1]).all() and (out[2] == planes[2]).all()
 
 
 @pytest.mark.gpu
 def test_gpu_full_size_4k_vs_reference(oracle, pi, gpu_ctx):
     """an all-intra 3840x2160 picture (the I picture of a RA GOP): CUDA level schedule vs the compiled reference"""
     w, h = 3840, 2160
-    planes, cmds = helpers_intra.intra_case(w, h, 85, 7, min_log2=3)
+    planes, cmds = helpers_intra.intra_case(w, h, 85, 7, min_log2=3, chroma=True)
     want = pi.intra_picture([p.copy() for p in planes], cmds.copy(), 7, impl="ref" if oracle.ref_available() else "port")
     out, nl = helpers_intra.gpu_intra(gpu_ctx, planes, cmds, 7)
-    assert (out[0] == want[0]).all()
+    for k in range(3):
+        assert (out[k] == want[k]).all()
