@@ -318,13 +318,20 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
  * In a single tree progress_field_c holds the same words (rcn_tu_st marks both with the same rectangles), so the chroma
  * blocks use them too.  They are decode-order information, so the recorder copies them; the samples come from the
  * picture on the GPU. */
-#define OVGPU_INTRA_NO_LUMA 255   /* mode value: no luma block in this command */
-#define OVGPU_INTRA_CHROMA  0x80  /* flags bit: predict Cb and Cr with mode flags & 0x7f (0 planar, 1 DC, 2..66 angular; DM resolved) */
+#define OVGPU_INTRA_LUMA   1    /* flags: the command predicts a luma block with `mode` */
+#define OVGPU_INTRA_CHROMA 2    /* flags: Cb and Cr blocks of half the size are predicted with `mode_c` (single tree: same availability) */
+#define OVGPU_INTRA_CIIP   4    /* flags: combined inter / intra: planar prediction blended over the inter prediction already in the
+                                * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
+                                * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
 typedef struct OVGPUIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */
-    uint8_t mode;                 /* ctudec->intra_mode: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
-    uint8_t flags;                /* OVGPU_INTRA_CHROMA | chroma mode, or 0 */
+    uint8_t mode;                 /* luma: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
+    uint8_t mode_c;               /* chroma: same range (DM already resolved) */
+    uint8_t flags;
+    uint8_t mrl_idx;              /* reserved (multi reference line index) */
+    uint8_t ciip_wt;              /* CIIP: 1 + above CU is intra + left CU is intra (1..3) */
+    uint8_t pad[5];
     uint64_t avail_cols, avail_rows;
 } OVGPUIntraCmd;
 

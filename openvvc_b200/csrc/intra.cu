@@ -5,7 +5,7 @@
 #include "intra_host.h"
 #include <stdlib.h>
 
-static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 24, "intra command layout");
+static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 32, "intra command layout");
 
 struct OVGPUIntraBatch {
     int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu, has_chroma;

@@ -9,8 +9,9 @@
 static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 {
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (c->mode > 66 && c->mode != OVGPU_INTRA_NO_LUMA) return -1;
-    if ((c->flags & OVGPU_INTRA_CHROMA) ? (c->flags & 0x7f) > 66 : (c->flags != 0 || c->mode == OVGPU_INTRA_NO_LUMA)) return -1;
+    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~7)) return -1;
+    if (((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) || ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 66)) return -1;
+    if ((c->flags & OVGPU_INTRA_CIIP) && (c->ciip_wt < 1 || c->ciip_wt > 3)) return -1;
     if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;
     return 0;
 }

@@ -4,6 +4,9 @@
 // units (rcn_fill_ref.c:147-230, 392-480), no reference filtering, 2-tap linear interpolation (rcn_intra_angular.c:
 // 270-470), PDPC only when both sides are >= 4 samples.  Grid y = component (0 luma, 1 Cb, 2 Cr).
 //
+// CIIP (rcn_ciip(_b), libovvc/rcn_inter.c:2968-3067): the MC stage has written the inter prediction into the picture;
+// a command with the CIIP flag computes the planar prediction and blends it over those samples in place.
+//
 // Luma: vvc_intra_pred (libovvc/rcn_intra.c:484-560): reference sample fill with availability-driven
 // substitution (libovvc/rcn_fill_ref.c:71-145, 320-390), [1 2 1] reference filter (:47-68), planar / DC with PDPC
 // (libovvc/rcn_intra_dc_planar.c:151-236), wide-angle remapping and the angular dispatch (rcn_intra.c:55-481), angular
@@ -20,7 +23,7 @@
 
 struct IntraCmdDev {          // == OVGPUIntraCmd
     int16_t x0, y0;
-    uint8_t log2_w, log2_h, mode, flags;
+    uint8_t log2_w, log2_h, mode, mode_c, flags, mrl_idx, ciip_wt, pad[5];
     uint64_t avail_cols, avail_rows;
 };
 
@@ -56,7 +59,7 @@ struct IntraK {
 
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
-        int valid, chroma, pd;                       // pd: planar / DC use their PDPC variant
+        int valid, chroma, pd, ciip;                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
         int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
         int mlw, mlh;                                // block size as seen by the class (swapped for the horizontal class)
@@ -74,12 +77,13 @@ struct IntraK {
         if (!b.valid) return b;
         const IntraCmdDev &c = a.cmds[a.order[idx]];
         b.chroma = comp > 0;
-        b.valid = b.chroma ? (c.flags & 0x80) != 0 : c.mode != 255;
+        b.ciip = (c.flags & 4) ? c.ciip_wt : 0;
+        b.valid = b.chroma ? ((c.flags & 2) && !(b.ciip && c.log2_w <= 2)) : (c.flags & 1);
         if (!b.valid) return b;
         const int sh = b.chroma;
         b.x0 = c.x0 >> sh; b.y0 = c.y0 >> sh; b.lw = c.log2_w - sh; b.lh = c.log2_h - sh; b.cols = c.avail_cols; b.rows = c.avail_rows;
         b.pd = !b.chroma || (b.lw > 1 && b.lh > 1);
-        int mode = b.chroma ? (c.flags & 0x7f) : c.mode;
+        int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
         b.mode = mode;                                 // 0 planar, 1 DC, else angular (the remapped value lives in mode_idx)
         b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
         b.mode_idx = b.a = b.angle = b.inv = b.frac = b.gauss = b.pdpc_scale = b.use_pdpc = b.filt_m = b.filt_s = b.ext = 0;
@@ -220,7 +224,10 @@ struct IntraK {
                     const int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
                     const int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
                     const int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
-                    dst[(size_t)y * pitch + x] = (uint16_t)(b.pd ? ovd_clamp((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv) : v);
+                    int r = b.pd ? ovd_clamp((xw * L[y + 1] + yw * A[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv) : v;
+                    uint16_t *d = &dst[(size_t)y * pitch + x];
+                    if (b.ciip) r = ovd_clamp((r * b.ciip + *d * (4 - b.ciip) + 2) >> 2, 0, maxv);     // put_weighted_ciip_pixels
+                    *d = (uint16_t)r;
                 }
             } else if (b.mode == 1) {                                       // intra_dc_pdpc
                 const int shift = ovd_max(b.lw, b.lh) + (b.lw == b.lh), scale = (b.lw + b.lh - 2) >> 2;

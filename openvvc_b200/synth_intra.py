@@ -6,14 +6,14 @@ import numpy as np
 from . import synth
 
 INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), ("log2_h", np.uint8), ("mode", np.uint8),
-                      ("flags", np.uint8), ("avail_cols", np.uint64), ("avail_rows", np.uint64)])
-assert INTRA_CMD.itemsize == 24
+                      ("mode_c", np.uint8), ("flags", np.uint8), ("mrl_idx", np.uint8), ("ciip_wt", np.uint8), ("pad", np.uint8, 5),
+                      ("avail_cols", np.uint64), ("avail_rows", np.uint64)])
+assert INTRA_CMD.itemsize == 32
+
+INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP = 1, 2, 4
 
 
-INTRA_NO_LUMA, INTRA_CHROMA = 255, 0x80
-
-
-def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False):
+def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0):
     rng = np.random.default_rng(seed)
     part = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
@@ -21,12 +21,17 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
         c = cmds[i]
         c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
         r = rng.random()
+        c["flags"] = INTRA_LUMA
         c["mode"] = 0 if r < 0.15 else (1 if r < 0.3 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.4 else int(rng.integers(2, 67))))
         if chroma:
             # single tree: Cb / Cr blocks of half the size, mode = DM (the luma mode) or an explicit planar / DC / ver / hor / random
             r = rng.random()
             mc = int(c["mode"]) if r < 0.4 else (0 if r < 0.5 else (1 if r < 0.6 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.7 else int(rng.integers(2, 67)))))
-            c["flags"] = INTRA_CHROMA | mc
+            c["flags"] |= INTRA_CHROMA
+            c["mode_c"] = mc
+        if p_ciip and lw + lh >= 6 and rng.random() < p_ciip:       # CIIP: CUs of >= 64 samples (4x16 has the narrow-chroma rule)
+            c["flags"] |= INTRA_CIIP
+            c["ciip_wt"] = int(rng.integers(1, 4))
     return cmds
 
 

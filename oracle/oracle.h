@@ -217,14 +217,20 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
 /* One rcn_funcs.intra_pred call (vvc_intra_pred, rcn_intra.c:484-560): luma block, no ISP / MRL / MIP / BDPCM.
  * avail_cols / avail_rows are progress_field.vfield[x0 >> 2] / .hfield[y0 >> 2] at call time (CTU-local, bit 0 = the
  * unit of the neighbouring CTU line, bit 1 + u = 4x4 unit u): syntax-order information recorded on the CPU. */
-#define OVO_INTRA_NO_LUMA 255    /* mode value: the command carries no luma block */
-#define OVO_INTRA_CHROMA  0x80   /* flags bit: Cb + Cr blocks of half the size are predicted (rcn_funcs.intra_pred_c) with mode  *
-                                  * flags & 0x7f (0 planar, 1 DC, 2..66 angular; DM already resolved; CCLM not supported)       */
+#define OVO_INTRA_LUMA   1    /* flags: the command predicts a luma block with `mode` */
+#define OVO_INTRA_CHROMA 2    /* flags: Cb and Cr blocks of half the size are predicted with `mode_c` (single tree: same availability) */
+#define OVO_INTRA_CIIP   4    /* flags: combined inter / intra: planar prediction blended over the inter prediction already in the
+                                * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
+                                * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
 typedef struct OVOIntraCmd {
-    int16_t x0, y0;              /* picture-absolute luma samples */
-    uint8_t log2_w, log2_h;      /* luma size */
-    uint8_t mode;                /* 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
+    int16_t x0, y0;               /* picture-absolute luma samples */
+    uint8_t log2_w, log2_h;       /* luma size */
+    uint8_t mode;                 /* luma: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
+    uint8_t mode_c;               /* chroma: same range (DM already resolved) */
     uint8_t flags;
+    uint8_t mrl_idx;              /* reserved (multi reference line index) */
+    uint8_t ciip_wt;              /* CIIP: 1 + above CU is intra + left CU is intra (1..3) */
+    uint8_t pad[5];
     uint64_t avail_cols, avail_rows;
 } OVOIntraCmd;
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,

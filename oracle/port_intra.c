@@ -141,7 +141,7 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
 
 /* one block of one plane; chroma: x0 / y0 / log2 sizes in chroma samples */
 static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int mode_in,
-                        uint64_t cols, uint64_t rows, int chroma)
+                        uint64_t cols, uint64_t rows, int chroma, int ciip_wt)
 {
     int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, us = chroma ? 1 : 2;
     uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
@@ -189,7 +189,12 @@ static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y
             free(t);
         }
     }
-    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[(size_t)y * stride + x] = (uint16_t)out[y * w + x];
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int v = out[y * w + x];
+            if (ciip_wt) v = clipi((v * ciip_wt + dst[(size_t)y * stride + x] * (4 - ciip_wt) + 2) >> 2, 0, maxv);   /* rcn_mc.c:1611-1627 */
+            dst[(size_t)y * stride + x] = (uint16_t)v;
+        }
     free(out);
 }
 
@@ -200,12 +205,13 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
     (void)pic_w; (void)pic_h;
     for (int i = 0; i < nb_cmds; i++) {
         const OVOIntraCmd *c = &cmds[i];
-        if (c->mode != OVO_INTRA_NO_LUMA)
-            intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, c->mode,
-                        c->avail_cols, c->avail_rows, 0);
-        if (c->flags & OVO_INTRA_CHROMA)           /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr, same availability */
+        int ciip = (c->flags & OVO_INTRA_CIIP) ? c->ciip_wt : 0;
+        if (c->flags & OVO_INTRA_LUMA)
+            intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, ciip ? 0 : c->mode,
+                        c->avail_cols, c->avail_rows, 0, ciip);
+        if ((c->flags & OVO_INTRA_CHROMA) && !(ciip && c->log2_w <= 2))    /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr */
             for (int k = 1; k < 3; k++)
                 intra_block(planes[k], stride[k], bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1,
-                            c->log2_w - 1, c->log2_h - 1, c->flags & 0x7f, c->avail_cols, c->avail_rows, 1);
+                            c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip);
     }
 }

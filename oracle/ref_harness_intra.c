@@ -20,6 +20,7 @@
 #include "drv_utils.h"
 #include "cu_utils.h"
 #include "rcn_intra_angular.h"
+#include "drv.h"
 
 #include "oracle.h"
 
@@ -28,10 +29,54 @@ void rcn_init_dc_planar_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_intra_angular_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_fill_ref_10(struct RCNFunctions *rcn_func);
 
+/* rcn_ciip / rcn_ciip_b (rcn_inter.c:3012-3067) from the point where the inter prediction exists: the block's current
+ * content plays tmp_inter (the MC stage wrote it), the reference's own slots do the rest -- intra_pred / intra_pred_c
+ * with OVINTRA_PLANAR into the CTU buffer, ciip.weighted for the blend, mc_c.unidir[0][0] for the narrow-chroma copy
+ * (rcn_ciip_weighted_sum, :2968-3010; the weight comes with the command, the shim derives it from part_map.cu_mode_x/y). */
+static void
+ciip_block(OVCTUDec *c, const OVOIntraCmd *m, int x0, int y0, uint16_t *const inter_pic[3], const int stride[3])
+{
+    /* The AVX2 blend works on 16-sample groups whatever the width (x86/rcn_mc_avx2.c:5024-5095): inside the reference that
+     * spills into CTU-buffer samples that are rewritten later; here the CTU buffer aliases the picture, so the blend runs
+     * on padded scratch copies and only the w x h block is stored back.  For the same reason (SIMD intra kernels of narrow
+     * blocks also spill to the right) the inter prediction is taken from a copy of the input picture made up front. */
+    enum { ST = 96 };
+    static uint16_t inter[3][64 * ST + 32], intra[64 * ST + 32], out[64 * ST + 32];
+    struct OVBuffInfo *b = &c->rcn_ctx.ctu_buff;
+    uint16_t *dst[3] = { b->y + x0 + (ptrdiff_t)y0 * b->stride, b->cb + (x0 >> 1) + (ptrdiff_t)(y0 >> 1) * b->stride_c,
+                         b->cr + (x0 >> 1) + (ptrdiff_t)(y0 >> 1) * b->stride_c };
+    int w = 1 << m->log2_w, h = 1 << m->log2_h;
+    for (int k = 0; k < 3; k++) {
+        int bw = k ? w >> 1 : w, bh = k ? h >> 1 : h, st = k ? b->stride_c : b->stride;
+        const uint16_t *src = inter_pic[k] + (size_t)(m->y0 >> (k != 0)) * stride[k] + (m->x0 >> (k != 0));
+        (void)st;
+        for (int y = 0; y < bh; y++) memcpy(&inter[k][y * ST], src + (size_t)y * stride[k], bw * 2);
+    }
+    c->rcn_funcs.intra_pred(&c->rcn_ctx, b, OVINTRA_PLANAR, x0, y0, m->log2_w, m->log2_h, 0);
+    c->rcn_funcs.intra_pred_c(&c->rcn_ctx, OVINTRA_PLANAR, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, 0);
+    for (int k = 0; k < 3; k++) {
+        int bw = k ? w >> 1 : w, bh = k ? h >> 1 : h, st = k ? b->stride_c : b->stride;
+        for (int y = 0; y < bh; y++) memcpy(&intra[y * ST], dst[k] + (ptrdiff_t)y * st, bw * 2);
+        if (k && m->log2_w <= 2) c->rcn_funcs.mc_c.unidir[0][0](out, ST, inter[k], ST, bh, 0, 0, bw);
+        else c->rcn_funcs.ciip.weighted(out, ST, intra, inter[k], ST, ST, bw, bh, m->ciip_wt);
+        for (int y = 0; y < bh; y++) memcpy(dst[k] + (ptrdiff_t)y * st, &out[y * ST], bw * 2);
+    }
+}
+
 void
-ovref_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
+ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
                     OVOIntraCmd *cmds, int nb_cmds)
 {
+    /* SIMD kernels of 2- and 4-sample-wide blocks store whole vectors; the reference's CTU buffer has padding for that
+     * (RCN_CTB_PADDING), so the harness works on copies of the planes with 64 samples of row padding */
+    uint16_t *planes[3];
+    int stride[3];
+    for (int k = 0; k < 3; k++) {
+        int ph = pic_h >> (k != 0), pw = pic_w >> (k != 0);
+        stride[k] = pw + 64;
+        planes[k] = calloc((size_t)stride[k] * (ph + 1), sizeof(uint16_t));
+        for (int y = 0; y < ph; y++) memcpy(planes[k] + (size_t)y * stride[k], user_planes[k] + (size_t)y * user_stride[k], pw * 2);
+    }
     OVCTUDec *c;
     OVPartInfo part;
     int ctu_s = 1 << log2_ctu_s;
@@ -54,6 +99,14 @@ ovref_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, i
         c->rcn_funcs.intra_angular_c_h = &angular_c_h_10; c->rcn_funcs.intra_angular_c_v = &angular_c_v_10;
         c->rcn_funcs.intra_angular_nofrac_v = &angular_nofrac_v_10; c->rcn_funcs.intra_angular_nofrac_h = &angular_nofrac_h_10;
     }
+    uint16_t *inter_pic[3] = { NULL, NULL, NULL };
+    for (int i = 0; i < nb_cmds; i++)
+        if ((cmds[i].flags & OVO_INTRA_CIIP) && !inter_pic[0])
+            for (int k = 0; k < 3; k++) {
+                size_t sz = (size_t)stride[k] * (pic_h >> (k != 0)) * sizeof(uint16_t);
+                inter_pic[k] = malloc(sz);
+                memcpy(inter_pic[k], planes[k], sz);
+            }
     int n = 0;
     for (int cy = 0; cy < nch; cy++)
         for (int cx = 0; cx < ncw; cx++) {
@@ -79,16 +132,26 @@ ovref_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, i
                 int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
                 m->avail_cols = c->rcn_ctx.progress_field.vfield[x0 >> 2];
                 m->avail_rows = c->rcn_ctx.progress_field.hfield[y0 >> 2];
-                if (m->mode != OVO_INTRA_NO_LUMA)
+                if (m->flags & OVO_INTRA_CIIP) {
+                    ciip_block(c, m, x0, y0, inter_pic, stride);
+                } else {
+                if (m->flags & OVO_INTRA_LUMA)
                     c->rcn_funcs.intra_pred(&c->rcn_ctx, &c->rcn_ctx.ctu_buff, m->mode, x0, y0, m->log2_w, m->log2_h, flg_pred_mode_flag);
                 if (m->flags & OVO_INTRA_CHROMA) {
                     /* single tree: the chroma field is updated with the same rectangles as the luma one (rcn_tu_st, :1275) */
                     if (c->rcn_ctx.progress_field_c.vfield[x0 >> 2] != m->avail_cols || c->rcn_ctx.progress_field_c.hfield[y0 >> 2] != m->avail_rows) abort();
-                    c->rcn_funcs.intra_pred_c(&c->rcn_ctx, m->flags & 0x7f, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flg_pred_mode_flag);
+                    c->rcn_funcs.intra_pred_c(&c->rcn_ctx, m->mode_c, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flg_pred_mode_flag);
+                }
                 }
                 ctu_field_set_rect_bitfield(&c->rcn_ctx.progress_field, x0 >> 2, y0 >> 2, (1 << m->log2_w) >> 2, (1 << m->log2_h) >> 2);
                 ctu_field_set_rect_bitfield(&c->rcn_ctx.progress_field_c, x0 >> 2, y0 >> 2, (1 << m->log2_w) >> 2, (1 << m->log2_h) >> 2);
             }
         }
+    for (int k = 0; k < 3; k++) {
+        int ph = pic_h >> (k != 0), pw = pic_w >> (k != 0);
+        for (int y = 0; y < ph; y++) memcpy(user_planes[k] + (size_t)y * user_stride[k], planes[k] + (size_t)y * stride[k], pw * 2);
+        free(planes[k]);
+        free(inter_pic[k]);
+    }
     free(c);
 }

@@ -11,7 +11,7 @@ import helpers
 import helpers_intra
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "intra_golden.json")))
-IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], "_yuv" if c["chroma"] else "")
+IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], ("", "_yuv", "_yuv_ciip")[c["chroma"]])
 
 
 @pytest.fixture(scope="module")
@@ -21,7 +21,8 @@ def pi(oracle):
 
 
 def _case(c):
-    planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"], chroma=bool(c["chroma"]))
+    planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"], chroma=bool(c["chroma"]),
+                                            p_ciip=0.4 if c["chroma"] == 2 else 0.0)
     assert helpers.md5(cmds, planes[0]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
     return planes, cmds
 
@@ -81,17 +82,32 @@ def test_chroma_only_and_luma_only_commands(pi, emu):
     """dual-tree style commands: luma-only, chroma-only and both in one list"""
     planes, cmds = helpers_intra.intra_case(416, 240, 77, 7, chroma=True)
     cmds = cmds.copy()
-    cmds["flags"][::3] = 0
-    cmds["mode"][1::3] = 255
+    cmds["flags"][::3] = 1          # luma only
+    cmds["flags"][1::3] = 2         # chroma only
     want = pi.intra_picture([p.copy() for p in planes], cmds, 7, impl="port")
     got, _ = helpers_intra.emu_intra(emu, planes, cmds, 7)
     assert all((got[k] == want[k]).all() for k in range(3))
-    bad = cmds.copy(); bad["flags"][0] = 0; bad["mode"][0] = 255                  # neither
+    bad = cmds.copy(); bad["flags"][0] = 0                                         # neither
     with pytest.raises(AssertionError):
         helpers_intra.emu_intra(emu, planes, bad, 7)
-    bad = cmds.copy(); bad["flags"][0] = 0x80 | 67                                 # CCLM is not a mode of this revision
+    bad = cmds.copy(); bad["flags"][0] = 2; bad["mode_c"][0] = 70                  # beyond the MDLM modes
     with pytest.raises(AssertionError):
         helpers_intra.emu_intra(emu, planes, bad, 7)
+
+
+@pytest.mark.parametrize("w,h,log2", [(416, 240, 7), (264, 136, 6)])
+def test_ciip_port_vs_reference_and_emu(oracle, pi, emu, w, h, log2):
+    """CIIP (a14): planar intra blended over the inter prediction in place, weights 1..3, narrow-chroma rule (4xN CUs)"""
+    planes, cmds = helpers_intra.intra_case(w, h, 31 * w + h, log2, chroma=True, p_ciip=0.5)
+    ciip = (cmds["flags"] & 4) != 0
+    assert ciip.sum() > 10 and (ciip & (cmds["log2_w"] == 2)).any() and set(cmds["ciip_wt"][ciip]) == {1, 2, 3}
+    want = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
+    if oracle.ref_available():
+        for simd in (0, 1):
+            got = pi.intra_picture([p.copy() for p in planes], cmds.copy(), log2, impl="ref", simd=simd)
+            assert all((got[k] == want[k]).all() for k in range(3)), "CIIP port vs reference (simd=%d)" % simd
+    got, _ = helpers_intra.emu_intra(emu, planes, cmds, log2)
+    assert all((got[k] == want[k]).all() for k in range(3))
 
 
 def test_emu_rejects_blocks_outside_the_picture(emu):
