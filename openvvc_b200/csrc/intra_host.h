@@ -12,6 +12,7 @@ static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
     if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~7)) return -1;
     if (((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) || ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 66)) return -1;
     if ((c->flags & OVGPU_INTRA_CIIP) && (c->ciip_wt < 1 || c->ciip_wt > 3)) return -1;
+    if (c->mrl_idx > 2 || (c->mrl_idx && (c->y0 < 4 || c->x0 + (1 << c->log2_w) > pic_w))) return -1;
     if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;
     return 0;
 }

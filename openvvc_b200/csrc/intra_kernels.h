@@ -44,7 +44,8 @@ OVD_CONST int8_t intra_cubic[32][4] = {
 struct IntraK {
     static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 4;
     static const int WARPS = 4;
-    static const int REF_OFF = 64, REF_LEN = 64 + 2 * 64 + 8;        // 64 negative-extension slots + 2 * 64 + 1 + 4 samples
+    static const int REF_OFF = 72, REF_LEN = 256;                    // 64 + 2 negative-extension slots (MRL: two more), then 2 * 64 + 1 +
+                                                                     // (m + 1) samples + up to 16 * (m + 1) of wide-angle padding
     static const int SM_WARP = 4 * REF_LEN * 2;                      // abv, lft, filtered abv, filtered lft (uint16)
     static const int SMEM_BYTES = WARPS * SM_WARP;
 
@@ -59,7 +60,7 @@ struct IntraK {
 
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
-        int valid, chroma, pd, ciip;                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
+        int valid, chroma, pd, ciip, mrl;                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
         int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
         int mlw, mlh;                                // block size as seen by the class (swapped for the horizontal class)
@@ -82,7 +83,8 @@ struct IntraK {
         if (!b.valid) return b;
         const int sh = b.chroma;
         b.x0 = c.x0 >> sh; b.y0 = c.y0 >> sh; b.lw = c.log2_w - sh; b.lh = c.log2_h - sh; b.cols = c.avail_cols; b.rows = c.avail_rows;
-        b.pd = !b.chroma || (b.lw > 1 && b.lh > 1);
+        b.mrl = (b.chroma || b.ciip) ? 0 : c.mrl_idx;
+        b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : !b.mrl;
         int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
         b.mode = mode;                                 // 0 planar, 1 DC, else angular (the remapped value lives in mode_idx)
         b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
@@ -96,7 +98,12 @@ struct IntraK {
             if (!b.vert) { b.mlw = b.lh; b.mlh = b.lw; }
             b.a = b.mode_idx < 0 ? -b.mode_idx : b.mode_idx;
             b.gauss = !b.chroma && (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
-            if (b.a == 0) {
+            if (b.mrl) {                                                                       // vvc_intra_pred_multi_ref: no filter, no PDPC
+                b.gauss = 0;
+                b.angle = b.a == 16 ? 32 : intra_angle_tab[b.a]; b.inv = intra_inv_angle_tab[b.a];
+                b.frac = (b.angle & 31) != 0;
+                if (b.mode_idx < 0) { b.ext = 1; b.angle = -b.angle; }
+            } else if (b.a == 0) {
                 b.use_pdpc = b.chroma ? b.pd : (b.gauss || b.mlh > 1);
             } else if (b.mode_idx == 16) {
                 b.use_pdpc = b.chroma ? b.pd : (b.gauss || b.mlh > 1);
@@ -112,7 +119,7 @@ struct IntraK {
                 else { b.filt_m = b.filt_s = f; b.use_pdpc = 1; }
             }
         } else if (mode == 0) {
-            b.filt_m = b.filt_s = !b.chroma && (b.lw + b.lh) > 5;                              // planar: rcn_intra.c:531-538
+            b.filt_m = b.filt_s = !b.chroma && !b.mrl && (b.lw + b.lh) > 5;                              // planar: rcn_intra.c:531-538
         }
         return b;
     }
@@ -145,10 +152,47 @@ struct IntraK {
         }
     }
 
+    // fill_ref_left_0_mref / fill_ref_above_0_mref (rcn_fill_ref.c:228-318, 493-590): raw[0] = the sample m + 1 away both ways,
+    // corner group of m + 1 samples, then 4-sample units; see oracle/port_intra.c for the two left / above differences
+    OVD void fill_ref_mref(uint16_t *raw, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                           uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int m, int is_left)
+    {
+        const int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1 + (m + 1);
+        const int ratio = ovd_max(1, (1 << log2_len) >> log2_other);
+        const uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask;
+        int nb_avl = 0;
+        for (uint64_t t = avl; t; t >>= 1) nb_avl++;
+        const int first = (avl & 1) ? 0 : (is_left ? 1 : m + 1);                               // replicated corner-group sample
+        const int grp_off = (is_left && !(avl & 1)) ? 1 : m + 1;                               // p index of the first unit sample
+        int pad = 1 << (bitdepth - 1);
+        if (!avl) {
+            const int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
+            const uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+            if (avl_o) pad = is_left ? p[(size_t)(1 + m) * other_step] : p[(ptrdiff_t)m * step + (ptrdiff_t)(m + 1) * other_step];
+        } else if (nb_avl > 1) pad = p[(ptrdiff_t)(grp_off + 4 * (nb_avl - 1) - 1) * step];
+        else if (!is_left) pad = p[(ptrdiff_t)m * step];
+        for (int i = lane; i < ref_len - 1 + ratio * (m + 1); i += 32) {
+            int v = pad;
+            const int k = ovd_min(i, ref_len - 2);         // the reference's wide-angle padding starts on the last sample (:312-316)
+            if (avl) {
+                if (k < m + 1) v = (avl & 1) ? p[(ptrdiff_t)k * step] : p[(ptrdiff_t)first * step];
+                else if (1 + ((k - (m + 1)) >> 2) < nb_avl) v = p[(ptrdiff_t)(grp_off + k - (m + 1)) * step];
+            }
+            raw[i] = (uint16_t)v;
+        }
+    }
+
     // one sample of the vertical-class prediction at (x along the main reference, y across)
     OVD int class_pixel(const Blk &b, const uint16_t *M, const uint16_t *S, int tl, int x, int y, int maxv)
     {
         const int W = 1 << b.mlw;
+        if (b.mrl) {                                                    // intra_angular_{v,h}_cubic_mref and the nofrac kernels
+            if (b.a == 0) return M[x + 1];
+            const int delta = (y + 1 + b.mrl) * b.angle, di = delta >> 5, df = delta & 31;
+            const uint16_t *r = M + x + di;
+            if (!b.frac) return r[1];
+            return ovd_clamp((r[0] * intra_cubic[df][0] + r[1] * intra_cubic[df][1] + r[2] * intra_cubic[df][2] + r[3] * intra_cubic[df][3] + 32) >> 6, 0, maxv);
+        }
         if (b.a == 0) {
             if (!b.use_pdpc) return M[x + 1];
             return ovd_clamp((pdpc_w((b.lw + b.lh - 2) >> 2, x) * (S[y + 1] - tl) + (M[x + 1] << 6) + 32) >> 6, 0, maxv);
@@ -191,7 +235,12 @@ struct IntraK {
         uint16_t *dst = plane + (size_t)b.y0 * pitch + b.x0;
 
         if (P == 0) {
-            const uint16_t *corner = dst - pitch - 1;
+            const uint16_t *corner = dst - (ptrdiff_t)(b.mrl + 1) * pitch - (b.mrl + 1);
+            if (b.mrl) {                                                    // abv / lft = raw + m: [1 + i] is the i-th sample of line m
+                fill_ref_mref(lft - b.mrl, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, b.mrl, 1);
+                fill_ref_mref(abv - b.mrl, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, b.mrl, 0);
+                return;
+            }
             fill_ref(lft, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, us, b.chroma);
             fill_ref(abv, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, us, 0);
             return;
@@ -210,7 +259,7 @@ struct IntraK {
         if (P == 2) {
             if (b.ext) {                                                    // rcn_intra.c:118-121
                 const int H = 1 << b.mlh;
-                for (int k = 1 + lane; k <= H; k += 32) M[-k] = S[ovd_min((256 + k * b.inv) >> 9, H)];
+                for (int k = 1 + lane; k <= H; k += 32) M[-b.mrl - k] = S[-b.mrl + ovd_min((256 + k * b.inv) >> 9, H)];
             }
             return;
         }

@@ -13,7 +13,7 @@ assert INTRA_CMD.itemsize == 32
 INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP = 1, 2, 4
 
 
-def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0):
+def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0):
     rng = np.random.default_rng(seed)
     part = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
@@ -32,6 +32,8 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
         if p_ciip and lw + lh >= 6 and rng.random() < p_ciip:       # CIIP: CUs of >= 64 samples (4x16 has the narrow-chroma rule)
             c["flags"] |= INTRA_CIIP
             c["ciip_wt"] = int(rng.integers(1, 4))
+        if p_mrl and (y & ((1 << log2_ctu) - 1)) and not (c["flags"] & INTRA_CIIP) and rng.random() < p_mrl:
+            c["mrl_idx"] = int(rng.integers(1, 3))                 # not on the first row of a CTU (vcl_coding_unit.c:1377)
     return cmds
 
 

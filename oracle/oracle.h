@@ -228,7 +228,8 @@ typedef struct OVOIntraCmd {
     uint8_t mode;                 /* luma: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
     uint8_t mode_c;               /* chroma: same range (DM already resolved) */
     uint8_t flags;
-    uint8_t mrl_idx;              /* reserved (multi reference line index) */
+    uint8_t mrl_idx;              /* luma reference line 0..2 (ctudec->cu_opaque with flg_mrl_flag; vvc_intra_pred_multi_ref,
+                                   * rcn_intra.c:645-786); needs y0 >= 4 inside the CTU */
     uint8_t ciip_wt;              /* CIIP: 1 + above CU is intra + left CU is intra (1..3) */
     uint8_t pad[5];
     uint64_t avail_cols, avail_rows;

@@ -63,6 +63,68 @@ static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t
     for (int i = 0; i < 4; i++) ref[ref_len + i] = ref[ref_len - 1];
 }
 
+/* fill_ref_left_0_mref / fill_ref_above_0_mref (rcn_fill_ref.c:228-318, 493-590) for reference line m = mrl_idx >= 1:
+ * raw[0] is the sample at distance m + 1 from the block both ways (p), the corner group is m + 1 samples, then 4-sample
+ * units; raw has 2 * len + 1 + (m + 1) samples + ratio * (m + 1) of wide-angle padding.  is_left selects the two places
+ * where the reference's left and above variants differ.  Cases the decoder cannot reach (MRL needs y0 > 0 inside the CTU,
+ * vcl_coding_unit.c:1377): left units available without the corner unit -- restated as written (:264-270, the unit copy
+ * then starts m rows early); no above unit at all -- the reference leaves m + 1 entries unwritten (:553-575), here they
+ * get the padding value. */
+static void fill_ref_mref(uint16_t *raw, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                          uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int m, int is_left)
+{
+    int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1 + (m + 1);
+    int ratio = (1 << log2_len) >> log2_other; if (ratio < 1) ratio = 1;
+    uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> 2)) & mask, navl = avl ^ mask;
+    if (!navl) {
+        for (int i = 0; i < ref_len; i++) raw[i] = p[i * step];
+    } else if (avl) {
+        int nb_avl = 64 - __builtin_clzll(avl), i;
+        const uint16_t *q = p;
+        uint16_t *d = raw;
+        uint16_t pad = (uint16_t)(1 << (bitdepth - 1));
+        if (avl & 1) { for (i = 0; i < m + 1; i++) { *d++ = *q; q += step; } }
+        else {
+            q += is_left ? step : (m + 1) * step;
+            for (i = 0; i < m + 1; i++) *d++ = *q;
+        }
+        if (!is_left) pad = q[-step];                              /* above: src_line[-1] after the copy loop (:541) */
+        for (i = 1; i < nb_avl; i++) { for (int k = 0; k < 4; k++) d[k] = q[k * step]; pad = q[3 * step]; q += 4 * step; d += 4; }
+        for (; i < nb_units; i++) { for (int k = 0; k < 4; k++) d[k] = pad; d += 4; }
+    } else {
+        int nb_units_o = ((1 << (log2_other + 1)) >> 2) + 1;
+        uint64_t avl_o = (other_map >> (other_pos >> 2)) & ((1ull << (nb_units_o + 1)) - 1);
+        uint16_t pad = (uint16_t)(1 << (bitdepth - 1));
+        if (avl_o) pad = is_left ? p[(1 + m) * other_step] : p[m * step + (m + 1) * other_step];
+        for (int i = 0; i < ref_len; i++) raw[i] = pad;
+    }
+    /* wide-angle padding as written (:312-316, :583-587): it starts ON the last sample, which is therefore replaced by its
+     * neighbour in every case */
+    for (int i = 0; i < ratio * (m + 1); i++) raw[ref_len - 1 + i] = raw[ref_len - 2 + i];
+}
+
+/* vvc_intra_pred_multi_ref (rcn_intra.c:645-786): no reference filtering, no PDPC, cubic interpolation only, every row
+ * m lines further along the prediction direction (intra_angular_{v,h}_cubic_mref, rcn_intra_angular.c:932-1005) */
+static void mrl_class(int *out, uint16_t *M, const uint16_t *S, int lw, int lh, int mode_idx, int maxv, int m)
+{
+    int W = 1 << lw, H = 1 << lh, a = abs(mode_idx);
+    int angle = a == 16 ? 32 : angle_table[a];
+    if (mode_idx < 0) {
+        int inv = inv_angle_table[a];
+        for (int k = -1, sum = 256; k >= -H; k--) { sum += inv; M[-m + k] = S[-m + imin(sum >> 9, H)]; }   /* :709-713 on the raw arrays */
+        angle = -angle;
+    }
+    for (int y = 0; y < H; y++) {
+        int delta = (y + 1 + m) * angle, di = delta >> 5, df = delta & 31;
+        for (int x = 0; x < W; x++) {
+            const uint16_t *r = M + x + di;
+            if (a == 0) out[y * W + x] = M[x + 1];
+            else if (!(angle & 31)) out[y * W + x] = r[1];
+            else out[y * W + x] = clipi((r[0] * cubic[df][0] + r[1] * cubic[df][1] + r[2] * cubic[df][2] + r[3] * cubic[df][3] + 32) >> 6, 0, maxv);
+        }
+    }
+}
+
 /* filter_ref_samples, rcn_fill_ref.c:47-68 */
 static void filter_ref(uint16_t *dst, const uint16_t *src, const uint16_t *src2, int length)
 {
@@ -141,20 +203,25 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
 
 /* one block of one plane; chroma: x0 / y0 / log2 sizes in chroma samples */
 static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int mode_in,
-                        uint64_t cols, uint64_t rows, int chroma, int ciip_wt)
+                        uint64_t cols, uint64_t rows, int chroma, int ciip_wt, int mrl)
 {
     int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, us = chroma ? 1 : 2;
     uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
     uint16_t *dst = plane + (size_t)y0 * stride + x0;
-    const uint16_t *corner = dst - stride - 1;
-    fill_ref(lft, corner, stride, 1, lh, lw, cols, rows, yl, xl, bitdepth, us, chroma);
-    fill_ref(abv, corner, 1, stride, lw, lh, rows, cols, xl, yl, bitdepth, us, 0);
+    const uint16_t *corner = dst - (ptrdiff_t)(mrl + 1) * stride - (mrl + 1);
+    if (mrl) {          /* abv / lft point at raw + mrl, so that [1 + i] is the i-th sample of the reference line (:676-677) */
+        fill_ref_mref(lft - mrl, corner, stride, 1, lh, lw, cols, rows, yl, xl, bitdepth, mrl, 1);
+        fill_ref_mref(abv - mrl, corner, 1, stride, lw, lh, rows, cols, xl, yl, bitdepth, mrl, 0);
+    } else {
+        fill_ref(lft, corner, stride, 1, lh, lw, cols, rows, yl, xl, bitdepth, us, chroma);
+        fill_ref(abv, corner, 1, stride, lw, lh, rows, cols, xl, yl, bitdepth, us, 0);
+    }
     int *out = malloc(sizeof(int) * w * h);
-    int pd = chroma ? (lw > 1 && lh > 1) : 1;
+    int pd = chroma ? (lw > 1 && lh > 1) : !mrl;
     if (mode_in == 0) {                                            /* intra_planar(_pdpc), rcn_intra_dc_planar.c:106-149, 196-236 */
         uint16_t fa[REF_LEN], fl[REF_LEN];
         const uint16_t *A = abv, *L = lft;
-        if (!chroma && lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
+        if (!chroma && !mrl && lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
         int ws = lw > 1 ? lw : 1, hs = lh > 1 ? lh : 1, scale = (lw + lh - 2) >> 2;
         if (!pd) { ws = lw; hs = lh; }
         for (int y = 0; y < h; y++)
@@ -181,10 +248,12 @@ static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y
         if (lw > lh && mode < 2 + ms) mode += 65;
         else if (lh > lw && mode > 66 - ms) mode -= 65;
         if (mode >= 34) {
-            angular_class(out, abv, lft, abv[0], lw, lh, mode - 50, maxv, chroma);
+            if (mrl) mrl_class(out, abv, lft, lw, lh, mode - 50, maxv, mrl);
+            else angular_class(out, abv, lft, abv[0], lw, lh, mode - 50, maxv, chroma);
         } else {
             int *t = malloc(sizeof(int) * w * h);
-            angular_class(t, lft, abv, abv[0], lh, lw, 18 - mode, maxv, chroma);
+            if (mrl) mrl_class(t, lft, abv, lh, lw, 18 - mode, maxv, mrl);
+            else angular_class(t, lft, abv, abv[0], lh, lw, 18 - mode, maxv, chroma);
             for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * w + x] = t[x * h + y];
             free(t);
         }
@@ -208,10 +277,10 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
         int ciip = (c->flags & OVO_INTRA_CIIP) ? c->ciip_wt : 0;
         if (c->flags & OVO_INTRA_LUMA)
             intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, ciip ? 0 : c->mode,
-                        c->avail_cols, c->avail_rows, 0, ciip);
+                        c->avail_cols, c->avail_rows, 0, ciip, ciip ? 0 : c->mrl_idx);
         if ((c->flags & OVO_INTRA_CHROMA) && !(ciip && c->log2_w <= 2))    /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr */
             for (int k = 1; k < 3; k++)
                 intra_block(planes[k], stride[k], bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1,
-                            c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip);
+                            c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip, 0);
     }
 }

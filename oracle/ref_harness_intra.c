@@ -135,7 +135,9 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
                 if (m->flags & OVO_INTRA_CIIP) {
                     ciip_block(c, m, x0, y0, inter_pic, stride);
                 } else {
-                if (m->flags & OVO_INTRA_LUMA)
+                if ((m->flags & OVO_INTRA_LUMA) && m->mrl_idx)       /* rcn_transform_tree.c:1413-1419 */
+                    c->rcn_funcs.intra_pred_mrl(c, c->rcn_ctx.ctu_buff.y, c->rcn_ctx.ctu_buff.stride, m->mode, x0, y0, m->log2_w, m->log2_h, m->mrl_idx);
+                else if (m->flags & OVO_INTRA_LUMA)
                     c->rcn_funcs.intra_pred(&c->rcn_ctx, &c->rcn_ctx.ctu_buff, m->mode, x0, y0, m->log2_w, m->log2_h, flg_pred_mode_flag);
                 if (m->flags & OVO_INTRA_CHROMA) {
                     /* single tree: the chroma field is updated with the same rectangles as the luma one (rcn_tu_st, :1275) */

@@ -17,14 +17,17 @@ CASES = [(128, 128, 901, 7, 0), (416, 240, 902, 7, 0), (832, 480, 903, 7, 0), (2
          # luma + Cb / Cr (rcn_funcs.intra_pred_c): md5 over the three planes
          (128, 128, 911, 7, 1), (416, 240, 912, 7, 1), (264, 136, 914, 6, 1), (200, 120, 915, 5, 1), (1920, 1080, 916, 7, 1),
          # + CIIP blocks (chroma = 2)
-         (416, 240, 922, 7, 2), (832, 480, 923, 7, 2)]
+         (416, 240, 922, 7, 2), (832, 480, 923, 7, 2),
+         # + multi reference line blocks (chroma = 3)
+         (416, 240, 932, 7, 3), (264, 136, 934, 6, 3)]
 
 
 def main():
     assert po.ref_available()
     out = []
     for (w, h, seed, log2, chroma) in CASES:
-        planes, cmds = helpers_intra.intra_case(w, h, seed, log2, chroma=bool(chroma), p_ciip=0.4 if chroma == 2 else 0.0)
+        planes, cmds = helpers_intra.intra_case(w, h, seed, log2, chroma=bool(chroma), p_ciip=0.4 if chroma >= 2 else 0.0,
+                                                p_mrl=0.4 if chroma == 3 else 0.0)
         inp = helpers.md5(cmds, planes[0])
         rc = cmds.copy()
         rc["avail_cols"] = 0; rc["avail_rows"] = 0

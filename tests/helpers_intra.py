@@ -6,9 +6,9 @@ import numpy as np
 from openvvc_b200 import synth, synth_intra
 
 
-def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0):
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0):
     """planes + intra commands in decode order with the availability words replayed from that order"""
-    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip), log2_ctu)
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl), log2_ctu)
     return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
 
 

@@ -11,7 +11,7 @@ import helpers
 import helpers_intra
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "intra_golden.json")))
-IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], ("", "_yuv", "_yuv_ciip")[c["chroma"]])
+IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], ("", "_yuv", "_yuv_ciip", "_yuv_ciip_mrl")[c["chroma"]])
 
 
 @pytest.fixture(scope="module")
@@ -22,7 +22,7 @@ def pi(oracle):
 
 def _case(c):
     planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"], chroma=bool(c["chroma"]),
-                                            p_ciip=0.4 if c["chroma"] == 2 else 0.0)
+                                            p_ciip=0.4 if c["chroma"] >= 2 else 0.0, p_mrl=0.4 if c["chroma"] == 3 else 0.0)
     assert helpers.md5(cmds, planes[0]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
     return planes, cmds
 
@@ -106,6 +106,22 @@ def test_ciip_port_vs_reference_and_emu(oracle, pi, emu, w, h, log2):
         for simd in (0, 1):
             got = pi.intra_picture([p.copy() for p in planes], cmds.copy(), log2, impl="ref", simd=simd)
             assert all((got[k] == want[k]).all() for k in range(3)), "CIIP port vs reference (simd=%d)" % simd
+    got, _ = helpers_intra.emu_intra(emu, planes, cmds, log2)
+    assert all((got[k] == want[k]).all() for k in range(3))
+
+
+@pytest.mark.parametrize("w,h,log2", [(416, 240, 7), (264, 136, 6), (200, 120, 5)])
+def test_mrl_port_vs_reference_and_emu(oracle, pi, emu, w, h, log2):
+    """multi reference line (a18): lines 1 and 2, every mode class, blocks on the picture's left edge (no left line)"""
+    planes, cmds = helpers_intra.intra_case(w, h, 17 * w + h, log2, chroma=True, p_mrl=0.5)
+    mrl = cmds["mrl_idx"] > 0
+    assert mrl.sum() > 20 and set(cmds["mrl_idx"]) == {0, 1, 2} and ((mrl & (cmds["x0"] == 0)).any() or w == 264)
+    assert ((cmds["y0"][mrl] & ((1 << log2) - 1)) > 0).all()
+    want = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
+    if oracle.ref_available():
+        for simd in (0, 1):
+            got = pi.intra_picture([p.copy() for p in planes], cmds.copy(), log2, impl="ref", simd=simd)
+            assert all((got[k] == want[k]).all() for k in range(3)), "MRL port vs reference (simd=%d)" % simd
     got, _ = helpers_intra.emu_intra(emu, planes, cmds, log2)
     assert all((got[k] == want[k]).all() for k in range(3))
 
