@@ -323,11 +323,13 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
 #define OVGPU_INTRA_CIIP   4    /* flags: combined inter / intra: planar prediction blended over the inter prediction already in the
                                 * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
                                 * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
+#define OVGPU_INTRA_CCLM_COLLOCATED 8   /* flags: sps_chroma_vertical_collocated_flag (5-tap cross luma down-sampling for CCLM) */
 typedef struct OVGPUIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */
     uint8_t mode;                 /* luma: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
-    uint8_t mode_c;               /* chroma: same range (DM already resolved) */
+    uint8_t mode_c;               /* chroma: same range (DM already resolved), 67 CCLM, 68 MDLM left, 69 MDLM top
+                                   * (rcn_intra_cclm.c; read the luma block of the same command, so luma goes first) */
     uint8_t flags;
     uint8_t mrl_idx;              /* luma reference line 0..2 (ctudec->cu_opaque with flg_mrl_flag; vvc_intra_pred_multi_ref,
                                    * rcn_intra.c:645-786); needs y0 >= 4 inside the CTU */

@@ -8,7 +8,7 @@
 static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 32, "intra command layout");
 
 struct OVGPUIntraBatch {
-    int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu, has_chroma;
+    int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu, has_chroma, has_cclm;
     IntraCmdDev *h_cmds, *d_cmds;
     uint32_t *h_order, *d_order, *level_start;      // level_start: host only, max_cmds + 2 entries
     StagingFence fence;
@@ -60,8 +60,9 @@ int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntra
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->nb_levels = 0;
     if (!nb_cmds) return 0;
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
-    b->has_chroma = 0;
-    for (int i = 0; i < nb_cmds; i++) b->has_chroma |= cmds[i].flags & OVGPU_INTRA_CHROMA;
+    b->has_chroma = b->has_cclm = 0;
+    for (int i = 0; i < nb_cmds; i++)
+        if (cmds[i].flags & OVGPU_INTRA_CHROMA) { b->has_chroma = 1; b->has_cclm |= cmds[i].mode_c >= 67; }
     b->nb_levels = intra_build_levels(b->h_order, b->level_start, b->max_cmds, cmds, nb_cmds, pic_w, pic_h);
     if (b->nb_levels < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
@@ -79,13 +80,15 @@ int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
     if (pic->width != b->pic_w || pic->height != b->pic_h)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
     PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);
-    StageScope scope(ctx, OVGPU_STAGE_INTRA, b->nb_levels);
-    for (int l = 0; l < b->nb_levels; l++) {
-        const int start = (int)b->level_start[l], n = (int)b->level_start[l + 1] - start;
-        if (n <= 0) continue;
-        IntraK::Args a = { { v0.p, v1.p, v2.p }, { v0.pitch, v1.pitch, v2.pitch }, b->log2_ctu, pic->bitdepth, b->d_cmds, b->d_order + start, n };
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), b->has_chroma ? 3 : 1, 1), IntraK::SMEM_BYTES, ctx->stream));
-    }
+    const int launches_per_level = b->has_cclm ? 2 : 1;
+    StageScope scope(ctx, OVGPU_STAGE_INTRA, b->nb_levels * launches_per_level);
+    cudaError_t err = cudaSuccess;
+    intra_for_each_launch(b->nb_levels, b->level_start, b->has_chroma, b->has_cclm, [&](int start, int n, int comp0, int ncomp) {
+        IntraK::Args a = { { v0.p, v1.p, v2.p }, { v0.pitch, v1.pitch, v2.pitch }, b->log2_ctu, pic->bitdepth, b->d_cmds, b->d_order + start, n, comp0 };
+        err = ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), ncomp, 1), IntraK::SMEM_BYTES, ctx->stream);
+        return err == cudaSuccess ? 0 : -1;
+    });
+    OVGPU_CUDA_CHECK(ctx, err);
     return 0;
 }
 

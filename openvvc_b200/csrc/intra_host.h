@@ -9,8 +9,8 @@
 static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 {
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~7)) return -1;
-    if (((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) || ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 66)) return -1;
+    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~15)) return -1;
+    if (((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) || ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 69)) return -1;
     if ((c->flags & OVGPU_INTRA_CIIP) && (c->ciip_wt < 1 || c->ciip_wt > 3)) return -1;
     if (c->mrl_idx > 2 || (c->mrl_idx && (c->y0 < 4 || c->x0 + (1 << c->log2_w) > pic_w))) return -1;
     if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;
@@ -55,4 +55,20 @@ static inline int intra_build_levels(uint32_t *order, uint32_t *level_start, int
     for (int l = 0; l <= nb_levels; l++) level_start[l] = level_start[l + 1];
     free(fill); free(lvl_map); free(lvl);
     return nb_levels;
+}
+
+// Launch sequence of a picture: one grid per dependency level covering the components present; a level whose chroma
+// blocks may use CCLM (they read the luma block of the same command) runs luma first, then Cb / Cr.
+// f(first command of the level in order[], number of commands, first component, number of components) -> 0 on success
+template <typename F>
+static inline int intra_for_each_launch(int nb_levels, const uint32_t *level_start, int has_chroma, int has_cclm, F f)
+{
+    for (int l = 0; l < nb_levels; l++) {
+        const int start = (int)level_start[l], n = (int)level_start[l + 1] - start;
+        if (n <= 0) continue;
+        int rc;
+        if (has_cclm) { if ((rc = f(start, n, 0, 1)) != 0 || (rc = f(start, n, 1, 2)) != 0) return rc; }
+        else if ((rc = f(start, n, 0, has_chroma ? 3 : 1)) != 0) return rc;
+    }
+    return 0;
 }

@@ -55,12 +55,13 @@ struct IntraK {
         const IntraCmdDev *cmds;
         const uint32_t *order;      // command indices of this level
         int nb;
+        int comp0;                  // component of grid row 0 (a level with CCLM blocks runs luma first, then Cb / Cr)
     };
     struct State { int dummy; };
 
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
-        int valid, chroma, pd, ciip, mrl;                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
+        int valid, chroma, pd, ciip, mrl, cclm, coll;  // cclm: 0 or the chroma mode 67 (LM) / 68 (MDLM left) / 69 (MDLM top)                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
         int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
         int mlw, mlh;                                // block size as seen by the class (swapped for the horizontal class)
@@ -86,6 +87,9 @@ struct IntraK {
         b.mrl = (b.chroma || b.ciip) ? 0 : c.mrl_idx;
         b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : !b.mrl;
         int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
+        b.cclm = mode >= 67 ? mode : 0;
+        b.coll = (c.flags & 8) != 0;
+        if (b.cclm) mode = 0;
         b.mode = mode;                                 // 0 planar, 1 DC, else angular (the remapped value lives in mode_idx)
         b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
         b.mode_idx = b.a = b.angle = b.inv = b.frac = b.gauss = b.pdpc_scale = b.use_pdpc = b.filt_m = b.filt_s = b.ext = 0;
@@ -182,6 +186,86 @@ struct IntraK {
         }
     }
 
+    // CCLM luma down-sampling at luma (2i, 2j): 6-tap over two rows, or the 5-tap cross when chroma is vertically collocated
+    // (compute_lm_subsample(_cl), rcn_intra_cclm.c:297-324, 626-657)
+    OVD int lm_luma(const uint16_t *y, ptrdiff_t st, int coll, int pad_left, int pad_abv)
+    {
+        const int l = pad_left ? 0 : -1;
+        if (coll) return (y[pad_abv ? 0 : -st] + 4 * y[0] + y[l] + y[1] + y[st] + 4) >> 3;
+        return (y[l] + 2 * y[0] + y[1] + y[st + l] + 2 * y[st] + y[st + 1] + 4) >> 3;
+    }
+    OVD int cclm_abv(const Blk &b, int cm) { return ((b.rows >> (((b.x0 & cm) >> 1) + 1)) & ((1ull << ((1 << b.lw) >> 1)) - 1)) != 0; }
+    OVD int cclm_lft(const Blk &b, int cm) { return ((b.cols >> (((b.y0 & cm) >> 1) + 1)) & ((1ull << ((1 << b.lh) >> 1)) - 1)) != 0; }
+    OVD int ctz64_ones(uint64_t v) { int n = 0; while (v & 1) { v >>= 1; n++; } return n; }       // ctz(~v)
+
+    // linear-model parameters of one chroma component (one lane): neighbour selection (intra_cclm / intra_mdlm_*,
+    // :659-883), min / max pairing (:137-186), a / b / shift (:72-135)
+    OVD void cclm_params(const Blk &b, const uint16_t *Y, ptrdiff_t sl, const uint16_t *C, ptrdiff_t sc, int cm, int bitdepth, int *prm)
+    {
+        const int w = 1 << b.lw, h = 1 << b.lh, xl = b.x0 & cm, yl = b.y0 & cm;
+        const int abv = cclm_abv(b, cm), lft = cclm_lft(b, cm);
+        int nb_abv = 0, nb_lft = 0, abv_step = 1, lft_step = 1;
+        if (b.cclm == 67) {
+            if (abv) { nb_abv = ovd_min(w, (abv + !lft) << 1); abv_step = w >> (abv + !lft); }
+            if (lft) { nb_lft = ovd_min(h, (lft + !abv) << 1); lft_step = h >> (lft + !abv); }
+        } else if (b.cclm == 69) {
+            if (abv) {
+                const int nb_units = (w + ovd_min(h, w)) >> 1;
+                const int len = ctz64_ones((b.rows >> ((xl >> 1) + 1)) & ((1ull << nb_units) - 1)) << 1;
+                nb_abv = ovd_min(len, 4); abv_step = len >> 2;
+            }
+        } else if (lft) {
+            const int nb_units = (h + ovd_min(h, w)) >> 1;
+            const int len = ctz64_ones((b.cols >> ((yl >> 1) + 1)) & ((1ull << nb_units) - 1)) << 1;
+            nb_lft = ovd_min(len, 4); lft_step = len >> 2;
+        }
+        abv_step = ovd_max(abv_step, 1); lft_step = ovd_max(lft_step, 1);
+        int sy[4] = { 0, 0, 0, 0 }, scv[4] = { 0, 0, 0, 0 };
+        const int n = nb_abv + nb_lft;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < nb_abv) {
+                const int x = (abv_step >> 1) + i * abv_step, pad_left = x == 0 && !lft;
+                if (yl == 0) { const uint16_t *r = Y - sl + 2 * x; sy[i] = (r[pad_left ? 0 : -1] + 2 * r[0] + r[1] + 2) >> 2; }
+                else sy[i] = lm_luma(Y - 2 * sl + 2 * x, sl, b.coll, pad_left, 0);
+                scv[i] = C[-sc + x];
+            } else if (i < n) {
+                const int y = (lft_step >> 1) + (i - nb_abv) * lft_step;
+                sy[i] = lm_luma(Y + (ptrdiff_t)(2 * y) * sl - 2, sl, b.coll, 0, y == 0 && !abv);
+                scv[i] = C[(ptrdiff_t)y * sc - 1];
+            }
+        }
+        prm[0] = 0; prm[1] = 1 << (bitdepth - 1); prm[2] = 0;
+        if (!n) return;
+        int min_l, max_l, min_c, max_c;
+        if (n == 2) {
+            const int sw = sy[0] >= sy[1];
+            min_l = sw ? sy[1] : sy[0]; max_l = sw ? sy[0] : sy[1];
+            min_c = sw ? scv[1] : scv[0]; max_c = sw ? scv[0] : scv[1];
+        } else {
+            // the reference's 4-element sorting network on (luma, chroma) pairs: {mn0, mn1} = the two smaller, {mx0, mx1} the larger
+            int l0 = sy[0], l1 = sy[2], l2 = sy[1], l3 = sy[3], c0 = scv[0], c1 = scv[2], c2 = scv[1], c3 = scv[3], t;
+            if (sy[0] > sy[2]) { t = l0; l0 = l1; l1 = t; t = c0; c0 = c1; c1 = t; }
+            if (sy[1] > sy[3]) { t = l2; l2 = l3; l3 = t; t = c2; c2 = c3; c3 = t; }
+            if (l0 > l3) { t = l0; l0 = l2; l2 = t; t = l1; l1 = l3; l3 = t; t = c0; c0 = c2; c2 = t; t = c1; c1 = c3; c3 = t; }
+            if (l1 > l2) { t = l1; l1 = l2; l2 = t; t = c1; c1 = c2; c2 = t; }
+            min_l = (l0 + l1 + 1) >> 1; max_l = (l2 + l3 + 1) >> 1;
+            min_c = (c0 + c1 + 1) >> 1; max_c = (c2 + c3 + 1) >> 1;
+        }
+        prm[0] = 0; prm[1] = min_c; prm[2] = 0;
+        const int range_l = max_l - min_l;
+        if (!range_l) return;
+        int l2r = floor_log2((unsigned)range_l);
+        const int norm = ((range_l << 4) >> l2r) & 15;
+        const int v = (int)((0x0111122334455670ull >> (4 * norm)) & 15) | 8;     // div_lut {0,7,6,5,5,4,4,3,3,2,2,1,1,1,1,0}
+        l2r += norm != 0;
+        const int range_c = max_c - min_c;
+        const int l2c = range_c ? floor_log2((unsigned)(range_c < 0 ? -range_c : range_c)) + 1 : 0;
+        int ac = (range_c * v + ((1 << l2c) >> 1)) >> l2c, shift = 3 + l2r - l2c;
+        if (shift < 1) { shift = 1; ac = ac ? (ac < 0 ? -15 : 15) : 0; }
+        prm[0] = ac; prm[1] = min_c - ((ac * min_l) >> shift); prm[2] = shift;
+    }
+
     // one sample of the vertical-class prediction at (x along the main reference, y across)
     OVD int class_pixel(const Blk &b, const uint16_t *M, const uint16_t *S, int tl, int x, int y, int maxv)
     {
@@ -224,15 +308,31 @@ struct IntraK {
     {
         (void)st; (void)bz;
         const int warp = tid >> 5, lane = tid & 31;
-        const Blk b = load(a, bx * WARPS + warp, by);
+        const int comp = a.comp0 + by;
+        const Blk b = load(a, bx * WARPS + warp, comp);
         if (!b.valid) return;
-        uint16_t *plane = by == 0 ? a.plane[0] : (by == 1 ? a.plane[1] : a.plane[2]);
-        const int pitch = by == 0 ? a.pitch[0] : (by == 1 ? a.pitch[1] : a.pitch[2]);
+        uint16_t *plane = comp == 0 ? a.plane[0] : (comp == 1 ? a.plane[1] : a.plane[2]);
+        const int pitch = comp == 0 ? a.pitch[0] : (comp == 1 ? a.pitch[1] : a.pitch[2]);
         uint16_t *base = (uint16_t *)(smem + warp * SM_WARP);
         uint16_t *abv = base + REF_OFF, *lft = base + REF_LEN + REF_OFF, *fabv = base + 2 * REF_LEN + REF_OFF, *flft = base + 3 * REF_LEN + REF_OFF;
         const int w = 1 << b.lw, h = 1 << b.lh, maxv = (1 << a.bitdepth) - 1, cm = (1 << (a.log2_ctu - b.chroma)) - 1;
         const int us = 2 - b.chroma;
         uint16_t *dst = plane + (size_t)b.y0 * pitch + b.x0;
+        if (b.cclm) {                                                       // parameters by lane 0 in phase 0, prediction in phase 3
+            int *prm = (int *)base;
+            const uint16_t *Y = a.plane[0] + (size_t)(2 * b.y0) * a.pitch[0] + 2 * b.x0;
+            if (P == 0 && lane == 0) cclm_params(b, Y, a.pitch[0], dst, pitch, cm, a.bitdepth, prm);
+            if (P == 3) {
+                const int abv = cclm_abv(b, cm), lft = cclm_lft(b, cm);
+                const int ac = prm[0], bc = prm[1], shift = prm[2];
+                for (int o = lane; o < w * h; o += 32) {
+                    const int x = o & (w - 1), y = o >> b.lw;
+                    const int lm = lm_luma(Y + (ptrdiff_t)(2 * y) * a.pitch[0] + 2 * x, a.pitch[0], b.coll, x == 0 && !lft, y == 0 && !abv);
+                    dst[(size_t)y * pitch + x] = (uint16_t)ovd_clamp(((lm * ac) >> shift) + bc, 0, maxv);
+                }
+            }
+            return;
+        }
 
         if (P == 0) {
             const uint16_t *corner = dst - (ptrdiff_t)(b.mrl + 1) * pitch - (b.mrl + 1);

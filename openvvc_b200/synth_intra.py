@@ -10,10 +10,15 @@ INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), 
                       ("avail_cols", np.uint64), ("avail_rows", np.uint64)])
 assert INTRA_CMD.itemsize == 32
 
-INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP = 1, 2, 4
+INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED = 1, 2, 4, 8
 
 
-def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0):
+def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0,
+                   collocated=False, p_inter=0.0):
+    """p_inter: fraction of coding units that are NOT intra (flags = 0 placeholders): they keep the picture's samples -- the
+    already reconstructed inter CUs of a real picture -- and only take part in the availability replay.  Without them an
+    all-intra picture without residual degenerates to the mid value everywhere.  The placeholders are for the oracle
+    harness (which has to mark them in the reference's progress field); drop them before handing commands to the GPU."""
     rng = np.random.default_rng(seed)
     part = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
@@ -21,6 +26,8 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
         c = cmds[i]
         c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
         r = rng.random()
+        if p_inter and rng.random() < p_inter:
+            continue
         c["flags"] = INTRA_LUMA
         c["mode"] = 0 if r < 0.15 else (1 if r < 0.3 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.4 else int(rng.integers(2, 67))))
         if chroma:
@@ -29,6 +36,10 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
             mc = int(c["mode"]) if r < 0.4 else (0 if r < 0.5 else (1 if r < 0.6 else (int(rng.choice([18, 50, 2, 34, 66])) if r < 0.7 else int(rng.integers(2, 67)))))
             c["flags"] |= INTRA_CHROMA
             c["mode_c"] = mc
+            if p_cclm and rng.random() < p_cclm:                   # CCLM / MDLM left / MDLM top (30 % of chroma)
+                c["mode_c"] = int(rng.integers(67, 70))
+                if collocated:
+                    c["flags"] |= INTRA_CCLM_COLLOCATED
         if p_ciip and lw + lh >= 6 and rng.random() < p_ciip:       # CIIP: CUs of >= 64 samples (4x16 has the narrow-chroma rule)
             c["flags"] |= INTRA_CIIP
             c["ciip_wt"] = int(rng.integers(1, 4))

@@ -217,16 +217,20 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
 /* One rcn_funcs.intra_pred call (vvc_intra_pred, rcn_intra.c:484-560): luma block, no ISP / MRL / MIP / BDPCM.
  * avail_cols / avail_rows are progress_field.vfield[x0 >> 2] / .hfield[y0 >> 2] at call time (CTU-local, bit 0 = the
  * unit of the neighbouring CTU line, bit 1 + u = 4x4 unit u): syntax-order information recorded on the CPU. */
+/* flags == 0: placeholder for a coding unit that is not intra (oracle only): its samples stay, the reference harness
+ * marks it in the progress field like the decoder does for every reconstructed CU */
 #define OVO_INTRA_LUMA   1    /* flags: the command predicts a luma block with `mode` */
 #define OVO_INTRA_CHROMA 2    /* flags: Cb and Cr blocks of half the size are predicted with `mode_c` (single tree: same availability) */
 #define OVO_INTRA_CIIP   4    /* flags: combined inter / intra: planar prediction blended over the inter prediction already in the
                                 * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
                                 * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
+#define OVO_INTRA_CCLM_COLLOCATED 8   /* flags: sps_chroma_vertical_collocated_flag (5-tap cross luma down-sampling for CCLM) */
 typedef struct OVOIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */
     uint8_t mode;                 /* luma: 0 planar, 1 DC, 2..66 angular (before wide-angle remapping) */
-    uint8_t mode_c;               /* chroma: same range (DM already resolved) */
+    uint8_t mode_c;               /* chroma: same range (DM already resolved), 67 CCLM, 68 MDLM left, 69 MDLM top
+                                   * (rcn_intra_cclm.c; read the luma block of the same command, so luma goes first) */
     uint8_t flags;
     uint8_t mrl_idx;              /* luma reference line 0..2 (ctudec->cu_opaque with flg_mrl_flag; vvc_intra_pred_multi_ref,
                                    * rcn_intra.c:645-786); needs y0 >= 4 inside the CTU */

@@ -201,6 +201,114 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
     }
 }
 
+/* ---- cross-component linear model (rcn_intra_cclm.c:57-903) -------------------------------------------------------------
+ * One luma sample per chroma position: 6-tap [1 2 1; 1 2 1] over two luma rows (compute_lm_subsample :626-657) or, with
+ * sps_chroma_vertical_collocated_flag, the 5-tap cross (compute_lm_subsample_cl :297-324); y points at luma (2i, 2j). */
+static int lm_luma(const uint16_t *y, ptrdiff_t st, int coll, int pad_left, int pad_abv)
+{
+    int l = pad_left ? 0 : -1;
+    if (coll) return (y[pad_abv ? 0 : -st] + 4 * y[0] + y[l] + y[1] + y[st] + 4) >> 3;
+    return (y[l] + 2 * y[0] + y[1] + y[st + l] + 2 * y[st] + y[st + 1] + 4) >> 3;
+}
+
+typedef struct { int a, b, shift; } LmParams;
+
+/* compute_lm_params, :72-106 */
+static LmParams lm_params_c(int min_l, int min_c, int max_c, int v, int log2_rng_l)
+{
+    LmParams p;
+    int range_c = max_c - min_c;
+    int l2c = range_c ? floor_log2u((unsigned)abs(range_c)) + 1 : 0;
+    p.a = (range_c * v + ((1 << l2c) >> 1)) >> l2c;
+    p.shift = 3 + log2_rng_l - l2c;
+    if (p.shift < 1) { p.shift = 1; p.a = p.a ? (p.a < 0 ? -15 : 15) : 0; }
+    p.b = min_c - ((p.a * min_l) >> p.shift);
+    return p;
+}
+
+static void cclm_block(uint16_t *const planes[3], const int stride[3], int bitdepth, int x0, int y0, int xl, int yl,
+                       int lw, int lh, int mode, uint64_t lft_map, uint64_t abv_map, int coll)
+{
+    static const uint8_t div_lut[16] = { 0, 7, 6, 5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 1, 1, 0 };
+    int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1;
+    ptrdiff_t sl = stride[0], sc = stride[1];
+    const uint16_t *Y = planes[0] + (size_t)(2 * y0) * sl + 2 * x0;
+    uint16_t *C[2] = { planes[1] + (size_t)y0 * sc + x0, planes[2] + (size_t)y0 * stride[2] + x0 };
+    /* derive_availibilty_status, :57-69: any unit along the block's own width / height */
+    int abv = ((abv_map >> ((xl >> 1) + 1)) & ((1ull << (w >> 1)) - 1)) != 0;
+    int lft = ((lft_map >> ((yl >> 1) + 1)) & ((1ull << (h >> 1)) - 1)) != 0;
+    int nb_abv = 0, nb_lft = 0, abv_step = 1, lft_step = 1;
+    if (mode == 67) {                                              /* intra_cclm(_cl), :659-744 */
+        if (abv) { nb_abv = imin(w, (abv + !lft) << 1); abv_step = w >> (abv + !lft); }
+        if (lft) { nb_lft = imin(h, (lft + !abv) << 1); lft_step = h >> (lft + !abv); }
+    } else if (mode == 69) {                                       /* intra_mdlm_abv(_cl), :746-815: above and above-right */
+        if (abv) {
+            int nb_units = (w + imin(h, w)) >> 1;
+            uint64_t usable = (abv_map >> ((xl >> 1) + 1)) & ((1ull << nb_units) - 1);
+            int len = __builtin_ctzll(~usable) << 1;
+            nb_abv = imin(len, 4); abv_step = len >> 2;
+        }
+    } else {                                                       /* intra_mdlm_lft(_cl), :817-883: left and below-left */
+        if (lft) {
+            int nb_units = (h + imin(h, w)) >> 1;
+            uint64_t usable = (lft_map >> ((yl >> 1) + 1)) & ((1ull << nb_units) - 1);
+            int len = __builtin_ctzll(~usable) << 1;
+            nb_lft = imin(len, 4); lft_step = len >> 2;
+        }
+    }
+    if (abv_step < 1) abv_step = 1;
+    if (lft_step < 1) lft_step = 1;
+    int sy[4], sc_[2][4], n = 0;
+    for (int i = 0; i < nb_abv; i++, n++) {                        /* sub_sample_lm_ref_abv0 / _abv(_cl), :188-212, 267-295, 588-624 */
+        int x = (abv_step >> 1) + i * abv_step, pad_left = x == 0 && !lft;
+        if (yl == 0) {                                             /* first line of the CTU: one luma row, [1 2 1] */
+            const uint16_t *r = Y - sl + 2 * x;
+            sy[n] = (r[pad_left ? 0 : -1] + 2 * r[0] + r[1] + 2) >> 2;
+        } else sy[n] = lm_luma(Y - 2 * sl + 2 * x, sl, coll, pad_left, 0);
+        sc_[0][n] = C[0][-sc + x]; sc_[1][n] = C[1][-(ptrdiff_t)stride[2] + x];
+    }
+    for (int i = 0; i < nb_lft; i++, n++) {                        /* sub_sample_lm_ref_lft(_cl), :214-265, 551-586 */
+        int y = (lft_step >> 1) + i * lft_step;
+        sy[n] = lm_luma(Y + (ptrdiff_t)(2 * y) * sl - 2, sl, coll, 0, y == 0 && !abv);
+        sc_[0][n] = C[0][(ptrdiff_t)y * sc - 1]; sc_[1][n] = C[1][(ptrdiff_t)y * stride[2] - 1];
+    }
+    LmParams prm[2] = { { 0, 1 << (bitdepth - 1), 0 }, { 0, 1 << (bitdepth - 1), 0 } };
+    if (n) {
+        /* sort_average_lm_ref_samples, :137-186 */
+        int min_l, max_l, min_c[2], max_c[2];
+        if (n == 2) {
+            int mi = sy[0] >= sy[1], ma = !mi;
+            min_l = sy[mi]; max_l = sy[ma];
+            for (int k = 0; k < 2; k++) { min_c[k] = sc_[k][mi]; max_c[k] = sc_[k][ma]; }
+        } else {
+            int idx[4] = { 0, 2, 1, 3 }, *mn = &idx[0], *mx = &idx[2], t;
+            if (sy[0] > sy[2]) { t = mn[0]; mn[0] = mn[1]; mn[1] = t; }
+            if (sy[1] > sy[3]) { t = mx[0]; mx[0] = mx[1]; mx[1] = t; }
+            if (sy[mn[0]] > sy[mx[1]]) { int *tp = mn; mn = mx; mx = tp; }
+            if (sy[mn[1]] > sy[mx[0]]) { t = mn[1]; mn[1] = mx[0]; mx[0] = t; }
+            min_l = (sy[mn[0]] + sy[mn[1]] + 1) >> 1; max_l = (sy[mx[0]] + sy[mx[1]] + 1) >> 1;
+            for (int k = 0; k < 2; k++) {
+                min_c[k] = (sc_[k][mn[0]] + sc_[k][mn[1]] + 1) >> 1;
+                max_c[k] = (sc_[k][mx[0]] + sc_[k][mx[1]] + 1) >> 1;
+            }
+        }
+        /* derive_cclm_params, :108-135 */
+        int range_l = max_l - min_l;
+        for (int k = 0; k < 2; k++) { prm[k].a = 0; prm[k].b = min_c[k]; prm[k].shift = 0; }
+        if (range_l) {
+            int l2 = floor_log2u((unsigned)range_l), norm = ((range_l << 4) >> l2) & 15, v = div_lut[norm] | 8;
+            l2 += norm != 0;
+            for (int k = 0; k < 2; k++) prm[k] = lm_params_c(min_l, min_c[k], max_c[k], v, l2);
+        }
+    }
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            int lm = lm_luma(Y + (ptrdiff_t)(2 * j) * sl + 2 * i, sl, coll, i == 0 && !lft, j == 0 && !abv);
+            for (int k = 0; k < 2; k++)
+                C[k][(ptrdiff_t)j * stride[1 + k] + i] = (uint16_t)clipi(((lm * prm[k].a) >> prm[k].shift) + prm[k].b, 0, maxv);
+        }
+}
+
 /* one block of one plane; chroma: x0 / y0 / log2 sizes in chroma samples */
 static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int mode_in,
                         uint64_t cols, uint64_t rows, int chroma, int ciip_wt, int mrl)
@@ -278,7 +386,10 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
         if (c->flags & OVO_INTRA_LUMA)
             intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, ciip ? 0 : c->mode,
                         c->avail_cols, c->avail_rows, 0, ciip, ciip ? 0 : c->mrl_idx);
-        if ((c->flags & OVO_INTRA_CHROMA) && !(ciip && c->log2_w <= 2))    /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr */
+        if ((c->flags & OVO_INTRA_CHROMA) && !ciip && c->mode_c >= 67)
+            cclm_block(planes, stride, bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1, c->log2_w - 1, c->log2_h - 1,
+                       c->mode_c, c->avail_cols, c->avail_rows, (c->flags & OVO_INTRA_CCLM_COLLOCATED) != 0);
+        else if ((c->flags & OVO_INTRA_CHROMA) && !(ciip && c->log2_w <= 2))    /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr */
             for (int k = 1; k < 3; k++)
                 intra_block(planes[k], stride[k], bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1,
                             c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip, 0);

@@ -87,7 +87,9 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
     c->part_ctx = &part;
     c->rcn_ctx.ctudec = c;
     c->pic_w = pic_w; c->pic_h = pic_h;
-    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 0, bitdepth);
+    int collocated = 0;
+    for (int i = 0; i < nb_cmds; i++) collocated |= (cmds[i].flags & OVO_INTRA_CCLM_COLLOCATED) != 0;
+    rcn_init_functions(&c->rcn_funcs, 0, 1, collocated, 0, bitdepth);
     if (!simd && bitdepth == 10) {      /* scalar C templates = arithmetic of record (rcn.c:98-117, 151-178) */
         extern const struct IntraAngularFunctions angular_gauss_h_10, angular_gauss_v_10, angular_cubic_h_10, angular_cubic_v_10,
                                                   angular_c_h_10, angular_c_v_10, angular_nofrac_v_10, angular_nofrac_h_10;
@@ -101,7 +103,7 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
     }
     uint16_t *inter_pic[3] = { NULL, NULL, NULL };
     for (int i = 0; i < nb_cmds; i++)
-        if ((cmds[i].flags & OVO_INTRA_CIIP) && !inter_pic[0])
+        if (((cmds[i].flags & OVO_INTRA_CIIP) || !cmds[i].flags) && !inter_pic[0])
             for (int k = 0; k < 3; k++) {
                 size_t sz = (size_t)stride[k] * (pic_h >> (k != 0)) * sizeof(uint16_t);
                 inter_pic[k] = malloc(sz);
@@ -132,7 +134,17 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
                 int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
                 m->avail_cols = c->rcn_ctx.progress_field.vfield[x0 >> 2];
                 m->avail_rows = c->rcn_ctx.progress_field.hfield[y0 >> 2];
-                if (m->flags & OVO_INTRA_CIIP) {
+                if (!m->flags) {
+                    /* a CU that is not intra: its reconstruction lands in the CTU buffer now (and replaces whatever the
+                     * vector stores of a narrow left neighbour spilled into it) */
+                    for (int k = 0; k < 3; k++) {
+                        int sh = k != 0, bw = (1 << m->log2_w) >> sh;
+                        for (int y = 0; y < (1 << m->log2_h) >> sh; y++) {
+                            size_t off = (size_t)((m->y0 >> sh) + y) * stride[k] + (m->x0 >> sh);
+                            memcpy(planes[k] + off, inter_pic[k] + off, bw * 2);
+                        }
+                    }
+                } else if (m->flags & OVO_INTRA_CIIP) {
                     ciip_block(c, m, x0, y0, inter_pic, stride);
                 } else {
                 if ((m->flags & OVO_INTRA_LUMA) && m->mrl_idx)       /* rcn_transform_tree.c:1413-1419 */

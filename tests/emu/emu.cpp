@@ -190,12 +190,15 @@ int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int
     std::vector<uint32_t> order(n + 1), level_start(n + 3);
     int nl = intra_build_levels(order.data(), level_start.data(), n + 1, cmds, n, w, h);
     if (nl < 0) return -1000000;
-    for (int l = 0; l < nl; l++) {
-        int start = (int)level_start[l], cnt = (int)level_start[l + 1] - start;
+    int has_chroma = 0, has_cclm = 0;
+    for (int i = 0; i < n; i++)
+        if (cmds[i].flags & OVGPU_INTRA_CHROMA) { has_chroma = 1; has_cclm |= cmds[i].mode_c >= 67; }
+    intra_for_each_launch(nl, level_start.data(), has_chroma, has_cclm, [&](int start, int cnt, int comp0, int ncomp) {
         IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
-                           (const IntraCmdDev *)cmds, order.data() + start, cnt };
-        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, 3, 1), IntraK::SMEM_BYTES);
-    }
+                           (const IntraCmdDev *)cmds, order.data() + start, cnt, comp0 };
+        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, ncomp, 1), IntraK::SMEM_BYTES);
+        return 0;
+    });
     return nl;
 }
 

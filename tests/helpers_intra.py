@@ -6,13 +6,16 @@ import numpy as np
 from openvvc_b200 import synth, synth_intra
 
 
-def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0):
-    """planes + intra commands in decode order with the availability words replayed from that order"""
-    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl), log2_ctu)
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0, collocated=False, p_inter=0.3):
+    """planes + intra commands in decode order with the availability words replayed from that order; commands with
+    flags == 0 are non-intra placeholders (see synth_intra.intra_commands) that emu_intra / gpu_intra drop"""
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm, collocated=collocated, p_inter=p_inter), log2_ctu)
     return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
 
 
-def emu_intra(emu, planes, cmds, log2_ctu=7, bitdepth=10):
+def emu_intra(emu, planes, cmds, log2_ctu=7, bitdepth=10, keep_placeholders=False):
+    if not keep_placeholders:
+        cmds = np.ascontiguousarray(cmds[cmds["flags"] != 0])
     out = [p.copy() for p in planes]
     h, w = out[0].shape
     ptrs = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
@@ -23,6 +26,7 @@ def emu_intra(emu, planes, cmds, log2_ctu=7, bitdepth=10):
 
 
 def gpu_intra(ctx, planes, cmds, log2_ctu=7):
+    cmds = np.ascontiguousarray(cmds[cmds["flags"] != 0])
     from openvvc_b200 import api
     h, w = planes[0].shape
     pic = ctx.picture(w, h)
