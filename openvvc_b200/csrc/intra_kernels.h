@@ -157,7 +157,7 @@ struct IntraK {
     }
 
     // fill_ref_left_0_mref / fill_ref_above_0_mref (rcn_fill_ref.c:228-318, 493-590): raw[0] = the sample m + 1 away both ways,
-    // corner group of m + 1 samples, then 4-sample units; see oracle/port_intra.c for the two left / above differences
+    // corner group of m + 1 samples, then 4-sample units; left and above differ in two places (rcn_fill_ref.c mref variants)
     OVD void fill_ref_mref(uint16_t *raw, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
                            uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int m, int is_left)
     {
