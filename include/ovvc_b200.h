@@ -348,6 +348,17 @@ int  ovgpu_intra_batch_levels(const OVGPUIntraBatch *b);
 /* predicts every block into pic (one launch per dependency level); neighbours are read from pic. Asynchronous. */
 int  ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch *b);
 
+/* ---- Reconstruction order  (replaces the CU loop of the reference: every coding unit is predicted and then gets its
+ *      residual through rcn_transform_tree before the next one is predicted, vcl_coding_unit.c -> rcn_res_wrap,
+ *      rcn_transform_tree.c:1433; intra blocks read neighbours holding prediction + residual) --------------------------
+ * One call per picture: motion compensation of `mc` (may be NULL), the residual of the transform units that lie outside
+ * intra commands, then for every dependency level of `intra` (may be NULL) the intra predictions (CIIP blends) followed
+ * by the residual of the transform units they cover -- with CCLM in the picture, luma (prediction + residual) before
+ * chroma inside a level.  Transform units are matched to intra commands by position.  The result equals predicting and
+ * adding the residual CU by CU in decode order.  Asynchronous. */
+int  ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *refs, const OVGPUMcBatch *mc,
+                         const OVGPULmcs *lmcs, OVGPUTuBatch *tu, const OVGPUIntraBatch *intra);
+
 #ifdef __cplusplus
 }
 #endif

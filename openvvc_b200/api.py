@@ -479,6 +479,19 @@ class IntraBatch:
             self.p = vp()
 
 
+def recon_picture(ctx, pic, tu=None, intra=None, mc=None, ref_lists=None, pocs=None, lmcs=None):
+    """ovgpu_recon_picture: motion compensation, then residual / intra prediction in the reference's CU order"""
+    r = McRefs()
+    if mc is not None:
+        for l in range(2):
+            for i, rp in enumerate(ref_lists[l]):
+                r.rpl[l][i] = rp.p
+                r.poc[l][i] = int(pocs[l][i])
+    _check(ctx.h, lib().ovgpu_recon_picture(ctx.h, pic.p, C.byref(r) if mc is not None else None, mc.p if mc is not None else None,
+                                            lmcs.p if lmcs else None, tu.p if tu is not None else None,
+                                            intra.p if intra is not None else None), "recon_picture")
+
+
 def mc_nb_items(cmds):
     """work items a PU list expands to: <=16x16 blocks of plain commands + one per BDOF / PROF command"""
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))

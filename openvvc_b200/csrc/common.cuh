@@ -73,6 +73,12 @@ struct StageScope {
     ~StageScope();
 };
 
+// internal hooks between the stage files (reconstruction order, intra.cu <-> tr.cu)
+int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint16_t *map_l, const uint16_t *map_c,
+                         int w_u, int h_u, int nb_levels, int split);
+int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group);
+int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b);
+
 #define OVGPU_CEIL_DIV(a, b) (((a) + (b) - 1) / (b))
 
 // Fence on a pinned staging buffer: the host may rewrite the buffer only after the last H2D copy out of it has

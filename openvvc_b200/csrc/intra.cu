@@ -11,6 +11,9 @@ struct OVGPUIntraBatch {
     int max_cmds, nb_cmds, nb_levels, device, pic_w, pic_h, log2_ctu, has_chroma, has_cclm;
     IntraCmdDev *h_cmds, *d_cmds;
     uint32_t *h_order, *d_order, *level_start;      // level_start: host only, max_cmds + 2 entries
+    uint16_t *map_l, *map_c;                        // host only: level of the command covering each 4x4 unit (luma / chroma tree)
+    size_t map_units;
+    uint64_t serial;
     StagingFence fence;
 };
 
@@ -44,6 +47,7 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_order) cudaFree(b->d_order);
     free(b->level_start);
+    free(b->map_l); free(b->map_c);
     fence_destroy(&b->fence);
     free(b);
 }
@@ -58,12 +62,20 @@ int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntra
         if (intra_check_cmd(&cmds[i], pic_w, pic_h)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->nb_levels = 0;
-    if (!nb_cmds) return 0;
+    b->serial++;
+    const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
+    if (units > b->map_units) {
+        free(b->map_l); free(b->map_c);
+        b->map_l = (uint16_t *)malloc(units * sizeof(uint16_t)); b->map_c = (uint16_t *)malloc(units * sizeof(uint16_t));
+        b->map_units = (b->map_l && b->map_c) ? units : 0;
+        if (!b->map_units) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra level maps");
+    }
+    if (!nb_cmds) { memset(b->map_l, 0, units * sizeof(uint16_t)); memset(b->map_c, 0, units * sizeof(uint16_t)); return 0; }
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
     b->has_chroma = b->has_cclm = 0;
     for (int i = 0; i < nb_cmds; i++)
         if (cmds[i].flags & OVGPU_INTRA_CHROMA) { b->has_chroma = 1; b->has_cclm |= cmds[i].mode_c >= 67; }
-    b->nb_levels = intra_build_levels(b->h_order, b->level_start, b->max_cmds, cmds, nb_cmds, pic_w, pic_h);
+    b->nb_levels = intra_build_levels(b->h_order, b->level_start, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->map_l, b->map_c);
     if (b->nb_levels < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_order, b->h_order, sizeof(uint32_t) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
@@ -90,6 +102,35 @@ int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
     });
     OVGPU_CUDA_CHECK(ctx, err);
     return 0;
+}
+
+/* Reconstruction of a picture in the reference's order: prediction of a CU, then its residual (coding_unit() ->
+ * prediction -> rcn_transform_tree, vcl_coding_unit.c / rcn_transform_tree.c:1433), expressed as picture-level passes:
+ * motion compensation, residual of the blocks outside intra CUs, then per dependency level intra prediction + residual. */
+int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *refs, const OVGPUMcBatch *mc,
+                        const OVGPULmcs *lmcs, OVGPUTuBatch *tu, const OVGPUIntraBatch *intra)
+{
+    if (!ctx || !pic || (mc && !refs)) return OVGPU_EINVAL;
+    int rc;
+    if (mc && (rc = ovgpu_mc_picture(ctx, pic, refs, mc, lmcs)) != 0) return rc;
+    if (!intra || !intra->nb_cmds) return tu ? ovgpu_residual_picture(ctx, pic, tu) : 0;
+    if (pic->width != intra->pic_w || pic->height != intra->pic_h)
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
+    const int split = intra->has_cclm ? 2 : 1;
+    if (tu) {
+        if ((rc = ovgpu_tu_check_picture(ctx, pic, tu)) != 0) return rc;
+        if ((rc = ovgpu_tu_bind_levels(ctx, tu, intra->serial, intra->map_l, intra->map_c, pic->width >> 2, pic->height >> 2,
+                                       intra->nb_levels, split)) != 0) return rc;
+    }
+    PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);
+    return recon_for_each_launch(intra->nb_levels, intra->level_start, intra->has_chroma, intra->has_cclm,
+        [&](int start, int n, int comp0, int ncomp) {
+            StageScope scope(ctx, OVGPU_STAGE_INTRA, 1);
+            IntraK::Args a = { { v0.p, v1.p, v2.p }, { v0.pitch, v1.pitch, v2.pitch }, intra->log2_ctu, pic->bitdepth, intra->d_cmds, intra->d_order + start, n, comp0 };
+            cudaError_t err = ovd_launch<IntraK>(a, dim3(OVGPU_CEIL_DIV(n, IntraK::WARPS), ncomp, 1), IntraK::SMEM_BYTES, ctx->stream);
+            return err == cudaSuccess ? 0 : ovgpu_set_error(ctx, OVGPU_ECUDA, "intra launch: %s", cudaGetErrorString(err));
+        },
+        [&](int group) { return tu ? ovgpu_tu_run_group(ctx, pic, tu, group) : 0; });
 }
 
 } // extern "C"

@@ -14,6 +14,9 @@ struct OVGPUTuBatch {
     TbItemDev *h_items, *d_items;       // small items first, then large ones
     int16_t *h_coeffs, *d_coeffs;
     StagingFence fence;
+    // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h
+    TuGroups groups;
+    uint64_t serial, bound_serial, bound_intra_serial;
 };
 
 template <int GROUP>
@@ -28,6 +31,8 @@ static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatc
     a.dep_quant = b->slice.dep_quant; a.sh_ts_disabled = b->slice.sh_ts_disabled; a.ict_type = b->slice.ict_type;
     return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, ctx->stream);
 }
+
+int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group);
 
 extern "C" {
 
@@ -61,6 +66,7 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     if (b->d_items) cudaFree(b->d_items);
     if (b->d_coeffs) cudaFree(b->d_coeffs);
     fence_destroy(&b->fence);
+    tu_groups_free(&b->groups);
     free(b);
 }
 
@@ -83,6 +89,8 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     b->slice = *slice;
     b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
+    b->serial++;
+    tu_groups_free(&b->groups);
     if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
     tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
     tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
@@ -116,6 +124,10 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
         if (c->x0 + (1 << c->log2_w) > pic->width || c->y0 + (1 << c->log2_h) > pic->height)
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
+    if (b->groups.nb_groups) {           // items were re-ordered for ovgpu_recon_picture: same blocks, group by group
+        for (int g = 0; g < b->groups.nb_groups; g++) { int rc = ovgpu_tu_run_group(ctx, pic, b, g); if (rc) return rc; }
+        return 0;
+    }
     const int nk = (b->nb_small > 0) + (b->nb_large > 0);
     if (!nk) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, nk);
@@ -125,3 +137,43 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
 }
 
 } // extern "C"
+
+// ---- internal: residual in reconstruction order (called by ovgpu_recon_picture, intra.cu) ---------------------------
+int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint16_t *map_l, const uint16_t *map_c,
+                         int w_u, int h_u, int nb_levels, int split)
+{
+    if (b->groups.nb_groups && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial) return 0;
+    for (int i = 0; i < b->nb_cmds; i++) {
+        const TuCmdDev *c = &b->h_cmds[i];
+        if ((c->x0 >> 2) >= w_u || (c->y0 >> 2) >= h_u) return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
+    }
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    const int n = tu_build_grouped_items(b->h_items, &b->groups, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, map_l, map_c, w_u, nb_levels, split);
+    if (n < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "TU groups");
+    if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+    b->bound_serial = b->serial; b->bound_intra_serial = intra_serial;
+    return 0;
+}
+
+int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group)
+{
+    if (group < 0 || group >= b->groups.nb_groups) return 0;
+    const int ns = b->groups.n_small[group], nl = b->groups.n_large[group];
+    if (!(ns + nl)) return 0;
+    StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, (ns > 0) + (nl > 0));
+    if (ns) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items + b->groups.start_small[group], ns));
+    if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->groups.start_large[group], nl));
+    return 0;
+}
+
+int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b)
+{
+    if (pic->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "residual path is built for 10-bit pictures");
+    for (int i = 0; i < b->nb_cmds; i++) {
+        const TuCmdDev *c = &b->h_cmds[i];
+        if (c->x0 + (1 << c->log2_w) > pic->width || c->y0 + (1 << c->log2_h) > pic->height)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
+    }
+    return 0;
+}

@@ -1,6 +1,7 @@
 // tr_host.h -- host-side preparation of the residual work lists, shared by tr.cu and tests/emu.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/ovvc_b200.h"
 #include "tr_kernels.h"
 
@@ -46,4 +47,70 @@ static inline void tu_build_items(TbItemDev *small, TbItemDev *large, int *nb_sm
         }
     }
     *nb_small = ns; *nb_large = nl;
+}
+
+// ---- reconstruction order ----------------------------------------------------------------------------------------
+// The reference reconstructs CU by CU: prediction, then rcn_transform_tree (vcl_coding_unit.c -> rcn_res_wrap), so an
+// intra block reads neighbours that already hold prediction + residual.  The picture-level schedule (recon_host.h)
+// keeps that order by dependency LEVEL: transform blocks covered by an intra command run right after that command's
+// level; all others (inter CUs) run first.  `map_l` / `map_c` hold, per 4x4 luma unit, the 1-based level of the intra
+// command covering it (0 = none) for the luma / chroma tree.  With `split` == 2 (pictures using CCLM, whose chroma
+// prediction reads the luma RECONSTRUCTION of the same CU) a level is run luma first, then chroma.
+struct TuGroups {
+    int nb_groups, split;
+    int *start_small, *n_small, *start_large, *n_large;   // per group, offsets into the re-ordered item array
+};
+
+static inline int tu_group_of(const OVGPUTuCmd *c, int kind, const uint16_t *map_l, const uint16_t *map_c, int w_u, int split)
+{
+    const uint16_t *m = kind == 0 ? map_l : map_c;
+    const int lvl = m ? m[(size_t)(c->y0 >> 2) * w_u + (c->x0 >> 2)] : 0;
+    return lvl * split + (split == 2 && kind != 0);
+}
+
+static inline void tu_groups_free(TuGroups *g)
+{
+    free(g->start_small); g->start_small = g->n_small = g->start_large = g->n_large = NULL; g->nb_groups = 0;
+}
+
+// items: room for every transform block of the batch.  Returns the number of items or -1 (out of memory).
+static inline int tu_build_grouped_items(TbItemDev *items, TuGroups *g, const OVGPUTuCmd *cmds, int n,
+                                         const uint16_t *map_l, const uint16_t *map_c, int w_u, int nb_levels, int split)
+{
+    tu_groups_free(g);
+    const int ng = (nb_levels + 1) * split;
+    int *mem = (int *)calloc((size_t)4 * ng, sizeof(int));
+    if (!mem) return -1;
+    g->nb_groups = ng; g->split = split;
+    g->start_small = mem; g->n_small = mem + ng; g->start_large = mem + 2 * ng; g->n_large = mem + 3 * ng;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int i = 0; i < n; i++) {
+            const OVGPUTuCmd *c = &cmds[i];
+            int kinds[3], nk = 0;
+            if (c->cbf_mask & 0x10) kinds[nk++] = 0;
+            if (c->cbf_mask & 0x08) kinds[nk++] = 3;
+            else {
+                if (c->cbf_mask & 0x02) kinds[nk++] = 1;
+                if (c->cbf_mask & 0x01) kinds[nk++] = 2;
+            }
+            for (int k = 0; k < nk; k++) {
+                const int s = c->log2_w + c->log2_h - (kinds[k] ? 2 : 0);
+                const int grp = tu_group_of(c, kinds[k], map_l, map_c, w_u, split);
+                if (pass == 0) { if (s <= 8) g->n_small[grp]++; else g->n_large[grp]++; }
+                else {
+                    TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };
+                    if (s <= 8) items[g->start_small[grp] + g->n_small[grp]++] = it;
+                    else        items[g->start_large[grp] + g->n_large[grp]++] = it;
+                }
+            }
+        }
+        if (pass == 0) {
+            int acc = 0;
+            for (int q = 0; q < ng; q++) {
+                g->start_small[q] = acc; acc += g->n_small[q]; g->n_small[q] = 0;
+                g->start_large[q] = acc; acc += g->n_large[q]; g->n_large[q] = 0;
+            }
+        }
+    }
+    return ng ? g->start_large[ng - 1] + g->n_large[ng - 1] : 0;
 }

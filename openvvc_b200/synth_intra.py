@@ -14,13 +14,13 @@ INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED = 1, 2, 4, 8
 
 
 def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0,
-                   collocated=False, p_inter=0.0):
+                   collocated=False, p_inter=0.0, blocks=None):
     """p_inter: fraction of coding units that are NOT intra (flags = 0 placeholders): they keep the picture's samples -- the
     already reconstructed inter CUs of a real picture -- and only take part in the availability replay.  Without them an
     all-intra picture without residual degenerates to the mid value everywhere.  The placeholders are for the oracle
     harness (which has to mark them in the reference's progress field); drop them before handing commands to the GPU."""
     rng = np.random.default_rng(seed)
-    part = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
+    part = blocks if blocks is not None else synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
     for i, (x, y, lw, lh) in enumerate(part):
         c = cmds[i]

@@ -102,10 +102,13 @@ def _cmax(qp, lw, lh, dep_quant, legal):
     return max(1, int(32000 / gain))
 
 
-def tu_commands(w, h, seed=1005, log2_ctu=7, ict_type=0, sh_ts_disabled=0, min_log2=2, p_cbf=0.6, dep_quant=1, legal=False, p_intra=0.0):
-    """Returns (cmds[TU_CMD], arena int16). One TU per partition block (<= 64x64 luma)."""
+def tu_commands(w, h, seed=1005, log2_ctu=7, ict_type=0, sh_ts_disabled=0, min_log2=2, p_cbf=0.6, dep_quant=1, legal=False, p_intra=0.0,
+                blocks=None, intra_mask=None):
+    """Returns (cmds[TU_CMD], arena int16). One TU per partition block (<= 64x64 luma).
+    blocks / intra_mask: use this partition (and these intra CUs) instead of drawing them (synth_recon)."""
     rng = np.random.default_rng(seed)
-    blocks = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(6, log2_ctu))
+    if blocks is None:
+        blocks = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(6, log2_ctu))
     cmds = np.zeros(len(blocks), dtype=TU_CMD)
     arena = []
     off = 0
@@ -128,6 +131,8 @@ def tu_commands(w, h, seed=1005, log2_ctu=7, ict_type=0, sh_ts_disabled=0, min_l
         # intra CUs (LFNST idx on intra): implicit MTS / LFNST on luma (rcn_tu_st), or a dual-tree
         # chroma TU with LFNST (rcn_tu_c)
         intra = rng.random() < p_intra
+        if intra_mask is not None:
+            intra = bool(intra_mask[i])
         dual_c = intra and lw >= 3 and lh >= 3 and rng.random() < 0.3
         lfnst_l = lfnst_c = False
         if intra:

@@ -241,6 +241,11 @@ typedef struct OVOIntraCmd {
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, int nb_cmds);
 
+/* ---- Reconstruction in CU order (port_recon.c): prediction, then residual, coding unit by coding unit -------- */
+void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                       const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
+                       int dep_quant, int sh_ts_disabled, int ict_type);
+
 #ifdef __cplusplus
 }
 #endif

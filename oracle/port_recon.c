@@ -1,0 +1,41 @@
+/* port_recon.c -- TEST INFRASTRUCTURE ONLY (oracle; never linked into the product).
+ *
+ * Reconstruction of a picture in the reference's CU order: for every coding unit, in decode order, the prediction and
+ * then the residual, exactly as coding_unit() drives it -- intra CU in a single tree: rcn_intra_tu (luma prediction,
+ * libovvc/rcn_transform_tree.c:1392-1431), then rcn_tu_st (:1228-1300): luma residual, chroma prediction (intra_pred_c,
+ * after the luma residual so that CCLM reads reconstructed luma), chroma residual.  CIIP: rcn_ciip blends both
+ * components (libovvc/rcn_inter.c:3012-3067) before the transform tree.  Inter CUs: their prediction is already in the
+ * picture (motion compensation); only the residual is added.
+ * Built from the two pinned pieces ovo_intra_picture / ovo_residual_picture, one command at a time. */
+#include <string.h>
+#include "oracle.h"
+
+/* cmds[i] and tus[i] describe the same coding unit (intra flags == 0: not intra; cbf_mask == 0: no residual) */
+void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                       const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
+                       int dep_quant, int sh_ts_disabled, int ict_type)
+{
+    for (int i = 0; i < nb_cu; i++) {
+        OVOIntraCmd c = cmds[i];
+        OVOTuCmd t = tus[i], tl = t, tc = t;
+        tl.cbf_mask = t.cbf_mask & 0x10;
+        tc.cbf_mask = t.cbf_mask & 0x0f;
+        if (c.flags & OVO_INTRA_CIIP) {
+            ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, &c, 1);
+            if (t.cbf_mask) ovo_residual_picture(planes, stride, pic_w, pic_h, bitdepth, &t, 1, arena, dep_quant, sh_ts_disabled, ict_type);
+            continue;
+        }
+        if (c.flags & OVO_INTRA_LUMA) {
+            OVOIntraCmd l = c;
+            l.flags &= ~OVO_INTRA_CHROMA;
+            ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, &l, 1);
+        }
+        if (tl.cbf_mask) ovo_residual_picture(planes, stride, pic_w, pic_h, bitdepth, &tl, 1, arena, dep_quant, sh_ts_disabled, ict_type);
+        if (c.flags & OVO_INTRA_CHROMA) {
+            OVOIntraCmd k = c;
+            k.flags &= ~OVO_INTRA_LUMA;
+            ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, &k, 1);
+        }
+        if (tc.cbf_mask) ovo_residual_picture(planes, stride, pic_w, pic_h, bitdepth, &tc, 1, arena, dep_quant, sh_ts_disabled, ict_type);
+    }
+}

@@ -202,4 +202,40 @@ int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int
     return nl;
 }
 
+// ovgpu_recon_picture's schedule (intra_host.h: recon_for_each_launch; tr_host.h: tu_build_grouped_items) on the emulated kernels
+int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth,
+                      const OVGPUIntraCmd *cmds, int n, const OVGPUTuCmd *tus, int nb_tus, const int16_t *arena, size_t nb_coeffs,
+                      int dep_quant, int sh_ts_disabled, int ict_type)
+{
+    for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
+    for (int i = 0; i < nb_tus; i++) if (tu_check_cmd(&tus[i], nb_coeffs)) return -(100000 + i);
+    const int w_u = w >> 2, h_u = h >> 2;
+    std::vector<uint32_t> order(n + 1), level_start(n + 3);
+    std::vector<uint16_t> map_l((size_t)w_u * h_u), map_c((size_t)w_u * h_u);
+    int nl = intra_build_levels(order.data(), level_start.data(), n + 1, cmds, n, w, h, map_l.data(), map_c.data());
+    if (nl < 0) return -1000000;
+    int has_chroma = 0, has_cclm = 0;
+    for (int i = 0; i < n; i++)
+        if (cmds[i].flags & OVGPU_INTRA_CHROMA) { has_chroma = 1; has_cclm |= cmds[i].mode_c >= 67; }
+    std::vector<TbItemDev> items(3 * (size_t)nb_tus + 1);
+    TuGroups g;
+    memset(&g, 0, sizeof(g));
+    if (tu_build_grouped_items(items.data(), &g, tus, nb_tus, map_l.data(), map_c.data(), w_u, nl, has_cclm ? 2 : 1) < 0) return -1000001;
+    OVGPUTuSlice sl = { (uint8_t)dep_quant, (uint8_t)sh_ts_disabled, (uint8_t)ict_type, 0 };
+    recon_for_each_launch(nl, level_start.data(), has_chroma, has_cclm,
+        [&](int start, int cnt, int comp0, int ncomp) {
+            IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
+                               (const IntraCmdDev *)cmds, order.data() + start, cnt, comp0 };
+            ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, ncomp, 1), IntraK::SMEM_BYTES);
+            return 0;
+        },
+        [&](int grp) {
+            if (g.n_small[grp]) emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + g.start_small[grp], g.n_small[grp], arena, &sl);
+            if (g.n_large[grp]) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + g.start_large[grp], g.n_large[grp], arena, &sl);
+            return 0;
+        });
+    tu_groups_free(&g);
+    return nl;
+}
+
 }
