@@ -311,8 +311,7 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
 
 /* ---- Intra prediction  (replaces the intra_pred slot: vvc_intra_pred, rcn_intra.c:484-560, and the intra_pred_c slot:
  *      vvc_intra_pred_chroma, rcn_intra.c:1015-1182, planar / DC / angular modes) -------------------------------------- */
-/* One intra coding unit: a luma block and / or its 4:2:0 Cb + Cr blocks of half the size (no ISP / MRL / MIP / BDPCM /
- * CCLM in this revision).  avail_cols / avail_rows are the two words the
+/* One intra coding unit: a luma block and / or its 4:2:0 Cb + Cr blocks of half the size (no ISP / BDPCM in this revision).  avail_cols / avail_rows are the two words the
  * reference reads from its progress bit-field at call time: rcn_ctx.progress_field.vfield[x0 >> 2] and .hfield[y0 >> 2]
  * (CTU-local x0 / y0; bit 0 = the unit in the neighbouring CTU line, bit 1 + u = 4x4 unit u, rcn_structures.h:81-85).
  * In a single tree progress_field_c holds the same words (rcn_tu_st marks both with the same rectangles), so the chroma
@@ -324,6 +323,9 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
                                 * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
                                 * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
 #define OVGPU_INTRA_CCLM_COLLOCATED 8   /* flags: sps_chroma_vertical_collocated_flag (5-tap cross luma down-sampling for CCLM) */
+#define OVGPU_INTRA_MIP    16   /* flags: matrix-based intra prediction of the luma block (mip.rcn_intra_mip slot, rcn_intra_mip.c:386-403;
+                                * called from rcn_intra_tu, rcn_transform_tree.c:1403-1406); `mode` = ctudec->cu_opaque: bit 7 = transposed,
+                                * bits 0-5 = matrix index (< 16 for 4x4, < 8 for the 8x8 class, < 6 otherwise); no MRL / CIIP */
 typedef struct OVGPUIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */

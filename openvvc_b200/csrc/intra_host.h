@@ -9,8 +9,13 @@
 static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 {
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~15)) return -1;
-    if (((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) || ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 69)) return -1;
+    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~31)) return -1;
+    if (c->flags & OVGPU_INTRA_MIP) {
+        const int small = c->log2_w == 2 && c->log2_h == 2, red = c->log2_w == 2 || c->log2_h == 2 || (c->log2_w <= 3 && c->log2_h <= 3);
+        if (!(c->flags & OVGPU_INTRA_LUMA) || (c->flags & OVGPU_INTRA_CIIP) || c->mrl_idx || (c->mode & 0x40) ||
+            (c->mode & 0x3f) >= (small ? 16 : (red ? 8 : 6))) return -1;
+    } else if ((c->flags & OVGPU_INTRA_LUMA) && c->mode > 66) return -1;
+    if ( ((c->flags & OVGPU_INTRA_CHROMA) && c->mode_c > 69)) return -1;
     if ((c->flags & OVGPU_INTRA_CIIP) && (c->ciip_wt < 1 || c->ciip_wt > 3)) return -1;
     if (c->mrl_idx > 2 || (c->mrl_idx && (c->y0 < 4 || c->x0 + (1 << c->log2_w) > pic_w))) return -1;
     if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;

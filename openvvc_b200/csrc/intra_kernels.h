@@ -18,8 +18,13 @@
 // two reference arrays in shared memory, phase 1 their filtered copies, phase 2 the negative-index extension, phase 3
 // predicts -- each lane computes samples straight from the arrays with closed-form per-sample expressions (the
 // horizontal class is the vertical class on swapped roles), so there is no transposition pass.
+//
+// MIP (rcn_intra_mip, libovvc/rcn_intra_mip.c:135-403): same reference fill; phase 1 averages the boundary to 2 / 4 samples
+// per side, phase 2 does the matrix product (one lane per reduced sample, weights from mip_tables.h), phase 3 evaluates
+// the two linear up-sampling passes in closed form per output sample.
 #pragma once
 #include "dev.h"
+#include "mip_tables.h"
 
 struct IntraCmdDev {          // == OVGPUIntraCmd
     int16_t x0, y0;
@@ -61,6 +66,7 @@ struct IntraK {
 
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
+        int mip, mip_tr, mip_idx;                    // matrix-based prediction: transposed variant, matrix index
         int valid, chroma, pd, ciip, mrl, cclm, coll;  // cclm: 0 or the chroma mode 67 (LM) / 68 (MDLM left) / 69 (MDLM top)                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
         int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
@@ -87,6 +93,9 @@ struct IntraK {
         b.mrl = (b.chroma || b.ciip) ? 0 : c.mrl_idx;
         b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : !b.mrl;
         int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
+        b.mip = !b.chroma && (c.flags & 16);
+        b.mip_tr = (c.mode >> 7) & 1; b.mip_idx = c.mode & 0x3f;
+        if (b.mip) mode = 1;                           // the phases below branch on b.mip first; DC keeps the derivation trivial
         b.cclm = mode >= 67 ? mode : 0;
         b.coll = (c.flags & 8) != 0;
         if (b.cclm) mode = 0;
@@ -330,6 +339,66 @@ struct IntraK {
                     const int lm = lm_luma(Y + (ptrdiff_t)(2 * y) * a.pitch[0] + 2 * x, a.pitch[0], b.coll, x == 0 && !lft, y == 0 && !abv);
                     dst[(size_t)y * pitch + x] = (uint16_t)ovd_clamp(((lm * ac) >> shift) + bc, 0, maxv);
                 }
+            }
+            return;
+        }
+
+        if (b.mip && P > 0) {
+            // vvc_intra_pred_mip(_tr): nb boundary samples per side, reduced block red x red
+            const int nb = (b.lw > 2 || b.lh > 2) ? 4 : 2, log2_nb = nb == 4 ? 2 : 1;
+            const int red_size = b.lh == 2 || b.lw == 2 || (b.lh <= 3 && b.lw <= 3), log2_red = red_size ? 2 : 3, red = 1 << log2_red;
+            int *in_raw = (int *)(base + 2 * REF_LEN);
+            uint16_t *pred = base + 3 * REF_LEN;
+            if (P == 1) {
+                if (lane < 2 * nb) {                                        // rcn_intra_mip.c:165-183 / :283-300
+                    const int j = lane & (nb - 1), is_abv = (lane < nb) != b.mip_tr;
+                    const int lb = (is_abv ? b.lw : b.lh) - log2_nb;
+                    const uint16_t *r = (is_abv ? abv : lft) + 1 + (j << lb);
+                    int sum = 0;
+                    for (int i = 0; i < (1 << lb); i++) sum += r[i];
+                    in_raw[lane] = (sum + ((1 << lb) >> 1)) >> lb;
+                }
+                return;
+            }
+            if (P == 2) {
+                int in[8], sum = 0;
+                const int input_offset = in_raw[0];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    int v = i < 2 * nb ? in_raw[i] : input_offset;
+                    if (i == 0 && red_size) v = 1 << (a.bitdepth - 1);     // :187-189
+                    in[i] = (int16_t)(v - input_offset);
+                    sum += in[i];
+                }
+                const int rnd = 32 - 32 * sum;                              // MIP_OFFSET - MIP_OFFSET * sum
+                const uint8_t *mt = (b.lw == 2 && b.lh == 2) ? &mip_w_4x4[b.mip_idx * 64] : (red_size ? &mip_w_8x8[b.mip_idx * 128] : &mip_w_16x16[b.mip_idx * 512]);
+                for (int pos = lane; pos < red * red; pos += 32) {
+                    const uint8_t *m = mt + pos * 2 * nb;
+                    int v = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) if (i < 2 * nb) v += in[i] * m[i];
+                    // the transposed variant reads the product as pred[j * red + i] (:337-341, :377-381): store it transposed
+                    const int q = b.mip_tr ? ((pos & (red - 1)) << log2_red) + (pos >> log2_red) : pos;
+                    pred[q] = (uint16_t)ovd_clamp(((v + rnd) >> 6) + input_offset, 0, maxv);
+                }
+                return;
+            }
+            // up_sample (:93-131) horizontally on the rows holding the reduced lines, then vertically, per output sample
+            const int lsx = b.lw - log2_red, lsy = b.lh - log2_red, sx = 1 << lsx, sy = 1 << lsy;
+            for (int o = lane; o < w * h; o += 32) {
+                const int x = o & (w - 1), y = o >> b.lw;
+                const int jx = x >> lsx, px = (x & (sx - 1)) + 1, jy = y >> lsy, py = (y & (sy - 1)) + 1;
+                // H(i): value of reduced row i at column x
+                int hv[2];
+#pragma unroll
+                for (int t = 0; t < 2; t++) {
+                    const int i = jy - 1 + t;
+                    if (i < 0) { hv[t] = abv[1 + x]; continue; }
+                    const int after = pred[(i << log2_red) + jx];
+                    const int before = jx ? pred[(i << log2_red) + jx - 1] : lft[(i + 1) * sy];
+                    hv[t] = lsx ? (before * (sx - px) + after * px + (sx >> 1)) >> lsx : after;
+                }
+                dst[(size_t)y * pitch + x] = (uint16_t)(lsy ? (hv[0] * (sy - py) + hv[1] * py + (sy >> 1)) >> lsy : hv[1]);
             }
             return;
         }

@@ -10,11 +10,11 @@ INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), 
                       ("avail_cols", np.uint64), ("avail_rows", np.uint64)])
 assert INTRA_CMD.itemsize == 32
 
-INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED = 1, 2, 4, 8
+INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED, INTRA_MIP = 1, 2, 4, 8, 16
 
 
 def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0,
-                   collocated=False, p_inter=0.0, blocks=None):
+                   collocated=False, p_inter=0.0, blocks=None, p_mip=0.0):
     """p_inter: fraction of coding units that are NOT intra (flags = 0 placeholders): they keep the picture's samples -- the
     already reconstructed inter CUs of a real picture -- and only take part in the availability replay.  Without them an
     all-intra picture without residual degenerates to the mid value everywhere.  The placeholders are for the oracle
@@ -45,6 +45,11 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
             c["ciip_wt"] = int(rng.integers(1, 4))
         if p_mrl and (y & ((1 << log2_ctu) - 1)) and not (c["flags"] & INTRA_CIIP) and rng.random() < p_mrl:
             c["mrl_idx"] = int(rng.integers(1, 3))                 # not on the first row of a CTU (vcl_coding_unit.c:1377)
+        if p_mip and not (c["flags"] & INTRA_CIIP) and not c["mrl_idx"] and rng.random() < p_mip:
+            # MIP (10 % of intra CUs): `mode` carries cu_opaque = transposed << 7 | matrix index
+            nm = 16 if (lw == 2 and lh == 2) else (8 if (lw == 2 or lh == 2 or (lw <= 3 and lh <= 3)) else 6)
+            c["flags"] |= INTRA_MIP
+            c["mode"] = (int(rng.integers(0, 2)) << 7) | int(rng.integers(0, nm))
     return cmds
 
 

@@ -225,6 +225,8 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
                                 * picture, (wt * intra + (4 - wt) * inter + 2) >> 2 (rcn_ciip_weighted_sum, rcn_inter.c:2968-3010;
                                 * put_weighted_ciip_pixels, rcn_mc.c:1611-1627); chroma keeps the inter prediction when log2_w <= 2 */
 #define OVO_INTRA_CCLM_COLLOCATED 8   /* flags: sps_chroma_vertical_collocated_flag (5-tap cross luma down-sampling for CCLM) */
+#define OVO_INTRA_MIP    16   /* flags: matrix-based intra prediction of the luma block; `mode` = ctudec->cu_opaque: bit 7 transposed,
+                                * bits 0-5 the matrix index (rcn_intra_mip, rcn_intra_mip.c:386-403) */
 typedef struct OVOIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */

@@ -8,6 +8,7 @@
  * swapped, which is how it is written here.
  */
 #include "oracle.h"
+#include "mip_tables.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -375,6 +376,68 @@ static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y
     free(out);
 }
 
+/* Matrix-based intra prediction: rcn_intra_mip -> vvc_intra_pred_mip(_tr) (libovvc/rcn_intra_mip.c:135-384): boundary
+ * averaging to 2 / 4 samples per side (:165-183; the transposed variant puts the left boundary first, :283-300), offset
+ * removal and the 4x4-class replacement of the first input by the mid value (:185-195), matrix product with the folded
+ * rounding term 32 - 32 * sum (mip_matmult, :63-91), transposition of the reduced block for the _tr variant (:337-341),
+ * then linear up-sampling, horizontally on the rows that hold the reduced lines and vertically over everything
+ * (up_sample, :93-131), the first neighbour being the left / above reference sample. */
+static void mip_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int opaque,
+                      uint64_t cols, uint64_t rows)
+{
+    int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1;
+    uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
+    uint16_t *dst = plane + (size_t)y0 * stride + x0;
+    const uint16_t *corner = dst - stride - 1;
+    fill_ref(lft, corner, stride, 1, lh, lw, cols, rows, yl, xl, bitdepth, 2, 0);
+    fill_ref(abv, corner, 1, stride, lw, lh, rows, cols, xl, yl, bitdepth, 2, 0);
+    int transpose = (opaque >> 7) & 1, mode = opaque & 0x3f;
+    int nb = (lw > 2 || lh > 2) ? 4 : 2, log2_nb = nb == 4 ? 2 : 1;
+    int red_size = lh == 2 || lw == 2 || (lh <= 3 && lw <= 3), red = red_size ? 4 : 8, log2_red = red_size ? 2 : 3;
+    int a_red[4], l_red[4], in[8];
+    for (int j = 0; j < nb; j++) {
+        int sa = 0, sl = 0, lbx = lw - log2_nb, lby = lh - log2_nb;
+        for (int i = 0; i < (1 << lbx); i++) sa += abv[1 + i + (j << lbx)];
+        for (int i = 0; i < (1 << lby); i++) sl += lft[1 + i + (j << lby)];
+        a_red[j] = (sa + ((1 << lbx) >> 1)) >> lbx;
+        l_red[j] = (sl + ((1 << lby) >> 1)) >> lby;
+    }
+    for (int j = 0; j < nb; j++) { in[j] = transpose ? l_red[j] : a_red[j]; in[nb + j] = transpose ? a_red[j] : l_red[j]; }
+    int input_offset = in[0], sum = 0;
+    if (red_size) in[0] = 1 << (bitdepth - 1);
+    for (int i = 0; i < 2 * nb; i++) { in[i] = (int16_t)(in[i] - input_offset); sum += in[i]; }
+    int rnd = 32 - 32 * sum;
+    const uint8_t *m = (lw == 2 && lh == 2) ? &mip_w_4x4[mode * 16 * 4] : (red_size ? &mip_w_8x8[mode * 16 * 8] : &mip_w_16x16[mode * 64 * 8]);
+    int pred[64], P[64];
+    for (int pos = 0; pos < red * red; pos++) {
+        int v = 0;
+        for (int i = 0; i < 2 * nb; i++) v += in[i] * m[pos * 2 * nb + i];
+        pred[pos] = clipi(((v + rnd) >> 6) + input_offset, 0, maxv);
+    }
+    for (int i = 0; i < red; i++) for (int j = 0; j < red; j++) P[i * red + j] = transpose ? pred[j * red + i] : pred[i * red + j];
+    int lsx = lw - log2_red, lsy = lh - log2_red, sx = 1 << lsx, sy = 1 << lsy;
+    int *H = malloc(sizeof(int) * red * w);                       /* reduced rows after the horizontal pass */
+    for (int i = 0; i < red; i++) {
+        int before = lft[1 + (i + 1) * sy - 1];
+        for (int j = 0; j < red; j++) {
+            int after = P[i * red + j];
+            for (int pos = 1; pos <= sx; pos++)
+                H[i * w + j * sx + pos - 1] = lsx ? (before * (sx - pos) + after * pos + (sx >> 1)) >> lsx : after;
+            before = after;
+        }
+    }
+    for (int x = 0; x < w; x++) {
+        int before = abv[1 + x];
+        for (int j = 0; j < red; j++) {
+            int after = H[j * w + x];
+            for (int pos = 1; pos <= sy; pos++)
+                dst[(size_t)(j * sy + pos - 1) * stride + x] = (uint16_t)(lsy ? (before * (sy - pos) + after * pos + (sy >> 1)) >> lsy : after);
+            before = after;
+        }
+    }
+    free(H);
+}
+
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, int nb_cmds)
 {
@@ -383,7 +446,9 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
     for (int i = 0; i < nb_cmds; i++) {
         const OVOIntraCmd *c = &cmds[i];
         int ciip = (c->flags & OVO_INTRA_CIIP) ? c->ciip_wt : 0;
-        if (c->flags & OVO_INTRA_LUMA)
+        if ((c->flags & OVO_INTRA_LUMA) && (c->flags & OVO_INTRA_MIP))
+            mip_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, c->mode, c->avail_cols, c->avail_rows);
+        else if (c->flags & OVO_INTRA_LUMA)
             intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, ciip ? 0 : c->mode,
                         c->avail_cols, c->avail_rows, 0, ciip, ciip ? 0 : c->mrl_idx);
         if ((c->flags & OVO_INTRA_CHROMA) && !ciip && c->mode_c >= 67)

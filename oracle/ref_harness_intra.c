@@ -28,6 +28,7 @@ void rcn_init_intra_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_dc_planar_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_intra_angular_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_fill_ref_10(struct RCNFunctions *rcn_func);
+void rcn_init_mip_functions_10(struct RCNFunctions *rcn_func);
 
 /* rcn_ciip / rcn_ciip_b (rcn_inter.c:3012-3067) from the point where the inter prediction exists: the block's current
  * content plays tmp_inter (the MC stage wrote it), the reference's own slots do the rest -- intra_pred / intra_pred_c
@@ -96,6 +97,7 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
         rcn_init_intra_functions_10(&c->rcn_funcs);
         rcn_init_dc_planar_functions_10(&c->rcn_funcs);
         rcn_init_fill_ref_10(&c->rcn_funcs);
+        rcn_init_mip_functions_10(&c->rcn_funcs);
         c->rcn_funcs.intra_angular_gauss_h = &angular_gauss_h_10; c->rcn_funcs.intra_angular_gauss_v = &angular_gauss_v_10;
         c->rcn_funcs.intra_angular_cubic_h = &angular_cubic_h_10; c->rcn_funcs.intra_angular_cubic_v = &angular_cubic_v_10;
         c->rcn_funcs.intra_angular_c_h = &angular_c_h_10; c->rcn_funcs.intra_angular_c_v = &angular_c_v_10;
@@ -147,7 +149,9 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
                 } else if (m->flags & OVO_INTRA_CIIP) {
                     ciip_block(c, m, x0, y0, inter_pic, stride);
                 } else {
-                if ((m->flags & OVO_INTRA_LUMA) && m->mrl_idx)       /* rcn_transform_tree.c:1413-1419 */
+                if ((m->flags & OVO_INTRA_LUMA) && (m->flags & OVO_INTRA_MIP))       /* rcn_intra_tu, rcn_transform_tree.c:1403-1406 */
+                    c->rcn_funcs.mip.rcn_intra_mip(&c->rcn_ctx, x0, y0, m->log2_w, m->log2_h, m->mode);
+                else if ((m->flags & OVO_INTRA_LUMA) && m->mrl_idx)       /* rcn_transform_tree.c:1413-1419 */
                     c->rcn_funcs.intra_pred_mrl(c, c->rcn_ctx.ctu_buff.y, c->rcn_ctx.ctu_buff.stride, m->mode, x0, y0, m->log2_w, m->log2_h, m->mrl_idx);
                 else if (m->flags & OVO_INTRA_LUMA)
                     c->rcn_funcs.intra_pred(&c->rcn_ctx, &c->rcn_ctx.ctu_buff, m->mode, x0, y0, m->log2_w, m->log2_h, flg_pred_mode_flag);

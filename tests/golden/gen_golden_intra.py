@@ -21,7 +21,9 @@ CASES = [(128, 128, 901, 7, 0), (416, 240, 902, 7, 0), (832, 480, 903, 7, 0), (2
          # + multi reference line blocks (chroma = 3)
          (416, 240, 932, 7, 3), (264, 136, 934, 6, 3),
          # + CCLM / MDLM chroma (4: 6-tap luma down-sampling, 5: vertically collocated chroma)
-         (416, 240, 942, 7, 4), (832, 480, 943, 7, 4), (200, 120, 945, 5, 4), (416, 240, 952, 7, 5), (264, 136, 954, 6, 5)]
+         (416, 240, 942, 7, 4), (832, 480, 943, 7, 4), (200, 120, 945, 5, 4), (416, 240, 952, 7, 5), (264, 136, 954, 6, 5),
+         # + MIP luma blocks (chroma = 6)
+         (416, 240, 962, 7, 6), (832, 480, 963, 7, 6), (200, 120, 965, 5, 6)]
 
 
 def main():
@@ -29,8 +31,8 @@ def main():
     out = []
     for (w, h, seed, log2, chroma) in CASES:
         planes, cmds = helpers_intra.intra_case(w, h, seed, log2, chroma=bool(chroma), p_ciip=0.4 if chroma in (2, 3) else 0.0,
-                                                p_mrl=0.4 if chroma == 3 else 0.0, p_cclm=0.4 if chroma >= 4 else 0.0,
-                                                collocated=chroma == 5)
+                                                p_mrl=0.4 if chroma == 3 else 0.0, p_cclm=0.4 if chroma in (4, 5) else 0.0,
+                                                collocated=chroma == 5, p_mip=0.4 if chroma == 6 else 0.0)
         inp = helpers.md5(cmds, planes[0])
         rc = cmds.copy()
         rc["avail_cols"] = 0; rc["avail_rows"] = 0

@@ -6,10 +6,10 @@ import numpy as np
 from openvvc_b200 import synth, synth_intra
 
 
-def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0, collocated=False, p_inter=0.3):
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0, collocated=False, p_inter=0.3, p_mip=0.0):
     """planes + intra commands in decode order with the availability words replayed from that order; commands with
     flags == 0 are non-intra placeholders (see synth_intra.intra_commands) that emu_intra / gpu_intra drop"""
-    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm, collocated=collocated, p_inter=p_inter), log2_ctu)
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm, collocated=collocated, p_inter=p_inter, p_mip=p_mip), log2_ctu)
     return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
 
 

@@ -11,7 +11,7 @@ import helpers
 import helpers_intra
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "intra_golden.json")))
-IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], ("", "_yuv", "_yuv_ciip", "_yuv_ciip_mrl", "_yuv_cclm", "_yuv_cclm_collocated")[c["chroma"]])
+IDS = lambda c: "%dx%d_ctu%d%s" % (c["w"], c["h"], 1 << c["log2_ctu"], ("", "_yuv", "_yuv_ciip", "_yuv_ciip_mrl", "_yuv_cclm", "_yuv_cclm_collocated", "_yuv_mip")[c["chroma"]])
 
 
 @pytest.fixture(scope="module")
@@ -23,7 +23,8 @@ def pi(oracle):
 def _case(c):
     planes, cmds = helpers_intra.intra_case(c["w"], c["h"], c["seed"], c["log2_ctu"], chroma=bool(c["chroma"]),
                                             p_ciip=0.4 if c["chroma"] in (2, 3) else 0.0, p_mrl=0.4 if c["chroma"] == 3 else 0.0,
-                                            p_cclm=0.4 if c["chroma"] >= 4 else 0.0, collocated=c["chroma"] == 5)
+                                            p_cclm=0.4 if c["chroma"] in (4, 5) else 0.0, collocated=c["chroma"] == 5,
+                                            p_mip=0.4 if c["chroma"] == 6 else 0.0)
     assert helpers.md5(cmds, planes[0]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
     return planes, cmds
 
@@ -147,6 +148,32 @@ def test_cclm_port_vs_reference_and_emu(oracle, pi, emu, w, h, log2, collocated)
         finally:
             emu.emu_set_reverse_block_order(0)
         assert all((got[k] == want[k]).all() for k in range(3))
+
+
+@pytest.mark.parametrize("w,h,log2", [(416, 240, 7), (832, 480, 7), (264, 136, 6), (200, 120, 5)])
+def test_mip_port_vs_reference_and_emu(oracle, pi, emu, w, h, log2):
+    """MIP (a21): the three matrix classes, plain and transposed, every up-sampling ratio incl. none (4x4, 8x8) and one-sided"""
+    planes, cmds = helpers_intra.intra_case(w, h, 11 * w + h, log2, chroma=True, p_mip=0.5)
+    mip = (cmds["flags"] & 16) != 0
+    shapes = set(zip(cmds["log2_w"][mip], cmds["log2_h"][mip]))
+    assert mip.sum() > 30 and (2, 2) in shapes and len(shapes) >= 12 and set(cmds["mode"][mip] >> 7) == {0, 1}
+    assert (3, 3) in shapes or w == 416
+    want = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
+    if oracle.ref_available():
+        for simd in (0, 1):
+            got = pi.intra_picture([p.copy() for p in planes], cmds.copy(), log2, impl="ref", simd=simd)
+            assert all((got[k] == want[k]).all() for k in range(3)), "MIP port vs reference (simd=%d)" % simd
+    for rev in (0, 1):
+        emu.emu_set_reverse_block_order(rev)
+        try:
+            got, _ = helpers_intra.emu_intra(emu, planes, cmds, log2)
+        finally:
+            emu.emu_set_reverse_block_order(0)
+        assert all((got[k] == want[k]).all() for k in range(3))
+    bad = np.ascontiguousarray(cmds[mip][:1]).copy()
+    bad["mode"] = 0x80 | 16                                                       # matrix index beyond the class
+    with pytest.raises(AssertionError):
+        helpers_intra.emu_intra(emu, planes, bad, log2)
 
 
 def test_emu_rejects_blocks_outside_the_picture(emu):
