@@ -158,6 +158,8 @@ typedef struct OVGPULmcs OVGPULmcs;   /* device copy of the LUTs of one slice */
 int  ovgpu_lmcs_create(OVGPUCtx *ctx, OVGPULmcs **l);
 void ovgpu_lmcs_destroy(OVGPULmcs *l);
 int  ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts);
+/* the slice's LMCS syntax: window range and chroma scaling offset for the on-device chroma scale derivation */
+int  ovgpu_lmcs_set_data(OVGPULmcs *l, const OVGPULmcsData *data);
 /* luma plane of pic <- bwd_lut[luma] (forward != 0: fwd_lut); the reference does this per CTU after
  * rcn_write_ctu_to_frame (slicedec.c:745-750). In place. */
 int  ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *l, int forward);
@@ -225,6 +227,8 @@ int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs,
 #define OVGPU_TU_IMPLICIT_MTS 1   /* luma TB of an intra, non-MIP CU while ctudec->mts_implicit (rcn_transform_tree.c:435) */
 #define OVGPU_TU_LFNST_L      2   /* TUInfo.lfnst_flag applies to the luma TB                                       */
 #define OVGPU_TU_LFNST_C      4   /* TUInfo.lfnst_flag applies to the chroma TBs (dual-tree chroma, rcn_tu_c)       */
+#define OVGPU_TU_SCALE_ANCHOR 8   /* the LMCS chroma scale is the one the GPU derives for anchor `scale_anchor` of the batch
+                                   * (ovgpu_tu_batch_set_anchors) instead of `chroma_scale`                         */
 
 /* One recorded transform unit; x0/y0 picture-absolute luma samples, log2_w/h the luma size (chroma TBs are half).
  * Per-TB arrays are indexed like TUInfo.tb_info (rcn_transform_tree.c:56-66): [0] Cb or joint CbCr, [1] Cr, [2] luma. */
@@ -242,7 +246,7 @@ typedef struct OVGPUTuCmd {
     int16_t chroma_scale;         /* lmcs_info.lmcs_chroma_scale at call time (2048 = neutral)     */
     uint8_t lfnst_mode_l;         /* ctudec->intra_mode (PLANAR for MIP CUs)                       */
     uint8_t lfnst_mode_c;         /* chroma mode with DM / CCLM resolved to the collocated luma mode (drv_lfnst.c:97-104) */
-    uint16_t pad;
+    uint16_t scale_anchor;        /* with OVGPU_TU_SCALE_ANCHOR: index into the batch's anchor list */
     uint32_t coeff_off[3];        /* int16 offsets into the coefficient arena; data in the reference's buffer order:
                                    * 4x4 sub-blocks of 16 contiguous values, min(32,w)/4 per row (rcn_dequant.c:243-253) */
     uint32_t pad2;
@@ -268,6 +272,19 @@ int  ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmd
  * commit. */
 int  ovgpu_tu_batch_staging(OVGPUCtx *ctx, OVGPUTuBatch *b, OVGPUTuCmd **cmds, int16_t **coeffs);
 int  ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb_coeffs, const OVGPUTuSlice *slice);
+/* LMCS chroma residual scaling needs lmcs_info.lmcs_chroma_scale, which the reference derives from RECONSTRUCTED luma
+ * (rcn_lmcs_compute_chroma_scale, rcn_lmcs.c:320-343) whenever a coding unit starts on a 64-aligned position
+ * (coding_unit, vcl_coding_unit.c:725-730) -- the CPU parser cannot know it.  The recorder instead lists those positions
+ * ("anchors") with the two 16-bit availability masks the reference reads there ((hfield[y0 >> 2] >> ((x0 >> 2) + 1)) & 0xffff
+ * and the vfield counterpart, CTU-local x0 / y0) and tags every transform unit with the anchor in force
+ * (OVGPU_TU_SCALE_ANCHOR + scale_anchor); ovgpu_recon_picture derives the scales on the GPU once the luma plane is
+ * reconstructed and before any chroma residual is added.  Needs the LMCS object given to ovgpu_recon_picture to carry the
+ * slice's OVGPULmcsData (ovgpu_lmcs_set_data). */
+typedef struct OVGPULmcsAnchor {
+    int16_t x0, y0;               /* picture-absolute luma position (multiples of 64 inside the CTU) */
+    uint16_t abv_mask, lft_mask;
+} OVGPULmcsAnchor;
+int  ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAnchor *anchors, int nb_anchors);
 /* pic += residual of every TU (pic holds the prediction). Asynchronous. */
 int  ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b);
 

@@ -287,6 +287,10 @@ class Lmcs:
         self._keep = luts
         _check((ctx or self.ctx).h, lib().ovgpu_lmcs_upload((ctx or self.ctx).h, self.p, C.byref(luts)), "lmcs_upload")
 
+    def set_data(self, data):
+        """LmcsData of the slice (window range, chroma scaling offset) for the on-device chroma scale"""
+        _check(self.ctx.h, lib().ovgpu_lmcs_set_data(self.p, C.byref(data)), "lmcs_set_data")
+
     def reshape(self, pic, forward=False, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_lmcs_reshape_picture((ctx or self.ctx).h, pic.p, self.p, int(forward)), "lmcs_reshape_picture")
 
@@ -384,6 +388,12 @@ class TuBatch:
         self._keep = (cmds, coeffs)
         _check((ctx or self.ctx).h, lib().ovgpu_tu_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds), vp(coeffs.ctypes.data),
                                                        C.c_size_t(len(coeffs)), C.byref(sl)), "tu_batch_upload")
+
+    def set_anchors(self, anchors, ctx=None):
+        """OVGPULmcsAnchor list for the on-device LMCS chroma scale; call before the commands that name them"""
+        anchors = np.ascontiguousarray(anchors)
+        assert anchors.dtype.itemsize == 8
+        _check((ctx or self.ctx).h, lib().ovgpu_tu_batch_set_anchors((ctx or self.ctx).h, self.p, vp(anchors.ctypes.data), len(anchors)), "tu_batch_set_anchors")
 
     def run(self, pic, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_residual_picture((ctx or self.ctx).h, pic.p, self.p), "residual_picture")

@@ -22,111 +22,112 @@ static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
     return 0;
 }
 
-// level[i] = 1 + the highest level among earlier blocks that cover one of block i's reference samples (left column of
-// 2h + 1 and above row of 2w + 1 samples, on the 4x4 unit grid).  Luma and chroma keep separate level maps (dual tree:
-// a chroma-only command depends on earlier chroma blocks, and -- for CCLM -- on the luma blocks under and around it).
-// order[] = command indices sorted by level (stable), level_start[l] .. level_start[l + 1] = the blocks of level l
-// (0-based).  map_l / map_c (optional, w/4 x h/4 entries each) receive the 1-based level of the command covering each
-// unit (0 = none): the residual schedule (tr_host.h) places transform blocks with them.  Returns the number of levels or -1.
-static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu, int yu, int nw, int nh, int own)
+// Dependency levels, per plane.  Luma never reads chroma, so the whole luma plane can be reconstructed before any chroma
+// (and CCLM / the LMCS chroma scale then read final luma): the luma blocks and the chroma blocks of a picture get
+// independent level numbers.  level = 1 + the highest level among earlier blocks of the same plane that cover one of the
+// block's reference samples (left column of 2h + 1 and above row of 2w + 1 samples, on the 4x4 luma-unit grid).
+// Per plane p (0 luma, 1 chroma): order[p][] = indices of the commands that have that plane, sorted by level (stable);
+// start[p][l] .. start[p][l + 1] = the blocks of level l (0-based); nb[p] = number of levels.
+// map_l / map_c (optional, w/4 x h/4 entries each) receive the 1-based level of the command covering each unit
+// (0 = none): the residual schedule (tr_host.h) places transform blocks with them.
+struct IntraLevels {
+    int nb[2];
+    uint32_t *order[2];      // n entries each
+    uint32_t *start[2];      // n + 2 entries each
+};
+
+static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu, int yu, int nw, int nh)
 {
     int lv = 0;
     if (xu > 0)
         for (int y = yu - 1; y < yu + 2 * nh && y < h_u; y++) if (y >= 0 && m[y * w_u + xu - 1] > lv) lv = m[y * w_u + xu - 1];
     if (yu > 0)
         for (int x = xu - 1; x < xu + 2 * nw && x < w_u; x++) if (x >= 0 && m[(yu - 1) * w_u + x] > lv) lv = m[(yu - 1) * w_u + x];
-    if (own)
-        for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) if (m[y * w_u + x] > lv) lv = m[y * w_u + x];
     return lv;
 }
 
-static inline int intra_build_levels(uint32_t *order, uint32_t *level_start, int max_levels, const OVGPUIntraCmd *cmds, int n,
+// Returns 0, or -1 (out of memory / more than max_levels levels).
+static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPUIntraCmd *cmds, int n,
                                      int pic_w, int pic_h, uint16_t *map_l_out = NULL, uint16_t *map_c_out = NULL)
 {
     const int w_u = pic_w >> 2, h_u = pic_h >> 2;
-    uint16_t *map_l = map_l_out ? map_l_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t));
-    uint16_t *map_c = map_c_out ? map_c_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t));
-    uint16_t *lvl = (uint16_t *)malloc(sizeof(uint16_t) * (n > 0 ? n : 1));
-    uint32_t *fill = NULL;
-    int nb_levels = 0, ret = -1;
-    if (!map_l || !map_c || !lvl) goto done;
-    memset(map_l, 0, (size_t)w_u * h_u * sizeof(uint16_t));
-    memset(map_c, 0, (size_t)w_u * h_u * sizeof(uint16_t));
-    for (int i = 0; i < n; i++) {
-        const OVGPUIntraCmd *c = &cmds[i];
-        const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
-        const int luma = c->flags & OVGPU_INTRA_LUMA, chroma = c->flags & OVGPU_INTRA_CHROMA;
-        int m = 0, v;
-        if (luma) m = intra_neigh_level(map_l, w_u, h_u, xu, yu, nw, nh, 0);
-        if (chroma) {
-            if ((v = intra_neigh_level(map_c, w_u, h_u, xu, yu, nw, nh, 0)) > m) m = v;
-            if (c->mode_c >= 67 && !luma && (v = intra_neigh_level(map_l, w_u, h_u, xu, yu, nw, nh, 1)) > m) m = v;
-        }
-        if (m + 1 > 65535 || m + 1 > max_levels) goto done;
-        lvl[i] = (uint16_t)(m + 1);
-        if (m + 1 > nb_levels) nb_levels = m + 1;
-        for (int y = yu; y < yu + nh; y++)
-            for (int x = xu; x < xu + nw; x++) {
-                if (luma) map_l[y * w_u + x] = lvl[i];
-                if (chroma) map_c[y * w_u + x] = lvl[i];
+    uint16_t *map[2] = { map_l_out ? map_l_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)),
+                         map_c_out ? map_c_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)) };
+    uint16_t *lvl = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (n > 0 ? n : 1));
+    uint32_t *fill = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 3));
+    int ret = -1;
+    L->nb[0] = L->nb[1] = 0;
+    if (map[0] && map[1] && lvl && fill) {
+        ret = 0;
+        for (int p = 0; p < 2 && !ret; p++) {
+            const int bit = p ? OVGPU_INTRA_CHROMA : OVGPU_INTRA_LUMA;
+            uint16_t *m = map[p], *lv = lvl + (size_t)p * n;
+            int nb_levels = 0;
+            memset(m, 0, (size_t)w_u * h_u * sizeof(uint16_t));
+            for (int i = 0; i < n; i++) {
+                const OVGPUIntraCmd *c = &cmds[i];
+                lv[i] = 0;
+                if (!(c->flags & bit)) continue;
+                const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
+                const int l = intra_neigh_level(m, w_u, h_u, xu, yu, nw, nh) + 1;
+                if (l > 65535 || l > max_levels) { ret = -1; break; }
+                lv[i] = (uint16_t)l;
+                if (l > nb_levels) nb_levels = l;
+                for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) m[y * w_u + x] = (uint16_t)l;
             }
+            if (ret) break;
+            // counting sort by level (level 0 = the command does not have this plane)
+            uint32_t *start = L->start[p];
+            memset(start, 0, sizeof(uint32_t) * (nb_levels + 2));
+            for (int i = 0; i < n; i++) if (lv[i]) start[lv[i]]++;            // counts at index level (1-based)
+            uint32_t acc = 0;
+            for (int l = 1; l <= nb_levels; l++) { uint32_t cnt = start[l]; start[l] = acc; acc += cnt; }
+            start[nb_levels + 1] = acc;
+            memcpy(fill, start, sizeof(uint32_t) * (nb_levels + 2));
+            for (int i = 0; i < n; i++) if (lv[i]) L->order[p][fill[lv[i]]++] = (uint32_t)i;
+            for (int l = 0; l <= nb_levels; l++) start[l] = start[l + 1];       // 0-based
+            L->nb[p] = nb_levels;
+        }
     }
-    // counting sort by level
-    memset(level_start, 0, sizeof(uint32_t) * (nb_levels + 2));
-    for (int i = 0; i < n; i++) level_start[lvl[i]]++;                 // counts at index level (1-based)
-    {
-        uint32_t acc = 0;
-        for (int l = 1; l <= nb_levels; l++) { uint32_t cnt = level_start[l]; level_start[l] = acc; acc += cnt; }
-        level_start[nb_levels + 1] = acc;
-    }
-    fill = (uint32_t *)malloc(sizeof(uint32_t) * (nb_levels + 2));
-    if (!fill) goto done;
-    memcpy(fill, level_start, sizeof(uint32_t) * (nb_levels + 2));
-    for (int i = 0; i < n; i++) order[fill[lvl[i]]++] = (uint32_t)i;
-    // shift to 0-based: level_start[l] for l in 0..nb_levels
-    for (int l = 0; l <= nb_levels; l++) level_start[l] = level_start[l + 1];
-    ret = nb_levels;
-done:
     free(fill); free(lvl);
-    if (!map_l_out) free(map_l);
-    if (!map_c_out) free(map_c);
+    if (!map_l_out) free(map[0]);
+    if (!map_c_out) free(map[1]);
     return ret;
 }
 
-// Launch sequence of a picture: one grid per dependency level covering the components present; a level whose chroma
-// blocks may use CCLM (they read the luma block of the same command) runs luma first, then Cb / Cr.
-// f(first command of the level in order[], number of commands, first component, number of components) -> 0 on success
+// Launch sequence of a picture's intra predictions alone: the luma levels, then the chroma levels (Cb and Cr together).
+// f(plane, first entry in order[plane], number of commands) -> 0 on success
 template <typename F>
-static inline int intra_for_each_launch(int nb_levels, const uint32_t *level_start, int has_chroma, int has_cclm, F f)
+static inline int intra_for_each_launch(const IntraLevels *L, F f)
 {
-    for (int l = 0; l < nb_levels; l++) {
-        const int start = (int)level_start[l], n = (int)level_start[l + 1] - start;
-        if (n <= 0) continue;
-        int rc;
-        if (has_cclm) { if ((rc = f(start, n, 0, 1)) != 0 || (rc = f(start, n, 1, 2)) != 0) return rc; }
-        else if ((rc = f(start, n, 0, has_chroma ? 3 : 1)) != 0) return rc;
-    }
+    for (int p = 0; p < 2; p++)
+        for (int l = 0; l < L->nb[p]; l++) {
+            const int start = (int)L->start[p][l], n = (int)L->start[p][l + 1] - start;
+            int rc;
+            if (n > 0 && (rc = f(p, start, n)) != 0) return rc;
+        }
     return 0;
 }
 
 // Whole reconstruction order of a picture (replaces the reference's CU loop: prediction, then rcn_transform_tree per CU,
-// vcl_coding_unit.c / rcn_transform_tree.c:1433): transform blocks outside intra commands first (group 0: their
-// predictions come from motion compensation, done before), then level by level the intra predictions followed by the
-// residual of the blocks they cover.  With CCLM a level is run luma first (prediction + residual), then chroma.
-// fi(first command in order[], count, first component, number of components), ft(residual group) -> 0 on success
-template <typename FI, typename FT>
-static inline int recon_for_each_launch(int nb_levels, const uint32_t *level_start, int has_chroma, int has_cclm, FI fi, FT ft)
+// vcl_coding_unit.c / rcn_transform_tree.c:1433), plane by plane.  Luma: the transform blocks outside intra commands
+// (residual group 0: their predictions come from motion compensation, done before), then level by level the intra
+// predictions followed by the residual of the blocks they cover (group = level).  Then the LMCS chroma scales, which read
+// the reconstructed luma (fs).  Then chroma the same way (groups nb[0] + 1 ...).
+// fi(plane, first entry in order[plane], count), ft(residual group), fs() -> 0 on success
+template <typename FI, typename FT, typename FS>
+static inline int recon_for_each_launch(const IntraLevels *L, FI fi, FT ft, FS fs)
 {
-    const int split = has_cclm ? 2 : 1;
-    int rc;
-    for (int s = 0; s < split; s++) if ((rc = ft(s)) != 0) return rc;
-    for (int l = 0; l < nb_levels; l++) {
-        const int start = (int)level_start[l], n = (int)level_start[l + 1] - start;
-        if (n <= 0) continue;
-        if (has_cclm) {
-            if ((rc = fi(start, n, 0, 1)) != 0 || (rc = ft((l + 1) * 2)) != 0 ||
-                (rc = fi(start, n, 1, 2)) != 0 || (rc = ft((l + 1) * 2 + 1)) != 0) return rc;
-        } else if ((rc = fi(start, n, 0, has_chroma ? 3 : 1)) != 0 || (rc = ft(l + 1)) != 0) return rc;
+    int rc, base = 0;
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && (rc = fs()) != 0) return rc;
+        if ((rc = ft(base)) != 0) return rc;
+        for (int l = 0; l < L->nb[p]; l++) {
+            const int start = (int)L->start[p][l], n = (int)L->start[p][l + 1] - start;
+            if (n > 0 && (rc = fi(p, start, n)) != 0) return rc;
+            if ((rc = ft(base + l + 1)) != 0) return rc;
+        }
+        base += L->nb[p] + 1;
     }
     return 0;
 }

@@ -26,6 +26,7 @@ static_assert(sizeof(DmvrMvDev) == sizeof(OVGPUDmvrMv), "DMVR result layout");
 struct OVGPULmcs {
     OVGPULmcsLuts *h_luts, *d_luts;
     int device;
+    int has_data, min_idx, max_idx_p1, crs_offset;      // ovgpu_lmcs_set_data (rcn_init_lmcs, rcn_lmcs.c:345-361)
     StagingFence fence;
 };
 
@@ -71,6 +72,16 @@ int ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts)
     memcpy(l->h_luts, luts, sizeof(*luts));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(l->d_luts, l->h_luts, sizeof(*luts), cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&l->fence, ctx->stream));
+    return 0;
+}
+
+int ovgpu_lmcs_set_data(OVGPULmcs *l, const OVGPULmcsData *d)
+{
+    if (!l || !d || d->lmcs_min_bin_idx > 15 || d->lmcs_delta_max_bin_idx > 15) return OVGPU_EINVAL;
+    l->min_idx = d->lmcs_min_bin_idx;
+    l->max_idx_p1 = 16 - d->lmcs_delta_max_bin_idx;
+    l->crs_offset = d->lmcs_delta_sign_crs_flag ? -(int)d->lmcs_delta_abs_crs : (int)d->lmcs_delta_abs_crs;
+    l->has_data = 1;
     return 0;
 }
 
@@ -259,3 +270,10 @@ int ovgpu_mc_batch_read_dmvr(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUDmvrMv *out, i
 }
 
 } // extern "C"
+
+int ovgpu_lmcs_scale_params(const OVGPULmcs *l, const uint16_t **d_wnd_bnd, int *min_idx, int *max_idx_p1, int *crs_offset)
+{
+    if (!l || !l->has_data) return -1;
+    *d_wnd_bnd = l->d_luts->wnd_bnd; *min_idx = l->min_idx; *max_idx_p1 = l->max_idx_p1; *crs_offset = l->crs_offset;
+    return 0;
+}

@@ -17,7 +17,12 @@ struct OVGPUTuBatch {
     // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h
     TuGroups groups;
     uint64_t serial, bound_serial, bound_intra_serial;
+    // LMCS chroma scale anchors (ovgpu_tu_batch_set_anchors) and the scales LmcsScaleK derives for them
+    LmcsAnchorDev *h_anchors, *d_anchors;
+    int16_t *d_scales;
+    int nb_anchors, max_anchors;
 };
+static_assert(sizeof(LmcsAnchorDev) == sizeof(OVGPULmcsAnchor) && sizeof(LmcsAnchorDev) == 8, "LMCS anchor layout");
 
 template <int GROUP>
 static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, const TbItemDev *items, int n)
@@ -29,6 +34,7 @@ static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatc
     a.bitdepth = pic->bitdepth;
     a.cmds = b->d_cmds; a.items = items; a.nb_items = n; a.arena = b->d_coeffs;
     a.dep_quant = b->slice.dep_quant; a.sh_ts_disabled = b->slice.sh_ts_disabled; a.ict_type = b->slice.ict_type;
+    a.scales = b->nb_anchors ? b->d_scales : NULL;
     return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, ctx->stream);
 }
 
@@ -67,6 +73,9 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     if (b->d_coeffs) cudaFree(b->d_coeffs);
     fence_destroy(&b->fence);
     tu_groups_free(&b->groups);
+    if (b->h_anchors) cudaFreeHost(b->h_anchors);
+    if (b->d_anchors) cudaFree(b->d_anchors);
+    if (b->d_scales) cudaFree(b->d_scales);
     free(b);
 }
 
@@ -91,6 +100,10 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
     b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
     b->serial++;
     tu_groups_free(&b->groups);
+    for (int i = 0; i < nb_cmds; i++)
+        if ((cmds[i].flags & OVGPU_TU_SCALE_ANCHOR) && cmds[i].scale_anchor >= b->nb_anchors)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d names LMCS anchor %d of %d (set the anchors before the commands)",
+                                   i, cmds[i].scale_anchor, b->nb_anchors);
     if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
     tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
     tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
@@ -113,6 +126,32 @@ int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds
     if (ret) return ret;
     if (nb_cmds) { memcpy(hc, cmds, sizeof(TuCmdDev) * nb_cmds); memcpy(hk, coeffs, sizeof(int16_t) * nb_coeffs); }
     return ovgpu_tu_batch_commit(ctx, b, nb_cmds, nb_coeffs, slice);
+}
+
+int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAnchor *anchors, int nb)
+{
+    if (!ctx || !b || nb < 0 || nb > 65536 || (nb && !anchors)) return OVGPU_EINVAL;
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    if (nb > b->max_anchors) {
+        if (b->h_anchors) cudaFreeHost(b->h_anchors);
+        if (b->d_anchors) cudaFree(b->d_anchors);
+        if (b->d_scales) cudaFree(b->d_scales);
+        b->h_anchors = NULL; b->d_anchors = NULL; b->d_scales = NULL; b->max_anchors = 0;
+        if (cudaMallocHost(&b->h_anchors, sizeof(LmcsAnchorDev) * nb) != cudaSuccess ||
+            cudaMalloc(&b->d_anchors, sizeof(LmcsAnchorDev) * nb) != cudaSuccess ||
+            cudaMalloc(&b->d_scales, sizeof(int16_t) * nb) != cudaSuccess)
+            return ovgpu_set_error(ctx, OVGPU_ENOMEM, "LMCS anchor buffers");
+        b->max_anchors = nb;
+    }
+    for (int i = 0; i < nb; i++)
+        if (anchors[i].x0 < 0 || anchors[i].y0 < 0 || (anchors[i].x0 & 63) || (anchors[i].y0 & 63)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "LMCS anchor %d malformed", i);
+    b->nb_anchors = nb;
+    if (nb) {
+        memcpy(b->h_anchors, anchors, sizeof(LmcsAnchorDev) * nb);
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_anchors, b->h_anchors, sizeof(LmcsAnchorDev) * nb, cudaMemcpyHostToDevice, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+    }
+    return 0;
 }
 
 int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b)
@@ -140,7 +179,7 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
 
 // ---- internal: residual in reconstruction order (called by ovgpu_recon_picture, intra.cu) ---------------------------
 int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint16_t *map_l, const uint16_t *map_c,
-                         int w_u, int h_u, int nb_levels, int split)
+                         int w_u, int h_u, int nl_l, int nl_c)
 {
     if (b->groups.nb_groups && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial) return 0;
     for (int i = 0; i < b->nb_cmds; i++) {
@@ -148,7 +187,7 @@ int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, 
         if ((c->x0 >> 2) >= w_u || (c->y0 >> 2) >= h_u) return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
-    const int n = tu_build_grouped_items(b->h_items, &b->groups, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, map_l, map_c, w_u, nb_levels, split);
+    const int n = tu_build_grouped_items(b->h_items, &b->groups, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, map_l, map_c, w_u, nl_l, nl_c);
     if (n < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "TU groups");
     if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
@@ -166,6 +205,27 @@ int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, 
     if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->groups.start_large[group], nl));
     return 0;
 }
+
+// the chroma scales of the batch's anchors from the reconstructed luma plane of pic (all luma must be done)
+int ovgpu_tu_derive_scales(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b, const uint16_t *d_wnd_bnd,
+                           int min_idx, int max_idx_p1, int crs_offset)
+{
+    if (!b->nb_anchors) return 0;
+    for (int i = 0; i < b->nb_anchors; i++) {
+        const LmcsAnchorDev *a = &b->h_anchors[i];
+        if (a->x0 >= pic->width || a->y0 >= pic->height || (a->abv_mask && !a->y0) || (a->lft_mask && !a->x0) ||
+            a->x0 + 4 * (32 - __builtin_clz(a->abv_mask | 1u)) > pic->width + 3 * !a->abv_mask ||
+            a->y0 + 4 * (32 - __builtin_clz(a->lft_mask | 1u)) > pic->height + 3 * !a->lft_mask)
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "LMCS anchor %d reads outside the picture", i);
+    }
+    StageScope scope(ctx, OVGPU_STAGE_LMCS, 1);
+    PlaneView v = plane_view(pic, 0);
+    LmcsScaleK::Args a = { v.p, v.pitch, pic->bitdepth, b->d_anchors, b->nb_anchors, b->d_scales, d_wnd_bnd, min_idx, max_idx_p1, crs_offset };
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<LmcsScaleK>(a, dim3(OVGPU_CEIL_DIV(b->nb_anchors, LmcsScaleK::WARPS), 1, 1), LmcsScaleK::SMEM_BYTES, ctx->stream));
+    return 0;
+}
+
+int ovgpu_tu_nb_anchors(const OVGPUTuBatch *b) { return b->nb_anchors; }
 
 int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b)
 {

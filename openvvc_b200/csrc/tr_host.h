@@ -51,21 +51,21 @@ static inline void tu_build_items(TbItemDev *small, TbItemDev *large, int *nb_sm
 
 // ---- reconstruction order ----------------------------------------------------------------------------------------
 // The reference reconstructs CU by CU: prediction, then rcn_transform_tree (vcl_coding_unit.c -> rcn_res_wrap), so an
-// intra block reads neighbours that already hold prediction + residual.  The picture-level schedule (recon_host.h)
-// keeps that order by dependency LEVEL: transform blocks covered by an intra command run right after that command's
-// level; all others (inter CUs) run first.  `map_l` / `map_c` hold, per 4x4 luma unit, the 1-based level of the intra
-// command covering it (0 = none) for the luma / chroma tree.  With `split` == 2 (pictures using CCLM, whose chroma
-// prediction reads the luma RECONSTRUCTION of the same CU) a level is run luma first, then chroma.
+// intra block reads neighbours that already hold prediction + residual.  The picture-level schedule (intra_host.h:
+// recon_for_each_launch) keeps that order per plane by dependency LEVEL: transform blocks covered by an intra command run
+// right after that command's level; all others (inter CUs) run first.  `map_l` / `map_c` hold, per 4x4 luma unit, the
+// 1-based level of the intra command covering it (0 = none) for the luma / chroma plane.  Groups: luma blocks 0 .. nl_l,
+// chroma blocks nl_l + 1 .. nl_l + 1 + nl_c.
 struct TuGroups {
-    int nb_groups, split;
+    int nb_groups;
     int *start_small, *n_small, *start_large, *n_large;   // per group, offsets into the re-ordered item array
 };
 
-static inline int tu_group_of(const OVGPUTuCmd *c, int kind, const uint16_t *map_l, const uint16_t *map_c, int w_u, int split)
+static inline int tu_group_of(const OVGPUTuCmd *c, int kind, const uint16_t *map_l, const uint16_t *map_c, int w_u, int nl_l)
 {
     const uint16_t *m = kind == 0 ? map_l : map_c;
     const int lvl = m ? m[(size_t)(c->y0 >> 2) * w_u + (c->x0 >> 2)] : 0;
-    return lvl * split + (split == 2 && kind != 0);
+    return kind == 0 ? lvl : nl_l + 1 + lvl;
 }
 
 static inline void tu_groups_free(TuGroups *g)
@@ -75,13 +75,13 @@ static inline void tu_groups_free(TuGroups *g)
 
 // items: room for every transform block of the batch.  Returns the number of items or -1 (out of memory).
 static inline int tu_build_grouped_items(TbItemDev *items, TuGroups *g, const OVGPUTuCmd *cmds, int n,
-                                         const uint16_t *map_l, const uint16_t *map_c, int w_u, int nb_levels, int split)
+                                         const uint16_t *map_l, const uint16_t *map_c, int w_u, int nl_l, int nl_c)
 {
     tu_groups_free(g);
-    const int ng = (nb_levels + 1) * split;
+    const int ng = nl_l + nl_c + 2;
     int *mem = (int *)calloc((size_t)4 * ng, sizeof(int));
     if (!mem) return -1;
-    g->nb_groups = ng; g->split = split;
+    g->nb_groups = ng;
     g->start_small = mem; g->n_small = mem + ng; g->start_large = mem + 2 * ng; g->n_large = mem + 3 * ng;
     for (int pass = 0; pass < 2; pass++) {
         for (int i = 0; i < n; i++) {
@@ -95,7 +95,7 @@ static inline int tu_build_grouped_items(TbItemDev *items, TuGroups *g, const OV
             }
             for (int k = 0; k < nk; k++) {
                 const int s = c->log2_w + c->log2_h - (kinds[k] ? 2 : 0);
-                const int grp = tu_group_of(c, kinds[k], map_l, map_c, w_u, split);
+                const int grp = tu_group_of(c, kinds[k], map_l, map_c, w_u, nl_l);
                 if (pass == 0) { if (s <= 8) g->n_small[grp]++; else g->n_large[grp]++; }
                 else {
                     TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };

@@ -22,6 +22,7 @@
 #define TU_IMPLICIT_MTS 1
 #define TU_LFNST_L 2
 #define TU_LFNST_C 4
+#define TU_SCALE_ANCHOR 8
 
 struct TuCmdDev {            // == OVGPUTuCmd
     int16_t x0, y0;
@@ -31,7 +32,7 @@ struct TuCmdDev {            // == OVGPUTuCmd
     uint16_t last_pos[3];
     int16_t chroma_scale;
     uint8_t lfnst_mode_l, lfnst_mode_c;
-    uint16_t pad;
+    uint16_t scale_anchor;
     uint32_t coeff_off[3];
     uint32_t pad2;
     uint64_t sig_sb_map[3];
@@ -66,6 +67,7 @@ struct TrK {
         int nb_items;
         const int16_t *arena;
         int dep_quant, sh_ts_disabled, ict_type;
+        const int16_t *scales;   // LMCS chroma scale per anchor (LmcsScaleK), for commands with TU_SCALE_ANCHOR
     };
     struct State { int dummy; };
 
@@ -113,7 +115,7 @@ struct TrK {
         t.sig |= !t.sig;
         t.src = a.arena + c.coeff_off[slot];
         t.cbf_c = c.cbf_mask & 3;
-        t.chroma_scale = c.chroma_scale;
+        t.chroma_scale = ((c.flags & TU_SCALE_ANCHOR) && a.scales) ? a.scales[c.scale_anchor] : c.chroma_scale;
         const int ts = (c.tr_skip_mask & bit) != 0;
         int qp;
         if (luma) qp = ts ? c.qp_ts[0] : c.qp[0];
@@ -326,5 +328,65 @@ struct TrK {
                 add_plane(a, t.kind, t, res, dcv, 0, 0, big && scale_on, t.chroma_scale, gt);
             }
         }
+    }
+};
+
+// =====================================================================================================================
+// LMCS chroma residual scale of a 64x64 luma region (rcn_lmcs_compute_chroma_scale, libovvc/rcn_lmcs.c:204-343): average
+// of the reconstructed (reshaped-domain) luma samples above and left of the region -- the available run of 4-sample units,
+// padded to 16 units with the run's last sample -- mapped through the LMCS window bounds to 2^17 / (window size + offset).
+// The reference evaluates it when a coding unit starts on a 64-aligned position (coding_unit, vcl_coding_unit.c:725-730)
+// from its CTU buffer; here one warp per recorded anchor reads the finished luma plane (the schedule runs all luma first).
+struct LmcsAnchorDev { int16_t x0, y0; uint16_t abv_mask, lft_mask; };   // == OVGPULmcsAnchor
+
+struct LmcsScaleK {
+    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 2;
+    static const int WARPS = 4;
+    static const int SMEM_BYTES = WARPS * 32 * 4;
+    struct Args {
+        const uint16_t *luma;
+        int pitch, bitdepth;
+        const LmcsAnchorDev *anchors;
+        int nb;
+        int16_t *scales;
+        const uint16_t *wnd_bnd;         // 17 entries (device)
+        int min_idx, max_idx_p1, crs_offset;
+    };
+    struct State { int dummy; };
+
+    OVD int run_len(unsigned m) { int n = 0; while (m) { n++; m >>= 1; } return n; }     // the reference walks until the mask is empty
+
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        const int warp = tid >> 5, lane = tid & 31, idx = bx * WARPS + warp;
+        if (idx >= a.nb) return;
+        int *part = (int *)smem + warp * 32;
+        const LmcsAnchorDev an = a.anchors[idx];
+        const int n_abv = run_len(an.abv_mask), n_lft = run_len(an.lft_mask);
+        const uint16_t *src = a.luma + (ptrdiff_t)an.y0 * a.pitch + an.x0;
+        if (P == 0) {
+            const int left = lane >> 4, u = lane & 15, n = left ? n_lft : n_abv;
+            const ptrdiff_t step = left ? a.pitch : 1;
+            const uint16_t *line = left ? src - 1 : src - a.pitch;
+            int sum = 0;
+            if (u < n) sum = line[(4 * u) * step] + line[(4 * u + 1) * step] + line[(4 * u + 2) * step] + line[(4 * u + 3) * step];
+            else if (n) sum = 4 * line[(4 * n - 1) * step];
+            part[lane] = sum;
+            return;
+        }
+        if (lane) return;
+        int sum = 0;
+        for (int i = 0; i < 32; i++) sum += part[i];
+        const int nb_units = (n_abv ? 16 : 0) + (n_lft ? 16 : 0);
+        int avg = 1 << (a.bitdepth - 1);
+        if (nb_units) { const int l2 = nb_units == 32 ? 6 : 5; avg = (sum + (1 << l2)) >> (l2 + 1); }
+        int i = a.min_idx;
+        for (; i < a.max_idx_p1; i++) if (avg < a.wnd_bnd[i + 1]) break;               // get_bwd_idx, rcn_lmcs.c:84-94
+        i = ovd_min(i, 15);
+        const int wnd_sz = (int)a.wnd_bnd[i + 1] - (int)a.wnd_bnd[i], den = wnd_sz + a.crs_offset;
+        const int scale = (wnd_sz == 0 || den == 0) ? 1 << 11 : (1 << (a.bitdepth - 4 + 11)) / den;
+        a.scales[idx] = (int16_t)(uint16_t)scale;                                      // uint16_t lmcs_chroma_scale, read as int16_t
     }
 };

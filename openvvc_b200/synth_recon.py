@@ -19,3 +19,25 @@ def recon_case(w, h, seed, log2_ctu=7, min_log2=2, p_inter=0.4, p_ciip=0.1, p_mr
                                       intra_mask=is_intra)
     assert len(tus) == len(cmds)
     return np.ascontiguousarray(cmds), tus, arena
+
+
+LMCS_ANCHOR = np.dtype([("x0", np.int16), ("y0", np.int16), ("abv_mask", np.uint16), ("lft_mask", np.uint16)])   # == OVGPULmcsAnchor
+
+
+def lmcs_anchors(cmds, tus, log2_ctu=7):
+    """What the recorder lists for the on-device LMCS chroma scale: the coding units that start on a 64-aligned position
+    (coding_unit, vcl_coding_unit.c:725-730) with the two 16-bit availability masks rcn_lmcs_compute_chroma_scale reads there
+    (rcn_lmcs.c:325-331), and for every transform unit the anchor in force (flag OVGPU_TU_SCALE_ANCHOR + scale_anchor)."""
+    cm = (1 << log2_ctu) - 1
+    anchors = []
+    tus = tus.copy()
+    for i, c in enumerate(cmds):
+        x0, y0 = int(c["x0"]), int(c["y0"])
+        if not (x0 & 63) and not (y0 & 63):
+            abv = (int(c["avail_rows"]) >> (((x0 & cm) >> 2) + 1)) & 0xffff
+            lft = (int(c["avail_cols"]) >> (((y0 & cm) >> 2) + 1)) & 0xffff
+            anchors.append((x0, y0, abv, lft))
+        assert anchors, "the first coding unit of a picture starts at (0, 0)"
+        tus["flags"][i] |= synth_tu.TU_SCALE_ANCHOR
+        tus["scale_anchor"][i] = len(anchors) - 1
+    return np.array(anchors, dtype=LMCS_ANCHOR), tus

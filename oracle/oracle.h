@@ -154,6 +154,8 @@ typedef struct OVOLmcsLuts {          /* struct LMCSLUTs, rcn_lmcs.c:77-82 (10-b
 } OVOLmcsLuts;
 
 void ovo_lmcs_build_luts(OVOLmcsLuts *luts, const OVOLmcsData *data, int bitdepth);
+int ovo_lmcs_chroma_scale(const uint16_t *src, int stride, unsigned abv_mask, unsigned lft_mask,
+                          const OVOLmcsLuts *luts, const OVOLmcsData *d, int bitdepth);
 void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uint16_t *lut, int bitdepth);
 
 /* ---- Residual: dequantisation, LFNST, inverse transform, residual add ------------------------------------- */
@@ -177,7 +179,7 @@ typedef struct OVOTuCmd {
     int16_t chroma_scale;        /* lmcs_chroma_scale (2048 = neutral) */
     uint8_t lfnst_mode_l;        /* intra mode LFNST derives its set from: ctudec->intra_mode, PLANAR for MIP   */
     uint8_t lfnst_mode_c;        /* chroma: resolved mode (DM / CCLM replaced by the collocated luma mode)      */
-    uint16_t pad;
+    uint16_t scale_anchor;       /* GPU side only (OVGPU_TU_SCALE_ANCHOR); the oracle takes chroma_scale        */
     uint32_t coeff_off[3];       /* int16 offsets into the coefficient arena */
     uint32_t pad2;
     uint64_t sig_sb_map[3];
@@ -244,9 +246,13 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
                        const OVOIntraCmd *cmds, int nb_cmds);
 
 /* ---- Reconstruction in CU order (port_recon.c): prediction, then residual, coding unit by coding unit -------- */
+typedef struct OVOLmcsAnchor { int16_t x0, y0; uint16_t abv_mask, lft_mask; } OVOLmcsAnchor;   /* == OVGPULmcsAnchor */
+/* anchors (may be NULL): 64-aligned CU origins where the reference derives lmcs_chroma_scale; the value stays in force for
+ * the following transform units flagged with bit 3 (OVGPU_TU_SCALE_ANCHOR), the others take their chroma_scale field */
 void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
-                       int dep_quant, int sh_ts_disabled, int ict_type);
+                       int dep_quant, int sh_ts_disabled, int ict_type,
+                       const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs);
 
 #ifdef __cplusplus
 }

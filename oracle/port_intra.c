@@ -385,7 +385,7 @@ static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y
 static void mip_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int opaque,
                       uint64_t cols, uint64_t rows)
 {
-    int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1;
+    int w = 1 << lw, maxv = (1 << bitdepth) - 1;
     uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
     uint16_t *dst = plane + (size_t)y0 * stride + x0;
     const uint16_t *corner = dst - stride - 1;

@@ -558,3 +558,29 @@ void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uin
         for (int x = 0; x < w; x++)
             plane[(size_t)y * stride + x] = lut[plane[(size_t)y * stride + x] & msk];
 }
+
+/* rcn_lmcs_compute_chroma_scale (libovvc/rcn_lmcs.c:204-343): src points at the top-left luma sample of the 64x64 region.
+ * The reference walks each mask until it is empty (so the run length is the position of the highest set bit), pads the
+ * run to 16 units with its last sample, and averages over 64 or 128 samples. */
+int ovo_lmcs_chroma_scale(const uint16_t *src, int stride, unsigned abv_mask, unsigned lft_mask,
+                          const OVOLmcsLuts *luts, const OVOLmcsData *d, int bitdepth)
+{
+    unsigned sum = 0;
+    int n_abv = 0, n_lft = 0, nb_units, log2_nb = 0, avg, i;
+    const uint16_t *p = src - stride;
+    while (abv_mask) { sum += p[0] + p[1] + p[2] + p[3]; p += 4; n_abv++; abv_mask >>= 1; }
+    if (n_abv) { sum += 4u * p[-1] * (16 - n_abv); n_abv = 16; }
+    p = src - 1;
+    while (lft_mask) { sum += p[0] + p[stride] + p[2 * stride] + p[3 * stride]; p += 4 * stride; n_lft++; lft_mask >>= 1; }
+    if (n_lft) { sum += 4u * p[-stride] * (16 - n_lft); n_lft = 16; }
+    nb_units = n_abv + n_lft;
+    while (nb_units) { log2_nb++; nb_units >>= 1; }
+    avg = log2_nb ? (int)((sum + (1u << log2_nb)) >> (log2_nb + 1)) : 1 << (bitdepth - 1);
+    int min_idx = d->lmcs_min_bin_idx, max_idx_p1 = 16 - d->lmcs_delta_max_bin_idx;
+    for (i = min_idx; i < max_idx_p1; i++) if (avg < luts->wnd_bnd[i + 1]) break;      /* get_bwd_idx, :84-94 */
+    if (i > 15) i = 15;
+    int wnd_sz = (int)luts->wnd_bnd[i + 1] - (int)luts->wnd_bnd[i];
+    int offset = d->lmcs_delta_sign_crs_flag ? -(int)d->lmcs_delta_abs_crs : (int)d->lmcs_delta_abs_crs;
+    if (wnd_sz == 0 || wnd_sz + offset == 0) return 1 << 11;                           /* (the reference would divide by zero) */
+    return (int16_t)(uint16_t)((1 << (bitdepth - 4 + 11)) / (wnd_sz + offset));         /* uint16_t field read as int16_t */
+}

@@ -13,11 +13,22 @@
 /* cmds[i] and tus[i] describe the same coding unit (intra flags == 0: not intra; cbf_mask == 0: no residual) */
 void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
-                       int dep_quant, int sh_ts_disabled, int ict_type)
+                       int dep_quant, int sh_ts_disabled, int ict_type,
+                       const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs)
 {
+    int next_anchor = 0, cur_scale = 1 << 11;
     for (int i = 0; i < nb_cu; i++) {
         OVOIntraCmd c = cmds[i];
-        OVOTuCmd t = tus[i], tl = t, tc = t;
+        OVOTuCmd t = tus[i], tl, tc;
+        /* coding_unit (vcl_coding_unit.c:725-730): the chroma scale is refreshed when a CU starts on a 64-aligned position,
+         * from the CTU buffer as it is then, and stays in force until the next refresh */
+        if (next_anchor < nb_anchors && anchors[next_anchor].x0 == c.x0 && anchors[next_anchor].y0 == c.y0) {
+            const OVOLmcsAnchor *a = &anchors[next_anchor++];
+            cur_scale = ovo_lmcs_chroma_scale(planes[0] + (size_t)a->y0 * stride[0] + a->x0, stride[0], a->abv_mask, a->lft_mask,
+                                              luts, lmcs, bitdepth);
+        }
+        if (t.flags & 8) t.chroma_scale = (int16_t)cur_scale;
+        tl = t; tc = t;
         tl.cbf_mask = t.cbf_mask & 0x10;
         tc.cbf_mask = t.cbf_mask & 0x0f;
         if (c.flags & OVO_INTRA_CIIP) {

@@ -244,6 +244,38 @@ void rcn_init_dmvr_functions_10(struct RCNFunctions *rcn_func);
 
 static void harness_no_synchro(const OVPicture *const ref_pic, int a, int b, int c, int d) { (void)ref_pic; (void)a; (void)b; (void)c; (void)d; }
 
+/* the reference's own slot on a synthetic CTU state: the picture plays the CTU buffer, the two availability words are
+ * placed in the progress field where the slot looks them up (rcn_lmcs.c:325-331) */
+int
+ovref_lmcs_chroma_scale(const uint16_t *src, int stride, unsigned abv_mask, unsigned lft_mask,
+                        const OVOLmcsLuts *luts, const OVOLmcsData *d, int bitdepth)
+{
+    OVCTUDec *c;
+    OVLMCSData data;
+    struct CTUBitField pf;
+    int ret;
+    ctudec_init(&c);
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 1, bitdepth);
+    memset(&data, 0, sizeof(data));
+    data.lmcs_min_bin_idx = d->lmcs_min_bin_idx;
+    data.lmcs_delta_max_bin_idx = d->lmcs_delta_max_bin_idx;
+    data.lmcs_delta_cw_prec_minus1 = d->lmcs_delta_cw_prec_minus1;
+    memcpy(data.lmcs_delta_abs_cw, d->lmcs_delta_abs_cw, sizeof(data.lmcs_delta_abs_cw));
+    memcpy(data.lmcs_delta_sign_cw_flag, d->lmcs_delta_sign_cw_flag, sizeof(data.lmcs_delta_sign_cw_flag));
+    data.lmcs_delta_abs_crs = d->lmcs_delta_abs_crs;
+    data.lmcs_delta_sign_crs_flag = d->lmcs_delta_sign_crs_flag;
+    c->rcn_funcs.rcn_init_lmcs(&c->lmcs_info, &data);
+    if (memcmp(c->lmcs_info.luts, luts, sizeof(*luts))) abort();      /* same LUTs as the caller's */
+    memset(&pf, 0, sizeof(pf));
+    pf.hfield[0] = (uint64_t)abv_mask << 1;
+    pf.vfield[0] = (uint64_t)lft_mask << 1;
+    c->rcn_funcs.rcn_lmcs_compute_chroma_scale(&c->lmcs_info, (int16_t)stride, &pf, src, 0, 0);
+    ret = (int16_t)c->lmcs_info.lmcs_chroma_scale;
+    free(c->lmcs_info.luts);
+    free(c);
+    return ret;
+}
+
 void
 ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
 {

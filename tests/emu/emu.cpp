@@ -9,6 +9,8 @@
 #include "../../openvvc_b200/csrc/dbf_kernels.h"
 #include "../../openvvc_b200/csrc/intra_host.h"
 
+static const int16_t *emu_tr_scales = NULL;     // LMCS chroma scales of the running emu_recon_picture call
+
 template <int GROUP>
 static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,
                           const TbItemDev *items, int n, const int16_t *arena, const OVGPUTuSlice *sl)
@@ -20,6 +22,7 @@ static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int b
     a.bitdepth = bitdepth;
     a.cmds = (const TuCmdDev *)cmds; a.items = items; a.nb_items = n; a.arena = arena;
     a.dep_quant = sl->dep_quant; a.sh_ts_disabled = sl->sh_ts_disabled; a.ict_type = sl->ict_type;
+    a.scales = emu_tr_scales;
     ovd_emulate<K>(a, ovd_dim3((n + K::GROUPS - 1) / K::GROUPS, 1, 1), K::SMEM_BYTES);
 }
 
@@ -184,58 +187,72 @@ int emu_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdepth
     return 0;
 }
 
+static void emu_intra_launch(uint16_t *const planes[3], const int stride[3], int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds,
+                             const uint32_t *order, int cnt, int plane)
+{
+    IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
+                       (const IntraCmdDev *)cmds, order, cnt, plane };
+    ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, plane ? 2 : 1, 1), IntraK::SMEM_BYTES);
+}
+
+struct EmuLevels {
+    std::vector<uint32_t> order[2], start[2];
+    IntraLevels lv;
+    EmuLevels(int n) { for (int p = 0; p < 2; p++) { order[p].resize(n + 1); start[p].resize(n + 3); lv.order[p] = order[p].data(); lv.start[p] = start[p].data(); } }
+};
+
 int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
 {
     for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
-    std::vector<uint32_t> order(n + 1), level_start(n + 3);
-    int nl = intra_build_levels(order.data(), level_start.data(), n + 1, cmds, n, w, h);
-    if (nl < 0) return -1000000;
-    int has_chroma = 0, has_cclm = 0;
-    for (int i = 0; i < n; i++)
-        if (cmds[i].flags & OVGPU_INTRA_CHROMA) { has_chroma = 1; has_cclm |= cmds[i].mode_c >= 67; }
-    intra_for_each_launch(nl, level_start.data(), has_chroma, has_cclm, [&](int start, int cnt, int comp0, int ncomp) {
-        IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
-                           (const IntraCmdDev *)cmds, order.data() + start, cnt, comp0 };
-        ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, ncomp, 1), IntraK::SMEM_BYTES);
+    EmuLevels L(n);
+    if (intra_build_levels(&L.lv, n + 1, cmds, n, w, h)) return -1000000;
+    intra_for_each_launch(&L.lv, [&](int plane, int start, int cnt) {
+        emu_intra_launch(planes, stride, log2_ctu, bitdepth, cmds, L.lv.order[plane] + start, cnt, plane);
         return 0;
     });
-    return nl;
+    return L.lv.nb[0] + L.lv.nb[1];
 }
 
 // ovgpu_recon_picture's schedule (intra_host.h: recon_for_each_launch; tr_host.h: tu_build_grouped_items) on the emulated kernels
 int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth,
                       const OVGPUIntraCmd *cmds, int n, const OVGPUTuCmd *tus, int nb_tus, const int16_t *arena, size_t nb_coeffs,
-                      int dep_quant, int sh_ts_disabled, int ict_type)
+                      int dep_quant, int sh_ts_disabled, int ict_type,
+                      const OVGPULmcsAnchor *anchors, int nb_anchors, const OVGPULmcsLuts *luts, const OVGPULmcsData *lmcs)
 {
     for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
     for (int i = 0; i < nb_tus; i++) if (tu_check_cmd(&tus[i], nb_coeffs)) return -(100000 + i);
     const int w_u = w >> 2, h_u = h >> 2;
-    std::vector<uint32_t> order(n + 1), level_start(n + 3);
+    EmuLevels L(n);
     std::vector<uint16_t> map_l((size_t)w_u * h_u), map_c((size_t)w_u * h_u);
-    int nl = intra_build_levels(order.data(), level_start.data(), n + 1, cmds, n, w, h, map_l.data(), map_c.data());
-    if (nl < 0) return -1000000;
-    int has_chroma = 0, has_cclm = 0;
-    for (int i = 0; i < n; i++)
-        if (cmds[i].flags & OVGPU_INTRA_CHROMA) { has_chroma = 1; has_cclm |= cmds[i].mode_c >= 67; }
+    if (intra_build_levels(&L.lv, n + 1, cmds, n, w, h, map_l.data(), map_c.data())) return -1000000;
     std::vector<TbItemDev> items(3 * (size_t)nb_tus + 1);
+    std::vector<int16_t> scales(nb_anchors + 1);
     TuGroups g;
     memset(&g, 0, sizeof(g));
-    if (tu_build_grouped_items(items.data(), &g, tus, nb_tus, map_l.data(), map_c.data(), w_u, nl, has_cclm ? 2 : 1) < 0) return -1000001;
+    if (tu_build_grouped_items(items.data(), &g, tus, nb_tus, map_l.data(), map_c.data(), w_u, L.lv.nb[0], L.lv.nb[1]) < 0) return -1000001;
     OVGPUTuSlice sl = { (uint8_t)dep_quant, (uint8_t)sh_ts_disabled, (uint8_t)ict_type, 0 };
-    recon_for_each_launch(nl, level_start.data(), has_chroma, has_cclm,
-        [&](int start, int cnt, int comp0, int ncomp) {
-            IntraK::Args a = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
-                               (const IntraCmdDev *)cmds, order.data() + start, cnt, comp0 };
-            ovd_emulate<IntraK>(a, ovd_dim3((cnt + IntraK::WARPS - 1) / IntraK::WARPS, ncomp, 1), IntraK::SMEM_BYTES);
+    emu_tr_scales = nb_anchors ? scales.data() : NULL;
+    recon_for_each_launch(&L.lv,
+        [&](int plane, int start, int cnt) {
+            emu_intra_launch(planes, stride, log2_ctu, bitdepth, cmds, L.lv.order[plane] + start, cnt, plane);
             return 0;
         },
         [&](int grp) {
             if (g.n_small[grp]) emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + g.start_small[grp], g.n_small[grp], arena, &sl);
             if (g.n_large[grp]) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + g.start_large[grp], g.n_large[grp], arena, &sl);
             return 0;
+        },
+        [&]() {
+            if (!nb_anchors) return 0;
+            LmcsScaleK::Args a = { planes[0], stride[0], bitdepth, (const LmcsAnchorDev *)anchors, nb_anchors, scales.data(), luts->wnd_bnd,
+                                   lmcs->lmcs_min_bin_idx, 16 - lmcs->lmcs_delta_max_bin_idx,
+                                   lmcs->lmcs_delta_sign_crs_flag ? -(int)lmcs->lmcs_delta_abs_crs : (int)lmcs->lmcs_delta_abs_crs };
+            ovd_emulate<LmcsScaleK>(a, ovd_dim3((nb_anchors + LmcsScaleK::WARPS - 1) / LmcsScaleK::WARPS, 1, 1), LmcsScaleK::SMEM_BYTES);
+            return 0;
         });
+    emu_tr_scales = NULL;
     tu_groups_free(&g);
-    return nl;
+    return L.lv.nb[0] + L.lv.nb[1];
 }
 
 }

@@ -78,7 +78,7 @@ def test_emulated_kernel_matches_oracle(pi, emu, w, h, log2, chroma):
             got, nl = helpers_intra.emu_intra(emu, planes, cmds, log2)
         finally:
             emu.emu_set_reverse_block_order(0)
-        assert all((got[k] == want[k]).all() for k in range(3)) and 1 < nl <= len(cmds)
+        assert all((got[k] == want[k]).all() for k in range(3)) and 1 < nl <= 2 * len(cmds)          # luma levels + chroma levels
 
 
 def test_chroma_only_and_luma_only_commands(pi, emu):

@@ -20,12 +20,32 @@ def pr(oracle):
     return pyoracle_recon
 
 
-def _case(w, h, log2, ict, p_cclm):
+class Lm:
+    """LMCS state of a case: with chroma residual scaling on (ict_type & 1) the scales are NOT given with the transform
+    units: they are derived from the reconstructed luma at the recorded anchors, by the oracle in CU order and by the product
+    between its luma and chroma passes"""
+    def __init__(self, po, cmds, tus, log2, ict, seed):
+        self.on = bool(ict & 1)
+        self.anchors, self.luts, self.data, self.tus = None, None, None, tus
+        if self.on:
+            d = synth.lmcs_data(seed)
+            self.data = po.make_lmcs_data(d)
+            self.luts = po.lmcs_build_luts(d, impl="port")
+            self.anchors, self.tus = synth_recon.lmcs_anchors(cmds, tus, log2)
+            self.tus["chroma_scale"] = 77                    # must not be used
+
+
+def _case(po, w, h, log2, ict, p_cclm):
     cmds, tus, arena = synth_recon.recon_case(w, h, 9 * w + h, log2, ict_type=ict, p_cclm=p_cclm)
-    return synth.planes(w, h, 3 * w + h), cmds, tus, arena
+    lm = Lm(po, cmds, tus, log2, ict, 5 * w + h)
+    return synth.planes(w, h, 3 * w + h), cmds, lm.tus, arena, lm
 
 
-def _emu(emu, planes, cmds, tus, arena, log2, ict):
+def _want(pr, planes, cmds, tus, arena, log2, ict, lm):
+    return pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict, anchors=lm.anchors, luts=lm.luts, lmcs_data=lm.data)
+
+
+def _emu(emu, planes, cmds, tus, arena, log2, ict, lm):
     out = [p.copy() for p in planes]
     h, w = out[0].shape
     gc = np.ascontiguousarray(cmds[cmds["flags"] != 0])
@@ -33,15 +53,21 @@ def _emu(emu, planes, cmds, tus, arena, log2, ict):
     ptrs = (C.c_void_p * 3)(*[p.ctypes.data for p in out])
     strides = (C.c_int * 3)(*[p.strides[0] // 2 for p in out])
     nl = emu.emu_recon_picture(ptrs, strides, w, h, log2, 10, gc.ctypes.data_as(C.c_void_p), len(gc), gt.ctypes.data_as(C.c_void_p), len(gt),
-                               arena.ctypes.data_as(C.c_void_p), C.c_size_t(len(arena)), 1, 0, ict)
+                               arena.ctypes.data_as(C.c_void_p), C.c_size_t(len(arena)), 1, 0, ict,
+                               lm.anchors.ctypes.data_as(C.c_void_p) if lm.on else None, len(lm.anchors) if lm.on else 0,
+                               C.byref(lm.luts) if lm.on else None, C.byref(lm.data) if lm.on else None)
     assert nl >= 0, nl
     return out, nl
 
 
 @pytest.mark.parametrize("w,h,log2,ict,p_cclm", CASES, ids=IDS)
-def test_emulated_schedule_matches_cu_order(pr, emu, w, h, log2, ict, p_cclm):
-    planes, cmds, tus, arena = _case(w, h, log2, ict, p_cclm)
-    want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict)
+def test_emulated_schedule_matches_cu_order(oracle, pr, emu, w, h, log2, ict, p_cclm):
+    planes, cmds, tus, arena, lm = _case(oracle, w, h, log2, ict, p_cclm)
+    want = _want(pr, planes, cmds, tus, arena, log2, ict, lm)
+    if lm.on:                                                   # the derived scales vary over the picture and matter
+        flat = tus.copy(); flat["flags"] &= 0xf7; flat["chroma_scale"] = 2048
+        other = pr.recon_picture([p.copy() for p in planes], cmds, flat, arena, log2, ict_type=ict)
+        assert (other[1] != want[1]).any() and (other[0] == want[0]).all()
     # the order matters: all predictions first, then all residuals, is a different picture
     from oracle import pyoracle_intra as pi, pyoracle_tr as pt
     naive = pi.intra_picture([p.copy() for p in planes], cmds, log2, impl="port")
@@ -50,7 +76,7 @@ def test_emulated_schedule_matches_cu_order(pr, emu, w, h, log2, ict, p_cclm):
     for rev in (0, 1):
         emu.emu_set_reverse_block_order(rev)
         try:
-            got, nl = _emu(emu, planes, cmds, tus, arena, log2, ict)
+            got, nl = _emu(emu, planes, cmds, tus, arena, log2, ict, lm)
         finally:
             emu.emu_set_reverse_block_order(0)
         for k in range(3):
@@ -58,21 +84,41 @@ def test_emulated_schedule_matches_cu_order(pr, emu, w, h, log2, ict, p_cclm):
         assert nl > 1
 
 
-def test_inter_only_picture_is_plain_residual(pr, emu):
-    """no intra commands: the schedule degenerates to the residual pass"""
-    planes, cmds, tus, arena = _case(416, 240, 7, 1, 0.0)
+@pytest.mark.parametrize("ict", [0, 1])
+def test_inter_only_picture_is_plain_residual(oracle, pr, emu, ict):
+    """no intra commands: the schedule degenerates to the residual pass (luma, chroma scales, chroma with LMCS)"""
+    planes, cmds, tus, arena, lm = _case(oracle, 416, 240, 7, ict, 0.0)
     cmds["flags"] = 0
-    want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, 7, ict_type=1)
-    got, nl = _emu(emu, planes, cmds, tus, arena, 7, 1)
+    want = _want(pr, planes, cmds, tus, arena, 7, ict, lm)
+    got, nl = _emu(emu, planes, cmds, tus, arena, 7, ict, lm)
     assert nl == 0 and all((got[k] == want[k]).all() for k in range(3))
+
+
+def test_chroma_scale_port_vs_compiled_reference(oracle, pr):
+    """rcn_lmcs_compute_chroma_scale: port == the reference's slot, incl. partial and non-contiguous availability masks"""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(5)
+    seen = set()
+    for t in range(200):
+        d = synth.lmcs_data(100 + t)
+        data, luts = oracle.make_lmcs_data(d), oracle.lmcs_build_luts(d, impl="port")
+        luma = synth.planes(256, 192, t)[0]
+        x0, y0 = 64 * int(rng.integers(1, 3)), 64
+        am = [0, 0xffff, 0x00ff, 0x0001, 0x7fff, 0x0f0f][int(rng.integers(0, 6))]
+        lm = [0, 0xffff, 0x003f, 0x0fff][int(rng.integers(0, 4))]
+        a = pr.lmcs_chroma_scale(luma, x0, y0, am, lm, luts, data, impl="port")
+        assert a == pr.lmcs_chroma_scale(luma, x0, y0, am, lm, luts, data, impl="ref")
+        seen.add(a)
+    assert len(seen) > 20
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("w,h,log2,ict,p_cclm", CASES + [(1920, 1080, 7, 1, 0.3)], ids=IDS + ["1080p"])
-def test_gpu_recon_matches_cu_order(pr, gpu_ctx, w, h, log2, ict, p_cclm):
+def test_gpu_recon_matches_cu_order(oracle, pr, gpu_ctx, w, h, log2, ict, p_cclm):
     from openvvc_b200 import api
-    planes, cmds, tus, arena = _case(w, h, log2, ict, p_cclm)
-    want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict)
+    planes, cmds, tus, arena, lm = _case(oracle, w, h, log2, ict, p_cclm)
+    want = _want(pr, planes, cmds, tus, arena, log2, ict, lm)
     gc = np.ascontiguousarray(cmds[cmds["flags"] != 0])
     gt = np.ascontiguousarray(tus[tus["cbf_mask"] != 0])
     pic = gpu_ctx.picture(w, h)
@@ -80,14 +126,23 @@ def test_gpu_recon_matches_cu_order(pr, gpu_ctx, w, h, log2, ict, p_cclm):
     ib = api.IntraBatch(gpu_ctx, max(1, len(gc)))
     ib.upload(gc, w, h, log2)
     tb = api.TuBatch(gpu_ctx, max(1, len(gt)), len(arena))
+    lmcs = None
+    if lm.on:
+        tb.set_anchors(lm.anchors)
+        gl = api.LmcsLuts()
+        C.memmove(C.byref(gl), C.byref(lm.luts), C.sizeof(gl))
+        lmcs = api.Lmcs(gpu_ctx, gl)
+        gd = api.LmcsData()
+        C.memmove(C.byref(gd), C.byref(lm.data), C.sizeof(gd))
+        lmcs.set_data(gd)
     tb.upload(gt, arena, 1, 0, ict)
-    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib)
+    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib, lmcs=lmcs)
     got = pic.download()
     for k in range(3):
         assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
     # a second run on a fresh prediction re-uses the binding; the plain residual entry point still works on a bound batch
     pic.upload(planes)
-    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib)
+    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib, lmcs=lmcs)
     got2 = pic.download()
     assert all((got2[k] == want[k]).all() for k in range(3))
     ib.destroy(); tb.destroy(); pic.destroy()
