@@ -25,7 +25,9 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["mc(uni/bi/bcw, bdof, dmvr, affine 4x4 + prof)+lmcs_fwd", "residual(dequant/lfnst/idct/jcbcr)", "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
+STAGES_IMPLEMENTED = ["recon[mc(uni/bi/bcw, bdof, dmvr, affine 4x4 + prof)+lmcs_fwd, then per plane: residual(dequant/lfnst/idct/jcbcr) of inter CUs, "
+                      "level-ordered intra(planar/dc/angular/mrl/mip/cclm/ciip)+residual, lmcs chroma scales from reconstructed luma]",
+                      "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
 def peaks():
@@ -74,7 +76,7 @@ class ClockSampler(threading.Thread):
 def make_workload(w, h, n_pics, seed0=5000):
     """Shared reference pictures + n_pics synthetic inter pictures: PU list, SAO and ALF decoder state
     (SURVEY.md §8(d) generators)."""
-    from openvvc_b200 import api, synth, synth_tu, synth_dbf
+    from openvvc_b200 import api, synth, synth_tu, synth_dbf, synth_recon
     refs = [[synth.planes(w, h, seed0 + 900 + i) for i in range(2)], [synth.planes(w, h, seed0 + 950 + i) for i in range(2)]]
     pocs = [[8, 16], [16, 24]]
     lmcs = api.lmcs_build_luts(synth.lmcs_data(seed0))
@@ -86,12 +88,17 @@ def make_workload(w, h, n_pics, seed0=5000):
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
         cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15)
         cmds = cmds.astype(api.MC_CMD)
-        tus, coeffs = synth_tu.tu_commands(w, h, seed0 + 400 + i, 7, ict_type=1, legal=True, p_intra=0.1, min_log2=3, p_cbf=0.4)
+        # one CU partition for the residual and the intra side: 10 % intra CUs (MRL / MIP / CCLM among them), 4 % CIIP, every TU
+        # takes its LMCS chroma scale from the anchor in force (derived on the GPU from reconstructed luma)
+        icmds, tus, coeffs = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15, p_cclm=0.3,
+                                                    ict_type=1, p_cbf=0.4, p_mip=0.1)
+        anchors, tus = synth_recon.lmcs_anchors(icmds, tus, 7)
+        icmds = np.ascontiguousarray(icmds[icmds["flags"] != 0])
         blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
         dbf = synth_dbf.dbf_maps(w, h, blks, 7)
         pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, prof=prof, tus=tus, coeffs=coeffs,
-                         dbf_blks=blks, dbf=dbf))
-    return dict(refs=refs, pocs=pocs, lmcs=lmcs, pics=pics)
+                         dbf_blks=blks, dbf=dbf, icmds=icmds, anchors=anchors))
+    return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), pics=pics)
 
 
 def residual_bytes(tus):
@@ -125,7 +132,7 @@ def reference_step(po, wl, threads):
     """The reference's own CPU implementation (oracle/_ref: rcn_mcp_b, rcn_sao_filter_line, rcn_alf_filter_line
     through the SSE4.1/AVX2 function table) of the same stages, one picture per host thread (the reference's
     frame parallelism, ovdec.h:47).  Falls back to the C port only if oracle/_ref was not built."""
-    from oracle import pyoracle_tr as pt, pyoracle_df as pdf
+    from oracle import pyoracle_tr as pt, pyoracle_df as pdf, pyoracle_intra as pi
     impl = "ref" if po.ref_available() else "port"
     h, w = wl["refs"][0][0][0].shape
     luts = po.LmcsLuts()
@@ -137,6 +144,7 @@ def reference_step(po, wl, threads):
         rec = [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
         po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts, prof=p["prof"])
         pt.residual_picture(rec, p["tus"], p["coeffs"], 7, impl=impl, dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=1)
+        pi.intra_picture(rec, p["icmds"].copy(), 7, impl=impl, simd=1)       # same blocks, the reference's own slots (CU order)
         po.port().ovo_lmcs_reshape_plane(rec[0].ctypes.data_as(po.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(po.u16p), 10)
         if impl == "ref":
             pdf.dbf_picture_ref(rec, p["dbf_blks"], 7, simd=1)
@@ -182,7 +190,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(intra prediction, CIIP and GPM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(ISP, GPM, IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
@@ -245,23 +253,26 @@ def main():
         for pic, planes in zip(lst, src):
             pic.upload(planes)
     lmcs = api.Lmcs(ctx, wl["lmcs"])
+    lmcs.set_data(wl["lmcs_data"])
     dev = []
     for p in pics:
         d = dict(rec=ctx.picture(w, h), mid=ctx.picture(w, h), dst=ctx.picture(w, h),
                  alf=api.AlfParams(ctx, w, h, 7), sao=api.SaoParams(ctx, w, h, 7),
                  mc=api.McBatch(ctx, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
-                 tu=api.TuBatch(ctx, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(ctx, w, h, 7))
+                 tu=api.TuBatch(ctx, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(ctx, w, h, 7),
+                 intra=api.IntraBatch(ctx, max(1, len(p["icmds"]))))
         d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
         d["sao"].upload(p["sao"])
         d["mc"].upload(p["cmds"], prof=p["prof"])
+        d["tu"].set_anchors(p["anchors"])
         d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
+        d["intra"].upload(p["icmds"], w, h, 7)
         d["dbf"].upload(p["dbf"])
         dev.append(d)
     ctx.sync()
 
     def run_stages(d):
-        d["mc"].run(d["rec"], ref_pics, wl["pocs"], lmcs)
-        d["tu"].run(d["rec"])
+        api.recon_picture(ctx, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
         lmcs.reshape(d["rec"], forward=False)
         d["dbf"].run(d["rec"])
         d["sao"].run(d["mid"], d["rec"])
@@ -310,9 +321,10 @@ def main():
     launches = ctx.launch_count() - n0
 
     # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
-    stage_names = ("mc", "residual", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
+    stage_names = ("mc", "residual", "intra", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
     ctx.profile(True); ctx.profile_reset()
-    for _ in range(max(2, min(args.steps, 5))):
+    nprof = max(2, min(args.steps, 5))
+    for _ in range(nprof):
         step_device()
     prof = {s: ctx.profile_get(s) for s in stage_names}
     ctx.profile(False)
@@ -343,12 +355,13 @@ def main():
         for i, d in enumerate(dev):
             p, c = pics[i], e_ctx[i % n_ctx]
             d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c)
+            d["tu"].set_anchors(p["anchors"], ctx=c)
             d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c)
+            d["intra"].upload(p["icmds"], w, h, 7, ctx=c)
             d["dbf"].commit(0, 0, ctx=c)
             d["sao"].upload(p["sao"], ctx=c)
             d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c)
-            d["mc"].run(d["rec"], ref_pics, wl["pocs"], lmcs, ctx=c)
-            d["tu"].run(d["rec"], ctx=c)
+            api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
             lmcs.reshape(d["rec"], forward=False, ctx=c)
             d["dbf"].run(d["rec"], ctx=c)
             d["sao"].run(d["mid"], d["rec"], ctx=c)
@@ -382,16 +395,19 @@ def main():
         L, Cc = w * h * 2, w * h     # luma plane bytes, both chroma planes bytes
         # algorithmic bytes per launch: MC (dirs+1)*P, SAO 2P, ALF luma 2L, ALF chroma 2C
         alg = {"mc": (dirs + 1) * pbytes, "residual": float(np.mean([residual_bytes(p["tus"]) for p in pics])),
+               "intra": float(np.mean([3.0 * ((1 << p["icmds"]["log2_w"].astype(np.int64)) * (1 << p["icmds"]["log2_h"].astype(np.int64))).sum() for p in pics])),
                "lmcs": 2 * L, "dbf_v": 2 * pbytes, "dbf_h": 2 * pbytes, "sao": 2 * pbytes, "alf_luma": 2 * L, "alf_chroma": 2 * Cc}
         stages = {}
         for s in stage_names:
             t_ms, n = prof[s]
             if n:
-                avg = t_ms / n
-                stages[s] = {"avg_launch_ms": avg, "algorithmic_bytes": alg[s], "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9,
-                             "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
+                # per PICTURE: a stage may take several launches per picture (the residual and intra stages run one
+                # group of launches per dependency level, the MC stage one kernel per tool)
+                avg = t_ms / (nprof * P)
+                stages[s] = {"avg_launch_ms": avg, "scopes_per_picture": n / (nprof * P), "algorithmic_bytes": alg[s],
+                             "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9, "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
-        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
+        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",

@@ -370,13 +370,15 @@ int  ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch
 /* ---- Reconstruction order  (replaces the CU loop of the reference: every coding unit is predicted and then gets its
  *      residual through rcn_transform_tree before the next one is predicted, vcl_coding_unit.c -> rcn_res_wrap,
  *      rcn_transform_tree.c:1433; intra blocks read neighbours holding prediction + residual) --------------------------
- * One call per picture: motion compensation of `mc` (may be NULL), the residual of the transform units that lie outside
- * intra commands, then for every dependency level of `intra` (may be NULL) the intra predictions (CIIP blends) followed
- * by the residual of the transform units they cover -- with CCLM in the picture, luma (prediction + residual) before
- * chroma inside a level.  Transform units are matched to intra commands by position.  The result equals predicting and
- * adding the residual CU by CU in decode order.  Asynchronous. */
+ * One call per picture: motion compensation of `mc` (may be NULL); then plane by plane (luma, then Cb + Cr -- luma never
+ * reads chroma): the residual of the transform blocks that lie outside intra commands, then ONE dataflow launch in which
+ * every intra command of `intra` (may be NULL) is predicted (CIIP: blended) as soon as the units its reference samples come
+ * from are reconstructed, followed at once by the residual of the transform blocks it covers.  Between the planes the LMCS
+ * chroma scales of the batch's anchors are derived from the reconstructed luma.  Transform units are matched to intra
+ * commands by position.  The result equals predicting and adding the residual CU by CU in decode order.  Asynchronous.
+ * A TU batch used here is re-ordered for this schedule; commit it again before handing it to ovgpu_residual_picture. */
 int  ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *refs, const OVGPUMcBatch *mc,
-                         const OVGPULmcs *lmcs, OVGPUTuBatch *tu, const OVGPUIntraBatch *intra);
+                         const OVGPULmcs *lmcs, OVGPUTuBatch *tu, OVGPUIntraBatch *intra);
 
 #ifdef __cplusplus
 }

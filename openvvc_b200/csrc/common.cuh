@@ -74,13 +74,15 @@ struct StageScope {
 };
 
 // internal hooks between the stage files (reconstruction order, intra.cu <-> tr.cu)
-int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint16_t *map_l, const uint16_t *map_c,
-                         int w_u, int h_u, int nl_l, int nl_c);
+struct ReconArgs;
+int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint32_t *pos_l, const uint32_t *pos_c,
+                        int w_u, int h_u, const uint32_t *const order[2], const int nb[2]);
+int ovgpu_tu_run_inter(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int plane);
+void ovgpu_tu_recon_args(const OVGPUTuBatch *b, int plane, ReconArgs *a);
 int ovgpu_tu_derive_scales(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b, const uint16_t *d_wnd_bnd,
                            int min_idx, int max_idx_p1, int crs_offset);
 int ovgpu_tu_nb_anchors(const OVGPUTuBatch *b);
 int ovgpu_lmcs_scale_params(const OVGPULmcs *l, const uint16_t **d_wnd_bnd, int *min_idx, int *max_idx_p1, int *crs_offset);
-int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group);
 int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b);
 
 #define OVGPU_CEIL_DIV(a, b) (((a) + (b) - 1) / (b))

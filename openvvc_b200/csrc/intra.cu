@@ -2,7 +2,9 @@
 // Replaces the intra_pred / intra_pred_c slots (vvc_intra_pred, libovvc/rcn_intra.c:484; vvc_intra_pred_chroma, :1015)
 // for the intra blocks of a picture.
 #include "common.cuh"
+#define OVGPU_RECON_KERNEL_IMPL
 #include "intra_host.h"
+#include "recon_kernels.h"
 #include <stdlib.h>
 
 static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev) == 32, "intra command layout");
@@ -12,8 +14,13 @@ struct OVGPUIntraBatch {
     IntraCmdDev *h_cmds, *d_cmds;
     IntraLevels lv;                                 // per plane: order (pinned, 2 * max_cmds) and level starts (host only)
     uint32_t *h_order, *d_order;                    // [plane][max_cmds]
-    uint16_t *map_l, *map_c;                        // host only: level of the command covering each 4x4 unit (luma / chroma tree)
+    uint32_t *pos_l, *pos_c;                        // host only: 1 + queue position of the command covering each 4x4 unit (luma / chroma plane)
     size_t map_units;
+    // dataflow state of ovgpu_recon_picture (recon_kernels.h): pending word per unit and plane, queue heads, epoch
+    uint32_t *d_pend;                               // [plane][dev_units]
+    size_t dev_units;
+    int *d_counter;                                 // [2]
+    uint32_t epoch;
     uint64_t serial;
     StagingFence fence;
 };
@@ -50,7 +57,9 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_order) cudaFree(b->d_order);
     free(b->lv.start[0]);
-    free(b->map_l); free(b->map_c);
+    free(b->pos_l); free(b->pos_c);
+    if (b->d_pend) cudaFree(b->d_pend);
+    if (b->d_counter) cudaFree(b->d_counter);
     fence_destroy(&b->fence);
     free(b);
 }
@@ -68,14 +77,14 @@ int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntra
     b->serial++;
     const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
     if (units > b->map_units) {
-        free(b->map_l); free(b->map_c);
-        b->map_l = (uint16_t *)malloc(units * sizeof(uint16_t)); b->map_c = (uint16_t *)malloc(units * sizeof(uint16_t));
-        b->map_units = (b->map_l && b->map_c) ? units : 0;
-        if (!b->map_units) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra level maps");
+        free(b->pos_l); free(b->pos_c);
+        b->pos_l = (uint32_t *)malloc(units * sizeof(uint32_t)); b->pos_c = (uint32_t *)malloc(units * sizeof(uint32_t));
+        b->map_units = (b->pos_l && b->pos_c) ? units : 0;
+        if (!b->map_units) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra position maps");
     }
-    if (!nb_cmds) { memset(b->map_l, 0, units * sizeof(uint16_t)); memset(b->map_c, 0, units * sizeof(uint16_t)); return 0; }
+    if (!nb_cmds) { memset(b->pos_l, 0, units * sizeof(uint32_t)); memset(b->pos_c, 0, units * sizeof(uint32_t)); return 0; }
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
-    if (intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->map_l, b->map_c))
+    if (intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c))
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_order, b->h_order, sizeof(uint32_t) * 2 * b->max_cmds, cudaMemcpyHostToDevice, ctx->stream));
@@ -113,38 +122,90 @@ static int recon_scales(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *lmcs,
     return ovgpu_tu_derive_scales(ctx, pic, tu, bnd, mn, mx, off);
 }
 
+// the intra commands of plane p + the transform blocks they cover: one dataflow launch
+static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, const OVGPUTuBatch *tu, int p, int nb_items)
+{
+    if (!nb_items) return 0;
+    static int configured = 0, blocks_per_sm = 1;
+    if (!configured) {
+        cudaFuncSetAttribute(ovd_recon_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ovd_recon_kernel, 128, RECON_SMEM_BYTES) != cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 1;
+        configured = 1;
+    }
+    PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);
+    ReconArgs a;
+    memset(&a, 0, sizeof(a));
+    a.plane[0] = v0.p; a.plane[1] = v1.p; a.plane[2] = v2.p; a.pitch[0] = v0.pitch; a.pitch[1] = v1.pitch; a.pitch[2] = v2.pitch;
+    a.log2_ctu = b->log2_ctu; a.bitdepth = pic->bitdepth; a.plane_id = p; a.cmds = b->d_cmds; a.nb_items = nb_items;
+    ovgpu_tu_recon_args(tu, p, &a);
+    a.pend = b->d_pend + (size_t)p * b->dev_units; a.serial = b->epoch; a.w_u = pic->width >> 2; a.h_u = pic->height >> 2;
+    a.counter = b->d_counter + p;
+    const int max_ctas = ctx->num_sms * blocks_per_sm;
+    StageScope scope(ctx, OVGPU_STAGE_INTRA, 1);
+    ovd_recon_kernel<<<nb_items < max_ctas ? nb_items : max_ctas, 128, RECON_SMEM_BYTES, ctx->stream>>>(a);
+    OVGPU_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 /* Reconstruction of a picture in the reference's order: prediction of a CU, then its residual (coding_unit() ->
- * prediction -> rcn_transform_tree, vcl_coding_unit.c / rcn_transform_tree.c:1433), expressed as picture-level passes:
- * motion compensation, residual of the blocks outside intra CUs, then per dependency level intra prediction + residual. */
+ * prediction -> rcn_transform_tree, vcl_coding_unit.c / rcn_transform_tree.c:1433), expressed as picture-level passes, plane
+ * by plane (luma never reads chroma): motion compensation; luma residual of the blocks outside intra CUs; the luma intra
+ * commands with their residual as one dataflow launch (recon_kernels.h); the LMCS chroma scales from the reconstructed luma;
+ * then chroma the same way (CCLM reads finished luma). */
 int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *refs, const OVGPUMcBatch *mc,
-                        const OVGPULmcs *lmcs, OVGPUTuBatch *tu, const OVGPUIntraBatch *intra)
+                        const OVGPULmcs *lmcs, OVGPUTuBatch *tu, OVGPUIntraBatch *intra)
 {
     if (!ctx || !pic || (mc && !refs)) return OVGPU_EINVAL;
     int rc;
     if (mc && (rc = ovgpu_mc_picture(ctx, pic, refs, mc, lmcs)) != 0) return rc;
-    if (!intra || !intra->nb_cmds) {
-        // no intra blocks: one residual pass -- unless chroma scales have to be derived from the reconstructed luma first
-        if (!tu) return 0;
-        if (!ovgpu_tu_nb_anchors(tu)) return ovgpu_residual_picture(ctx, pic, tu);
-        if ((rc = ovgpu_tu_check_picture(ctx, pic, tu)) != 0) return rc;
-        if ((rc = ovgpu_tu_bind_levels(ctx, tu, 0, NULL, NULL, pic->width >> 2, pic->height >> 2, 0, 0)) != 0) return rc;
-        if ((rc = ovgpu_tu_run_group(ctx, pic, tu, 0)) != 0 || (rc = recon_scales(ctx, pic, lmcs, tu)) != 0) return rc;
-        return ovgpu_tu_run_group(ctx, pic, tu, 1);
-    }
-    if (pic->width != intra->pic_w || pic->height != intra->pic_h)
+    const int has_intra = intra && intra->nb_cmds;
+    if (!tu && !has_intra) return 0;
+    if (has_intra && (pic->width != intra->pic_w || pic->height != intra->pic_h))
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
-    if (tu) {
-        if ((rc = ovgpu_tu_check_picture(ctx, pic, tu)) != 0) return rc;
-        if ((rc = ovgpu_tu_bind_levels(ctx, tu, intra->serial, intra->map_l, intra->map_c, pic->width >> 2, pic->height >> 2,
-                                       intra->lv.nb[0], intra->lv.nb[1])) != 0) return rc;
+    if (!has_intra && !ovgpu_tu_nb_anchors(tu)) return ovgpu_residual_picture(ctx, pic, tu);      // one plain residual pass
+    OVGPUTuBatch *own_tu = NULL;
+    if (!tu) {          // prediction only: an empty residual batch keeps one code path
+        if ((rc = ovgpu_tu_batch_create(ctx, 1, 1, &own_tu)) != 0) return rc;
+        OVGPUTuSlice sl = { 0, 0, 0, 0 };
+        if ((rc = ovgpu_tu_batch_commit(ctx, own_tu, 0, 0, &sl)) != 0) { ovgpu_tu_batch_destroy(own_tu); return rc; }
+        tu = own_tu;
     }
-    return recon_for_each_launch(&intra->lv,
-        [&](int plane, int start, int n) {
+    const int w_u = pic->width >> 2, h_u = pic->height >> 2;
+    const uint32_t *order[2] = { has_intra ? intra->lv.order[0] : NULL, has_intra ? intra->lv.order[1] : NULL };
+    const int nb[2] = { has_intra ? (int)intra->lv.start[0][intra->lv.nb[0]] : 0, has_intra ? (int)intra->lv.start[1][intra->lv.nb[1]] : 0 };
+    rc = ovgpu_tu_check_picture(ctx, pic, tu);
+    if (!rc) rc = ovgpu_tu_bind_recon(ctx, tu, has_intra ? intra->serial : 0, has_intra ? intra->pos_l : NULL, has_intra ? intra->pos_c : NULL,
+                                      w_u, h_u, order, nb);
+    if (!rc && has_intra) {
+        // device state: pending words (never cleared: an epoch number marks the units of this run) and the queue heads
+        const size_t units = (size_t)w_u * h_u;
+        if (units > intra->dev_units) {
+            if (intra->d_pend) cudaFree(intra->d_pend);
+            intra->d_pend = NULL; intra->dev_units = 0;
+            if (cudaMalloc(&intra->d_pend, 2 * units * sizeof(uint32_t)) != cudaSuccess) rc = ovgpu_set_error(ctx, OVGPU_ENOMEM, "recon pending maps");
+            else { intra->dev_units = units; cudaMemsetAsync(intra->d_pend, 0, 2 * units * sizeof(uint32_t), ctx->stream); }
+        }
+        if (!rc && !intra->d_counter && cudaMalloc(&intra->d_counter, 2 * sizeof(int)) != cudaSuccess) rc = ovgpu_set_error(ctx, OVGPU_ENOMEM, "recon counters");
+        if (!rc) {
+            if (++intra->epoch == 0) intra->epoch = 1;
+            ReconArgs t0, t1;
+            ovgpu_tu_recon_args(tu, 0, &t0); ovgpu_tu_recon_args(tu, 1, &t1);
+            ReconPrepK::Args pa = { intra->d_cmds, { t0.ritems, t1.ritems }, { nb[0], nb[1] }, { intra->d_pend, intra->d_pend + intra->dev_units },
+                                    intra->d_counter, intra->epoch, w_u };
+            const int mx = nb[0] > nb[1] ? nb[0] : nb[1];
             StageScope scope(ctx, OVGPU_STAGE_INTRA, 1);
-            return launch_intra(ctx, pic, intra, plane, start, n);
-        },
-        [&](int group) { return tu ? ovgpu_tu_run_group(ctx, pic, tu, group) : 0; },
-        [&]() { return recon_scales(ctx, pic, lmcs, tu); });
+            cudaError_t e = ovd_launch<ReconPrepK>(pa, dim3(OVGPU_CEIL_DIV(mx, ReconPrepK::WARPS), 2, 1), 0, ctx->stream);
+            if (e != cudaSuccess) rc = ovgpu_set_error(ctx, OVGPU_ECUDA, "recon prep launch: %s", cudaGetErrorString(e));
+        }
+    }
+    for (int p = 0; p < 2 && !rc; p++) {
+        if (p == 1) rc = recon_scales(ctx, pic, lmcs, tu);
+        if (!rc) rc = ovgpu_tu_run_inter(ctx, pic, tu, p);
+        if (!rc && has_intra) rc = recon_plane(ctx, pic, intra, tu, p, nb[p]);
+    }
+    if (own_tu) { cudaStreamSynchronize(ctx->stream); ovgpu_tu_batch_destroy(own_tu); }
+    return rc;
 }
 
 } // extern "C"

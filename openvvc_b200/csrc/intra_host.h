@@ -28,8 +28,8 @@ static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 // block's reference samples (left column of 2h + 1 and above row of 2w + 1 samples, on the 4x4 luma-unit grid).
 // Per plane p (0 luma, 1 chroma): order[p][] = indices of the commands that have that plane, sorted by level (stable);
 // start[p][l] .. start[p][l + 1] = the blocks of level l (0-based); nb[p] = number of levels.
-// map_l / map_c (optional, w/4 x h/4 entries each) receive the 1-based level of the command covering each unit
-// (0 = none): the residual schedule (tr_host.h) places transform blocks with them.
+// pos_l / pos_c (optional, w/4 x h/4 entries each) receive 1 + the position in order[plane] of the command covering each
+// unit (0 = none): the residual schedule (tr_host.h) attaches transform blocks to commands with them.
 struct IntraLevels {
     int nb[2];
     uint32_t *order[2];      // n entries each
@@ -48,11 +48,11 @@ static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu,
 
 // Returns 0, or -1 (out of memory / more than max_levels levels).
 static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPUIntraCmd *cmds, int n,
-                                     int pic_w, int pic_h, uint16_t *map_l_out = NULL, uint16_t *map_c_out = NULL)
+                                     int pic_w, int pic_h, uint32_t *pos_l = NULL, uint32_t *pos_c = NULL)
 {
     const int w_u = pic_w >> 2, h_u = pic_h >> 2;
-    uint16_t *map[2] = { map_l_out ? map_l_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)),
-                         map_c_out ? map_c_out : (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)) };
+    uint32_t *pos[2] = { pos_l, pos_c };
+    uint16_t *map[2] = { (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)), (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)) };
     uint16_t *lvl = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (n > 0 ? n : 1));
     uint32_t *fill = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 3));
     int ret = -1;
@@ -87,11 +87,17 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
             for (int i = 0; i < n; i++) if (lv[i]) L->order[p][fill[lv[i]]++] = (uint32_t)i;
             for (int l = 0; l <= nb_levels; l++) start[l] = start[l + 1];       // 0-based
             L->nb[p] = nb_levels;
+            if (pos[p]) {
+                memset(pos[p], 0, (size_t)w_u * h_u * sizeof(uint32_t));
+                for (uint32_t q = 0; q < start[nb_levels]; q++) {
+                    const OVGPUIntraCmd *c = &cmds[L->order[p][q]];
+                    const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
+                    for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) pos[p][y * w_u + x] = q + 1;
+                }
+            }
         }
     }
-    free(fill); free(lvl);
-    if (!map_l_out) free(map[0]);
-    if (!map_c_out) free(map[1]);
+    free(fill); free(lvl); free(map[0]); free(map[1]);
     return ret;
 }
 
@@ -109,25 +115,3 @@ static inline int intra_for_each_launch(const IntraLevels *L, F f)
     return 0;
 }
 
-// Whole reconstruction order of a picture (replaces the reference's CU loop: prediction, then rcn_transform_tree per CU,
-// vcl_coding_unit.c / rcn_transform_tree.c:1433), plane by plane.  Luma: the transform blocks outside intra commands
-// (residual group 0: their predictions come from motion compensation, done before), then level by level the intra
-// predictions followed by the residual of the blocks they cover (group = level).  Then the LMCS chroma scales, which read
-// the reconstructed luma (fs).  Then chroma the same way (groups nb[0] + 1 ...).
-// fi(plane, first entry in order[plane], count), ft(residual group), fs() -> 0 on success
-template <typename FI, typename FT, typename FS>
-static inline int recon_for_each_launch(const IntraLevels *L, FI fi, FT ft, FS fs)
-{
-    int rc, base = 0;
-    for (int p = 0; p < 2; p++) {
-        if (p == 1 && (rc = fs()) != 0) return rc;
-        if ((rc = ft(base)) != 0) return rc;
-        for (int l = 0; l < L->nb[p]; l++) {
-            const int start = (int)L->start[p][l], n = (int)L->start[p][l + 1] - start;
-            if (n > 0 && (rc = fi(p, start, n)) != 0) return rc;
-            if ((rc = ft(base + l + 1)) != 0) return rc;
-        }
-        base += L->nb[p] + 1;
-    }
-    return 0;
-}

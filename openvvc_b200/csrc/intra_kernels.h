@@ -60,7 +60,8 @@ struct IntraK {
         const IntraCmdDev *cmds;
         const uint32_t *order;      // command indices of this level
         int nb;
-        int comp0;                  // component of grid row 0 (a level with CCLM blocks runs luma first, then Cb / Cr)
+        int comp0;                  // component of grid row 0 (luma levels: 0; chroma levels: 1, grid rows = Cb, Cr)
+        int warp_comps;             // 0, or (dataflow kernel, recon_kernels.h) the CTA owns ONE block: warp k predicts component comp0 + k, k < warp_comps
     };
     struct State { int dummy; };
 
@@ -317,8 +318,8 @@ struct IntraK {
     {
         (void)st; (void)bz;
         const int warp = tid >> 5, lane = tid & 31;
-        const int comp = a.comp0 + by;
-        const Blk b = load(a, bx * WARPS + warp, comp);
+        const int comp = a.warp_comps ? a.comp0 + warp : a.comp0 + by;
+        const Blk b = load(a, a.warp_comps ? (warp < a.warp_comps ? bx : a.nb) : bx * WARPS + warp, comp);
         if (!b.valid) return;
         uint16_t *plane = comp == 0 ? a.plane[0] : (comp == 1 ? a.plane[1] : a.plane[2]);
         const int pitch = comp == 0 ? a.pitch[0] : (comp == 1 ? a.pitch[1] : a.pitch[2]);

@@ -1,0 +1,167 @@
+// recon_kernels.h -- dependency-driven reconstruction of a picture's intra blocks (sm_100a).
+//
+// Reference behaviour: the CU loop -- every coding unit is predicted and gets its residual before the next one is predicted
+// (coding_unit -> prediction -> rcn_transform_tree, libovvc/vcl_coding_unit.c, libovvc/rcn_transform_tree.c:1433), because
+// intra prediction reads reconstructed neighbours.  On the CPU that is a serial chain per entry thread; here it is a
+// dataflow over the whole picture: the host sorts the intra commands of a plane topologically (by dependency level,
+// intra_host.h) and ONE launch per plane executes them -- every CTA repeatedly takes the next command from a device queue
+// (atomic counter, in sorted order), waits until the 4x4 units its reference samples come from are reconstructed (a
+// "pending" word per unit, acquire loads), runs the prediction phases of IntraK and the residual phases of TrK for that
+// block, and publishes its units (fence + release).  A command only ever waits on commands that precede it in the queue
+// order, and those have been taken by CTAs that are running, so the scheme cannot deadlock however few CTAs are resident.
+//
+// The kernel body re-uses the phase functions of intra_kernels.h / tr_kernels.h unchanged; tests/emu runs the same item
+// sequence serially (one "CTA", no waiting needed in queue order).
+#pragma once
+#include "intra_kernels.h"
+#include "tr_kernels.h"
+
+struct ReconItemDev {           // one intra command of one plane, in queue order
+    uint32_t cmd;               // index into the intra command array
+    uint32_t tb_start;          // its transform blocks: tb[tb_start .. tb_start + nb_tb)
+    uint16_t nb_tb;
+    uint16_t large;             // they are > 256 samples each (TrK<128>: one CTA per block) -- all blocks of a CU plane have one size
+};
+
+struct ReconArgs {
+    uint16_t *plane[3];
+    int pitch[3], log2_ctu, bitdepth;
+    int plane_id;                       // 0: luma commands, 1: chroma commands (Cb and Cr)
+    const IntraCmdDev *cmds;
+    const ReconItemDev *ritems;
+    int nb_items;
+    // residual
+    const TuCmdDev *tu_cmds;
+    const TbItemDev *tb;
+    const int16_t *arena;
+    int dep_quant, sh_ts_disabled, ict_type;
+    const int16_t *scales;
+    // dataflow state
+    uint32_t *pend;                     // per 4x4 unit of this plane: == serial while an intra command covering it is not reconstructed
+    uint32_t serial;
+    int w_u, h_u;
+    int *counter;                       // queue head
+};
+
+OVD IntraK::Args recon_intra_args(const ReconArgs &a, const uint32_t *one_cmd)
+{
+    IntraK::Args ia;
+    for (int c = 0; c < 3; c++) { ia.plane[c] = a.plane[c]; ia.pitch[c] = a.pitch[c]; }
+    ia.log2_ctu = a.log2_ctu; ia.bitdepth = a.bitdepth; ia.cmds = a.cmds; ia.order = one_cmd; ia.nb = 1;
+    ia.comp0 = a.plane_id; ia.warp_comps = a.plane_id ? 2 : 1;
+    return ia;
+}
+
+template <int GROUP>
+OVD typename TrK<GROUP>::Args recon_tr_args(const ReconArgs &a, const TbItemDev *items, int n)
+{
+    typename TrK<GROUP>::Args ta;
+    for (int c = 0; c < 3; c++) { ta.dst[c] = a.plane[c]; ta.dst_pitch[c] = a.pitch[c]; }
+    ta.bitdepth = a.bitdepth; ta.cmds = a.tu_cmds; ta.items = items; ta.nb_items = n; ta.arena = a.arena;
+    ta.dep_quant = a.dep_quant; ta.sh_ts_disabled = a.sh_ts_disabled; ta.ict_type = a.ict_type; ta.scales = a.scales;
+    return ta;
+}
+
+// marks the units of every intra command of a plane as pending and resets the queue head (grid.y = plane)
+struct ReconPrepK {
+    static const int THREADS = 128, MIN_BLOCKS = 8, PHASES = 1;
+    static const int WARPS = 4;
+    struct Args {
+        const IntraCmdDev *cmds;
+        const ReconItemDev *ritems[2];
+        int nb_items[2];
+        uint32_t *pend[2];
+        int *counter;                   // [2]
+        uint32_t serial;
+        int w_u;
+    };
+    struct State { int dummy; };
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)smem; (void)st; (void)bz;
+        const int warp = tid >> 5, lane = tid & 31, idx = bx * WARPS + warp, p = by;
+        if (bx == 0 && tid == 0) a.counter[p] = 0;
+        if (idx >= a.nb_items[p]) return;
+        const IntraCmdDev c = a.cmds[a.ritems[p][idx].cmd];
+        const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
+        for (int o = lane; o < nw * nh; o += 32) a.pend[p][(size_t)(yu + o / nw) * a.w_u + xu + o % nw] = a.serial;
+    }
+};
+
+#if !defined(OVGPU_HOST_EMU) && defined(OVGPU_RECON_KERNEL_IMPL)      // the one translation unit that launches it (intra.cu)
+__device__ __forceinline__ uint32_t recon_ld_acquire(const uint32_t *p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void recon_st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// One CTA = one worker.  Phases of IntraK / TrK are separated by CTA barriers exactly as ovd_kernel does.
+__global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
+{
+    extern __shared__ __align__(16) unsigned char ovd_smem[];
+    __shared__ int s_item;
+    const int tid = threadIdx.x;
+    IntraK::State ist; TrK<32>::State ts; TrK<128>::State tl;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(a.counter, 1);
+        __syncthreads();
+        const int i = s_item;
+        __syncthreads();
+        if (i >= a.nb_items) return;
+        const ReconItemDev it = a.ritems[i];
+        const IntraCmdDev c = a.cmds[it.cmd];
+        const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
+        {   // wait for the available neighbour units this block's reference samples come from: the left column from the
+            // corner down to 2h below the top (avail_cols: bit 1 + row inside the CTU), the above row over 2w (avail_rows)
+            const int um = ((1 << a.log2_ctu) >> 2) - 1, xl = xu & um, yl = yu & um;
+            for (int k = tid; k < 2 * nh + 1 + 2 * nw; k += 128) {
+                int ux, uy, bit;
+                if (k < 2 * nh + 1) { ux = xu - 1; uy = yu - 1 + k; bit = yl + k; bit = bit < 64 ? (int)((c.avail_cols >> bit) & 1) : 0; }
+                else { const int col = k - (2 * nh + 1); ux = xu + col; uy = yu - 1; bit = xl + col + 1; bit = bit < 64 ? (int)((c.avail_rows >> bit) & 1) : 0; }
+                if (bit && ux >= 0 && uy >= 0 && ux < a.w_u && uy < a.h_u) {
+                    const uint32_t *f = a.pend + (size_t)uy * a.w_u + ux;
+                    while (recon_ld_acquire(f) == a.serial) __nanosleep(64);
+                }
+            }
+            __syncthreads();
+            __threadfence();
+        }
+        // ---- prediction
+        const IntraK::Args ia = recon_intra_args(a, &a.ritems[i].cmd);
+        IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+        IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+        IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+        IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+        // ---- residual of the blocks this command covers
+        if (it.large) {
+            for (int k = 0; k < it.nb_tb; k++) {
+                const TrK<128>::Args ta = recon_tr_args<128>(a, a.tb + it.tb_start + k, 1);
+                TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+            }
+        } else {
+            for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS) {
+                const TrK<32>::Args ta = recon_tr_args<32>(a, a.tb + it.tb_start + k, ovd_min(TrK<32>::GROUPS, it.nb_tb - k));
+                TrK<32>::phase<0>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                TrK<32>::phase<1>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                TrK<32>::phase<2>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                TrK<32>::phase<3>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+            }
+        }
+        // ---- publish: every thread's stores are ordered before the barrier above; fence, then release the units
+        __threadfence();
+        for (int o = tid; o < nw * nh; o += 128) recon_st_release(a.pend + (size_t)(yu + o / nw) * a.w_u + xu + o % nw, 0u);
+    }
+}
+#endif
+
+static const int RECON_SMEM_BYTES = TrK<128>::SMEM_BYTES > IntraK::SMEM_BYTES ? (TrK<128>::SMEM_BYTES > TrK<32>::SMEM_BYTES ? TrK<128>::SMEM_BYTES : TrK<32>::SMEM_BYTES)
+                                                                              : (IntraK::SMEM_BYTES > TrK<32>::SMEM_BYTES ? IntraK::SMEM_BYTES : TrK<32>::SMEM_BYTES);

@@ -15,7 +15,9 @@ struct OVGPUTuBatch {
     int16_t *h_coeffs, *d_coeffs;
     StagingFence fence;
     // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h
-    TuGroups groups;
+    TuReconLists lists;
+    ReconItemDev *h_ritems, *d_ritems;  // [plane][max_ritems]
+    int max_ritems, nb_ritems[2];
     uint64_t serial, bound_serial, bound_intra_serial;
     // LMCS chroma scale anchors (ovgpu_tu_batch_set_anchors) and the scales LmcsScaleK derives for them
     LmcsAnchorDev *h_anchors, *d_anchors;
@@ -37,8 +39,6 @@ static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatc
     a.scales = b->nb_anchors ? b->d_scales : NULL;
     return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, ctx->stream);
 }
-
-int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group);
 
 extern "C" {
 
@@ -72,7 +72,8 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     if (b->d_items) cudaFree(b->d_items);
     if (b->d_coeffs) cudaFree(b->d_coeffs);
     fence_destroy(&b->fence);
-    tu_groups_free(&b->groups);
+    if (b->h_ritems) cudaFreeHost(b->h_ritems);
+    if (b->d_ritems) cudaFree(b->d_ritems);
     if (b->h_anchors) cudaFreeHost(b->h_anchors);
     if (b->d_anchors) cudaFree(b->d_anchors);
     if (b->d_scales) cudaFree(b->d_scales);
@@ -99,7 +100,7 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
     b->slice = *slice;
     b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
     b->serial++;
-    tu_groups_free(&b->groups);
+    b->lists.built = 0;
     for (int i = 0; i < nb_cmds; i++)
         if ((cmds[i].flags & OVGPU_TU_SCALE_ANCHOR) && cmds[i].scale_anchor >= b->nb_anchors)
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d names LMCS anchor %d of %d (set the anchors before the commands)",
@@ -163,10 +164,8 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
         if (c->x0 + (1 << c->log2_w) > pic->width || c->y0 + (1 << c->log2_h) > pic->height)
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
-    if (b->groups.nb_groups) {           // items were re-ordered for ovgpu_recon_picture: same blocks, group by group
-        for (int g = 0; g < b->groups.nb_groups; g++) { int rc = ovgpu_tu_run_group(ctx, pic, b, g); if (rc) return rc; }
-        return 0;
-    }
+    if (b->lists.built)
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "the batch is bound to ovgpu_recon_picture; commit it again to use ovgpu_residual_picture");
     const int nk = (b->nb_small > 0) + (b->nb_large > 0);
     if (!nk) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, nk);
@@ -178,32 +177,57 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
 } // extern "C"
 
 // ---- internal: residual in reconstruction order (called by ovgpu_recon_picture, intra.cu) ---------------------------
-int ovgpu_tu_bind_levels(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint16_t *map_l, const uint16_t *map_c,
-                         int w_u, int h_u, int nl_l, int nl_c)
+// order[p] / nb[p]: the intra commands of plane p in queue order (NULL / 0 without intra commands)
+int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint32_t *pos_l, const uint32_t *pos_c,
+                        int w_u, int h_u, const uint32_t *const order[2], const int nb[2])
 {
-    if (b->groups.nb_groups && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial) return 0;
+    if (b->lists.built && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial) return 0;
     for (int i = 0; i < b->nb_cmds; i++) {
         const TuCmdDev *c = &b->h_cmds[i];
         if ((c->x0 >> 2) >= w_u || (c->y0 >> 2) >= h_u) return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
-    const int n = tu_build_grouped_items(b->h_items, &b->groups, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, map_l, map_c, w_u, nl_l, nl_c);
-    if (n < 0) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "TU groups");
+    const int need = nb[0] > nb[1] ? nb[0] : nb[1];
+    if (need > b->max_ritems) {
+        if (b->h_ritems) cudaFreeHost(b->h_ritems);
+        if (b->d_ritems) cudaFree(b->d_ritems);
+        b->h_ritems = NULL; b->d_ritems = NULL; b->max_ritems = 0;
+        if (cudaMallocHost(&b->h_ritems, sizeof(ReconItemDev) * 2 * need) != cudaSuccess ||
+            cudaMalloc(&b->d_ritems, sizeof(ReconItemDev) * 2 * need) != cudaSuccess)
+            return ovgpu_set_error(ctx, OVGPU_ENOMEM, "recon item buffers");
+        b->max_ritems = need;
+    }
+    ReconItemDev *ritems[2] = { b->h_ritems, b->h_ritems + b->max_ritems };
+    for (int p = 0; p < 2; p++) {
+        b->nb_ritems[p] = nb[p];
+        for (int q = 0; q < nb[p]; q++) ritems[p][q].cmd = order[p][q];
+    }
+    const int n = tu_build_recon_lists(b->h_items, &b->lists, ritems, nb, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, pos_l, pos_c, w_u);
     if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (need) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_ritems, b->h_ritems, sizeof(ReconItemDev) * 2 * b->max_ritems, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
     b->bound_serial = b->serial; b->bound_intra_serial = intra_serial;
     return 0;
 }
 
-int ovgpu_tu_run_group(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int group)
+// residual of the transform blocks of plane p that lie outside intra commands
+int ovgpu_tu_run_inter(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int p)
 {
-    if (group < 0 || group >= b->groups.nb_groups) return 0;
-    const int ns = b->groups.n_small[group], nl = b->groups.n_large[group];
+    const int ns = b->lists.n_small[p], nl = b->lists.n_large[p];
     if (!(ns + nl)) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, (ns > 0) + (nl > 0));
-    if (ns) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items + b->groups.start_small[group], ns));
-    if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->groups.start_large[group], nl));
+    if (ns) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items + b->lists.start_small[p], ns));
+    if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->lists.start_large[p], nl));
     return 0;
+}
+
+// the residual side of the dataflow kernel's arguments for plane p
+void ovgpu_tu_recon_args(const OVGPUTuBatch *b, int p, ReconArgs *a)
+{
+    a->ritems = b->d_ritems + (size_t)p * b->max_ritems;
+    a->tu_cmds = b->d_cmds; a->tb = b->d_items; a->arena = b->d_coeffs;
+    a->dep_quant = b->slice.dep_quant; a->sh_ts_disabled = b->slice.sh_ts_disabled; a->ict_type = b->slice.ict_type;
+    a->scales = b->nb_anchors ? b->d_scales : NULL;
 }
 
 // the chroma scales of the batch's anchors from the reconstructed luma plane of pic (all luma must be done)

@@ -3,7 +3,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include "../../include/ovvc_b200.h"
-#include "tr_kernels.h"
+#include "recon_kernels.h"
 
 // Validates one command against the coefficient arena; returns 0 when well-formed.
 static inline int tu_check_cmd(const OVGPUTuCmd *c, size_t nb_coeffs)
@@ -51,38 +51,24 @@ static inline void tu_build_items(TbItemDev *small, TbItemDev *large, int *nb_sm
 
 // ---- reconstruction order ----------------------------------------------------------------------------------------
 // The reference reconstructs CU by CU: prediction, then rcn_transform_tree (vcl_coding_unit.c -> rcn_res_wrap), so an
-// intra block reads neighbours that already hold prediction + residual.  The picture-level schedule (intra_host.h:
-// recon_for_each_launch) keeps that order per plane by dependency LEVEL: transform blocks covered by an intra command run
-// right after that command's level; all others (inter CUs) run first.  `map_l` / `map_c` hold, per 4x4 luma unit, the
-// 1-based level of the intra command covering it (0 = none) for the luma / chroma plane.  Groups: luma blocks 0 .. nl_l,
-// chroma blocks nl_l + 1 .. nl_l + 1 + nl_c.
-struct TuGroups {
-    int nb_groups;
-    int *start_small, *n_small, *start_large, *n_large;   // per group, offsets into the re-ordered item array
+// intra block reads neighbours that already hold prediction + residual.  ovgpu_recon_picture keeps that order per plane:
+// the transform blocks that lie outside intra commands (inter CUs, whose prediction motion compensation wrote before) run
+// first as ordinary launches; the blocks covered by an intra command are attached to that command and run inside the
+// dataflow kernel right after its prediction (recon_kernels.h).  `pos_l` / `pos_c` hold, per 4x4 luma unit, 1 + the queue
+// position of the intra command covering it in the luma / chroma plane (0 = none).
+struct TuReconLists {
+    int built;
+    int start_small[2], n_small[2], start_large[2], n_large[2];    // [plane] blocks outside intra commands
+    int nb_tb;                                                     // all transform blocks of the batch
 };
 
-static inline int tu_group_of(const OVGPUTuCmd *c, int kind, const uint16_t *map_l, const uint16_t *map_c, int w_u, int nl_l)
+// items: room for every transform block of the batch; ritems[p]: one entry per intra command of plane p in queue order
+// (cmd already filled by the caller), receives the block lists.  Returns the number of blocks.
+static inline int tu_build_recon_lists(TbItemDev *items, TuReconLists *g, ReconItemDev *const ritems[2], const int nb_ritems[2],
+                                       const OVGPUTuCmd *cmds, int n, const uint32_t *pos_l, const uint32_t *pos_c, int w_u)
 {
-    const uint16_t *m = kind == 0 ? map_l : map_c;
-    const int lvl = m ? m[(size_t)(c->y0 >> 2) * w_u + (c->x0 >> 2)] : 0;
-    return kind == 0 ? lvl : nl_l + 1 + lvl;
-}
-
-static inline void tu_groups_free(TuGroups *g)
-{
-    free(g->start_small); g->start_small = g->n_small = g->start_large = g->n_large = NULL; g->nb_groups = 0;
-}
-
-// items: room for every transform block of the batch.  Returns the number of items or -1 (out of memory).
-static inline int tu_build_grouped_items(TbItemDev *items, TuGroups *g, const OVGPUTuCmd *cmds, int n,
-                                         const uint16_t *map_l, const uint16_t *map_c, int w_u, int nl_l, int nl_c)
-{
-    tu_groups_free(g);
-    const int ng = nl_l + nl_c + 2;
-    int *mem = (int *)calloc((size_t)4 * ng, sizeof(int));
-    if (!mem) return -1;
-    g->nb_groups = ng;
-    g->start_small = mem; g->n_small = mem + ng; g->start_large = mem + 2 * ng; g->n_large = mem + 3 * ng;
+    memset(g, 0, sizeof(*g));
+    for (int p = 0; p < 2; p++) for (int q = 0; q < nb_ritems[p]; q++) { ritems[p][q].tb_start = 0; ritems[p][q].nb_tb = 0; ritems[p][q].large = 0; }
     for (int pass = 0; pass < 2; pass++) {
         for (int i = 0; i < n; i++) {
             const OVGPUTuCmd *c = &cmds[i];
@@ -94,23 +80,32 @@ static inline int tu_build_grouped_items(TbItemDev *items, TuGroups *g, const OV
                 if (c->cbf_mask & 0x01) kinds[nk++] = 2;
             }
             for (int k = 0; k < nk; k++) {
-                const int s = c->log2_w + c->log2_h - (kinds[k] ? 2 : 0);
-                const int grp = tu_group_of(c, kinds[k], map_l, map_c, w_u, nl_l);
-                if (pass == 0) { if (s <= 8) g->n_small[grp]++; else g->n_large[grp]++; }
-                else {
-                    TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };
-                    if (s <= 8) items[g->start_small[grp] + g->n_small[grp]++] = it;
-                    else        items[g->start_large[grp] + g->n_large[grp]++] = it;
+                const int p = kinds[k] != 0, large = c->log2_w + c->log2_h - (p ? 2 : 0) > 8;
+                const uint32_t *m = p ? pos_c : pos_l;
+                const uint32_t pos = m ? m[(size_t)(c->y0 >> 2) * w_u + (c->x0 >> 2)] : 0;
+                TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };
+                if (!pos) {
+                    if (pass == 0) { if (large) g->n_large[p]++; else g->n_small[p]++; }
+                    else if (large) items[g->start_large[p] + g->n_large[p]++] = it;
+                    else            items[g->start_small[p] + g->n_small[p]++] = it;
+                } else {
+                    ReconItemDev *r = &ritems[p][pos - 1];
+                    if (pass == 0) { r->nb_tb++; r->large = (uint16_t)large; }
+                    else items[r->tb_start + r->nb_tb++] = it;
                 }
             }
         }
         if (pass == 0) {
             int acc = 0;
-            for (int q = 0; q < ng; q++) {
-                g->start_small[q] = acc; acc += g->n_small[q]; g->n_small[q] = 0;
-                g->start_large[q] = acc; acc += g->n_large[q]; g->n_large[q] = 0;
+            for (int p = 0; p < 2; p++) {
+                g->start_small[p] = acc; acc += g->n_small[p]; g->n_small[p] = 0;
+                g->start_large[p] = acc; acc += g->n_large[p]; g->n_large[p] = 0;
             }
+            for (int p = 0; p < 2; p++)
+                for (int q = 0; q < nb_ritems[p]; q++) { ritems[p][q].tb_start = (uint32_t)acc; acc += ritems[p][q].nb_tb; ritems[p][q].nb_tb = 0; }
+            g->nb_tb = acc;
         }
     }
-    return ng ? g->start_large[ng - 1] + g->n_large[ng - 1] : 0;
+    g->built = 1;
+    return g->nb_tb;
 }

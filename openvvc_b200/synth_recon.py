@@ -7,12 +7,12 @@ from . import synth, synth_intra, synth_tu
 
 
 def recon_case(w, h, seed, log2_ctu=7, min_log2=2, p_inter=0.4, p_ciip=0.1, p_mrl=0.15, p_cclm=0.3, collocated=False, ict_type=0,
-               p_cbf=0.6, chroma=True):
+               p_cbf=0.6, chroma=True, p_mip=0.0):
     """Returns (intra cmds incl. flags == 0 placeholders, tu cmds, arena); cmds[i] and tus[i] are the same coding unit."""
     rng = np.random.default_rng(seed)
     blocks = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(6, log2_ctu), p_split=0.5)
     cmds = synth_intra.intra_commands(w, h, seed + 1, log2_ctu, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm,
-                                      collocated=collocated, p_inter=p_inter, blocks=blocks)
+                                      collocated=collocated, p_inter=p_inter, blocks=blocks, p_mip=p_mip)
     cmds = synth_intra.availability(w, h, cmds, log2_ctu)
     is_intra = (cmds["flags"] != 0) & ((cmds["flags"] & synth_intra.INTRA_CIIP) == 0)
     tus, arena = synth_tu.tu_commands(w, h, seed + 2, log2_ctu, ict_type=ict_type, p_cbf=p_cbf, legal=True, blocks=blocks,

@@ -213,7 +213,9 @@ int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int
     return L.lv.nb[0] + L.lv.nb[1];
 }
 
-// ovgpu_recon_picture's schedule (intra_host.h: recon_for_each_launch; tr_host.h: tu_build_grouped_items) on the emulated kernels
+// ovgpu_recon_picture's schedule on the emulated kernels: the same host lists (intra_host.h, tr_host.h), the same per-item
+// sequence as ovd_recon_kernel (recon_kernels.h) -- prediction phases, then the residual phases of the blocks the command
+// covers -- executed serially in queue order, where every dependency is already satisfied (no waiting to emulate).
 int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth,
                       const OVGPUIntraCmd *cmds, int n, const OVGPUTuCmd *tus, int nb_tus, const int16_t *arena, size_t nb_coeffs,
                       int dep_quant, int sh_ts_disabled, int ict_type,
@@ -223,35 +225,64 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
     for (int i = 0; i < nb_tus; i++) if (tu_check_cmd(&tus[i], nb_coeffs)) return -(100000 + i);
     const int w_u = w >> 2, h_u = h >> 2;
     EmuLevels L(n);
-    std::vector<uint16_t> map_l((size_t)w_u * h_u), map_c((size_t)w_u * h_u);
-    if (intra_build_levels(&L.lv, n + 1, cmds, n, w, h, map_l.data(), map_c.data())) return -1000000;
+    std::vector<uint32_t> pos_l((size_t)w_u * h_u), pos_c((size_t)w_u * h_u);
+    if (intra_build_levels(&L.lv, n + 1, cmds, n, w, h, pos_l.data(), pos_c.data())) return -1000000;
+    const int nb[2] = { (int)L.lv.start[0][L.lv.nb[0]], (int)L.lv.start[1][L.lv.nb[1]] };
     std::vector<TbItemDev> items(3 * (size_t)nb_tus + 1);
+    std::vector<ReconItemDev> ri[2] = { std::vector<ReconItemDev>(nb[0] + 1), std::vector<ReconItemDev>(nb[1] + 1) };
+    for (int p = 0; p < 2; p++) for (int q = 0; q < nb[p]; q++) ri[p][q].cmd = L.lv.order[p][q];
+    ReconItemDev *rip[2] = { ri[0].data(), ri[1].data() };
+    TuReconLists g;
+    tu_build_recon_lists(items.data(), &g, rip, nb, tus, nb_tus, pos_l.data(), pos_c.data(), w_u);
     std::vector<int16_t> scales(nb_anchors + 1);
-    TuGroups g;
-    memset(&g, 0, sizeof(g));
-    if (tu_build_grouped_items(items.data(), &g, tus, nb_tus, map_l.data(), map_c.data(), w_u, L.lv.nb[0], L.lv.nb[1]) < 0) return -1000001;
     OVGPUTuSlice sl = { (uint8_t)dep_quant, (uint8_t)sh_ts_disabled, (uint8_t)ict_type, 0 };
     emu_tr_scales = nb_anchors ? scales.data() : NULL;
-    recon_for_each_launch(&L.lv,
-        [&](int plane, int start, int cnt) {
-            emu_intra_launch(planes, stride, log2_ctu, bitdepth, cmds, L.lv.order[plane] + start, cnt, plane);
-            return 0;
-        },
-        [&](int grp) {
-            if (g.n_small[grp]) emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + g.start_small[grp], g.n_small[grp], arena, &sl);
-            if (g.n_large[grp]) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + g.start_large[grp], g.n_large[grp], arena, &sl);
-            return 0;
-        },
-        [&]() {
-            if (!nb_anchors) return 0;
+    // the pending words as ReconPrepK leaves them (checked below: every unit is released exactly by its command)
+    std::vector<uint32_t> pend(2 * (size_t)w_u * h_u, 0);
+    int counter[2] = { -1, -1 };
+    {
+        ReconPrepK::Args pa = { (const IntraCmdDev *)cmds, { rip[0], rip[1] }, { nb[0], nb[1] }, { pend.data(), pend.data() + (size_t)w_u * h_u }, counter, 7u, w_u };
+        const int mx = nb[0] > nb[1] ? nb[0] : nb[1];
+        if (mx) ovd_emulate<ReconPrepK>(pa, ovd_dim3((mx + ReconPrepK::WARPS - 1) / ReconPrepK::WARPS, 2, 1), 0);
+    }
+    for (int p = 0; p < 2; p++) {
+        if (p == 1 && nb_anchors) {
             LmcsScaleK::Args a = { planes[0], stride[0], bitdepth, (const LmcsAnchorDev *)anchors, nb_anchors, scales.data(), luts->wnd_bnd,
                                    lmcs->lmcs_min_bin_idx, 16 - lmcs->lmcs_delta_max_bin_idx,
                                    lmcs->lmcs_delta_sign_crs_flag ? -(int)lmcs->lmcs_delta_abs_crs : (int)lmcs->lmcs_delta_abs_crs };
             ovd_emulate<LmcsScaleK>(a, ovd_dim3((nb_anchors + LmcsScaleK::WARPS - 1) / LmcsScaleK::WARPS, 1, 1), LmcsScaleK::SMEM_BYTES);
-            return 0;
-        });
+        }
+        if (g.n_small[p]) emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + g.start_small[p], g.n_small[p], arena, &sl);
+        if (g.n_large[p]) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + g.start_large[p], g.n_large[p], arena, &sl);
+        for (int q = 0; q < nb[p]; q++) {
+            const ReconItemDev &it = ri[p][q];
+            const OVGPUIntraCmd &c = cmds[it.cmd];
+            const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
+            uint32_t *pd = pend.data() + (size_t)p * w_u * h_u;
+            // what the kernel would wait for must already be released in queue order
+            {
+                const int um = ((1 << log2_ctu) >> 2) - 1, xl = xu & um, yl = yu & um;
+                for (int k = 0; k < 2 * nh + 1 + 2 * nw; k++) {
+                    int ux, uy, bit;
+                    if (k < 2 * nh + 1) { ux = xu - 1; uy = yu - 1 + k; bit = yl + k; bit = bit < 64 ? (int)((c.avail_cols >> bit) & 1) : 0; }
+                    else { const int col = k - (2 * nh + 1); ux = xu + col; uy = yu - 1; bit = xl + col + 1; bit = bit < 64 ? (int)((c.avail_rows >> bit) & 1) : 0; }
+                    if (bit && ux >= 0 && uy >= 0 && ux < w_u && uy < h_u && pd[(size_t)uy * w_u + ux] == 7u) return -2000000 - q;
+                }
+            }
+            IntraK::Args ia = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
+                                (const IntraCmdDev *)cmds, &it.cmd, 1, p, p ? 2 : 1 };
+            ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
+            if (it.large) for (int k = 0; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
+            else for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS)
+                emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, it.nb_tb - k < TrK<32>::GROUPS ? it.nb_tb - k : TrK<32>::GROUPS, arena, &sl);
+            for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) {
+                if (pd[(size_t)y * w_u + x] != 7u) return -3000000 - q;
+                pd[(size_t)y * w_u + x] = 0;
+            }
+        }
+    }
     emu_tr_scales = NULL;
-    tu_groups_free(&g);
+    for (size_t i = 0; i < pend.size(); i++) if (pend[i]) return -4000000;
     return L.lv.nb[0] + L.lv.nb[1];
 }
 
