@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
-STAGES_IMPLEMENTED = ["recon[mc(uni/bi/bcw, bdof, dmvr, affine 4x4 + prof)+lmcs_fwd, then per plane: residual(dequant/lfnst/idct/jcbcr) of inter CUs, "
+STAGES_IMPLEMENTED = ["recon[mc(uni/bi/bcw, bdof, dmvr, gpm, affine 4x4 + prof)+lmcs_fwd, then per plane: residual(dequant/lfnst/idct/jcbcr) of inter CUs, "
                       "level-ordered intra(planar/dc/angular/mrl/mip/cclm/ciip)+residual, lmcs chroma scales from reconstructed luma]",
                       "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
@@ -86,7 +86,7 @@ def make_workload(w, h, n_pics, seed0=5000):
         tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
-        cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15)
+        cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15, p_gpm=0.1)
         cmds = cmds.astype(api.MC_CMD)
         # one CU partition for the residual and the intra side: 10 % intra CUs (MRL / MIP / CCLM among them), 4 % CIIP, every TU
         # takes its LMCS chroma scale from the anchor in force (derived on the GPU from reconstructed luma)
@@ -190,7 +190,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(ISP, GPM, IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(ISP, IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 

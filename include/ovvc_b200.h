@@ -177,6 +177,11 @@ int  ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmc
 #define OVGPU_MC_TOOL_DMVR  3  /* rcn_dmvr_mv_refine (rcn_inter.c:873): one <=16x16 sub-block of a DMVR CU, luma AND chroma, as
                                 * called from vcl_coding_unit.c:2621; aux bit 0 = apply_bdof.  The refined MVs come back
                                 * through ovgpu_mc_batch_read_dmvr (the caller stores them for TMVP, :2628-2645).        */
+#define OVGPU_MC_TOOL_GPM   4  /* rcn_gpm_b (rcn_inter.c:3118): geometric partitioning of a CU of 8..64 samples a side, luma AND chroma:
+                                * two uni-predictions blended sample by sample with the weights of split `aux & 63`
+                                * (rcn_gpm_weights_and_steps :3080, rcn_init_gpm_params rcn_gpm.c:150, put_weighted_gpm_bi_pixels
+                                * rcn_mc.c:1631).  mv0 / ref_idx0 address list (aux >> 8) & 1 (gpm_ctx.inter_dir0 - 1), mv1 / ref_idx1
+                                * list (aux >> 9) & 1; inter_dir = 3, default BCW                                           */
 typedef struct OVGPUDmvrMv { int32_t mv0_x, mv0_y, mv1_x, mv1_y; } OVGPUDmvrMv;
 /* struct PROFInfo (rcn_inter.c:1128-1134): the 16 per-sample delta-MV scales of an affine CU and list */
 typedef struct OVGPUProfInfo {

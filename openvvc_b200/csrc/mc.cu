@@ -164,9 +164,12 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
         const int w = 1 << c->log2_w, h = 1 << c->log2_h;
         if (c->x0 + w > max_x) max_x = c->x0 + w;
         if (c->y0 + h > max_y) max_y = c->y0 + h;
-        if (c->inter_dir & 1) used[0] |= 1u << c->ref_idx0;
-        if (c->inter_dir & 2) used[1] |= 1u << c->ref_idx1;
-        if (c->tool == OVGPU_MC_TOOL_PLAIN) {
+        if (c->tool == OVGPU_MC_TOOL_GPM) { used[(c->aux >> 8) & 1] |= 1u << c->ref_idx0; used[(c->aux >> 9) & 1] |= 1u << c->ref_idx1; }
+        else {
+            if (c->inter_dir & 1) used[0] |= 1u << c->ref_idx0;
+            if (c->inter_dir & 2) used[1] |= 1u << c->ref_idx1;
+        }
+        if (c->tool == OVGPU_MC_TOOL_PLAIN || c->tool == OVGPU_MC_TOOL_GPM) {
             if (np + ((w + 15) >> 4) * ((h + 15) >> 4) > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch: too many work items");
             for (int oy = 0; oy < h; oy += 16)
                 for (int ox = 0; ox < w; ox += 16) {

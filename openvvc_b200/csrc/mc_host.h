@@ -9,7 +9,7 @@ static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
 {
     int total = 0;
     for (int i = 0; i < n; i++) {
-        if (cmds[i].tool != 0) continue;
+        if (cmds[i].tool != OVGPU_MC_TOOL_PLAIN && cmds[i].tool != OVGPU_MC_TOOL_GPM) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         total += ((w + 15) >> 4) * ((h + 15) >> 4);
     }
@@ -43,6 +43,9 @@ static inline int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
         c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->x0 < 0 || c->y0 < 0)
         return -1;
     if (c->tool == OVGPU_MC_TOOL_PLAIN) return 0;
+    if (c->tool == OVGPU_MC_TOOL_GPM)       /* rcn_gpm_b: CU of 8..64 samples a side, two uni-predictions, luma and chroma, default BCW */
+        return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 6 && c->log2_h >= 3 && c->log2_h <= 6 && (c->flags & 3) == 3 &&
+                (c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3) && (c->aux & ~0x33fu) == 0) ? 0 : -1;
     if (c->tool == OVGPU_MC_TOOL_BDOF)      /* rcn_bdof_mcp_l: bi-predicted luma sub-block of 8 or 16 samples a side */
         return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 4 && c->log2_h >= 3 && c->log2_h <= 4 &&
                 (c->flags & 3) == OVGPU_MC_LUMA) ? 0 : -1;
@@ -59,7 +62,7 @@ static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (cmds[i].tool != 0) continue;
+        if (cmds[i].tool != OVGPU_MC_TOOL_PLAIN && cmds[i].tool != OVGPU_MC_TOOL_GPM) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         for (int oy = 0; oy < h; oy += 16)
             for (int ox = 0; ox < w; ox += 16) {

@@ -45,6 +45,41 @@ struct McRefsDev {
     int poc[2][16];
 };
 
+// GPM blend weights (rcn_init_gpm_params, libovvc/rcn_gpm.c:150-204; rcn_gpm_weights_and_steps, libovvc/rcn_inter.c:3080-3115):
+// the reference keeps six 112 x 112 masks and walks them mirrored for the other angles; the same value in closed form.
+OVD_CONST int8_t gpm_angle2mask[32] = { 0, -1, 1, 2, 3, 4, -1, -1, 5, -1, -1, 4, 3, 2, 1, -1, 0, -1, 1, 2, 3, 4, -1, -1, 5, -1, -1, 4, 3, 2, 1, -1 };
+OVD_CONST int8_t gpm_angle2mirror[32] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2 };
+OVD_CONST int8_t gpm_dis[32] = { 8, 8, 8, 8, 4, 4, 2, 1, 0, -1, -2, -4, -4, -8, -8, -8, -8, -8, -8, -8, -4, -4, -2, -1, 0, 1, 2, 4, 4, 8, 8, 8 };
+OVD_CONST uint8_t gpm_angle[64] = { 0, 0, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 8, 8, 11, 11, 11, 11, 12, 12, 12, 12, 13, 13, 13, 13,
+                                    14, 14, 14, 14, 16, 16, 18, 18, 18, 19, 19, 19, 20, 20, 20, 21, 21, 21, 24, 24, 27, 27, 27, 28, 28, 28, 29, 29, 29, 30, 30, 30 };
+OVD_CONST uint8_t gpm_dist[64] = { 1, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 1, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3,
+                                   0, 1, 2, 3, 1, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3 };
+OVD_CONST int8_t gpm_base_angle[6] = { 0, 2, 3, 4, 5, 8 };
+
+struct GpmGeom { int mirror, ox, oy, dx, dy, rho; };       // per CU: everything but the sample position
+OVD GpmGeom gpm_geom(int split_dir, int lw, int lh)
+{
+    GpmGeom g;
+    const int angle = gpm_angle[split_dir], distance = gpm_dist[split_dir], w = 1 << lw, h = 1 << lh;
+    g.ox = (112 - w) >> 1; g.oy = (112 - h) >> 1;
+    if (distance > 0) {
+        if ((angle & 15) == 8 || ((angle & 15) != 0 && h >= w)) g.oy += angle < 16 ? (distance * h) >> 3 : -((distance * h) >> 3);
+        else                                                    g.ox += angle < 16 ? (distance * w) >> 3 : -((distance * w) >> 3);
+    }
+    g.mirror = gpm_angle2mirror[angle];
+    const int a0 = gpm_base_angle[gpm_angle2mask[angle]];
+    g.dx = gpm_dis[a0]; g.dy = gpm_dis[(a0 + 8) & 31];
+    g.rho = (g.dx << 7) + (g.dy << 7);
+    return g;
+}
+// weight (0..8) of the FIRST prediction at luma position (x, y) of the CU
+OVD int gpm_weight(const GpmGeom &g, int x, int y)
+{
+    const int mx = g.mirror == 1 ? 111 - g.ox - x : g.ox + x, my = g.mirror == 2 ? 111 - g.oy - y : g.oy + y;
+    const int idx = (((mx + 8) << 1) + 1) * g.dx + (((my + 8) << 1) + 1) * g.dy - g.rho;
+    return ovd_clamp((32 + idx + 4) >> 3, 0, 8);
+}
+
 struct McK {
     static const int THREADS = 128, MIN_BLOCKS = 6, PHASES = 3;
     static const int WARPS = 4;
@@ -80,6 +115,7 @@ struct McK {
         int list[2], ridx[2];
         int mvx[2], mvy[2];              // clipped MVs
         int flags, bcw;
+        int gpm;                         // 0, or 1 + split | ox << 8 | oy << 16 | log2_w << 24 | log2_h << 28 (offset of the item inside the CU)
     };
 
     OVD Item load_item(const Args &a, int item_idx)
@@ -97,8 +133,14 @@ struct McK {
         const int identical = c.inter_dir == 3 &&
                               (uint16_t)a.refs.poc[0][c.ref_idx0] == (uint16_t)a.refs.poc[1][c.ref_idx1] &&
                               c.mv0_x == c.mv1_x && c.mv0_y == c.mv1_y;
-        const int bi = c.inter_dir == 3 && !identical;
-        if (bi) {
+        const int gpm = c.tool == 4;                                // OVGPU_MC_TOOL_GPM: both predictions always, lists from aux
+        const int bi = (c.inter_dir == 3 && !identical) || gpm;
+        it.gpm = gpm ? (int)(1 + (c.aux & 63)) | (im.ox << 8) | (im.oy << 16) | (c.log2_w << 24) | (c.log2_h << 28) : 0;
+        if (gpm) {
+            it.nref = 2;
+            it.list[0] = (c.aux >> 8) & 1; it.ridx[0] = c.ref_idx0; it.mvx[0] = c.mv0_x; it.mvy[0] = c.mv0_y;
+            it.list[1] = (c.aux >> 9) & 1; it.ridx[1] = c.ref_idx1; it.mvx[1] = c.mv1_x; it.mvy[1] = c.mv1_y;
+        } else if (bi) {
             it.nref = 2;
             it.list[0] = 0; it.ridx[0] = c.ref_idx0; it.mvx[0] = c.mv0_x; it.mvy[0] = c.mv0_y;
             it.list[1] = 1; it.ridx[1] = c.ref_idx1; it.mvx[1] = c.mv1_x; it.mvy[1] = c.mv1_y;
@@ -109,7 +151,7 @@ struct McK {
             it.mvx[0] = l1 ? c.mv1_x : c.mv0_x; it.mvy[0] = l1 ? c.mv1_y : c.mv0_y;
             it.list[1] = 0; it.ridx[1] = 0; it.mvx[1] = 0; it.mvy[1] = 0;
         }
-        it.bcw = (c.bcw_idx_plus1 == 0 || c.bcw_idx_plus1 == 3) ? 0 : c.bcw_idx_plus1;
+        it.bcw = (gpm || c.bcw_idx_plus1 == 0 || c.bcw_idx_plus1 == 3) ? 0 : c.bcw_idx_plus1;
         // clip_mv (rcn_inter.c:96-108) with the PU's position and size
         const int x_max = (a.pic_w + 2 - c.x0) << 4, y_max = (a.pic_h + 2 - c.y0) << 4;
         const int x_min = -((pu_w + 3 + c.x0) << 4), y_min = -((pu_h + 3 + c.y0) << 4);
@@ -180,9 +222,13 @@ struct McK {
         return ovd_clamp(v, 0, maxv);
     }
     // 8 horizontally adjacent final samples: two 16-byte reads of the exchange buffer, one 16-byte (or 8-byte) store
+    // gpm != 0: the two predictions are blended with the geometric weights; (gx, gy) = luma position of the first sample
+    // inside the CU, gstep = 1 (luma) or 2 (chroma samples the luma mask, rcn_inter.c:3090)
     OVD void store_row8(const Args &a, int plane, const int16_t *e0, const int16_t *e1, uint16_t *d, int n, int nref, int bcw, int w1,
-                        int maxv, bool lut)
+                        int maxv, bool lut, int gpm = 0, int gx = 0, int gy = 0, int gstep = 1)
     {
+        GpmGeom gg;
+        if (gpm) gg = gpm_geom((gpm & 0xff) - 1, (gpm >> 24) & 15, (gpm >> 28) & 15);
         const ovd_u4 q0 = *(const ovd_u4 *)e0;
         ovd_u4 q1; q1.x = q1.y = q1.z = q1.w = 0;
         if (nref == 2) q1 = *(const ovd_u4 *)e1;
@@ -191,8 +237,14 @@ struct McK {
         (void)plane;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            int va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), nref, bcw, w1, a.bitdepth, maxv);
-            int vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), nref, bcw, w1, a.bitdepth, maxv);
+            int va, vb;
+            if (gpm) {      // put_weighted_gpm_bi_pixels: the BCW formula with a per-sample weight, w1 = 8 - w0
+                va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), 2, 1, 8 - gpm_weight(gg, gx + (2 * k) * gstep, gy), a.bitdepth, maxv);
+                vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), 2, 1, 8 - gpm_weight(gg, gx + (2 * k + 1) * gstep, gy), a.bitdepth, maxv);
+            } else {
+                va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), nref, bcw, w1, a.bitdepth, maxv);
+                vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), nref, bcw, w1, a.bitdepth, maxv);
+            }
             if (lut) { va = a.lmcs_fwd[va]; vb = a.lmcs_fwd[vb]; }
             o[k] = (uint32_t)va | ((uint32_t)vb << 16);
         }
@@ -290,6 +342,7 @@ struct McK {
             }
             if (lane == 0) {
                 sit[1] = it.bx; sit[2] = it.by; sit[3] = it.w; sit[4] = it.h; sit[5] = it.nref; sit[6] = it.flags; sit[7] = it.bcw;
+                sit[11] = it.gpm;
             }
             return;
         }
@@ -350,19 +403,20 @@ struct McK {
         // ---- combination + store ----------------------------------------------------------------------------------
         const int maxv = (1 << a.bitdepth) - 1;
         const int w1 = bcw == 1 ? -2 : bcw == 2 ? 3 : bcw == 4 ? 5 : 10;           // rcn_inter.c:89
+        const int gpm = sit[11], gox = (gpm >> 8) & 0xff, goy = (gpm >> 16) & 0xff;
         if (do_y) {
             // lane -> (row, 8-sample half): 16 rows x 2 halves
             const int y = lane >> 1, x = (lane & 1) * 8;
             if (y < ih && x < iw)
                 store_row8(a, 0, ex_y + y * 16 + x, ex_y + (16 + y) * 16 + x, a.dst[0] + (size_t)(iby + y) * a.dst_pitch[0] + ibx + x,
-                           iw - x, nref, bcw, w1, maxv, a.lmcs_fwd != 0);
+                           iw - x, nref, bcw, w1, maxv, a.lmcs_fwd != 0, gpm, gox + x, goy + y, 1);
         }
         if (do_c) {
             // lanes 0-15 -> (component, row): 2 x 8 rows of <= 8 samples
             const int comp = (lane >> 3) & 1, y = lane & 7;
             if (lane < 16 && y < (ih >> 1)) {
                 uint16_t *d = (comp ? a.dst[2] : a.dst[1]) + (size_t)((iby >> 1) + y) * (comp ? a.dst_pitch[2] : a.dst_pitch[1]) + (ibx >> 1);
-                store_row8(a, 1, ex_c + (comp * 8 + y) * 8, ex_c + ((2 + comp) * 8 + y) * 8, d, iw >> 1, nref, bcw, w1, maxv, false);
+                store_row8(a, 1, ex_c + (comp * 8 + y) * 8, ex_c + ((2 + comp) * 8 + y) * 8, d, iw >> 1, nref, bcw, w1, maxv, false, gpm, gox, goy + 2 * y, 2);
             }
         }
     }

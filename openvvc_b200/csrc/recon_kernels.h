@@ -101,21 +101,33 @@ __device__ __forceinline__ void recon_st_release(uint32_t *p, uint32_t v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// One CTA = one worker.  Phases of IntraK / TrK are separated by CTA barriers exactly as ovd_kernel does.
+// One CTA = one worker.  Phases of IntraK / TrK are separated by CTA barriers exactly as ovd_kernel does.  The command, its
+// transform-block items and their TU commands are staged in shared memory once per item, so the phase functions (which
+// re-read their command in every phase) do not go back to global memory.
+struct ReconStage {
+    IntraCmdDev cmd;
+    uint32_t zero;
+    TbItemDev tb[4];
+    TuCmdDev tu[4];
+};
+
 __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
 {
     extern __shared__ __align__(16) unsigned char ovd_smem[];
     __shared__ int s_item;
+    __shared__ __align__(16) ReconStage sg;
     const int tid = threadIdx.x;
     IntraK::State ist; TrK<32>::State ts; TrK<128>::State tl;
     for (;;) {
         if (tid == 0) s_item = atomicAdd(a.counter, 1);
         __syncthreads();
         const int i = s_item;
-        __syncthreads();
         if (i >= a.nb_items) return;
         const ReconItemDev it = a.ritems[i];
-        const IntraCmdDev c = a.cmds[it.cmd];
+        if (tid < (int)(sizeof(IntraCmdDev) / 4)) ((uint32_t *)&sg.cmd)[tid] = ((const uint32_t *)&a.cmds[it.cmd])[tid];
+        if (tid == 32) sg.zero = 0;
+        __syncthreads();
+        const IntraCmdDev c = sg.cmd;
         const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
         {   // wait for the available neighbour units this block's reference samples come from: the left column from the
             // corner down to 2h below the top (avail_cols: bit 1 + row inside the CTU), the above row over 2w (avail_rows)
@@ -133,23 +145,35 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
             __threadfence();
         }
         // ---- prediction
-        const IntraK::Args ia = recon_intra_args(a, &a.ritems[i].cmd);
+        IntraK::Args ia = recon_intra_args(a, &sg.zero);
+        ia.cmds = &sg.cmd;
         IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
         IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
         IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
         IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-        // ---- residual of the blocks this command covers
-        if (it.large) {
-            for (int k = 0; k < it.nb_tb; k++) {
-                const TrK<128>::Args ta = recon_tr_args<128>(a, a.tb + it.tb_start + k, 1);
-                TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+        // ---- residual of the blocks this command covers, up to four at a time
+        for (int k0 = 0; k0 < it.nb_tb; k0 += 4) {
+            const int nk = ovd_min(4, it.nb_tb - k0);
+            if (tid < nk) { TbItemDev t = a.tb[it.tb_start + k0 + tid]; sg.tb[tid].cmd = tid; sg.tb[tid].kind = t.kind; sg.zero = 0;
+                            /* the TU command index travels through a register to the copy below */ ((uint32_t *)ovd_smem)[tid] = t.cmd; }
+            __syncthreads();
+            for (int o = tid; o < nk * (int)(sizeof(TuCmdDev) / 4); o += 128) {
+                const int k = o / (int)(sizeof(TuCmdDev) / 4), wd = o - k * (int)(sizeof(TuCmdDev) / 4);
+                ((uint32_t *)&sg.tu[k])[wd] = ((const uint32_t *)&a.tu_cmds[((const uint32_t *)ovd_smem)[k]])[wd];
             }
-        } else {
-            for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS) {
-                const TrK<32>::Args ta = recon_tr_args<32>(a, a.tb + it.tb_start + k, ovd_min(TrK<32>::GROUPS, it.nb_tb - k));
+            __syncthreads();
+            if (it.large) {
+                for (int k = 0; k < nk; k++) {
+                    TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + k, 1);
+                    ta.cmds = sg.tu;
+                    TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                    TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                    TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                    TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                }
+            } else {
+                TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb, nk);
+                ta.cmds = sg.tu;
                 TrK<32>::phase<0>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
                 TrK<32>::phase<1>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
                 TrK<32>::phase<2>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();

@@ -200,10 +200,10 @@ def mc_commands(w, h, seed=1004, log2_ctu=7, n_refs=2, p_bi=0.7, mv_range=64, mi
     return cmds
 
 
-MC_TOOL_PLAIN, MC_TOOL_BDOF, MC_TOOL_PROF, MC_TOOL_DMVR = 0, 1, 2, 3
+MC_TOOL_PLAIN, MC_TOOL_BDOF, MC_TOOL_PROF, MC_TOOL_DMVR, MC_TOOL_GPM = 0, 1, 2, 3, 4
 
 
-def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_log2=3, p_bdof=0.3, p_affine=0.2, p_dmvr=0.0):
+def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_log2=3, p_bdof=0.3, p_affine=0.2, p_dmvr=0.0, p_gpm=0.0):
     """PU list with BDOF and affine/PROF coding units mixed in (25 % of eligible bi blocks BDOF, 15 %
     affine 4x4).  Returns (cmds, prof_table): BDOF CUs become <=16x16 luma sub-block commands (tool 1) + one chroma
     command; affine CUs become 4x4 luma commands (tool 2 with PROF, or plain 6-tap) + 8x8-luma chroma commands with the
@@ -279,6 +279,10 @@ def mc_commands_tools(w, h, seed=1004, log2_ctu=7, n_refs=2, mv_range=32, min_lo
                         ax += ax < 0; ay += ay < 0
                         avg.append((ax >> 1, ay >> 1))
                     new(x + 4 * i, y + 4 * j, 3, 3, inter_dir, 2, r0, r1, avg[0], avg[1], bcw=bcw)
+        elif p_gpm and 3 <= lw <= 6 and 3 <= lh <= 6 and abs(lw - lh) < 3 and rng.random() < p_gpm:
+            # GPM CU (rcn_gpm_b): two uni-predictions from any list, one of the 64 splits; MVs are merge candidates, no half-pel AMVR
+            new(x, y, lw, lh, 3, 3, r0, r1, mv0, mv1, tool=MC_TOOL_GPM,
+                aux=int(rng.integers(0, 64)) | (int(rng.integers(0, 2)) << 8) | (int(rng.integers(0, 2)) << 9))
         else:
             bi = rng.random() < 0.7 and lw + lh >= 6
             new(x, y, lw, lh, 3 if bi else int(rng.integers(1, 3)), 3 | hpel, r0, r1, mv0, mv1,

@@ -102,6 +102,7 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                                  * aux = prof_dir (bits 0-1) | index into the PROF table << 8                          */
 #define OVO_MC_TOOL_DMVR  3     /* rcn_dmvr_mv_refine (rcn_inter.c:873): one <= 16x16 sub-block, luma AND chroma;          *
                                  * aux bit 0 = apply_bdof.  The refined MVs are an OUTPUT (fed back to TMVP on the CPU).   */
+#define OVO_MC_TOOL_GPM   4     /* rcn_gpm_b (rcn_inter.c:3118): aux = split_dir | list of mv0 << 8 | list of mv1 << 9      */
 typedef struct OVODmvrMv { int32_t mv0_x, mv0_y, mv1_x, mv1_y; } OVODmvrMv;
 typedef struct OVOProfInfo {    /* struct PROFInfo, rcn_inter.c:1128-1134 */
     int16_t dmv_scale_h_0[16], dmv_scale_v_0[16], dmv_scale_h_1[16], dmv_scale_v_1[16];

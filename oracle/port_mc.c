@@ -429,6 +429,57 @@ static void prof_block(uint16_t *d, int stride, const OVOMcRefs *refs, const OVO
         }
 }
 
+/* ---------------------------------------------------------------------------------------------------
+ * GPM (rcn_gpm_b, rcn_inter.c:3118-3146 -> rcn_mc_rpr_b_l / _c with a gpm_ctx, :2525-2592, 2653-2731): two 14-bit
+ * uni-predictions (rcn_mcp_bidir0_l / _c) blended with per-sample weights 0..8 taken from the pre-computed masks of
+ * rcn_init_gpm_params (libovvc/rcn_gpm.c:150-204): six base masks of 112 x 112, a start offset per (split, size) and a
+ * traversal that mirrors the mask for the other angles (rcn_gpm_weights_and_steps, rcn_inter.c:3080-3115); chroma samples
+ * the luma mask with step 2 (put_weighted_gpm_bi_pixels, rcn_mc.c:1631-1655).
+ * ------------------------------------------------------------------------------------------------- */
+static const int8_t gpm_angle2mask[32] = { 0, -1, 1, 2, 3, 4, -1, -1, 5, -1, -1, 4, 3, 2, 1, -1, 0, -1, 1, 2, 3, 4, -1, -1, 5, -1, -1, 4, 3, 2, 1, -1 };
+static const int8_t gpm_angle2mirror[32] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2 };
+static const int8_t gpm_dis[32] = { 8, 8, 8, 8, 4, 4, 2, 1, 0, -1, -2, -4, -4, -8, -8, -8, -8, -8, -8, -8, -4, -4, -2, -1, 0, 1, 2, 4, 4, 8, 8, 8 };
+static const uint8_t gpm_angle[64] = { 0, 0, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 8, 8, 11, 11, 11, 11, 12, 12, 12, 12, 13, 13, 13, 13,
+                                       14, 14, 14, 14, 16, 16, 18, 18, 18, 19, 19, 19, 20, 20, 20, 21, 21, 21, 24, 24, 27, 27, 27, 28, 28, 28, 29, 29, 29, 30, 30, 30 };
+static const uint8_t gpm_dist[64] = { 1, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3, 1, 3, 0, 1, 2, 3, 0, 1, 2, 3, 0, 1, 2, 3,
+                                      0, 1, 2, 3, 1, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3, 1, 2, 3 };
+
+/* weight of the FIRST prediction at luma position (x, y) of a (1 << lw) x (1 << lh) CU */
+static int gpm_weight(int split_dir, int lw, int lh, int x, int y)
+{
+    int angle = gpm_angle[split_dir], distance = gpm_dist[split_dir], w = 1 << lw, h = 1 << lh;
+    int ox = (112 - w) >> 1, oy = (112 - h) >> 1;                              /* g_weightOffset, rcn_gpm.c:182-201 */
+    if (distance > 0) {
+        if (angle % 16 == 8 || (angle % 16 != 0 && h >= w)) oy += angle < 16 ? (distance * h) >> 3 : -((distance * h) >> 3);
+        else                                                ox += angle < 16 ? (distance * w) >> 3 : -((distance * w) >> 3);
+    }
+    int mirror = gpm_angle2mirror[angle];
+    int mx = mirror == 1 ? 111 - ox - x : ox + x, my = mirror == 2 ? 111 - oy - y : oy + y;   /* rcn_inter.c:3100-3114 */
+    static const int8_t base_angle[6] = { 0, 2, 3, 4, 5, 8 };                  /* the angle each stored mask was built for */
+    int a0 = base_angle[gpm_angle2mask[angle]], dx = a0, dy = (a0 + 8) % 32;
+    int rho = (int16_t)((gpm_dis[dx] << 7) + (gpm_dis[dy] << 7));             /* rcn_gpm.c:160-161 */
+    int idx = (int16_t)((((mx + 8) << 1) + 1) * gpm_dis[dx] + (int16_t)((((my + 8) << 1) + 1) * gpm_dis[dy]) - rho);
+    return clipi((32 + idx + 4) >> 3, 0, 8);
+}
+
+static void gpm_block(uint16_t *const dst[3], const int dst_stride[3], const OVOMcRefs *refs, const OVOMcCmd *c,
+                      int pic_w, int pic_h, int bitdepth, int16_t *p0, int16_t *p1)
+{
+    int split = c->aux & 63, l0 = (c->aux >> 8) & 1, l1 = (c->aux >> 9) & 1, maxv = (1 << bitdepth) - 1;
+    MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
+    for (int comp = 0; comp < 3; comp++) {
+        int sh = comp ? 1 : 0, w = (1 << c->log2_w) >> sh, h = (1 << c->log2_h) >> sh;
+        uint16_t *d = dst[comp] + (size_t)(c->y0 >> sh) * dst_stride[comp] + (c->x0 >> sh);
+        pu_pred14(p0, refs, l0, c->ref_idx0, comp, pic_w, pic_h, c, mv0, bitdepth);
+        pu_pred14(p1, refs, l1, c->ref_idx1, comp, pic_w, pic_h, c, mv1, bitdepth);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int w0 = gpm_weight(split, c->log2_w, c->log2_h, x << sh, y << sh);
+                d[(size_t)y * dst_stride[comp] + x] = (uint16_t)clipi((p1[y * 128 + x] * (8 - w0) + p0[y * 128 + x] * w0 + (1 << (16 - bitdepth))) >> (17 - bitdepth), 0, maxv);
+            }
+    }
+}
+
 void ovo_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
                     const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut)
 {
@@ -460,6 +511,16 @@ void ovo_mc_picture3(uint16_t *const dst[3], const int dst_stride[3], int pic_w,
                 for (int y = 0; y < (1 << c->log2_h); y++)
                     for (int x = 0; x < (1 << c->log2_w); x++) {
                         uint16_t *q = &d[(size_t)y * dst_stride[0] + x];
+                        *q = lmcs_fwd_lut[*q & maxv];
+                    }
+            continue;
+        }
+        if (c->tool == OVO_MC_TOOL_GPM) {
+            gpm_block(dst, dst_stride, refs, c, pic_w, pic_h, bitdepth, p0, p1);
+            if (lmcs_fwd_lut)                                             /* rcn_inter.c:2591 */
+                for (int y = 0; y < (1 << c->log2_h); y++)
+                    for (int x = 0; x < (1 << c->log2_w); x++) {
+                        uint16_t *q = dst[0] + (size_t)(c->y0 + y) * dst_stride[0] + c->x0 + x;
                         *q = lmcs_fwd_lut[*q & maxv];
                     }
             continue;

@@ -370,7 +370,16 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
             if (dmvr_out) { dmvr_out->mv0_x = mv0.x; dmvr_out->mv0_y = mv0.y; dmvr_out->mv1_x = mv1.x; dmvr_out->mv1_y = mv1.y; dmvr_out++; }
         } else if (m->tool == OVO_MC_TOOL_BDOF)
             c->rcn_funcs.rcn_bdof_mcp_l(c, b, x0, y0, m->log2_w, m->log2_h, mv0, mv1, m->ref_idx0, m->ref_idx1);
-        else if (m->tool == OVO_MC_TOOL_PROF)      /* struct PROFInfo (rcn_inter.c:1128) has OVOProfInfo's layout */
+        else if (m->tool == OVO_MC_TOOL_GPM) {
+            static int gpm_init = 0;
+            if (!gpm_init) { rcn_init_gpm_params(); gpm_init = 1; }          /* process-global tables, ovdec.c */
+            struct VVCGPM g;
+            memset(&g, 0, sizeof(g));
+            g.split_dir = m->aux & 63; g.inter_dir0 = 1 + ((m->aux >> 8) & 1); g.inter_dir1 = 1 + ((m->aux >> 9) & 1);
+            g.mv0 = mv0; g.mv1 = mv1;
+            c->rcn_ctx.ctu_buff = b;                                           /* rcn_gpm_b writes to the CTU buffer */
+            c->rcn_funcs.rcn_gpm_b(c, &g, x0, y0, m->log2_w, m->log2_h);
+        } else if (m->tool == OVO_MC_TOOL_PROF)      /* struct PROFInfo (rcn_inter.c:1128) has OVOProfInfo's layout */
             c->rcn_funcs.rcn_prof_mcp_b_l(c, b, ic, &part, mv0, mv1, x0, y0, 2, 2, m->inter_dir, m->ref_idx0, m->ref_idx1,
                                           m->aux & 3, (const void *)&prof_tab[m->aux >> 8]);
         else if ((m->flags & 3) == 3)

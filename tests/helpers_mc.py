@@ -19,12 +19,12 @@ def blank(w, h):
     return [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
 
 
-def mc_tools_case(po, w, h, seed, log2_ctu=7, lmcs=False, min_log2=3, n_refs=2):
+def mc_tools_case(po, w, h, seed, log2_ctu=7, lmcs=False, min_log2=3, n_refs=2, p_gpm=0.0):
     """like mc_case, with BDOF and affine/PROF coding units mixed in; returns the PROF table as well"""
     refs0 = [synth.planes(w, h, seed + 10 + i) for i in range(n_refs)]
     refs1 = [synth.planes(w, h, seed + 20 + i) for i in range(n_refs)]
     pocs = [[8 * (i + 1) for i in range(n_refs)], [8 * (i + 2) for i in range(n_refs)]]
-    cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, n_refs=n_refs, min_log2=min_log2)
+    cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, n_refs=n_refs, min_log2=min_log2, p_gpm=p_gpm)
     luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
     return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof
 

@@ -194,6 +194,62 @@ def test_tools_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
     helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=prof), a, "CUDA MC tools vs reference at 4K")
 
 
+# ================================================================================================ GPM
+GPM_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_gpm_golden.json")))
+
+
+def _gpm_case(po, c):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(po, c["w"], c["h"], c["seed"], c["log2_ctu"], c["lmcs"], c["min_log2"], p_gpm=0.6)
+    assert helpers.md5(cmds, prof, *refs0[0], *refs1[-1]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return refs0, refs1, pocs, cmds, luts, prof
+
+
+@pytest.mark.parametrize("c", GPM_GOLDEN, ids=IDS)
+def test_gpm_port_and_emulated_kernel_match_golden(oracle, emu, c):
+    """rcn_gpm_b (a15): two uni-predictions from any list blended with the 64 geometric splits, luma and chroma, LMCS"""
+    refs0, refs1, pocs, cmds, luts, prof = _gpm_case(oracle, c)
+    g = cmds[cmds["tool"] == 4]
+    assert len(g) > 10 and len(set((g["aux"] & 63).tolist())) > 10 and set(((g["aux"] >> 8) & 3).tolist()) == {0, 1, 2, 3}
+    dst = helpers_mc.blank(c["w"], c["h"])
+    oracle.mc_picture(dst, [refs0, refs1], pocs, cmds, c["log2_ctu"], impl="port", lmcs=luts, prof=prof)
+    assert [helpers.md5(p) for p in dst] == c["md5"]
+    if c["w"] <= 832:
+        helpers.assert_planes_equal(helpers_mc.emu_mc(emu, oracle, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, prof=prof), dst,
+                                    "emulated GPM kernel vs oracle")
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs", [(416, 240, 7, False), (832, 480, 7, True), (264, 136, 6, False), (200, 120, 5, True)])
+def test_gpm_port_vs_compiled_reference(oracle, w, h, log2, lmcs):
+    po = oracle
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(po, w, h, 3 * w + h + 2, log2, lmcs, p_gpm=0.6)
+    a = helpers_mc.blank(w, h)
+    po.mc_picture(a, [refs0, refs1], pocs, cmds, log2, impl="port", lmcs=luts, prof=prof)
+    for simd in (0, 1):
+        b = helpers_mc.blank(w, h)
+        po.mc_picture(b, [refs0, refs1], pocs, cmds, log2, impl="ref", lmcs=luts, prof=prof, simd=simd)
+        helpers.assert_planes_equal(a, b, "GPM port vs reference (simd=%d)" % simd)
+
+
+def test_gpm_malformed_commands_rejected(oracle, emu):
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, 256, 128, 3, 7, False, p_gpm=0.8)
+    i = int(np.nonzero(cmds["tool"] == 4)[0][0])
+    for field, val in (("inter_dir", 1), ("flags", 1), ("aux", 1 << 12), ("bcw_idx_plus1", 1), ("log2_w", 7)):
+        bad = cmds.copy()
+        bad[field][i] = val
+        with pytest.raises(AssertionError):
+            helpers_mc.emu_mc(emu, oracle, 256, 128, refs0, refs1, pocs, bad, luts, prof=prof)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", GPM_GOLDEN, ids=IDS)
+def test_gpm_gpu_matches_golden(oracle, gpu_ctx, c):
+    refs0, refs1, pocs, cmds, luts, prof = _gpm_case(oracle, c)
+    out = helpers_mc.gpu_mc(gpu_ctx, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, prof=prof)
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
 # ================================================================================================ DMVR
 DMVR_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_dmvr_golden.json")))
 DIDS = lambda c: "%dx%d_ctu%d_%s%s" % (c["w"], c["h"], 1 << c["log2_ctu"], c["kind"], "_lmcs" if c["lmcs"] else "")
