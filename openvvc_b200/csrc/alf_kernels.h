@@ -62,10 +62,12 @@ struct AlfLumaK {
     {
         Tile t;
         const int ctu_s = 1 << a.log2_ctu;
-        int cx = bx / a.tiles_x_per_ctu, cy = by / a.tiles_y_per_ctu;
-        t.x0 = cx * ctu_s + (bx % a.tiles_x_per_ctu) * a.tw;
+        // tiles per CTU are 1, 2 or 4 each way (CTU 32..128, tile 128 x 32): n >> 1 is log2(n); no integer division
+        const int sx = a.tiles_x_per_ctu >> 1, sy = a.tiles_y_per_ctu >> 1;
+        int cx = bx >> sx, cy = by >> sy;
+        t.x0 = cx * ctu_s + (bx & (a.tiles_x_per_ctu - 1)) * a.tw;
         t.ctu_y0 = cy * ctu_s;
-        t.y0 = t.ctu_y0 + (by % a.tiles_y_per_ctu) * a.th;
+        t.y0 = t.ctu_y0 + (by & (a.tiles_y_per_ctu - 1)) * a.th;
         t.ctu_h = ovd_min(ctu_s, a.pic_h - t.ctu_y0);
         t.tw = ovd_min(a.tw, a.pic_w - t.x0);
         t.th = ovd_min(a.th, t.ctu_y0 + t.ctu_h - t.y0);
@@ -342,9 +344,10 @@ struct AlfChromaK {
         Tile t;
         const int ctu_c = (1 << a.log2_ctu) >> 1;
         const int w = a.pic_w >> 1, h = a.pic_h >> 1;
-        int cx = bx / a.tiles_x_per_ctu, cy = by / a.tiles_y_per_ctu;
-        t.x0 = cx * ctu_c + (bx % a.tiles_x_per_ctu) * a.tw;
-        t.y0 = cy * ctu_c + (by % a.tiles_y_per_ctu) * a.th;
+        const int sx = a.tiles_x_per_ctu >> 1, sy = a.tiles_y_per_ctu >> 1;       // 1, 2 or 4 tiles per CTU each way
+        int cx = bx >> sx, cy = by >> sy;
+        t.x0 = cx * ctu_c + (bx & (a.tiles_x_per_ctu - 1)) * a.tw;
+        t.y0 = cy * ctu_c + (by & (a.tiles_y_per_ctu - 1)) * a.th;
         int ctu_h = ovd_min(ctu_c, h - cy * ctu_c);
         t.tw = ovd_min(a.tw, w - t.x0);
         t.th = ovd_min(a.th, cy * ctu_c + ctu_h - t.y0);

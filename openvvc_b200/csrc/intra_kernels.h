@@ -61,7 +61,8 @@ struct IntraK {
         const uint32_t *order;      // command indices of this level
         int nb;
         int comp0;                  // component of grid row 0 (luma levels: 0; chroma levels: 1, grid rows = Cb, Cr)
-        int warp_comps;             // 0, or (dataflow kernel, recon_kernels.h) the CTA owns ONE block: warp k predicts component comp0 + k, k < warp_comps
+        int warp_comps;             // 0, or (dataflow kernel, recon_kernels.h) the CTA owns ONE command: its threads split into warp_comps groups,
+                                    // group k predicts component comp0 + k (1: luma, 2: Cb and Cr)
     };
     struct State { int dummy; };
 
@@ -140,7 +141,7 @@ struct IntraK {
 
     // fill_ref_left_0 / fill_ref_above_0 (offset 0): one lane per sample
     OVD void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
-                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int us, int left_chroma)
+                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int nl, int us, int left_chroma)
     {
         // us = log2 of the availability unit in samples of this plane (2 luma, 1 chroma)
         const int nb_units = ((1 << (log2_len + 1)) >> us) + 1, ref_len = (1 << (log2_len + 1)) + 1;
@@ -155,7 +156,7 @@ struct IntraK {
         } else if (nb_avl > 1) pad = p[(size_t)((nb_avl - 1) << us) * step];
         else if (!left_chroma) pad = p[0];                                                     // only the corner unit: its sample
         // (fill_ref_left_0_chroma keeps the mid value there, rcn_fill_ref.c:193-200)
-        for (int i = lane; i < ref_len + 4; i += 32) {
+        for (int i = lane; i < ref_len + 4; i += nl) {
             int v = pad;
             const int k = ovd_min(i, ref_len - 1);                                             // wide-angle padding repeats the last sample
             if (avl) {
@@ -169,7 +170,7 @@ struct IntraK {
     // fill_ref_left_0_mref / fill_ref_above_0_mref (rcn_fill_ref.c:228-318, 493-590): raw[0] = the sample m + 1 away both ways,
     // corner group of m + 1 samples, then 4-sample units; left and above differ in two places (rcn_fill_ref.c mref variants)
     OVD void fill_ref_mref(uint16_t *raw, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
-                           uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int m, int is_left)
+                           uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int nl, int m, int is_left)
     {
         const int nb_units = ((1 << (log2_len + 1)) >> 2) + 1, ref_len = (1 << (log2_len + 1)) + 1 + (m + 1);
         const int ratio = ovd_max(1, (1 << log2_len) >> log2_other);
@@ -185,7 +186,7 @@ struct IntraK {
             if (avl_o) pad = is_left ? p[(size_t)(1 + m) * other_step] : p[(ptrdiff_t)m * step + (ptrdiff_t)(m + 1) * other_step];
         } else if (nb_avl > 1) pad = p[(ptrdiff_t)(grp_off + 4 * (nb_avl - 1) - 1) * step];
         else if (!is_left) pad = p[(ptrdiff_t)m * step];
-        for (int i = lane; i < ref_len - 1 + ratio * (m + 1); i += 32) {
+        for (int i = lane; i < ref_len - 1 + ratio * (m + 1); i += nl) {
             int v = pad;
             const int k = ovd_min(i, ref_len - 2);         // the reference's wide-angle padding starts on the last sample (:312-316)
             if (avl) {
@@ -317,9 +318,12 @@ struct IntraK {
     OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
     {
         (void)st; (void)bz;
-        const int warp = tid >> 5, lane = tid & 31;
+        // a worker = the group of `nl` threads that owns one block: a warp (one launch per level), or -- in the dataflow kernel,
+        // where the CTA owns ONE command and latency is what counts -- the whole CTA (luma) / one half each for Cb and Cr
+        const int nl = a.warp_comps ? THREADS / a.warp_comps : 32;
+        const int warp = tid / nl, lane = tid - warp * nl;
         const int comp = a.warp_comps ? a.comp0 + warp : a.comp0 + by;
-        const Blk b = load(a, a.warp_comps ? (warp < a.warp_comps ? bx : a.nb) : bx * WARPS + warp, comp);
+        const Blk b = load(a, a.warp_comps ? bx : bx * WARPS + warp, comp);
         if (!b.valid) return;
         uint16_t *plane = comp == 0 ? a.plane[0] : (comp == 1 ? a.plane[1] : a.plane[2]);
         const int pitch = comp == 0 ? a.pitch[0] : (comp == 1 ? a.pitch[1] : a.pitch[2]);
@@ -335,7 +339,7 @@ struct IntraK {
             if (P == 3) {
                 const int abv = cclm_abv(b, cm), lft = cclm_lft(b, cm);
                 const int ac = prm[0], bc = prm[1], shift = prm[2];
-                for (int o = lane; o < w * h; o += 32) {
+                for (int o = lane; o < w * h; o += nl) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int lm = lm_luma(Y + (ptrdiff_t)(2 * y) * a.pitch[0] + 2 * x, a.pitch[0], b.coll, x == 0 && !lft, y == 0 && !abv);
                     dst[(size_t)y * pitch + x] = (uint16_t)ovd_clamp(((lm * ac) >> shift) + bc, 0, maxv);
@@ -373,7 +377,7 @@ struct IntraK {
                 }
                 const int rnd = 32 - 32 * sum;                              // MIP_OFFSET - MIP_OFFSET * sum
                 const uint8_t *mt = (b.lw == 2 && b.lh == 2) ? &mip_w_4x4[b.mip_idx * 64] : (red_size ? &mip_w_8x8[b.mip_idx * 128] : &mip_w_16x16[b.mip_idx * 512]);
-                for (int pos = lane; pos < red * red; pos += 32) {
+                for (int pos = lane; pos < red * red; pos += nl) {
                     const uint8_t *m = mt + pos * 2 * nb;
                     int v = 0;
 #pragma unroll
@@ -386,7 +390,7 @@ struct IntraK {
             }
             // up_sample (:93-131) horizontally on the rows holding the reduced lines, then vertically, per output sample
             const int lsx = b.lw - log2_red, lsy = b.lh - log2_red, sx = 1 << lsx, sy = 1 << lsy;
-            for (int o = lane; o < w * h; o += 32) {
+            for (int o = lane; o < w * h; o += nl) {
                 const int x = o & (w - 1), y = o >> b.lw;
                 const int jx = x >> lsx, px = (x & (sx - 1)) + 1, jy = y >> lsy, py = (y & (sy - 1)) + 1;
                 // H(i): value of reduced row i at column x
@@ -407,19 +411,19 @@ struct IntraK {
         if (P == 0) {
             const uint16_t *corner = dst - (ptrdiff_t)(b.mrl + 1) * pitch - (b.mrl + 1);
             if (b.mrl) {                                                    // abv / lft = raw + m: [1 + i] is the i-th sample of line m
-                fill_ref_mref(lft - b.mrl, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, b.mrl, 1);
-                fill_ref_mref(abv - b.mrl, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, b.mrl, 0);
+                fill_ref_mref(lft - b.mrl, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, nl, b.mrl, 1);
+                fill_ref_mref(abv - b.mrl, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, nl, b.mrl, 0);
                 return;
             }
-            fill_ref(lft, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, us, b.chroma);
-            fill_ref(abv, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, us, 0);
+            fill_ref(lft, corner, pitch, 1, b.lh, b.lw, b.cols, b.rows, b.y0 & cm, b.x0 & cm, a.bitdepth, lane, nl, us, b.chroma);
+            fill_ref(abv, corner, 1, pitch, b.lw, b.lh, b.rows, b.cols, b.x0 & cm, b.y0 & cm, a.bitdepth, lane, nl, us, 0);
             return;
         }
         if (P == 1) {
             // filter_ref_samples over 2 * len samples of both arrays (the consumers read inside that range)
-            for (int i = lane; i <= 2 * w; i += 32)
+            for (int i = lane; i <= 2 * w; i += nl)
                 fabv[i] = (uint16_t)(i == 0 ? (lft[1] + (abv[0] << 1) + abv[1] + 2) >> 2 : (i == 2 * w ? abv[i] : (abv[i + 1] + (abv[i] << 1) + abv[i - 1] + 2) >> 2));
-            for (int i = lane; i <= 2 * h; i += 32)
+            for (int i = lane; i <= 2 * h; i += nl)
                 flft[i] = (uint16_t)(i == 0 ? (abv[1] + (lft[0] << 1) + lft[1] + 2) >> 2 : (i == 2 * h ? lft[i] : (lft[i + 1] + (lft[i] << 1) + lft[i - 1] + 2) >> 2));
             return;
         }
@@ -429,7 +433,7 @@ struct IntraK {
         if (P == 2) {
             if (b.ext) {                                                    // rcn_intra.c:118-121
                 const int H = 1 << b.mlh;
-                for (int k = 1 + lane; k <= H; k += 32) M[-b.mrl - k] = S[-b.mrl + ovd_min((256 + k * b.inv) >> 9, H)];
+                for (int k = 1 + lane; k <= H; k += nl) M[-b.mrl - k] = S[-b.mrl + ovd_min((256 + k * b.inv) >> 9, H)];
             }
             return;
         }
@@ -438,7 +442,7 @@ struct IntraK {
             if (b.mode == 0) {                                              // intra_planar_pdpc
                 const uint16_t *A = b.filt_m ? fabv : abv, *L = b.filt_m ? flft : lft;
                 const int ws = ovd_max(b.lw, 1), hs = ovd_max(b.lh, 1), scale = (b.lw + b.lh - 2) >> 2;
-                for (int o = lane; o < w * h; o += 32) {
+                for (int o = lane; o < w * h; o += nl) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);
                     const int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
@@ -454,13 +458,13 @@ struct IntraK {
                 if (b.lw >= b.lh) for (int i = 0; i < w; i++) dc += abv[1 + i];
                 if (b.lw <= b.lh) for (int i = 0; i < h; i++) dc += lft[1 + i];
                 dc = (dc + ((1 << shift) >> 1)) >> shift;
-                for (int o = lane; o < w * h; o += 32) {
+                for (int o = lane; o < w * h; o += nl) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
                     dst[(size_t)y * pitch + x] = (uint16_t)(b.pd ? ovd_clamp((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv) : dc);
                 }
             } else {
-                for (int o = lane; o < w * h; o += 32) {
+                for (int o = lane; o < w * h; o += nl) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int v = b.vert ? class_pixel(b, M, S, tl, x, y, maxv) : class_pixel(b, M, S, tl, y, x, maxv);
                     dst[(size_t)y * pitch + x] = (uint16_t)v;

@@ -90,10 +90,11 @@ struct ReconPrepK {
 };
 
 #if !defined(OVGPU_HOST_EMU) && defined(OVGPU_RECON_KERNEL_IMPL)      // the one translation unit that launches it (intra.cu)
-__device__ __forceinline__ uint32_t recon_ld_acquire(const uint32_t *p)
+// polling load: relaxed (no cache maintenance per iteration); the acquire fence follows once the flag has flipped
+__device__ __forceinline__ uint32_t recon_ld_relaxed(const uint32_t *p)
 {
     uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void recon_st_release(uint32_t *p, uint32_t v)
@@ -118,11 +119,14 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
     __shared__ __align__(16) ReconStage sg;
     const int tid = threadIdx.x;
     IntraK::State ist; TrK<32>::State ts; TrK<128>::State tl;
+    int next = 0;
+    if (tid == 0) next = atomicAdd(a.counter, 1);
     for (;;) {
-        if (tid == 0) s_item = atomicAdd(a.counter, 1);
+        if (tid == 0) s_item = next;
         __syncthreads();
         const int i = s_item;
         if (i >= a.nb_items) return;
+        if (tid == 0) next = atomicAdd(a.counter, 1);      // the next command is claimed now: its round trip overlaps this one's work
         const ReconItemDev it = a.ritems[i];
         if (tid < (int)(sizeof(IntraCmdDev) / 4)) ((uint32_t *)&sg.cmd)[tid] = ((const uint32_t *)&a.cmds[it.cmd])[tid];
         if (tid == 32) sg.zero = 0;
@@ -138,11 +142,11 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
                 else { const int col = k - (2 * nh + 1); ux = xu + col; uy = yu - 1; bit = xl + col + 1; bit = bit < 64 ? (int)((c.avail_rows >> bit) & 1) : 0; }
                 if (bit && ux >= 0 && uy >= 0 && ux < a.w_u && uy < a.h_u) {
                     const uint32_t *f = a.pend + (size_t)uy * a.w_u + ux;
-                    while (recon_ld_acquire(f) == a.serial) __nanosleep(64);
+                    while (recon_ld_relaxed(f) == a.serial) __nanosleep(32);
                 }
             }
+            __threadfence();                                // acquire side of the units' release stores (fence.acq_rel.gpu)
             __syncthreads();
-            __threadfence();
         }
         // ---- prediction
         IntraK::Args ia = recon_intra_args(a, &sg.zero);
@@ -180,8 +184,7 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
                 TrK<32>::phase<3>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
             }
         }
-        // ---- publish: every thread's stores are ordered before the barrier above; fence, then release the units
-        __threadfence();
+        // ---- publish: every thread's stores are ordered before the barrier above; the release stores are cumulative over it
         for (int o = tid; o < nw * nh; o += 128) recon_st_release(a.pend + (size_t)(yu + o / nw) * a.w_u + xu + o % nw, 0u);
     }
 }
