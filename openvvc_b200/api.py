@@ -506,7 +506,7 @@ def mc_nb_items(cmds):
     """work items a PU list expands to: <=16x16 blocks of plain commands + one per BDOF / PROF command"""
     w = (1 << cmds["log2_w"].astype(np.int64)); h = (1 << cmds["log2_h"].astype(np.int64))
     n = ((w + 15) >> 4) * ((h + 15) >> 4)
-    return int(np.where(cmds["tool"] == 0, n, 1).sum())
+    return int(np.where((cmds["tool"] == 0) | (cmds["tool"] == 4), n, 1).sum())
 
 
 class SaoParams:

@@ -4,12 +4,22 @@
 #include "../../include/ovvc_b200.h"
 #include "mc_tools_kernels.h"
 
+// Which kernel runs a command: plain 4x4 luma-only commands (affine sub-blocks without PROF) take the packed 4x4 path of
+// ProfK (four sub-blocks per warp, refinement off) instead of a whole McK warp each.
+static inline int mc_route(const OVGPUMcCmd *c)
+{
+    if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA) return OVGPU_MC_TOOL_PROF;
+    // plain chroma-only commands of 8x8 luma samples (the chroma blocks of affine CUs): two per warp in McSmallCK
+    if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 3 && c->log2_h == 3 && (c->flags & 3) == OVGPU_MC_CHROMA && !(c->x0 & 3)) return MC_ROUTE_SMALL_C;
+    return c->tool == OVGPU_MC_TOOL_GPM ? OVGPU_MC_TOOL_PLAIN : c->tool;
+}
+
 // number of <=16x16 work items of the plain (tool 0) commands of a PU list
 static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
 {
     int total = 0;
     for (int i = 0; i < n; i++) {
-        if (cmds[i].tool != OVGPU_MC_TOOL_PLAIN && cmds[i].tool != OVGPU_MC_TOOL_GPM) continue;
+        if (mc_route(&cmds[i]) != OVGPU_MC_TOOL_PLAIN) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         total += ((w + 15) >> 4) * ((h + 15) >> 4);
     }
@@ -20,7 +30,7 @@ static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
 static inline int mc_count_tool_items(const OVGPUMcCmd *cmds, int n, int tool)
 {
     int total = 0;
-    for (int i = 0; i < n; i++) total += cmds[i].tool == tool;
+    for (int i = 0; i < n; i++) total += mc_route(&cmds[i]) == tool;
     return total;
 }
 
@@ -28,7 +38,7 @@ static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, 
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (cmds[i].tool != tool) continue;
+        if (mc_route(&cmds[i]) != tool) continue;
         items[k].cmd = (uint32_t)i; items[k].ox = items[k].oy = 0;
         items[k].w = (uint8_t)(1 << cmds[i].log2_w); items[k].h = (uint8_t)(1 << cmds[i].log2_h);
         k++;
@@ -62,7 +72,7 @@ static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (cmds[i].tool != OVGPU_MC_TOOL_PLAIN && cmds[i].tool != OVGPU_MC_TOOL_GPM) continue;
+        if (mc_route(&cmds[i]) != OVGPU_MC_TOOL_PLAIN) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         for (int oy = 0; oy < h; oy += 16)
             for (int ox = 0; ox < w; ox += 16) {

@@ -271,7 +271,9 @@ struct ProfK {
                 si[4 + 4 * r] = xs - x_al;
                 si[5 + 4 * r] = McToolCommon::filter_row(px, 0, 1) | (McToolCommon::filter_row(py, 0, 1) << 8);
                 si[6 + 4 * r] = ((px >> 3) != 0) | (((py >> 3) != 0) << 1);
-                if (r == 0) { si[1] = c.x0; si[2] = c.y0; si[3] = c.inter_dir | ((c.aux & 3) << 4) | (c.bcw_idx_plus1 << 8) | ((c.aux >> 8) << 12); }
+                // bit 2: a plain (tool 0) 4x4 luma command routed here by mc_route: same prediction, no refinement
+                if (r == 0) { si[1] = c.x0; si[2] = c.y0; si[3] = c.tool == 0 ? (c.inter_dir | 4 | (c.bcw_idx_plus1 << 8))
+                                                                              : (c.inter_dir | ((c.aux & 3) << 4) | (c.bcw_idx_plus1 << 8) | ((c.aux >> 8) << 12)); }
             }
             if (!used) return;
             const int ridx = r ? c.ref_idx1 : c.ref_idx0;
@@ -312,7 +314,7 @@ struct ProfK {
             // gradients + refinement: lane = (sub-block, list, row), 4 samples each
             const int r = (lane >> 2) & 1, y = lane & 3;
             if (!((inter_dir >> r) & 1)) return;
-            const int apply = inter_dir == 3 ? (prof_dir >> r) & 1 : 1;       // uni-prediction always refines (rcn_prof_mcp_l)
+            const int apply = (info & 4) ? 0 : (inter_dir == 3 ? (prof_dir >> r) & 1 : 1);       // uni-prediction always refines (rcn_prof_mcp_l)
             const int16_t *e = ex + (sb * 2 + r) * 16;
             const int16_t *dh = aa.prof[tab].dmv[2 * r], *dv = aa.prof[tab].dmv[2 * r + 1];
             const int ext = si[6 + 4 * r], c0 = si[4 + 4 * r] + 3 + (ext & 1), r0 = 3 + (ext >> 1), sh = 14 - a.bitdepth;
@@ -348,6 +350,98 @@ struct ProfK {
             }
             *(uint32_t *)(a.dst[0] + (size_t)(si[2] + y) * a.dst_pitch[0] + si[1] + x0) = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
         }
+    }
+};
+
+// =================================================================================================================
+// Small chroma blocks: plain (tool 0) chroma-only commands of 8x8 luma samples -- the Cb / Cr blocks of affine coding
+// units (one per 2x2 luma sub-blocks with the averaged MV, drv_affine_mvp.c:3380-3410; rcn_mcp_b_c, rcn_inter.c:2921).  A
+// whole McK warp per 4x4 chroma block wastes three quarters of its lanes; here a warp takes TWO commands:
+// lane = (command, component, list, column).  Same arithmetic as McK's chroma path (4-tap, rcn_mc.c:904-1100).
+#define MC_ROUTE_SMALL_C 5
+struct McSmallCK {
+    static const int THREADS = 128, MIN_BLOCKS = 6, PHASES = 3;
+    static const int WARPS = 4, SBS = 2;                     // 2 commands per warp
+    static const int WW = 6, WR = 7;                         // 12 samples x 7 rows per (command, component, list)
+    static const int SM_ITEM = SBS * 16, SM_WIN = SBS * 4 * WR * WW, SM_EX = SBS * 4 * 16 / 2;
+    static const int SM_WARP = (SM_ITEM + SM_WIN + SM_EX) * 4;
+    static const int SMEM_BYTES = WARPS * SM_WARP;
+    typedef McK::Args Args;
+    struct State { int dummy; };
+
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        const int warp = tid >> 5, lane = tid & 31;
+        uint32_t *sm = (uint32_t *)(smem + warp * SM_WARP);
+        int *sit = (int *)sm;                                // [command][16]
+        uint32_t *win = sm + SM_ITEM;                        // [command][component][list][row][word]
+        int16_t *ex = (int16_t *)(win + SM_WIN);             // [command][component][list][4][4] 14-bit predictions
+        const int sb = lane >> 4, item = (bx * WARPS + warp) * SBS + sb;
+        int *si = sit + sb * 16;
+        const int cw = a.pic_w >> 1, ch = a.pic_h >> 1;
+
+        if (P == 0) {
+            const int comp = (lane >> 3) & 1, r = (lane >> 2) & 1, cc = lane & 3;
+            if ((lane & 15) == 0) si[0] = item < a.nb_items;
+            if (item >= a.nb_items) return;
+            const McCmdDev c = a.cmds[a.items[item].cmd];
+            const int used = (c.inter_dir >> r) & 1;
+            int mvx = r ? c.mv1_x : c.mv0_x, mvy = r ? c.mv1_y : c.mv0_y;
+            McToolCommon::clip_mv(a.pic_w, a.pic_h, c.x0, c.y0, 8, 8, mvx, mvy);
+            const int xc = (c.x0 >> 1) + (mvx >> 5) - 1, yc = (c.y0 >> 1) + (mvy >> 5) - 1, xc_al = xc & ~3;
+            if (cc == 0 && comp == 0) {
+                si[4 + 2 * r] = xc - xc_al;
+                si[5 + 2 * r] = (mvx & 31) | ((mvy & 31) << 8);
+                if (r == 0) { si[1] = c.x0 >> 1; si[2] = c.y0 >> 1; si[3] = c.inter_dir | (c.bcw_idx_plus1 << 8); }
+            }
+            if (!used || cc >= 3) return;
+            const int ridx = r ? c.ref_idx1 : c.ref_idx0;
+            const uint16_t *pl = a.refs.plane[r][ridx][1 + comp];
+            const int pitch = a.refs.pitch[r][ridx][1 + comp];
+            uint32_t *wv = win + ((sb * 2 + comp) * 2 + r) * WR * WW;
+            if (xc_al >= 0 && xc_al + 2 * WW <= cw && yc >= 0 && yc + WR <= ch) {
+                ovd_u2 v[WR];
+#pragma unroll
+                for (int k = 0; k < WR; k++) v[k] = ovd_ld8(pl + (size_t)(yc + k) * pitch + xc_al + 4 * cc);
+#pragma unroll
+                for (int k = 0; k < WR; k++) { wv[k * WW + 2 * cc] = v[k].x; wv[k * WW + 2 * cc + 1] = v[k].y; }
+            } else {
+                for (int i = cc; i < WR * WW; i += 3) {
+                    const int row = i / WW, wd = i - row * WW;
+                    wv[i] = McK::load_pair(pl, pitch, cw, ch, xc_al + 2 * wd, yc + row);
+                }
+            }
+            return;
+        }
+        if (!si[0]) return;
+        const int info = si[3], inter_dir = info & 3, bcw_raw = (info >> 8) & 15;
+        if (P == 1) {
+            const int comp = (lane >> 3) & 1, r = (lane >> 2) & 1, x = lane & 3, sh1 = a.bitdepth - 8;
+            if (!((inter_dir >> r) & 1)) return;
+            const int o = si[4 + 2 * r] + x, frc = si[5 + 2 * r];
+            uint32_t Bh[3], Bv0[2], Bv1[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) { Bh[j] = mc_cw_c[frc & 0xff][o & 1][j]; Bv1[j] = mc_cw_c[frc >> 8][1][j]; }
+#pragma unroll
+            for (int j = 0; j < 2; j++) Bv0[j] = mc_cw_c[frc >> 8][0][j];
+            McK::column<4, 4, 3>(win + ((sb * 2 + comp) * 2 + r) * WR * WW + (o >> 1), WW, Bh, Bv0, Bv1, sh1, ex + ((sb * 2 + comp) * 2 + r) * 16 + x, 4);
+            return;
+        }
+        // combine + store: lane = (command, component, row, half): 2 samples
+        const int comp = (lane >> 3) & 1, y = (lane >> 1) & 3, x0 = (lane & 1) * 2, maxv = (1 << a.bitdepth) - 1;
+        const int bcw = (bcw_raw == 0 || bcw_raw == 3) ? 0 : bcw_raw;
+        const int w1 = bcw == 1 ? -2 : bcw == 2 ? 3 : bcw == 4 ? 5 : 10;
+        const int16_t *e0 = ex + ((sb * 2 + comp) * 2 + (inter_dir == 2 ? 1 : 0)) * 16, *e1 = ex + ((sb * 2 + comp) * 2 + 1) * 16;
+        int v[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = y * 4 + x0 + k;
+            v[k] = McK::combine(e0[i], inter_dir == 3 ? e1[i] : 0, inter_dir == 3 ? 2 : 1, bcw, w1, a.bitdepth, maxv);
+        }
+        uint16_t *d = (comp ? a.dst[2] : a.dst[1]) + (size_t)(si[2] + y) * (comp ? a.dst_pitch[2] : a.dst_pitch[1]) + si[1] + x0;
+        *(uint32_t *)d = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
     }
 };
 

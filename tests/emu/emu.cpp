@@ -104,13 +104,14 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
     for (int i = 0; i < nb_cmds; i++) if (mc_check_cmd(&cmds[i], nb_prof)) return -(i + 1);
     int n_dmvr = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_DMVR);
     int n_items = mc_count_items(cmds, nb_cmds), n_bdof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_BDOF),
-        n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
-    std::vector<McItemDev> items(n_items + n_bdof + n_prof + n_dmvr + 1);
+        n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF), n_sc = mc_count_tool_items(cmds, nb_cmds, MC_ROUTE_SMALL_C);
+    std::vector<McItemDev> items(n_items + n_bdof + n_prof + n_dmvr + n_sc + 1);
     std::vector<DmvrMvDev> dm(n_dmvr + 1);
     mc_build_tool_items(items.data() + n_items + n_bdof + n_prof, cmds, nb_cmds, OVGPU_MC_TOOL_DMVR);
     mc_build_items(items.data(), cmds, nb_cmds);
     mc_build_tool_items(items.data() + n_items, cmds, nb_cmds, OVGPU_MC_TOOL_BDOF);
     mc_build_tool_items(items.data() + n_items + n_bdof, cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
+    mc_build_tool_items(items.data() + n_items + n_bdof + n_prof + n_dmvr, cmds, nb_cmds, MC_ROUTE_SMALL_C);
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
@@ -133,13 +134,18 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
         t.mc = a; t.mc.items = items.data() + n_items + n_bdof; t.mc.nb_items = n_prof; t.prof = (const ProfInfoDev *)prof;
         ovd_emulate<ProfK>(t, ovd_dim3((n_prof + ProfK::WARPS * ProfK::SBS - 1) / (ProfK::WARPS * ProfK::SBS), 1, 1), ProfK::SMEM_BYTES);
     }
+    if (n_sc) {
+        McK::Args t = a;
+        t.items = items.data() + n_items + n_bdof + n_prof + n_dmvr; t.nb_items = n_sc;
+        ovd_emulate<McSmallCK>(t, ovd_dim3((n_sc + McSmallCK::WARPS * McSmallCK::SBS - 1) / (McSmallCK::WARPS * McSmallCK::SBS), 1, 1), McSmallCK::SMEM_BYTES);
+    }
     if (n_dmvr) {
         DmvrK::Args t;
         t.mc = a; t.mc.items = items.data() + n_items + n_bdof + n_prof; t.mc.nb_items = n_dmvr; t.out = dm.data();
         ovd_emulate<DmvrK>(t, ovd_dim3((n_dmvr + DmvrK::WARPS - 1) / DmvrK::WARPS, 1, 1), DmvrK::SMEM_BYTES);
         if (dmvr_out) memcpy(dmvr_out, dm.data(), sizeof(DmvrMvDev) * n_dmvr);
     }
-    return n_items + n_bdof + n_prof + n_dmvr;
+    return n_items + n_bdof + n_prof + n_dmvr + n_sc;
 }
 
 int emu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *d, int bitdepth)
