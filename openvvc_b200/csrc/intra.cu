@@ -139,8 +139,7 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
     a.plane[0] = v0.p; a.plane[1] = v1.p; a.plane[2] = v2.p; a.pitch[0] = v0.pitch; a.pitch[1] = v1.pitch; a.pitch[2] = v2.pitch;
     a.log2_ctu = b->log2_ctu; a.bitdepth = pic->bitdepth; a.plane_id = p; a.cmds = b->d_cmds; a.nb_items = nb_items;
     ovgpu_tu_recon_args(tu, p, &a);
-    a.pend = b->d_pend + (size_t)p * b->dev_units; a.serial = b->epoch;
-    if (getenv("OVGPU_DEBUG_RECON_NOWAIT")) a.serial = ~b->epoch;     // timing experiment only: nothing is ever pending (results are wrong) a.w_u = pic->width >> 2; a.h_u = pic->height >> 2;
+    a.pend = b->d_pend + (size_t)p * b->dev_units; a.serial = b->epoch; a.w_u = pic->width >> 2; a.h_u = pic->height >> 2;
     a.counter = b->d_counter + p;
     const int max_ctas = ctx->num_sms * blocks_per_sm;
     StageScope scope(ctx, OVGPU_STAGE_INTRA, 1);
