@@ -188,10 +188,10 @@ def run_reference(args, w, h):
     print(json.dumps(line))
 
 
-def workload_config(w, h, pics_per_step):
+def workload_config(w, h, pics_per_step, dev_streams=1):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
                         "(ISP, IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
-            "pictures_per_step": pics_per_step, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
+            "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
 
@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="4k", choices=sorted(SIZES))
     ap.add_argument("--pics", type=int, default=8, help="pictures per step per GPU")
+    ap.add_argument("--dev-streams", type=int, default=4, help="streams the device-resident pictures of a step are spread over")
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
     args = ap.parse_args()
     w, h = SIZES[args.size]
@@ -271,12 +272,21 @@ def main():
         dev.append(d)
     ctx.sync()
 
-    def run_stages(d):
-        api.recon_picture(ctx, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
-        lmcs.reshape(d["rec"], forward=False)
-        d["dbf"].run(d["rec"])
-        d["sao"].run(d["mid"], d["rec"])
-        d["alf"].run(d["dst"], d["mid"])
+    # Frame parallelism on one GPU: the pictures of a step are independent (same temporal layer), so they are spread over
+    # a few streams -- the latency-bound dataflow kernel of one picture then overlaps the throughput-bound kernels of the
+    # others, like the reference's frame threads overlap on the CPU (ovdec.h:47).  Stream 0 is the timed stream: the other
+    # streams start after an event recorded on it and it waits for their last kernels before the hand-off.
+    n_ds = max(1, min(args.dev_streams, P))
+    d_streams = [stream] + [torch.cuda.Stream() for _ in range(n_ds - 1)]
+    d_ctx = [ctx] + [api.Ctx(local, st.cuda_stream) for st in d_streams[1:]]
+
+    def run_stages(d, c=None):
+        c = c or ctx
+        api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
+        lmcs.reshape(d["rec"], forward=False, ctx=c)
+        d["dbf"].run(d["rec"], ctx=c)
+        d["sao"].run(d["mid"], d["rec"], ctx=c)
+        d["alf"].run(d["dst"], d["mid"], ctx=c)
 
     step_no = [0]
 
@@ -290,9 +300,21 @@ def main():
             api._check(ctx.h, api.lib().ovgpu_picture_copy(ctx.h, ref_pics[slot // 2][slot % 2].p, dev[0]["dst"].p), "picture_copy")
         ovdist.publish_reference(ref_shared[slot // 2][slot % 2], owner, world)
 
-    def step_device():
-        for d in dev:
-            run_stages(d)
+    def step_device(parallel=True):
+        if not parallel or n_ds == 1:
+            for d in dev:
+                run_stages(d)
+        else:
+            ev0 = torch.cuda.Event()
+            ev0.record(stream)
+            for st in d_streams[1:]:
+                st.wait_event(ev0)
+            for i, d in enumerate(dev):
+                run_stages(d, d_ctx[i % n_ds])
+            for st in d_streams[1:]:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                stream.wait_event(ev)
         hand_off_reference()
 
     def barrier():
@@ -309,7 +331,7 @@ def main():
     time.sleep(0.3)
 
     # ---- value: device-resident throughput, CUDA events on the launching stream
-    n0 = ctx.launch_count()
+    n0 = sum(c.launch_count() for c in d_ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
@@ -318,14 +340,14 @@ def main():
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count() - n0
+    launches = sum(c.launch_count() for c in d_ctx) - n0
 
     # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
     stage_names = ("mc", "residual", "intra", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
     ctx.profile(True); ctx.profile_reset()
     nprof = max(2, min(args.steps, 5))
     for _ in range(nprof):
-        step_device()
+        step_device(parallel=False)          # stage by stage on one stream: per-kernel times without overlap
     prof = {s: ctx.profile_get(s) for s in stage_names}
     ctx.profile(False)
 
@@ -351,38 +373,52 @@ def main():
         for k in range(3):
             st["qp"][k][:] = p["dbf"]["qp"][k]
 
-    def e2e_worker(t):
+    def e2e_worker(t, ev_start):
         """one host thread per context, like the reference's frame threads (ovdec.h:47): stages, commits and launches its
-        pictures; ctypes releases the GIL inside the C-ABI calls, so the host-side work of different pictures overlaps"""
+        pictures; ctypes releases the GIL inside the C-ABI calls, so the host-side work of different pictures overlaps.
+        Nothing here waits for the GPU: staging + H2D of a step run while the kernels of the previous step are still
+        busy (the staging fences of the C ABI keep a pinned buffer from being rewritten before its last copy left);
+        only the kernels wait, on the device, for the previous step's reference hand-off (ev_start)."""
         torch.cuda.set_device(local)
-        c = e_ctx[t]
+        c, st = e_ctx[t], e_streams[t]
+        prof_host = os.environ.get("BENCH_HOST_PROFILE") and t == 0
         for i in range(t, len(dev), n_ctx):
             p, d = pics[i], dev[i]
-            d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c)
+            tt = [time.perf_counter()]
+            d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c); tt.append(time.perf_counter())
             d["tu"].set_anchors(p["anchors"], ctx=c)
-            d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c)
-            d["intra"].upload(p["icmds"], w, h, 7, ctx=c)
-            d["dbf"].commit(0, 0, ctx=c)
+            d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c); tt.append(time.perf_counter())
+            d["intra"].upload(p["icmds"], w, h, 7, ctx=c); tt.append(time.perf_counter())
+            d["dbf"].commit(0, 0, ctx=c); tt.append(time.perf_counter())
             d["sao"].upload(p["sao"], ctx=c)
-            d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c)
-            api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
+            d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c); tt.append(time.perf_counter())
+            if st is not stream:
+                st.wait_event(ev_start)
+            api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs); tt.append(time.perf_counter())
+            if prof_host:
+                sys.stderr.write("host ms: mc_commit %.2f tu_commit %.2f intra_upload %.2f dbf_commit %.2f sao+alf %.2f recon_call %.2f\n"
+                                 % tuple(1e3 * (b - a) for a, b in zip(tt, tt[1:])))
             lmcs.reshape(d["rec"], forward=False, ctx=c)
             d["dbf"].run(d["rec"], ctx=c)
             d["sao"].run(d["mid"], d["rec"], ctx=c)
             d["alf"].run(d["dst"], d["mid"], ctx=c)
             api._check(c.h, api.lib().ovgpu_picture_download(c.h, d["dst"].p, *api._host_planes(np_out[i])), "download")
-        c.sync()
+        ev = torch.cuda.Event()
+        ev.record(st)
+        return ev
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=n_ctx)
 
     def step_e2e():
-        for f in [pool.submit(e2e_worker, t) for t in range(n_ctx)]:
-            f.result()
+        ev_start = torch.cuda.Event()
+        ev_start.record(stream)                     # after the previous step's hand-off
+        for ev in [f.result() for f in [pool.submit(e2e_worker, t, ev_start) for t in range(n_ctx)]]:
+            stream.wait_event(ev)                   # the timed stream joins the step's pictures on the device, not on the host
         hand_off_reference()
 
     step_e2e()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(2, args.steps)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -421,7 +457,7 @@ def main():
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",
-                "config": workload_config(w, h, P),
+                "config": workload_config(w, h, P, n_ds),
                 "gpu_launches": launches,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": n_ctx, "host_threads": n_ctx},

@@ -43,6 +43,9 @@ int ovgpu_intra_batch_create(OVGPUCtx *ctx, int max_cmds, OVGPUIntraBatch **out)
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
     }
     b->lv.start[1] = b->lv.start[0] + max_cmds + 3;
+    b->lv.ws_lvl = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (size_t)max_cmds);
+    b->lv.ws_fill = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)max_cmds + 3));
+    if (!b->lv.ws_lvl || !b->lv.ws_fill) { ovgpu_intra_batch_destroy(b); return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra level scratch"); }
     b->lv.order[0] = b->h_order; b->lv.order[1] = b->h_order + max_cmds;
     *out = b;
     return 0;
@@ -57,7 +60,7 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_order) cudaFree(b->d_order);
     free(b->lv.start[0]);
-    free(b->pos_l); free(b->pos_c);
+    free(b->pos_l); free(b->pos_c); free(b->lv.ws_map); free(b->lv.ws_lvl); free(b->lv.ws_fill);
     if (b->d_pend) cudaFree(b->d_pend);
     if (b->d_counter) cudaFree(b->d_counter);
     fence_destroy(&b->fence);
@@ -77,9 +80,10 @@ int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntra
     b->serial++;
     const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
     if (units > b->map_units) {
-        free(b->pos_l); free(b->pos_c);
+        free(b->pos_l); free(b->pos_c); free(b->lv.ws_map);
         b->pos_l = (uint32_t *)malloc(units * sizeof(uint32_t)); b->pos_c = (uint32_t *)malloc(units * sizeof(uint32_t));
-        b->map_units = (b->pos_l && b->pos_c) ? units : 0;
+        b->lv.ws_map = (uint16_t *)malloc(units * sizeof(uint16_t));
+        b->map_units = (b->pos_l && b->pos_c && b->lv.ws_map) ? units : 0;
         if (!b->map_units) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra position maps");
     }
     if (!nb_cmds) { memset(b->pos_l, 0, units * sizeof(uint32_t)); memset(b->pos_c, 0, units * sizeof(uint32_t)); return 0; }

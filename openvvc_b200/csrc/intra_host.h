@@ -34,6 +34,9 @@ struct IntraLevels {
     int nb[2];
     uint32_t *order[2];      // n entries each
     uint32_t *start[2];      // n + 2 entries each
+    // optional caller-owned scratch (a per-picture malloc / free of megabytes costs page faults and serialises host threads
+    // on the process's memory-map lock): level map of w/4 x h/4 uint16, 2 * n uint16, n + 3 uint32
+    uint16_t *ws_map; uint16_t *ws_lvl; uint32_t *ws_fill;
 };
 
 static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu, int yu, int nw, int nh)
@@ -52,9 +55,11 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
 {
     const int w_u = pic_w >> 2, h_u = pic_h >> 2;
     uint32_t *pos[2] = { pos_l, pos_c };
-    uint16_t *map[2] = { (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)), (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)) };
-    uint16_t *lvl = (uint16_t *)malloc(sizeof(uint16_t) * 2 * (n > 0 ? n : 1));
-    uint32_t *fill = (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 3));
+    const int own = !L->ws_map;
+    uint16_t *map1 = own ? (uint16_t *)malloc((size_t)w_u * h_u * sizeof(uint16_t)) : L->ws_map;       // one plane at a time
+    uint16_t *map[2] = { map1, map1 };
+    uint16_t *lvl = own ? (uint16_t *)malloc(sizeof(uint16_t) * 2 * (n > 0 ? n : 1)) : L->ws_lvl;
+    uint32_t *fill = own ? (uint32_t *)malloc(sizeof(uint32_t) * ((size_t)n + 3)) : L->ws_fill;
     int ret = -1;
     L->nb[0] = L->nb[1] = 0;
     if (map[0] && map[1] && lvl && fill) {
@@ -97,7 +102,7 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
             }
         }
     }
-    free(fill); free(lvl); free(map[0]); free(map[1]);
+    if (own) { free(fill); free(lvl); free(map1); }
     return ret;
 }
 
