@@ -235,19 +235,29 @@ struct McK {
         const uint32_t w0[4] = { q0.x, q0.y, q0.z, q0.w }, w1v[4] = { q1.x, q1.y, q1.z, q1.w };
         uint32_t o[4];
         (void)plane;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int va, vb;
-            if (gpm) {      // put_weighted_gpm_bi_pixels: the BCW formula with a per-sample weight, w1 = 8 - w0
-                va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), 2, 1, 8 - gpm_weight(gg, gx + (2 * k) * gstep, gy), a.bitdepth, maxv);
-                vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), 2, 1, 8 - gpm_weight(gg, gx + (2 * k + 1) * gstep, gy), a.bitdepth, maxv);
-            } else {
-                va = combine((int16_t)(w0[k] & 0xffff), (int16_t)(w1v[k] & 0xffff), nref, bcw, w1, a.bitdepth, maxv);
-                vb = combine((int16_t)(w0[k] >> 16), (int16_t)(w1v[k] >> 16), nref, bcw, w1, a.bitdepth, maxv);
-            }
-            if (lut) { va = a.lmcs_fwd[va]; vb = a.lmcs_fwd[vb]; }
-            o[k] = (uint32_t)va | ((uint32_t)vb << 16);
+        // one warp-uniform choice of the combination, then a straight loop: the per-sample code holds only that formula
+        const int bd = a.bitdepth;
+#define MC_ROW(EXPR_A, EXPR_B)                                                                     \
+        _Pragma("unroll")                                                                          \
+        for (int k = 0; k < 4; k++) {                                                              \
+            const int a0 = (int16_t)(w0[k] & 0xffff), a1 = (int16_t)(w0[k] >> 16);                \
+            const int b0 = (int16_t)(w1v[k] & 0xffff), b1 = (int16_t)(w1v[k] >> 16);              \
+            (void)b0; (void)b1;                                                                    \
+            int va = ovd_clamp(EXPR_A, 0, maxv), vb = ovd_clamp(EXPR_B, 0, maxv);                  \
+            if (lut) { va = a.lmcs_fwd[va]; vb = a.lmcs_fwd[vb]; }                                 \
+            o[k] = (uint32_t)va | ((uint32_t)vb << 16);                                            \
         }
+        if (gpm) {              // put_weighted_gpm_bi_pixels: the BCW formula with a per-sample weight, w1 = 8 - w0
+            MC_ROW((b0 * (8 - gpm_weight(gg, gx + (2 * k) * gstep, gy)) + a0 * gpm_weight(gg, gx + (2 * k) * gstep, gy) + (1 << (16 - bd))) >> (17 - bd),
+                   (b1 * (8 - gpm_weight(gg, gx + (2 * k + 1) * gstep, gy)) + a1 * gpm_weight(gg, gx + (2 * k + 1) * gstep, gy) + (1 << (16 - bd))) >> (17 - bd))
+        } else if (nref == 1) {
+            MC_ROW((a0 + (1 << (13 - bd))) >> (14 - bd), (a1 + (1 << (13 - bd))) >> (14 - bd))
+        } else if (!bcw) {
+            MC_ROW((a0 + b0 + (1 << (14 - bd))) >> (15 - bd), (a1 + b1 + (1 << (14 - bd))) >> (15 - bd))
+        } else {
+            MC_ROW((b0 * w1 + a0 * (8 - w1) + (1 << (16 - bd))) >> (17 - bd), (b1 * w1 + a1 * (8 - w1) + (1 << (16 - bd))) >> (17 - bd))
+        }
+#undef MC_ROW
         // block positions are multiples of 4 luma samples only (ternary splits): pick the widest aligned store
         const unsigned al = (unsigned)(uintptr_t)d;
         if (n >= 8 && !(al & 15)) { ovd_u4 r; r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3]; ovd_st16(d, r); }

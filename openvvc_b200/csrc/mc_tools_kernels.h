@@ -57,8 +57,9 @@ struct BdofCore {
     // gradients of the interior (compute_prof_grad, rcn_prof_bdof.c:153-171): G = [gx0, gy0, gx1, gy1][16][16]
     OVD void grad(const int16_t *ex, int16_t *G, int iw, int ih, const Ring *ring, int sh, int lane)
     {
+        const int lw = iw == 16 ? 4 : 3;                                   // sub-blocks are 8 or 16 samples wide: no integer division
         for (int i = lane; i < iw * ih; i += 32) {
-            const int x = i % iw, y = i / iw;
+            const int x = i & (iw - 1), y = i >> lw;
 #pragma unroll
             for (int r = 0; r < 2; r++) {
                 const int gx = ((pint(ex, ring[r], r, x + 1, y, iw, ih, sh) - 8192) >> 6) - ((pint(ex, ring[r], r, x - 1, y, iw, ih, sh) - 8192) >> 6);
@@ -74,7 +75,7 @@ struct BdofCore {
     {
         const int sb = lane >> 1, half = lane & 1, nsx = iw >> 2, nsb = nsx * (ih >> 2);
         if (sb >= nsb) return;
-        const int sx = (sb % nsx) * 4, sy = (sb / nsx) * 4;
+        const int sx = (sb & (nsx - 1)) * 4, sy = (sb >> (nsx >> 1)) * 4;    // nsx is 2 or 4
         int s_ax = 0, s_ay = 0, s_dx = 0, s_dy = 0, s_sign = 0;
         for (int i = 3 * half; i < 3 * half + 3; i++) {
             const int y = ovd_clamp(sy + i - 1, 0, ih - 1);
@@ -553,7 +554,8 @@ struct DmvrK {
             // bilinear samples at window positions (j - 2, i - 2); sample (x, y) of the padded window sits at column x + 5
             const int n = (ih + 4) * (iw + 4);
             for (int o = lane; o < 2 * n; o += 32) {
-                const int r = o >= n, k = o - r * n, i = k / (iw + 4), j = k - i * (iw + 4);
+                // iw + 4 is 12 or 20: a warp-uniform choice between two constant divisors instead of a run-time division
+                const int r = o >= n, k = o - r * n, i = iw == 16 ? k / 20 : k / 12, j = k - i * (iw + 4);
                 const int fx = sit[8 + 2 * r] & 15, fy = sit[9 + 2 * r] & 15;
                 const uint16_t *s = pw16 + (r * PWR + i + 3) * (2 * PWW) + j + 3;
                 int v;

@@ -49,7 +49,7 @@ OVD_CONST uint8_t tr_wide_shift[6] = { 0, 6, 10, 12, 14, 15 };                  
 
 template <int GROUP>
 struct TrK {
-    static const int THREADS = 128, MIN_BLOCKS = (GROUP == 32 ? 4 : 2), PHASES = 4;
+    static const int THREADS = 128, MIN_BLOCKS = 8, PHASES = 4;       // <= 64 registers: the line-tiled passes would otherwise take 80+
     static const int GROUPS = THREADS / GROUP;
     // shared memory per group, int16 units (see the size derivation in DESIGN.md "Residual")
     static const int SM_CT = GROUP == 32 ? 320 : 32 * 34;     // dequantised block, transposed: [x][k = y], line stride kv4 + 2
@@ -203,21 +203,31 @@ struct TrK {
         return (int16_t)ovd_clamp((sum + 64) >> 7, -32768, 32768);       // sic: +32768 wraps in the int16 store (rcn_lfnst.c:64)
     }
 
-    // one 1-D pass: out[j][line] = clip16((sum_k in[line][k] * T[j][k] + rnd) >> shift)
+    // one 1-D pass: out[j][line] = clip16((sum_k in[line][k] * T[j][k] + rnd) >> shift).  A thread owns output j of L
+    // consecutive lines: one matrix word (fetched once, pointer stepped instead of re-derived) feeds 2 * L IDP.2A.
     OVD void tr_pass(const int16_t *in, int ls, int nlines, int log2n, int k4n, const uint32_t *Tw, int shift,
                      int16_t *out, int out_sj, int out_sl, int gt)
     {
-        const int n = 1 << log2n, total = nlines << log2n, rnd = 1 << (shift - 1);
+        const int L = GROUP == 32 ? 2 : 4;
+        const int n = 1 << log2n, total = ((nlines + L - 1) / L) << log2n, rnd = 1 << (shift - 1);
         for (int o = gt; o < total; o += GROUP) {
-            const int j = o & (n - 1), line = o >> log2n;
-            const uint32_t *iw = (const uint32_t *)(in + line * ls);
-            int acc = 0;
-            for (int k4 = 0; k4 < k4n; k4++) {
-                const uint32_t tw = Tw[k4 * n + j];
-                acc = ovd_dp2a_lo(iw[2 * k4], tw, acc);
-                acc = ovd_dp2a_hi(iw[2 * k4 + 1], tw, acc);
+            const int j = o & (n - 1), line0 = (o >> log2n) * L;
+            const uint32_t *tp = Tw + j;
+            const uint32_t *iw[L];
+            int acc[L];
+#pragma unroll
+            for (int l = 0; l < L; l++) { iw[l] = (const uint32_t *)(in + ovd_min(line0 + l, nlines - 1) * ls); acc[l] = 0; }
+            for (int k4 = 0; k4 < k4n; k4++, tp += n) {
+                const uint32_t tw = *tp;
+#pragma unroll
+                for (int l = 0; l < L; l++) {
+                    acc[l] = ovd_dp2a_lo(iw[l][2 * k4], tw, acc[l]);
+                    acc[l] = ovd_dp2a_hi(iw[l][2 * k4 + 1], tw, acc[l]);
+                }
             }
-            out[j * out_sj + line * out_sl] = (int16_t)ovd_clamp((acc + rnd) >> shift, -32768, 32767);
+#pragma unroll
+            for (int l = 0; l < L; l++)
+                if (line0 + l < nlines) out[j * out_sj + (line0 + l) * out_sl] = (int16_t)ovd_clamp((acc[l] + rnd) >> shift, -32768, 32767);
         }
     }
 
