@@ -32,7 +32,7 @@ OVD uint32_t alf_odd_pair(uint32_t w0, uint32_t w1) { return ovd_byte_perm(w0, w
 // =========================================================================================================
 template <bool WIDE>
 struct AlfLumaK {
-    static const int THREADS = 256, MIN_BLOCKS = 2, PHASES = 3;
+    static const int THREADS = 256, MIN_BLOCKS = 3, PHASES = 3;          // 80 registers: 3 CTAs / SM (was 128 -> 2)
     static const int TW = 128, TH = 32;
     static const int PIX_STRIDE = TW + 8;            // samples; halo of 4 left/right keeps 8-byte alignment
     static const int PIX_ROWS = TH + 6;
@@ -168,8 +168,9 @@ struct AlfLumaK {
     // ---- phase 2: class of the thread's 4x4 block, then filter it -----------------------------------------------
     OVD void tap(int &acc0, int &acc1, uint32_t na, uint32_t nb, uint32_t neg_p, const uint32_t *e, int k)
     {
-        uint32_t t1 = ovd_vmax_s16x2(ovd_viaddmin_s16x2(na, neg_p, e[12 + k]), e[24 + k]);
-        uint32_t t2 = ovd_vmax_s16x2(ovd_viaddmin_s16x2(nb, neg_p, e[12 + k]), e[24 + k]);
+        const uint32_t ncl = ovd_vsub_16x2(0u, e[12 + k]);          // -clip, recomputed: 12 fewer live registers than a third table row
+        uint32_t t1 = ovd_vmax_s16x2(ovd_viaddmin_s16x2(na, neg_p, e[12 + k]), ncl);
+        uint32_t t2 = ovd_vmax_s16x2(ovd_viaddmin_s16x2(nb, neg_p, e[12 + k]), ncl);
         uint32_t s = ovd_vadd_16x2(t1, t2);
         if (WIDE) {
             int c = (int)e[k];
@@ -262,31 +263,33 @@ struct AlfLumaK {
         const int entry = derive_class(svh & 0xffff, svh >> 16, sdd & 0xffff, sdd >> 16, a.bitdepth + 4, near_vb);
 
         // ---- coefficients of (transpose, class)
-        uint32_t e[ALF_TAB_ENTRY_WORDS];
+        uint32_t e[24];                                             // coefficient operands + clips (the -clip row of the table is not read)
         {
             const ovd_u4 *tp = (const ovd_u4 *)(tab + entry * ALF_TAB_ENTRY_WORDS);
 #pragma unroll
-            for (int i = 0; i < ALF_TAB_ENTRY_WORDS / 4; i++) {
+            for (int i = 0; i < 24 / 4; i++) {
                 ovd_u4 q = tp[i];
                 e[4 * i] = q.x; e[4 * i + 1] = q.y; e[4 * i + 2] = q.z; e[4 * i + 3] = q.w;
             }
         }
 
-        // ---- 10 rows x 12 samples around the block
+        // ---- 10 rows x 12 samples around the block; row r is first needed by output row r - 6, so rows 7..9 are loaded
+        // inside the row loop: seven rows (42 registers) are live at a time instead of ten
         uint32_t R[10][6];
         const ovd_u2 *pp = (const ovd_u2 *)(pix + (4 * byi) * PIX_STRIDE + 4 * bxi);
-#pragma unroll
-        for (int r = 0; r < 10; r++) {
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                ovd_u2 v = pp[r * (PIX_STRIDE / 4) + q];
-                R[r][2 * q] = v.x; R[r][2 * q + 1] = v.y;
-            }
+#define ALF_LOAD_ROW(r_)                                                                   \
+        _Pragma("unroll")                                                                   \
+        for (int q = 0; q < 3; q++) {                                                       \
+            ovd_u2 v = pp[(r_) * (PIX_STRIDE / 4) + q];                                     \
+            R[r_][2 * q] = v.x; R[r_][2 * q + 1] = v.y;                                     \
         }
+#pragma unroll
+        for (int r = 0; r < 7; r++) { ALF_LOAD_ROW(r) }
 
         uint16_t *drow = a.dst + (size_t)(t.y0 + 4 * byi) * a.dst_pitch + t.x0 + 4 * bxi;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            if (j > 0) { ALF_LOAD_ROW(j + 6) }
             const int y_vb = (t.y0 + 4 * byi + j) & (ctu_s - 1);
             // rows near the virtual boundary do not reach across it (rcn_alf.c:1200-1221)
             int reach = 3;
@@ -311,6 +314,7 @@ struct AlfLumaK {
             }
             ovd_st8(drow + (size_t)j * a.dst_pitch, o);
         }
+#undef ALF_LOAD_ROW
     }
 };
 
