@@ -81,7 +81,7 @@ OVD int gpm_weight(const GpmGeom &g, int x, int y)
 }
 
 struct McK {
-    static const int THREADS = 128, MIN_BLOCKS = 6, PHASES = 3;
+    static const int THREADS = 128, MIN_BLOCKS = 8, PHASES = 3;
     static const int WARPS = 4;
     // per-warp shared memory, 32-bit words
     static const int WIN_Y_WORDS = 14, WIN_Y_ROWS = 23;      // 28 samples x (16 + 7) rows per list

@@ -131,7 +131,7 @@ struct BdofCore {
 
 // =================================================================================================================
 struct BdofK {
-    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 5;
+    static const int THREADS = 128, MIN_BLOCKS = 6, PHASES = 5;
     static const int WARPS = 4;
     static const int WW = McK::WIN_Y_WORDS, WR = McK::WIN_Y_ROWS;
     static const int SM_ITEM = 16, SM_WIN = 2 * WR * WW, SM_EX = 2 * 16 * 16 / 2, SM_G = 4 * 16 * 16 / 2, SM_PART = 16 * 2 * 5;
@@ -461,7 +461,7 @@ struct McSmallCK {
 struct DmvrMvDev { int32_t mv0_x, mv0_y, mv1_x, mv1_y; };      // == OVGPUDmvrMv
 
 struct DmvrK {
-    static const int THREADS = 128, MIN_BLOCKS = 2, PHASES = 8;
+    static const int THREADS = 128, MIN_BLOCKS = 3, PHASES = 8;
     static const int WARPS = 4;
     static const int PWW = 14, PWR = 27, PCW = 8, PCR = 15, BLS = 20;
     static const int SM_ITEM = 32, SM_PW = 2 * PWR * PWW, SM_PWC = 2 * 2 * PCR * PCW, SM_BL = 2 * BLS * BLS / 2, SM_SAD = 32,
