@@ -101,6 +101,28 @@ def make_workload(w, h, n_pics, seed0=5000):
     return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), pics=pics)
 
 
+STAGE_KERNELS = {"mc": ("McK", "BdofK", "DmvrK", "ProfK", "McSmallCK"), "residual": ("TrK",), "intra": ("ovd_recon_kernel", "ReconPrepK"),
+                 "lmcs": ("Lmcs",), "dbf_v": ("DbfK<0>",), "dbf_h": ("DbfK<1>",), "sao": ("SaoK",), "alf_luma": ("AlfLumaK",),
+                 "alf_chroma": ("AlfChromaK",)}
+
+
+def ncu_traffic(stage):
+    """DRAM bytes (read + write) per picture of a stage's kernels, from the newest committed `ncu --set full` summary under
+    profiles/ (tools/ncu_summary.py; a capture of the same command with --pics 1).  None when there is no summary."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_ncu_full_all_stages_v*.json")),
+                   key=lambda f: int(re.search(r"_v(\d+)", f).group(1)))
+    if not files:
+        return None, None
+    launches = json.load(open(files[-1]))["launches"]
+    pics = max(1, sum("AlfLumaK" in l["kernel"] for l in launches))
+    sel = [l for l in launches if any(k in l["kernel"] for k in STAGE_KERNELS[stage])]
+    if not sel:
+        return None, os.path.basename(files[-1])
+    return 1e6 * sum(l.get("dram_read_MB", 0.0) + l.get("dram_write_MB", 0.0) for l in sel) / pics, os.path.basename(files[-1])
+
+
 def residual_bytes(tus):
     """Algorithmic bytes of the residual stage: coded coefficient sub-blocks (32 B each) + read-modify-write of the
     samples of every coded transform block."""
@@ -451,7 +473,8 @@ def main():
                 # group of launches per dependency level, the MC stage one kernel per tool)
                 avg = t_ms / (nprof * P)
                 stages[s] = {"avg_launch_ms": avg, "scopes_per_picture": n / (nprof * P), "algorithmic_bytes": alg[s],
-                             "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9, "frac": alg[s] / (avg * 1e-3) / 1e9 / peak}
+                             "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9, "frac": alg[s] / (avg * 1e-3) / 1e9 / peak,
+                             "traffic": ncu_traffic(s)[0]}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
         h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -462,7 +485,8 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": n_ctx, "host_threads": n_ctx},
                 "roofline": {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak,
-                             "peak_source": peak_src, "unit": "GB/s", "frac": stages[top]["frac"], "traffic": None,
+                             "peak_source": peak_src, "unit": "GB/s", "frac": stages[top]["frac"], "traffic": ncu_traffic(top)[0],
+                             "traffic_source": ncu_traffic(top)[1],
                              "algorithmic_bytes_per_launch": stages[top]["algorithmic_bytes"],
                              "avg_launch_ms": stages[top]["avg_launch_ms"]},
                 "stages": stages, "mc_dirs_per_sample": dirs,
