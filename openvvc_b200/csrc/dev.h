@@ -89,6 +89,12 @@ OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return min(a, b); }
 #endif
 
 OVD int ovd_clamp(int v, int lo, int hi) { return ovd_min(ovd_max(v, lo), hi); }
+// floor(log2(v)) for v >= 1, 0 for v == 0 (one FLO instead of a shift loop)
+#ifdef OVGPU_HOST_EMU
+OVD int ovd_floor_log2(unsigned v) { return v > 1 ? 31 - __builtin_clz(v) : 0; }
+#else
+OVD int ovd_floor_log2(unsigned v) { return v > 1 ? 31 - __clz((int)v) : 0; }
+#endif
 
 // ---- global memory access ----------------------------------------------------------------------------------
 struct ovd_u2 { uint32_t x, y; };

@@ -77,7 +77,7 @@ struct IntraK {
         uint64_t cols, rows;
     };
 
-    OVD int floor_log2(unsigned v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
+    OVD int floor_log2(unsigned v) { return ovd_floor_log2(v); }
     OVD int pdpc_w(int scale, int pos) { const int s = (pos << 1) >> scale; return s > 5 ? 0 : 32 >> s; }
 
     OVD Blk load(const Args &a, int idx, int comp)

@@ -43,7 +43,7 @@ struct BdofCore {
     // is the 16-bit sample (col0 + x, row0 + y) of a window stored as packed pairs with ww words per row
     struct Ring { const uint32_t *win; int ww, col0, row0; };
 
-    OVD int floor_log2(unsigned v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
+    OVD int floor_log2(unsigned v) { return ovd_floor_log2(v); }
     OVD int ring_sample(const Ring &g, int x, int y, int sh)
     {
         const int col = g.col0 + x;
@@ -463,7 +463,7 @@ struct DmvrMvDev { int32_t mv0_x, mv0_y, mv1_x, mv1_y; };      // == OVGPUDmvrMv
 struct DmvrK {
     static const int THREADS = 128, MIN_BLOCKS = 3, PHASES = 8;
     static const int WARPS = 4;
-    static const int PWW = 14, PWR = 27, PCW = 8, PCR = 15, BLS = 20;
+    static const int PWW = 14, PWR = 27, PCW = 8, PCR = 15, BLS = 20;      // PCW must stay 8 (phase 0 splits indices with shifts)
     static const int SM_ITEM = 32, SM_PW = 2 * PWR * PWW, SM_PWC = 2 * 2 * PCR * PCW, SM_BL = 2 * BLS * BLS / 2, SM_SAD = 32,
                      SM_EX = 256, SM_EXC = 128, SM_G = 512, SM_PART = 160;
     static const int SM_WARP = (SM_ITEM + SM_PW + SM_PWC + SM_BL + SM_SAD + SM_EX + SM_EXC + SM_G + SM_PART) * 4;
@@ -532,7 +532,7 @@ struct DmvrK {
                 }
                 const int bxc = (c.x0 >> 1) + (mvx >> 5), byc = (c.y0 >> 1) + (mvy >> 5);
                 for (int i = lane; i < 2 * (hc + 7) * PCW; i += 32) {
-                    const int comp = i / ((hc + 7) * PCW), k = i - comp * (hc + 7) * PCW, row = k / PCW, wd = k - row * PCW;
+                    const int nc1 = (hc + 7) * PCW, comp = i >= nc1, k = i - comp * nc1, row = k >> 3, wd = k & 7;          // PCW == 8: no division
                     const uint16_t *plc = a.refs.plane[r][ridx][1 + comp];
                     const int pitch_c = a.refs.pitch[r][ridx][1 + comp];
                     const int y = ovd_clamp(byc + ovd_clamp(row - 3, -1, hc + 1), 0, ch - 1);
