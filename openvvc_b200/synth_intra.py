@@ -10,11 +10,11 @@ INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), 
                       ("avail_cols", np.uint64), ("avail_rows", np.uint64)])
 assert INTRA_CMD.itemsize == 32
 
-INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED, INTRA_MIP = 1, 2, 4, 8, 16
+INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED, INTRA_MIP, INTRA_ISP, INTRA_ISP_VER = 1, 2, 4, 8, 16, 32, 64
 
 
 def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0,
-                   collocated=False, p_inter=0.0, blocks=None, p_mip=0.0):
+                   collocated=False, p_inter=0.0, blocks=None, p_mip=0.0, p_isp=0.0):
     """p_inter: fraction of coding units that are NOT intra (flags = 0 placeholders): they keep the picture's samples -- the
     already reconstructed inter CUs of a real picture -- and only take part in the availability replay.  Without them an
     all-intra picture without residual degenerates to the mid value everywhere.  The placeholders are for the oracle
@@ -50,12 +50,18 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
             nm = 16 if (lw == 2 and lh == 2) else (8 if (lw == 2 or lh == 2 or (lw <= 3 and lh <= 3)) else 6)
             c["flags"] |= INTRA_MIP
             c["mode"] = (int(rng.integers(0, 2)) << 7) | int(rng.integers(0, nm))
+        if p_isp and not (c["flags"] & (INTRA_CIIP | INTRA_MIP)) and not c["mrl_idx"] and lw + lh >= 5 and rng.random() < p_isp:
+            # ISP (10 % of intra CUs): whole luma coding block, split direction in the flags; the per-partition
+            # transform blocks and availability words live in the ISP table (isp_info), indexed through pad[0..1]
+            c["flags"] |= INTRA_ISP | (INTRA_ISP_VER if rng.random() < 0.5 else 0)
     return cmds
 
 
-def availability(w, h, cmds, log2_ctu=7):
+def availability(w, h, cmds, log2_ctu=7, isp_words=None):
     """avail_cols / avail_rows of every command = progress_field.vfield[x0 >> 2] / .hfield[y0 >> 2] at call time
-    (init_ctu_bitfield(_border), drv_utils.h:110-260; ctu_field_set_rect_bitfield :46-72), replayed from the decode order."""
+    (init_ctu_bitfield(_border), drv_utils.h:110-260; ctu_field_set_rect_bitfield :46-72), replayed from the decode order.
+    isp_words (ISP_WORDS array, filled in place): the words vvc_intra_pred_isp reads for the partitions of ISP commands, taken
+    after the whole coding block has been marked (vcl_transform_unit.c:1878)."""
     ctu = 1 << log2_ctu
     n_u = ctu >> 2
     ncw, nch = -(-w // ctu), -(-h // ctu)
@@ -98,4 +104,101 @@ def availability(w, h, cmds, log2_ctu=7):
             hf[yu + i] |= ((1 << nw) - 1) << (1 + xu)
         for i in range(1, nw + 1):
             vf[xu + i] |= ((1 << nh) - 1) << (1 + yu)
+        if isp_words is not None and (int(c["flags"]) & INTRA_ISP):
+            wd = isp_words[int(c["pad"][0]) | (int(c["pad"][1]) << 8)]
+            ver = bool(int(c["flags"]) & INTRA_ISP_VER)
+            lp, nb = isp_partitions(int(c["log2_w"]), int(c["log2_h"]), ver)
+            wd["common"] = np.uint64((hf[y0 >> 2] if ver else vf[x0 >> 2]) & 0xFFFFFFFFFFFFFFFF)
+            q = 0
+            for i in range(nb):
+                off = i << lp
+                if ver and (off & 3):
+                    continue
+                v = vf[(x0 + off) >> 2] if ver else hf[((y0 + off) >> 2) + (1 if (y0 + off) % 4 else 0)]
+                wd["part"][q] = np.uint64(v & 0xFFFFFFFFFFFFFFFF)
+                q += 1
     return out
+
+
+# == OVGPUIspInfo / the head of OVOIspInfo: availability words of an ISP coding unit
+ISP_WORDS = np.dtype([("common", np.uint64), ("part", np.uint64, 4)])
+
+
+def isp_partitions(lw, lh, ver):
+    """(log2 partition size along the split, number of partitions), recon_isp_subtree_{v,h} (rcn_transform_tree.c:1097-1108, 1166-1176)"""
+    lp, lo = (lw if ver else lh) - 2, (lh if ver else lw)
+    if lo < 4 and lp <= 4 - lo:
+        lp = 4 - lo
+    return lp, (1 << (lw if ver else lh)) >> lp
+
+
+def isp_tables(cmds, seed, dep_quant=1, mts_enabled=1, p_cbf=0.7):
+    """Transform blocks of the ISP commands: returns (cmds with the table index in pad[0..1], words[ISP_WORDS] zeroed -- the
+    harness / availability replay fills them, tus[n_isp][4] of TU_CMD with the OVGPU_TU_ISP flag, arena)."""
+    from . import synth_tu
+    rng = np.random.default_rng(seed)
+    cmds = cmds.copy()
+    idx = np.nonzero(cmds["flags"] & INTRA_ISP)[0]
+    words = np.zeros(len(idx), dtype=ISP_WORDS)
+    tus = np.zeros((len(idx), 4), dtype=synth_tu.TU_CMD)
+    arena, off = [], 0
+    for k, i in enumerate(idx):
+        c = cmds[i]
+        c["pad"][0], c["pad"][1] = k & 255, k >> 8
+        lw, lh, ver = int(c["log2_w"]), int(c["log2_h"]), bool(c["flags"] & INTRA_ISP_VER)
+        lp, nb = isp_partitions(lw, lh, ver)
+        tlw, tlh = (lp, lh) if ver else (lw, lp)
+        qp = int(rng.integers(22, 38)) + 12
+        lfnst = tlw >= 2 and tlh >= 2 and rng.random() < 0.3
+        lfnst_idx = int(rng.integers(0, 2))
+        # drv_lfnst_mode_l(coding block, intra mode): the wide-angle mapping of drv_lfnst.c:50-76
+        mode = int(c["mode"])
+        if mode > 1:
+            ms = (0, 6, 10, 12, 14, 15)[abs(lw - lh)]
+            if lw > lh and mode < 2 + ms:
+                mode += 65
+            elif lh > lw and mode > 66 - ms:
+                mode -= 67
+        lmode = mode + 14 + 67 if mode < 0 else (mode + 14 if mode >= 67 else mode)
+        for p in range(nb):
+            if rng.random() >= p_cbf:
+                continue
+            t = tus[k, p]
+            t["x0"], t["y0"] = int(c["x0"]) + (p << lp if ver else 0), int(c["y0"]) + (0 if ver else p << lp)
+            t["log2_w"], t["log2_h"], t["cbf_mask"] = tlw, tlh, 0x10
+            t["flags"] = synth_tu.TU_ISP | (synth_tu.TU_LFNST_L if lfnst else 0)
+            t["qp"] = [qp, qp, qp, qp]; t["qp_ts"] = [max(qp, 16)] * 4
+            t["lfnst_idx"], t["lfnst_mode_l"] = lfnst_idx, lmode
+            dst_h = mts_enabled and 1 < tlw <= 4 if ver else mts_enabled and lw <= 4
+            dst_v = mts_enabled and lh <= 4 if ver else mts_enabled and 1 < tlh <= 4
+            t["cu_mts_idx"] = (1 if dst_h else 0) | (2 if dst_v else 0)
+            cmax = synth_tu._cmax(qp, tlw, tlh, dep_quant, True)
+            if tlw < 2 or tlh < 2:
+                # 1xN / 2xN / Nx1 / Nx2: raster coefficients (dequant_non_4x4_sb), nothing beyond the 32nd row / column
+                # (64-point zero-out); last significant position as the parser reports it
+                w, n = 1 << tlw, 1 << (tlw + tlh)
+                co = np.rint(rng.laplace(0, 10, size=n)).astype(np.int64)
+                co[rng.random(n) < 0.5] = 0
+                c2 = co.reshape(1 << tlh, w)
+                c2[32:, :] = 0; c2[:, 32:] = 0
+                co = np.clip(co, -min(2000, cmax), min(2000, cmax)).astype(np.int16)
+                nz = np.nonzero(co)[0]
+                if not len(nz):
+                    co[0] = 3; nz = np.array([0])
+                last = ((int(nz[-1]) // w) << 8) | (int(nz[-1]) % w)
+                # significance map by coefficient group (8x2 / 2x8 for the two-sample-thin shapes, rcn_transform_tree.c:927-928,
+                # 1008-1009: the transforms skip what it does not flag); one-sample-thin blocks use last_pos instead
+                sig = 1
+                gw, gh = (8, 2) if tlh == 1 else ((2, 8) if tlw == 1 else (w, 1 << tlh))
+                c3 = co.reshape(1 << tlh, w)
+                for sy in range(max(1, (1 << tlh) // gh)):
+                    for sx in range(max(1, w // gw)):
+                        if sy < 8 and sx < 8 and c3[sy * gh:(sy + 1) * gh, sx * gw:(sx + 1) * gw].any():
+                            sig |= 1 << (sy * 8 + sx)
+                sig = np.uint64(sig)
+            else:
+                co, last, sig = synth_tu._tb_coeffs(rng, tlw, tlh, "lfnst" if lfnst else "tr", False, cmax)
+            t["coeff_off"][2], t["last_pos"][2], t["sig_sb_map"][2] = off, last, sig
+            arena.append(co); off += len(co)
+    arena = np.concatenate(arena + [np.zeros(64, np.int16)]) if arena else np.zeros(64, np.int16)
+    return cmds, words, tus, np.ascontiguousarray(arena, dtype=np.int16)

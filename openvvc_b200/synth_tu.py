@@ -6,7 +6,7 @@ import numpy as np
 from . import synth
 
 CLIP_P = 0.02   # share of sub-blocks with out-of-range coefficients (exercise the dequant / transform clips)
-TU_IMPLICIT_MTS, TU_LFNST_L, TU_LFNST_C, TU_SCALE_ANCHOR = 1, 2, 4, 8
+TU_IMPLICIT_MTS, TU_LFNST_L, TU_LFNST_C, TU_SCALE_ANCHOR, TU_ISP = 1, 2, 4, 8, 16
 # == OVGPUTuCmd (include/ovvc_b200.h)
 TU_CMD = np.dtype({"names": ["x0", "y0", "log2_w", "log2_h", "cbf_mask", "tr_skip_mask", "cu_mts_flag", "cu_mts_idx",
                              "flags", "lfnst_idx", "qp", "qp_ts", "last_pos", "chroma_scale", "lfnst_mode_l", "lfnst_mode_c",

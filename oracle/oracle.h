@@ -166,6 +166,9 @@ void ovo_lmcs_reshape_plane(uint16_t *plane, int stride, int w, int h, const uin
 #define OVO_TU_IMPLICIT_MTS 1   /* luma: intra, non-MIP CU in a slice with mts_implicit (rcn_transform_tree.c:435) */
 #define OVO_TU_LFNST_L      2   /* TUInfo.lfnst_flag applies to the luma TB  (rcn_tu_st / rcn_tu_l)              */
 #define OVO_TU_LFNST_C      4   /* TUInfo.lfnst_flag applies to the chroma TBs (rcn_tu_c only)                    */
+#define OVO_TU_ISP         16   /* luma transform block of an ISP partition (rcn_tu_isp_{v,h}, rcn_transform_tree.c:970-1085): log2_w / log2_h
+                                 * may be 0 or 1, x0 / y0 any; cu_mts_idx bit 0 / bit 1 = DST-VII (else DCT-II) horizontally / vertically;
+                                 * lfnst_mode_l = drv_lfnst_mode_l(coding block size, intra mode), already wide-angle mapped */
 typedef struct OVOTuCmd {
     int16_t x0, y0;
     uint8_t log2_w, log2_h;      /* luma TU size */
@@ -230,6 +233,10 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
 #define OVO_INTRA_CCLM_COLLOCATED 8   /* flags: sps_chroma_vertical_collocated_flag (5-tap cross luma down-sampling for CCLM) */
 #define OVO_INTRA_MIP    16   /* flags: matrix-based intra prediction of the luma block; `mode` = ctudec->cu_opaque: bit 7 transposed,
                                 * bits 0-5 the matrix index (rcn_intra_mip, rcn_intra_mip.c:386-403) */
+#define OVO_INTRA_ISP      32  /* flags: intra sub-partitions (recon_isp_subtree_{h,v}, rcn_transform_tree.c:1087-1205): the command is the whole
+                                * luma coding block; its partitions are predicted AND reconstructed one after the other, so the
+                                * command carries its transform blocks (isp index in pad[0] | pad[1] << 8) */
+#define OVO_INTRA_ISP_VER  64  /* flags: vertical split (cu_opaque == 2), else horizontal */
 typedef struct OVOIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */
@@ -245,6 +252,20 @@ typedef struct OVOIntraCmd {
 } OVOIntraCmd;
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, int nb_cmds);
+/* Per ISP coding unit: the availability words vvc_intra_pred_isp reads (rcn_intra.c:586-596; the progress field does not
+ * change during the CU -- the whole block is marked before the sub-tree, vcl_transform_unit.c:1878) and the transform blocks
+ * of the (at most 4) partitions in order, cbf_mask == 0 where a partition has none.  TU flags carry OVO_TU_ISP. */
+typedef struct OVOIspInfo {
+    uint64_t common;             /* vertical split: hfield[y0 >> 2];  horizontal split: vfield[x0 >> 2]                         */
+    uint64_t part[4];            /* per prediction call q: vertical: vfield[x_q >> 2]; horizontal: hfield[(y_q >> 2) + !!(y_q % 4)] */
+    OVOTuCmd tu[4];
+} OVOIspInfo;
+typedef struct OVOIspSlice { uint8_t dep_quant, mts_enabled, pad[2]; } OVOIspSlice;
+/* like ovo_intra_picture; commands flagged OVO_INTRA_ISP are reconstructed (prediction + residual per partition) */
+void ovo_intra_picture2(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                        const OVOIntraCmd *cmds, int nb_cmds, const OVOIspInfo *isp, const int16_t *arena, int dep_quant);
+/* residual of one transform block flagged OVO_TU_ISP into res (raster, w x h) */
+void ovo_isp_residual(int16_t *res, const int16_t *arena, const OVOTuCmd *c, int dep_quant, int bitdepth);
 
 /* ---- Reconstruction in CU order (port_recon.c): prediction, then residual, coding unit by coding unit -------- */
 typedef struct OVOLmcsAnchor { int16_t x0, y0; uint16_t abv_mask, lft_mask; } OVOLmcsAnchor;   /* == OVGPULmcsAnchor */

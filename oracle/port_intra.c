@@ -39,8 +39,18 @@ enum { REF_OFF = 128, REF_LEN = 128 + 2 * 128 + 16 };
 /* us = log2 of the availability unit in samples of this plane: 2 for luma, 1 for 4:2:0 chroma (fill_ref_*_0_chroma,
  * rcn_fill_ref.c:147-230, 392-480).  left_chroma: fill_ref_left_0_chroma pads with the mid value when only the corner
  * unit is available (its padding value is only updated inside the copy loop, :193-200). */
+static void fill_ref_off(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                         uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int us, int left_chroma, int off);
 static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int us, int left_chroma)
+{
+    fill_ref_off(ref, p, step, other_step, log2_len, log2_other, map, other_map, pos, other_pos, bitdepth, us, left_chroma, 0);
+}
+/* off != 0 (ISP, rcn_fill_ref.c:71-145 / 320-390 with offset_y / offset_x): the array is filled for the whole coding block
+ * starting `off` samples before the partition; only the corner sample, the "nothing available" padding value and the
+ * length of the wide-angle padding depend on it */
+static void fill_ref_off(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
+                         uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int us, int left_chroma, int off)
 {
     int un = 1 << us, nb_units = ((1 << (log2_len + 1)) >> us) + 1, ref_len = (1 << (log2_len + 1)) + 1;
     uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> us)) & mask, navl = avl ^ mask;
@@ -48,7 +58,7 @@ static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t
         for (int i = 0; i < ref_len; i++) ref[i] = p[i * step];
     } else if (avl) {
         int nb_avl = 64 - __builtin_clzll(avl), i;
-        ref[0] = (avl & 1) ? p[0] : p[step];
+        ref[0] = (avl & 1) ? p[off * step] : p[step];
         for (i = 1; i < nb_avl; i++)
             for (int k = 0; k < un; k++) ref[1 + un * (i - 1) + k] = p[(1 + un * (i - 1) + k) * step];
         uint16_t pad = ref[un * (nb_avl - 1)];
@@ -58,10 +68,10 @@ static void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t
     } else {
         int nb_units_o = ((1 << (log2_other + 1)) >> us) + 1;
         uint64_t avl_o = (other_map >> (other_pos >> us)) & ((1ull << (nb_units_o + 1)) - 1);
-        uint16_t pad = avl_o ? p[other_step] : (uint16_t)(1 << (bitdepth - 1));     /* first sample of the other line */
+        uint16_t pad = avl_o ? p[other_step + off * step] : (uint16_t)(1 << (bitdepth - 1));     /* first sample of the other line */
         for (int i = 0; i < ref_len; i++) ref[i] = pad;
     }
-    for (int i = 0; i < 4; i++) ref[ref_len + i] = ref[ref_len - 1];
+    for (int i = 0; i < 4 + off; i++) ref[ref_len + i] = ref[ref_len - 1];
 }
 
 /* fill_ref_left_0_mref / fill_ref_above_0_mref (rcn_fill_ref.c:228-318, 493-590) for reference line m = mrl_idx >= 1:
@@ -136,21 +146,29 @@ static void filter_ref(uint16_t *dst, const uint16_t *src, const uint16_t *src2,
 
 /* vertical-class angular prediction of a W x H block (W along the main reference): out[y * W + x].
  * M = main reference (M[0] corner, negative indices writable), S = side reference, tl = ref_above[0]. */
+static void angular_class2(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv, int chroma, int isp_lh);
 static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv, int chroma)
 {
-    int W = 1 << lw, H = 1 << lh, a = abs(mode_idx);
-    int gauss = !chroma && (lw + lh) > 5 && a > intra_filter_thr[(lw + lh) >> 1];
+    angular_class2(out, M, S, tl, lw, lh, mode_idx, maxv, chroma, -1);
+}
+/* isp_lh >= 0: intra_angular_cubic_{v,h} of the ISP path (rcn_intra.c:288-452): cubic interpolation only, no reference
+ * filtering, and the PDPC decisions test log2_pb_h of the BLOCK (isp_lh) -- also in the horizontal variant, where every other
+ * quantity is the transposed one */
+static void angular_class2(int *out, uint16_t *M, uint16_t *S, int tl, int lw, int lh, int mode_idx, int maxv, int chroma, int isp_lh)
+{
+    int W = 1 << lw, H = 1 << lh, a = abs(mode_idx), isp = isp_lh >= 0;
+    int gauss = !isp && !chroma && (lw + lh) > 5 && a > intra_filter_thr[(lw + lh) >> 1];
     uint16_t fM[REF_LEN], fS[REF_LEN];
     int cpd = lw > 1 && lh > 1;                                    /* chroma: PDPC only when both sides are >= 4 (rcn_intra.c:954-1008) */
     if (a == 0) {                                                  /* pure vertical: intra_angular_ver(_pdpc) */
-        int pd = chroma ? cpd : (gauss || lh > 1), scale = (lw + lh - 2) >> 2;
+        int pd = isp ? isp_lh > 1 : (chroma ? cpd : (gauss || lh > 1)), scale = (lw + lh - 2) >> 2;
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++)
                 out[y * W + x] = pd ? clipi((pdpc_w(scale, x) * (S[y + 1] - tl) + (M[x + 1] << 6) + 32) >> 6, 0, maxv) : M[x + 1];
         return;
     }
     if (mode_idx == 16) {                                          /* pure diagonal: intra_angular_vdia(_pdpc) */
-        int pd = chroma ? cpd : (gauss || lh > 1), scale = imin(2, lh - 2);
+        int pd = isp ? isp_lh > 1 : (chroma ? cpd : (gauss || lh > 1)), scale = imin(2, lh - 2);
         if (gauss) {
             filter_ref(fM + REF_OFF, M, S, 2 * W); filter_ref(fS + REF_OFF, S, M, 2 * H);
             M = fM + REF_OFF; S = fS + REF_OFF;
@@ -173,7 +191,7 @@ static void angular_class(int *out, uint16_t *M, uint16_t *S, int tl, int lw, in
         }
         for (int k = -1, sum = 256; k >= -H; k--) { sum += inv; M[k] = S[imin(sum >> 9, H)]; }     /* rcn_intra.c:118-121 */
         angle = -angle;
-    } else if (pdpc_scale < 0 || (!gauss && lh < 2) || (chroma && !cpd)) {
+    } else if (pdpc_scale < 0 || (isp ? isp_lh < 2 : ((!gauss && lh < 2) || (chroma && !cpd)))) {
         if (gauss && !frac) { filter_ref(fM + REF_OFF, M, S, 2 * W); M = fM + REF_OFF; }
     } else {
         if (gauss && !frac) {
@@ -436,6 +454,102 @@ static void mip_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0,
         }
     }
     free(H);
+}
+
+/* vvc_intra_pred_isp (rcn_intra.c:567-643): prediction of one partition (lpw x lph, at offset (ox, oy) inside the coding
+ * block of the command) from references filled for the whole coding block */
+static void isp_pred_block(uint16_t *plane, int stride, int bitdepth, int cm, const OVOIntraCmd *c, uint64_t cols, uint64_t rows,
+                           int ox, int oy, int lpw, int lph)
+{
+    int lcw = c->log2_w, lch = c->log2_h, w = 1 << lpw, h = 1 << lph, maxv = (1 << bitdepth) - 1;
+    int x0 = c->x0 + ox, y0 = c->y0 + oy;
+    uint16_t abv_buf[REF_LEN + 64], lft_buf[REF_LEN + 64], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
+    uint16_t *dst = plane + (size_t)y0 * stride + x0;
+    /* left: column x0 - 1 from the block's top - 1 down; above: row y0 - 1 from the block's left - 1 on */
+    fill_ref_off(lft, plane + (size_t)(c->y0 - 1) * stride + x0 - 1, stride, 1, lch, lcw, cols, rows, c->y0 & cm, x0 & cm, bitdepth, 2, 0, oy);
+    fill_ref_off(abv, plane + (size_t)(y0 - 1) * stride + c->x0 - 1, 1, stride, lcw, lch, rows, cols, c->x0 & cm, y0 & cm, bitdepth, 2, 0, ox);
+    abv += ox; lft += oy;
+    for (int i = 0; i < 4; i++) lft[(1 << lch) + h + 1 + i] = lft[(1 << lch) + h + i];       /* rcn_intra.c:601-607 */
+    for (int i = 0; i < 4; i++) abv[(1 << lcw) + w + 1 + i] = abv[(1 << lcw) + w + i];
+    int *out = malloc(sizeof(int) * w * h);
+    int pd = lph > 1;
+    if (c->mode == 0) {
+        int ws = pd ? (lpw > 1 ? lpw : 1) : lpw, hs = pd ? (lph > 1 ? lph : 1) : lph, scale = (lpw + lph - 2) >> 2;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int hor = (lft[y + 1] << ws) + (x + 1) * (abv[w + 1] - lft[y + 1]), ver = (abv[x + 1] << hs) + (y + 1) * (lft[h + 1] - abv[x + 1]);
+                int v = ((hor << hs) + (ver << ws) + (1 << (ws + hs))) >> (ws + hs + 1);
+                int xw = pdpc_w(scale, x), yw = pdpc_w(scale, y);
+                out[y * w + x] = pd ? clipi((xw * lft[y + 1] + yw * abv[x + 1] + (64 - (xw + yw)) * v + 32) >> 6, 0, maxv) : v;
+            }
+    } else if (c->mode == 1) {
+        int shift = (lpw > lph ? lpw : lph) + (lpw == lph), dc = 0, scale = (lpw + lph - 2) >> 2;
+        if (lpw >= lph) for (int i = 0; i < w; i++) dc += abv[1 + i];
+        if (lpw <= lph) for (int i = 0; i < h; i++) dc += lft[1 + i];
+        dc = (dc + ((1 << shift) >> 1)) >> shift;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                int tw = pdpc_w(scale, x), lwg = pdpc_w(scale, y);
+                out[y * w + x] = pd ? clipi((tw * lft[y + 1] + lwg * abv[x + 1] + (64 - (tw + lwg)) * dc + 32) >> 6, 0, maxv) : dc;
+            }
+    } else {
+        static const uint8_t mode_shift_tab[6] = { 0, 6, 10, 12, 14, 15 };
+        int mode = c->mode, ms = mode_shift_tab[abs(lcw - lch)];                   /* wide angles from the CODING BLOCK's shape */
+        if (lcw > lch && mode < 2 + ms) mode += 65;
+        else if (lch > lcw && mode > 66 - ms) mode -= 65;
+        if (mode >= 34) angular_class2(out, abv, lft, abv[0], lpw, lph, mode - 50, maxv, 0, lph);
+        else {
+            int *t = malloc(sizeof(int) * w * h);
+            angular_class2(t, lft, abv, abv[0], lph, lpw, 18 - mode, maxv, 0, lph);
+            for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * w + x] = t[x * h + y];
+            free(t);
+        }
+    }
+    for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) dst[(size_t)y * stride + x] = (uint16_t)out[y * w + x];
+    free(out);
+}
+
+/* recon_isp_subtree_v / _h (rcn_transform_tree.c:1087-1205): partitions in order, each predicted (vertical split: in groups
+ * of at least 4 columns) and then reconstructed with its own transform block */
+static void isp_cu(uint16_t *plane, int stride, int bitdepth, int cm, const OVOIntraCmd *c, const OVOIspInfo *info,
+                   const int16_t *arena, int dep_quant)
+{
+    int lcw = c->log2_w, lch = c->log2_h, ver = (c->flags & OVO_INTRA_ISP_VER) != 0, maxv = (1 << bitdepth) - 1;
+    int lp = (ver ? lcw : lch) - 2, lo = ver ? lch : lcw;                          /* partition size along the split, the other side */
+    if (lo < 4 && lp <= 4 - lo) lp = 4 - lo;
+    int nb = (1 << (ver ? lcw : lch)) >> lp, q = 0;
+    int16_t res[64 * 64];
+    for (int i = 0; i < nb; i++) {
+        int off = i << lp;
+        if (ver) { if (!(off & 3)) { isp_pred_block(plane, stride, bitdepth, cm, c, info->part[q], info->common, off, 0, lp < 2 ? 2 : lp, lch); q++; } }
+        else     { isp_pred_block(plane, stride, bitdepth, cm, c, info->common, info->part[q], 0, off, lcw, lp); q++; }
+        const OVOTuCmd *t = &info->tu[i];
+        if (!(t->cbf_mask & 0x10)) continue;
+        ovo_isp_residual(res, arena, t, dep_quant, bitdepth);
+        int tw = 1 << t->log2_w, th = 1 << t->log2_h;
+        for (int y = 0; y < th; y++)
+            for (int x = 0; x < tw; x++) {
+                uint16_t *d = plane + (size_t)(t->y0 + y) * stride + t->x0 + x;
+                *d = (uint16_t)clipi(*d + res[y * tw + x], 0, maxv);
+            }
+    }
+}
+
+void ovo_intra_picture2(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                        const OVOIntraCmd *cmds, int nb_cmds, const OVOIspInfo *isp, const int16_t *arena, int dep_quant)
+{
+    int cm = (1 << log2_ctu_s) - 1;
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVOIntraCmd *c = &cmds[i];
+        if (c->flags & OVO_INTRA_ISP) {
+            isp_cu(planes[0], stride[0], bitdepth, cm, c, &isp[c->pad[0] | (c->pad[1] << 8)], arena, dep_quant);
+            if (c->flags & OVO_INTRA_CHROMA) {          /* the chroma blocks of the CU are ordinary ones */
+                OVOIntraCmd k = *c;
+                k.flags &= ~(OVO_INTRA_LUMA | OVO_INTRA_ISP | OVO_INTRA_ISP_VER);
+                ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, &k, 1);
+            }
+        } else ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, c, 1);
+    }
 }
 
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,

@@ -120,10 +120,15 @@ static int lfnst_wide_mode(int lw, int lh, int mode)
 
 /* process_lfnst(_luma) (drv_lfnst.c:120-156) + compute_lfnst_{4x4,8x8}(_tr) (rcn_lfnst.c:41-162), in place on the
  * dequantised block C (stride 1 << lcw). */
+static void lfnst_apply2(int16_t *C, int lcw, int lw, int lh, int lfnst_idx, int mode);
 static void lfnst_apply(int16_t *C, int lcw, int lw, int lh, int lfnst_idx, int intra_mode)
 {
+    lfnst_apply2(C, lcw, lw, lh, lfnst_idx, lfnst_wide_mode(lw, lh, intra_mode));
+}
+/* mode: already mapped by drv_lfnst_mode_l (ISP maps with the coding block's size, rcn_transform_tree.c:1118, 1172) */
+static void lfnst_apply2(int16_t *C, int lcw, int lw, int lh, int lfnst_idx, int mode)
+{
     static const uint8_t scan[16] = { 0, 4, 1, 8, 5, 2, 12, 9, 6, 3, 13, 10, 7, 14, 11, 15 };   /* nibbles of 0xfbe7ad369c258140 */
-    int mode = lfnst_wide_mode(lw, lh, intra_mode);
     int set = mode <= 1 ? 0 : ((mode <= 12 || mode >= 56) ? 1 : ((mode <= 23 || (mode >= 45 && mode <= 55)) ? 2 : 3));
     int tr = (mode < 67 && mode > 34) || mode >= 67 + 14;
     int is8 = lw >= 3 && lh >= 3;
@@ -167,6 +172,32 @@ static void luma_tb(int16_t *res, const int16_t *src, const OVOTuCmd *c, const R
         else inv_transform_2d(res, C, lw, lh, 2, 2, cfg->bitdepth);
     } else {
         inv_transform_2d(res, C, lw, lh, c->cu_mts_idx & 1, c->cu_mts_idx >> 1, cfg->bitdepth);
+    }
+}
+
+/* ISP transform blocks: rcn_isp_tu (:870-917, >= 4 samples both ways: dequantisation by sub-blocks, optional LFNST which
+ * forces DCT-II, full 2-D transform, no DC shortcut), rcn_2xX_tb / rcn_Xx2_tb (:919-945, 1000-1026: plain dequantisation, 2-D
+ * transform with a 2-point pass) and rcn_1xX_tb / rcn_Xx1_tb (:947-966, 1028-1048: ONE 1-D pass with shift TR_SHIFT_H + 1). */
+void ovo_isp_residual(int16_t *res, const int16_t *arena, const OVOTuCmd *c, int dep_quant, int bitdepth)
+{
+    int lw = c->log2_w, lh = c->log2_h, w = 1 << lw, h = 1 << lh;
+    int type_h = (c->cu_mts_idx & 1) ? 0 : 2, type_v = (c->cu_mts_idx & 2) ? 0 : 2;
+    const int16_t *src = arena + c->coeff_off[2];
+    Deq d = derive_dequant(dep_quant, c->qp[0], lw, lh, bitdepth);
+    int16_t C[32 * 32];
+    if (lw >= 2 && lh >= 2) {
+        dequant_deswizzle(C, src, d, lw, lh, c->sig_sb_map[2]);
+        if (c->flags & OVO_TU_LFNST_L) { lfnst_apply2(C, imin(5, lw), lw, lh, c->lfnst_idx, c->lfnst_mode_l); type_h = type_v = 2; }
+        inv_transform_2d(res, C, lw, lh, type_h, type_v, bitdepth);
+    } else if (lw == 0 || lh == 0) {
+        for (int i = 0; i < w * h; i++) C[i] = (int16_t)dequant_one(src[i], d);
+        tr_1d(res, C, 1, 1, lw == 0 ? type_v : type_h, lw == 0 ? lh : lw, imin(32, w * h), 20 - bitdepth + 1);
+    } else {
+        /* raster source with stride w; the 2-D transform works on the min(32, w) x min(32, h) coded area (a 64-sample side
+         * carries coefficients in its first half only) */
+        int cw = imin(32, w), chh = imin(32, h);
+        for (int y = 0; y < chh; y++) for (int x = 0; x < cw; x++) C[y * cw + x] = (int16_t)dequant_one(src[y * w + x], d);
+        inv_transform_2d(res, C, lw, lh, type_h, type_v, bitdepth);
     }
 }
 
@@ -216,7 +247,10 @@ void ovo_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int p
         uint16_t *dy = dst[0] + (size_t)c->y0 * dst_stride[0] + c->x0;
         uint16_t *dcb = dst[1] + (size_t)(c->y0 >> 1) * dst_stride[1] + (c->x0 >> 1);
         uint16_t *dcr = dst[2] + (size_t)(c->y0 >> 1) * dst_stride[2] + (c->x0 >> 1);
-        if (c->cbf_mask & 0x10) {
+        if ((c->cbf_mask & 0x10) && (c->flags & OVO_TU_ISP)) {
+            ovo_isp_residual(res, arena, c, dep_quant, bitdepth);
+            add_res(dy, dst_stride[0], res, c->log2_w, c->log2_h, 0, 0, 0, 0, bitdepth);
+        } else if (c->cbf_mask & 0x10) {
             luma_tb(res, arena + c->coeff_off[2], c, &cfg);
             add_res(dy, dst_stride[0], res, c->log2_w, c->log2_h, 0, 0, 0, 0, bitdepth);
         }

@@ -29,6 +29,59 @@ void rcn_init_dc_planar_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_intra_angular_functions_10(struct RCNFunctions *rcn_func);
 void rcn_init_fill_ref_10(struct RCNFunctions *rcn_func);
 void rcn_init_mip_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_tr_functions_10(struct RCNFunctions *rcn_func);
+void rcn_init_dequant_10(struct RCNFunctions *rcn_func);
+void rcn_init_ict_functions_10(struct RCNFunctions *rcn_func, uint8_t type, uint8_t bitdepth);
+void rcn_init_lfnst_functions(struct RCNFunctions *rcn_func);
+uint64_t residual_coding_dpq(OVCTUDec *const ctu_dec, int16_t *const dst, uint8_t log2_tb_w, uint8_t log2_tb_h, uint16_t last_pos);
+uint64_t residual_coding_sdh(OVCTUDec *const ctu_dec, int16_t *const dst, uint8_t log2_tb_w, uint8_t log2_tb_h, uint16_t last_pos);
+
+/* private to rcn_transform_tree.c:51-76 and vcl_transform_unit.c -- must match field for field */
+struct HTBInfo { uint16_t last_pos; uint64_t sig_sb_map; };
+struct HISPTUInfo {
+   uint8_t cbf_mask;
+   uint8_t tr_skip_mask;
+   uint8_t cu_mts_flag;
+   uint8_t cu_mts_idx;
+   uint8_t lfnst_flag;
+   uint8_t lfnst_idx;
+   struct HTBInfo tb_info[4];
+};
+
+/* One ISP coding unit through the reference's own slot (tmp.recon_isp_subtree_{v,h}): the whole block is marked in the
+ * progress field first (vcl_transform_unit.c:1878), the coefficients of partition i sit at residual_y + (i << (log2 w +
+ * log2 h)) (rcn_transform_tree.c:981, 1065).  The availability words the prediction reads are written back into `info`. */
+static void
+isp_cu(OVCTUDec *c, const OVOIntraCmd *m, OVOIspInfo *info, const int16_t *arena, int x0, int y0, int mts_enabled)
+{
+    int ver = (m->flags & OVO_INTRA_ISP_VER) != 0, lcw = m->log2_w, lch = m->log2_h;
+    int lp = (ver ? lcw : lch) - 2, lo = ver ? lch : lcw;
+    if (lo < 4 && lp <= 4 - lo) lp = 4 - lo;
+    int nb = (1 << (ver ? lcw : lch)) >> lp, q = 0;
+    struct HISPTUInfo tu;
+    memset(&tu, 0, sizeof(tu));
+    ctu_field_set_rect_bitfield(&c->rcn_ctx.progress_field, x0 >> 2, y0 >> 2, (1 << lcw) >> 2, (1 << lch) >> 2);
+    info->common = ver ? c->rcn_ctx.progress_field.hfield[y0 >> 2] : c->rcn_ctx.progress_field.vfield[x0 >> 2];
+    for (int i = 0; i < nb; i++) {
+        int off = i << lp;
+        if (ver) { if (!(off & 3)) info->part[q++] = c->rcn_ctx.progress_field.vfield[(x0 + off) >> 2]; }
+        else info->part[q++] = c->rcn_ctx.progress_field.hfield[((y0 + off) >> 2) + !!((y0 + off) % 4)];
+        const OVOTuCmd *t = &info->tu[i];
+        if (!(t->cbf_mask & 0x10)) continue;
+        tu.cbf_mask |= 1 << (nb - i - 1);
+        tu.tb_info[i].last_pos = t->last_pos[2];
+        tu.tb_info[i].sig_sb_map = t->sig_sb_map[2];
+        if (t->flags & OVO_TU_LFNST_L) { tu.lfnst_flag = 1; tu.lfnst_idx = t->lfnst_idx; }
+        c->dequant_luma.qp = t->qp[0];
+        int tw = 1 << t->log2_w, th = 1 << t->log2_h;
+        int n = (t->log2_w >= 2 && t->log2_h >= 2) ? (tw < 32 ? tw : 32) * (th < 32 ? th : 32) : tw * th;
+        memcpy(c->residual_y + (i << (t->log2_w + t->log2_h)), arena + t->coeff_off[2], n * sizeof(int16_t));
+    }
+    c->mts_enabled = mts_enabled;
+    if (ver) c->rcn_funcs.tmp.recon_isp_subtree_v(c, x0, y0, lcw, lch, m->mode, (const void *)&tu);
+    else     c->rcn_funcs.tmp.recon_isp_subtree_h(c, x0, y0, lcw, lch, m->mode, (const void *)&tu);
+}
+
 
 /* rcn_ciip / rcn_ciip_b (rcn_inter.c:3012-3067) from the point where the inter prediction exists: the block's current
  * content plays tmp_inter (the MC stage wrote it), the reference's own slots do the rest -- intra_pred / intra_pred_c
@@ -64,9 +117,18 @@ ciip_block(OVCTUDec *c, const OVOIntraCmd *m, int x0, int y0, uint16_t *const in
     }
 }
 
+void ovref_intra_picture2(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
+                          OVOIntraCmd *cmds, int nb_cmds, OVOIspInfo *isp, const int16_t *arena, int dep_quant, int mts_enabled);
 void
 ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
                     OVOIntraCmd *cmds, int nb_cmds)
+{
+    ovref_intra_picture2(user_planes, user_stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd, cmds, nb_cmds, NULL, NULL, 1, 0);
+}
+
+void
+ovref_intra_picture2(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
+                     OVOIntraCmd *cmds, int nb_cmds, OVOIspInfo *isp, const int16_t *arena, int dep_quant, int mts_enabled)
 {
     /* SIMD kernels of 2- and 4-sample-wide blocks store whole vectors; the reference's CTU buffer has padding for that
      * (RCN_CTB_PADDING), so the harness works on copies of the planes with 64 samples of row padding */
@@ -98,11 +160,16 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
         rcn_init_dc_planar_functions_10(&c->rcn_funcs);
         rcn_init_fill_ref_10(&c->rcn_funcs);
         rcn_init_mip_functions_10(&c->rcn_funcs);
+        rcn_init_tr_functions_10(&c->rcn_funcs);
+        rcn_init_dequant_10(&c->rcn_funcs);
+        rcn_init_ict_functions_10(&c->rcn_funcs, 0, bitdepth);
+        rcn_init_lfnst_functions(&c->rcn_funcs);
         c->rcn_funcs.intra_angular_gauss_h = &angular_gauss_h_10; c->rcn_funcs.intra_angular_gauss_v = &angular_gauss_v_10;
         c->rcn_funcs.intra_angular_cubic_h = &angular_cubic_h_10; c->rcn_funcs.intra_angular_cubic_v = &angular_cubic_v_10;
         c->rcn_funcs.intra_angular_c_h = &angular_c_h_10; c->rcn_funcs.intra_angular_c_v = &angular_c_v_10;
         c->rcn_funcs.intra_angular_nofrac_v = &angular_nofrac_v_10; c->rcn_funcs.intra_angular_nofrac_h = &angular_nofrac_h_10;
     }
+    c->residual_coding_l = dep_quant ? &residual_coding_dpq : &residual_coding_sdh;
     uint16_t *inter_pic[3] = { NULL, NULL, NULL };
     for (int i = 0; i < nb_cmds; i++)
         if (((cmds[i].flags & OVO_INTRA_CIIP) || !cmds[i].flags) && !inter_pic[0])
@@ -148,6 +215,11 @@ ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], in
                     }
                 } else if (m->flags & OVO_INTRA_CIIP) {
                     ciip_block(c, m, x0, y0, inter_pic, stride);
+                } else if (m->flags & OVO_INTRA_ISP) {
+                    /* isp_subtree_{v,h} (vcl_transform_unit.c:1344-1760): luma sub-tree, then the chroma blocks of the CU (rcn_tu_c) */
+                    isp_cu(c, m, &isp[m->pad[0] | (m->pad[1] << 8)], arena, x0, y0, mts_enabled);
+                    if (m->flags & OVO_INTRA_CHROMA)
+                        c->rcn_funcs.intra_pred_c(&c->rcn_ctx, m->mode_c, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flg_pred_mode_flag);
                 } else {
                 if ((m->flags & OVO_INTRA_LUMA) && (m->flags & OVO_INTRA_MIP))       /* rcn_intra_tu, rcn_transform_tree.c:1403-1406 */
                     c->rcn_funcs.mip.rcn_intra_mip(&c->rcn_ctx, x0, y0, m->log2_w, m->log2_h, m->mode);

@@ -38,3 +38,12 @@ def gpu_intra(ctx, planes, cmds, log2_ctu=7):
     out = pic.download()
     b.destroy(); pic.destroy()
     return out, nl
+
+
+def isp_case(w, h, seed, log2_ctu=7, p_isp=0.5, p_inter=0.3):
+    """planes, intra commands (single tree, ISP on half of the eligible luma CUs) with availability words, the ISP table words,
+    the partitions' transform blocks [n_isp][4] and the coefficient arena"""
+    cmds = synth_intra.intra_commands(w, h, seed, log2_ctu, chroma=True, p_inter=p_inter, p_isp=p_isp, p_mrl=0.2, p_mip=0.1)
+    cmds, words, tus, arena = synth_intra.isp_tables(cmds, seed + 7)
+    cmds = synth_intra.availability(w, h, cmds, log2_ctu, isp_words=words)
+    return synth.planes(w, h, seed + 1), np.ascontiguousarray(cmds), words, tus, arena
