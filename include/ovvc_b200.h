@@ -235,6 +235,11 @@ int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs,
 #define OVGPU_TU_SCALE_ANCHOR 8   /* the LMCS chroma scale is the one the GPU derives for anchor `scale_anchor` of the batch
                                    * (ovgpu_tu_batch_set_anchors) instead of `chroma_scale`                         */
 
+#define OVGPU_TU_ISP         16   /* luma transform block of an ISP partition (rcn_tu_isp_{v,h}, rcn_transform_tree.c:970-1085): luma only, log2_w /
+                                   * log2_h from 0 (1xN, Nx1 blocks) to 6, x0 / y0 any; cu_mts_idx bit 0 / bit 1 = DST-VII (else DCT-II) for the
+                                   * horizontal / vertical pass (recon_isp_subtree_{v,h} :1110-1111, 1178-1179); lfnst_mode_l = the value of
+                                   * drv_lfnst_mode_l(coding block size, intra mode), i.e. already wide-angle mapped; coefficients of blocks
+                                   * thinner than 4 in raster order with stride 1 << log2_w.  Only through ovgpu_recon_picture. */
 /* One recorded transform unit; x0/y0 picture-absolute luma samples, log2_w/h the luma size (chroma TBs are half).
  * Per-TB arrays are indexed like TUInfo.tb_info (rcn_transform_tree.c:56-66): [0] Cb or joint CbCr, [1] Cr, [2] luma. */
 typedef struct OVGPUTuCmd {
@@ -348,6 +353,18 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
 #define OVGPU_INTRA_MIP    16   /* flags: matrix-based intra prediction of the luma block (mip.rcn_intra_mip slot, rcn_intra_mip.c:386-403;
                                 * called from rcn_intra_tu, rcn_transform_tree.c:1403-1406); `mode` = ctudec->cu_opaque: bit 7 = transposed,
                                 * bits 0-5 = matrix index (< 16 for 4x4, < 8 for the 8x8 class, < 6 otherwise); no MRL / CIIP */
+#define OVGPU_INTRA_ISP      32  /* flags: intra sub-partitions (tmp.recon_isp_subtree_{h,v}, rcn_transform_tree.c:1087-1205; intra_pred_isp,
+                                  * rcn_intra.c:567-643): the command is the WHOLE luma coding block; its 2 or 4 partitions are predicted and
+                                  * reconstructed one after the other inside ovgpu_recon_picture, with the transform units flagged
+                                  * OVGPU_TU_ISP that lie inside the block.  pad[0] | pad[1] << 8 = index into the batch's OVGPUIspInfo table.
+                                  * Not accepted by ovgpu_intra_picture (prediction alone is meaningless for ISP). */
+#define OVGPU_INTRA_ISP_VER  64  /* flags: vertical split (cu_opaque == 2), else horizontal */
+/* The availability words vvc_intra_pred_isp reads for an ISP coding unit at CTU-local (x0, y0): the progress field does not
+ * change during the CU (the whole block is marked before the sub-tree, vcl_transform_unit.c:1878), so with q counting the
+ * prediction calls (one per partition; vertical split of 1- or 2-wide partitions: one per 4 columns):
+ *   vertical:   common = hfield[y0 >> 2],  part[q] = vfield[x_q >> 2]
+ *   horizontal: common = vfield[x0 >> 2],  part[q] = hfield[(y_q >> 2) + !!(y_q % 4)] */
+typedef struct OVGPUIspInfo { uint64_t common, part[4]; } OVGPUIspInfo;
 typedef struct OVGPUIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */
     uint8_t log2_w, log2_h;       /* luma size */
@@ -368,6 +385,9 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b);
 /* cmds in decode order; the host sorts them into dependency levels (blocks of a level only read blocks of lower levels) */
 int  ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
                               int pic_w, int pic_h, int log2_ctu_s);
+/* same, with the ISP table that OVGPU_INTRA_ISP commands index (may be NULL when nb_isp == 0) */
+int  ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
+                               const OVGPUIspInfo *isp, int nb_isp, int pic_w, int pic_h, int log2_ctu_s);
 int  ovgpu_intra_batch_levels(const OVGPUIntraBatch *b);
 /* predicts every block into pic (one launch per dependency level); neighbours are read from pic. Asynchronous. */
 int  ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch *b);

@@ -470,12 +470,16 @@ class IntraBatch:
         self.p = vp()
         _check(ctx.h, lib().ovgpu_intra_batch_create(ctx.h, int(max_cmds), C.byref(self.p)), "intra_batch_create")
 
-    def upload(self, cmds, w, h, log2_ctu=7, ctx=None):
+    def upload(self, cmds, w, h, log2_ctu=7, ctx=None, isp=None):
+        """isp: OVGPUIspInfo array (synth_intra.ISP_WORDS) the ISP commands index through pad[0..1]"""
         from .synth_intra import INTRA_CMD
         cmds = np.ascontiguousarray(cmds, dtype=INTRA_CMD)
-        self._keep = cmds
-        _check((ctx or self.ctx).h, lib().ovgpu_intra_batch_upload((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds), w, h, log2_ctu),
-               "intra_batch_upload")
+        isp = np.ascontiguousarray(isp) if isp is not None and len(isp) else None
+        assert isp is None or isp.dtype.itemsize == 40
+        self._keep = (cmds, isp)
+        _check((ctx or self.ctx).h, lib().ovgpu_intra_batch_upload2((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds),
+                                                                    vp(isp.ctypes.data) if isp is not None else None, len(isp) if isp is not None else 0,
+                                                                    w, h, log2_ctu), "intra_batch_upload2")
 
     def levels(self):
         return int(lib().ovgpu_intra_batch_levels(self.p))

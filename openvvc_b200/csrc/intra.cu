@@ -14,6 +14,8 @@ struct OVGPUIntraBatch {
     IntraCmdDev *h_cmds, *d_cmds;
     IntraLevels lv;                                 // per plane: order (pinned, 2 * max_cmds) and level starts (host only)
     uint32_t *h_order, *d_order;                    // [plane][max_cmds]
+    IspInfoDev *h_isp, *d_isp;                      // ISP table (grown on demand)
+    int nb_isp, max_isp, has_isp;
     uint32_t *pos_l, *pos_c;                        // host only: 1 + queue position of the command covering each 4x4 unit (luma / chroma plane)
     size_t map_units;
     // dataflow state of ovgpu_recon_picture (recon_kernels.h): pending word per unit and plane, queue heads, epoch
@@ -60,6 +62,8 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_order) cudaFree(b->d_order);
     free(b->lv.start[0]);
+    if (b->h_isp) cudaFreeHost(b->h_isp);
+    if (b->d_isp) cudaFree(b->d_isp);
     free(b->pos_l); free(b->pos_c); free(b->lv.ws_map); free(b->lv.ws_lvl); free(b->lv.ws_fill);
     if (b->d_pend) cudaFree(b->d_pend);
     if (b->d_counter) cudaFree(b->d_counter);
@@ -70,12 +74,36 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
 int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
                              int pic_w, int pic_h, int log2_ctu_s)
 {
+    return ovgpu_intra_batch_upload2(ctx, b, cmds, nb_cmds, NULL, 0, pic_w, pic_h, log2_ctu_s);
+}
+
+int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
+                              const OVGPUIspInfo *isp, int nb_isp, int pic_w, int pic_h, int log2_ctu_s)
+{
+    if (!ctx || !b || nb_isp < 0 || nb_isp > 65536 || (nb_isp && !isp)) return OVGPU_EINVAL;
     if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || (nb_cmds && !cmds) || log2_ctu_s < 5 || log2_ctu_s > 7 ||
         pic_w <= 0 || pic_h <= 0 || (pic_w & 7) || (pic_h & 7))
         return OVGPU_EINVAL;
     for (int i = 0; i < nb_cmds; i++)
-        if (intra_check_cmd(&cmds[i], pic_w, pic_h)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
+        if (intra_check_cmd(&cmds[i], pic_w, pic_h) ||
+            ((cmds[i].flags & OVGPU_INTRA_ISP) && (cmds[i].pad[0] | (cmds[i].pad[1] << 8)) >= nb_isp))
+            return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    b->has_isp = 0;
+    for (int i = 0; i < nb_cmds; i++) b->has_isp |= (cmds[i].flags & OVGPU_INTRA_ISP) != 0;
+    if (nb_isp > b->max_isp) {
+        if (b->h_isp) cudaFreeHost(b->h_isp);
+        if (b->d_isp) cudaFree(b->d_isp);
+        b->h_isp = NULL; b->d_isp = NULL; b->max_isp = 0;
+        if (cudaMallocHost(&b->h_isp, sizeof(IspInfoDev) * nb_isp) != cudaSuccess || cudaMalloc(&b->d_isp, sizeof(IspInfoDev) * nb_isp) != cudaSuccess)
+            return ovgpu_set_error(ctx, OVGPU_ENOMEM, "ISP table");
+        b->max_isp = nb_isp;
+    }
+    b->nb_isp = nb_isp;
+    if (nb_isp) {
+        memcpy(b->h_isp, isp, sizeof(IspInfoDev) * nb_isp);
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_isp, b->h_isp, sizeof(IspInfoDev) * nb_isp, cudaMemcpyHostToDevice, ctx->stream));
+    }
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->lv.nb[0] = b->lv.nb[1] = 0;
     b->serial++;
     const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
@@ -111,6 +139,7 @@ int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
 {
     if (!ctx || !pic || !b) return OVGPU_EINVAL;
     if (!b->nb_cmds) return 0;
+    if (b->has_isp) return ovgpu_set_error(ctx, OVGPU_EINVAL, "ISP commands are reconstructed by ovgpu_recon_picture only");
     if (pic->width != b->pic_w || pic->height != b->pic_h)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
     StageScope scope(ctx, OVGPU_STAGE_INTRA, b->lv.nb[0] + b->lv.nb[1]);
@@ -141,7 +170,7 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
     ReconArgs a;
     memset(&a, 0, sizeof(a));
     a.plane[0] = v0.p; a.plane[1] = v1.p; a.plane[2] = v2.p; a.pitch[0] = v0.pitch; a.pitch[1] = v1.pitch; a.pitch[2] = v2.pitch;
-    a.log2_ctu = b->log2_ctu; a.bitdepth = pic->bitdepth; a.plane_id = p; a.cmds = b->d_cmds; a.nb_items = nb_items;
+    a.log2_ctu = b->log2_ctu; a.bitdepth = pic->bitdepth; a.plane_id = p; a.cmds = b->d_cmds; a.nb_items = nb_items; a.isp = b->d_isp;
     ovgpu_tu_recon_args(tu, p, &a);
     a.pend = b->d_pend + (size_t)p * b->dev_units; a.serial = b->epoch; a.w_u = pic->width >> 2; a.h_u = pic->height >> 2;
     a.counter = b->d_counter + p;

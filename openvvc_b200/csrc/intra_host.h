@@ -9,7 +9,10 @@
 static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 {
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~31)) return -1;
+    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~127)) return -1;
+    if (c->flags & OVGPU_INTRA_ISP) {       /* whole luma coding block of 32 samples or more, plain modes only */
+        if (!(c->flags & OVGPU_INTRA_LUMA) || (c->flags & (OVGPU_INTRA_CIIP | OVGPU_INTRA_MIP)) || c->mrl_idx || c->log2_w + c->log2_h < 5) return -1;
+    } else if (c->flags & OVGPU_INTRA_ISP_VER) return -1;
     if (c->flags & OVGPU_INTRA_MIP) {
         const int small = c->log2_w == 2 && c->log2_h == 2, red = c->log2_w == 2 || c->log2_h == 2 || (c->log2_w <= 3 && c->log2_h <= 3);
         if (!(c->flags & OVGPU_INTRA_LUMA) || (c->flags & OVGPU_INTRA_CIIP) || c->mrl_idx || (c->mode & 0x40) ||

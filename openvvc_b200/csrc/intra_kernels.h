@@ -61,6 +61,10 @@ struct IntraK {
         const uint32_t *order;      // command indices of this level
         int nb;
         int comp0;                  // component of grid row 0 (luma levels: 0; chroma levels: 1, grid rows = Cb, Cr)
+        // ISP (dataflow kernel only): the partition to predict inside the command's coding block and the two availability
+        // words of this prediction call (vvc_intra_pred_isp, rcn_intra.c:586-596)
+        int isp_ox, isp_oy, isp_lpw, isp_lph;
+        uint64_t isp_cols, isp_rows;
         int warp_comps;             // 0, or (dataflow kernel, recon_kernels.h) the CTA owns ONE command: its threads split into warp_comps groups,
                                     // group k predicts component comp0 + k (1: luma, 2: Cb and Cr)
     };
@@ -69,6 +73,7 @@ struct IntraK {
     // everything the phases derive from the command (warp-uniform)
     struct Blk {
         int mip, mip_tr, mip_idx;                    // matrix-based prediction: transposed variant, matrix index
+        int isp, cb_x0, cb_y0, cb_lw, cb_lh, ox, oy; // ISP partition: the coding block it belongs to and its offset inside
         int valid, chroma, pd, ciip, mrl, cclm, coll;  // cclm: 0 or the chroma mode 67 (LM) / 68 (MDLM left) / 69 (MDLM top)                 // pd: planar / DC use their PDPC variant; ciip: blend weight or 0
         int x0, y0, lw, lh, mode;                    // in samples of the component; mode as signalled: 0 planar, 1 DC, 2..66 angular
         int vert;                                    // angular: vertical class
@@ -92,8 +97,14 @@ struct IntraK {
         if (!b.valid) return b;
         const int sh = b.chroma;
         b.x0 = c.x0 >> sh; b.y0 = c.y0 >> sh; b.lw = c.log2_w - sh; b.lh = c.log2_h - sh; b.cols = c.avail_cols; b.rows = c.avail_rows;
-        b.mrl = (b.chroma || b.ciip) ? 0 : c.mrl_idx;
-        b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : !b.mrl;
+        b.isp = !b.chroma && (c.flags & 32) != 0;
+        b.cb_x0 = b.x0; b.cb_y0 = b.y0; b.cb_lw = b.lw; b.cb_lh = b.lh; b.ox = b.oy = 0;
+        if (b.isp) {
+            b.ox = a.isp_ox; b.oy = a.isp_oy; b.x0 += b.ox; b.y0 += b.oy; b.lw = a.isp_lpw; b.lh = a.isp_lph;
+            b.cols = a.isp_cols; b.rows = a.isp_rows;
+        }
+        b.mrl = (b.chroma || b.ciip || b.isp) ? 0 : c.mrl_idx;
+        b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : (b.isp ? b.lh > 1 : !b.mrl);     // ISP: planar / DC PDPC iff log2_pb_h > 1 (rcn_intra.c:612-631)
         int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
         b.mip = !b.chroma && (c.flags & 16);
         b.mip_tr = (c.mode >> 7) & 1; b.mip_idx = c.mode & 0x3f;
@@ -105,15 +116,27 @@ struct IntraK {
         b.vert = 1; b.mlw = b.lw; b.mlh = b.lh;
         b.mode_idx = b.a = b.angle = b.inv = b.frac = b.gauss = b.pdpc_scale = b.use_pdpc = b.filt_m = b.filt_s = b.ext = 0;
         if (mode > 1) {
-            const int d = b.lw - b.lh, ms = intra_wide_shift[d < 0 ? -d : d];                  // derive_wide_angular_mode
-            if (b.lw > b.lh && mode < 2 + ms) mode += 65;
-            else if (b.lh > b.lw && mode > 66 - ms) mode -= 65;
+            const int d = b.cb_lw - b.cb_lh, ms = intra_wide_shift[d < 0 ? -d : d];            // derive_wide_angular_mode (ISP: the coding block's shape)
+            if (b.cb_lw > b.cb_lh && mode < 2 + ms) mode += 65;
+            else if (b.cb_lh > b.cb_lw && mode > 66 - ms) mode -= 65;
             b.vert = mode >= 34;
             b.mode_idx = b.vert ? mode - 50 : 18 - mode;
             if (!b.vert) { b.mlw = b.lh; b.mlh = b.lw; }
             b.a = b.mode_idx < 0 ? -b.mode_idx : b.mode_idx;
-            b.gauss = !b.chroma && (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
-            if (b.mrl) {                                                                       // vvc_intra_pred_multi_ref: no filter, no PDPC
+            b.gauss = !b.isp && !b.chroma && (b.lw + b.lh) > 5 && b.a > intra_filter_thr[(b.lw + b.lh) >> 1];
+            if (b.isp) {
+                // intra_angular_cubic_{v,h} (rcn_intra.c:288-452): cubic only, unfiltered references, and every PDPC decision
+                // tests log2_pb_h of the block -- also in the horizontal class
+                if (b.a == 0) b.use_pdpc = b.lh > 1;
+                else if (b.mode_idx == 16) { b.use_pdpc = b.lh > 1; b.pdpc_scale = ovd_min(2, b.mlh - 2); }
+                else {
+                    b.angle = intra_angle_tab[b.a]; b.inv = intra_inv_angle_tab[b.a];
+                    b.frac = (b.angle & 31) != 0;
+                    b.pdpc_scale = ovd_min(2, b.mlh - (floor_log2((unsigned)(3 * b.inv - 2)) - 8));
+                    if (b.mode_idx < 0) { b.ext = 1; b.angle = -b.angle; }
+                    else if (!(b.pdpc_scale < 0 || b.lh < 2)) b.use_pdpc = 1;
+                }
+            } else if (b.mrl) {                                                                       // vvc_intra_pred_multi_ref: no filter, no PDPC
                 b.gauss = 0;
                 b.angle = b.a == 16 ? 32 : intra_angle_tab[b.a]; b.inv = intra_inv_angle_tab[b.a];
                 b.frac = (b.angle & 31) != 0;
@@ -134,15 +157,17 @@ struct IntraK {
                 else { b.filt_m = b.filt_s = f; b.use_pdpc = 1; }
             }
         } else if (mode == 0) {
-            b.filt_m = b.filt_s = !b.chroma && !b.mrl && (b.lw + b.lh) > 5;                              // planar: rcn_intra.c:531-538
+            b.filt_m = b.filt_s = !b.chroma && !b.mrl && !b.isp && (b.lw + b.lh) > 5;                    // planar: rcn_intra.c:531-538
         }
         return b;
     }
 
     // fill_ref_left_0 / fill_ref_above_0 (offset 0): one lane per sample
     OVD void fill_ref(uint16_t *ref, const uint16_t *p, ptrdiff_t step, ptrdiff_t other_step, int log2_len, int log2_other,
-                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int nl, int us, int left_chroma)
+                      uint64_t map, uint64_t other_map, int pos, int other_pos, int bitdepth, int lane, int nl, int us, int left_chroma, int off = 0)
     {
+        // off (ISP, rcn_fill_ref.c:71-145 / 320-390 with offset_y / offset_x): the array covers the whole coding block and starts
+        // `off` samples before the partition; the corner sample, the "nothing available" value and the padding length move with it
         // us = log2 of the availability unit in samples of this plane (2 luma, 1 chroma)
         const int nb_units = ((1 << (log2_len + 1)) >> us) + 1, ref_len = (1 << (log2_len + 1)) + 1;
         const uint64_t mask = (1ull << (nb_units + 1)) - 1, avl = (map >> (pos >> us)) & mask;
@@ -152,15 +177,15 @@ struct IntraK {
         if (!avl) {
             const int nb_units_o = ((1 << (log2_other + 1)) >> us) + 1;
             const uint64_t avl_o = (other_map >> (other_pos >> us)) & ((1ull << (nb_units_o + 1)) - 1);
-            if (avl_o) pad = p[other_step];
+            if (avl_o) pad = p[other_step + (ptrdiff_t)off * step];
         } else if (nb_avl > 1) pad = p[(size_t)((nb_avl - 1) << us) * step];
-        else if (!left_chroma) pad = p[0];                                                     // only the corner unit: its sample
+        else if (!left_chroma) pad = p[(ptrdiff_t)off * step];                                 // only the corner unit: its sample
         // (fill_ref_left_0_chroma keeps the mid value there, rcn_fill_ref.c:193-200)
-        for (int i = lane; i < ref_len + 4; i += nl) {
+        for (int i = lane; i < ref_len + 4 + off; i += nl) {
             int v = pad;
             const int k = ovd_min(i, ref_len - 1);                                             // wide-angle padding repeats the last sample
             if (avl) {
-                if (k == 0) v = (avl & 1) ? p[0] : p[step];
+                if (k == 0) v = avl == mask ? p[0] : ((avl & 1) ? p[(ptrdiff_t)off * step] : p[step]);   // (everything available: plain copy)
                 else if (1 + ((k - 1) >> us) < nb_avl) v = p[(size_t)k * step];
             }
             ref[i] = (uint16_t)v;
@@ -328,7 +353,8 @@ struct IntraK {
         uint16_t *plane = comp == 0 ? a.plane[0] : (comp == 1 ? a.plane[1] : a.plane[2]);
         const int pitch = comp == 0 ? a.pitch[0] : (comp == 1 ? a.pitch[1] : a.pitch[2]);
         uint16_t *base = (uint16_t *)(smem + warp * SM_WARP);
-        uint16_t *abv = base + REF_OFF, *lft = base + REF_LEN + REF_OFF, *fabv = base + 2 * REF_LEN + REF_OFF, *flft = base + 3 * REF_LEN + REF_OFF;
+        // ISP: the reference arrays are filled for the whole coding block (phase 0) and then read from the partition's offset on
+        uint16_t *abv = base + REF_OFF + b.ox, *lft = base + REF_LEN + REF_OFF + b.oy, *fabv = base + 2 * REF_LEN + REF_OFF, *flft = base + 3 * REF_LEN + REF_OFF;
         const int w = 1 << b.lw, h = 1 << b.lh, maxv = (1 << a.bitdepth) - 1, cm = (1 << (a.log2_ctu - b.chroma)) - 1;
         const int us = 2 - b.chroma;
         uint16_t *dst = plane + (size_t)b.y0 * pitch + b.x0;
@@ -408,6 +434,18 @@ struct IntraK {
             return;
         }
 
+        if (b.isp && P < 2) {
+            if (P == 0) {           // vvc_intra_pred_isp (rcn_intra.c:586-596): left column x0 - 1 from the block's top, above row y0 - 1 from its left
+                fill_ref(lft - b.oy, plane + (size_t)(b.cb_y0 - 1) * pitch + b.x0 - 1, pitch, 1, b.cb_lh, b.cb_lw, b.cols, b.rows,
+                         b.cb_y0 & cm, b.x0 & cm, a.bitdepth, lane, nl, 2, 0, b.oy);
+                fill_ref(abv - b.ox, plane + (size_t)(b.y0 - 1) * pitch + b.cb_x0 - 1, 1, pitch, b.cb_lw, b.cb_lh, b.rows, b.cols,
+                         b.cb_x0 & cm, b.y0 & cm, a.bitdepth, lane, nl, 2, 0, b.ox);
+            } else {                // :601-607: four more samples replicated from index (block size + partition size)
+                if (lane < 4) lft[(1 << b.cb_lh) + h + 1 + lane] = lft[(1 << b.cb_lh) + h];
+                else if (lane < 8) abv[(1 << b.cb_lw) + w + 1 + (lane - 4)] = abv[(1 << b.cb_lw) + w];
+            }
+            return;
+        }
         if (P == 0) {
             const uint16_t *corner = dst - (ptrdiff_t)(b.mrl + 1) * pitch - (b.mrl + 1);
             if (b.mrl) {                                                    // abv / lft = raw + m: [1 + i] is the i-th sample of line m
@@ -441,7 +479,7 @@ struct IntraK {
             const int tl = abv[0];
             if (b.mode == 0) {                                              // intra_planar_pdpc
                 const uint16_t *A = b.filt_m ? fabv : abv, *L = b.filt_m ? flft : lft;
-                const int ws = ovd_max(b.lw, 1), hs = ovd_max(b.lh, 1), scale = (b.lw + b.lh - 2) >> 2;
+                const int ws = b.pd ? ovd_max(b.lw, 1) : b.lw, hs = b.pd ? ovd_max(b.lh, 1) : b.lh, scale = (b.lw + b.lh - 2) >> 2;
                 for (int o = lane; o < w * h; o += nl) {
                     const int x = o & (w - 1), y = o >> b.lw;
                     const int hor = (L[y + 1] << ws) + (x + 1) * (A[w + 1] - L[y + 1]), ver = (A[x + 1] << hs) + (y + 1) * (L[h + 1] - A[x + 1]);

@@ -23,11 +23,23 @@ struct ReconItemDev {           // one intra command of one plane, in queue orde
     uint16_t large;             // they are > 256 samples each (TrK<128>: one CTA per block) -- all blocks of a CU plane have one size
 };
 
+struct IspInfoDev { uint64_t common, part[4]; };      // == OVGPUIspInfo: availability words of an ISP coding unit
+
+// recon_isp_subtree_{v,h} (rcn_transform_tree.c:1097-1108, 1166-1176): log2 of the partition size along the split, partition count
+OVD void isp_geometry(int log2_w, int log2_h, int ver, int *lp, int *nb)
+{
+    int p = (ver ? log2_w : log2_h) - 2;
+    const int o = ver ? log2_h : log2_w;
+    if (o < 4 && p <= 4 - o) p = 4 - o;
+    *lp = p; *nb = (1 << (ver ? log2_w : log2_h)) >> p;
+}
+
 struct ReconArgs {
     uint16_t *plane[3];
     int pitch[3], log2_ctu, bitdepth;
     int plane_id;                       // 0: luma commands, 1: chroma commands (Cb and Cr)
     const IntraCmdDev *cmds;
+    const IspInfoDev *isp;              // table the ISP commands index through pad[0..1]
     const ReconItemDev *ritems;
     int nb_items;
     // residual
@@ -49,6 +61,7 @@ OVD IntraK::Args recon_intra_args(const ReconArgs &a, const uint32_t *one_cmd)
     for (int c = 0; c < 3; c++) { ia.plane[c] = a.plane[c]; ia.pitch[c] = a.pitch[c]; }
     ia.log2_ctu = a.log2_ctu; ia.bitdepth = a.bitdepth; ia.cmds = a.cmds; ia.order = one_cmd; ia.nb = 1;
     ia.comp0 = a.plane_id; ia.warp_comps = a.plane_id ? 2 : 1;
+    ia.isp_ox = ia.isp_oy = ia.isp_lpw = ia.isp_lph = 0; ia.isp_cols = ia.isp_rows = 0;
     return ia;
 }
 
@@ -110,6 +123,7 @@ struct ReconStage {
     uint32_t zero;
     TbItemDev tb[4];
     TuCmdDev tu[4];
+    IspInfoDev isp;
 };
 
 __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
@@ -148,25 +162,68 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
             __threadfence();                                // acquire side of the units' release stores (fence.acq_rel.gpu)
             __syncthreads();
         }
-        // ---- prediction
         IntraK::Args ia = recon_intra_args(a, &sg.zero);
         ia.cmds = &sg.cmd;
-        IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-        IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-        IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-        IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-        // ---- residual of the blocks this command covers, up to four at a time
-        for (int k0 = 0; k0 < it.nb_tb; k0 += 4) {
+        const int isp = a.plane_id == 0 && (c.flags & 32);
+        if (!isp) {
+            // ---- prediction
+            IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+            IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+            IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+            IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+        }
+        // ---- residual of the blocks this command covers, up to four at a time (an ISP command has at most four)
+        for (int k0 = 0; k0 < (isp ? 1 : it.nb_tb); k0 += 4) {
             const int nk = ovd_min(4, it.nb_tb - k0);
-            if (tid < nk) { TbItemDev t = a.tb[it.tb_start + k0 + tid]; sg.tb[tid].cmd = tid; sg.tb[tid].kind = t.kind; sg.zero = 0;
-                            /* the TU command index travels through a register to the copy below */ ((uint32_t *)ovd_smem)[tid] = t.cmd; }
+            if (tid < nk) { TbItemDev t = a.tb[it.tb_start + k0 + tid]; sg.tb[tid].cmd = tid; sg.tb[tid].kind = t.kind;
+                            /* the TU command index travels through shared memory to the copy below */ ((uint32_t *)ovd_smem)[tid] = t.cmd; }
+            if (isp && tid >= 32 && tid < 32 + (int)(sizeof(IspInfoDev) / 4))
+                ((uint32_t *)&sg.isp)[tid - 32] = ((const uint32_t *)&a.isp[c.pad[0] | (c.pad[1] << 8)])[tid - 32];
             __syncthreads();
             for (int o = tid; o < nk * (int)(sizeof(TuCmdDev) / 4); o += 128) {
                 const int k = o / (int)(sizeof(TuCmdDev) / 4), wd = o - k * (int)(sizeof(TuCmdDev) / 4);
                 ((uint32_t *)&sg.tu[k])[wd] = ((const uint32_t *)&a.tu_cmds[((const uint32_t *)ovd_smem)[k]])[wd];
             }
             __syncthreads();
-            if (it.large) {
+            if (isp) {
+                // recon_isp_subtree_{v,h} (rcn_transform_tree.c:1087-1205): the partitions one after the other, each predicted
+                // (vertical split: in groups of at least four columns) and then reconstructed with its own transform block
+                const int ver = (c.flags & 64) != 0;
+                int lp, nb, q = 0;
+                isp_geometry(c.log2_w, c.log2_h, ver, &lp, &nb);
+                for (int i = 0; i < nb; i++) {
+                    const int off = i << lp;
+                    if (!ver || !(off & 3)) {
+                        ia.isp_ox = ver ? off : 0; ia.isp_oy = ver ? 0 : off;
+                        ia.isp_lpw = ver ? ovd_max(lp, 2) : c.log2_w; ia.isp_lph = ver ? c.log2_h : lp;
+                        ia.isp_cols = ver ? sg.isp.part[q] : sg.isp.common; ia.isp_rows = ver ? sg.isp.common : sg.isp.part[q];
+                        q++;
+                        IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+                        IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+                        IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+                        IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+                    }
+                    int kb = -1;                                    // the transform block of this partition, if it has one
+                    for (int k = 0; k < nk; k++)
+                        if ((ver ? (sg.tu[k].x0 - c.x0) : (sg.tu[k].y0 - c.y0)) == off) kb = k;
+                    if (kb < 0) continue;
+                    if (it.large) {
+                        TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + kb, 1);
+                        ta.cmds = sg.tu;
+                        TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                        TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                        TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                        TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                    } else {
+                        TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb + kb, 1);
+                        ta.cmds = sg.tu;
+                        TrK<32>::phase<0>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                        TrK<32>::phase<1>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                        TrK<32>::phase<2>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                        TrK<32>::phase<3>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                    }
+                }
+            } else if (it.large) {
                 for (int k = 0; k < nk; k++) {
                     TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + k, 1);
                     ta.cmds = sg.tu;

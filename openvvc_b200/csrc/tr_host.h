@@ -8,6 +8,15 @@
 // Validates one command against the coefficient arena; returns 0 when well-formed.
 static inline int tu_check_cmd(const OVGPUTuCmd *c, size_t nb_coeffs)
 {
+    if (c->flags & OVGPU_TU_ISP) {          /* luma block of an ISP partition: 1xN .. 64x16, at least 16 samples, luma only */
+        if (c->log2_w > 6 || c->log2_h > 6 || c->log2_w + c->log2_h < 4 || c->x0 < 0 || c->y0 < 0 || c->cbf_mask != 0x10 || c->tr_skip_mask ||
+            c->cu_mts_flag || c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 127 || (c->flags & (OVGPU_TU_IMPLICIT_MTS | OVGPU_TU_LFNST_C)) ||
+            c->qp[0] > 75)
+            return -1;
+        const int thin = c->log2_w < 2 || c->log2_h < 2;
+        const size_t n = thin ? (size_t)1 << (c->log2_w + c->log2_h) : (size_t)(c->log2_w < 5 ? 1 << c->log2_w : 32) * (c->log2_h < 5 ? 1 << c->log2_h : 32);
+        return (size_t)c->coeff_off[2] + n > nb_coeffs ? -1 : 0;
+    }
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
     if (c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 66 || c->lfnst_mode_c > 66) return -1;
     if (c->cu_mts_flag && (c->log2_w > 5 || c->log2_h > 5)) return -1;

@@ -23,6 +23,7 @@
 #define TU_LFNST_L 2
 #define TU_LFNST_C 4
 #define TU_SCALE_ANCHOR 8
+#define TU_ISP 16            // luma block of an ISP partition: any size from 1xN up, explicit DST-VII / DCT-II choice, no DC shortcut
 
 struct TuCmdDev {            // == OVGPUTuCmd
     int16_t x0, y0;
@@ -82,7 +83,8 @@ struct TrK {
         int cw, ch;              // coded extent: min(32, w), min(32, h)
         int kv, kh;              // rows / columns that can be non-zero
         int kv4, kh4;            // rounded up to 4
-        int thin;                // chroma block with a dimension < 4: raster coefficient order
+        int thin;                // block with a dimension < 4 (chroma, ISP): raster coefficient order with row stride sw
+        int isp, one_d, sw;      // ISP partition; 1xN / Nx1: ONE 1-D pass with shift TR_SHIFT_H + 1 (rcn_1xX_tb / rcn_Xx1_tb)
         int lfnst, lf_set, lf_tr, lf_is8, lf_idx;
         int scale, shift, neg;   // dequantisation
         uint64_t sig;
@@ -111,6 +113,9 @@ struct TrK {
         t.px = luma ? c.x0 : c.x0 >> 1; t.py = luma ? c.y0 : c.y0 >> 1;
         t.cw = 1 << ovd_min(5, t.lw); t.ch = 1 << ovd_min(5, t.lh);
         t.thin = t.lw < 2 || t.lh < 2;
+        t.isp = luma && (c.flags & TU_ISP) != 0;
+        t.one_d = t.isp && (t.lw == 0 || t.lh == 0);
+        t.sw = 1 << t.lw;
         t.sig = c.sig_sb_map[slot];
         t.sig |= !t.sig;
         t.src = a.arena + c.coeff_off[slot];
@@ -135,6 +140,13 @@ struct TrK {
         t.tr_h = t.tr_v = 2;
         if (ts) {
             t.mode = MODE_TS;
+        } else if (t.isp) {
+            // rcn_isp_tu / rcn_2xX_tb / rcn_Xx2_tb (rcn_transform_tree.c:870-945, 1000-1026): always the full transform; the
+            // recorder passes the DST-VII / DCT-II choice of recon_isp_subtree_{v,h} (:1110-1111, 1178-1179); LFNST forces DCT-II
+            t.mode = MODE_TR;
+            t.tr_h = (c.cu_mts_idx & 1) ? 0 : 2; t.tr_v = (c.cu_mts_idx & 2) ? 0 : 2;
+            t.lfnst = !t.thin && (c.flags & TU_LFNST_L) != 0;
+            if (t.lfnst) t.tr_h = t.tr_v = 2;
         } else {
             const int lf = luma ? (c.flags & TU_LFNST_L) : (c.flags & TU_LFNST_C);
             if (luma && (c.flags & TU_IMPLICIT_MTS) && !c.cu_mts_flag && (t.lw <= 4 || t.lh <= 4) && !lf) {
@@ -149,12 +161,12 @@ struct TrK {
         if (t.lfnst) {
             // drv_lfnst_mode_l / derive_lfnst_mode_c + process_lfnst(_luma), drv_lfnst.c:50-156
             int mode = luma ? c.lfnst_mode_l : c.lfnst_mode_c;
-            if (mode > 1) {
+            if (mode > 1 && !t.isp) {                 // ISP: already mapped with the coding block's shape (drv_lfnst_mode_l, :1118)
                 const int d = t.lw - t.lh, ms = tr_wide_shift[d < 0 ? -d : d];
                 if (t.lw > t.lh && mode < 2 + ms) mode += 65;
                 else if (t.lh > t.lw && mode > 66 - ms) mode -= 67;
             }
-            mode = mode < 0 ? mode + 14 + 67 : (mode >= 67 ? mode + 14 : mode);
+            if (!t.isp) mode = mode < 0 ? mode + 14 + 67 : (mode >= 67 ? mode + 14 : mode);
             t.lf_set = mode <= 1 ? 0 : ((mode <= 12 || mode >= 56) ? 1 : ((mode <= 23 || (mode >= 45 && mode <= 55)) ? 2 : 3));
             t.lf_tr = (mode < 67 && mode > 34) || mode >= 67 + 14;
             t.lf_is8 = t.lw >= 3 && t.lh >= 3;
@@ -184,7 +196,7 @@ struct TrK {
     OVD int coeff_at(const Tb &t, int x, int y)
     {
         if (x >= t.cw || y >= t.ch) return 0;
-        if (t.thin) return dequant(t.src[y * t.cw + x], t);                                   // dequant_non_4x4_sb
+        if (t.thin) return dequant(t.src[y * t.sw + x], t);                                   // dequant_non_4x4_sb (raster, stride w)
         if (!((t.sig >> (((y >> 2) << 3) + (x >> 2))) & 1)) return 0;
         return dequant(t.src[(((y >> 2) * (t.cw >> 2) + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3)], t);
     }
@@ -295,11 +307,18 @@ struct TrK {
                 }
                 if (li >= 0) v = lfnst_out(t, li);
                 else v = (x < t.kh && y < t.kv) ? coeff_at(t, x, y) : 0;
-                ct[x * ls1 + y] = (int16_t)v;
+                if (t.one_d && t.lh == 0) t2[y * ls2 + x] = (int16_t)v;       // Nx1: the row is the input of the only (horizontal) pass
+                else ct[x * ls1 + y] = (int16_t)v;
             }
             return;
         }
         if (t.mode != MODE_TR) {
+            if (P != 3) return;
+        }
+        if (t.one_d) {
+            // rcn_1xX_tb / rcn_Xx1_tb (:947-966, 1028-1048): one pass straight into the residual, shift TR_SHIFT_H + 1
+            if (P == 1 && t.lw == 0) tr_pass(ct, ls1, 1, t.lh, t.kv4 >> 2, vvc_tr_words + vvc_tr_woff[t.tr_v][t.lh], 21 - a.bitdepth, res, 1, 0, gt);
+            if (P == 2 && t.lh == 0) tr_pass(t2, ls2, 1, t.lw, t.kh4 >> 2, vvc_tr_words + vvc_tr_woff[t.tr_h][t.lw], 21 - a.bitdepth, res, 1, 0, gt);
             if (P != 3) return;
         }
         if (P == 1) {

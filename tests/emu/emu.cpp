@@ -225,9 +225,11 @@ int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int
 int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth,
                       const OVGPUIntraCmd *cmds, int n, const OVGPUTuCmd *tus, int nb_tus, const int16_t *arena, size_t nb_coeffs,
                       int dep_quant, int sh_ts_disabled, int ict_type,
-                      const OVGPULmcsAnchor *anchors, int nb_anchors, const OVGPULmcsLuts *luts, const OVGPULmcsData *lmcs)
+                      const OVGPULmcsAnchor *anchors, int nb_anchors, const OVGPULmcsLuts *luts, const OVGPULmcsData *lmcs,
+                      const OVGPUIspInfo *isp, int nb_isp)
 {
-    for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);
+    for (int i = 0; i < n; i++)
+        if (intra_check_cmd(&cmds[i], w, h) || ((cmds[i].flags & OVGPU_INTRA_ISP) && (cmds[i].pad[0] | (cmds[i].pad[1] << 8)) >= nb_isp)) return -(i + 1);
     for (int i = 0; i < nb_tus; i++) if (tu_check_cmd(&tus[i], nb_coeffs)) return -(100000 + i);
     const int w_u = w >> 2, h_u = h >> 2;
     EmuLevels L(n);
@@ -275,12 +277,42 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
                     if (bit && ux >= 0 && uy >= 0 && ux < w_u && uy < h_u && pd[(size_t)uy * w_u + ux] == 7u) return -2000000 - q;
                 }
             }
-            IntraK::Args ia = { { planes[0], planes[1], planes[2] }, { stride[0], stride[1], stride[2] }, log2_ctu, bitdepth,
-                                (const IntraCmdDev *)cmds, &it.cmd, 1, p, p ? 2 : 1 };
-            ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
-            if (it.large) for (int k = 0; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
-            else for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS)
-                emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, it.nb_tb - k < TrK<32>::GROUPS ? it.nb_tb - k : TrK<32>::GROUPS, arena, &sl);
+            IntraK::Args ia;
+            memset(&ia, 0, sizeof(ia));
+            for (int k = 0; k < 3; k++) { ia.plane[k] = planes[k]; ia.pitch[k] = stride[k]; }
+            ia.log2_ctu = log2_ctu; ia.bitdepth = bitdepth; ia.cmds = (const IntraCmdDev *)cmds; ia.order = &it.cmd; ia.nb = 1;
+            ia.comp0 = p; ia.warp_comps = p ? 2 : 1;
+            if (p == 0 && (c.flags & OVGPU_INTRA_ISP)) {
+                // the partition loop of ovd_recon_kernel
+                if (it.nb_tb > 4) return -5000000 - q;
+                const IspInfoDev *wd = (const IspInfoDev *)&isp[c.pad[0] | (c.pad[1] << 8)];
+                const int ver = (c.flags & OVGPU_INTRA_ISP_VER) != 0;
+                int lp, nbp, qq = 0;
+                isp_geometry(c.log2_w, c.log2_h, ver, &lp, &nbp);
+                for (int i = 0; i < nbp; i++) {
+                    const int off = i << lp;
+                    if (!ver || !(off & 3)) {
+                        ia.isp_ox = ver ? off : 0; ia.isp_oy = ver ? 0 : off;
+                        ia.isp_lpw = ver ? (lp > 2 ? lp : 2) : c.log2_w; ia.isp_lph = ver ? c.log2_h : lp;
+                        ia.isp_cols = ver ? wd->part[qq] : wd->common; ia.isp_rows = ver ? wd->common : wd->part[qq];
+                        qq++;
+                        ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
+                    }
+                    int kb = -1;
+                    for (int k = 0; k < it.nb_tb; k++) {
+                        const OVGPUTuCmd &t = tus[items[it.tb_start + k].cmd];
+                        if ((ver ? t.x0 - c.x0 : t.y0 - c.y0) == off) kb = k;
+                    }
+                    if (kb < 0) continue;
+                    if (it.large) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + kb, 1, arena, &sl);
+                    else emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + kb, 1, arena, &sl);
+                }
+            } else {
+                ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
+                if (it.large) for (int k = 0; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
+                else for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS)
+                    emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, it.nb_tb - k < TrK<32>::GROUPS ? it.nb_tb - k : TrK<32>::GROUPS, arena, &sl);
+            }
             for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) {
                 if (pd[(size_t)y * w_u + x] != 7u) return -3000000 - q;
                 pd[(size_t)y * w_u + x] = 0;

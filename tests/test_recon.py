@@ -45,7 +45,7 @@ def _want(pr, planes, cmds, tus, arena, log2, ict, lm):
     return pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict, anchors=lm.anchors, luts=lm.luts, lmcs_data=lm.data)
 
 
-def _emu(emu, planes, cmds, tus, arena, log2, ict, lm):
+def _emu(emu, planes, cmds, tus, arena, log2, ict, lm, isp=None):
     out = [p.copy() for p in planes]
     h, w = out[0].shape
     gc = np.ascontiguousarray(cmds[cmds["flags"] != 0])
@@ -55,7 +55,8 @@ def _emu(emu, planes, cmds, tus, arena, log2, ict, lm):
     nl = emu.emu_recon_picture(ptrs, strides, w, h, log2, 10, gc.ctypes.data_as(C.c_void_p), len(gc), gt.ctypes.data_as(C.c_void_p), len(gt),
                                arena.ctypes.data_as(C.c_void_p), C.c_size_t(len(arena)), 1, 0, ict,
                                lm.anchors.ctypes.data_as(C.c_void_p) if lm.on else None, len(lm.anchors) if lm.on else 0,
-                               C.byref(lm.luts) if lm.on else None, C.byref(lm.data) if lm.on else None)
+                               C.byref(lm.luts) if lm.on else None, C.byref(lm.data) if lm.on else None,
+                               isp.ctypes.data_as(C.c_void_p) if isp is not None else None, len(isp) if isp is not None else 0)
     assert nl >= 0, nl
     return out, nl
 
@@ -145,4 +146,47 @@ def test_gpu_recon_matches_cu_order(oracle, pr, gpu_ctx, w, h, log2, ict, p_cclm
     api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib, lmcs=lmcs)
     got2 = pic.download()
     assert all((got2[k] == want[k]).all() for k in range(3))
+    ib.destroy(); tb.destroy(); pic.destroy()
+
+
+# ------------------------------------------------------------------------------------------------ ISP inside the schedule
+def _isp_case(w, h, log2, seed):
+    """single-tree intra picture with ISP coding units: commands, ISP words, all transform units (the partitions' blocks flagged
+    OVGPU_TU_ISP in decode order), arena; oracle = ovo_intra_picture2 (ISP CUs reconstructed, the others predicted)"""
+    import helpers_intra
+    planes, cmds, words, tus, arena = helpers_intra.isp_case(w, h, seed, log2)
+    flat = np.ascontiguousarray(tus.reshape(-1)[tus.reshape(-1)["cbf_mask"] != 0])
+    return planes, cmds, words, tus, flat, arena
+
+
+@pytest.mark.parametrize("w,h,log2", [(128, 128, 7), (416, 240, 7), (832, 480, 7), (264, 136, 6), (200, 120, 5)])
+def test_emulated_isp_items_match_oracle(oracle, emu, w, h, log2):
+    from oracle import pyoracle_intra as pi
+    planes, cmds, words, tus, flat, arena = _isp_case(w, h, log2, 5 * w + h + 3)
+    want = pi.intra_picture_isp([p.copy() for p in planes], cmds, pi.isp_info_array(words, tus), arena, log2, impl="port")
+    got, nl = _emu(emu, planes, cmds, flat, arena, log2, 0, Lm(oracle, cmds, flat, log2, 0, 1), isp=np.ascontiguousarray(words))
+    for k in range(3):
+        assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2", [(128, 128, 7), (416, 240, 7), (832, 480, 7), (264, 136, 6), (200, 120, 5), (1920, 1080, 7)])
+def test_gpu_isp_matches_oracle(oracle, gpu_ctx, w, h, log2):
+    from oracle import pyoracle_intra as pi
+    from openvvc_b200 import api
+    planes, cmds, words, tus, flat, arena = _isp_case(w, h, log2, 5 * w + h + 3)
+    want = pi.intra_picture_isp([p.copy() for p in planes], cmds, pi.isp_info_array(words, tus), arena, log2, impl="port")
+    gc = np.ascontiguousarray(cmds[cmds["flags"] != 0])
+    pic = gpu_ctx.picture(w, h)
+    pic.upload(planes)
+    ib = api.IntraBatch(gpu_ctx, max(1, len(gc)))
+    ib.upload(gc, w, h, log2, isp=words)
+    tb = api.TuBatch(gpu_ctx, max(1, len(flat)), len(arena))
+    tb.upload(flat, arena, 1, 0, 0)
+    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib)
+    got = pic.download()
+    for k in range(3):
+        assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
+    with pytest.raises(api.OVGPUError):          # prediction alone is not defined for ISP commands
+        ib.run(pic)
     ib.destroy(); tb.destroy(); pic.destroy()
