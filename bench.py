@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SIZES = {"1080p": (1920, 1080), "4k": (3840, 2160), "8k": (7680, 4320)}
 STAGES_IMPLEMENTED = ["recon[mc(uni/bi/bcw, bdof, dmvr, gpm, affine 4x4 + prof)+lmcs_fwd, then per plane: residual(dequant/lfnst/idct/jcbcr) of inter CUs, "
-                      "level-ordered intra(planar/dc/angular/mrl/mip/cclm/ciip)+residual, lmcs chroma scales from reconstructed luma]",
+                      "dataflow intra(planar/dc/angular/mrl/mip/isp/cclm/ciip)+residual, lmcs chroma scales from reconstructed luma]",
                       "lmcs_bwd", "dbf(v+h,luma+chroma)", "sao", "alf+ccalf"]   # widened as §8 rows land
 
 
@@ -90,14 +90,15 @@ def make_workload(w, h, n_pics, seed0=5000):
         cmds = cmds.astype(api.MC_CMD)
         # one CU partition for the residual and the intra side: 10 % intra CUs (MRL / MIP / CCLM among them), 4 % CIIP, every TU
         # takes its LMCS chroma scale from the anchor in force (derived on the GPU from reconstructed luma)
-        icmds, tus, coeffs = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15, p_cclm=0.3,
-                                                    ict_type=1, p_cbf=0.4, p_mip=0.1)
+        icmds, tus, coeffs, isp_words, isp_tus = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15,
+                                                                        p_cclm=0.3, ict_type=1, p_cbf=0.4, p_mip=0.1, p_isp=0.1)
         anchors, tus = synth_recon.lmcs_anchors(icmds, tus, 7)
         icmds = np.ascontiguousarray(icmds[icmds["flags"] != 0])
+        tus = np.ascontiguousarray(np.concatenate([tus, isp_tus.reshape(-1)[isp_tus.reshape(-1)["cbf_mask"] != 0]]))   # + the ISP partitions' blocks
         blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
         dbf = synth_dbf.dbf_maps(w, h, blks, 7)
         pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, prof=prof, tus=tus, coeffs=coeffs,
-                         dbf_blks=blks, dbf=dbf, icmds=icmds, anchors=anchors))
+                         dbf_blks=blks, dbf=dbf, icmds=icmds, anchors=anchors, isp_words=isp_words, isp_tus=isp_tus))
     return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), pics=pics)
 
 
@@ -165,8 +166,10 @@ def reference_step(po, wl, threads):
         C.memmove(C.byref(t), C.byref(p["tab"]), C.sizeof(t))
         rec = [np.zeros((h, w), np.uint16), np.zeros((h // 2, w // 2), np.uint16), np.zeros((h // 2, w // 2), np.uint16)]
         po.mc_picture(rec, wl["refs"], wl["pocs"], p["cmds"].astype(po.McCmd), 7, impl=impl, lmcs=luts, prof=p["prof"])
-        pt.residual_picture(rec, p["tus"], p["coeffs"], 7, impl=impl, dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=1)
-        pi.intra_picture(rec, p["icmds"].copy(), 7, impl=impl, simd=1)       # same blocks, the reference's own slots (CU order)
+        pt.residual_picture(rec, p["tus"][(p["tus"]["flags"] & 16) == 0], p["coeffs"], 7, impl=impl, dep_quant=1, sh_ts_disabled=0, ict_type=1, simd=1)
+        # same blocks through the reference's own slots in CU order (intra_pred*, mip, recon_isp_subtree_*); the ISP partitions'
+        # transform blocks are part of that call, so they are left out of the residual pass above
+        pi.intra_picture_isp(rec, p["icmds"].copy(), pi.isp_info_array(p["isp_words"], p["isp_tus"]), p["coeffs"], 7, impl=impl, simd=1)
         po.port().ovo_lmcs_reshape_plane(rec[0].ctypes.data_as(po.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(po.u16p), 10)
         if impl == "ref":
             pdf.dbf_picture_ref(rec, p["dbf_blks"], 7, simd=1)
@@ -212,7 +215,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step, dev_streams=1):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(ISP, IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
@@ -289,7 +292,7 @@ def main():
         d["mc"].upload(p["cmds"], prof=p["prof"])
         d["tu"].set_anchors(p["anchors"])
         d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
-        d["intra"].upload(p["icmds"], w, h, 7)
+        d["intra"].upload(p["icmds"], w, h, 7, isp=p["isp_words"])
         d["dbf"].upload(p["dbf"])
         dev.append(d)
     ctx.sync()
@@ -410,7 +413,7 @@ def main():
             d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c); tt.append(time.perf_counter())
             d["tu"].set_anchors(p["anchors"], ctx=c)
             d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c); tt.append(time.perf_counter())
-            d["intra"].upload(p["icmds"], w, h, 7, ctx=c); tt.append(time.perf_counter())
+            d["intra"].upload(p["icmds"], w, h, 7, ctx=c, isp=p["isp_words"]); tt.append(time.perf_counter())
             d["dbf"].commit(0, 0, ctx=c); tt.append(time.perf_counter())
             d["sao"].upload(p["sao"], ctx=c)
             d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c); tt.append(time.perf_counter())
@@ -476,7 +479,7 @@ def main():
                              "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9, "frac": alg[s] / (avg * 1e-3) / 1e9 / peak,
                              "traffic": ncu_traffic(s)[0]}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
-        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
+        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["isp_words"].nbytes + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",

@@ -264,6 +264,9 @@ typedef struct OVOIspSlice { uint8_t dep_quant, mts_enabled, pad[2]; } OVOIspSli
 /* like ovo_intra_picture; commands flagged OVO_INTRA_ISP are reconstructed (prediction + residual per partition) */
 void ovo_intra_picture2(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                         const OVOIntraCmd *cmds, int nb_cmds, const OVOIspInfo *isp, const int16_t *arena, int dep_quant);
+/* one ISP coding unit, luma: partitions predicted and reconstructed in order; cm = CTU size - 1 */
+void ovo_isp_cu(uint16_t *plane, int stride, int bitdepth, int cm, const OVOIntraCmd *c, const OVOIspInfo *info,
+                const int16_t *arena, int dep_quant);
 /* residual of one transform block flagged OVO_TU_ISP into res (raster, w x h) */
 void ovo_isp_residual(int16_t *res, const int16_t *arena, const OVOTuCmd *c, int dep_quant, int bitdepth);
 
@@ -275,6 +278,13 @@ void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w
                        const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
                        int dep_quant, int sh_ts_disabled, int ict_type,
                        const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs);
+/* same; commands flagged OVO_INTRA_ISP take their luma from the ISP table (isp_subtree_{v,h}: the luma sub-tree, then the CU's
+ * chroma blocks through rcn_tu_c, vcl_transform_unit.c:1536-1556): tus[i] then only contributes its chroma blocks */
+void ovo_recon_picture2(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                        const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
+                        int dep_quant, int sh_ts_disabled, int ict_type,
+                        const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs,
+                        const OVOIspInfo *isp);
 
 #ifdef __cplusplus
 }

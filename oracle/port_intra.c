@@ -511,8 +511,8 @@ static void isp_pred_block(uint16_t *plane, int stride, int bitdepth, int cm, co
 
 /* recon_isp_subtree_v / _h (rcn_transform_tree.c:1087-1205): partitions in order, each predicted (vertical split: in groups
  * of at least 4 columns) and then reconstructed with its own transform block */
-static void isp_cu(uint16_t *plane, int stride, int bitdepth, int cm, const OVOIntraCmd *c, const OVOIspInfo *info,
-                   const int16_t *arena, int dep_quant)
+void ovo_isp_cu(uint16_t *plane, int stride, int bitdepth, int cm, const OVOIntraCmd *c, const OVOIspInfo *info,
+                const int16_t *arena, int dep_quant)
 {
     int lcw = c->log2_w, lch = c->log2_h, ver = (c->flags & OVO_INTRA_ISP_VER) != 0, maxv = (1 << bitdepth) - 1;
     int lp = (ver ? lcw : lch) - 2, lo = ver ? lch : lcw;                          /* partition size along the split, the other side */
@@ -542,7 +542,7 @@ void ovo_intra_picture2(uint16_t *const planes[3], const int stride[3], int pic_
     for (int i = 0; i < nb_cmds; i++) {
         const OVOIntraCmd *c = &cmds[i];
         if (c->flags & OVO_INTRA_ISP) {
-            isp_cu(planes[0], stride[0], bitdepth, cm, c, &isp[c->pad[0] | (c->pad[1] << 8)], arena, dep_quant);
+            ovo_isp_cu(planes[0], stride[0], bitdepth, cm, c, &isp[c->pad[0] | (c->pad[1] << 8)], arena, dep_quant);
             if (c->flags & OVO_INTRA_CHROMA) {          /* the chroma blocks of the CU are ordinary ones */
                 OVOIntraCmd k = *c;
                 k.flags &= ~(OVO_INTRA_LUMA | OVO_INTRA_ISP | OVO_INTRA_ISP_VER);

@@ -16,6 +16,16 @@ void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w
                        int dep_quant, int sh_ts_disabled, int ict_type,
                        const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs)
 {
+    ovo_recon_picture2(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, cmds, tus, nb_cu, arena, dep_quant, sh_ts_disabled, ict_type,
+                       anchors, nb_anchors, luts, lmcs, NULL);
+}
+
+void ovo_recon_picture2(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                        const OVOIntraCmd *cmds, const OVOTuCmd *tus, int nb_cu, const int16_t *arena,
+                        int dep_quant, int sh_ts_disabled, int ict_type,
+                        const OVOLmcsAnchor *anchors, int nb_anchors, const OVOLmcsLuts *luts, const OVOLmcsData *lmcs,
+                        const OVOIspInfo *isp)
+{
     int next_anchor = 0, cur_scale = 1 << 11;
     for (int i = 0; i < nb_cu; i++) {
         OVOIntraCmd c = cmds[i];
@@ -35,6 +45,11 @@ void ovo_recon_picture(uint16_t *const planes[3], const int stride[3], int pic_w
             ovo_intra_picture(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, &c, 1);
             if (t.cbf_mask) ovo_residual_picture(planes, stride, pic_w, pic_h, bitdepth, &t, 1, arena, dep_quant, sh_ts_disabled, ict_type);
             continue;
+        }
+        if (c.flags & OVO_INTRA_ISP) {
+            ovo_isp_cu(planes[0], stride[0], bitdepth, (1 << log2_ctu_s) - 1, &c, &isp[c.pad[0] | (c.pad[1] << 8)], arena, dep_quant);
+            tl.cbf_mask = 0;
+            c.flags &= ~(OVO_INTRA_ISP | OVO_INTRA_ISP_VER | OVO_INTRA_LUMA);
         }
         if (c.flags & OVO_INTRA_LUMA) {
             OVOIntraCmd l = c;

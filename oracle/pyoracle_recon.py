@@ -21,15 +21,16 @@ def lmcs_chroma_scale(luma, x0, y0, abv_mask, lft_mask, luts, data, bitdepth=10,
 
 
 def recon_picture(planes, cmds, tus, arena, log2_ctu=7, bitdepth=10, dep_quant=1, sh_ts_disabled=0, ict_type=0,
-                  anchors=None, luts=None, lmcs_data=None):
+                  anchors=None, luts=None, lmcs_data=None, isp=None):
     """prediction then residual, coding unit by coding unit in decode order (oracle/port_recon.c), in place"""
     h, w = planes[0].shape
     assert cmds.dtype == INTRA_CMD and tus.dtype == TU_CMD and len(cmds) == len(tus)
     cmds = np.ascontiguousarray(cmds); tus = np.ascontiguousarray(tus)
     arena = np.ascontiguousarray(arena, dtype=np.int16)
     dst, ds = po._planes_arg(planes)
-    po.port().ovo_recon_picture(dst, ds, w, h, log2_ctu, bitdepth, cmds.ctypes.data_as(C.c_void_p), tus.ctypes.data_as(C.c_void_p),
+    po.port().ovo_recon_picture2(dst, ds, w, h, log2_ctu, bitdepth, cmds.ctypes.data_as(C.c_void_p), tus.ctypes.data_as(C.c_void_p),
                                 len(cmds), arena.ctypes.data_as(C.c_void_p), dep_quant, sh_ts_disabled, ict_type,
                                 anchors.ctypes.data_as(C.c_void_p) if anchors is not None else None, len(anchors) if anchors is not None else 0,
-                                C.byref(luts) if luts is not None else None, C.byref(lmcs_data) if lmcs_data is not None else None)
+                                C.byref(luts) if luts is not None else None, C.byref(lmcs_data) if lmcs_data is not None else None,
+                                isp.ctypes.data_as(C.c_void_p) if isp is not None else None)
     return planes

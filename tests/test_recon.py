@@ -190,3 +190,52 @@ def test_gpu_isp_matches_oracle(oracle, gpu_ctx, w, h, log2):
     with pytest.raises(api.OVGPUError):          # prediction alone is not defined for ISP commands
         ib.run(pic)
     ib.destroy(); tb.destroy(); pic.destroy()
+
+
+def _mixed_isp_case(po, w, h, log2, ict):
+    cmds, tus, arena, words, isp_tus = synth_recon.recon_case(w, h, 13 * w + h, log2, ict_type=ict, p_cclm=0.3, p_mip=0.1, p_isp=0.4)
+    lm = Lm(po, cmds, tus, log2, ict, 5 * w + h)
+    flat = np.ascontiguousarray(np.concatenate([lm.tus[lm.tus["cbf_mask"] != 0], isp_tus.reshape(-1)[isp_tus.reshape(-1)["cbf_mask"] != 0]]))
+    return synth.planes(w, h, 3 * w + h), cmds, lm.tus, flat, arena, words, isp_tus, lm
+
+
+@pytest.mark.parametrize("w,h,log2,ict", [(416, 240, 7, 1), (832, 480, 7, 0), (264, 136, 6, 1)])
+def test_emulated_mixed_picture_with_isp(oracle, pr, emu, w, h, log2, ict):
+    """everything at once: inter CUs with residual, CIIP, plain / MRL / MIP / CCLM / ISP intra CUs, LMCS chroma scales from luma"""
+    from oracle import pyoracle_intra as pi
+    planes, cmds, tus, flat, arena, words, isp_tus, lm = _mixed_isp_case(oracle, w, h, log2, ict)
+    assert ((cmds["flags"] & 32) != 0).sum() > 5
+    want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict, anchors=lm.anchors, luts=lm.luts,
+                            lmcs_data=lm.data, isp=pi.isp_info_array(words, isp_tus))
+    got, _ = _emu(emu, planes, cmds, flat, arena, log2, ict, lm, isp=np.ascontiguousarray(words))
+    for k in range(3):
+        assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,ict", [(416, 240, 7, 1), (832, 480, 7, 0), (264, 136, 6, 1), (1920, 1080, 7, 1)])
+def test_gpu_mixed_picture_with_isp(oracle, pr, gpu_ctx, w, h, log2, ict):
+    from oracle import pyoracle_intra as pi
+    from openvvc_b200 import api
+    planes, cmds, tus, flat, arena, words, isp_tus, lm = _mixed_isp_case(oracle, w, h, log2, ict)
+    want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict, anchors=lm.anchors, luts=lm.luts,
+                            lmcs_data=lm.data, isp=pi.isp_info_array(words, isp_tus))
+    gc = np.ascontiguousarray(cmds[cmds["flags"] != 0])
+    pic = gpu_ctx.picture(w, h)
+    pic.upload(planes)
+    ib = api.IntraBatch(gpu_ctx, max(1, len(gc)))
+    ib.upload(gc, w, h, log2, isp=words)
+    tb = api.TuBatch(gpu_ctx, max(1, len(flat)), len(arena))
+    lmcs = None
+    if lm.on:
+        tb.set_anchors(lm.anchors)
+        gl = api.LmcsLuts(); C.memmove(C.byref(gl), C.byref(lm.luts), C.sizeof(gl))
+        lmcs = api.Lmcs(gpu_ctx, gl)
+        gd = api.LmcsData(); C.memmove(C.byref(gd), C.byref(lm.data), C.sizeof(gd))
+        lmcs.set_data(gd)
+    tb.upload(flat, arena, 1, 0, ict)
+    api.recon_picture(gpu_ctx, pic, tu=tb, intra=ib, lmcs=lmcs)
+    got = pic.download()
+    for k in range(3):
+        assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
+    ib.destroy(); tb.destroy(); pic.destroy()
