@@ -259,7 +259,9 @@ typedef struct OVGPUTuCmd {
     uint16_t scale_anchor;        /* with OVGPU_TU_SCALE_ANCHOR: index into the batch's anchor list */
     uint32_t coeff_off[3];        /* int16 offsets into the coefficient arena; data in the reference's buffer order:
                                    * 4x4 sub-blocks of 16 contiguous values, min(32,w)/4 per row (rcn_dequant.c:243-253) */
-    uint32_t pad2;
+    uint32_t bdpcm;               /* BDPCM of the transform-skip blocks (rcn_bdpcm_tb, rcn_transform_tree.c:630-688; cu_flags
+                                   * flg_intra_bdpcm_*): bit 0 luma, bit 1 luma direction (1 = vertical accumulation), bit 2 chroma, bit 3
+                                   * chroma direction; the blocks must carry their tr_skip_mask bit */
     uint64_t sig_sb_map[3];
 } OVGPUTuCmd;
 

@@ -10,7 +10,7 @@ static inline int tu_check_cmd(const OVGPUTuCmd *c, size_t nb_coeffs)
 {
     if (c->flags & OVGPU_TU_ISP) {          /* luma block of an ISP partition: 1xN .. 64x16, at least 16 samples, luma only */
         if (c->log2_w > 6 || c->log2_h > 6 || c->log2_w + c->log2_h < 4 || c->x0 < 0 || c->y0 < 0 || c->cbf_mask != 0x10 || c->tr_skip_mask ||
-            c->cu_mts_flag || c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 127 || (c->flags & (OVGPU_TU_IMPLICIT_MTS | OVGPU_TU_LFNST_C)) ||
+            c->cu_mts_flag || c->bdpcm || c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 127 || (c->flags & (OVGPU_TU_IMPLICIT_MTS | OVGPU_TU_LFNST_C)) ||
             c->qp[0] > 75)
             return -1;
         const int thin = c->log2_w < 2 || c->log2_h < 2;
@@ -18,7 +18,7 @@ static inline int tu_check_cmd(const OVGPUTuCmd *c, size_t nb_coeffs)
         return (size_t)c->coeff_off[2] + n > nb_coeffs ? -1 : 0;
     }
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 66 || c->lfnst_mode_c > 66) return -1;
+    if (c->cu_mts_idx > 3 || c->lfnst_idx > 1 || c->lfnst_mode_l > 66 || c->lfnst_mode_c > 66 || c->bdpcm > 15) return -1;
     if (c->cu_mts_flag && (c->log2_w > 5 || c->log2_h > 5)) return -1;
     for (int k = 0; k < 3; k++) {
         int used = k == 2 ? (c->cbf_mask & 0x10) : (k == 0 ? (c->cbf_mask & 0x0a) : ((c->cbf_mask & 0x01) && !(c->cbf_mask & 0x08)));

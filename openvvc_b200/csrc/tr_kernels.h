@@ -35,7 +35,7 @@ struct TuCmdDev {            // == OVGPUTuCmd
     uint8_t lfnst_mode_l, lfnst_mode_c;
     uint16_t scale_anchor;
     uint32_t coeff_off[3];
-    uint32_t pad2;
+    uint32_t bdpcm;          // bit 0 luma BDPCM, bit 1 its direction, bit 2 chroma BDPCM, bit 3 its direction
     uint64_t sig_sb_map[3];
 };
 
@@ -84,10 +84,11 @@ struct TrK {
         int kv, kh;              // rows / columns that can be non-zero
         int kv4, kh4;            // rounded up to 4
         int thin;                // block with a dimension < 4 (chroma, ISP): raster coefficient order with row stride sw
+        int bdpcm, bdpcm_dir;    // transform-skip block of a BDPCM coding unit: running sum along rows (0) / columns (1)
         int isp, one_d, sw;      // ISP partition; 1xN / Nx1: ONE 1-D pass with shift TR_SHIFT_H + 1 (rcn_1xX_tb / rcn_Xx1_tb)
         int lfnst, lf_set, lf_tr, lf_is8, lf_idx;
         int scale, shift, neg;   // dequantisation
-        uint64_t sig;
+        uint64_t sig, sig_raw;   // sig_sb_map with bit 0 forced for the all-zero case / as recorded (reorder_tb_4x4 does not force it)
         const int16_t *src;
         int cbf_c, chroma_scale;
     };
@@ -116,7 +117,7 @@ struct TrK {
         t.isp = luma && (c.flags & TU_ISP) != 0;
         t.one_d = t.isp && (t.lw == 0 || t.lh == 0);
         t.sw = 1 << t.lw;
-        t.sig = c.sig_sb_map[slot];
+        t.sig = t.sig_raw = c.sig_sb_map[slot];
         t.sig |= !t.sig;
         t.src = a.arena + c.coeff_off[slot];
         t.cbf_c = c.cbf_mask & 3;
@@ -138,6 +139,8 @@ struct TrK {
 
         t.lfnst = 0; t.lf_set = t.lf_tr = t.lf_is8 = t.lf_idx = 0;
         t.tr_h = t.tr_v = 2;
+        t.bdpcm = ts && ((c.bdpcm >> (luma ? 0 : 2)) & 1);
+        t.bdpcm_dir = (c.bdpcm >> (luma ? 1 : 3)) & 1;
         if (ts) {
             t.mode = MODE_TS;
         } else if (t.isp) {
@@ -279,6 +282,24 @@ struct TrK {
         const int ls1 = t.kv4 + 2, ls2 = t.kh4 + 2;
 
         if (P == 0) {
+            if (t.mode == MODE_TS && t.bdpcm) {
+                // rcn_bdpcm_tb (:666-688): levels in raster order (reorder_tb_4x4 when they arrive by sub-block), clipped running
+                // sum along the rows or columns -- one thread per line --, then every WHOLE group of 16 values is dequantised
+                const int w = 1 << t.lw, h = 1 << t.lh, n = w * h, nl = t.bdpcm_dir ? w : h, len = t.bdpcm_dir ? h : w;
+                const int sb_order = a.sh_ts_disabled && !t.thin;
+                for (int l = gt; l < nl; l += GROUP) {
+                    int acc = 0;
+                    for (int k = 0; k < len; k++) {
+                        const int x = t.bdpcm_dir ? l : k, y = t.bdpcm_dir ? k : l, o = y * w + x;
+                        int v;
+                        if (!sb_order) v = t.src[o];
+                        else v = ((t.sig_raw >> (((y >> 2) << 3) + (x >> 2))) & 1) ? t.src[(((y >> 2) * (w >> 2) + (x >> 2)) << 4) + ((y & 3) << 2) + (x & 3)] : 0;
+                        acc = k ? ovd_clamp(acc + v, -32768, 32767) : v;
+                        res[o] = (int16_t)(o < ((n >> 4) << 4) ? dequant(acc, t) : acc);
+                    }
+                }
+                return;
+            }
             if (t.mode == MODE_TS) {
                 // rcn_transform_skip_tb_{l,c} without BDPCM (:691-716, :1207-1225)
                 const int n = 1 << (t.lw + t.lh), w = 1 << t.lw;

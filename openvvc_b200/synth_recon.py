@@ -7,7 +7,7 @@ from . import synth, synth_intra, synth_tu
 
 
 def recon_case(w, h, seed, log2_ctu=7, min_log2=2, p_inter=0.4, p_ciip=0.1, p_mrl=0.15, p_cclm=0.3, collocated=False, ict_type=0,
-               p_cbf=0.6, chroma=True, p_mip=0.0, p_isp=0.0):
+               p_cbf=0.6, chroma=True, p_mip=0.0, p_isp=0.0, p_bdpcm=0.0):
     """Returns (intra cmds incl. flags == 0 placeholders, tu cmds, arena); cmds[i] and tus[i] are the same coding unit.
     With p_isp: also (isp words, isp transform blocks [n_isp][4]); the luma residual of an ISP coding unit lives there (its
     tus[i] keeps the chroma blocks only) and the coefficients share the arena."""
@@ -21,7 +21,7 @@ def recon_case(w, h, seed, log2_ctu=7, min_log2=2, p_inter=0.4, p_ciip=0.1, p_mr
     cmds = synth_intra.availability(w, h, cmds, log2_ctu, isp_words=words)
     is_intra = (cmds["flags"] != 0) & ((cmds["flags"] & synth_intra.INTRA_CIIP) == 0)
     tus, arena = synth_tu.tu_commands(w, h, seed + 2, log2_ctu, ict_type=ict_type, p_cbf=p_cbf, legal=True, blocks=blocks,
-                                      intra_mask=is_intra)
+                                      intra_mask=is_intra, p_bdpcm=p_bdpcm)
     assert len(tus) == len(cmds)
     if p_isp:
         tus["cbf_mask"][(cmds["flags"] & synth_intra.INTRA_ISP) != 0] &= 0x0f

@@ -10,7 +10,7 @@ TU_IMPLICIT_MTS, TU_LFNST_L, TU_LFNST_C, TU_SCALE_ANCHOR, TU_ISP = 1, 2, 4, 8, 1
 # == OVGPUTuCmd (include/ovvc_b200.h)
 TU_CMD = np.dtype({"names": ["x0", "y0", "log2_w", "log2_h", "cbf_mask", "tr_skip_mask", "cu_mts_flag", "cu_mts_idx",
                              "flags", "lfnst_idx", "qp", "qp_ts", "last_pos", "chroma_scale", "lfnst_mode_l", "lfnst_mode_c",
-                             "scale_anchor", "coeff_off", "pad2", "sig_sb_map"],
+                             "scale_anchor", "coeff_off", "bdpcm", "sig_sb_map"],
                    "formats": [np.int16, np.int16, np.uint8, np.uint8, np.uint8, np.uint8, np.uint8, np.uint8,
                                np.uint8, np.uint8, (np.uint8, 4), (np.uint8, 4), (np.uint16, 3), np.int16, np.uint8, np.uint8,
                                np.uint16, (np.uint32, 3), np.uint32, (np.uint64, 3)],
@@ -103,7 +103,7 @@ def _cmax(qp, lw, lh, dep_quant, legal):
 
 
 def tu_commands(w, h, seed=1005, log2_ctu=7, ict_type=0, sh_ts_disabled=0, min_log2=2, p_cbf=0.6, dep_quant=1, legal=False, p_intra=0.0,
-                blocks=None, intra_mask=None):
+                blocks=None, intra_mask=None, p_bdpcm=0.0):
     """Returns (cmds[TU_CMD], arena int16). One TU per partition block (<= 64x64 luma).
     blocks / intra_mask: use this partition (and these intra CUs) instead of drawing them (synth_recon)."""
     rng = np.random.default_rng(seed)
@@ -184,6 +184,14 @@ def tu_commands(w, h, seed=1005, log2_ctu=7, ict_type=0, sh_ts_disabled=0, min_l
                     mode = ("ts_deq" if sh_ts_disabled else "ts_raw") if is_ts else ("lfnst" if lfnst_c else ("dc" if rng.random() < 0.15 else "tr"))
                     co, last, sig = _tb_coeffs(rng, lwc, lhc, mode, False, _cmax(qp, lwc, lhc, dep_quant, legal))
                     c["coeff_off"][k] = push(co); c["last_pos"][k] = last; c["sig_sb_map"][k] = sig
+        if p_bdpcm and intra and ts and rng.random() < p_bdpcm:
+            # BDPCM CU (screen content): its transform-skip blocks accumulate along rows or columns; luma and chroma flagged apart
+            b = 0
+            if ts & 0x10:
+                b |= 1 | (int(rng.integers(0, 2)) << 1)
+            if (ts & 0x3) and rng.random() < 0.7:
+                b |= 4 | (int(rng.integers(0, 2)) << 3)
+            c["bdpcm"] = b
         c["cbf_mask"], c["tr_skip_mask"] = cbf, ts
     arena = np.concatenate(arena + [np.zeros(64, np.int16)]) if arena else np.zeros(64, np.int16)
     return cmds, np.ascontiguousarray(arena, dtype=np.int16)

@@ -185,7 +185,7 @@ typedef struct OVOTuCmd {
     uint8_t lfnst_mode_c;        /* chroma: resolved mode (DM / CCLM replaced by the collocated luma mode)      */
     uint16_t scale_anchor;       /* GPU side only (OVGPU_TU_SCALE_ANCHOR); the oracle takes chroma_scale        */
     uint32_t coeff_off[3];       /* int16 offsets into the coefficient arena */
-    uint32_t pad2;
+    uint32_t bdpcm;              /* bit 0 luma BDPCM, bit 1 its direction, bit 2 chroma BDPCM, bit 3 its direction (rcn_bdpcm_tb) */
     uint64_t sig_sb_map[3];
 } OVOTuCmd;
 

@@ -93,6 +93,30 @@ static void dc_fill(int16_t *res, int lw, int lh, int dc, int bitdepth)
 typedef struct { int dep_quant, sh_ts_disabled, ict_type, bitdepth; } ResCfg;
 
 /* transform-skip block (no BDPCM: non-intra CU), rcn_transform_tree.c:691-716 / 1208-1225 */
+/* rcn_bdpcm_tb (:666-688): with sh_ts_disabled the levels of blocks >= 4x4 arrive in sub-block order and are put in raster
+ * order first (reorder_tb_4x4 :134-206, insignificant sub-blocks zero); clipped running sum along rows (dir 0, apply_bdpcm_1)
+ * or columns (dir 1, apply_bdpcm_2); then every whole group of 16 values is dequantised with the transform-skip scale */
+static void bdpcm_block(int16_t *res, const int16_t *src, int lw, int lh, int qp, uint64_t sig, const ResCfg *cfg, int dir)
+{
+    int w = 1 << lw, h = 1 << lh, n = w * h;
+    int16_t tmp[32 * 32];
+    const int16_t *in = src;
+    Deq d = derive_dequant(2, qp, lw, lh, cfg->bitdepth);
+    if (cfg->sh_ts_disabled && lw > 1 && lh > 1) {
+        for (int i = 0; i < h / 4; i++)
+            for (int j = 0; j < w / 4; j++)
+                for (int k = 0; k < 16; k++)
+                    tmp[(4 * i + (k >> 2)) * w + 4 * j + (k & 3)] = ((sig >> (8 * i + j)) & 1) ? src[(size_t)i * 4 * w + (j << 4) + k] : 0;
+        in = tmp;
+    }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            int first = dir ? y == 0 : x == 0, prev = first ? 0 : res[dir ? (y - 1) * w + x : y * w + x - 1];
+            res[y * w + x] = (int16_t)(first ? in[y * w + x] : clipi(prev + in[y * w + x], -32768, 32767));
+        }
+    for (int i = 0; i < (n >> 4) * 16; i++) res[i] = (int16_t)dequant_one(res[i], d);
+}
+
 static void ts_block(int16_t *res, const int16_t *src, int lw, int lh, int qp, uint64_t sig, const ResCfg *cfg, int is_chroma)
 {
     int n = 1 << (lw + lh);
@@ -161,6 +185,7 @@ static void luma_tb(int16_t *res, const int16_t *src, const OVOTuCmd *c, const R
 {
     int lw = c->log2_w, lh = c->log2_h;
     int lfnst = (c->flags & OVO_TU_LFNST_L) != 0;
+    if ((c->tr_skip_mask & 0x10) && (c->bdpcm & 1)) { bdpcm_block(res, src, lw, lh, c->qp_ts[0], c->sig_sb_map[2], cfg, (c->bdpcm >> 1) & 1); return; }
     if (c->tr_skip_mask & 0x10) { ts_block(res, src, lw, lh, c->qp_ts[0], c->sig_sb_map[2], cfg, 0); return; }
     int16_t C[32 * 32];
     dequant_deswizzle(C, src, derive_dequant(cfg->dep_quant, c->qp[0], lw, lh, cfg->bitdepth), lw, lh, c->sig_sb_map[2]);
@@ -261,7 +286,8 @@ void ovo_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int p
                 chroma_tb(res, arena + c->coeff_off[0], lwc, lhc, qp, c->last_pos[0], c->sig_sb_map[0], &cfg, lfnst_c, c->lfnst_idx, c->lfnst_mode_c);
             } else {
                 int qp = cbf_c == 3 ? c->qp_ts[3] : (cbf_c == 2 ? c->qp_ts[1] : c->qp_ts[2]);
-                ts_block(res, arena + c->coeff_off[0], lwc, lhc, qp, c->sig_sb_map[0], &cfg, 1);
+                if (c->bdpcm & 4) bdpcm_block(res, arena + c->coeff_off[0], lwc, lhc, qp, c->sig_sb_map[0], &cfg, (c->bdpcm >> 3) & 1);
+                else ts_block(res, arena + c->coeff_off[0], lwc, lhc, qp, c->sig_sb_map[0], &cfg, 1);
             }
             int scale = (lwc + lhc == 2) ? 1 << 11 : c->chroma_scale;
             if (!scale_on) scale = 1 << 11;
@@ -282,7 +308,8 @@ void ovo_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int p
                 if (!(c->tr_skip_mask & bit))
                     chroma_tb(res, arena + c->coeff_off[k], lwc, lhc, c->qp[1 + k], c->last_pos[k], c->sig_sb_map[k], &cfg, lfnst_c, c->lfnst_idx, c->lfnst_mode_c);
                 else
-                    ts_block(res, arena + c->coeff_off[k], lwc, lhc, c->qp_ts[1 + k], c->sig_sb_map[k], &cfg, 1);
+                    if (c->bdpcm & 4) bdpcm_block(res, arena + c->coeff_off[k], lwc, lhc, c->qp_ts[1 + k], c->sig_sb_map[k], &cfg, (c->bdpcm >> 3) & 1);
+                    else ts_block(res, arena + c->coeff_off[k], lwc, lhc, c->qp_ts[1 + k], c->sig_sb_map[k], &cfg, 1);
                 int big = lwc + lhc > 2;                             /* ict.ict[..][0] vs ict.add[..], :749-753 */
                 add_res(k == 0 ? dcb : dcr, dst_stride[1 + k], res, lwc, lhc, 0, 0, big && scale_on, c->chroma_scale, bitdepth);
             }

@@ -140,10 +140,14 @@ ovref_residual_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_
         c->intra_mode_c = m->lfnst_mode_c;
         if (m->flags & OVO_TU_LFNST_C) {
             /* dual-tree chroma TU: tmp.rcn_tu_c takes chroma coordinates and sizes (rcn_transform_tree.c:1349) */
-            c->rcn_funcs.tmp.rcn_tu_c(c, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flg_pred_mode_flag, m->cbf_mask, (void *)&tu);
+            CUFlags flc = flg_pred_mode_flag;
+            if (m->bdpcm & 4) flc |= flg_intra_bdpcm_chroma_flag | ((m->bdpcm & 8) ? flg_intra_bdpcm_chroma_dir : 0);
+            c->rcn_funcs.tmp.rcn_tu_c(c, x0 >> 1, y0 >> 1, m->log2_w - 1, m->log2_h - 1, flc, m->cbf_mask, (void *)&tu);
         } else {
             /* intra CU <=> implicit MTS or LFNST requested (an inter CU never uses either, :1247-1249) */
             CUFlags fl = (m->flags & (OVO_TU_IMPLICIT_MTS | OVO_TU_LFNST_L)) ? flg_pred_mode_flag : 0;
+            if (m->bdpcm & 1) fl |= flg_pred_mode_flag | flg_intra_bdpcm_luma_flag | ((m->bdpcm & 2) ? flg_intra_bdpcm_luma_dir : 0);
+            if (m->bdpcm & 4) fl |= flg_pred_mode_flag | flg_intra_bdpcm_chroma_flag | ((m->bdpcm & 8) ? flg_intra_bdpcm_chroma_dir : 0);
             c->mts_implicit = (m->flags & OVO_TU_IMPLICIT_MTS) != 0;
             c->rcn_funcs.tmp.rcn_tu_st(c, x0, y0, m->log2_w, m->log2_h, fl, m->cbf_mask, (void *)&tu);
         }

@@ -6,10 +6,10 @@ import numpy as np
 from openvvc_b200 import synth, synth_tu
 
 
-def tr_case(w, h, seed, log2_ctu=7, ict_type=0, sh_ts_disabled=0, dep_quant=1, legal=False, p_intra=0.3, min_log2=2):
+def tr_case(w, h, seed, log2_ctu=7, ict_type=0, sh_ts_disabled=0, dep_quant=1, legal=False, p_intra=0.3, min_log2=2, p_bdpcm=0.0):
     """prediction planes + TU commands + coefficient arena for one seeded picture"""
     cmds, arena = synth_tu.tu_commands(w, h, seed, log2_ctu, ict_type=ict_type, sh_ts_disabled=sh_ts_disabled,
-                                       dep_quant=dep_quant, legal=legal, p_intra=p_intra, min_log2=min_log2)
+                                       dep_quant=dep_quant, legal=legal, p_intra=p_intra, min_log2=min_log2, p_bdpcm=p_bdpcm)
     return synth.planes(w, h, seed + 3), cmds, arena
 
 

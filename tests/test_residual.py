@@ -15,7 +15,7 @@ import helpers
 import helpers_tr
 
 GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "tr_golden.json")))
-IDS = lambda c: "%dx%d_ict%d_tsd%d_dq%d" % (c["w"], c["h"], c["ict_type"], c["sh_ts_disabled"], c["dep_quant"])
+IDS = lambda c: "%dx%d_ict%d_tsd%d_dq%d%s" % (c["w"], c["h"], c["ict_type"], c["sh_ts_disabled"], c["dep_quant"], "_bdpcm" if c["p_bdpcm"] else "")
 KW = lambda c: dict(dep_quant=c["dep_quant"], sh_ts_disabled=c["sh_ts_disabled"], ict_type=c["ict_type"])
 
 
@@ -27,7 +27,7 @@ def pt(oracle):
 
 def _case(c):
     planes, cmds, arena = helpers_tr.tr_case(c["w"], c["h"], c["seed"], c["log2_ctu"], c["ict_type"], c["sh_ts_disabled"],
-                                             c["dep_quant"], c["legal"])
+                                             c["dep_quant"], c["legal"], **(dict(p_intra=0.6, p_bdpcm=c["p_bdpcm"]) if c["p_bdpcm"] else {}))
     assert helpers.md5(cmds, arena, *planes) == c["input_md5"], "synthetic generator drifted; regenerate golden"
     return planes, cmds, arena
 
@@ -71,6 +71,23 @@ def test_emulated_kernel_matches_oracle(pt, emu, w, h, log2, ict, tsd, dq, legal
     helpers.assert_planes_equal(got, want, "emulated residual kernels vs oracle")
 
 
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq", [(416, 240, 7, 0, 0, 1), (416, 240, 7, 1, 1, 1), (832, 480, 7, 3, 1, 0), (264, 136, 6, 2, 0, 1)])
+def test_bdpcm_port_vs_reference_and_emulation(oracle, pt, emu, w, h, log2, ict, tsd, dq):
+    """BDPCM coding units (rcn_bdpcm_tb, rcn_transform_tree.c:630-688): row / column accumulation of the transform-skip
+    levels, luma and chroma, raster and sub-block coefficient order; port pinned to the scalar reference, kernel to the port."""
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 11 * w + h, log2, ict, tsd, dq, legal=True, p_intra=0.6, p_bdpcm=0.9)
+    assert (cmds["bdpcm"] & 1).sum() > 2 and (cmds["bdpcm"] & 4).any() and (cmds["bdpcm"] & 2).any() and (cmds["bdpcm"] & 8).any()
+    kw = dict(dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    want = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", **kw)
+    if oracle.ref_available():
+        ref = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="ref", simd=0, **kw)
+        helpers.assert_planes_equal(want, ref, "BDPCM port vs reference (scalar C)")
+    plain = cmds.copy()
+    plain["bdpcm"] = 0
+    assert any((a != b).any() for a, b in zip(want, pt.residual_picture([p.copy() for p in planes], plain, arena, log2, impl="port", **kw)))
+    helpers.assert_planes_equal(helpers_tr.emu_residual(emu, planes, cmds, arena, dq, tsd, ict), want, "emulated BDPCM vs oracle")
+
+
 def test_zero_residual_is_identity(pt, emu):
     planes, cmds, arena = helpers_tr.tr_case(256, 128, 9, 7)
     arena[:] = 0
@@ -102,6 +119,15 @@ def test_gpu_matches_oracle(pt, gpu_ctx, w, h, log2, ict, tsd, dq):
     planes, cmds, arena = helpers_tr.tr_case(w, h, 9 * w + h, log2, ict, tsd, dq, p_intra=0.35)
     want = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
     helpers.assert_planes_equal(helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena, dq, tsd, ict), want, "CUDA residual vs oracle")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,ict,tsd,dq", [(416, 240, 7, 1, 1, 1), (1920, 1080, 7, 3, 0, 1)])
+def test_gpu_bdpcm_matches_oracle(pt, gpu_ctx, w, h, log2, ict, tsd, dq):
+    planes, cmds, arena = helpers_tr.tr_case(w, h, 13 * w + h, log2, ict, tsd, dq, legal=True, p_intra=0.6, p_bdpcm=0.9)
+    assert (cmds["bdpcm"] != 0).sum() > 5
+    want = pt.residual_picture([p.copy() for p in planes], cmds, arena, log2, impl="port", dep_quant=dq, sh_ts_disabled=tsd, ict_type=ict)
+    helpers.assert_planes_equal(helpers_tr.gpu_residual(gpu_ctx, planes, cmds, arena, dq, tsd, ict), want, "CUDA BDPCM vs oracle")
 
 
 @pytest.mark.gpu
