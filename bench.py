@@ -91,7 +91,7 @@ def make_workload(w, h, n_pics, seed0=5000):
         # one CU partition for the residual and the intra side: 10 % intra CUs (MRL / MIP / CCLM among them), 4 % CIIP, every TU
         # takes its LMCS chroma scale from the anchor in force (derived on the GPU from reconstructed luma)
         icmds, tus, coeffs, isp_words, isp_tus = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15,
-                                                                        p_cclm=0.3, ict_type=1, p_cbf=0.4, p_mip=0.1, p_isp=0.1)
+                                                                        p_cclm=0.3, ict_type=1, p_cbf=0.4, p_mip=0.1, p_isp=0.1, p_bdpcm=0.3)
         anchors, tus = synth_recon.lmcs_anchors(icmds, tus, 7)
         icmds = np.ascontiguousarray(icmds[icmds["flags"] != 0])
         tus = np.ascontiguousarray(np.concatenate([tus, isp_tus.reshape(-1)[isp_tus.reshape(-1)["cbf_mask"] != 0]]))   # + the ISP partitions' blocks
@@ -215,7 +215,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step, dev_streams=1):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(IBC, BDPCM not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(IBC not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 
@@ -230,6 +230,8 @@ def main():
     ap.add_argument("--size", default="4k", choices=sorted(SIZES))
     ap.add_argument("--pics", type=int, default=8, help="pictures per step per GPU")
     ap.add_argument("--dev-streams", type=int, default=4, help="streams the device-resident pictures of a step are spread over")
+    ap.add_argument("--e2e-share", type=int, default=1, help="e2e contexts (host threads) that share one stream")
+    ap.add_argument("--e2e-sets", type=int, default=2, help="picture sets in flight in the e2e leg (1 or 2)")
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
     args = ap.parse_args()
     w, h = SIZES[args.size]
@@ -280,13 +282,12 @@ def main():
             pic.upload(planes)
     lmcs = api.Lmcs(ctx, wl["lmcs"])
     lmcs.set_data(wl["lmcs_data"])
-    dev = []
-    for p in pics:
-        d = dict(rec=ctx.picture(w, h), mid=ctx.picture(w, h), dst=ctx.picture(w, h),
-                 alf=api.AlfParams(ctx, w, h, 7), sao=api.SaoParams(ctx, w, h, 7),
-                 mc=api.McBatch(ctx, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
-                 tu=api.TuBatch(ctx, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(ctx, w, h, 7),
-                 intra=api.IntraBatch(ctx, max(1, len(p["icmds"]))))
+    def make_dev(p, c):
+        d = dict(rec=c.picture(w, h), mid=c.picture(w, h), dst=c.picture(w, h),
+                 alf=api.AlfParams(c, w, h, 7), sao=api.SaoParams(c, w, h, 7),
+                 mc=api.McBatch(c, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
+                 tu=api.TuBatch(c, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(c, w, h, 7),
+                 intra=api.IntraBatch(c, max(1, len(p["icmds"]))))
         d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
         d["sao"].upload(p["sao"])
         d["mc"].upload(p["cmds"], prof=p["prof"])
@@ -294,7 +295,9 @@ def main():
         d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
         d["intra"].upload(p["icmds"], w, h, 7, isp=p["isp_words"])
         d["dbf"].upload(p["dbf"])
-        dev.append(d)
+        return d
+
+    dev = [make_dev(p, ctx) for p in pics]
     ctx.sync()
 
     # Frame parallelism on one GPU: the pictures of a step are independent (same temporal layer), so they are spread over
@@ -315,14 +318,14 @@ def main():
 
     step_no = [0]
 
-    def hand_off_reference():
+    def hand_off_reference(src=None):
         """the newest reconstructed picture of this step's owner rank becomes a reference on every rank: device copy
         into the owner's DPB slot, then ncclBroadcast of the 3 planes (P bytes) to the other ranks"""
         k = step_no[0]
         step_no[0] += 1
         slot, owner = k % 4, k % world
         if rank == owner:
-            api._check(ctx.h, api.lib().ovgpu_picture_copy(ctx.h, ref_pics[slot // 2][slot % 2].p, dev[0]["dst"].p), "picture_copy")
+            api._check(ctx.h, api.lib().ovgpu_picture_copy(ctx.h, ref_pics[slot // 2][slot % 2].p, (src or dev[0])["dst"].p), "picture_copy")
         ovdist.publish_reference(ref_shared[slot // 2][slot % 2], owner, world)
 
     def step_device(parallel=True):
@@ -381,35 +384,51 @@ def main():
     # so the copies of one picture overlap the kernels of another.  The big inputs (coefficients, deblocking maps)
     # sit in the objects' pinned staging buffers -- where the north-star recorder writes them -- and are copied to
     # the device inside the timed region by commit(); the small per-CTU tables go through upload().
+    # Two picture sets in flight (even / odd steps), each with its own contexts, streams, device objects and pinned output: the
+    # H2D copies of step k+1 and the D2H copies of step k-1 then run under the kernels of step k instead of queueing behind
+    # them in stream order -- 2 x n_ctx pictures in flight, like a decoder with that many frame threads.
     n_ctx = max(1, min(args.e2e_streams, P, os.cpu_count() or 1))
-    e_streams = [stream] + [torch.cuda.Stream() for _ in range(n_ctx - 1)]
-    e_ctx = [ctx] + [api.Ctx(local, st.cuda_stream) for st in e_streams[1:]]
-    pinned_out = [[torch.empty((hh, ww), dtype=torch.uint16).pin_memory() for (hh, ww) in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
-                  for _ in pics]
-    np_out = [[t.numpy() for t in pin] for pin in pinned_out]
-    for p, d in zip(pics, dev):
-        mc_c, mc_p = d["mc"].staging()
-        mc_c[:len(p["cmds"])] = p["cmds"]; mc_p[:len(p["prof"])] = p["prof"]
-        hc, hk = d["tu"].staging()
-        hc[:len(p["tus"])] = p["tus"]; hk[:len(p["coeffs"])] = p["coeffs"]
-        st = d["dbf"].staging()
-        for k in range(9):
-            st["ver"][k][:] = p["dbf"]["ver"][k]; st["hor"][k][:] = p["dbf"]["hor"][k]
-        for k in range(3):
-            st["qp"][k][:] = p["dbf"]["qp"][k]
+    n_sets = max(1, min(2, args.e2e_sets))
+    share = max(1, args.e2e_share)                 # contexts (host threads) per stream
+    real_streams = [torch.cuda.Stream() for _ in range((n_sets * n_ctx + share - 1) // share)]
+    e_streams = [real_streams[j // share] for j in range(n_sets * n_ctx)]
+    e_ctx = [api.Ctx(local, st.cuda_stream) for st in e_streams]
+    e_dev = [dev] + [[make_dev(p, ctx) for p in pics] for _ in range(n_sets - 1)]
+    ctx.sync()
+    pinned_out = [[[torch.empty((hh, ww), dtype=torch.uint16).pin_memory() for (hh, ww) in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
+                   for _ in pics] for _ in range(n_sets)]
+    np_out = [[[t.numpy() for t in pin] for pin in half] for half in pinned_out]
+    for half in e_dev:
+        for p, d in zip(pics, half):
+            mc_c, mc_p = d["mc"].staging()
+            mc_c[:len(p["cmds"])] = p["cmds"]; mc_p[:len(p["prof"])] = p["prof"]
+            hc, hk = d["tu"].staging()
+            hc[:len(p["tus"])] = p["tus"]; hk[:len(p["coeffs"])] = p["coeffs"]
+            st = d["dbf"].staging()
+            for k in range(9):
+                st["ver"][k][:] = p["dbf"]["ver"][k]; st["hor"][k][:] = p["dbf"]["hor"][k]
+            for k in range(3):
+                st["qp"][k][:] = p["dbf"]["qp"][k]
 
-    def e2e_worker(t, ev_start):
+    def e2e_worker(t, ev_start, half):
         """one host thread per context, like the reference's frame threads (ovdec.h:47): stages, commits and launches its
         pictures; ctypes releases the GIL inside the C-ABI calls, so the host-side work of different pictures overlaps.
         Nothing here waits for the GPU: staging + H2D of a step run while the kernels of the previous step are still
-        busy (the staging fences of the C ABI keep a pinned buffer from being rewritten before its last copy left);
+        busy, and the D2H of a finished picture runs under the kernels of the next step (the staging fences of the C ABI keep a pinned buffer from being rewritten before its last copy left);
         only the kernels wait, on the device, for the previous step's reference hand-off (ev_start)."""
         torch.cuda.set_device(local)
-        c, st = e_ctx[t], e_streams[t]
-        prof_host = os.environ.get("BENCH_HOST_PROFILE") and t == 0
+        c, st = e_ctx[half * n_ctx + t], e_streams[half * n_ctx + t]
+        evs = []
+        tl = timeline is not None
+
+        def mark(name, i):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(st)
+            timeline.append((e2e_no[0], i, name, e, time.perf_counter()))
         for i in range(t, len(dev), n_ctx):
-            p, d = pics[i], dev[i]
+            p, d = pics[i], e_dev[half][i]
             tt = [time.perf_counter()]
+            if tl: mark("h2d0", i)
             d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c); tt.append(time.perf_counter())
             d["tu"].set_anchors(p["anchors"], ctx=c)
             d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c); tt.append(time.perf_counter())
@@ -417,32 +436,42 @@ def main():
             d["dbf"].commit(0, 0, ctx=c); tt.append(time.perf_counter())
             d["sao"].upload(p["sao"], ctx=c)
             d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c); tt.append(time.perf_counter())
-            if st is not stream:
-                st.wait_event(ev_start)
+            if tl: mark("h2d1", i)
+            st.wait_event(ev_start)
+            if tl: mark("k0", i)
             api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs); tt.append(time.perf_counter())
-            if prof_host:
-                sys.stderr.write("host ms: mc_commit %.2f tu_commit %.2f intra_upload %.2f dbf_commit %.2f sao+alf %.2f recon_call %.2f\n"
-                                 % tuple(1e3 * (b - a) for a, b in zip(tt, tt[1:])))
             lmcs.reshape(d["rec"], forward=False, ctx=c)
             d["dbf"].run(d["rec"], ctx=c)
             d["sao"].run(d["mid"], d["rec"], ctx=c)
-            d["alf"].run(d["dst"], d["mid"], ctx=c)
-            api._check(c.h, api.lib().ovgpu_picture_download(c.h, d["dst"].p, *api._host_planes(np_out[i])), "download")
-        ev = torch.cuda.Event()
-        ev.record(st)
-        return ev
+            d["alf"].run(d["dst"], d["mid"], ctx=c); tt.append(time.perf_counter())
+            if host_prof is not None:
+                host_prof.append([1e3 * (b - a) for a, b in zip(tt, tt[1:])])
+            ev = torch.cuda.Event()
+            ev.record(st)                           # the picture is final on the device: what the reference hand-off needs
+            evs.append(ev)
+            if tl: mark("k1", i)
+            api._check(c.h, api.lib().ovgpu_picture_download(c.h, d["dst"].p, *api._host_planes(np_out[half][i])), "download")
+            if tl: mark("d2h1", i)
+        return evs
 
     from concurrent.futures import ThreadPoolExecutor
     pool = ThreadPoolExecutor(max_workers=n_ctx)
 
+    e2e_no = [0]
+    host_prof = [] if os.environ.get("BENCH_HOST_PROFILE") else None   # debugging aid: host time of the C-ABI calls, every thread
+    timeline = [] if os.environ.get("BENCH_TIMELINE") else None      # debugging aid: device + host time of every phase of every picture
+
     def step_e2e():
         ev_start = torch.cuda.Event()
         ev_start.record(stream)                     # after the previous step's hand-off
-        for ev in [f.result() for f in [pool.submit(e2e_worker, t, ev_start) for t in range(n_ctx)]]:
-            stream.wait_event(ev)                   # the timed stream joins the step's pictures on the device, not on the host
-        hand_off_reference()
+        half = e2e_no[0] % n_sets
+        e2e_no[0] += 1
+        for evs in [f.result() for f in [pool.submit(e2e_worker, t, ev_start, half) for t in range(n_ctx)]]:
+            for ev in evs:
+                stream.wait_event(ev)               # the hand-off waits, on the device, for the step's pictures to be final (their
+        hand_off_reference(e_dev[half][0])          # D2H copies run on under the next step's kernels; the closing barrier covers them)
 
-    step_e2e()
+    step_e2e(); step_e2e()
     e2e_steps = max(2, args.steps)
     barrier()
     t0 = time.perf_counter()
@@ -451,6 +480,15 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    if host_prof:
+        a = np.array(host_prof)
+        for k, name in enumerate(("mc_commit", "tu_commit", "intra_upload", "dbf_commit", "sao+alf", "recon_call", "inloop_calls")):
+            sys.stderr.write("host ms %-13s median %.2f p90 %.2f max %.2f\n" % (name, np.median(a[:, k]), np.percentile(a[:, k], 90), a[:, k].max()))
+        sys.stderr.write("host ms total per picture: median %.2f; step wall %.2f ms\n" % (np.median(a.sum(1)), 1e3 * e2e_s / e2e_steps))
+    if timeline:
+        base = min(timeline, key=lambda r: r[4])
+        for (stp, i, name, e, th) in sorted(timeline, key=lambda r: (r[0], r[1], r[4])):
+            sys.stderr.write("timeline step %d pic %d %-5s gpu %8.3f ms host %8.3f ms\n" % (stp, i, name, base[3].elapsed_time(e), 1e3 * (th - base[4])))
 
     # ---- max over ranks
     if world > 1:
@@ -486,7 +524,7 @@ def main():
                 "config": workload_config(w, h, P, n_ds),
                 "gpu_launches": launches,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": n_ctx, "host_threads": n_ctx},
+                        "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": len(real_streams), "host_threads": n_ctx, "pictures_in_flight": n_sets * P},
                 "roofline": {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak,
                              "peak_source": peak_src, "unit": "GB/s", "frac": stages[top]["frac"], "traffic": ncu_traffic(top)[0],
                              "traffic_source": ncu_traffic(top)[1],

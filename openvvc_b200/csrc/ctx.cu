@@ -138,6 +138,24 @@ int ovgpu_flush_l2(OVGPUCtx *ctx)
 }
 
 // ---- pictures ---------------------------------------------------------------------------------------
+// Device-to-device picture copy on the SMs: a DMA copy would queue on the copy engines behind the pictures being downloaded,
+// and the reference hand-off (the next pictures' motion compensation waits for it) must not.
+struct CopyPlanes {
+    const uint8_t *src[3];
+    uint8_t *dst[3];
+    uint32_t src_pitch[3], dst_pitch[3], row_bytes[3], rows[3];
+};
+__global__ void __launch_bounds__(256) ovgpu_copy_planes_kernel(CopyPlanes a)
+{
+    const int c = blockIdx.y;
+    const uint32_t per_row = a.row_bytes[c] >> 3;
+    const uint64_t n = (uint64_t)per_row * a.rows[c];
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t y = (uint32_t)(i / per_row), x = (uint32_t)(i - (uint64_t)y * per_row);
+        *(uint2 *)(a.dst[c] + (size_t)y * a.dst_pitch[c] + 8 * x) = *(const uint2 *)(a.src[c] + (size_t)y * a.src_pitch[c] + 8 * x);
+    }
+}
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **out)
@@ -219,6 +237,20 @@ int ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pi
 int ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src)
 {
     if (!ctx || !dst || !src || dst->width != src->width || dst->height != src->height) return OVGPU_EINVAL;
+    CopyPlanes a;
+    int aligned = 1;
+    for (int c = 0; c < 3; c++) {
+        a.src[c] = (const uint8_t *)src->plane[c]; a.dst[c] = (uint8_t *)dst->plane[c];
+        a.src_pitch[c] = (uint32_t)src->pitch[c]; a.dst_pitch[c] = (uint32_t)dst->pitch[c];
+        a.row_bytes[c] = (uint32_t)((c ? src->width >> 1 : src->width) * 2); a.rows[c] = (uint32_t)(c ? src->height >> 1 : src->height);
+        aligned &= !(((uintptr_t)a.src[c] | (uintptr_t)a.dst[c] | a.src_pitch[c] | a.dst_pitch[c] | a.row_bytes[c]) & 7);
+    }
+    if (aligned) {
+        ovgpu_copy_planes_kernel<<<dim3(148 * 2, 3, 1), 256, 0, ctx->stream>>>(a);
+        OVGPU_CUDA_CHECK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     for (int c = 0; c < 3; c++) {
         int w = c ? src->width >> 1 : src->width, h = c ? src->height >> 1 : src->height;
         OVGPU_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst->plane[c], dst->pitch[c], src->plane[c], src->pitch[c],

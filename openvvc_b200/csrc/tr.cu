@@ -13,9 +13,13 @@ struct OVGPUTuBatch {
     TuCmdDev *h_cmds, *d_cmds;
     TbItemDev *h_items, *d_items;       // small items first, then large ones
     int16_t *h_coeffs, *d_coeffs;
-    StagingFence fence;
-    // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h
+    StagingFence fence;                 // h_cmds, h_items, h_coeffs (staging / commit)
+    // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h.  Built into staging
+    // buffers of their own (h_bitems, h_ritems) behind their own fence, so that binding never waits for the coefficient
+    // copy the commit has just queued.
     TuReconLists lists;
+    TbItemDev *h_bitems;
+    StagingFence fence_bind, fence_anchors;
     ReconItemDev *h_ritems, *d_ritems;  // [plane][max_ritems]
     int max_ritems, nb_ritems[2];
     uint64_t serial, bound_serial, bound_intra_serial;
@@ -50,6 +54,7 @@ int ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPUT
     b->max_cmds = max_cmds; b->max_coeffs = max_coeffs; b->device = ctx->device;
     if (cudaMallocHost(&b->h_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
         cudaMallocHost(&b->h_items, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
+        cudaMallocHost(&b->h_bitems, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
         cudaMallocHost(&b->h_coeffs, sizeof(int16_t) * max_coeffs) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
         cudaMalloc(&b->d_items, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
@@ -67,11 +72,12 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     cudaSetDevice(b->device);
     if (b->h_cmds) cudaFreeHost(b->h_cmds);
     if (b->h_items) cudaFreeHost(b->h_items);
+    if (b->h_bitems) cudaFreeHost(b->h_bitems);
     if (b->h_coeffs) cudaFreeHost(b->h_coeffs);
     if (b->d_cmds) cudaFree(b->d_cmds);
     if (b->d_items) cudaFree(b->d_items);
     if (b->d_coeffs) cudaFree(b->d_coeffs);
-    fence_destroy(&b->fence);
+    fence_destroy(&b->fence); fence_destroy(&b->fence_bind); fence_destroy(&b->fence_anchors);
     if (b->h_ritems) cudaFreeHost(b->h_ritems);
     if (b->d_ritems) cudaFree(b->d_ritems);
     if (b->h_anchors) cudaFreeHost(b->h_anchors);
@@ -132,7 +138,7 @@ int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds
 int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAnchor *anchors, int nb)
 {
     if (!ctx || !b || nb < 0 || nb > 65536 || (nb && !anchors)) return OVGPU_EINVAL;
-    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence_anchors));
     if (nb > b->max_anchors) {
         if (b->h_anchors) cudaFreeHost(b->h_anchors);
         if (b->d_anchors) cudaFree(b->d_anchors);
@@ -150,7 +156,7 @@ int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAn
     if (nb) {
         memcpy(b->h_anchors, anchors, sizeof(LmcsAnchorDev) * nb);
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_anchors, b->h_anchors, sizeof(LmcsAnchorDev) * nb, cudaMemcpyHostToDevice, ctx->stream));
-        OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence_anchors, ctx->stream));
     }
     return 0;
 }
@@ -186,7 +192,7 @@ int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, c
         const TuCmdDev *c = &b->h_cmds[i];
         if ((c->x0 >> 2) >= w_u || (c->y0 >> 2) >= h_u) return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
-    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence_bind));
     const int need = nb[0] > nb[1] ? nb[0] : nb[1];
     if (need > b->max_ritems) {
         if (b->h_ritems) cudaFreeHost(b->h_ritems);
@@ -202,10 +208,10 @@ int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, c
         b->nb_ritems[p] = nb[p];
         for (int q = 0; q < nb[p]; q++) ritems[p][q].cmd = order[p][q];
     }
-    const int n = tu_build_recon_lists(b->h_items, &b->lists, ritems, nb, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, pos_l, pos_c, w_u);
-    if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
+    const int n = tu_build_recon_lists(b->h_bitems, &b->lists, ritems, nb, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, pos_l, pos_c, w_u);
+    if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_bitems, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (need) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_ritems, b->h_ritems, sizeof(ReconItemDev) * 2 * b->max_ritems, cudaMemcpyHostToDevice, ctx->stream));
-    OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence_bind, ctx->stream));
     b->bound_serial = b->serial; b->bound_intra_serial = intra_serial;
     return 0;
 }
