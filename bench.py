@@ -215,7 +215,7 @@ def run_reference(args, w, h):
 
 def workload_config(w, h, pics_per_step, dev_streams=1):
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
-                        "(IBC not yet in the timed path)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
+                        "(intra block copy: off, as for natural video in the common test conditions)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
             "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
             "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
 

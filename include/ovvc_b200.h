@@ -360,6 +360,11 @@ int  ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p
                                   * reconstructed one after the other inside ovgpu_recon_picture, with the transform units flagged
                                   * OVGPU_TU_ISP that lie inside the block.  pad[0] | pad[1] << 8 = index into the batch's OVGPUIspInfo table.
                                   * Not accepted by ovgpu_intra_picture (prediction alone is meaningless for ISP). */
+#define OVGPU_INTRA_IBC     128  /* flags: intra block copy (rcn_ibc_l / rcn_ibc_c slots, rcn_ibc.c:8-140): the block (luma and / or both chroma
+                                  * blocks, per the LUMA / CHROMA flags) is a copy of samples of the same picture reconstructed before it;
+                                  * block vector in luma samples, int16 little endian: x in pad[0..1], y in pad[2..3] (the reference's
+                                  * position in its CTU ring buffer = picture position (x0 + bv.x, y0 + bv.y) for every vector a stream
+                                  * may carry); chroma reads ((x0 + bv.x) >> 1, (y0 + bv.y) >> 1).  Only through ovgpu_recon_picture. */
 #define OVGPU_INTRA_ISP_VER  64  /* flags: vertical split (cu_opaque == 2), else horizontal */
 /* The availability words vvc_intra_pred_isp reads for an ISP coding unit at CTU-local (x0, y0): the progress field does not
  * change during the CU (the whole block is marked before the sub-tree, vcl_transform_unit.c:1878), so with q counting the

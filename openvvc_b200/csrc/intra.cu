@@ -90,7 +90,7 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     b->has_isp = 0;
-    for (int i = 0; i < nb_cmds; i++) b->has_isp |= (cmds[i].flags & OVGPU_INTRA_ISP) != 0;
+    for (int i = 0; i < nb_cmds; i++) b->has_isp |= (cmds[i].flags & (OVGPU_INTRA_ISP | OVGPU_INTRA_IBC)) != 0;
     if (nb_isp > b->max_isp) {
         if (b->h_isp) cudaFreeHost(b->h_isp);
         if (b->d_isp) cudaFree(b->d_isp);
@@ -116,7 +116,9 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
     }
     if (!nb_cmds) { memset(b->pos_l, 0, units * sizeof(uint32_t)); memset(b->pos_c, 0, units * sizeof(uint32_t)); return 0; }
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
-    if (intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c))
+    const int lrc = intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c);
+    if (lrc == -2) { b->nb_cmds = 0; return ovgpu_set_error(ctx, OVGPU_EINVAL, "a block copy command reads samples that are not reconstructed before it"); }
+    if (lrc)
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_order, b->h_order, sizeof(uint32_t) * 2 * b->max_cmds, cudaMemcpyHostToDevice, ctx->stream));
@@ -139,7 +141,7 @@ int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
 {
     if (!ctx || !pic || !b) return OVGPU_EINVAL;
     if (!b->nb_cmds) return 0;
-    if (b->has_isp) return ovgpu_set_error(ctx, OVGPU_EINVAL, "ISP commands are reconstructed by ovgpu_recon_picture only");
+    if (b->has_isp) return ovgpu_set_error(ctx, OVGPU_EINVAL, "ISP and block copy commands are reconstructed by ovgpu_recon_picture only");
     if (pic->width != b->pic_w || pic->height != b->pic_h)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
     StageScope scope(ctx, OVGPU_STAGE_INTRA, b->lv.nb[0] + b->lv.nb[1]);

@@ -9,7 +9,16 @@
 static inline int intra_check_cmd(const OVGPUIntraCmd *c, int pic_w, int pic_h)
 {
     if (c->log2_w < 2 || c->log2_w > 6 || c->log2_h < 2 || c->log2_h > 6 || c->x0 < 0 || c->y0 < 0) return -1;
-    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || (c->flags & ~127)) return -1;
+    if (!(c->flags & (OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA))) return -1;
+    if (c->flags & OVGPU_INTRA_IBC) {       /* block copy: nothing else applies; the source block lies in the picture and apart from the block */
+        if ((c->flags & ~(OVGPU_INTRA_IBC | OVGPU_INTRA_LUMA | OVGPU_INTRA_CHROMA)) || c->mrl_idx) return -1;
+        if ((c->x0 & 3) || (c->y0 & 3) || c->x0 + (1 << c->log2_w) > pic_w || c->y0 + (1 << c->log2_h) > pic_h) return -1;
+        const int bvx = (int16_t)(c->pad[0] | (c->pad[1] << 8)), bvy = (int16_t)(c->pad[2] | (c->pad[3] << 8));
+        const int sx = c->x0 + bvx, sy = c->y0 + bvy, w = 1 << c->log2_w, h = 1 << c->log2_h;
+        if (sx < 0 || sy < 0 || sx + w > pic_w || sy + h > pic_h) return -1;
+        if (sx < c->x0 + w && sx + w > c->x0 && sy < c->y0 + h && sy + h > c->y0) return -1;
+        return 0;
+    }
     if (c->flags & OVGPU_INTRA_ISP) {       /* whole luma coding block of 32 samples or more, plain modes only */
         if (!(c->flags & OVGPU_INTRA_LUMA) || (c->flags & (OVGPU_INTRA_CIIP | OVGPU_INTRA_MIP)) || c->mrl_idx || c->log2_w + c->log2_h < 5) return -1;
     } else if (c->flags & OVGPU_INTRA_ISP_VER) return -1;
@@ -52,7 +61,7 @@ static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu,
     return lv;
 }
 
-// Returns 0, or -1 (out of memory / more than max_levels levels).
+// Returns 0, -1 (out of memory / more than max_levels levels) or -2 (a block copy reads samples that are not reconstructed before it).
 static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPUIntraCmd *cmds, int n,
                                      int pic_w, int pic_h, uint32_t *pos_l = NULL, uint32_t *pos_c = NULL)
 {
@@ -77,7 +86,15 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
                 lv[i] = 0;
                 if (!(c->flags & bit)) continue;
                 const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
-                const int l = intra_neigh_level(m, w_u, h_u, xu, yu, nw, nh) + 1;
+                int l;
+                if (c->flags & OVGPU_INTRA_IBC) {       // block copy: depends on the commands covering its source block
+                    if (!pos[p]) { ret = -2; break; }   // (validated against the queue below, which needs the position map)
+                    int bvx = (int16_t)(c->pad[0] | (c->pad[1] << 8)), bvy = (int16_t)(c->pad[2] | (c->pad[3] << 8));
+                    l = 0;
+                    for (int y = (c->y0 + bvy) >> 2; y <= (c->y0 + bvy + (nh << 2) - 1) >> 2; y++)
+                        for (int x = (c->x0 + bvx) >> 2; x <= (c->x0 + bvx + (nw << 2) - 1) >> 2; x++) if (m[y * w_u + x] > l) l = m[y * w_u + x];
+                    l++;
+                } else l = intra_neigh_level(m, w_u, h_u, xu, yu, nw, nh) + 1;
                 if (l > 65535 || l > max_levels) { ret = -1; break; }
                 lv[i] = (uint16_t)l;
                 if (l > nb_levels) nb_levels = l;
@@ -101,6 +118,15 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
                     const OVGPUIntraCmd *c = &cmds[L->order[p][q]];
                     const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
                     for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) pos[p][y * w_u + x] = q + 1;
+                }
+                // a block copy may only read units that no command covers or that a command EARLIER in the queue covers: the
+                // dataflow kernel waits for them, and a wait on a later command (or on itself) would never end
+                for (uint32_t q = 0; q < start[nb_levels] && !ret; q++) {
+                    const OVGPUIntraCmd *c = &cmds[L->order[p][q]];
+                    if (!(c->flags & OVGPU_INTRA_IBC)) continue;
+                    int bvx = (int16_t)(c->pad[0] | (c->pad[1] << 8)), bvy = (int16_t)(c->pad[2] | (c->pad[3] << 8));
+                    for (int y = (c->y0 + bvy) >> 2; y <= (c->y0 + bvy + (1 << c->log2_h) - 1) >> 2; y++)
+                        for (int x = (c->x0 + bvx) >> 2; x <= (c->x0 + bvx + (1 << c->log2_w) - 1) >> 2; x++) if (pos[p][y * w_u + x] > q) ret = -2;
                 }
             }
         }

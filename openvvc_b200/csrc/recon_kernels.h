@@ -34,6 +34,32 @@ OVD void isp_geometry(int log2_w, int log2_h, int ver, int *lp, int *nb)
     *lp = p; *nb = (1 << (ver ? log2_w : log2_h)) >> p;
 }
 
+// Intra block copy (rcn_ibc_l / rcn_ibc_c, rcn_ibc.c:8-140): block vector in pad[0..3]; the 4x4 units the source block touches
+// (the luma range also bounds the chroma one) and the copy itself, strided over `nt` workers
+OVD void ibc_vector(const IntraCmdDev &c, int *bvx, int *bvy)
+{
+    *bvx = (int16_t)(c.pad[0] | (c.pad[1] << 8)); *bvy = (int16_t)(c.pad[2] | (c.pad[3] << 8));
+}
+OVD void ibc_source_units(const IntraCmdDev &c, int *ux0, int *uy0, int *ux1, int *uy1)
+{
+    int bvx, bvy;
+    ibc_vector(c, &bvx, &bvy);
+    *ux0 = (c.x0 + bvx) >> 2; *uy0 = (c.y0 + bvy) >> 2;
+    *ux1 = (c.x0 + bvx + (1 << c.log2_w) - 1) >> 2; *uy1 = (c.y0 + bvy + (1 << c.log2_h) - 1) >> 2;
+}
+OVD void ibc_copy(uint16_t *const plane[3], const int pitch[3], int plane_id, const IntraCmdDev &c, int tid, int nt)
+{
+    int bvx, bvy;
+    ibc_vector(c, &bvx, &bvy);
+    const int sh = plane_id ? 1 : 0, lw = c.log2_w - sh, n = 1 << (lw + c.log2_h - sh);
+    const int dx = c.x0 >> sh, dy = c.y0 >> sh, sx = (c.x0 + bvx) >> sh, sy = (c.y0 + bvy) >> sh;
+    for (int k = plane_id ? 1 : 0; k < (plane_id ? 3 : 1); k++)
+        for (int o = tid; o < n; o += nt) {
+            const int y = o >> lw, x = o & ((1 << lw) - 1);
+            plane[k][(size_t)(dy + y) * pitch[k] + dx + x] = plane[k][(size_t)(sy + y) * pitch[k] + sx + x];
+        }
+}
+
 struct ReconArgs {
     uint16_t *plane[3];
     int pitch[3], log2_ctu, bitdepth;
@@ -147,7 +173,19 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
         __syncthreads();
         const IntraCmdDev c = sg.cmd;
         const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
-        {   // wait for the available neighbour units this block's reference samples come from: the left column from the
+        const int ibc = (c.flags & 128) != 0;
+        if (ibc) {  // intra block copy: the units of the source block
+            int ux0, uy0, ux1, uy1;
+            ibc_source_units(c, &ux0, &uy0, &ux1, &uy1);
+            const int sw = ux1 - ux0 + 1;
+            for (int k = tid; k < sw * (uy1 - uy0 + 1); k += 128) {
+                const uint32_t *f = a.pend + (size_t)(uy0 + k / sw) * a.w_u + ux0 + k % sw;
+                while (recon_ld_relaxed(f) == a.serial) __nanosleep(32);
+            }
+            __threadfence();
+            __syncthreads();
+        } else {
+            // wait for the available neighbour units this block's reference samples come from: the left column from the
             // corner down to 2h below the top (avail_cols: bit 1 + row inside the CTU), the above row over 2w (avail_rows)
             const int um = ((1 << a.log2_ctu) >> 2) - 1, xl = xu & um, yl = yu & um;
             for (int k = tid; k < 2 * nh + 1 + 2 * nw; k += 128) {
@@ -165,7 +203,10 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
         IntraK::Args ia = recon_intra_args(a, &sg.zero);
         ia.cmds = &sg.cmd;
         const int isp = a.plane_id == 0 && (c.flags & 32);
-        if (!isp) {
+        if (ibc) {
+            ibc_copy(a.plane, a.pitch, a.plane_id, c, tid, 128);
+            __syncthreads();
+        } else if (!isp) {
             // ---- prediction
             IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
             IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();

@@ -11,10 +11,11 @@ INTRA_CMD = np.dtype([("x0", np.int16), ("y0", np.int16), ("log2_w", np.uint8), 
 assert INTRA_CMD.itemsize == 32
 
 INTRA_LUMA, INTRA_CHROMA, INTRA_CIIP, INTRA_CCLM_COLLOCATED, INTRA_MIP, INTRA_ISP, INTRA_ISP_VER = 1, 2, 4, 8, 16, 32, 64
+INTRA_IBC = 128
 
 
 def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0,
-                   collocated=False, p_inter=0.0, blocks=None, p_mip=0.0, p_isp=0.0):
+                   collocated=False, p_inter=0.0, blocks=None, p_mip=0.0, p_isp=0.0, p_ibc=0.0):
     """p_inter: fraction of coding units that are NOT intra (flags = 0 placeholders): they keep the picture's samples -- the
     already reconstructed inter CUs of a real picture -- and only take part in the availability replay.  Without them an
     all-intra picture without residual degenerates to the mid value everywhere.  The placeholders are for the oracle
@@ -22,9 +23,30 @@ def intra_commands(w, h, seed=1006, log2_ctu=7, min_log2=2, max_log2=6, chroma=F
     rng = np.random.default_rng(seed)
     part = blocks if blocks is not None else synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(max_log2, log2_ctu), p_split=0.5)
     cmds = np.zeros(len(part), dtype=INTRA_CMD)
+    done = np.zeros((h >> 2, w >> 2), bool) if p_ibc else None      # 4x4 units of the coding units decoded so far
+    ctu = 1 << log2_ctu
     for i, (x, y, lw, lh) in enumerate(part):
         c = cmds[i]
         c["x0"], c["y0"], c["log2_w"], c["log2_h"] = x, y, lw, lh
+        if p_ibc:
+            if i:
+                px, py, plw, plh = part[i - 1]
+                done[py >> 2:(py + (1 << plh)) >> 2, px >> 2:(px + (1 << plw)) >> 2] = True
+            if rng.random() < p_ibc:
+                # intra block copy (screen content): a block vector to samples decoded before, in this CTU or the one to its left,
+                # rows inside the CTU row -- what the reference's CTU ring buffer holds (rcn_ibc.c:14-27); any sample alignment
+                bw, bh, cx, cy = 1 << lw, 1 << lh, x >> log2_ctu, y >> log2_ctu
+                for _ in range(16):
+                    sx = int(rng.integers(max(0, (cx - 1) * ctu), min(w - bw, x + bw) + 1))
+                    sy = int(rng.integers(cy * ctu, min(h, (cy + 1) * ctu) - bh + 1))
+                    if rng.random() < 0.3:
+                        sx &= ~3; sy &= ~3
+                    if done[sy >> 2:((sy + bh - 1) >> 2) + 1, sx >> 2:((sx + bw - 1) >> 2) + 1].all():
+                        c["flags"] = INTRA_IBC | INTRA_LUMA | (INTRA_CHROMA if chroma else 0)
+                        c["pad"][:4] = np.array([sx - x, sy - y], np.int16).view(np.uint8)
+                        break
+                if c["flags"]:
+                    continue
         r = rng.random()
         if p_inter and rng.random() < p_inter:
             continue

@@ -7,14 +7,14 @@ from . import synth, synth_intra, synth_tu
 
 
 def recon_case(w, h, seed, log2_ctu=7, min_log2=2, p_inter=0.4, p_ciip=0.1, p_mrl=0.15, p_cclm=0.3, collocated=False, ict_type=0,
-               p_cbf=0.6, chroma=True, p_mip=0.0, p_isp=0.0, p_bdpcm=0.0):
+               p_cbf=0.6, chroma=True, p_mip=0.0, p_isp=0.0, p_bdpcm=0.0, p_ibc=0.0):
     """Returns (intra cmds incl. flags == 0 placeholders, tu cmds, arena); cmds[i] and tus[i] are the same coding unit.
     With p_isp: also (isp words, isp transform blocks [n_isp][4]); the luma residual of an ISP coding unit lives there (its
     tus[i] keeps the chroma blocks only) and the coefficients share the arena."""
     rng = np.random.default_rng(seed)
     blocks = synth.partition(w, h, rng, log2_ctu, min_log2=min_log2, max_log2=min(6, log2_ctu), p_split=0.5)
     cmds = synth_intra.intra_commands(w, h, seed + 1, log2_ctu, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm,
-                                      collocated=collocated, p_inter=p_inter, blocks=blocks, p_mip=p_mip, p_isp=p_isp)
+                                      collocated=collocated, p_inter=p_inter, blocks=blocks, p_mip=p_mip, p_isp=p_isp, p_ibc=p_ibc)
     words = isp_tus = isp_arena = None
     if p_isp:
         cmds, words, isp_tus, isp_arena = synth_intra.isp_tables(cmds, seed + 3)

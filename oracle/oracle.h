@@ -236,6 +236,8 @@ void ovo_dbf_picture(uint16_t *const planes[3], const int stride[3], int bitdept
 #define OVO_INTRA_ISP      32  /* flags: intra sub-partitions (recon_isp_subtree_{h,v}, rcn_transform_tree.c:1087-1205): the command is the whole
                                 * luma coding block; its partitions are predicted AND reconstructed one after the other, so the
                                 * command carries its transform blocks (isp index in pad[0] | pad[1] << 8) */
+#define OVO_INTRA_IBC      128 /* flags: intra block copy (rcn_ibc_l / rcn_ibc_c, rcn_ibc.c:8-140): the block is a copy of already reconstructed
+                                * samples of the same picture at the block vector pad[0..1] (x) / pad[2..3] (y), int16 little endian, luma samples */
 #define OVO_INTRA_ISP_VER  64  /* flags: vertical split (cu_opaque == 2), else horizontal */
 typedef struct OVOIntraCmd {
     int16_t x0, y0;               /* picture-absolute luma samples */

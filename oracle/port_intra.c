@@ -552,6 +552,25 @@ void ovo_intra_picture2(uint16_t *const planes[3], const int stride[3], int pic_
     }
 }
 
+/* rcn_ibc_l / rcn_ibc_c (rcn_ibc.c:8-140).  The reference copies inside its CTU ring buffer (256 * 128 >> log2_ctu_s luma columns:
+ * the current CTU and the ones decoded before it in the row, addressed modulo the ring width; rows modulo the CTU height).  For a
+ * block vector that points at samples already reconstructed in the current CTU or in the CTUs the ring still holds -- the only ones
+ * a conforming stream uses -- the ring position is the picture position (x0 + bv.x, y0 + bv.y), which is what is restated here.
+ * Chroma: position ((x0 + bv.x) >> 1, (y0 + bv.y) >> 1), both planes (:84-89, :107-112). */
+static void ibc_block(uint16_t *const planes[3], const int stride[3], const OVOIntraCmd *c)
+{
+    const int bvx = (int16_t)(c->pad[0] | (c->pad[1] << 8)), bvy = (int16_t)(c->pad[2] | (c->pad[3] << 8));
+    const int w = 1 << c->log2_w, h = 1 << c->log2_h;
+    if (c->flags & OVO_INTRA_LUMA)
+        for (int y = 0; y < h; y++)
+            memcpy(planes[0] + (size_t)(c->y0 + y) * stride[0] + c->x0, planes[0] + (size_t)(c->y0 + bvy + y) * stride[0] + c->x0 + bvx, 2 * w);
+    if (c->flags & OVO_INTRA_CHROMA)
+        for (int k = 1; k < 3; k++)
+            for (int y = 0; y < h / 2; y++)
+                memcpy(planes[k] + (size_t)((c->y0 >> 1) + y) * stride[k] + (c->x0 >> 1),
+                       planes[k] + (size_t)(((c->y0 + bvy) >> 1) + y) * stride[k] + ((c->x0 + bvx) >> 1), w);
+}
+
 void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                        const OVOIntraCmd *cmds, int nb_cmds)
 {
@@ -559,6 +578,7 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
     (void)pic_w; (void)pic_h;
     for (int i = 0; i < nb_cmds; i++) {
         const OVOIntraCmd *c = &cmds[i];
+        if (c->flags & OVO_INTRA_IBC) { ibc_block(planes, stride, c); continue; }
         int ciip = (c->flags & OVO_INTRA_CIIP) ? c->ciip_wt : 0;
         if ((c->flags & OVO_INTRA_LUMA) && (c->flags & OVO_INTRA_MIP))
             mip_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, c->mode, c->avail_cols, c->avail_rows);

@@ -119,6 +119,52 @@ ciip_block(OVCTUDec *c, const OVOIntraCmd *m, int x0, int y0, uint16_t *const in
 
 void ovref_intra_picture2(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
                           OVOIntraCmd *cmds, int nb_cmds, OVOIspInfo *isp, const int16_t *arena, int dep_quant, int mts_enabled);
+
+/* Intra block copy through the reference's own slots (rcn_funcs.rcn_ibc_l / rcn_ibc_c).  The harness keeps the CTUs in the picture
+ * planes, the reference copies inside its CTU ring buffer, so a ring is set up for the call: 256 * 128 >> log2_ctu_s luma columns
+ * (rcn_ctu.c:558-560), slot (ctb_x & mask) = the current CTU as reconstructed so far, every other slot = the CTU decoded most
+ * recently into it in this CTU row (slots no CTU of the row has reached yet stay zero); the copied block then goes back to the planes. */
+static void
+ibc_block(OVCTUDec *c, const OVOIntraCmd *m, uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h, int log2_ctu_s, int cx, int cy)
+{
+    const int ctu_s = 1 << log2_ctu_s, nslots = 256 * 128 >> (2 * log2_ctu_s), ring_w = nslots << log2_ctu_s;
+    const int slot = cx & (nslots - 1), ctb_pos = slot << log2_ctu_s;
+    struct OVBuffInfo saved = c->rcn_ctx.ctu_buff;
+    uint16_t *ring[3];
+    int rstride[3];
+    for (int k = 0; k < 3; k++) {
+        const int sh = k != 0;
+        rstride[k] = (ring_w >> sh) + 64;
+        ring[k] = calloc((size_t)rstride[k] * ((ctu_s >> sh) + 1), sizeof(uint16_t));
+        for (int s = 0; s < nslots; s++) {
+            const int src_cx = cx - ((slot - s) & (nslots - 1));
+            if (src_cx < 0) continue;
+            for (int y = 0; y < (ctu_s >> sh) && ((cy << log2_ctu_s) >> sh) + y < (pic_h >> sh); y++) {
+                int n = (pic_w >> sh) - ((src_cx << log2_ctu_s) >> sh);
+                if (n > (ctu_s >> sh)) n = ctu_s >> sh;
+                memcpy(ring[k] + (size_t)y * rstride[k] + ((s << log2_ctu_s) >> sh),
+                       planes[k] + (size_t)(((cy << log2_ctu_s) >> sh) + y) * stride[k] + ((src_cx << log2_ctu_s) >> sh), n * 2);
+            }
+        }
+    }
+    c->ctb_x = cx;
+    c->rcn_ctx.ctu_buff.y = ring[0] + ctb_pos; c->rcn_ctx.ctu_buff.stride = rstride[0];
+    c->rcn_ctx.ctu_buff.cb = ring[1] + (ctb_pos >> 1); c->rcn_ctx.ctu_buff.cr = ring[2] + (ctb_pos >> 1); c->rcn_ctx.ctu_buff.stride_c = rstride[1];
+    IBCMV mv = { (int16_t)(m->pad[0] | (m->pad[1] << 8)), (int16_t)(m->pad[2] | (m->pad[3] << 8)) };
+    const int x0 = m->x0 & (ctu_s - 1), y0 = m->y0 & (ctu_s - 1);
+    if (m->flags & OVO_INTRA_LUMA) c->rcn_funcs.rcn_ibc_l(c, x0, y0, m->log2_w, m->log2_h, log2_ctu_s, mv);
+    if (m->flags & OVO_INTRA_CHROMA) c->rcn_funcs.rcn_ibc_c(c, x0, y0, m->log2_w, m->log2_h, log2_ctu_s, mv);
+    for (int k = 0; k < 3; k++) {
+        const int sh = k != 0;
+        if ((k == 0 && (m->flags & OVO_INTRA_LUMA)) || (k && (m->flags & OVO_INTRA_CHROMA)))
+            for (int y = 0; y < (1 << m->log2_h) >> sh; y++)
+                memcpy(planes[k] + (size_t)((m->y0 >> sh) + y) * stride[k] + (m->x0 >> sh),
+                       ring[k] + (size_t)((y0 >> sh) + y) * rstride[k] + ((ctb_pos + x0) >> sh), ((1 << m->log2_w) >> sh) * 2);
+        free(ring[k]);
+    }
+    c->rcn_ctx.ctu_buff = saved;
+}
+
 void
 ovref_intra_picture(uint16_t *const user_planes[3], const int user_stride[3], int pic_w, int pic_h, int log2_ctu_s, int bitdepth, int simd,
                     OVOIntraCmd *cmds, int nb_cmds)
@@ -213,6 +259,8 @@ ovref_intra_picture2(uint16_t *const user_planes[3], const int user_stride[3], i
                             memcpy(planes[k] + off, inter_pic[k] + off, bw * 2);
                         }
                     }
+                } else if (m->flags & OVO_INTRA_IBC) {
+                    ibc_block(c, m, planes, stride, pic_w, pic_h, log2_ctu_s, cx, cy);
                 } else if (m->flags & OVO_INTRA_CIIP) {
                     ciip_block(c, m, x0, y0, inter_pic, stride);
                 } else if (m->flags & OVO_INTRA_ISP) {

@@ -268,7 +268,11 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
             const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
             uint32_t *pd = pend.data() + (size_t)p * w_u * h_u;
             // what the kernel would wait for must already be released in queue order
-            {
+            if (c.flags & OVGPU_INTRA_IBC) {
+                int ux0, uy0, ux1, uy1;
+                ibc_source_units(*(const IntraCmdDev *)&c, &ux0, &uy0, &ux1, &uy1);
+                for (int y = uy0; y <= uy1; y++) for (int x = ux0; x <= ux1; x++) if (pd[(size_t)y * w_u + x] == 7u) return -2000000 - q;
+            } else {
                 const int um = ((1 << log2_ctu) >> 2) - 1, xl = xu & um, yl = yu & um;
                 for (int k = 0; k < 2 * nh + 1 + 2 * nw; k++) {
                     int ux, uy, bit;
@@ -282,6 +286,11 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
             for (int k = 0; k < 3; k++) { ia.plane[k] = planes[k]; ia.pitch[k] = stride[k]; }
             ia.log2_ctu = log2_ctu; ia.bitdepth = bitdepth; ia.cmds = (const IntraCmdDev *)cmds; ia.order = &it.cmd; ia.nb = 1;
             ia.comp0 = p; ia.warp_comps = p ? 2 : 1;
+            const int ibc = (c.flags & OVGPU_INTRA_IBC) != 0;
+            if (ibc) {
+                uint16_t *pl[3] = { planes[0], planes[1], planes[2] };
+                ibc_copy(pl, stride, p, *(const IntraCmdDev *)&c, 0, 1);
+            }
             if (p == 0 && (c.flags & OVGPU_INTRA_ISP)) {
                 // the partition loop of ovd_recon_kernel
                 if (it.nb_tb > 4) return -5000000 - q;
@@ -308,7 +317,7 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
                     else emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + kb, 1, arena, &sl);
                 }
             } else {
-                ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
+                if (!ibc) ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
                 if (it.large) for (int k = 0; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
                 else for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS)
                     emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, it.nb_tb - k < TrK<32>::GROUPS ? it.nb_tb - k : TrK<32>::GROUPS, arena, &sl);

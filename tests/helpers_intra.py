@@ -6,10 +6,10 @@ import numpy as np
 from openvvc_b200 import synth, synth_intra
 
 
-def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0, collocated=False, p_inter=0.3, p_mip=0.0):
+def intra_case(w, h, seed, log2_ctu=7, min_log2=2, kind="natural", chroma=False, p_ciip=0.0, p_mrl=0.0, p_cclm=0.0, collocated=False, p_inter=0.3, p_mip=0.0, p_ibc=0.0):
     """planes + intra commands in decode order with the availability words replayed from that order; commands with
     flags == 0 are non-intra placeholders (see synth_intra.intra_commands) that emu_intra / gpu_intra drop"""
-    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm, collocated=collocated, p_inter=p_inter, p_mip=p_mip), log2_ctu)
+    cmds = synth_intra.availability(w, h, synth_intra.intra_commands(w, h, seed, log2_ctu, min_log2=min_log2, chroma=chroma, p_ciip=p_ciip, p_mrl=p_mrl, p_cclm=p_cclm, collocated=collocated, p_inter=p_inter, p_mip=p_mip, p_ibc=p_ibc), log2_ctu)
     return synth.planes(w, h, seed + 1, kind), np.ascontiguousarray(cmds)
 
 
@@ -47,3 +47,8 @@ def isp_case(w, h, seed, log2_ctu=7, p_isp=0.5, p_inter=0.3):
     cmds, words, tus, arena = synth_intra.isp_tables(cmds, seed + 7)
     cmds = synth_intra.availability(w, h, cmds, log2_ctu, isp_words=words)
     return synth.planes(w, h, seed + 1), np.ascontiguousarray(cmds), words, tus, arena
+
+
+def ibc_case(w, h, seed, log2_ctu=7, chroma=True, p_ibc=0.35):
+    """planes + single-tree commands in decode order, a third of them intra block copies (block vector in pad[0..3])"""
+    return intra_case(w, h, seed, log2_ctu, chroma=chroma, p_cclm=0.3 if chroma else 0.0, p_mrl=0.1, p_inter=0.3, p_ibc=p_ibc)

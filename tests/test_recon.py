@@ -193,7 +193,7 @@ def test_gpu_isp_matches_oracle(oracle, gpu_ctx, w, h, log2):
 
 
 def _mixed_isp_case(po, w, h, log2, ict):
-    cmds, tus, arena, words, isp_tus = synth_recon.recon_case(w, h, 13 * w + h, log2, ict_type=ict, p_cclm=0.3, p_mip=0.1, p_isp=0.4, p_bdpcm=0.8)
+    cmds, tus, arena, words, isp_tus = synth_recon.recon_case(w, h, 13 * w + h, log2, ict_type=ict, p_cclm=0.3, p_mip=0.1, p_isp=0.4, p_bdpcm=0.8, p_ibc=0.15)
     lm = Lm(po, cmds, tus, log2, ict, 5 * w + h)
     flat = np.ascontiguousarray(np.concatenate([lm.tus[lm.tus["cbf_mask"] != 0], isp_tus.reshape(-1)[isp_tus.reshape(-1)["cbf_mask"] != 0]]))
     return synth.planes(w, h, 3 * w + h), cmds, lm.tus, flat, arena, words, isp_tus, lm
@@ -201,10 +201,10 @@ def _mixed_isp_case(po, w, h, log2, ict):
 
 @pytest.mark.parametrize("w,h,log2,ict", [(416, 240, 7, 1), (832, 480, 7, 0), (264, 136, 6, 1)])
 def test_emulated_mixed_picture_with_isp(oracle, pr, emu, w, h, log2, ict):
-    """everything at once: inter CUs with residual, CIIP, plain / MRL / MIP / CCLM / ISP / BDPCM intra CUs, LMCS chroma scales from luma"""
+    """everything at once: inter CUs with residual, CIIP, plain / MRL / MIP / CCLM / ISP / BDPCM intra CUs, intra block copy, LMCS chroma scales from luma"""
     from oracle import pyoracle_intra as pi
     planes, cmds, tus, flat, arena, words, isp_tus, lm = _mixed_isp_case(oracle, w, h, log2, ict)
-    assert ((cmds["flags"] & 32) != 0).sum() > 5 and (tus["bdpcm"] != 0).sum() > 2
+    assert ((cmds["flags"] & 32) != 0).sum() > 5 and (tus["bdpcm"] != 0).sum() > 2 and ((cmds["flags"] & 128) != 0).sum() > 5
     want = pr.recon_picture([p.copy() for p in planes], cmds, tus, arena, log2, ict_type=ict, anchors=lm.anchors, luts=lm.luts,
                             lmcs_data=lm.data, isp=pi.isp_info_array(words, isp_tus))
     got, _ = _emu(emu, planes, cmds, flat, arena, log2, ict, lm, isp=np.ascontiguousarray(words))
