@@ -166,6 +166,10 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
         cudaFuncSetAttribute(ovd_recon_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ovd_recon_kernel, 128, RECON_SMEM_BYTES) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
+        // tuning knob: resident workers per SM (default: what fits).  Fewer workers leave shared memory and issue slots to the
+        // kernels of other pictures running next to this one; the queue order keeps any number >= 1 deadlock-free.
+        const char *e = getenv("OVGPU_RECON_WORKERS_PER_SM");
+        if (e && atoi(e) >= 1 && atoi(e) < blocks_per_sm) blocks_per_sm = atoi(e);
         configured = 1;
     }
     PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);

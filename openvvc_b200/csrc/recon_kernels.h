@@ -128,6 +128,10 @@ struct ReconPrepK {
     }
 };
 
+// Shared memory of a worker: the residual blocks (TrK's layout) and, behind them, the prediction's reference arrays (IntraK's):
+// the residual of a command is transformed BEFORE the command waits for its neighbours and is held while the prediction runs.
+static const int RECON_TR_SMEM_BYTES = ((TrK<128>::SMEM_BYTES > TrK<32>::SMEM_BYTES ? TrK<128>::SMEM_BYTES : TrK<32>::SMEM_BYTES) + 15) & ~15;
+
 #if !defined(OVGPU_HOST_EMU) && defined(OVGPU_RECON_KERNEL_IMPL)      // the one translation unit that launches it (intra.cu)
 // polling load: relaxed (no cache maintenance per iteration); the acquire fence follows once the flag has flipped
 __device__ __forceinline__ uint32_t recon_ld_relaxed(const uint32_t *p)
@@ -174,6 +178,44 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
         const IntraCmdDev c = sg.cmd;
         const int xu = c.x0 >> 2, yu = c.y0 >> 2, nw = (1 << c.log2_w) >> 2, nh = (1 << c.log2_h) >> 2;
         const int ibc = (c.flags & 128) != 0;
+        const int isp = a.plane_id == 0 && (c.flags & 32);
+        unsigned char *const sm_tr = ovd_smem, *const sm_intra = ovd_smem + RECON_TR_SMEM_BYTES;
+#define RECON_TR_PHASES(G, st, ta, P0, P1)                                                                                      \
+        do {                                                                                                                    \
+            if (P0 <= 0 && P1 >= 0) { TrK<G>::phase<0>(ta, sm_tr, st, tid, 0, 0, 0); __syncthreads(); }                         \
+            if (P0 <= 1 && P1 >= 1) { TrK<G>::phase<1>(ta, sm_tr, st, tid, 0, 0, 0); __syncthreads(); }                         \
+            if (P0 <= 2 && P1 >= 2) { TrK<G>::phase<2>(ta, sm_tr, st, tid, 0, 0, 0); __syncthreads(); }                         \
+            if (P0 <= 3 && P1 >= 3) { TrK<G>::phase<3>(ta, sm_tr, st, tid, 0, 0, 0); __syncthreads(); }                         \
+        } while (0)
+#define RECON_INTRA_PHASES()                                                                                                    \
+        do {                                                                                                                    \
+            IntraK::phase<0>(ia, sm_intra, ist, tid, 0, 0, 0); __syncthreads();                                                 \
+            IntraK::phase<1>(ia, sm_intra, ist, tid, 0, 0, 0); __syncthreads();                                                 \
+            IntraK::phase<2>(ia, sm_intra, ist, tid, 0, 0, 0); __syncthreads();                                                 \
+            IntraK::phase<3>(ia, sm_intra, ist, tid, 0, 0, 0); __syncthreads();                                                 \
+        } while (0)
+        // stages the transform-block items k0 .. k0 + nk of the command and their TU commands (+ the ISP words) in shared memory
+        auto stage_tbs = [&](int k0, int nk) {
+            if (tid < nk) { TbItemDev t = a.tb[it.tb_start + k0 + tid]; sg.tb[tid].cmd = tid; sg.tb[tid].kind = t.kind;
+                            /* the TU command index travels through shared memory to the copy below */ ((uint32_t *)sm_tr)[tid] = t.cmd; }
+            if (isp && tid >= 32 && tid < 32 + (int)(sizeof(IspInfoDev) / 4))
+                ((uint32_t *)&sg.isp)[tid - 32] = ((const uint32_t *)&a.isp[c.pad[0] | (c.pad[1] << 8)])[tid - 32];
+            __syncthreads();
+            for (int o = tid; o < nk * (int)(sizeof(TuCmdDev) / 4); o += 128) {
+                const int k = o / (int)(sizeof(TuCmdDev) / 4), wd = o - k * (int)(sizeof(TuCmdDev) / 4);
+                ((uint32_t *)&sg.tu[k])[wd] = ((const uint32_t *)&a.tu_cmds[((const uint32_t *)sm_tr)[k]])[wd];
+            }
+            __syncthreads();
+        };
+        // ---- before waiting for anything: the residual of the first blocks does not depend on the picture (dequantisation and
+        // both transform passes read coefficients only), so it is computed into shared memory now, off the dependency chain;
+        // only its addition to the prediction (phase 3) has to follow the prediction
+        const int nk0 = ovd_min(4, (int)it.nb_tb);
+        if (nk0 || isp) stage_tbs(0, nk0);                   // (an ISP command without coded partitions still needs its words)
+        if (nk0 && !isp) {
+            if (it.large) { TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb, 1); ta.cmds = sg.tu; RECON_TR_PHASES(128, tl, ta, 0, 2); }
+            else          { TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb, nk0); ta.cmds = sg.tu; RECON_TR_PHASES(32, ts, ta, 0, 2); }
+        }
         if (ibc) {  // intra block copy: the units of the source block
             int ux0, uy0, ux1, uy1;
             ibc_source_units(c, &ux0, &uy0, &ux1, &uy1);
@@ -182,8 +224,6 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
                 const uint32_t *f = a.pend + (size_t)(uy0 + k / sw) * a.w_u + ux0 + k % sw;
                 while (recon_ld_relaxed(f) == a.serial) __nanosleep(32);
             }
-            __threadfence();
-            __syncthreads();
         } else {
             // wait for the available neighbour units this block's reference samples come from: the left column from the
             // corner down to 2h below the top (avail_cols: bit 1 + row inside the CTU), the above row over 2w (avail_rows)
@@ -197,35 +237,21 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
                     while (recon_ld_relaxed(f) == a.serial) __nanosleep(32);
                 }
             }
-            __threadfence();                                // acquire side of the units' release stores (fence.acq_rel.gpu)
-            __syncthreads();
         }
+        __threadfence();                                    // acquire side of the units' release stores (fence.acq_rel.gpu)
+        __syncthreads();
         IntraK::Args ia = recon_intra_args(a, &sg.zero);
         ia.cmds = &sg.cmd;
-        const int isp = a.plane_id == 0 && (c.flags & 32);
         if (ibc) {
             ibc_copy(a.plane, a.pitch, a.plane_id, c, tid, 128);
             __syncthreads();
         } else if (!isp) {
-            // ---- prediction
-            IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-            IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-            IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-            IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+            RECON_INTRA_PHASES();                           // ---- prediction
         }
         // ---- residual of the blocks this command covers, up to four at a time (an ISP command has at most four)
         for (int k0 = 0; k0 < (isp ? 1 : it.nb_tb); k0 += 4) {
             const int nk = ovd_min(4, it.nb_tb - k0);
-            if (tid < nk) { TbItemDev t = a.tb[it.tb_start + k0 + tid]; sg.tb[tid].cmd = tid; sg.tb[tid].kind = t.kind;
-                            /* the TU command index travels through shared memory to the copy below */ ((uint32_t *)ovd_smem)[tid] = t.cmd; }
-            if (isp && tid >= 32 && tid < 32 + (int)(sizeof(IspInfoDev) / 4))
-                ((uint32_t *)&sg.isp)[tid - 32] = ((const uint32_t *)&a.isp[c.pad[0] | (c.pad[1] << 8)])[tid - 32];
-            __syncthreads();
-            for (int o = tid; o < nk * (int)(sizeof(TuCmdDev) / 4); o += 128) {
-                const int k = o / (int)(sizeof(TuCmdDev) / 4), wd = o - k * (int)(sizeof(TuCmdDev) / 4);
-                ((uint32_t *)&sg.tu[k])[wd] = ((const uint32_t *)&a.tu_cmds[((const uint32_t *)ovd_smem)[k]])[wd];
-            }
-            __syncthreads();
+            if (k0) stage_tbs(k0, nk);
             if (isp) {
                 // recon_isp_subtree_{v,h} (rcn_transform_tree.c:1087-1205): the partitions one after the other, each predicted
                 // (vertical split: in groups of at least four columns) and then reconstructed with its own transform block
@@ -239,54 +265,35 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
                         ia.isp_lpw = ver ? ovd_max(lp, 2) : c.log2_w; ia.isp_lph = ver ? c.log2_h : lp;
                         ia.isp_cols = ver ? sg.isp.part[q] : sg.isp.common; ia.isp_rows = ver ? sg.isp.common : sg.isp.part[q];
                         q++;
-                        IntraK::phase<0>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-                        IntraK::phase<1>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-                        IntraK::phase<2>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
-                        IntraK::phase<3>(ia, ovd_smem, ist, tid, 0, 0, 0); __syncthreads();
+                        RECON_INTRA_PHASES();
                     }
                     int kb = -1;                                    // the transform block of this partition, if it has one
                     for (int k = 0; k < nk; k++)
                         if ((ver ? (sg.tu[k].x0 - c.x0) : (sg.tu[k].y0 - c.y0)) == off) kb = k;
                     if (kb < 0) continue;
-                    if (it.large) {
-                        TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + kb, 1);
-                        ta.cmds = sg.tu;
-                        TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                        TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                        TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                        TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                    } else {
-                        TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb + kb, 1);
-                        ta.cmds = sg.tu;
-                        TrK<32>::phase<0>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                        TrK<32>::phase<1>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                        TrK<32>::phase<2>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                        TrK<32>::phase<3>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                    }
+                    if (it.large) { TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + kb, 1); ta.cmds = sg.tu; RECON_TR_PHASES(128, tl, ta, 0, 3); }
+                    else          { TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb + kb, 1); ta.cmds = sg.tu; RECON_TR_PHASES(32, ts, ta, 0, 3); }
                 }
             } else if (it.large) {
                 for (int k = 0; k < nk; k++) {
                     TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb + k, 1);
                     ta.cmds = sg.tu;
-                    TrK<128>::phase<0>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                    TrK<128>::phase<1>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                    TrK<128>::phase<2>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
-                    TrK<128>::phase<3>(ta, ovd_smem, tl, tid, 0, 0, 0); __syncthreads();
+                    if (k0 == 0 && k == 0) RECON_TR_PHASES(128, tl, ta, 3, 3);      // computed before the wait
+                    else RECON_TR_PHASES(128, tl, ta, 0, 3);
                 }
             } else {
                 TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb, nk);
                 ta.cmds = sg.tu;
-                TrK<32>::phase<0>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                TrK<32>::phase<1>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                TrK<32>::phase<2>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
-                TrK<32>::phase<3>(ta, ovd_smem, ts, tid, 0, 0, 0); __syncthreads();
+                if (k0 == 0) RECON_TR_PHASES(32, ts, ta, 3, 3);                      // computed before the wait
+                else RECON_TR_PHASES(32, ts, ta, 0, 3);
             }
         }
+#undef RECON_TR_PHASES
+#undef RECON_INTRA_PHASES
         // ---- publish: every thread's stores are ordered before the barrier above; the release stores are cumulative over it
         for (int o = tid; o < nw * nh; o += 128) recon_st_release(a.pend + (size_t)(yu + o / nw) * a.w_u + xu + o % nw, 0u);
     }
 }
 #endif
 
-static const int RECON_SMEM_BYTES = TrK<128>::SMEM_BYTES > IntraK::SMEM_BYTES ? (TrK<128>::SMEM_BYTES > TrK<32>::SMEM_BYTES ? TrK<128>::SMEM_BYTES : TrK<32>::SMEM_BYTES)
-                                                                              : (IntraK::SMEM_BYTES > TrK<32>::SMEM_BYTES ? IntraK::SMEM_BYTES : TrK<32>::SMEM_BYTES);
+static const int RECON_SMEM_BYTES = RECON_TR_SMEM_BYTES + IntraK::SMEM_BYTES;

@@ -26,6 +26,31 @@ static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int b
     ovd_emulate<K>(a, ovd_dim3((n + K::GROUPS - 1) / K::GROUPS, 1, 1), K::SMEM_BYTES);
 }
 
+// one CTA of kernel K, phases p0 .. p1, on a caller-owned shared-memory buffer (the worker of ovd_recon_kernel interleaves the
+// phases of two kernels on one buffer)
+template <class K>
+static void emu_phases(const typename K::Args &a, unsigned char *sm, int p0, int p1)
+{
+    std::vector<typename K::State> st(K::THREADS);
+    if (p0 <= 0 && p1 >= 0) for (int t = 0; t < K::THREADS; t++) K::template phase<0>(a, sm, st[t], t, 0, 0, 0);
+    if (p0 <= 1 && p1 >= 1) for (int t = 0; t < K::THREADS; t++) K::template phase<1>(a, sm, st[t], t, 0, 0, 0);
+    if (p0 <= 2 && p1 >= 2) for (int t = 0; t < K::THREADS; t++) K::template phase<2>(a, sm, st[t], t, 0, 0, 0);
+    if (p0 <= 3 && p1 >= 3) for (int t = 0; t < K::THREADS; t++) K::template phase<3>(a, sm, st[t], t, 0, 0, 0);
+}
+template <int GROUP>
+static typename TrK<GROUP>::Args emu_tr_args(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,
+                                             const TbItemDev *items, int n, const int16_t *arena, const OVGPUTuSlice *sl)
+{
+    typename TrK<GROUP>::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
+    a.bitdepth = bitdepth;
+    a.cmds = (const TuCmdDev *)cmds; a.items = items; a.nb_items = n; a.arena = arena;
+    a.dep_quant = sl->dep_quant; a.sh_ts_disabled = sl->sh_ts_disabled; a.ict_type = sl->ict_type;
+    a.scales = emu_tr_scales;
+    return a;
+}
+
 extern "C" {
 
 void emu_set_reverse_block_order(int on) { ovd_emu_reverse_blocks = on; }
@@ -287,10 +312,6 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
             ia.log2_ctu = log2_ctu; ia.bitdepth = bitdepth; ia.cmds = (const IntraCmdDev *)cmds; ia.order = &it.cmd; ia.nb = 1;
             ia.comp0 = p; ia.warp_comps = p ? 2 : 1;
             const int ibc = (c.flags & OVGPU_INTRA_IBC) != 0;
-            if (ibc) {
-                uint16_t *pl[3] = { planes[0], planes[1], planes[2] };
-                ibc_copy(pl, stride, p, *(const IntraCmdDev *)&c, 0, 1);
-            }
             if (p == 0 && (c.flags & OVGPU_INTRA_ISP)) {
                 // the partition loop of ovd_recon_kernel
                 if (it.nb_tb > 4) return -5000000 - q;
@@ -317,9 +338,24 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
                     else emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + kb, 1, arena, &sl);
                 }
             } else {
-                if (!ibc) ovd_emulate<IntraK>(ia, ovd_dim3(1, 1, 1), IntraK::SMEM_BYTES);
-                if (it.large) for (int k = 0; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
-                else for (int k = 0; k < it.nb_tb; k += TrK<32>::GROUPS)
+                // as in ovd_recon_kernel: the residual of the first blocks is transformed into shared memory first (phases 0-2),
+                // held there while the prediction runs behind it in the same buffer, and added afterwards (phase 3)
+                std::vector<uint64_t> smv(RECON_SMEM_BYTES / 8 + 2);
+                unsigned char *sm = (unsigned char *)smv.data();
+                memset(sm, 0xcd, RECON_SMEM_BYTES);
+                const int nk0 = it.nb_tb < 4 ? it.nb_tb : 4;
+                TrK<128>::Args tl = emu_tr_args<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start, 1, arena, &sl);
+                TrK<32>::Args ts = emu_tr_args<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start, nk0, arena, &sl);
+                if (nk0 && it.large) emu_phases<TrK<128> >(tl, sm, 0, 2);
+                else if (nk0) emu_phases<TrK<32> >(ts, sm, 0, 2);
+                if (ibc) {
+                    uint16_t *pl[3] = { planes[0], planes[1], planes[2] };
+                    ibc_copy(pl, stride, p, *(const IntraCmdDev *)&c, 0, 1);
+                } else emu_phases<IntraK>(ia, sm + RECON_TR_SMEM_BYTES, 0, 3);
+                if (nk0 && it.large) emu_phases<TrK<128> >(tl, sm, 3, 3);
+                else if (nk0) emu_phases<TrK<32> >(ts, sm, 3, 3);
+                if (it.large) for (int k = 1; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
+                else for (int k = 4; k < it.nb_tb; k += TrK<32>::GROUPS)
                     emu_tr_launch<32>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, it.nb_tb - k < TrK<32>::GROUPS ? it.nb_tb - k : TrK<32>::GROUPS, arena, &sl);
             }
             for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) {
