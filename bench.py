@@ -93,13 +93,41 @@ def make_workload(w, h, n_pics, seed0=5000):
         icmds, tus, coeffs, isp_words, isp_tus = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15,
                                                                         p_cclm=0.3, ict_type=1, p_cbf=0.4, p_mip=0.1, p_isp=0.1, p_bdpcm=0.3)
         anchors, tus = synth_recon.lmcs_anchors(icmds, tus, 7)
+        icmds_all, tus_all = icmds, tus                     # one entry per coding unit, decode order (what the CU-order oracle walks)
         icmds = np.ascontiguousarray(icmds[icmds["flags"] != 0])
         tus = np.ascontiguousarray(np.concatenate([tus, isp_tus.reshape(-1)[isp_tus.reshape(-1)["cbf_mask"] != 0]]))   # + the ISP partitions' blocks
         blks = synth_dbf.dbf_blocks(w, h, seed0 + 500 + i, 7, min_log2=3)
         dbf = synth_dbf.dbf_maps(w, h, blks, 7)
         pics.append(dict(tab=tab, ctu=ap["ctu"], alf_ctu=api.alf_ctu_array(ap["ctu"]), sao=sao, cmds=cmds, prof=prof, tus=tus, coeffs=coeffs,
-                         dbf_blks=blks, dbf=dbf, icmds=icmds, anchors=anchors, isp_words=isp_words, isp_tus=isp_tus))
-    return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), pics=pics)
+                         dbf_blks=blks, dbf=dbf, icmds=icmds, anchors=anchors, isp_words=isp_words, isp_tus=isp_tus,
+                         icmds_all=icmds_all, tus_all=tus_all))
+    return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), lmcs_dict=synth.lmcs_data(seed0), pics=pics)
+
+
+def make_dev(api, c, p, w, h):
+    """device objects of one picture (C-ABI handles) with its decoder state uploaded"""
+    d = dict(rec=c.picture(w, h), mid=c.picture(w, h), dst=c.picture(w, h),
+             alf=api.AlfParams(c, w, h, 7), sao=api.SaoParams(c, w, h, 7),
+             mc=api.McBatch(c, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
+             tu=api.TuBatch(c, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(c, w, h, 7),
+             intra=api.IntraBatch(c, max(1, len(p["icmds"]))))
+    d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
+    d["sao"].upload(p["sao"])
+    d["mc"].upload(p["cmds"], prof=p["prof"])
+    d["tu"].set_anchors(p["anchors"])
+    d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
+    d["intra"].upload(p["icmds"], w, h, 7, isp=p["isp_words"])
+    d["dbf"].upload(p["dbf"])
+    return d
+
+
+def run_stages(api, c, d, ref_pics, pocs, lmcs):
+    """one pass of the hot path over one picture: MC + residual + intra (reconstruction order), LMCS backward reshape, DBF, SAO, ALF"""
+    api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=pocs, lmcs=lmcs)
+    lmcs.reshape(d["rec"], forward=False, ctx=c)
+    d["dbf"].run(d["rec"], ctx=c)
+    d["sao"].run(d["mid"], d["rec"], ctx=c)
+    d["alf"].run(d["dst"], d["mid"], ctx=c)
 
 
 STAGE_KERNELS = {"mc": ("McK", "BdofK", "DmvrK", "ProfK", "McSmallCK"), "residual": ("TrK",), "intra": ("ovd_recon_kernel", "ReconPrepK"),
@@ -282,22 +310,7 @@ def main():
             pic.upload(planes)
     lmcs = api.Lmcs(ctx, wl["lmcs"])
     lmcs.set_data(wl["lmcs_data"])
-    def make_dev(p, c):
-        d = dict(rec=c.picture(w, h), mid=c.picture(w, h), dst=c.picture(w, h),
-                 alf=api.AlfParams(c, w, h, 7), sao=api.SaoParams(c, w, h, 7),
-                 mc=api.McBatch(c, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
-                 tu=api.TuBatch(c, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(c, w, h, 7),
-                 intra=api.IntraBatch(c, max(1, len(p["icmds"]))))
-        d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
-        d["sao"].upload(p["sao"])
-        d["mc"].upload(p["cmds"], prof=p["prof"])
-        d["tu"].set_anchors(p["anchors"])
-        d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
-        d["intra"].upload(p["icmds"], w, h, 7, isp=p["isp_words"])
-        d["dbf"].upload(p["dbf"])
-        return d
-
-    dev = [make_dev(p, ctx) for p in pics]
+    dev = [make_dev(api, ctx, p, w, h) for p in pics]
     ctx.sync()
 
     # Frame parallelism on one GPU: the pictures of a step are independent (same temporal layer), so they are spread over
@@ -308,13 +321,8 @@ def main():
     d_streams = [stream] + [torch.cuda.Stream() for _ in range(n_ds - 1)]
     d_ctx = [ctx] + [api.Ctx(local, st.cuda_stream) for st in d_streams[1:]]
 
-    def run_stages(d, c=None):
-        c = c or ctx
-        api.recon_picture(c, d["rec"], tu=d["tu"], intra=d["intra"], mc=d["mc"], ref_lists=ref_pics, pocs=wl["pocs"], lmcs=lmcs)
-        lmcs.reshape(d["rec"], forward=False, ctx=c)
-        d["dbf"].run(d["rec"], ctx=c)
-        d["sao"].run(d["mid"], d["rec"], ctx=c)
-        d["alf"].run(d["dst"], d["mid"], ctx=c)
+    def run_picture(d, c=None):
+        run_stages(api, c or ctx, d, ref_pics, wl["pocs"], lmcs)
 
     step_no = [0]
 
@@ -331,14 +339,14 @@ def main():
     def step_device(parallel=True):
         if not parallel or n_ds == 1:
             for d in dev:
-                run_stages(d)
+                run_picture(d)
         else:
             ev0 = torch.cuda.Event()
             ev0.record(stream)
             for st in d_streams[1:]:
                 st.wait_event(ev0)
             for i, d in enumerate(dev):
-                run_stages(d, d_ctx[i % n_ds])
+                run_picture(d, d_ctx[i % n_ds])
             for st in d_streams[1:]:
                 ev = torch.cuda.Event()
                 ev.record(st)
@@ -393,7 +401,7 @@ def main():
     real_streams = [torch.cuda.Stream() for _ in range((n_sets * n_ctx + share - 1) // share)]
     e_streams = [real_streams[j // share] for j in range(n_sets * n_ctx)]
     e_ctx = [api.Ctx(local, st.cuda_stream) for st in e_streams]
-    e_dev = [dev] + [[make_dev(p, ctx) for p in pics] for _ in range(n_sets - 1)]
+    e_dev = [dev] + [[make_dev(api, ctx, p, w, h) for p in pics] for _ in range(n_sets - 1)]
     ctx.sync()
     pinned_out = [[[torch.empty((hh, ww), dtype=torch.uint16).pin_memory() for (hh, ww) in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
                    for _ in pics] for _ in range(n_sets)]
