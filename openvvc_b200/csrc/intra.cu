@@ -16,6 +16,7 @@ struct OVGPUIntraBatch {
     uint32_t *h_order, *d_order;                    // [plane][max_cmds]
     IspInfoDev *h_isp, *d_isp;                      // ISP table (grown on demand)
     int nb_isp, max_isp, has_isp;
+    int map_w_u, map_cmds;              // row length of the position maps and how many of h_cmds are mapped into them
     uint32_t *pos_l, *pos_c;                        // host only: 1 + queue position of the command covering each 4x4 unit (luma / chroma plane)
     size_t map_units;
     // dataflow state of ovgpu_recon_picture (recon_kernels.h): pending word per unit and plane, queue heads, epoch
@@ -106,16 +107,25 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
     }
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->lv.nb[0] = b->lv.nb[1] = 0;
     b->serial++;
+    // the position maps stay all zero between pictures except for the blocks of the commands last mapped into them, which are
+    // cleared here block by block (b->h_cmds still holds those commands) instead of clearing 2 x 2 MB per 4K picture
     const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
-    if (units > b->map_units) {
+    if (units > b->map_units || (pic_w >> 2) != b->map_w_u) {
         free(b->pos_l); free(b->pos_c); free(b->lv.ws_map);
-        b->pos_l = (uint32_t *)malloc(units * sizeof(uint32_t)); b->pos_c = (uint32_t *)malloc(units * sizeof(uint32_t));
-        b->lv.ws_map = (uint16_t *)malloc(units * sizeof(uint16_t));
+        b->pos_l = (uint32_t *)calloc(units, sizeof(uint32_t)); b->pos_c = (uint32_t *)calloc(units, sizeof(uint32_t));
+        b->lv.ws_map = (uint16_t *)calloc(units, sizeof(uint16_t));
         b->map_units = (b->pos_l && b->pos_c && b->lv.ws_map) ? units : 0;
+        b->map_w_u = pic_w >> 2; b->map_cmds = 0;
         if (!b->map_units) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra position maps");
+    } else if (b->map_cmds) {
+        intra_clear_units(b->pos_l, b->map_w_u, (const OVGPUIntraCmd *)b->h_cmds, b->map_cmds, OVGPU_INTRA_LUMA);
+        intra_clear_units(b->pos_c, b->map_w_u, (const OVGPUIntraCmd *)b->h_cmds, b->map_cmds, OVGPU_INTRA_CHROMA);
+        b->map_cmds = 0;
     }
-    if (!nb_cmds) { memset(b->pos_l, 0, units * sizeof(uint32_t)); memset(b->pos_c, 0, units * sizeof(uint32_t)); return 0; }
+    b->lv.ws_clean = 1;
+    if (!nb_cmds) return 0;
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
+    b->map_cmds = nb_cmds;
     const int lrc = intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c);
     if (lrc == -2) { b->nb_cmds = 0; return ovgpu_set_error(ctx, OVGPU_EINVAL, "a block copy command reads samples that are not reconstructed before it"); }
     if (lrc)

@@ -49,7 +49,22 @@ struct IntraLevels {
     // optional caller-owned scratch (a per-picture malloc / free of megabytes costs page faults and serialises host threads
     // on the process's memory-map lock): level map of w/4 x h/4 uint16, 2 * n uint16, n + 3 uint32
     uint16_t *ws_map; uint16_t *ws_lvl; uint32_t *ws_fill;
+    // ws_clean: ws_map and the position maps handed to intra_build_levels are all zero on entry (and ws_map is left all zero):
+    // clearing megabytes of maps per picture costs more than everything else in here when only a tenth of the picture is intra
+    int ws_clean;
 };
+
+// zeroes the units of the commands' blocks in a position / level map (the inverse of what intra_build_levels writes)
+template <typename T>
+static inline void intra_clear_units(T *map, int w_u, const OVGPUIntraCmd *cmds, int n, int bit)
+{
+    for (int i = 0; i < n; i++) {
+        const OVGPUIntraCmd *c = &cmds[i];
+        if (!(c->flags & bit)) continue;
+        const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
+        for (int y = yu; y < yu + nh; y++) memset(map + (size_t)y * w_u + xu, 0, sizeof(T) * nw);
+    }
+}
 
 static inline int intra_neigh_level(const uint16_t *m, int w_u, int h_u, int xu, int yu, int nw, int nh)
 {
@@ -80,7 +95,8 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
             const int bit = p ? OVGPU_INTRA_CHROMA : OVGPU_INTRA_LUMA;
             uint16_t *m = map[p], *lv = lvl + (size_t)p * n;
             int nb_levels = 0;
-            memset(m, 0, (size_t)w_u * h_u * sizeof(uint16_t));
+            const int clean = !own && L->ws_clean;
+            if (!clean) memset(m, 0, (size_t)w_u * h_u * sizeof(uint16_t));
             for (int i = 0; i < n; i++) {
                 const OVGPUIntraCmd *c = &cmds[i];
                 lv[i] = 0;
@@ -100,6 +116,7 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
                 if (l > nb_levels) nb_levels = l;
                 for (int y = yu; y < yu + nh; y++) for (int x = xu; x < xu + nw; x++) m[y * w_u + x] = (uint16_t)l;
             }
+            if (clean) intra_clear_units(m, w_u, cmds, n, bit);
             if (ret) break;
             // counting sort by level (level 0 = the command does not have this plane)
             uint32_t *start = L->start[p];
@@ -113,7 +130,7 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
             for (int l = 0; l <= nb_levels; l++) start[l] = start[l + 1];       // 0-based
             L->nb[p] = nb_levels;
             if (pos[p]) {
-                memset(pos[p], 0, (size_t)w_u * h_u * sizeof(uint32_t));
+                if (!clean) memset(pos[p], 0, (size_t)w_u * h_u * sizeof(uint32_t));
                 for (uint32_t q = 0; q < start[nb_levels]; q++) {
                     const OVGPUIntraCmd *c = &cmds[L->order[p][q]];
                     const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;

@@ -229,8 +229,37 @@ static void emu_intra_launch(uint16_t *const planes[3], const int stride[3], int
 struct EmuLevels {
     std::vector<uint32_t> order[2], start[2];
     IntraLevels lv;
-    EmuLevels(int n) { lv.ws_map = NULL; lv.ws_lvl = NULL; lv.ws_fill = NULL; for (int p = 0; p < 2; p++) { order[p].resize(n + 1); start[p].resize(n + 3); lv.order[p] = order[p].data(); lv.start[p] = start[p].data(); } }
+    EmuLevels(int n) { lv.ws_clean = 0; lv.ws_map = NULL; lv.ws_lvl = NULL; lv.ws_fill = NULL; for (int p = 0; p < 2; p++) { order[p].resize(n + 1); start[p].resize(n + 3); lv.order[p] = order[p].data(); lv.start[p] = start[p].data(); } }
 };
+
+// The product keeps its level / position maps all zero between pictures and clears only the blocks it wrote (intra.cu,
+// IntraLevels::ws_clean).  Replays that protocol over two command lists on the same maps and compares the second result with
+// a build on fresh maps.  Returns 0 when identical and the maps are left as the protocol says.
+int emu_levels_reuse_check(const OVGPUIntraCmd *a, int na, const OVGPUIntraCmd *b, int nb, int w, int h)
+{
+    const int w_u = w >> 2, h_u = h >> 2, nmax = na > nb ? na : nb;
+    const size_t units = (size_t)w_u * h_u;
+    std::vector<uint32_t> pos_l(units, 0), pos_c(units, 0), ref_l(units, 0), ref_c(units, 0);
+    std::vector<uint16_t> map(units, 0), lvl(2 * nmax + 2);
+    std::vector<uint32_t> fill(nmax + 4);
+    EmuLevels P(nmax), F(nb);
+    P.lv.ws_map = map.data(); P.lv.ws_lvl = lvl.data(); P.lv.ws_fill = fill.data(); P.lv.ws_clean = 1;
+    if (intra_build_levels(&P.lv, nmax + 1, a, na, w, h, pos_l.data(), pos_c.data())) return -1;
+    for (size_t i = 0; i < units; i++) if (map[i]) return -2;
+    intra_clear_units(pos_l.data(), w_u, a, na, OVGPU_INTRA_LUMA);
+    intra_clear_units(pos_c.data(), w_u, a, na, OVGPU_INTRA_CHROMA);
+    for (size_t i = 0; i < units; i++) if (pos_l[i] || pos_c[i]) return -3;
+    if (intra_build_levels(&P.lv, nmax + 1, b, nb, w, h, pos_l.data(), pos_c.data())) return -4;
+    if (intra_build_levels(&F.lv, nb + 1, b, nb, w, h, ref_l.data(), ref_c.data())) return -5;
+    if (pos_l != ref_l || pos_c != ref_c) return -6;
+    for (int p = 0; p < 2; p++) {
+        if (P.lv.nb[p] != F.lv.nb[p]) return -7;
+        for (int l = 0; l <= F.lv.nb[p]; l++) if (P.lv.start[p][l] != F.lv.start[p][l]) return -8;
+        for (uint32_t q = 0; q < F.lv.start[p][F.lv.nb[p]]; q++) if (P.lv.order[p][q] != F.lv.order[p][q]) return -9;
+    }
+    for (size_t i = 0; i < units; i++) if (map[i]) return -10;
+    return 0;
+}
 
 int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
 {

@@ -239,3 +239,13 @@ def test_gpu_mixed_picture_with_isp(oracle, pr, gpu_ctx, w, h, log2, ict):
     for k in range(3):
         assert (got[k] == want[k]).all(), "plane %d: %d samples differ" % (k, (got[k] != want[k]).sum())
     ib.destroy(); tb.destroy(); pic.destroy()
+
+
+def test_position_maps_are_reused_without_full_clears(emu):
+    """the host keeps its level / position maps zero between pictures by clearing only the blocks it wrote: a second picture
+    on the same maps must give the lists a fresh build gives"""
+    a = synth_recon.recon_case(416, 240, 31, 7, p_cclm=0.3, p_ibc=0.1)[0]
+    b = synth_recon.recon_case(416, 240, 32, 7, p_cclm=0.3, p_inter=0.7, p_ibc=0.1)[0]
+    a = np.ascontiguousarray(a[a["flags"] != 0]); b = np.ascontiguousarray(b[b["flags"] != 0])
+    assert emu.emu_levels_reuse_check(a.ctypes.data_as(C.c_void_p), len(a), b.ctypes.data_as(C.c_void_p), len(b), 416, 240) == 0
+    assert emu.emu_levels_reuse_check(b.ctypes.data_as(C.c_void_p), len(b), a.ctypes.data_as(C.c_void_p), len(a), 416, 240) == 0
