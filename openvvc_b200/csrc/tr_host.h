@@ -35,27 +35,48 @@ static inline int tu_check_cmd(const OVGPUTuCmd *c, size_t nb_coeffs)
 
 // Splits the TUs into transform blocks: `small` (<= 256 samples, one warp each) and `large` (one CTA each).
 // Either output may be NULL to only count. Returns the totals through nb_small / nb_large.
+// Both lists are ordered by DECREASING block size (counting sort on log2 of the sample count; transform blocks write disjoint
+// samples, so any order gives the same picture): the warps of a CTA, which meet at the barriers between the phases, then
+// hold blocks of one size instead of waiting for the largest, and the last wave of a launch is made of the cheapest blocks.
+static inline int tu_kinds(const OVGPUTuCmd *c, int kinds[3])
+{
+    int nk = 0;
+    if (c->cbf_mask & 0x10) kinds[nk++] = 0;
+    if (c->cbf_mask & 0x08) kinds[nk++] = 3;
+    else {
+        if (c->cbf_mask & 0x02) kinds[nk++] = 1;
+        if (c->cbf_mask & 0x01) kinds[nk++] = 2;
+    }
+    return nk;
+}
+// cursors of a size-bucketed list: keys (log2 samples) hi .. lo in decreasing order, starting at `base`; returns the end
+static inline int tu_bucket_starts(const int cnt[16], int cur[16], int hi, int lo, int base)
+{
+    for (int k = hi; k >= lo; k--) { cur[k] = base; base += cnt[k]; }
+    return base;
+}
 static inline void tu_build_items(TbItemDev *small, TbItemDev *large, int *nb_small, int *nb_large,
                                   const OVGPUTuCmd *cmds, int n)
 {
-    int ns = 0, nl = 0;
+    int cnt[16] = { 0 }, cur[16], kinds[3];
     for (int i = 0; i < n; i++) {
-        const OVGPUTuCmd *c = &cmds[i];
-        int kinds[3], nk = 0;
-        if (c->cbf_mask & 0x10) kinds[nk++] = 0;
-        if (c->cbf_mask & 0x08) kinds[nk++] = 3;
-        else {
-            if (c->cbf_mask & 0x02) kinds[nk++] = 1;
-            if (c->cbf_mask & 0x01) kinds[nk++] = 2;
-        }
+        const int nk = tu_kinds(&cmds[i], kinds);
+        for (int k = 0; k < nk; k++) cnt[(cmds[i].log2_w + cmds[i].log2_h - (kinds[k] ? 2 : 0)) & 15]++;
+    }
+    const int ns = tu_bucket_starts(cnt, cur, 8, 0, 0);
+    const int nl = tu_bucket_starts(cnt, cur, 15, 9, 0);
+    *nb_small = ns; *nb_large = nl;
+    if (!small && !large) return;
+    for (int i = 0; i < n; i++) {
+        const int nk = tu_kinds(&cmds[i], kinds);
         for (int k = 0; k < nk; k++) {
-            int s = c->log2_w + c->log2_h - (kinds[k] ? 2 : 0);
+            const int s = (cmds[i].log2_w + cmds[i].log2_h - (kinds[k] ? 2 : 0)) & 15;
             TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };
-            if (s <= 8) { if (small) small[ns] = it; ns++; }
-            else        { if (large) large[nl] = it; nl++; }
+            if (s <= 8) { if (small) small[cur[s]] = it; }
+            else        { if (large) large[cur[s]] = it; }
+            cur[s]++;
         }
     }
-    *nb_small = ns; *nb_large = nl;
 }
 
 // ---- reconstruction order ----------------------------------------------------------------------------------------
@@ -78,25 +99,21 @@ static inline int tu_build_recon_lists(TbItemDev *items, TuReconLists *g, ReconI
 {
     memset(g, 0, sizeof(*g));
     for (int p = 0; p < 2; p++) for (int q = 0; q < nb_ritems[p]; q++) { ritems[p][q].tb_start = 0; ritems[p][q].nb_tb = 0; ritems[p][q].large = 0; }
+    int cnt[2][16], cur[2][16];                         // blocks outside intra commands, per plane and log2 size (see tu_build_items)
+    memset(cnt, 0, sizeof(cnt));
     for (int pass = 0; pass < 2; pass++) {
         for (int i = 0; i < n; i++) {
             const OVGPUTuCmd *c = &cmds[i];
-            int kinds[3], nk = 0;
-            if (c->cbf_mask & 0x10) kinds[nk++] = 0;
-            if (c->cbf_mask & 0x08) kinds[nk++] = 3;
-            else {
-                if (c->cbf_mask & 0x02) kinds[nk++] = 1;
-                if (c->cbf_mask & 0x01) kinds[nk++] = 2;
-            }
+            int kinds[3];
+            const int nk = tu_kinds(c, kinds);
             for (int k = 0; k < nk; k++) {
-                const int p = kinds[k] != 0, large = c->log2_w + c->log2_h - (p ? 2 : 0) > 8;
+                const int p = kinds[k] != 0, s = (c->log2_w + c->log2_h - (p ? 2 : 0)) & 15, large = s > 8;
                 const uint32_t *m = p ? pos_c : pos_l;
                 const uint32_t pos = m ? m[(size_t)(c->y0 >> 2) * w_u + (c->x0 >> 2)] : 0;
                 TbItemDev it = { (uint32_t)i, (uint32_t)kinds[k] };
                 if (!pos) {
-                    if (pass == 0) { if (large) g->n_large[p]++; else g->n_small[p]++; }
-                    else if (large) items[g->start_large[p] + g->n_large[p]++] = it;
-                    else            items[g->start_small[p] + g->n_small[p]++] = it;
+                    if (pass == 0) cnt[p][s]++;
+                    else items[cur[p][s]++] = it;
                 } else {
                     ReconItemDev *r = &ritems[p][pos - 1];
                     if (pass == 0) { r->nb_tb++; r->large = (uint16_t)large; }
@@ -107,8 +124,8 @@ static inline int tu_build_recon_lists(TbItemDev *items, TuReconLists *g, ReconI
         if (pass == 0) {
             int acc = 0;
             for (int p = 0; p < 2; p++) {
-                g->start_small[p] = acc; acc += g->n_small[p]; g->n_small[p] = 0;
-                g->start_large[p] = acc; acc += g->n_large[p]; g->n_large[p] = 0;
+                g->start_small[p] = acc; acc = tu_bucket_starts(cnt[p], cur[p], 8, 0, acc);  g->n_small[p] = acc - g->start_small[p];
+                g->start_large[p] = acc; acc = tu_bucket_starts(cnt[p], cur[p], 15, 9, acc); g->n_large[p] = acc - g->start_large[p];
             }
             for (int p = 0; p < 2; p++)
                 for (int q = 0; q < nb_ritems[p]; q++) { ritems[p][q].tb_start = (uint32_t)acc; acc += ritems[p][q].nb_tb; ritems[p][q].nb_tb = 0; }
