@@ -322,7 +322,7 @@ struct AlfLumaK {
 // Chroma 5x5 + CC-ALF (one CTA = one 64x32 chroma tile of one component)
 // =========================================================================================================
 struct AlfChromaK {
-    static const int THREADS = 256, MIN_BLOCKS = 2, PHASES = 2;
+    static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 2;
     static const int TW = 64, TH = 32;
     static const int PIX_STRIDE = TW + 8, PIX_ROWS = TH + 4;
     static const int SMEM_BYTES = PIX_ROWS * PIX_STRIDE * 2;
@@ -405,6 +405,12 @@ struct AlfChromaK {
         const int16_t *cc = a.tab.cc[comp][t.cc_idx ? t.cc_idx - 1 : 0];
         const int half = 1 << (a.bitdepth - 1);
         uint16_t *dst = a.dst[comp];
+        int wide = 0;                                   // a coefficient outside int8 (IDP.2A's multiplier width): scalar path
+#pragma unroll
+        for (int k = 0; k < 6; k++) wide |= cf[k] < -128 || cf[k] > 127;
+        int cc_wide = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) cc_wide |= cc[k] < -128 || cc[k] > 127;
 #pragma unroll
         for (int rr = 0; rr < 2; rr++) {
             const int ly = 2 * ty + rr;                      // row inside tile
@@ -429,11 +435,77 @@ struct AlfChromaK {
             const uint16_t *l2 = a.luma + (size_t)ovd_clamp(ly2 + o2, 0, a.pic_h - 1) * a.luma_pitch;
             const uint16_t *l3 = a.luma + (size_t)ovd_clamp(ly2 + o3, 0, a.pic_h - 1) * a.luma_pitch;
             uint32_t outv[4];
+            int alfv[4] = { c0[0], c0[1], c0[2], c0[3] };
+            if (t.do_alf && !wide) {
+                // 5x5 diamond on packed sample pairs (VIADDMNMX.S16x2 clip, IDP.2A accumulate), as the luma kernel does: the
+                // thread's four samples are words 1 and 2 of the four-word windows below (samples -2 .. 5)
+                const uint32_t *Cw = (const uint32_t *)(c0 - 2), *U1w = (const uint32_t *)(u1 - 2), *E1w = (const uint32_t *)(e1 - 2);
+                const uint32_t *U2w = (const uint32_t *)u2, *E2w = (const uint32_t *)e2;
+                const uint32_t cw0 = Cw[0], cw1 = Cw[1], cw2 = Cw[2], cw3 = Cw[3];
+                const uint32_t uw0 = U1w[0], uw1 = U1w[1], uw2 = U1w[2], uw3 = U1w[3];
+                const uint32_t ew0 = E1w[0], ew1 = E1w[1], ew2 = E1w[2], ew3 = E1w[3];
+                const uint32_t cwv[4] = { cw0, cw1, cw2, cw3 }, uwv[4] = { uw0, uw1, uw2, uw3 }, ewv[4] = { ew0, ew1, ew2, ew3 };
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const uint32_t pp = cwv[1 + p], neg_p = ovd_vsub_16x2(0u, pp);
+                    int acc0 = 0, acc1 = 0;
+#define CP2(k, A, B)                                                                                                          \
+                    do {                                                                                                      \
+                        const uint32_t cl2 = (uint32_t)(uint16_t)cl[k] * 0x10001u, ncl2 = ovd_vsub_16x2(0u, cl2);                 \
+                        const uint32_t s2 = ovd_vadd_16x2(ovd_vmax_s16x2(ovd_viaddmin_s16x2(A, neg_p, cl2), ncl2),                \
+                                                          ovd_vmax_s16x2(ovd_viaddmin_s16x2(B, neg_p, cl2), ncl2));               \
+                        const uint32_t cf2 = (uint32_t)(uint8_t)cf[k] * 0x01000001u;                                              \
+                        acc0 = ovd_dp2a_lo(s2, cf2, acc0); acc1 = ovd_dp2a_hi(s2, cf2, acc1);                                     \
+                    } while (0)
+                    CP2(0, E2w[p], U2w[p]);
+                    CP2(1, alf_odd_pair(ewv[1 + p], ewv[2 + p]), alf_odd_pair(uwv[p], uwv[1 + p]));
+                    CP2(2, ewv[1 + p], uwv[1 + p]);
+                    CP2(3, alf_odd_pair(ewv[p], ewv[1 + p]), alf_odd_pair(uwv[1 + p], uwv[2 + p]));
+                    CP2(4, cwv[2 + p], cwv[p]);
+                    CP2(5, alf_odd_pair(cwv[1 + p], cwv[2 + p]), alf_odd_pair(cwv[p], cwv[1 + p]));
+#undef CP2
+                    acc0 = coarse ? (acc0 + 512) >> 10 : (acc0 + 64) >> 7;
+                    acc1 = coarse ? (acc1 + 512) >> 10 : (acc1 + 64) >> 7;
+                    alfv[2 * p] = ovd_clamp(acc0 + (int)(pp & 0xffff), 0, maxv);
+                    alfv[2 * p + 1] = ovd_clamp(acc1 + (int)(pp >> 16), 0, maxv);
+                }
+            }
+            int ccv[4] = { 0, 0, 0, 0 };
+            if (t.cc_idx && !cc_wide) {
+                // CC-ALF (rcn_alf.c:826-870) for the four chroma samples at once: their eight luma columns come in as four 8-byte
+                // loads per row (+ the column to the left), the seven differences to the collocated luma sample are formed on
+                // packed pairs (even / odd luma columns picked with PRMT) and accumulated with IDP.2A
+                const int lx0 = (t.x0 + 4 * tx) << 1, lxm = ovd_max(lx0 - 1, 0);
+                const ovd_u2 r0a = ovd_ld8(l0 + lx0), r0b = ovd_ld8(l0 + lx0 + 4), r1a = ovd_ld8(l1 + lx0), r1b = ovd_ld8(l1 + lx0 + 4);
+                const ovd_u2 r2a = ovd_ld8(l2 + lx0), r2b = ovd_ld8(l2 + lx0 + 4), r3a = ovd_ld8(l3 + lx0), r3b = ovd_ld8(l3 + lx0 + 4);
+                const uint32_t w0[5] = { (uint32_t)l0[lxm] << 16, r0a.x, r0a.y, r0b.x, r0b.y };
+                const uint32_t w1[5] = { (uint32_t)l1[lxm] << 16, r1a.x, r1a.y, r1b.x, r1b.y };
+                const uint32_t w2[4] = { r2a.x, r2a.y, r2b.x, r2b.y }, w3[4] = { r3a.x, r3a.y, r3b.x, r3b.y };
+                uint32_t ccw[7];
+#pragma unroll
+                for (int k = 0; k < 7; k++) ccw[k] = (uint32_t)(uint8_t)cc[k] * 0x01000001u;
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const uint32_t ctr = ovd_byte_perm(w0[1 + 2 * p], w0[2 + 2 * p], 0x5410);       // l0[lx], l0[lx + 2]
+                    int acc0 = 0, acc1 = 0;
+#define CC2(k, X) do { const uint32_t d2 = ovd_vsub_16x2(X, ctr); acc0 = ovd_dp2a_lo(d2, ccw[k], acc0); acc1 = ovd_dp2a_hi(d2, ccw[k], acc1); } while (0)
+                    CC2(0, ovd_byte_perm(w2[2 * p], w2[1 + 2 * p], 0x5410));
+                    CC2(1, ovd_byte_perm(w0[2 * p], w0[1 + 2 * p], 0x7632));
+                    CC2(2, ovd_byte_perm(w0[1 + 2 * p], w0[2 + 2 * p], 0x7632));
+                    CC2(3, ovd_byte_perm(w1[2 * p], w1[1 + 2 * p], 0x7632));
+                    CC2(4, ovd_byte_perm(w1[1 + 2 * p], w1[2 + 2 * p], 0x5410));
+                    CC2(5, ovd_byte_perm(w1[1 + 2 * p], w1[2 + 2 * p], 0x7632));
+                    CC2(6, ovd_byte_perm(w3[2 * p], w3[1 + 2 * p], 0x5410));
+#undef CC2
+                    ccv[2 * p] = acc0; ccv[2 * p + 1] = acc1;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int cur = c0[i];
-                int v = cur;
-                if (t.do_alf) {
+                int v = alfv[i];
+                if (t.do_alf && wide) {
+
                     int sum = 0;
 #define CP(k, A, B) sum += cf[k] * (ovd_clamp((int)(A) - cur, -cl[k], cl[k]) + ovd_clamp((int)(B) - cur, -cl[k], cl[k]))
                     CP(0, e2[i], u2[i]);
@@ -447,12 +519,15 @@ struct AlfChromaK {
                     v = ovd_clamp(sum + cur, 0, maxv);
                 }
                 if (t.cc_idx) {
-                    const int lx = (t.x0 + 4 * tx + i) << 1;
-                    const int lxm = ovd_max(lx - 1, 0), lxp = ovd_min(lx + 1, a.pic_w - 1);
-                    const int lc = l0[lx];
-                    int sum = cc[0] * (l2[lx] - lc) + cc[1] * (l0[lxm] - lc) + cc[2] * (l0[lxp] - lc)
+                    int sum = ccv[i];
+                    if (cc_wide) {
+                        const int lx = (t.x0 + 4 * tx + i) << 1;
+                        const int lxm = ovd_max(lx - 1, 0), lxp = ovd_min(lx + 1, a.pic_w - 1);
+                        const int lc = l0[lx];
+                        sum = cc[0] * (l2[lx] - lc) + cc[1] * (l0[lxm] - lc) + cc[2] * (l0[lxp] - lc)
                             + cc[3] * (l1[lxm] - lc) + cc[4] * (l1[lx] - lc) + cc[5] * (l1[lxp] - lc)
                             + cc[6] * (l3[lx] - lc);
+                    }
                     sum = (sum + 64) >> 7;
                     sum = ovd_clamp(sum + half, 0, maxv);
                     v = ovd_clamp(sum + v - half, 0, maxv);
