@@ -20,6 +20,9 @@ def alf_case(po, w, h, seed, log2_ctu=7, kind="natural", wide=False):
     ap = synth.alf_params(w, h, seed + 1, log2_ctu)
     if wide:
         ap["luma_aps"][0]["luma_coeff"][:, 3] = 300     # outside int8: exercises the WIDE kernel variant
+        ap["chroma_aps"]["chroma_coeff"][0, 2] = 200    # ... and the scalar fall-backs of the chroma kernel (5x5 core, CC-ALF)
+        ap["cc_coeff"][0, 1, 3] = 130
+        ap["cc_coeff"][1, 0, 5] = -140
     tab = po.alf_build_tables(ap["luma_aps"], ap["chroma_aps"], impl="port")
     tab.np("cc_coeff")[:] = ap["cc_coeff"]
     return planes, tab, ap["ctu"], ap
