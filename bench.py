@@ -488,6 +488,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    if os.environ.get("OVGPU_HOST_TIMING"):
+        api.lib().ovgpu_host_timing_dump()
     if host_prof:
         a = np.array(host_prof)
         for k, name in enumerate(("mc_commit", "tu_commit", "intra_upload", "dbf_commit", "sao+alf", "recon_call", "inloop_calls")):

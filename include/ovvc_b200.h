@@ -37,6 +37,9 @@ int  ovgpu_ctx_sync(OVGPUCtx *ctx);
 const char *ovgpu_last_error(const OVGPUCtx *ctx);
 /* number of kernels this context launched since creation (bench.py's "gpu_launches") */
 uint64_t ovgpu_launch_count(const OVGPUCtx *ctx);
+/* debugging aid: with OVGPU_HOST_TIMING=1 in the environment the library accumulates the host time of its commit / launch
+ * sections (all contexts); this prints the table to stderr */
+void ovgpu_host_timing_dump(void);
 /* per-stage device timing with CUDA events on the context's stream */
 enum OVGPUStage { OVGPU_STAGE_ALF_LUMA = 0, OVGPU_STAGE_ALF_CHROMA, OVGPU_STAGE_SAO, OVGPU_STAGE_DBF_V,
                   OVGPU_STAGE_DBF_H, OVGPU_STAGE_MC, OVGPU_STAGE_RESIDUAL, OVGPU_STAGE_INTRA,

@@ -65,6 +65,20 @@ int ovgpu_set_error(OVGPUCtx *ctx, int code, const char *fmt, ...);
                                    #call, cudaGetErrorString(e__));                          \
     } while (0)
 
+// Host-side section timer (debugging aid): accumulates wall time per labelled section of the commit / launch code, all
+// contexts and threads together; ovgpu_host_timing_dump() prints the table.  Off (two loads per section) unless the
+// environment has OVGPU_HOST_TIMING=1.
+enum { HT_MC_LOOP, HT_MC_COPIES, HT_TU_CHECK, HT_TU_ITEMS, HT_TU_COPIES, HT_TU_ANCHORS, HT_INTRA_CHECK, HT_INTRA_LEVELS, HT_INTRA_COPIES,
+       HT_BIND_LISTS, HT_BIND_COPIES, HT_RECON_MC, HT_RECON_LAUNCHES, HT_FENCE_WAIT, HT_NB };
+extern unsigned long long ovgpu_ht_ns[HT_NB], ovgpu_ht_n[HT_NB];
+extern int ovgpu_ht_on;
+unsigned long long ovgpu_ht_now();
+struct HostSection {
+    int id; unsigned long long t0;
+    explicit HostSection(int i) : id(i), t0(ovgpu_ht_on ? ovgpu_ht_now() : 0) {}
+    ~HostSection() { if (ovgpu_ht_on) { __atomic_fetch_add(&ovgpu_ht_ns[id], ovgpu_ht_now() - t0, __ATOMIC_RELAXED); __atomic_fetch_add(&ovgpu_ht_n[id], 1ull, __ATOMIC_RELAXED); } }
+};
+
 // Stage bracket: counts the launch and, when profiling, records events around it.
 struct StageScope {
     OVGPUCtx *ctx;
@@ -97,7 +111,7 @@ struct StagingFence {
 static inline cudaError_t fence_wait(StagingFence *f)
 {
     cudaError_t e = cudaSuccess;
-    if (f->pending) { e = cudaEventSynchronize(f->ev); f->pending = 0; }
+    if (f->pending) { HostSection hs(HT_FENCE_WAIT); e = cudaEventSynchronize(f->ev); f->pending = 0; }
     return e;
 }
 static inline cudaError_t fence_mark(StagingFence *f, cudaStream_t s)

@@ -43,6 +43,16 @@ StageScope::~StageScope()
     if (slot >= 0) cudaEventRecord(ctx->pending[slot].b, ctx->stream);
 }
 
+#include <time.h>
+unsigned long long ovgpu_ht_ns[HT_NB], ovgpu_ht_n[HT_NB];
+int ovgpu_ht_on = getenv("OVGPU_HOST_TIMING") != NULL;
+unsigned long long ovgpu_ht_now()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (unsigned long long)ts.tv_sec * 1000000000ull + (unsigned long long)ts.tv_nsec;
+}
+
 extern "C" {
 
 int ovgpu_ctx_create(OVGPUCtx **out, int device, void *cuda_stream)
@@ -90,6 +100,15 @@ int ovgpu_ctx_sync(OVGPUCtx *ctx)
 }
 
 const char *ovgpu_last_error(const OVGPUCtx *ctx) { return ctx ? ctx->err : "no context"; }
+void ovgpu_host_timing_dump(void)
+{
+    static const char *const names[HT_NB] = { "mc commit: validate + route + items", "mc commit: copy calls", "tu commit: validation", "tu commit: item lists",
+        "tu commit: copy calls", "tu anchors", "intra upload: validation", "intra upload: levels + maps", "intra upload: copy calls",
+        "recon bind: lists", "recon bind: copy calls", "recon: motion compensation launches", "recon: other launches", "staging fence waits (inside the above)" };
+    for (int i = 0; i < HT_NB; i++)
+        if (ovgpu_ht_n[i]) fprintf(stderr, "host timing %-42s %8llu calls  %8.1f us/call\n", names[i], ovgpu_ht_n[i], 1e-3 * ovgpu_ht_ns[i] / ovgpu_ht_n[i]);
+}
+
 uint64_t ovgpu_launch_count(const OVGPUCtx *ctx) { return ctx ? ctx->launches : 0; }
 
 int ovgpu_profile_enable(OVGPUCtx *ctx, int on)

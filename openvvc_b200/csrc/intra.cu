@@ -85,10 +85,13 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
     if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || (nb_cmds && !cmds) || log2_ctu_s < 5 || log2_ctu_s > 7 ||
         pic_w <= 0 || pic_h <= 0 || (pic_w & 7) || (pic_h & 7))
         return OVGPU_EINVAL;
-    for (int i = 0; i < nb_cmds; i++)
-        if (intra_check_cmd(&cmds[i], pic_w, pic_h) ||
-            ((cmds[i].flags & OVGPU_INTRA_ISP) && (cmds[i].pad[0] | (cmds[i].pad[1] << 8)) >= nb_isp))
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
+    {
+        HostSection hs(HT_INTRA_CHECK);
+        for (int i = 0; i < nb_cmds; i++)
+            if (intra_check_cmd(&cmds[i], pic_w, pic_h) ||
+                ((cmds[i].flags & OVGPU_INTRA_ISP) && (cmds[i].pad[0] | (cmds[i].pad[1] << 8)) >= nb_isp))
+                return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra command %d malformed", i);
+    }
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     b->has_isp = 0;
     for (int i = 0; i < nb_cmds; i++) b->has_isp |= (cmds[i].flags & (OVGPU_INTRA_ISP | OVGPU_INTRA_IBC)) != 0;
@@ -126,10 +129,12 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
     if (!nb_cmds) return 0;
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
     b->map_cmds = nb_cmds;
-    const int lrc = intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c);
+    int lrc;
+    { HostSection hs(HT_INTRA_LEVELS); lrc = intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c); }
     if (lrc == -2) { b->nb_cmds = 0; return ovgpu_set_error(ctx, OVGPU_EINVAL, "a block copy command reads samples that are not reconstructed before it"); }
     if (lrc)
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
+    HostSection hs_copies(HT_INTRA_COPIES);
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(IntraCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_order, b->h_order, sizeof(uint32_t) * 2 * b->max_cmds, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
@@ -207,7 +212,7 @@ int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *ref
 {
     if (!ctx || !pic || (mc && !refs)) return OVGPU_EINVAL;
     int rc;
-    if (mc && (rc = ovgpu_mc_picture(ctx, pic, refs, mc, lmcs)) != 0) return rc;
+    if (mc) { HostSection hs(HT_RECON_MC); if ((rc = ovgpu_mc_picture(ctx, pic, refs, mc, lmcs)) != 0) return rc; }
     const int has_intra = intra && intra->nb_cmds;
     if (!tu && !has_intra) return 0;
     if (has_intra && (pic->width != intra->pic_w || pic->height != intra->pic_h))
@@ -223,9 +228,10 @@ int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *ref
     const int w_u = pic->width >> 2, h_u = pic->height >> 2;
     const uint32_t *order[2] = { has_intra ? intra->lv.order[0] : NULL, has_intra ? intra->lv.order[1] : NULL };
     const int nb[2] = { has_intra ? (int)intra->lv.start[0][intra->lv.nb[0]] : 0, has_intra ? (int)intra->lv.start[1][intra->lv.nb[1]] : 0 };
-    rc = ovgpu_tu_check_picture(ctx, pic, tu);
+    { HostSection hs(HT_TU_CHECK); rc = ovgpu_tu_check_picture(ctx, pic, tu); }
     if (!rc) rc = ovgpu_tu_bind_recon(ctx, tu, has_intra ? intra->serial : 0, has_intra ? intra->pos_l : NULL, has_intra ? intra->pos_c : NULL,
                                       w_u, h_u, order, nb);
+    HostSection hs_launches(HT_RECON_LAUNCHES);
     if (!rc && has_intra) {
         // device state: pending words (never cleared: an epoch number marks the units of this run) and the queue heads
         const size_t units = (size_t)w_u * h_u;

@@ -158,6 +158,8 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items, *id = b->h_items + 3 * b->max_items, *is = b->h_items + 4 * b->max_items;
     int np = 0, nb = 0, nq = 0, nd = 0, ns = 0, max_x = 0, max_y = 0;
     uint32_t used[2] = { 0, 0 };
+    {
+    HostSection hs_loop(HT_MC_LOOP);
     for (int i = 0; i < nb_cmds; i++) {
         const OVGPUMcCmd *c = &cmds[i];
         if (mc_check_cmd(c, nb_prof)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC command %d malformed", i);
@@ -187,6 +189,8 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     }
     b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq; b->nb_dmvr = nd; b->nb_small_c = ns;
     b->max_x = max_x; b->max_y = max_y; b->used_refs[0] = used[0]; b->used_refs[1] = used[1];
+    }
+    HostSection hs_copies(HT_MC_COPIES);
     if (nb_cmds) {
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
         if (np) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, ip, sizeof(McItemDev) * np, cudaMemcpyHostToDevice, ctx->stream));

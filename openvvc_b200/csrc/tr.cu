@@ -8,12 +8,14 @@ static_assert(sizeof(TuCmdDev) == sizeof(OVGPUTuCmd) && sizeof(TuCmdDev) == 72, 
 
 struct OVGPUTuBatch {
     int max_cmds, nb_cmds, nb_small, nb_large, device;
+    int items_built;                    // the plain (non-reconstruction-order) item lists exist for this commit: built on first use
+    uint64_t checked_serial; int checked_w, checked_h;      // last (commit, picture size) ovgpu_tu_check_picture passed
     size_t max_coeffs, nb_coeffs;
     OVGPUTuSlice slice;
     TuCmdDev *h_cmds, *d_cmds;
-    TbItemDev *h_items, *d_items;       // small items first, then large ones
+    TbItemDev *d_items;                 // small items first, then large ones (staged through h_bitems)
     int16_t *h_coeffs, *d_coeffs;
-    StagingFence fence;                 // h_cmds, h_items, h_coeffs (staging / commit)
+    StagingFence fence;                 // h_cmds, h_coeffs (staging / commit)
     // reconstruction order (ovgpu_recon_picture): items re-ordered by dependency group, see tr_host.h.  Built into staging
     // buffers of their own (h_bitems, h_ritems) behind their own fence, so that binding never waits for the coefficient
     // copy the commit has just queued.
@@ -53,7 +55,6 @@ int ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPUT
     if (!b) return OVGPU_ENOMEM;
     b->max_cmds = max_cmds; b->max_coeffs = max_coeffs; b->device = ctx->device;
     if (cudaMallocHost(&b->h_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMallocHost(&b->h_items, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
         cudaMallocHost(&b->h_bitems, sizeof(TbItemDev) * 3 * max_cmds) != cudaSuccess ||
         cudaMallocHost(&b->h_coeffs, sizeof(int16_t) * max_coeffs) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(TuCmdDev) * max_cmds) != cudaSuccess ||
@@ -71,7 +72,6 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
     if (!b) return;
     cudaSetDevice(b->device);
     if (b->h_cmds) cudaFreeHost(b->h_cmds);
-    if (b->h_items) cudaFreeHost(b->h_items);
     if (b->h_bitems) cudaFreeHost(b->h_bitems);
     if (b->h_coeffs) cudaFreeHost(b->h_coeffs);
     if (b->d_cmds) cudaFree(b->d_cmds);
@@ -99,9 +99,12 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
 {
     if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs) return OVGPU_EINVAL;
     const OVGPUTuCmd *cmds = (const OVGPUTuCmd *)b->h_cmds;
-    for (int i = 0; i < nb_cmds; i++)
-        if (tu_check_cmd(&cmds[i], nb_coeffs))
-            return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d malformed", i);
+    {
+        HostSection hs(HT_TU_CHECK);
+        for (int i = 0; i < nb_cmds; i++)
+            if (tu_check_cmd(&cmds[i], nb_coeffs))
+                return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d malformed", i);
+    }
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     b->slice = *slice;
     b->nb_cmds = nb_cmds; b->nb_coeffs = nb_coeffs;
@@ -111,12 +114,12 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
         if ((cmds[i].flags & OVGPU_TU_SCALE_ANCHOR) && cmds[i].scale_anchor >= b->nb_anchors)
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d names LMCS anchor %d of %d (set the anchors before the commands)",
                                    i, cmds[i].scale_anchor, b->nb_anchors);
-    if (!nb_cmds) { b->nb_small = b->nb_large = 0; return 0; }
-    tu_build_items(NULL, NULL, &b->nb_small, &b->nb_large, cmds, nb_cmds);
-    tu_build_items(b->h_items, b->h_items + b->nb_small, &b->nb_small, &b->nb_large, cmds, nb_cmds);
+    // the item lists of ovgpu_residual_picture are built when it first runs on this commit: ovgpu_recon_picture orders the
+    // blocks its own way (ovgpu_tu_bind_recon) and never needs them
+    b->nb_small = b->nb_large = 0; b->items_built = 0;
+    if (!nb_cmds) { b->items_built = 1; return 0; }
+    HostSection hs_copies(HT_TU_COPIES);
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(TuCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ctx->stream));
-    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_items, sizeof(TbItemDev) * (b->nb_small + b->nb_large),
-                                          cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_coeffs, b->h_coeffs, sizeof(int16_t) * nb_coeffs, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
     return 0;
@@ -138,6 +141,7 @@ int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds
 int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAnchor *anchors, int nb)
 {
     if (!ctx || !b || nb < 0 || nb > 65536 || (nb && !anchors)) return OVGPU_EINVAL;
+    HostSection hs(HT_TU_ANCHORS);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence_anchors));
     if (nb > b->max_anchors) {
         if (b->h_anchors) cudaFreeHost(b->h_anchors);
@@ -172,6 +176,16 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
     }
     if (b->lists.built)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "the batch is bound to ovgpu_recon_picture; commit it again to use ovgpu_residual_picture");
+    if (!b->items_built) {          // first plain run on this commit (the lists are a cache inside the batch)
+        OVGPUTuBatch *m = const_cast<OVGPUTuBatch *>(b);
+        HostSection hs(HT_TU_ITEMS);
+        OVGPU_CUDA_CHECK(ctx, fence_wait(&m->fence_bind));
+        tu_build_items(NULL, NULL, &m->nb_small, &m->nb_large, (const OVGPUTuCmd *)m->h_cmds, m->nb_cmds);
+        tu_build_items(m->h_bitems, m->h_bitems + m->nb_small, &m->nb_small, &m->nb_large, (const OVGPUTuCmd *)m->h_cmds, m->nb_cmds);
+        OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(m->d_items, m->h_bitems, sizeof(TbItemDev) * (m->nb_small + m->nb_large), cudaMemcpyHostToDevice, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, fence_mark(&m->fence_bind, ctx->stream));
+        m->items_built = 1;
+    }
     const int nk = (b->nb_small > 0) + (b->nb_large > 0);
     if (!nk) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, nk);
@@ -208,7 +222,9 @@ int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, c
         b->nb_ritems[p] = nb[p];
         for (int q = 0; q < nb[p]; q++) ritems[p][q].cmd = order[p][q];
     }
-    const int n = tu_build_recon_lists(b->h_bitems, &b->lists, ritems, nb, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, pos_l, pos_c, w_u);
+    int n;
+    { HostSection hs(HT_BIND_LISTS); n = tu_build_recon_lists(b->h_bitems, &b->lists, ritems, nb, (const OVGPUTuCmd *)b->h_cmds, b->nb_cmds, pos_l, pos_c, w_u); }
+    HostSection hs_copies(HT_BIND_COPIES);
     if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_bitems, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (need) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_ritems, b->h_ritems, sizeof(ReconItemDev) * 2 * b->max_ritems, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence_bind, ctx->stream));
@@ -260,10 +276,13 @@ int ovgpu_tu_nb_anchors(const OVGPUTuBatch *b) { return b->nb_anchors; }
 int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b)
 {
     if (pic->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "residual path is built for 10-bit pictures");
+    if (b->checked_serial == b->serial && b->checked_w == pic->width && b->checked_h == pic->height) return 0;      // same commit, same size
     for (int i = 0; i < b->nb_cmds; i++) {
         const TuCmdDev *c = &b->h_cmds[i];
         if (c->x0 + (1 << c->log2_w) > pic->width || c->y0 + (1 << c->log2_h) > pic->height)
             return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
     }
+    OVGPUTuBatch *m = const_cast<OVGPUTuBatch *>(b);
+    m->checked_serial = b->serial; m->checked_w = pic->width; m->checked_h = pic->height;
     return 0;
 }
