@@ -395,7 +395,9 @@ def main():
     # Two picture sets in flight (even / odd steps), each with its own contexts, streams, device objects and pinned output: the
     # H2D copies of step k+1 and the D2H copies of step k-1 then run under the kernels of step k instead of queueing behind
     # them in stream order -- 2 x n_ctx pictures in flight, like a decoder with that many frame threads.
-    n_ctx = max(1, min(args.e2e_streams, P, os.cpu_count() or 1))
+    # host threads per rank: never more than this rank's share of the box's cores (an 8-GPU box with 32 cores runs 8 ranks: the
+    # staging fences spin while they wait, so oversubscribed threads would take cores from the threads that have work)
+    n_ctx = max(1, min(args.e2e_streams, P, max(1, (os.cpu_count() or 1) // world)))
     n_sets = max(1, min(2, args.e2e_sets))
     share = max(1, args.e2e_share)                 # contexts (host threads) per stream
     real_streams = [torch.cuda.Stream() for _ in range((n_sets * n_ctx + share - 1) // share)]
