@@ -261,6 +261,14 @@ int emu_levels_reuse_check(const OVGPUIntraCmd *a, int na, const OVGPUIntraCmd *
     return 0;
 }
 
+// the product's plain transform-block lists (tr_host.h): items[0 .. ns) small, items[ns .. ns + nl) large
+int emu_tu_items(const OVGPUTuCmd *cmds, int n, TbItemDev *items, int *ns, int *nl)
+{
+    tu_build_items(NULL, NULL, ns, nl, cmds, n);
+    tu_build_items(items, items + *ns, ns, nl, cmds, n);
+    return *ns + *nl;
+}
+
 int emu_intra_picture(uint16_t *const planes[3], const int stride[3], int w, int h, int log2_ctu, int bitdepth, const OVGPUIntraCmd *cmds, int n)
 {
     for (int i = 0; i < n; i++) if (intra_check_cmd(&cmds[i], w, h)) return -(i + 1);

@@ -88,6 +88,26 @@ def test_bdpcm_port_vs_reference_and_emulation(oracle, pt, emu, w, h, log2, ict,
     helpers.assert_planes_equal(helpers_tr.emu_residual(emu, planes, cmds, arena, dq, tsd, ict), want, "emulated BDPCM vs oracle")
 
 
+def test_item_lists_cover_every_block_once_in_decreasing_size(emu):
+    """host work lists (tr_host.h): every coded transform block exactly once, <= 256 samples in the warp list, larger ones in
+    the CTA list, both ordered by decreasing size (the kernels rely on nothing else)"""
+    import ctypes as C
+    _, cmds, _ = helpers_tr.tr_case(832, 480, 4242, 7, 1, 0, 1, p_intra=0.3)
+    items = np.zeros((3 * len(cmds) + 1, 2), np.uint32)
+    ns, nl = C.c_int(), C.c_int()
+    n = emu.emu_tu_items(cmds.ctypes.data_as(C.c_void_p), len(cmds), items.ctypes.data_as(C.c_void_p), C.byref(ns), C.byref(nl))
+    want = set()
+    for i, c in enumerate(cmds):
+        m = int(c["cbf_mask"])
+        kinds = ([0] if m & 0x10 else []) + ([3] if m & 0x08 else ([1] if m & 0x02 else []) + ([2] if m & 0x01 else []))
+        want |= {(i, k) for k in kinds}
+    got = [(int(a), int(b)) for a, b in items[:n]]
+    assert len(got) == len(set(got)) == len(want) and set(got) == want and n == ns.value + nl.value
+    size = [int(cmds["log2_w"][i]) + int(cmds["log2_h"][i]) - (2 if k else 0) for i, k in got]
+    assert all(s <= 8 for s in size[:ns.value]) and all(s > 8 for s in size[ns.value:]) and ns.value and nl.value
+    assert size[:ns.value] == sorted(size[:ns.value], reverse=True) and size[ns.value:] == sorted(size[ns.value:], reverse=True)
+
+
 def test_zero_residual_is_identity(pt, emu):
     planes, cmds, arena = helpers_tr.tr_case(256, 128, 9, 7)
     arena[:] = 0
