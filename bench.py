@@ -257,7 +257,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", default="4k", choices=sorted(SIZES))
     ap.add_argument("--pics", type=int, default=8, help="pictures per step per GPU")
-    ap.add_argument("--dev-streams", type=int, default=4, help="streams the device-resident pictures of a step are spread over")
+    ap.add_argument("--dev-streams", type=int, default=8, help="streams the device-resident pictures of a step are spread over")
     ap.add_argument("--e2e-share", type=int, default=1, help="e2e contexts (host threads) that share one stream")
     ap.add_argument("--e2e-sets", type=int, default=2, help="picture sets in flight in the e2e leg (1 or 2)")
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
