@@ -5,9 +5,12 @@
 
 One "step" = one pass of the hot path over a batch of `pictures_per_step` synthetic inter pictures per GPU
 (frame-parallel sharding: every rank owns whole pictures); value = pictures/s over all
-ranks with inputs resident in HBM; e2e = the same through the host-buffer C-ABI calls (H2D of reference
-planes' worth of decoder state: PU lists + in-loop parameters, D2H of the output picture, inside the timed
-region).  Prints ONE JSON line on rank 0.
+ranks with inputs resident in HBM (the pictures of a step spread over --dev-streams streams); e2e = the same
+through the host-buffer C-ABI calls: every step the decoder state of every picture (PU / TU / intra command
+lists, coefficients, deblocking maps, SAO / ALF parameters: 15 MB per 4K picture) is committed from pinned
+host memory (host-side validation + work lists + H2D) and the output picture is copied back (D2H, 25 MB),
+all inside the timed region, one host thread per picture like the reference's frame threads, two picture
+sets in flight.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import ctypes as C
