@@ -76,9 +76,9 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(w, h, n_pics, seed0=5000):
+def make_workload(w, h, n_pics, seed0=5000, all_intra=False):
     """Shared reference pictures + n_pics synthetic inter pictures: PU list, SAO and ALF decoder state
-    (SURVEY.md §8(d) generators)."""
+    (SURVEY.md §8(d) generators).  all_intra: every coding unit is intra and there is no PU list (an I picture)."""
     from openvvc_b200 import api, synth, synth_tu, synth_dbf, synth_recon
     refs = [[synth.planes(w, h, seed0 + 900 + i) for i in range(2)], [synth.planes(w, h, seed0 + 950 + i) for i in range(2)]]
     pocs = [[8, 16], [16, 24]]
@@ -91,9 +91,11 @@ def make_workload(w, h, n_pics, seed0=5000):
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
         cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15, p_gpm=0.1)
         cmds = cmds.astype(api.MC_CMD)
+        if all_intra:
+            cmds, prof = cmds[:0], prof[:0]
         # one CU partition for the residual and the intra side: 10 % intra CUs (MRL / MIP / CCLM among them), 4 % CIIP, every TU
         # takes its LMCS chroma scale from the anchor in force (derived on the GPU from reconstructed luma)
-        icmds, tus, coeffs, isp_words, isp_tus = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.86, p_ciip=0.3, p_mrl=0.15,
+        icmds, tus, coeffs, isp_words, isp_tus = synth_recon.recon_case(w, h, seed0 + 400 + i, 7, min_log2=3, p_inter=0.0 if all_intra else 0.86, p_ciip=0.3, p_mrl=0.15,
                                                                         p_cclm=0.3, ict_type=1, p_cbf=0.4, p_mip=0.1, p_isp=0.1, p_bdpcm=0.3)
         anchors, tus = synth_recon.lmcs_anchors(icmds, tus, 7)
         icmds_all, tus_all = icmds, tus                     # one entry per coding unit, decode order (what the CU-order oracle walks)
@@ -107,16 +109,20 @@ def make_workload(w, h, n_pics, seed0=5000):
     return dict(refs=refs, pocs=pocs, lmcs=lmcs, lmcs_data=api.LmcsData.from_dict(synth.lmcs_data(seed0)), lmcs_dict=synth.lmcs_data(seed0), pics=pics)
 
 
-def make_dev(api, c, p, w, h):
-    """device objects of one picture (C-ABI handles) with its decoder state uploaded"""
+def make_dev(api, c, p, w, h, upload=True):
+    """device objects of one picture (C-ABI handles); upload=True: with its decoder state uploaded (device-resident leg),
+    False: empty, to be filled through stage_picture / commit_picture (end-to-end leg)"""
     d = dict(rec=c.picture(w, h), mid=c.picture(w, h), dst=c.picture(w, h),
              alf=api.AlfParams(c, w, h, 7), sao=api.SaoParams(c, w, h, 7),
-             mc=api.McBatch(c, len(p["cmds"]), api.mc_nb_items(p["cmds"])),
+             mc=api.McBatch(c, len(p["cmds"]), api.mc_nb_items(p["cmds"])) if len(p["cmds"]) else None,
              tu=api.TuBatch(c, len(p["tus"]), len(p["coeffs"])), dbf=api.DbfParams(c, w, h, 7),
              intra=api.IntraBatch(c, max(1, len(p["icmds"]))))
+    if not upload:
+        return d
     d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]))
     d["sao"].upload(p["sao"])
-    d["mc"].upload(p["cmds"], prof=p["prof"])
+    if d["mc"]:
+        d["mc"].upload(p["cmds"], prof=p["prof"])
     d["tu"].set_anchors(p["anchors"])
     d["tu"].upload(p["tus"], p["coeffs"], 1, 0, 1)
     d["intra"].upload(p["icmds"], w, h, 7, isp=p["isp_words"])
@@ -131,6 +137,39 @@ def run_stages(api, c, d, ref_pics, pocs, lmcs):
     d["dbf"].run(d["rec"], ctx=c)
     d["sao"].run(d["mid"], d["rec"], ctx=c)
     d["alf"].run(d["dst"], d["mid"], ctx=c)
+
+
+def stage_picture(d, p):
+    """what the recorder does while the CPU parses picture p: writes its PU / TU commands, coefficients and deblocking maps
+    straight into the PINNED staging buffers of the picture's objects (ovgpu_*_staging)"""
+    if d["mc"]:
+        mc_c, mc_p = d["mc"].staging()
+        mc_c[:len(p["cmds"])] = p["cmds"]; mc_p[:len(p["prof"])] = p["prof"]
+    hc, hk = d["tu"].staging()
+    hc[:len(p["tus"])] = p["tus"]; hk[:len(p["coeffs"])] = p["coeffs"]
+    st = d["dbf"].staging()
+    for k in range(9):
+        st["ver"][k][:] = p["dbf"]["ver"][k]; st["hor"][k][:] = p["dbf"]["hor"][k]
+    for k in range(3):
+        st["qp"][k][:] = p["dbf"]["qp"][k]
+
+
+def commit_picture(api, c, d, p, w, h, tt=None):
+    """end of the parse of picture p on context c: every *_commit (validation + work lists + asynchronous H2D out of the pinned
+    staging buffers) and the small per-CTU tables"""
+    if d["mc"]:
+        d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c)
+    if tt is not None: tt.append(time.perf_counter())
+    d["tu"].set_anchors(p["anchors"], ctx=c)
+    d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c)
+    if tt is not None: tt.append(time.perf_counter())
+    d["intra"].upload(p["icmds"], w, h, 7, ctx=c, isp=p["isp_words"])
+    if tt is not None: tt.append(time.perf_counter())
+    d["dbf"].commit(0, 0, ctx=c)
+    if tt is not None: tt.append(time.perf_counter())
+    d["sao"].upload(p["sao"], ctx=c)
+    d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c)
+    if tt is not None: tt.append(time.perf_counter())
 
 
 STAGE_KERNELS = {"mc": ("McK", "BdofK", "DmvrK", "ProfK", "McSmallCK"), "residual": ("TrK",), "intra": ("ovd_recon_kernel", "ReconPrepK"),
@@ -339,7 +378,7 @@ def main():
             api._check(ctx.h, api.lib().ovgpu_picture_copy(ctx.h, ref_pics[slot // 2][slot % 2].p, (src or dev[0])["dst"].p), "picture_copy")
         ovdist.publish_reference(ref_shared[slot // 2][slot % 2], owner, world)
 
-    def step_device(parallel=True):
+    def step_device(parallel=True, hand_off=True):
         if not parallel or n_ds == 1:
             for d in dev:
                 run_picture(d)
@@ -354,7 +393,8 @@ def main():
                 ev = torch.cuda.Event()
                 ev.record(st)
                 stream.wait_event(ev)
-        hand_off_reference()
+        if hand_off:
+            hand_off_reference()
 
     def barrier():
         if world > 1:
@@ -413,15 +453,7 @@ def main():
     np_out = [[[t.numpy() for t in pin] for pin in half] for half in pinned_out]
     for half in e_dev:
         for p, d in zip(pics, half):
-            mc_c, mc_p = d["mc"].staging()
-            mc_c[:len(p["cmds"])] = p["cmds"]; mc_p[:len(p["prof"])] = p["prof"]
-            hc, hk = d["tu"].staging()
-            hc[:len(p["tus"])] = p["tus"]; hk[:len(p["coeffs"])] = p["coeffs"]
-            st = d["dbf"].staging()
-            for k in range(9):
-                st["ver"][k][:] = p["dbf"]["ver"][k]; st["hor"][k][:] = p["dbf"]["hor"][k]
-            for k in range(3):
-                st["qp"][k][:] = p["dbf"]["qp"][k]
+            stage_picture(d, p)
 
     def e2e_worker(t, ev_start, half):
         """one host thread per context, like the reference's frame threads (ovdec.h:47): stages, commits and launches its
@@ -442,13 +474,7 @@ def main():
             p, d = pics[i], e_dev[half][i]
             tt = [time.perf_counter()]
             if tl: mark("h2d0", i)
-            d["mc"].commit(len(p["cmds"]), len(p["prof"]), ctx=c); tt.append(time.perf_counter())
-            d["tu"].set_anchors(p["anchors"], ctx=c)
-            d["tu"].commit(len(p["tus"]), len(p["coeffs"]), 1, 0, 1, ctx=c); tt.append(time.perf_counter())
-            d["intra"].upload(p["icmds"], w, h, 7, ctx=c, isp=p["isp_words"]); tt.append(time.perf_counter())
-            d["dbf"].commit(0, 0, ctx=c); tt.append(time.perf_counter())
-            d["sao"].upload(p["sao"], ctx=c)
-            d["alf"].upload(p["tab"], p["alf_ctu"], (p["ctu"]["cc_cb"], p["ctu"]["cc_cr"]), ctx=c); tt.append(time.perf_counter())
+            commit_picture(api, c, d, p, w, h, tt)
             if tl: mark("h2d1", i)
             st.wait_event(ev_start)
             if tl: mark("k0", i)
@@ -474,7 +500,7 @@ def main():
     host_prof = [] if os.environ.get("BENCH_HOST_PROFILE") else None   # debugging aid: host time of the C-ABI calls, every thread
     timeline = [] if os.environ.get("BENCH_TIMELINE") else None      # debugging aid: device + host time of every phase of every picture
 
-    def step_e2e():
+    def step_e2e(hand_off=True):
         ev_start = torch.cuda.Event()
         ev_start.record(stream)                     # after the previous step's hand-off
         half = e2e_no[0] % n_sets
@@ -482,7 +508,9 @@ def main():
         for evs in [f.result() for f in [pool.submit(e2e_worker, t, ev_start, half) for t in range(n_ctx)]]:
             for ev in evs:
                 stream.wait_event(ev)               # the hand-off waits, on the device, for the step's pictures to be final (their
-        hand_off_reference(e_dev[half][0])          # D2H copies run on under the next step's kernels; the closing barrier covers them)
+        if hand_off:                                # D2H copies run on under the next step's kernels; the closing barrier covers them)
+            hand_off_reference(e_dev[half][0])
+        return half
 
     step_e2e(); step_e2e()
     e2e_steps = max(2, args.steps)
@@ -493,6 +521,29 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
+
+    # ---- verification of the end-to-end leg (untimed): one more end-to-end step and one device-resident step with NO reference
+    # hand-off in between, so both see the same reference pictures.  Every picture that came back through the pinned host buffers
+    # must be identical to the device-resident leg's, and (rank 0, one GPU) picture 0 must equal the CPU oracle chain on those
+    # references -- a fast end-to-end number over wrong pictures is worth nothing.
+    import helpers
+    half = step_e2e(hand_off=False)
+    barrier()
+    e2e_md5 = [helpers.md5(*np_out[half][i]) for i in range(P)]
+    e2e_pic0 = [a.copy() for a in np_out[half][0]]
+    step_device(hand_off=False)
+    barrier()
+    dev_md5 = [helpers.md5(*dev[i]["dst"].download()) for i in range(P)]
+    if e2e_md5 != dev_md5:
+        raise SystemExit("bench.py: end-to-end pictures differ from the device-resident ones: %s vs %s" % (e2e_md5, dev_md5))
+    e2e_check = {"pictures_identical_to_device_leg": P, "md5_picture0": e2e_md5[0], "oracle_pictures_checked": 0}
+    if rank == 0 and world == 1 and not os.environ.get("BENCH_SKIP_ORACLE_CHECK"):
+        import helpers_chain
+        from oracle import pyoracle as po_chk
+        refs_now = [[pic.download() for pic in lst] for lst in ref_pics]
+        want = helpers_chain.oracle_picture(po_chk, dict(wl, refs=refs_now), pics[0])
+        helpers.assert_planes_equal(e2e_pic0, want, "bench.py: end-to-end picture 0 vs the oracle chain")
+        e2e_check["oracle_pictures_checked"] = 1
     if os.environ.get("OVGPU_HOST_TIMING"):
         api.lib().ovgpu_host_timing_dump()
     if host_prof:
@@ -539,7 +590,8 @@ def main():
                 "config": workload_config(w, h, P, n_ds),
                 "gpu_launches": launches,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": len(real_streams), "host_threads": n_ctx, "pictures_in_flight": n_sets * P},
+                        "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": len(real_streams), "host_threads": n_ctx, "pictures_in_flight": n_sets * P,
+                        "check": e2e_check},
                 "roofline": {"kernel": top, "bound": "hbm", "achieved": stages[top]["achieved_gbs"], "peak": peak,
                              "peak_source": peak_src, "unit": "GB/s", "frac": stages[top]["frac"], "traffic": ncu_traffic(top)[0],
                              "traffic_source": ncu_traffic(top)[1],

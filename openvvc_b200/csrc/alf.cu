@@ -128,6 +128,7 @@ int ovgpu_alf_reconstruct_coeff_aps(OVGPUAlfTables *t, const OVGPUAlfAps *luma_a
 
 int ovgpu_alf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUAlfParams **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || width <= 0 || height <= 0 || (width & 7) || (height & 7) || log2_ctu_s < 5 || log2_ctu_s > 7)
         return OVGPU_EINVAL;
     OVGPUAlfParams *p = (OVGPUAlfParams *)calloc(1, sizeof(*p));
@@ -163,6 +164,7 @@ int ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTabl
                             const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
                             int cc_cb_enabled, int cc_cr_enabled)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !p || !tab || !ctu) return OVGPU_EINVAL;
     // the pinned staging buffers are reused: wait for the previous H2D copy out of them
     OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
@@ -181,6 +183,7 @@ int ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTabl
 
 int ovgpu_alf_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUAlfParams *p)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !dst || !src || !p) return OVGPU_EINVAL;
     if (dst == src || dst->plane[0] == src->plane[0]) return ovgpu_set_error(ctx, OVGPU_EINVAL, "ALF needs dst != src");
     if (src->width != p->width || src->height != p->height || dst->width != p->width || dst->height != p->height)
@@ -229,6 +232,7 @@ int ovgpu_alf_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t ds
                          const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
                          int cc_cb_enabled, int cc_cr_enabled)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     OVGPUPicture *src = NULL, *dst = NULL;
     OVGPUAlfParams *p = NULL;
     int ret = ovgpu_picture_create(ctx, width, height, bitdepth, &src);

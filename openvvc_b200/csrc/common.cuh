@@ -57,6 +57,19 @@ static inline PlaneView plane_view(const OVGPUPicture *pic, int c)
 
 int ovgpu_set_error(OVGPUCtx *ctx, int code, const char *fmt, ...);
 
+// Every C-ABI entry that allocates, copies or launches runs on the CONTEXT's device, whatever the calling thread's current
+// device is (a decoder's entry threads default to device 0); the caller's device is restored on return.
+struct DeviceGuard {
+    int prev;
+    explicit DeviceGuard(const OVGPUCtx *ctx) : prev(-1)
+    {
+        int cur = -1;
+        if (ctx && cudaGetDevice(&cur) == cudaSuccess && cur != ctx->device) { prev = cur; cudaSetDevice(ctx->device); }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define OVGPU_DEVICE_GUARD(ctx) DeviceGuard ovgpu_device_guard__(ctx)
+
 #define OVGPU_CUDA_CHECK(ctx, call)                                                          \
     do {                                                                                     \
         cudaError_t e__ = (call);                                                            \

@@ -81,6 +81,7 @@ int ovgpu_ctx_create(OVGPUCtx **out, int device, void *cuda_stream)
 
 void ovgpu_ctx_destroy(OVGPUCtx *ctx)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -93,6 +94,7 @@ void ovgpu_ctx_destroy(OVGPUCtx *ctx)
 
 int ovgpu_ctx_sync(OVGPUCtx *ctx)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaGetLastError());
@@ -113,6 +115,7 @@ uint64_t ovgpu_launch_count(const OVGPUCtx *ctx) { return ctx ? ctx->launches : 
 
 int ovgpu_profile_enable(OVGPUCtx *ctx, int on)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx) return OVGPU_EINVAL;
     ctx->profile = on;
     return 0;
@@ -120,6 +123,7 @@ int ovgpu_profile_enable(OVGPUCtx *ctx, int on)
 
 int ovgpu_profile_get(OVGPUCtx *ctx, int stage, double *ms, uint64_t *launches)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || stage < 0 || stage >= OVGPU_NB_STAGES) return OVGPU_EINVAL;
     if (ctx->nb_pending) {
         OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -138,6 +142,7 @@ int ovgpu_profile_get(OVGPUCtx *ctx, int stage, double *ms, uint64_t *launches)
 
 int ovgpu_profile_reset(OVGPUCtx *ctx)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx) return OVGPU_EINVAL;
     double ms; uint64_t n;
     ovgpu_profile_get(ctx, 0, &ms, &n);
@@ -147,6 +152,7 @@ int ovgpu_profile_reset(OVGPUCtx *ctx)
 
 int ovgpu_flush_l2(OVGPUCtx *ctx)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx) return OVGPU_EINVAL;
     if (!ctx->flush_buf) {
         ctx->flush_bytes = (size_t)256 << 20;   // 2x the 126 MB L2
@@ -179,6 +185,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || width <= 0 || height <= 0 || (width & 7) || (height & 7)) return OVGPU_EINVAL;
     if (bitdepth != 10 && bitdepth != 8) return OVGPU_EINVAL;
     OVGPUPicture *pic = (OVGPUPicture *)calloc(1, sizeof(*pic));
@@ -200,9 +207,12 @@ int ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVG
 int ovgpu_picture_wrap(OVGPUCtx *ctx, int width, int height, int bitdepth,
                        void *const dev_planes[3], const size_t pitch_bytes[3], OVGPUPicture **out)
 {
-    if (!ctx || !out || !dev_planes || !pitch_bytes || (width & 7) || (height & 7)) return OVGPU_EINVAL;
-    for (int c = 0; c < 3; c++)
-        if (!dev_planes[c] || ((uintptr_t)dev_planes[c] & 15) || (pitch_bytes[c] & 15)) return OVGPU_EINVAL;
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !out || !dev_planes || !pitch_bytes || width <= 0 || height <= 0 || (width & 7) || (height & 7) ||
+        (bitdepth != 8 && bitdepth != 10)) return OVGPU_EINVAL;
+    for (int c = 0; c < 3; c++)      // every kernel indexes the planes from width / height / pitch: a short pitch would be out-of-bounds writes
+        if (!dev_planes[c] || ((uintptr_t)dev_planes[c] & 15) || (pitch_bytes[c] & 15) ||
+            pitch_bytes[c] < (size_t)(c ? width >> 1 : width) * sizeof(uint16_t)) return OVGPU_EINVAL;
     OVGPUPicture *pic = (OVGPUPicture *)calloc(1, sizeof(*pic));
     if (!pic) return OVGPU_ENOMEM;
     pic->width = width; pic->height = height; pic->bitdepth = bitdepth; pic->device = ctx->device;
@@ -220,6 +230,7 @@ void ovgpu_picture_destroy(OVGPUPicture *pic)
 
 int ovgpu_picture_upload(OVGPUCtx *ctx, OVGPUPicture *pic, const void *const data[3], const size_t linesize[3])
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
     for (int c = 0; c < 3; c++) {
         int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
@@ -231,6 +242,7 @@ int ovgpu_picture_upload(OVGPUCtx *ctx, OVGPUPicture *pic, const void *const dat
 
 int ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const data[3], const size_t linesize[3])
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
     for (int c = 0; c < 3; c++) {
         int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
@@ -255,6 +267,7 @@ int ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pi
 
 int ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !dst || !src || dst->width != src->width || dst->height != src->height) return OVGPU_EINVAL;
     CopyPlanes a;
     int aligned = 1;

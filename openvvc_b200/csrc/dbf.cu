@@ -19,6 +19,7 @@ extern "C" {
 
 int ovgpu_dbf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUDbfParams **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || width <= 0 || height <= 0 || (width & 7) || (height & 7) || log2_ctu_s < 5 || log2_ctu_s > 7)
         return OVGPU_EINVAL;
     OVGPUDbfParams *p = (OVGPUDbfParams *)calloc(1, sizeof(*p));
@@ -49,6 +50,7 @@ void ovgpu_dbf_params_destroy(OVGPUDbfParams *p)
 
 int ovgpu_dbf_params_staging(OVGPUCtx *ctx, OVGPUDbfParams *p, OVGPUDbfMaps *maps)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !p || !maps) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
     maps->width = p->width; maps->height = p->height; maps->log2_ctu_s = p->log2_ctu;
@@ -61,6 +63,7 @@ int ovgpu_dbf_params_staging(OVGPUCtx *ctx, OVGPUDbfParams *p, OVGPUDbfMaps *map
 
 int ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, int tc_offset)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !p) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
     p->beta_offset = beta_offset; p->tc_offset = tc_offset;
@@ -72,6 +75,7 @@ int ovgpu_dbf_params_commit(OVGPUCtx *ctx, OVGPUDbfParams *p, int beta_offset, i
 
 int ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps *maps)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !p || !maps) return OVGPU_EINVAL;
     if (maps->width != p->width || maps->height != p->height || maps->log2_ctu_s != p->log2_ctu)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "DBF maps geometry differs from the parameter object");
@@ -90,6 +94,7 @@ int ovgpu_dbf_params_upload(OVGPUCtx *ctx, OVGPUDbfParams *p, const OVGPUDbfMaps
 
 int ovgpu_dbf_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUDbfParams *p)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !p) return OVGPU_EINVAL;
     if (!p->loaded || pic->width != p->width || pic->height != p->height)
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "DBF parameters not uploaded or of another geometry");

@@ -103,10 +103,12 @@ struct ovd_u4 { uint32_t x, y, z, w; };
 #ifdef OVGPU_HOST_EMU
 OVD ovd_u2 ovd_ld8(const void *p) { ovd_u2 r; memcpy(&r, p, 8); return r; }
 OVD ovd_u4 ovd_ld16(const void *p) { ovd_u4 r; memcpy(&r, p, 16); return r; }
+OVD ovd_u4 ovd_ld16_rw(const void *p) { ovd_u4 r; memcpy(&r, p, 16); return r; }
 OVD void ovd_st8(void *p, ovd_u2 v) { memcpy(p, &v, 8); }
 OVD void ovd_st16(void *p, ovd_u4 v) { memcpy(p, &v, 16); }
 #else
-// streaming (touch-once) accesses: bypass L1 allocation
+// streaming (touch-once) accesses: bypass L1 allocation.  ovd_ld8 / ovd_ld16 use the READ-ONLY path (ld.global.nc): only for
+// memory that no thread of the running kernel writes; kernels that work in place use ovd_ld16_rw.
 OVD ovd_u2 ovd_ld8(const void *p)
 {
     ovd_u2 r;
@@ -118,6 +120,13 @@ OVD ovd_u4 ovd_ld16(const void *p)
     ovd_u4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+OVD ovd_u4 ovd_ld16_rw(const void *p)
+{
+    ovd_u4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
     return r;
 }
 OVD void ovd_st8(void *p, ovd_u2 v)
@@ -154,15 +163,20 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const ty
 template <class K>
 static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_t smem, cudaStream_t s)
 {
-    static bool configured = false;          // per kernel instantiation
-    if (!configured) {
+    // per kernel instantiation AND device: function attributes are per device.  Two threads may both find the bit clear and
+    // both set the (idempotent) attributes; the bit is published only after they are set.
+    static unsigned configured_mask = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned bit = 1u << (dev & 31);
+    if (!(__atomic_load_n(&configured_mask, __ATOMIC_ACQUIRE) & bit)) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
         // ask for the largest shared-memory carve-out so that occupancy is bounded by registers, not by the L1 split
         if (smem > 0) cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        __atomic_fetch_or(&configured_mask, bit, __ATOMIC_RELEASE);
     }
     ovd_kernel<K><<<grid, K::THREADS, smem, s>>>(a);
     return cudaGetLastError();

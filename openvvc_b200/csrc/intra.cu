@@ -12,6 +12,7 @@ static_assert(sizeof(IntraCmdDev) == sizeof(OVGPUIntraCmd) && sizeof(IntraCmdDev
 struct OVGPUIntraBatch {
     int max_cmds, nb_cmds, device, pic_w, pic_h, log2_ctu;
     IntraCmdDev *h_cmds, *d_cmds;
+    OVGPUTuBatch *empty_tu;                         // residual batch without commands for prediction-only reconstruction calls
     IntraLevels lv;                                 // per plane: order (pinned, 2 * max_cmds) and level starts (host only)
     uint32_t *h_order, *d_order;                    // [plane][max_cmds]
     IspInfoDev *h_isp, *d_isp;                      // ISP table (grown on demand)
@@ -32,6 +33,7 @@ extern "C" {
 
 int ovgpu_intra_batch_create(OVGPUCtx *ctx, int max_cmds, OVGPUIntraBatch **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || max_cmds <= 0) return OVGPU_EINVAL;
     OVGPUIntraBatch *b = (OVGPUIntraBatch *)calloc(1, sizeof(*b));
     if (!b) return OVGPU_ENOMEM;
@@ -65,6 +67,7 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
     free(b->lv.start[0]);
     if (b->h_isp) cudaFreeHost(b->h_isp);
     if (b->d_isp) cudaFree(b->d_isp);
+    if (b->empty_tu) ovgpu_tu_batch_destroy(b->empty_tu);
     free(b->pos_l); free(b->pos_c); free(b->lv.ws_map); free(b->lv.ws_lvl); free(b->lv.ws_fill);
     if (b->d_pend) cudaFree(b->d_pend);
     if (b->d_counter) cudaFree(b->d_counter);
@@ -75,12 +78,14 @@ void ovgpu_intra_batch_destroy(OVGPUIntraBatch *b)
 int ovgpu_intra_batch_upload(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
                              int pic_w, int pic_h, int log2_ctu_s)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     return ovgpu_intra_batch_upload2(ctx, b, cmds, nb_cmds, NULL, 0, pic_w, pic_h, log2_ctu_s);
 }
 
 int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntraCmd *cmds, int nb_cmds,
                               const OVGPUIspInfo *isp, int nb_isp, int pic_w, int pic_h, int log2_ctu_s)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || nb_isp < 0 || nb_isp > 65536 || (nb_isp && !isp)) return OVGPU_EINVAL;
     if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || (nb_cmds && !cmds) || log2_ctu_s < 5 || log2_ctu_s > 7 ||
         pic_w <= 0 || pic_h <= 0 || (pic_w & 7) || (pic_h & 7))
@@ -109,7 +114,10 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
         OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_isp, b->h_isp, sizeof(IspInfoDev) * nb_isp, cudaMemcpyHostToDevice, ctx->stream));
     }
     b->nb_cmds = nb_cmds; b->pic_w = pic_w; b->pic_h = pic_h; b->log2_ctu = log2_ctu_s; b->lv.nb[0] = b->lv.nb[1] = 0;
-    b->serial++;
+    {   // process-wide unique: the TU batch keys its cached reconstruction lists on it, and two intra batches must never share a value
+        static uint64_t next_serial = 0;
+        b->serial = __atomic_add_fetch(&next_serial, 1, __ATOMIC_RELAXED);
+    }
     // the position maps stay all zero between pictures except for the blocks of the commands last mapped into them, which are
     // cleared here block by block (b->h_cmds still holds those commands) instead of clearing 2 x 2 MB per 4K picture
     const size_t units = (size_t)(pic_w >> 2) * (pic_h >> 2);
@@ -126,12 +134,13 @@ int ovgpu_intra_batch_upload2(OVGPUCtx *ctx, OVGPUIntraBatch *b, const OVGPUIntr
         b->map_cmds = 0;
     }
     b->lv.ws_clean = 1;
+    b->lv.units_mask = ((1 << log2_ctu_s) >> 2) - 1;
     if (!nb_cmds) return 0;
     memcpy(b->h_cmds, cmds, sizeof(IntraCmdDev) * nb_cmds);
     b->map_cmds = nb_cmds;
     int lrc;
     { HostSection hs(HT_INTRA_LEVELS); lrc = intra_build_levels(&b->lv, b->max_cmds, cmds, nb_cmds, pic_w, pic_h, b->pos_l, b->pos_c); }
-    if (lrc == -2) { b->nb_cmds = 0; return ovgpu_set_error(ctx, OVGPU_EINVAL, "a block copy command reads samples that are not reconstructed before it"); }
+    if (lrc == -2) { b->nb_cmds = 0; return ovgpu_set_error(ctx, OVGPU_EINVAL, "a command waits on samples that are not reconstructed before it (block copy source, or an availability word that flags a unit of a later command)"); }
     if (lrc)
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "intra dependency levels");
     HostSection hs_copies(HT_INTRA_COPIES);
@@ -154,6 +163,7 @@ static int launch_intra(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch 
 
 int ovgpu_intra_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUIntraBatch *b)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !b) return OVGPU_EINVAL;
     if (!b->nb_cmds) return 0;
     if (b->has_isp) return ovgpu_set_error(ctx, OVGPU_EINVAL, "ISP and block copy commands are reconstructed by ovgpu_recon_picture only");
@@ -176,8 +186,11 @@ static int recon_scales(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *lmcs,
 static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, const OVGPUTuBatch *tu, int p, int nb_items)
 {
     if (!nb_items) return 0;
-    static int configured = 0, blocks_per_sm = 1;
-    if (!configured) {
+    // per DEVICE (function attributes and occupancy are): slot = the context's device; a racing second thread computes the same values
+    static int configured_dev[64], blocks_per_sm_dev[64];
+    const int slot = ctx->device & 63;
+    int blocks_per_sm = __atomic_load_n(&blocks_per_sm_dev[slot], __ATOMIC_RELAXED);
+    if (!__atomic_load_n(&configured_dev[slot], __ATOMIC_ACQUIRE)) {
         cudaFuncSetAttribute(ovd_recon_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, ovd_recon_kernel, 128, RECON_SMEM_BYTES) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
@@ -185,7 +198,8 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
         // kernels of other pictures running next to this one; the queue order keeps any number >= 1 deadlock-free.
         const char *e = getenv("OVGPU_RECON_WORKERS_PER_SM");
         if (e && atoi(e) >= 1 && atoi(e) < blocks_per_sm) blocks_per_sm = atoi(e);
-        configured = 1;
+        __atomic_store_n(&blocks_per_sm_dev[slot], blocks_per_sm, __ATOMIC_RELAXED);
+        __atomic_store_n(&configured_dev[slot], 1, __ATOMIC_RELEASE);
     }
     PlaneView v0 = plane_view(pic, 0), v1 = plane_view(pic, 1), v2 = plane_view(pic, 2);
     ReconArgs a;
@@ -210,6 +224,7 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
 int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *refs, const OVGPUMcBatch *mc,
                         const OVGPULmcs *lmcs, OVGPUTuBatch *tu, OVGPUIntraBatch *intra)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || (mc && !refs)) return OVGPU_EINVAL;
     int rc;
     if (mc) { HostSection hs(HT_RECON_MC); if ((rc = ovgpu_mc_picture(ctx, pic, refs, mc, lmcs)) != 0) return rc; }
@@ -218,12 +233,13 @@ int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *ref
     if (has_intra && (pic->width != intra->pic_w || pic->height != intra->pic_h))
         return ovgpu_set_error(ctx, OVGPU_EINVAL, "intra batch was built for another picture size");
     if (!has_intra && !ovgpu_tu_nb_anchors(tu)) return ovgpu_residual_picture(ctx, pic, tu);      // one plain residual pass
-    OVGPUTuBatch *own_tu = NULL;
-    if (!tu) {          // prediction only: an empty residual batch keeps one code path
-        if ((rc = ovgpu_tu_batch_create(ctx, 1, 1, &own_tu)) != 0) return rc;
-        OVGPUTuSlice sl = { 0, 0, 0, 0 };
-        if ((rc = ovgpu_tu_batch_commit(ctx, own_tu, 0, 0, &sl)) != 0) { ovgpu_tu_batch_destroy(own_tu); return rc; }
-        tu = own_tu;
+    if (!tu) {          // prediction only: an empty residual batch keeps one code path; it lives with the intra batch (no allocation
+        if (!intra->empty_tu) {                                    // or stream synchronisation per call)
+            if ((rc = ovgpu_tu_batch_create(ctx, 1, 1, &intra->empty_tu)) != 0) return rc;
+            OVGPUTuSlice sl = { 0, 0, 0, 0 };
+            if ((rc = ovgpu_tu_batch_commit(ctx, intra->empty_tu, 0, 0, &sl)) != 0) { ovgpu_tu_batch_destroy(intra->empty_tu); intra->empty_tu = NULL; return rc; }
+        }
+        tu = intra->empty_tu;
     }
     const int w_u = pic->width >> 2, h_u = pic->height >> 2;
     const uint32_t *order[2] = { has_intra ? intra->lv.order[0] : NULL, has_intra ? intra->lv.order[1] : NULL };
@@ -259,7 +275,6 @@ int ovgpu_recon_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUMcRefs *ref
         if (!rc) rc = ovgpu_tu_run_inter(ctx, pic, tu, p);
         if (!rc && has_intra) rc = recon_plane(ctx, pic, intra, tu, p, nb[p]);
     }
-    if (own_tu) { cudaStreamSynchronize(ctx->stream); ovgpu_tu_batch_destroy(own_tu); }
     return rc;
 }
 

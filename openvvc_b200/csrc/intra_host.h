@@ -52,6 +52,8 @@ struct IntraLevels {
     // ws_clean: ws_map and the position maps handed to intra_build_levels are all zero on entry (and ws_map is left all zero):
     // clearing megabytes of maps per picture costs more than everything else in here when only a tenth of the picture is intra
     int ws_clean;
+    // (CTU size >> 2) - 1: with it the availability words of every command are checked against the queue order (0: no check)
+    int units_mask;
 };
 
 // zeroes the units of the commands' blocks in a position / level map (the inverse of what intra_build_levels writes)
@@ -144,6 +146,29 @@ static inline int intra_build_levels(IntraLevels *L, int max_levels, const OVGPU
                     int bvx = (int16_t)(c->pad[0] | (c->pad[1] << 8)), bvy = (int16_t)(c->pad[2] | (c->pad[3] << 8));
                     for (int y = (c->y0 + bvy) >> 2; y <= (c->y0 + bvy + (1 << c->log2_h) - 1) >> 2; y++)
                         for (int x = (c->x0 + bvx) >> 2; x <= (c->x0 + bvx + (1 << c->log2_w) - 1) >> 2; x++) if (pos[p][y * w_u + x] > q) ret = -2;
+                }
+                // the same for ordinary commands: the kernel waits on every neighbour unit the caller's availability words flag
+                // (recon_kernels.h: left column from the corner down to 2h, above row over 2w).  The levels above come from geometry
+                // and input order only, so a word that flags a unit covered by a LATER command of the queue (only an inconsistent
+                // recorder produces one) would make that wait cyclic: refuse it here instead of hanging the GPU.
+                const int um = L->units_mask;
+                for (uint32_t q = 0; q < start[nb_levels] && !ret && um; q++) {
+                    const OVGPUIntraCmd *c = &cmds[L->order[p][q]];
+                    if (c->flags & OVGPU_INTRA_IBC) continue;
+                    const int xu = c->x0 >> 2, yu = c->y0 >> 2, nw = (1 << c->log2_w) >> 2, nh = (1 << c->log2_h) >> 2;
+                    const int xl = xu & um, yl = yu & um;
+                    if (xu > 0)
+                        for (int k = 0; k < 2 * nh + 1; k++) {
+                            const int uy = yu - 1 + k, bit = yl + k;
+                            if (uy < 0 || uy >= h_u || bit >= 64 || !((c->avail_cols >> bit) & 1)) continue;
+                            if (pos[p][uy * w_u + xu - 1] > q) ret = -2;
+                        }
+                    if (yu > 0)
+                        for (int k = 0; k < 2 * nw; k++) {
+                            const int ux = xu + k, bit = xl + k + 1;
+                            if (ux >= w_u || bit >= 64 || !((c->avail_rows >> bit) & 1)) continue;
+                            if (pos[p][(yu - 1) * w_u + ux] > q) ret = -2;
+                        }
                 }
             }
         }

@@ -42,6 +42,7 @@ int ovgpu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *data, int bi
 
 int ovgpu_lmcs_create(OVGPUCtx *ctx, OVGPULmcs **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out) return OVGPU_EINVAL;
     OVGPULmcs *l = (OVGPULmcs *)calloc(1, sizeof(*l));
     if (!l) return OVGPU_ENOMEM;
@@ -67,6 +68,7 @@ void ovgpu_lmcs_destroy(OVGPULmcs *l)
 
 int ovgpu_lmcs_upload(OVGPUCtx *ctx, OVGPULmcs *l, const OVGPULmcsLuts *luts)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !l || !luts) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, fence_wait(&l->fence));
     memcpy(l->h_luts, luts, sizeof(*luts));
@@ -87,6 +89,7 @@ int ovgpu_lmcs_set_data(OVGPULmcs *l, const OVGPULmcsData *d)
 
 int ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs *l, int forward)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !l) return OVGPU_EINVAL;
     StageScope scope(ctx, OVGPU_STAGE_LMCS, 1);
     PlaneView v = plane_view(pic, 0);
@@ -98,6 +101,7 @@ int ovgpu_lmcs_reshape_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPULmcs
 
 int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBatch **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || max_cmds <= 0 || max_items < max_cmds) return OVGPU_EINVAL;
     OVGPUMcBatch *b = (OVGPUMcBatch *)calloc(1, sizeof(*b));
     if (!b) return OVGPU_ENOMEM;
@@ -136,11 +140,13 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
 
 int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     return ovgpu_mc_batch_upload2(ctx, b, cmds, nb_cmds, NULL, 0);
 }
 
 int ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || !cmds) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));           // previous H2D copy out of the staging buffers
     *cmds = (OVGPUMcCmd *)b->h_cmds;
@@ -150,6 +156,7 @@ int ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OV
 
 int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_prof)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0) return OVGPU_EINVAL;
     if (nb_prof > b->max_prof) return ovgpu_set_error(ctx, OVGPU_EINVAL, "PROF table too large (%d > %d)", nb_prof, b->max_prof);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
@@ -208,6 +215,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
 int ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
                            const OVGPUProfInfo *prof, int nb_prof)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || !cmds || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_prof < 0 || (nb_prof && !prof)) return OVGPU_EINVAL;
     if (nb_prof > b->max_prof) return ovgpu_set_error(ctx, OVGPU_EINVAL, "PROF table too large (%d > %d)", nb_prof, b->max_prof);
     OVGPUMcCmd *hc; OVGPUProfInfo *hp;
@@ -221,6 +229,7 @@ int ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmd
 int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                      const OVGPULmcs *lmcs)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !dst || !refs || !b) return OVGPU_EINVAL;
     if (!(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr + b->nb_small_c)) return 0;
     McK::Args a;
@@ -275,6 +284,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
 
 int ovgpu_mc_batch_read_dmvr(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUDmvrMv *out, int max)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || (max > 0 && !out)) return OVGPU_EINVAL;
     const int n = b->nb_dmvr < max ? b->nb_dmvr : max;
     if (n > 0) {

@@ -132,7 +132,7 @@ struct LmcsReshapeK {
         if (x >= a.w || y >= a.h) return;
         const int msk = (1 << a.bitdepth) - 1;
         uint16_t *p = a.plane + (size_t)y * a.pitch + x;
-        ovd_u4 v = ovd_ld16(p);
+        ovd_u4 v = ovd_ld16_rw(p);         // in place: not the read-only (.nc) path
         uint32_t in[4] = { v.x, v.y, v.z, v.w }, o[4];
 #pragma unroll
         for (int i = 0; i < 4; i++)

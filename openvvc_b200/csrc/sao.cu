@@ -17,6 +17,7 @@ extern "C" {
 
 int ovgpu_sao_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s, OVGPUSaoParams **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || width <= 0 || height <= 0 || (width & 7) || (height & 7) || log2_ctu_s < 5 || log2_ctu_s > 7)
         return OVGPU_EINVAL;
     OVGPUSaoParams *p = (OVGPUSaoParams *)calloc(1, sizeof(*p));
@@ -47,6 +48,7 @@ void ovgpu_sao_params_destroy(OVGPUSaoParams *p)
 
 int ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu *ctu)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !p || !ctu) return OVGPU_EINVAL;
     // the kernel keeps the five offsets of a CTU as packed bytes (|offset| <= 31 at 10 bit, vcl_sao.c:69)
     for (int i = 0; i < p->nb_ctu; i++)
@@ -64,6 +66,7 @@ int ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu 
 
 int ovgpu_sao_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUSaoParams *p)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !dst || !src || !p) return OVGPU_EINVAL;
     if (dst == src || dst->plane[0] == src->plane[0]) return ovgpu_set_error(ctx, OVGPU_EINVAL, "SAO needs dst != src");
     if (src->width != p->width || src->height != p->height || dst->width != p->width || dst->height != p->height)
@@ -86,6 +89,7 @@ int ovgpu_sao_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t ds
                          const void *const src_data[3], const size_t src_linesize[3],
                          int width, int height, int log2_ctu_s, int bitdepth, const OVGPUSaoCtu *ctu)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     OVGPUPicture *src = NULL, *dst = NULL;
     OVGPUSaoParams *p = NULL;
     int ret = ovgpu_picture_create(ctx, width, height, bitdepth, &src);

@@ -25,6 +25,7 @@ struct OVGPUTuBatch {
     ReconItemDev *h_ritems, *d_ritems;  // [plane][max_ritems]
     int max_ritems, nb_ritems[2];
     uint64_t serial, bound_serial, bound_intra_serial;
+    int bound_w_u, bound_h_u;
     // LMCS chroma scale anchors (ovgpu_tu_batch_set_anchors) and the scales LmcsScaleK derives for them
     LmcsAnchorDev *h_anchors, *d_anchors;
     int16_t *d_scales;
@@ -50,6 +51,7 @@ extern "C" {
 
 int ovgpu_tu_batch_create(OVGPUCtx *ctx, int max_cmds, size_t max_coeffs, OVGPUTuBatch **out)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !out || max_cmds <= 0 || !max_coeffs) return OVGPU_EINVAL;
     OVGPUTuBatch *b = (OVGPUTuBatch *)calloc(1, sizeof(*b));
     if (!b) return OVGPU_ENOMEM;
@@ -88,6 +90,7 @@ void ovgpu_tu_batch_destroy(OVGPUTuBatch *b)
 
 int ovgpu_tu_batch_staging(OVGPUCtx *ctx, OVGPUTuBatch *b, OVGPUTuCmd **cmds, int16_t **coeffs)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || !cmds || !coeffs) return OVGPU_EINVAL;
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));           // previous H2D copy out of the staging buffers
     *cmds = (OVGPUTuCmd *)b->h_cmds;
@@ -97,6 +100,7 @@ int ovgpu_tu_batch_staging(OVGPUCtx *ctx, OVGPUTuBatch *b, OVGPUTuCmd **cmds, in
 
 int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb_coeffs, const OVGPUTuSlice *slice)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs) return OVGPU_EINVAL;
     const OVGPUTuCmd *cmds = (const OVGPUTuCmd *)b->h_cmds;
     {
@@ -128,6 +132,7 @@ int ovgpu_tu_batch_commit(OVGPUCtx *ctx, OVGPUTuBatch *b, int nb_cmds, size_t nb
 int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds, int nb_cmds,
                           const int16_t *coeffs, size_t nb_coeffs, const OVGPUTuSlice *slice)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || !slice || nb_cmds < 0 || nb_cmds > b->max_cmds || nb_coeffs > b->max_coeffs ||
         (nb_cmds && (!cmds || !coeffs)))
         return OVGPU_EINVAL;
@@ -140,6 +145,7 @@ int ovgpu_tu_batch_upload(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPUTuCmd *cmds
 
 int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAnchor *anchors, int nb)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !b || nb < 0 || nb > 65536 || (nb && !anchors)) return OVGPU_EINVAL;
     HostSection hs(HT_TU_ANCHORS);
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence_anchors));
@@ -167,6 +173,7 @@ int ovgpu_tu_batch_set_anchors(OVGPUCtx *ctx, OVGPUTuBatch *b, const OVGPULmcsAn
 
 int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !b) return OVGPU_EINVAL;
     if (pic->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "residual path is built for 10-bit pictures");
     for (int i = 0; i < b->nb_cmds; i++) {
@@ -201,7 +208,8 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
 int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, const uint32_t *pos_l, const uint32_t *pos_c,
                         int w_u, int h_u, const uint32_t *const order[2], const int nb[2])
 {
-    if (b->lists.built && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial) return 0;
+    OVGPU_DEVICE_GUARD(ctx);
+    if (b->lists.built && b->bound_serial == b->serial && b->bound_intra_serial == intra_serial && b->bound_w_u == w_u && b->bound_h_u == h_u) return 0;
     for (int i = 0; i < b->nb_cmds; i++) {
         const TuCmdDev *c = &b->h_cmds[i];
         if ((c->x0 >> 2) >= w_u || (c->y0 >> 2) >= h_u) return ovgpu_set_error(ctx, OVGPU_EINVAL, "TU command %d lies outside the picture", i);
@@ -228,13 +236,14 @@ int ovgpu_tu_bind_recon(OVGPUCtx *ctx, OVGPUTuBatch *b, uint64_t intra_serial, c
     if (n) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items, b->h_bitems, sizeof(TbItemDev) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (need) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_ritems, b->h_ritems, sizeof(ReconItemDev) * 2 * b->max_ritems, cudaMemcpyHostToDevice, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence_bind, ctx->stream));
-    b->bound_serial = b->serial; b->bound_intra_serial = intra_serial;
+    b->bound_serial = b->serial; b->bound_intra_serial = intra_serial; b->bound_w_u = w_u; b->bound_h_u = h_u;
     return 0;
 }
 
 // residual of the transform blocks of plane p that lie outside intra commands
 int ovgpu_tu_run_inter(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, int p)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     const int ns = b->lists.n_small[p], nl = b->lists.n_large[p];
     if (!(ns + nl)) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, (ns > 0) + (nl > 0));
@@ -256,6 +265,7 @@ void ovgpu_tu_recon_args(const OVGPUTuBatch *b, int p, ReconArgs *a)
 int ovgpu_tu_derive_scales(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b, const uint16_t *d_wnd_bnd,
                            int min_idx, int max_idx_p1, int crs_offset)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (!b->nb_anchors) return 0;
     for (int i = 0; i < b->nb_anchors; i++) {
         const LmcsAnchorDev *a = &b->h_anchors[i];
@@ -275,6 +285,7 @@ int ovgpu_tu_nb_anchors(const OVGPUTuBatch *b) { return b->nb_anchors; }
 
 int ovgpu_tu_check_picture(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUTuBatch *b)
 {
+    OVGPU_DEVICE_GUARD(ctx);
     if (pic->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "residual path is built for 10-bit pictures");
     if (b->checked_serial == b->serial && b->checked_w == pic->width && b->checked_h == pic->height) return 0;      // same commit, same size
     for (int i = 0; i < b->nb_cmds; i++) {

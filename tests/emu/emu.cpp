@@ -229,7 +229,7 @@ static void emu_intra_launch(uint16_t *const planes[3], const int stride[3], int
 struct EmuLevels {
     std::vector<uint32_t> order[2], start[2];
     IntraLevels lv;
-    EmuLevels(int n) { lv.ws_clean = 0; lv.ws_map = NULL; lv.ws_lvl = NULL; lv.ws_fill = NULL; for (int p = 0; p < 2; p++) { order[p].resize(n + 1); start[p].resize(n + 3); lv.order[p] = order[p].data(); lv.start[p] = start[p].data(); } }
+    EmuLevels(int n) { lv.ws_clean = 0; lv.units_mask = 0; lv.ws_map = NULL; lv.ws_lvl = NULL; lv.ws_fill = NULL; for (int p = 0; p < 2; p++) { order[p].resize(n + 1); start[p].resize(n + 3); lv.order[p] = order[p].data(); lv.start[p] = start[p].data(); } }
 };
 
 // The product keeps its level / position maps all zero between pictures and clears only the blocks it wrote (intra.cu,
