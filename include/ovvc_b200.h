@@ -51,6 +51,12 @@ int  ovgpu_profile_reset(OVGPUCtx *ctx);
 /* write `bytes` of device scratch (> L2) so the next timed launch starts cold; bench.py uses it */
 int  ovgpu_flush_l2(OVGPUCtx *ctx);
 
+/* Page-locks caller memory (cudaHostRegister) so that copies to / from it are asynchronous DMA: what the reference's frame pool
+ * would do at allocation time (ovframepool_request_planes -> ovmempool_popelem -> ov_mallocz, ovframepool.c:194-231, mempool.c:73-86).
+ * Registering a range twice is not an error.  _unregister before the memory is freed. */
+int  ovgpu_host_register(OVGPUCtx *ctx, void *ptr, size_t bytes);
+int  ovgpu_host_unregister(OVGPUCtx *ctx, void *ptr);
+
 /* ---- pictures  (replaces the ov_mallocz'ed planes of ovframepool_request_planes, ovframepool.c:194) --- */
 int  ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **pic);
 /* wrap caller-owned device memory (e.g. a torch tensor that NCCL broadcasts) */

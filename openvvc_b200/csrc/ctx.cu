@@ -183,6 +183,25 @@ __global__ void __launch_bounds__(256) ovgpu_copy_planes_kernel(CopyPlanes a)
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+int ovgpu_host_register(OVGPUCtx *ctx, void *ptr, size_t bytes)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !ptr || !bytes) return OVGPU_EINVAL;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) { cudaGetLastError(); return ovgpu_set_error(ctx, OVGPU_ECUDA, "cudaHostRegister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int ovgpu_host_unregister(OVGPUCtx *ctx, void *ptr)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !ptr) return OVGPU_EINVAL;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { cudaGetLastError(); return ovgpu_set_error(ctx, OVGPU_ECUDA, "cudaHostUnregister: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
 int ovgpu_picture_create(OVGPUCtx *ctx, int width, int height, int bitdepth, OVGPUPicture **out)
 {
     OVGPU_DEVICE_GUARD(ctx);
