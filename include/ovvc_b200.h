@@ -391,7 +391,10 @@ typedef struct OVGPUIntraCmd {
     uint8_t mrl_idx;              /* luma reference line 0..2 (ctudec->cu_opaque with flg_mrl_flag; vvc_intra_pred_multi_ref,
                                    * rcn_intra.c:645-786); needs y0 >= 4 inside the CTU */
     uint8_t ciip_wt;              /* CIIP: 1 + above CU is intra + left CU is intra (1..3) */
-    uint8_t pad[5];
+    uint8_t pad[5];               /* pad[0..3]: ISP table index / block vector (see the flags); pad[4]: BDPCM prediction of the block
+                                   * (cu_flags flg_intra_bdpcm_*; vvc_intra_pred rcn_intra.c:511-522, vvc_intra_pred_chroma :1043-1074: the pure
+                                   * horizontal / vertical kernel on the unfiltered references, no PDPC) -- bit 0 luma, bit 1 luma direction
+                                   * (1 = vertical), bit 2 chroma, bit 3 chroma direction, the layout of OVGPUTuCmd.bdpcm */
     uint64_t avail_cols, avail_rows;
 } OVGPUIntraCmd;
 

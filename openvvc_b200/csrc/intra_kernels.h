@@ -106,6 +106,10 @@ struct IntraK {
         b.mrl = (b.chroma || b.ciip || b.isp) ? 0 : c.mrl_idx;
         b.pd = b.chroma ? (b.lw > 1 && b.lh > 1) : (b.isp ? b.lh > 1 : !b.mrl);     // ISP: planar / DC PDPC iff log2_pb_h > 1 (rcn_intra.c:612-631)
         int mode = b.ciip ? 0 : (b.chroma ? c.mode_c : c.mode);
+        // BDPCM block (pad[4]: bit 0 luma, bit 1 its direction, bit 2 chroma, bit 3 its direction, as OVGPUTuCmd.bdpcm): the pure
+        // horizontal / vertical kernel on the plain references -- no PDPC, no filtering (rcn_intra.c:511-522, 1043-1074)
+        const int bd = (b.ciip || b.isp || (!b.chroma && (c.flags & 16))) ? 0 : (b.chroma ? (c.pad[4] >> 2) & 3 : c.pad[4] & 3);
+        if (bd & 1) mode = (bd & 2) ? 50 : 18;
         b.mip = !b.chroma && (c.flags & 16);
         b.mip_tr = (c.mode >> 7) & 1; b.mip_idx = c.mode & 0x3f;
         if (b.mip) mode = 1;                           // the phases below branch on b.mip first; DC keeps the derivation trivial
@@ -159,6 +163,7 @@ struct IntraK {
         } else if (mode == 0) {
             b.filt_m = b.filt_s = !b.chroma && !b.mrl && !b.isp && (b.lw + b.lh) > 5;                    // planar: rcn_intra.c:531-538
         }
+        if (bd & 1) { b.use_pdpc = 0; b.gauss = 0; b.filt_m = b.filt_s = 0; b.mrl = 0; }
         return b;
     }
 

@@ -330,7 +330,7 @@ static void cclm_block(uint16_t *const planes[3], const int stride[3], int bitde
 
 /* one block of one plane; chroma: x0 / y0 / log2 sizes in chroma samples */
 static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y0, int xl, int yl, int lw, int lh, int mode_in,
-                        uint64_t cols, uint64_t rows, int chroma, int ciip_wt, int mrl)
+                        uint64_t cols, uint64_t rows, int chroma, int ciip_wt, int mrl, int bdpcm)
 {
     int w = 1 << lw, h = 1 << lh, maxv = (1 << bitdepth) - 1, us = chroma ? 1 : 2;
     uint16_t abv_buf[REF_LEN], lft_buf[REF_LEN], *abv = abv_buf + REF_OFF, *lft = lft_buf + REF_OFF;
@@ -345,7 +345,10 @@ static void intra_block(uint16_t *plane, int stride, int bitdepth, int x0, int y
     }
     int *out = malloc(sizeof(int) * w * h);
     int pd = chroma ? (lw > 1 && lh > 1) : !mrl;
-    if (mode_in == 0) {                                            /* intra_planar(_pdpc), rcn_intra_dc_planar.c:106-149, 196-236 */
+    if (bdpcm) {                                                   /* BDPCM block: cubic_{h,v}->pure on the plain references, nothing else
+                                                                    * (vvc_intra_pred rcn_intra.c:511-522, vvc_intra_pred_chroma :1043-1074) */
+        for (int y = 0; y < h; y++) for (int x = 0; x < w; x++) out[y * w + x] = bdpcm == 2 ? abv[x + 1] : lft[y + 1];
+    } else if (mode_in == 0) {                                            /* intra_planar(_pdpc), rcn_intra_dc_planar.c:106-149, 196-236 */
         uint16_t fa[REF_LEN], fl[REF_LEN];
         const uint16_t *A = abv, *L = lft;
         if (!chroma && !mrl && lw + lh > 5) { filter_ref(fa, abv, lft, w + 4); filter_ref(fl, lft, abv, h + 4); A = fa; L = fl; }
@@ -584,13 +587,14 @@ void ovo_intra_picture(uint16_t *const planes[3], const int stride[3], int pic_w
             mip_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, c->mode, c->avail_cols, c->avail_rows);
         else if (c->flags & OVO_INTRA_LUMA)
             intra_block(planes[0], stride[0], bitdepth, c->x0, c->y0, c->x0 & cm, c->y0 & cm, c->log2_w, c->log2_h, ciip ? 0 : c->mode,
-                        c->avail_cols, c->avail_rows, 0, ciip, ciip ? 0 : c->mrl_idx);
+                        c->avail_cols, c->avail_rows, 0, ciip, ciip ? 0 : c->mrl_idx, (!ciip && (c->pad[4] & 1)) ? 1 + ((c->pad[4] >> 1) & 1) : 0);
         if ((c->flags & OVO_INTRA_CHROMA) && !ciip && c->mode_c >= 67)
             cclm_block(planes, stride, bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1, c->log2_w - 1, c->log2_h - 1,
                        c->mode_c, c->avail_cols, c->avail_rows, (c->flags & OVO_INTRA_CCLM_COLLOCATED) != 0);
         else if ((c->flags & OVO_INTRA_CHROMA) && !(ciip && c->log2_w <= 2))    /* vvc_intra_pred_chroma (rcn_intra.c:1015-1182): Cb then Cr */
             for (int k = 1; k < 3; k++)
                 intra_block(planes[k], stride[k], bitdepth, c->x0 >> 1, c->y0 >> 1, (c->x0 & cm) >> 1, (c->y0 & cm) >> 1,
-                            c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip, 0);
+                            c->log2_w - 1, c->log2_h - 1, ciip ? 0 : c->mode_c, c->avail_cols, c->avail_rows, 1, ciip, 0,
+                            (!ciip && (c->pad[4] & 4)) ? 1 + ((c->pad[4] >> 3) & 1) : 0);
     }
 }

@@ -64,8 +64,6 @@ struct ISPTUInfo { uint8_t cbf_mask, tr_skip_mask, cu_mts_flag, cu_mts_idx, lfns
 
 #define SHIM_MAX_RECS   64
 #define SHIM_MAX_FRAMES 96
-#define SHIM_EXT_BDPCM      1   /* OVGPUIntraCmd.pad[4]: pure horizontal / vertical prediction of a BDPCM block (rcn_intra.c:511-522, 1043-1074) */
-#define SHIM_EXT_BDPCM_VER  2
 
 enum { FRAME_IDLE = 0, FRAME_IN_FLIGHT = 1, FRAME_DONE = 2 };
 
@@ -274,6 +272,9 @@ static void rec_begin_picture(ShimRec *r, const OVFrame *f, const struct RectEnt
 static OVGPUMcCmd *mc_new(ShimRec *r, int x0, int y0, int lw, int lh, int dir, OVMV mv0, OVMV mv1, int ref0, int ref1, int flags, int tool, uint32_t aux)
 {
     OVCTUDec *c = r->ctudec;
+    /* the fields of a list the block does not use are whatever the caller's stack held: never pass them on */
+    if (dir == 1) { memset(&mv1, 0, sizeof(mv1)); ref1 = 0; mv0.bcw_idx_plus1 = 0; }
+    if (dir == 2) { memset(&mv0, 0, sizeof(mv0)); ref0 = 0; }
     rec_grow_mc(r, r->nb_mc + 1, r->nb_prof);
     OVGPUMcCmd *m = &r->mc_cmds[r->nb_mc++];
     memset(m, 0, sizeof(*m));
@@ -370,7 +371,7 @@ static void rec_intra_pred(const struct OVRCNCtx *const rc, const struct OVBuffI
     (void)buf;
     m->flags = OVGPU_INTRA_LUMA; m->mode = mode;
     m->avail_cols = rc->progress_field.vfield[x0 >> 2]; m->avail_rows = rc->progress_field.hfield[y0 >> 2];
-    if (fl & flg_intra_bdpcm_luma_flag) m->pad[4] = SHIM_EXT_BDPCM | ((fl & flg_intra_bdpcm_luma_dir) ? SHIM_EXT_BDPCM_VER : 0);
+    if (fl & flg_intra_bdpcm_luma_flag) m->pad[4] = 1 | ((fl & flg_intra_bdpcm_luma_dir) ? 2 : 0);
 }
 static void rec_intra_pred_mrl(const OVCTUDec *const c, OVSample *const src, ptrdiff_t stride, uint8_t mode, int x0, int y0, int lw, int lh, int mrl_idx)
 {
@@ -392,7 +393,7 @@ static void rec_intra_pred_c(const struct OVRCNCtx *const rc, uint8_t mode_c, in
     OVGPUIntraCmd *m = intra_new(r, x0 << 1, y0 << 1, lw + 1, lh + 1);
     m->flags = (uint8_t)(OVGPU_INTRA_CHROMA | (r->collocated ? OVGPU_INTRA_CCLM_COLLOCATED : 0)); m->mode_c = mode_c;
     m->avail_cols = rc->progress_field_c.vfield[x0 >> 1]; m->avail_rows = rc->progress_field_c.hfield[y0 >> 1];
-    if (fl & flg_intra_bdpcm_chroma_flag) { m->pad[4] = SHIM_EXT_BDPCM | ((fl & flg_intra_bdpcm_chroma_dir) ? SHIM_EXT_BDPCM_VER : 0); return; }
+    if (fl & flg_intra_bdpcm_chroma_flag) { m->pad[4] = 4 | ((fl & flg_intra_bdpcm_chroma_dir) ? 8 : 0); return; }
     fill_bs_map(&rc->ctudec->dbf_info.bs2_map_c, x0 << 1, y0 << 1, lw + 1, lh + 1);        /* the stock slot's bookkeeping (:1180) */
 }
 static void nop_intra_pred_isp(const OVCTUDec *const c, OVSample *const src, ptrdiff_t stride, uint8_t mode, int x0, int y0, int lw, int lh,
