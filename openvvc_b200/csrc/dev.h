@@ -15,11 +15,13 @@
 #include <stdlib.h>
 #include <vector>
 #define OVD static inline
+#define OVDM inline                 /* non-static member functions (functors) */
 #define OVD_CONST static const
 struct ovd_dim3 { unsigned x, y, z; ovd_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 #else
 #include <cuda_runtime.h>
 #define OVD static __device__ __forceinline__
+#define OVDM __device__ __forceinline__
 #define OVD_CONST __device__ const
 typedef dim3 ovd_dim3;
 #endif
@@ -63,6 +65,8 @@ OVD uint32_t ovd_prmt(uint32_t x, uint32_t y, uint32_t s)
 // CUDA __byte_perm: 3-bit selectors only
 OVD uint32_t ovd_byte_perm(uint32_t x, uint32_t y, uint32_t s) { return ovd_prmt(x, y, s & 0x7777u); }
 OVD int ovd_sad(int a, int b, int c) { return c + (a > b ? a - b : b - a); }
+// low 32 bits of (hi:lo) >> (sh & 31)   (SHF.R)
+OVD uint32_t ovd_funnel_r(uint32_t lo, uint32_t hi, int sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 OVD int ovd_min(int a, int b) { return a < b ? a : b; }
 OVD int ovd_max(int a, int b) { return a > b ? a : b; }
 OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -83,6 +87,7 @@ OVD uint32_t ovd_prmt(uint32_t x, uint32_t y, uint32_t s)
     return r;
 }
 OVD int ovd_sad(int a, int b, int c) { return (int)__sad(a, b, (unsigned)c); }
+OVD uint32_t ovd_funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, (unsigned)sh); }
 OVD int ovd_min(int a, int b) { return min(a, b); }
 OVD int ovd_max(int a, int b) { return max(a, b); }
 OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return min(a, b); }
@@ -160,6 +165,10 @@ __global__ void __launch_bounds__(K::THREADS, K::MIN_BLOCKS) ovd_kernel(const ty
     if (K::PHASES > 7) { __syncthreads(); K::template phase<7>(a, ovd_smem, st, tid, bx, by, bz); }
 }
 
+// K::L1_HEAVY (optional): shared-memory carve-out in percent for kernels whose global loads rely on L1 hits
+template <class K> static inline auto ovd_l1_heavy(int) -> decltype(K::L1_HEAVY, 0) { return K::L1_HEAVY; }
+template <class K> static inline int ovd_l1_heavy(long) { return 0; }
+
 template <class K>
 static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_t smem, cudaStream_t s)
 {
@@ -175,7 +184,9 @@ static inline cudaError_t ovd_launch(const typename K::Args &a, dim3 grid, size_
             if (e != cudaSuccess) return e;
         }
         // ask for the largest shared-memory carve-out so that occupancy is bounded by registers, not by the L1 split
-        if (smem > 0) cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        // (kernels that lean on L1 for their global loads say so with K::L1_HEAVY and keep the default split)
+        if (smem > 0 && !ovd_l1_heavy<K>(0)) cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        else if (ovd_l1_heavy<K>(0)) cudaFuncSetAttribute(ovd_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, ovd_l1_heavy<K>(0));
         __atomic_fetch_or(&configured_mask, bit, __ATOMIC_RELEASE);
     }
     ovd_kernel<K><<<grid, K::THREADS, smem, s>>>(a);
