@@ -17,12 +17,14 @@
 #define OVD static inline
 #define OVDM inline                 /* non-static member functions (functors) */
 #define OVD_CONST static const
+#define OVD_CTAB static const
 struct ovd_dim3 { unsigned x, y, z; ovd_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 #else
 #include <cuda_runtime.h>
 #define OVD static __device__ __forceinline__
 #define OVDM __device__ __forceinline__
 #define OVD_CONST __device__ const
+#define OVD_CTAB __constant__ const       /* small tables indexed (nearly) uniformly across a warp: constant cache */
 typedef dim3 ovd_dim3;
 #endif
 
@@ -143,6 +145,19 @@ OVD void ovd_st16(void *p, ovd_u4 v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#endif
+
+// ---- asynchronous copies global -> shared (cp.async = LDGSTS): 16 bytes, both addresses 16-byte aligned, L1 bypassed ----------
+#ifdef OVGPU_HOST_EMU
+OVD void ovd_cp_async16(void *smem_dst, const void *gsrc) { memcpy(smem_dst, gsrc, 16); }
+OVD void ovd_cp_async_wait_all() {}
+#else
+OVD void ovd_cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+// the calling thread's copies have landed; a barrier afterwards publishes them to the other threads
+OVD void ovd_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif
 
 // ---- kernel entry / emulation driver -----------------------------------------------------------------------

@@ -10,10 +10,10 @@ static_assert(sizeof(McCmdDev) == sizeof(OVGPUMcCmd) && sizeof(McCmdDev) == 32, 
 struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
     int nb_bdof, nb_prof_items, nb_prof;      // BDOF / PROF work items (appended to the item list), PROF table entries
-    int nb_dmvr, nb_small_c;
+    int nb_dmvr, nb_small_c, nb_big;
     DmvrMvDev *d_dmvr, *h_dmvr;               // refined MVs, one per DMVR item (device result + pinned read-back)
     McCmdDev *h_cmds, *d_cmds;
-    McItemDev *h_items, *d_items;             // five regions of max_items entries: plain | BDOF | PROF | DMVR | small chroma
+    McItemDev *h_items, *d_items;             // six regions of max_items entries: plain | BDOF | PROF | DMVR | small chroma | big tiles
     int max_x, max_y;                         // furthest sample any command writes (checked against the picture at run time)
     uint32_t used_refs[2];                    // reference indices the commands name, per list
     ProfInfoDev *h_prof, *d_prof;             // max_cmds / 16 + 1 entries (one per affine CU of >= 16 sub-blocks)
@@ -110,11 +110,11 @@ int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBat
     if (cudaMallocHost(&b->h_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMalloc(&b->d_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMallocHost(&b->h_items, sizeof(McItemDev) * 5 * max_items) != cudaSuccess ||
+        cudaMallocHost(&b->h_items, sizeof(McItemDev) * 6 * max_items) != cudaSuccess ||
         cudaMallocHost(&b->h_dmvr, sizeof(DmvrMvDev) * max_items) != cudaSuccess ||
         cudaMalloc(&b->d_dmvr, sizeof(DmvrMvDev) * max_items) != cudaSuccess ||
         cudaMalloc(&b->d_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
-        cudaMalloc(&b->d_items, sizeof(McItemDev) * 5 * max_items) != cudaSuccess) {
+        cudaMalloc(&b->d_items, sizeof(McItemDev) * 6 * max_items) != cudaSuccess) {
         ovgpu_mc_batch_destroy(b);
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "MC batch buffers: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -162,8 +162,8 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     OVGPU_CUDA_CHECK(ctx, fence_wait(&b->fence));
     // one pass over the commands: validate, split into <=16x16 work items per kernel, note extents and references
     const OVGPUMcCmd *cmds = (const OVGPUMcCmd *)b->h_cmds;
-    McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items, *id = b->h_items + 3 * b->max_items, *is = b->h_items + 4 * b->max_items;
-    int np = 0, nb = 0, nq = 0, nd = 0, ns = 0, max_x = 0, max_y = 0;
+    McItemDev *ip = b->h_items, *ib = b->h_items + b->max_items, *iq = b->h_items + 2 * b->max_items, *id = b->h_items + 3 * b->max_items, *is = b->h_items + 4 * b->max_items, *ig = b->h_items + 5 * b->max_items;
+    int np = 0, nb = 0, nq = 0, nd = 0, ns = 0, ng = 0, max_x = 0, max_y = 0;
     uint32_t used[2] = { 0, 0 };
     {
     HostSection hs_loop(HT_MC_LOOP);
@@ -186,6 +186,14 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
                     McItemDev it = { (uint32_t)i, (uint8_t)ox, (uint8_t)oy, (uint8_t)(w - ox < 16 ? w - ox : 16), (uint8_t)(h - oy < 16 ? h - oy : 16) };
                     ip[np++] = it;
                 }
+        } else if (route == MC_ROUTE_BIG) {
+            const int th = h >= 32 ? 32 : 16;
+            if (ng + (w >> 5) * (h / th) > b->max_items) return ovgpu_set_error(ctx, OVGPU_EINVAL, "MC batch: too many work items");
+            for (int oy = 0; oy < h; oy += th)
+                for (int ox = 0; ox < w; ox += 32) {
+                    McItemDev it = { (uint32_t)i, (uint8_t)ox, (uint8_t)oy, 32, (uint8_t)th };
+                    ig[ng++] = it;
+                }
         } else {
             McItemDev it = { (uint32_t)i, 0, 0, (uint8_t)w, (uint8_t)h };
             if (route == OVGPU_MC_TOOL_BDOF)      { if (nb >= b->max_items) return OVGPU_EINVAL; ib[nb++] = it; }
@@ -194,7 +202,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
             else                                    { if (nq >= b->max_items) return OVGPU_EINVAL; iq[nq++] = it; }
         }
     }
-    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq; b->nb_dmvr = nd; b->nb_small_c = ns;
+    b->nb_cmds = nb_cmds; b->nb_prof = nb_prof; b->nb_items = np; b->nb_bdof = nb; b->nb_prof_items = nq; b->nb_dmvr = nd; b->nb_small_c = ns; b->nb_big = ng;
     b->max_x = max_x; b->max_y = max_y; b->used_refs[0] = used[0]; b->used_refs[1] = used[1];
     }
     HostSection hs_copies(HT_MC_COPIES);
@@ -205,6 +213,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
         if (nq) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 2 * b->max_items, iq, sizeof(McItemDev) * nq, cudaMemcpyHostToDevice, ctx->stream));
         if (nd) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 3 * b->max_items, id, sizeof(McItemDev) * nd, cudaMemcpyHostToDevice, ctx->stream));
         if (ns) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 4 * b->max_items, is, sizeof(McItemDev) * ns, cudaMemcpyHostToDevice, ctx->stream));
+        if (ng) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_items + 5 * b->max_items, ig, sizeof(McItemDev) * ng, cudaMemcpyHostToDevice, ctx->stream));
         if (nb_prof)
             OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_prof, b->h_prof, sizeof(ProfInfoDev) * nb_prof, cudaMemcpyHostToDevice, ctx->stream));
         OVGPU_CUDA_CHECK(ctx, fence_mark(&b->fence, ctx->stream));
@@ -231,7 +240,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
 {
     OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !dst || !refs || !b) return OVGPU_EINVAL;
-    if (!(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr + b->nb_small_c)) return 0;
+    if (!(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr + b->nb_small_c + b->nb_big)) return 0;
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { PlaneView v = plane_view(dst, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
@@ -254,7 +263,12 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
                 return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture size differs (RPR is not supported)");
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = p->plane[c]; a.refs.pitch[l][i][c] = (int)(p->pitch[c] / 2); }
         }
-    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0) + (b->nb_small_c > 0));
+    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0) + (b->nb_small_c > 0) + (b->nb_big > 0));
+    if (b->nb_big) {
+        McK::Args t = a;
+        t.items = b->d_items + 5 * b->max_items; t.nb_items = b->nb_big;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McBigK>(t, dim3(OVGPU_CEIL_DIV(b->nb_big, McBigK::WARPS), 1, 1), McBigK::SMEM_BYTES, ctx->stream));
+    }
     if (b->nb_items)
         OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, ctx->stream));
     if (b->nb_bdof) {

@@ -3,6 +3,9 @@
 #include <stdint.h>
 #include "../../include/ovvc_b200.h"
 #include "mc_tools_kernels.h"
+#include "mc_big_kernels.h"
+
+#define MC_ROUTE_BIG 6
 
 // Which kernel runs a command: plain 4x4 luma-only commands (affine sub-blocks without PROF) take the packed 4x4 path of
 // ProfK (four sub-blocks per warp, refinement off) instead of a whole McK warp each.
@@ -11,6 +14,8 @@ static inline int mc_route(const OVGPUMcCmd *c)
     if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA) return OVGPU_MC_TOOL_PROF;
     // plain chroma-only commands of 8x8 luma samples (the chroma blocks of affine CUs): two per warp in McSmallCK
     if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 3 && c->log2_h == 3 && (c->flags & 3) == OVGPU_MC_CHROMA && !(c->x0 & 3)) return MC_ROUTE_SMALL_C;
+    // plain commands of at least 32 x 16 luma samples: 32 x 32 / 32 x 16 tiles in McBigK
+    if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w >= 5 && c->log2_h >= 4) return MC_ROUTE_BIG;
     return c->tool == OVGPU_MC_TOOL_GPM ? OVGPU_MC_TOOL_PLAIN : c->tool;
 }
 
@@ -66,6 +71,22 @@ static inline int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
         return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 4 && c->log2_h >= 3 && c->log2_h <= 4 &&
                 (c->flags & 3) == 3 && (c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3)) ? 0 : -1;
     return -1;
+}
+
+// 32 x 32 (32 x 16 for 16-row commands) tiles of the commands routed to McBigK
+static inline int mc_build_big_items(McItemDev *items, const OVGPUMcCmd *cmds, int n)
+{
+    int k = 0;
+    for (int i = 0; i < n; i++) {
+        if (mc_route(&cmds[i]) != MC_ROUTE_BIG) continue;
+        const int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h, th = h >= 32 ? 32 : 16;
+        for (int oy = 0; oy < h; oy += th)
+            for (int ox = 0; ox < w; ox += 32) {
+                if (items) { items[k].cmd = (uint32_t)i; items[k].ox = (uint8_t)ox; items[k].oy = (uint8_t)oy; items[k].w = 32; items[k].h = (uint8_t)th; }
+                k++;
+            }
+    }
+    return k;
 }
 
 static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n)

@@ -149,6 +149,14 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = refs->plane[l][i][c]; a.refs.pitch[l][i][c] = refs->stride[l][i][c]; }
         }
     if (n_items) ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
+    const int n_big = mc_build_big_items(NULL, cmds, nb_cmds);
+    if (n_big) {
+        std::vector<McItemDev> big(n_big);
+        mc_build_big_items(big.data(), cmds, nb_cmds);
+        McK::Args t = a;
+        t.items = big.data(); t.nb_items = n_big;
+        ovd_emulate<McBigK>(t, ovd_dim3((n_big + McBigK::WARPS - 1) / McBigK::WARPS, 1, 1), McBigK::SMEM_BYTES);
+    }
     if (n_bdof) {
         McK::Args t = a;
         t.items = items.data() + n_items; t.nb_items = n_bdof;
@@ -170,7 +178,7 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
         ovd_emulate<DmvrK>(t, ovd_dim3((n_dmvr + DmvrK::WARPS - 1) / DmvrK::WARPS, 1, 1), DmvrK::SMEM_BYTES);
         if (dmvr_out) memcpy(dmvr_out, dm.data(), sizeof(DmvrMvDev) * n_dmvr);
     }
-    return n_items + n_bdof + n_prof + n_dmvr + n_sc;
+    return n_items + n_bdof + n_prof + n_dmvr + n_sc + n_big;
 }
 
 int emu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *d, int bitdepth)
