@@ -303,6 +303,7 @@ def main():
     ap.add_argument("--e2e-share", type=int, default=1, help="e2e contexts (host threads) that share one stream")
     ap.add_argument("--e2e-sets", type=int, default=2, help="picture sets in flight in the e2e leg (1 or 2)")
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
+    ap.add_argument("--e2e-dl-streams", type=int, default=0, help="1: the output copy of a picture runs on a stream of its own (measured: no gain)")
     args = ap.parse_args()
     w, h = SIZES[args.size]
 
@@ -446,6 +447,12 @@ def main():
     real_streams = [torch.cuda.Stream() for _ in range((n_sets * n_ctx + share - 1) // share)]
     e_streams = [real_streams[j // share] for j in range(n_sets * n_ctx)]
     e_ctx = [api.Ctx(local, st.cuda_stream) for st in e_streams]
+    # the output copy of a picture runs on a stream of its own (like a decoder's output stage): the PCIe link out is as busy as the
+    # SMs (25 MB per 4K picture as 16-bit samples), and queued on the picture's stream it would hold back the uploads of the next
+    # picture that context handles
+    dl_streams = [torch.cuda.Stream() for _ in e_streams] if args.e2e_dl_streams else e_streams
+    dl_ctx = [api.Ctx(local, st.cuda_stream) for st in dl_streams] if args.e2e_dl_streams else e_ctx
+    dl_done = [[None] * P for _ in range(n_sets)]
     e_dev = [dev] + [[make_dev(api, ctx, p, w, h) for p in pics] for _ in range(n_sets - 1)]
     ctx.sync()
     pinned_out = [[[torch.empty((hh, ww), dtype=torch.uint16).pin_memory() for (hh, ww) in ((h, w), (h // 2, w // 2), (h // 2, w // 2))]
@@ -470,6 +477,7 @@ def main():
             e = torch.cuda.Event(enable_timing=True)
             e.record(st)
             timeline.append((e2e_no[0], i, name, e, time.perf_counter()))
+        dc, dst_ = dl_ctx[half * n_ctx + t], dl_streams[half * n_ctx + t]
         for i in range(t, len(dev), n_ctx):
             p, d = pics[i], e_dev[half][i]
             tt = [time.perf_counter()]
@@ -482,6 +490,8 @@ def main():
             lmcs.reshape(d["rec"], forward=False, ctx=c)
             d["dbf"].run(d["rec"], ctx=c)
             d["sao"].run(d["mid"], d["rec"], ctx=c)
+            if args.e2e_dl_streams and dl_done[half][i] is not None:
+                st.wait_event(dl_done[half][i])     # (on the device) ALF rewrites the planes the previous output copy of this set read
             d["alf"].run(d["dst"], d["mid"], ctx=c); tt.append(time.perf_counter())
             if host_prof is not None:
                 host_prof.append([1e3 * (b - a) for a, b in zip(tt, tt[1:])])
@@ -489,8 +499,14 @@ def main():
             ev.record(st)                           # the picture is final on the device: what the reference hand-off needs
             evs.append(ev)
             if tl: mark("k1", i)
-            api._check(c.h, api.lib().ovgpu_picture_download(c.h, d["dst"].p, *api._host_planes(np_out[half][i])), "download")
-            if tl: mark("d2h1", i)
+            dst_.wait_event(ev)
+            api._check(dc.h, api.lib().ovgpu_picture_download(dc.h, d["dst"].p, *api._host_planes(np_out[half][i])), "download")
+            evd = torch.cuda.Event()
+            evd.record(dst_)
+            dl_done[half][i] = evd
+            if tl:
+                e = torch.cuda.Event(enable_timing=True); e.record(dst_)
+                timeline.append((e2e_no[0], i, "d2h1", e, time.perf_counter()))
         return evs
 
     from concurrent.futures import ThreadPoolExecutor
@@ -583,7 +599,7 @@ def main():
                              "achieved_gbs": alg[s] / (avg * 1e-3) / 1e9, "frac": alg[s] / (avg * 1e-3) / 1e9 / peak,
                              "traffic": ncu_traffic(s)[0]}
         top = max(stages, key=lambda s: stages[s]["avg_launch_ms"])
-        h2d = sum(p["cmds"].nbytes + 8 * api.mc_nb_items(p["cmds"]) + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["isp_words"].nbytes + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
+        h2d = sum(p["cmds"].nbytes + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["isp_words"].nbytes + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",

@@ -231,6 +231,12 @@ int  ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_p
 /* Refined MVs of the DMVR commands of the last ovgpu_mc_picture call on this batch, in command order: D2H copy into
  * `out` (up to max entries) + stream sync; returns the number of DMVR commands or a negative error. */
 int  ovgpu_mc_batch_read_dmvr(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUDmvrMv *out, int max);
+/* The commands are validated, routed and split into work items ON THE DEVICE (three small kernels behind the commit; the host
+ * only counts items to size the launches and never waits).  What that walk refuses -- a malformed command, more work items
+ * than the batch holds, commands outside the picture, a reference the caller did not supply -- makes the batch's kernels do
+ * nothing and is reported, as OVGPU_EINVAL with the message the old host-side walk gave, by this call (blocking: it waits
+ * for the batch's last run) and by the next ovgpu_mc_picture / ovgpu_mc_batch_read_dmvr on the batch. */
+int  ovgpu_mc_batch_status(OVGPUCtx *ctx, OVGPUMcBatch *b);
 /* writes the prediction of every command into dst; lmcs may be NULL (no forward reshape). Asynchronous. */
 int  ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, const OVGPUMcBatch *b,
                       const OVGPULmcs *lmcs);

@@ -336,6 +336,10 @@ class McBatch:
         assert ret == n, "batch holds %d DMVR commands, asked for %d" % (ret, n)
         return out
 
+    def status(self, ctx=None):
+        """ovgpu_mc_batch_status: raises what the device-side walk of the last run refused (blocking)"""
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_status((ctx or self.ctx).h, self.p), "mc_batch_status")
+
     def commit(self, nb_cmds, nb_prof=0, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_commit((ctx or self.ctx).h, self.p, int(nb_cmds), int(nb_prof)), "mc_batch_commit")
 

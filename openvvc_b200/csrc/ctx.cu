@@ -263,6 +263,29 @@ int ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const d
 {
     OVGPU_DEVICE_GUARD(ctx);
     if (!ctx || !pic || !data || !linesize) return OVGPU_EINVAL;
+    // OVGPU_DOWNLOAD_SM=1 (measurement knob): pinned (page-locked, hence device-mapped) destinations are written by an SM kernel
+    // straight over PCIe instead of by the copy engine.  Measured on the 4K benchmark: 960 against 1100 pictures/s end to end -- the
+    // kernel holds SM slots while it waits for the link -- so the DMA copy stays the default.
+    {
+        CopyPlanes a;
+        static const int use_sm = getenv("OVGPU_DOWNLOAD_SM") != NULL;
+        int mapped = use_sm;
+        for (int c = 0; c < 3 && mapped; c++) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, data[c]) != cudaSuccess) { cudaGetLastError(); mapped = 0; break; }
+            if (at.type != cudaMemoryTypeHost || !at.devicePointer) { mapped = 0; break; }
+            a.src[c] = (const uint8_t *)pic->plane[c]; a.dst[c] = (uint8_t *)at.devicePointer;
+            a.src_pitch[c] = (uint32_t)pic->pitch[c]; a.dst_pitch[c] = (uint32_t)linesize[c];
+            a.row_bytes[c] = (uint32_t)((c ? pic->width >> 1 : pic->width) * 2); a.rows[c] = (uint32_t)(c ? pic->height >> 1 : pic->height);
+            mapped &= !(((uintptr_t)a.src[c] | (uintptr_t)a.dst[c] | a.src_pitch[c] | a.dst_pitch[c] | a.row_bytes[c]) & 7) && linesize[c] <= 0xffffffffu;
+        }
+        if (mapped) {
+            ovgpu_copy_planes_kernel<<<dim3(64, 3, 1), 256, 0, ctx->stream>>>(a);
+            OVGPU_CUDA_CHECK(ctx, cudaGetLastError());
+            ctx->launches++;
+            return 0;
+        }
+    }
     for (int c = 0; c < 3; c++) {
         int w = c ? pic->width >> 1 : pic->width, h = c ? pic->height >> 1 : pic->height;
         if (linesize[c] == (size_t)w * 2 && pic->pitch[c] == (size_t)w * 2)      // contiguous on both sides: one flat copy

@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <vector>
 #define OVD static inline
+#define OVHD static inline          /* helpers shared by host code and kernels */
 #define OVDM inline                 /* non-static member functions (functors) */
 #define OVD_CONST static const
 #define OVD_CTAB static const
@@ -22,6 +23,7 @@ struct ovd_dim3 { unsigned x, y, z; ovd_dim3(unsigned a = 1, unsigned b = 1, uns
 #else
 #include <cuda_runtime.h>
 #define OVD static __device__ __forceinline__
+#define OVHD static __host__ __device__ __forceinline__
 #define OVDM __device__ __forceinline__
 #define OVD_CONST __device__ const
 #define OVD_CTAB __constant__ const       /* small tables indexed (nearly) uniformly across a warp: constant cache */
@@ -145,6 +147,17 @@ OVD void ovd_st16(void *p, ovd_u4 v)
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#endif
+
+// ---- global atomics (kernels that build work lists on the device) -------------------------------------------------------------
+#ifdef OVGPU_HOST_EMU
+OVD void ovd_atomic_max(int *p, int v) { if (v > *p) *p = v; }
+OVD void ovd_atomic_or(uint32_t *p, uint32_t v) { *p |= v; }
+OVD void ovd_threadfence_system() {}
+#else
+OVD void ovd_threadfence_system() { __threadfence_system(); }      // orders stores to mapped host memory
+OVD void ovd_atomic_max(int *p, int v) { atomicMax(p, v); }
+OVD void ovd_atomic_or(uint32_t *p, uint32_t v) { atomicOr(p, v); }
 #endif
 
 // ---- asynchronous copies global -> shared (cp.async = LDGSTS): 16 bytes, both addresses 16-byte aligned, L1 bypassed ----------

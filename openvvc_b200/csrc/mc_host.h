@@ -1,4 +1,6 @@
-// mc_host.h -- host-side preparation of the MC work list, shared by mc.cu and tests/emu.
+// mc_host.h -- routing of MC commands to kernels and the work lists: built ON THE DEVICE from the uploaded commands (McPrep*K
+// below; the host only copies the commands and reads back six counters), with a plain host restatement that tests/emu checks
+// the kernels against.
 #pragma once
 #include <stdint.h>
 #include "../../include/ovvc_b200.h"
@@ -9,7 +11,7 @@
 
 // Which kernel runs a command: plain 4x4 luma-only commands (affine sub-blocks without PROF) take the packed 4x4 path of
 // ProfK (four sub-blocks per warp, refinement off) instead of a whole McK warp each.
-static inline int mc_route(const OVGPUMcCmd *c)
+OVHD int mc_route(const OVGPUMcCmd *c)
 {
     if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA) return OVGPU_MC_TOOL_PROF;
     // plain chroma-only commands of 8x8 luma samples (the chroma blocks of affine CUs): two per warp in McSmallCK
@@ -52,7 +54,7 @@ static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, 
 }
 
 // well-formedness of one command; nb_prof = entries of the PROF table
-static inline int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
+OVHD int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
 {
     if (c->log2_w < 2 || c->log2_w > 7 || c->log2_h < 2 || c->log2_h > 7 || c->inter_dir < 1 || c->inter_dir > 3 ||
         c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->x0 < 0 || c->y0 < 0)
@@ -160,5 +162,250 @@ struct LmcsReshapeK {
             o[i] = (uint32_t)a.lut[in[i] & msk] | ((uint32_t)a.lut[(in[i] >> 16) & msk] << 16);
         ovd_u4 r; r.x = o[0]; r.y = o[1]; r.z = o[2]; r.w = o[3];
         ovd_st16(p, r);
+    }
+};
+
+// ==================================================================================================================
+// Work lists built on the device.  The host used to walk the picture's commands (validate, route, split into work items:
+// 0.87 ms per 4K picture and host thread, the largest single piece of host work of the end-to-end path); now it copies the
+// commands and three small kernels do the walk:
+//   McPrepCountK    one thread per command: validate, route, number of work items; per block and region the item count,
+//                   picture-wide the furthest sample written, the references named, the first malformed command
+//   McPrepScanK     one CTA: exclusive scan of the block counts per region -> block offsets, totals (the six counters the
+//                   host reads back to size the launches), overflow of a region's capacity
+//   McPrepScatterK  one thread per command again: its items written at block offset + offset inside the block -- so every
+//                   region lists its items in COMMAND ORDER (the refined MVs of DMVR items are returned in that order)
+// Regions of the item array: 0 plain (<=16x16 blocks, GPM), 1 BDOF, 2 PROF / plain 4x4, 3 DMVR, 4 small chroma, 5 big tiles.
+#define MC_NB_REGIONS 6
+// region and number of work items of a (well-formed) command
+OVHD int mc_region_items(const OVGPUMcCmd *c, int *nb)
+{
+    const int route = mc_route(c), w = 1 << c->log2_w, h = 1 << c->log2_h;
+    *nb = 1;
+    if (route == OVGPU_MC_TOOL_PLAIN) { *nb = ((w + 15) >> 4) * ((h + 15) >> 4); return 0; }
+    if (route == MC_ROUTE_BIG) { *nb = (w >> 5) * (h >= 32 ? h >> 5 : 1); return 5; }
+    return route == OVGPU_MC_TOOL_BDOF ? 1 : route == OVGPU_MC_TOOL_DMVR ? 3 : route == MC_ROUTE_SMALL_C ? 4 : 2;
+}
+
+struct McPrepInfo {                  // device result, copied to pinned host memory
+    int32_t count[MC_NB_REGIONS];    // work items per region
+    int32_t bad_rev;                 // nb_cmds - index of the first malformed command (0: every command is well-formed)
+    int32_t max_x, max_y;            // furthest sample any command writes
+    uint32_t used_refs[2];           // reference indices named, per list
+    int32_t overflow;                // 1 + a region whose items did not fit (0: none)
+    int32_t seq;                     // (unused)
+    // written by McGuardK when the batch runs on a picture:
+    int32_t limit[MC_NB_REGIONS];    // items the MC kernels may process: count[], or 0 everywhere when status != 0
+    int32_t status;                  // 0 ok, 1 malformed command (bad_rev), 2 too many items, 3 commands outside the picture, 4 reference missing
+    int32_t status_arg;              // the command / region / list * 16 + index concerned
+};
+
+// Number of work items per region as the HOST counts them, to size the launches without waiting for the device: no validation,
+// no lists, three byte loads and a table look-up per command (fields masked so that garbage cannot index out of range; the
+// device-side walk is the one that validates, and the kernels stop at ITS counts).
+struct McCountLut {                  // (tool, log2_w, log2_h, flags & 3, x0 & 3 != 0) -> region << 8 | items
+    uint16_t v[8 * 8 * 8 * 4 * 2];
+    McCountLut()
+    {
+        for (int key = 0; key < 8 * 8 * 8 * 4 * 2; key++) {
+            OVGPUMcCmd c;
+            memset(&c, 0, sizeof(c));
+            c.tool = (uint8_t)(key >> 9); c.log2_w = (key >> 6) & 7; c.log2_h = (key >> 3) & 7; c.flags = (key >> 1) & 3; c.x0 = (int16_t)(key & 1);
+            int k;
+            const int r = mc_region_items(&c, &k);
+            v[key] = (uint16_t)((r << 8) | k);
+        }
+    }
+};
+static inline void mc_count_regions(const OVGPUMcCmd *cmds, int n, int cap, int cnt[MC_NB_REGIONS])
+{
+    static const McCountLut lut;
+    long long c64[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (int i = 0; i < n; i++) {
+        const OVGPUMcCmd *c = &cmds[i];
+        const unsigned key = ((c->tool & 7u) << 9) | ((c->log2_w & 7u) << 6) | ((c->log2_h & 7u) << 3) | ((c->flags & 3u) << 1) | ((c->x0 & 3) != 0);
+        const unsigned e = lut.v[key];
+        c64[e >> 8] += e & 0xff;
+    }
+    for (int r = 0; r < MC_NB_REGIONS; r++) cnt[r] = (int)(c64[r] < cap ? c64[r] : cap);
+}
+
+// One warp: the walk's findings against the picture the batch is about to run on -> limit[] / status
+struct McGuardArgs { McPrepInfo *info; int pic_w, pic_h; uint32_t present[2]; McPrepInfo *info_host; };   // info_host: mapped pinned copy (or NULL)
+struct McGuardK {
+    static const int THREADS = 32, MIN_BLOCKS = 1, PHASES = 1;
+    typedef McGuardArgs Args;
+    struct State { int dummy; };
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)smem; (void)st; (void)bx; (void)by; (void)bz;
+        if (tid) return;
+        McPrepInfo *f = a.info;
+        int status = 0, arg = 0;
+        if (f->bad_rev) { status = 1; arg = f->bad_rev; }
+        else if (f->overflow) { status = 2; arg = f->overflow - 1; }
+        else if (f->max_x > a.pic_w || f->max_y > a.pic_h) status = 3;
+        else
+            for (int l = 0; l < 2 && !status; l++) {
+                const uint32_t miss = f->used_refs[l] & ~a.present[l];
+                if (miss) { status = 4; arg = l * 16 + ovd_floor_log2(miss & (0u - miss)); }
+            }
+        for (int r = 0; r < MC_NB_REGIONS; r++) f->limit[r] = status ? 0 : f->count[r];
+        f->status = status; f->status_arg = arg;
+        if (a.info_host) *a.info_host = *f;                // the verdict goes to the host as a store over PCIe, not as a DMA copy
+    }
+};
+
+// The commands are read where the recorder wrote them -- PINNED HOST memory, through the mapping every cudaMallocHost buffer has
+// (zero copy) -- and McPrepCountK leaves the device copy the MC kernels use; the counters go back the same way (a store to mapped
+// No copy engine is involved: a DMA copy of the commands would queue behind the megabytes of coefficient and picture copies of
+// the other pictures in flight.  The HOST NEVER WAITS for the walk: it sizes the launches from its own cheap count of the commands
+// (mc_count_regions) and the kernels stop at the walk's counts; what the walk refuses (a malformed command ...) zeroes those
+// counts (McGuardK) and is reported by ovgpu_mc_batch_status / the next call that synchronises with the batch.
+struct McPrepArgs {
+    const McCmdDev *src;             // commands as recorded (mapped pinned host memory, or plain memory under emulation)
+    McCmdDev *cmds;                  // device copy written by McPrepCountK (== src: none needed)
+    const uint32_t *prof_src;        // PROF table as recorded / its device copy, in 32-bit words
+    uint32_t *prof;
+    int nb_cmds, nb_prof, nb_blocks, max_items;
+    int32_t *block_sum;              // [region][block] item counts, then (after the scan) exclusive offsets
+    McItemDev *items;                // MC_NB_REGIONS regions of max_items entries
+    McPrepInfo *info;                // device
+};
+
+struct McPrepCountK {
+    static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 2;
+    static const int SMEM_BYTES = THREADS * 6 * 4;
+    typedef McPrepArgs Args;
+    struct State { int dummy; };
+    // per thread: region (-1: no command / malformed), items, extents, references
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        int *s_reg = (int *)smem, *s_cnt = s_reg + THREADS, *s_mx = s_cnt + THREADS, *s_my = s_mx + THREADS;
+        uint32_t *s_u0 = (uint32_t *)(s_my + THREADS), *s_u1 = s_u0 + THREADS;
+        if (P == 0) {
+            const int i = bx * THREADS + tid;
+            int reg = -1, cnt = 0, mx = 0, my = 0;
+            uint32_t u0 = 0, u1 = 0;
+            if (a.prof != a.prof_src)        // PROF table: 32 words per entry
+                for (int j = i; j < a.nb_prof * 32; j += a.nb_blocks * THREADS) a.prof[j] = a.prof_src[j];
+            if (i < a.nb_cmds) {
+                const McCmdDev cd = a.src[i];
+                if (a.cmds != a.src) a.cmds[i] = cd;
+                const OVGPUMcCmd *c = (const OVGPUMcCmd *)&cd;
+                if (mc_check_cmd(c, a.nb_prof)) ovd_atomic_max(&a.info->bad_rev, a.nb_cmds - i);
+                else {
+                    reg = mc_region_items(c, &cnt);
+                    mx = c->x0 + (1 << c->log2_w); my = c->y0 + (1 << c->log2_h);
+                    if (c->tool == OVGPU_MC_TOOL_GPM) { if ((c->aux >> 8) & 1) u1 |= 1u << c->ref_idx0; else u0 |= 1u << c->ref_idx0;
+                                                        if ((c->aux >> 9) & 1) u1 |= 1u << c->ref_idx1; else u0 |= 1u << c->ref_idx1; }
+                    else { if (c->inter_dir & 1) u0 |= 1u << c->ref_idx0; if (c->inter_dir & 2) u1 |= 1u << c->ref_idx1; }
+                }
+            }
+            s_reg[tid] = reg; s_cnt[tid] = cnt; s_mx[tid] = mx; s_my[tid] = my; s_u0[tid] = u0; s_u1[tid] = u1;
+            return;
+        }
+        if (tid < MC_NB_REGIONS) {
+            int sum = 0;
+            for (int t = 0; t < THREADS; t++) if (s_reg[t] == tid) sum += s_cnt[t];
+            a.block_sum[tid * a.nb_blocks + bx] = sum;
+        } else if (tid == 32) {
+            int mx = 0, my = 0;
+            uint32_t u0 = 0, u1 = 0;
+            for (int t = 0; t < THREADS; t++) { mx = ovd_max(mx, s_mx[t]); my = ovd_max(my, s_my[t]); u0 |= s_u0[t]; u1 |= s_u1[t]; }
+            ovd_atomic_max(&a.info->max_x, mx); ovd_atomic_max(&a.info->max_y, my);
+            if (u0) ovd_atomic_or(&a.info->used_refs[0], u0);
+            if (u1) ovd_atomic_or(&a.info->used_refs[1], u1);
+        }
+    }
+};
+
+struct McPrepScanK {
+    static const int THREADS = 256, MIN_BLOCKS = 1, PHASES = 3;
+    static const int SMEM_BYTES = MC_NB_REGIONS * THREADS * 4;
+    typedef McPrepArgs Args;
+    struct State { int dummy; };
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)bx; (void)by; (void)bz;
+        int *part = (int *)smem;                                  // [region][thread]: sum of the thread's chunk of blocks, then its offset
+        const int chunk = (a.nb_blocks + THREADS - 1) / THREADS, b0 = tid * chunk, b1 = ovd_min(b0 + chunk, a.nb_blocks);
+        if (P == 0) {
+            for (int r = 0; r < MC_NB_REGIONS; r++) {
+                int s = 0;
+                for (int b = b0; b < b1; b++) s += a.block_sum[r * a.nb_blocks + b];
+                part[r * THREADS + tid] = s;
+            }
+            return;
+        }
+        if (P == 1) {
+            if (tid < MC_NB_REGIONS) {
+                int acc = 0;
+                for (int t = 0; t < THREADS; t++) { const int v = part[tid * THREADS + t]; part[tid * THREADS + t] = acc; acc += v; }
+                a.info->count[tid] = acc;
+                if (acc > a.max_items) ovd_atomic_max(&a.info->overflow, tid + 1);
+            }
+            return;
+        }
+        for (int r = 0; r < MC_NB_REGIONS; r++) {
+            int acc = part[r * THREADS + tid];
+            for (int b = b0; b < b1; b++) { const int v = a.block_sum[r * a.nb_blocks + b]; a.block_sum[r * a.nb_blocks + b] = acc; acc += v; }
+        }
+
+    }
+};
+
+struct McPrepScatterK {
+    static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 3;
+    static const int SMEM_BYTES = THREADS * 3 * 4;
+    typedef McPrepArgs Args;
+    struct State { int dummy; };
+    template <int P>
+    OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
+    {
+        (void)st; (void)by; (void)bz;
+        int *s_reg = (int *)smem, *s_cnt = s_reg + THREADS, *s_off = s_cnt + THREADS;
+        const int i = bx * THREADS + tid;
+        if (P == 0) {
+            int reg = -1, cnt = 0;
+            if (i < a.nb_cmds) {
+                const McCmdDev cd = a.cmds[i];
+                const OVGPUMcCmd *c = (const OVGPUMcCmd *)&cd;
+                if (!mc_check_cmd(c, a.nb_prof)) reg = mc_region_items(c, &cnt);
+            }
+            s_reg[tid] = reg; s_cnt[tid] = cnt;
+            return;
+        }
+        if (P == 1) {
+            if (tid < MC_NB_REGIONS) {
+                int acc = a.block_sum[tid * a.nb_blocks + bx];
+                for (int t = 0; t < THREADS; t++) if (s_reg[t] == tid) { s_off[t] = acc; acc += s_cnt[t]; }
+            }
+            return;
+        }
+        const int reg = s_reg[tid], cnt = s_cnt[tid], off = reg >= 0 ? s_off[tid] : 0;
+        if (reg < 0 || off + cnt > a.max_items) return;           // (an overflowing region is reported by McPrepScanK)
+        McItemDev *it = a.items + (size_t)reg * a.max_items + off;
+        const McCmdDev cd = a.cmds[i];
+        const int w = 1 << cd.log2_w, h = 1 << cd.log2_h;
+        if (reg == 0 || reg == 5) {
+            const int tw = reg ? 32 : 16, th = reg ? (h >= 32 ? 32 : 16) : 16;
+            int k = 0;
+            for (int oy = 0; oy < h; oy += th)
+                for (int ox = 0; ox < w; ox += tw, k++) {
+                    McItemDev v;
+                    v.cmd = (uint32_t)i; v.ox = (uint8_t)ox; v.oy = (uint8_t)oy;
+                    v.w = (uint8_t)(w - ox < tw ? w - ox : tw); v.h = (uint8_t)(h - oy < th ? h - oy : th);
+                    it[k] = v;
+                }
+        } else {
+            McItemDev v;
+            v.cmd = (uint32_t)i; v.ox = v.oy = 0; v.w = (uint8_t)w; v.h = (uint8_t)h;
+            it[0] = v;
+        }
     }
 };

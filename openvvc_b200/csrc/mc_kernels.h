@@ -100,11 +100,16 @@ struct McK {
         int pic_w, pic_h, bitdepth;
         const McCmdDev *cmds;
         const McItemDev *items;
-        int nb_items;
+        int nb_items;                    // items the launch was sized for (the host's count)
+        const int32_t *limit;            // device: items the list really holds (the device-side walk's count; NULL: nb_items)
         const uint16_t *lmcs_fwd;        // device LUT or NULL
         McRefsDev refs;
     };
     struct State { int dummy; };
+
+    // The lists are built on the device (mc_host.h); the host sizes the launch from its own count of the commands and the kernels
+    // stop at the list's real length, which is 0 when the walk found a malformed command or the picture / references do not fit.
+    OVD int nb_items(const Args &a) { return a.limit ? ovd_min(a.nb_items, *a.limit) : a.nb_items; }
 
     // everything a phase needs to know about the warp's item
     struct Item {
@@ -121,7 +126,7 @@ struct McK {
     OVD Item load_item(const Args &a, int item_idx)
     {
         Item it;
-        it.valid = item_idx < a.nb_items;
+        it.valid = item_idx < nb_items(a);
         if (!it.valid) return it;
         const McItemDev im = a.items[item_idx];
         const McCmdDev c = a.cmds[im.cmd];

@@ -154,8 +154,8 @@ struct BdofK {
         const int item = bx * WARPS + warp;
 
         if (P == 0) {
-            if (lane == 0) sit[0] = item < a.nb_items;
-            if (item >= a.nb_items) return;
+            if (lane == 0) sit[0] = item < McK::nb_items(a);
+            if (item >= McK::nb_items(a)) return;
             const McCmdDev c = a.cmds[a.items[item].cmd];
             const int w = 1 << c.log2_w, h = 1 << c.log2_h, hpel = (c.flags & MC_HPEL_AMVR) != 0;
 #pragma unroll
@@ -260,8 +260,8 @@ struct ProfK {
 
         if (P == 0) {
             const int r = (lane >> 2) & 1, cc = lane & 3;
-            if ((lane & 7) == 0) si[0] = item < a.nb_items;
-            if (item >= a.nb_items) return;
+            if ((lane & 7) == 0) si[0] = item < McK::nb_items(a);
+            if (item >= McK::nb_items(a)) return;
             const McCmdDev c = a.cmds[a.items[item].cmd];
             const int used = (c.inter_dir >> r) & 1;
             int mvx = r ? c.mv1_x : c.mv0_x, mvy = r ? c.mv1_y : c.mv0_y;
@@ -385,8 +385,8 @@ struct McSmallCK {
 
         if (P == 0) {
             const int comp = (lane >> 3) & 1, r = (lane >> 2) & 1, cc = lane & 3;
-            if ((lane & 15) == 0) si[0] = item < a.nb_items;
-            if (item >= a.nb_items) return;
+            if ((lane & 15) == 0) si[0] = item < McK::nb_items(a);
+            if (item >= McK::nb_items(a)) return;
             const McCmdDev c = a.cmds[a.items[item].cmd];
             const int used = (c.inter_dir >> r) & 1;
             int mvx = r ? c.mv1_x : c.mv0_x, mvy = r ? c.mv1_y : c.mv0_y;
@@ -508,8 +508,8 @@ struct DmvrK {
         const int cw = a.pic_w >> 1, ch = a.pic_h >> 1;
 
         if (P == 0) {
-            if (lane == 0) sit[0] = item < a.nb_items;
-            if (item >= a.nb_items) return;
+            if (lane == 0) sit[0] = item < McK::nb_items(a);
+            if (item >= McK::nb_items(a)) return;
             const McCmdDev c = a.cmds[a.items[item].cmd];
             const int w = 1 << c.log2_w, h = 1 << c.log2_h, wc = w >> 1, hc = h >> 1;
 #pragma unroll

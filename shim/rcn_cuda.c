@@ -877,6 +877,7 @@ static void rec_end_picture(ShimRec *r)
     /* host-readable planes for ovdec_receive_picture (dectest.c:393-406 writes frame->data) */
     if (!r->failed) SHIM_CHECK(r, ovgpu_picture_download(x, final, (void *const *)r->frame->data, r->frame->linesize));
     SHIM_CHECK(r, ovgpu_ctx_sync(x));
+    if (r->nb_mc) SHIM_CHECK(r, ovgpu_mc_batch_status(x, r->mc));       /* the command walk runs on the device: its verdict */
     patch_dmvr(r);
     OVPicture *pic;
     pthread_mutex_lock(&g.mtx);

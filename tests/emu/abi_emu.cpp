@@ -65,6 +65,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *c, OVGPUMcBatch *b, int nb, int nb_prof)
     b->nb = nb; b->nb_prof = nb_prof;
     return 0;
 }
+int ovgpu_mc_batch_status(OVGPUCtx *, OVGPUMcBatch *) { return 0; }      // (this emulation validates in the commit)
 int ovgpu_mc_batch_read_dmvr(OVGPUCtx *, OVGPUMcBatch *b, OVGPUDmvrMv *out, int max)
 {
     for (int i = 0; i < b->nb_dmvr && i < max; i++) out[i] = b->dmvr[i];

@@ -2,6 +2,7 @@
 // on the CPU through the serial CTA emulation of csrc/dev.h (-DOVGPU_HOST_EMU), so kernel logic can be
 // checked against the oracle on a machine without a GPU.  Never linked into libovvc_b200.so.
 #include <vector>
+#include <algorithm>
 #include "../../openvvc_b200/csrc/alf_host.h"
 #include "../../openvvc_b200/csrc/sao_kernels.h"
 #include "../../openvvc_b200/csrc/mc_host.h"
@@ -126,55 +127,85 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
                    const EmuMcRefs *refs, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd,
                    const OVGPUProfInfo *prof, int nb_prof, OVGPUDmvrMv *dmvr_out)
 {
-    for (int i = 0; i < nb_cmds; i++) if (mc_check_cmd(&cmds[i], nb_prof)) return -(i + 1);
-    int n_dmvr = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_DMVR);
-    int n_items = mc_count_items(cmds, nb_cmds), n_bdof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_BDOF),
-        n_prof = mc_count_tool_items(cmds, nb_cmds, OVGPU_MC_TOOL_PROF), n_sc = mc_count_tool_items(cmds, nb_cmds, MC_ROUTE_SMALL_C);
-    std::vector<McItemDev> items(n_items + n_bdof + n_prof + n_dmvr + n_sc + 1);
+    // the work lists come from the product's device-side construction (McPrep*K), checked here against the host restatement
+    const int max_items = mc_count_items(cmds, nb_cmds) + nb_cmds + 1;
+    std::vector<McItemDev> items((size_t)MC_NB_REGIONS * max_items);
+    McPrepInfo info;
+    memset(&info, 0, sizeof(info));
+    {
+        const int nblk = (nb_cmds + McPrepCountK::THREADS - 1) / McPrepCountK::THREADS;
+        std::vector<int32_t> bsum((size_t)MC_NB_REGIONS * (nblk + 1));
+        McPrepArgs pa = { (const McCmdDev *)cmds, (McCmdDev *)cmds, NULL, NULL, nb_cmds, nb_prof, nblk, max_items, bsum.data(), items.data(), &info };
+        if (nb_cmds) {
+            ovd_emulate<McPrepCountK>(pa, ovd_dim3(nblk, 1, 1), McPrepCountK::SMEM_BYTES);
+            ovd_emulate<McPrepScanK>(pa, ovd_dim3(1, 1, 1), McPrepScanK::SMEM_BYTES);
+            ovd_emulate<McPrepScatterK>(pa, ovd_dim3(nblk, 1, 1), McPrepScatterK::SMEM_BYTES);
+        }
+    }
+    for (int i = 0; i < nb_cmds; i++)
+        if (mc_check_cmd(&cmds[i], nb_prof)) return info.bad_rev == nb_cmds - i ? -(i + 1) : -1000000;      // first malformed command, both ways
+    if (info.bad_rev || info.overflow) return -1000001;
+    {   // the host's cheap count sizes the launches; the guard kernel publishes the limits the MC kernels stop at
+        int cnt[MC_NB_REGIONS];
+        mc_count_regions(cmds, nb_cmds, max_items, cnt);
+        for (int r = 0; r < MC_NB_REGIONS; r++) if (cnt[r] != info.count[r]) return -1000020 - r;
+        McGuardArgs ga = { &info, w, h, { 0, 0 }, NULL };
+        for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) if (refs->plane[l][i][0]) ga.present[l] |= 1u << i;
+        ovd_emulate<McGuardK>(ga, ovd_dim3(1, 1, 1), 0);
+        if (info.status) return -1000030 - info.status;
+    }
+    const int n_items = info.count[0], n_bdof = info.count[1], n_prof = info.count[2], n_dmvr = info.count[3], n_sc = info.count[4], n_big = info.count[5];
+    {
+        std::vector<McItemDev> want(max_items);
+        const int routes[MC_NB_REGIONS] = { OVGPU_MC_TOOL_PLAIN, OVGPU_MC_TOOL_BDOF, OVGPU_MC_TOOL_PROF, OVGPU_MC_TOOL_DMVR, MC_ROUTE_SMALL_C, MC_ROUTE_BIG };
+        for (int r = 0; r < MC_NB_REGIONS; r++) {
+            const int n = r == 0 ? mc_build_items(want.data(), cmds, nb_cmds) : r == 5 ? mc_build_big_items(want.data(), cmds, nb_cmds)
+                                                                               : mc_build_tool_items(want.data(), cmds, nb_cmds, routes[r]);
+            if (n != info.count[r] || (n && memcmp(want.data(), items.data() + (size_t)r * max_items, sizeof(McItemDev) * n))) return -1000002 - r;
+        }
+        int mx = 0, my = 0;
+        for (int i = 0; i < nb_cmds; i++) { mx = std::max(mx, cmds[i].x0 + (1 << cmds[i].log2_w)); my = std::max(my, cmds[i].y0 + (1 << cmds[i].log2_h)); }
+        if (mx != info.max_x || my != info.max_y) return -1000010;
+    }
     std::vector<DmvrMvDev> dm(n_dmvr + 1);
-    mc_build_tool_items(items.data() + n_items + n_bdof + n_prof, cmds, nb_cmds, OVGPU_MC_TOOL_DMVR);
-    mc_build_items(items.data(), cmds, nb_cmds);
-    mc_build_tool_items(items.data() + n_items, cmds, nb_cmds, OVGPU_MC_TOOL_BDOF);
-    mc_build_tool_items(items.data() + n_items + n_bdof, cmds, nb_cmds, OVGPU_MC_TOOL_PROF);
-    mc_build_tool_items(items.data() + n_items + n_bdof + n_prof + n_dmvr, cmds, nb_cmds, MC_ROUTE_SMALL_C);
+    McItemDev *const it_plain = items.data(), *const it_bdof = items.data() + max_items, *const it_prof = items.data() + 2 * (size_t)max_items,
+              *const it_dmvr = items.data() + 3 * (size_t)max_items, *const it_sc = items.data() + 4 * (size_t)max_items, *const it_big = items.data() + 5 * (size_t)max_items;
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; }
     a.pic_w = w; a.pic_h = h; a.bitdepth = bitdepth;
-    a.cmds = (const McCmdDev *)cmds; a.items = items.data(); a.nb_items = n_items;
+    a.cmds = (const McCmdDev *)cmds; a.items = it_plain; a.nb_items = n_items;
     a.lmcs_fwd = lmcs_fwd;
+    a.limit = info.limit;
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
             a.refs.poc[l][i] = refs->poc[l][i];
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = refs->plane[l][i][c]; a.refs.pitch[l][i][c] = refs->stride[l][i][c]; }
         }
     if (n_items) ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
-    const int n_big = mc_build_big_items(NULL, cmds, nb_cmds);
     if (n_big) {
-        std::vector<McItemDev> big(n_big);
-        mc_build_big_items(big.data(), cmds, nb_cmds);
         McK::Args t = a;
-        t.items = big.data(); t.nb_items = n_big;
+        t.items = it_big; t.nb_items = n_big; t.limit = info.limit + 5;
         ovd_emulate<McBigK>(t, ovd_dim3((n_big + McBigK::WARPS - 1) / McBigK::WARPS, 1, 1), McBigK::SMEM_BYTES);
     }
     if (n_bdof) {
         McK::Args t = a;
-        t.items = items.data() + n_items; t.nb_items = n_bdof;
+        t.items = it_bdof; t.nb_items = n_bdof; t.limit = info.limit + 1;
         ovd_emulate<BdofK>(t, ovd_dim3((n_bdof + BdofK::WARPS - 1) / BdofK::WARPS, 1, 1), BdofK::SMEM_BYTES);
     }
     if (n_prof) {
         ProfK::Args t;
-        t.mc = a; t.mc.items = items.data() + n_items + n_bdof; t.mc.nb_items = n_prof; t.prof = (const ProfInfoDev *)prof;
+        t.mc = a; t.mc.items = it_prof; t.mc.nb_items = n_prof; t.mc.limit = info.limit + 2; t.prof = (const ProfInfoDev *)prof;
         ovd_emulate<ProfK>(t, ovd_dim3((n_prof + ProfK::WARPS * ProfK::SBS - 1) / (ProfK::WARPS * ProfK::SBS), 1, 1), ProfK::SMEM_BYTES);
     }
     if (n_sc) {
         McK::Args t = a;
-        t.items = items.data() + n_items + n_bdof + n_prof + n_dmvr; t.nb_items = n_sc;
+        t.items = it_sc; t.nb_items = n_sc; t.limit = info.limit + 4;
         ovd_emulate<McSmallCK>(t, ovd_dim3((n_sc + McSmallCK::WARPS * McSmallCK::SBS - 1) / (McSmallCK::WARPS * McSmallCK::SBS), 1, 1), McSmallCK::SMEM_BYTES);
     }
     if (n_dmvr) {
         DmvrK::Args t;
-        t.mc = a; t.mc.items = items.data() + n_items + n_bdof + n_prof; t.mc.nb_items = n_dmvr; t.out = dm.data();
+        t.mc = a; t.mc.items = it_dmvr; t.mc.nb_items = n_dmvr; t.mc.limit = info.limit + 3; t.out = dm.data();
         ovd_emulate<DmvrK>(t, ovd_dim3((n_dmvr + DmvrK::WARPS - 1) / DmvrK::WARPS, 1, 1), DmvrK::SMEM_BYTES);
         if (dmvr_out) memcpy(dmvr_out, dm.data(), sizeof(DmvrMvDev) * n_dmvr);
     }

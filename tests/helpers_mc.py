@@ -71,6 +71,7 @@ def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None, dmvr_out=None):
         C.memmove(C.byref(gl), C.byref(luts), C.sizeof(gl))
         lm = api.Lmcs(ctx, gl)
     batch.run(dst, pics, pocs, lm)
+    batch.status()                      # the command walk runs on the device: this is where a refused batch is reported
     if dmvr_out is not None:
         dmvr_out[:] = batch.read_dmvr(len(dmvr_out))
     out = dst.download()

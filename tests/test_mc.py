@@ -177,6 +177,22 @@ def test_tools_malformed_commands_rejected(oracle, emu):
 
 
 @pytest.mark.gpu
+def test_gpu_malformed_commands_rejected(oracle, gpu_ctx):
+    """The command walk (validation, routing, work-item lists) runs on the GPU: a malformed command is reported, with its index,
+    by the call that would run the batch, nothing is launched for it, and the batch is usable again afterwards."""
+    from openvvc_b200 import api
+    refs0, refs1, pocs, cmds, luts, prof = helpers_mc.mc_tools_case(oracle, 256, 128, 3, 7, False)
+    good = helpers_mc.gpu_mc(gpu_ctx, 256, 128, refs0, refs1, pocs, cmds, luts, prof=prof)
+    for tool, field, val in ((2, "aux", (len(prof) << 8) | 1), (1, "inter_dir", 1), (0, "log2_w", 9)):
+        bad = cmds.copy()
+        i = int(np.nonzero(bad["tool"] == tool)[0][-1])
+        bad[field][i] = val
+        with pytest.raises(api.OVGPUError, match="MC command %d malformed" % i):
+            helpers_mc.gpu_mc(gpu_ctx, 256, 128, refs0, refs1, pocs, bad, luts, prof=prof)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, 256, 128, refs0, refs1, pocs, cmds, luts, prof=prof), good, "after the rejected batches")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("c", TOOLS_GOLDEN, ids=IDS)
 def test_tools_gpu_matches_golden(oracle, gpu_ctx, c):
     refs0, refs1, pocs, cmds, luts, prof = _tools_case(oracle, c)
