@@ -283,11 +283,143 @@ def run_reference(args, w, h):
     print(json.dumps(line))
 
 
-def workload_config(w, h, pics_per_step, dev_streams=1):
+def workload_config(w, h, pics_per_step, dev_streams=1, dag=0):
+    par = ("random-access GOP32 as a dependency graph (a step = one GOP of 32 pictures, 1-1-2-4-8-16 wide): picture k of the decoding order on "
+           "rank k mod N, every picture predicted from its two reference pictures of the hierarchy, a finished reference sent to exactly the "
+           "ranks whose pictures name it (ovgpu_picture_publish / consume: grouped ncclSend / ncclRecv of the 3 planes, ordered by events); "
+           "the e2e number is measured on independent pictures per step with one picture per step handed to all ranks"
+           if dag else
+           "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference "
+           "(device copy + ncclBroadcast of 3 planes)")
     return {"workload": "%dx%d 10-bit 4:2:0 CTU128 synthetic RA inter picture, rcn stages in the timed path: %s "
                         "(intra block copy: off, as for natural video in the common test conditions)" % (w, h, " -> ".join(STAGES_IMPLEMENTED)),
-            "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": "frame-parallel: every rank reconstructs its own pictures; per step one finished picture is handed to all ranks as a reference (device copy + ncclBroadcast of 3 planes)",
-            "l2": "inputs larger than L2: %d pictures x (recon+mid+dst) + 4 reference pictures per step" % pics_per_step}
+            "pictures_per_step": pics_per_step, "streams_per_gpu": dev_streams, "parallelism": par,
+            "l2": "inputs larger than L2: every picture in flight has its own recon + mid planes and writes its own DPB slot (72 slots), "
+                  "%d pictures per step" % pics_per_step}
+
+
+def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl, lmcs, d_streams, d_ctx, barrier):
+    """`value` leg: warmup + steps GOPs of a random-access stream, reconstructed as the dependency graph it is.
+    Returns (milliseconds of the timed GOPs on the device, max over nothing -- the caller reduces over ranks --, info)."""
+    import helpers
+    n_ds = len(d_streams)
+    nb_slots = 168                                  # DPB copies: the issue order keeps 3-4 GOPs in flight, a slot is reused 5 GOPs later
+    W, K = max(1, args.warmup), args.steps
+    sched = ovdist.GopSchedule(W + K, world)
+    pics = wl["pics"]
+    mk_ctx = d_ctx[0]
+    slots = [mk_ctx.picture(w, h) for _ in range(nb_slots)]
+    slots[0].upload(wl["refs"][0][0])               # POC 0: given, resident on every rank
+    dsets = [make_dev(api, d_ctx[j], pics[j % len(pics)], w, h) for j in range(n_ds)]
+    for j in range(n_ds):
+        d_ctx[j].sync()
+    # The sends / receives of one communicator run in issue order on one stream (that is what keeps them matched between the
+    # ranks), so a receive that waits for a picture deep in one GOP's dependency chain holds back everything queued behind it: in
+    # decoding order that is one GOP per chain latency (7.2 ms on 8 GPUs).  The issue order (wave order, dist.py) interleaves the
+    # chains of consecutive GOPs instead.  (More communicators -- lanes -- were tried and starve each other.)
+    L = max(1, args.dag_lanes) if world > 1 else 1
+    xstreams = [torch.cuda.Stream() for _ in range(L)]
+    xctxs = [api.Ctx(local, st_.cuda_stream) for st_ in xstreams]
+    xds = [None] * L
+    for l in range(L if world > 1 else 0):
+        uid = torch.zeros(api.Dist.ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(api.Dist.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        torch.cuda.synchronize()
+        xds[l] = api.Dist(xctxs[l], world, rank, bytes(uid.cpu().numpy().tobytes()))
+
+    def lane(poc):
+        return ((poc - 1) // 32) % L
+    ready, readers, nxt = {}, {}, [0]
+    ev0 = torch.cuda.Event(); ev0.record(stream); ready[0] = ev0
+
+    def wait_slot_free(s, poc):
+        for ev in readers.pop(poc % nb_slots, []):
+            s.wait_event(ev)                        # kernels / sends that still read the slot's previous picture
+
+    def reconstruct(poc, parents):
+        j = nxt[0]; nxt[0] = (j + 1) % n_ds
+        s, c, d = d_streams[j], d_ctx[j], dsets[j]
+        for p in set(parents):
+            s.wait_event(ready[p])
+        wait_slot_free(s, poc)
+        ra, rb = slots[parents[0] % nb_slots], slots[parents[1] % nb_slots]
+        run_stages(api, c, dict(d, dst=slots[poc % nb_slots]), [[ra, rb], [rb, ra]], [[parents[0], parents[1]], [parents[1], parents[0]]], lmcs)
+        ev = torch.cuda.Event(); ev.record(s); ready[poc] = ev
+        for p in set(parents):
+            readers.setdefault(p % nb_slots, []).append(ev)
+
+    def publish(poc, consumers):
+        l = lane(poc)
+        xstreams[l].wait_event(ready[poc])
+        xds[l].publish(slots[poc % nb_slots], consumers, ctx=xctxs[l])
+        ev = torch.cuda.Event(); ev.record(xstreams[l])
+        readers.setdefault(poc % nb_slots, []).append(ev)
+
+    def consume(poc, owner):
+        l = lane(poc)
+        wait_slot_free(xstreams[l], poc)
+        xds[l].consume(slots[poc % nb_slots], owner, ctx=xctxs[l])
+        ev = torch.cuda.Event(); ev.record(xstreams[l]); ready[poc] = ev
+
+    def join():
+        for s in list(d_streams[1:]) + xstreams:
+            ev = torch.cuda.Event(); ev.record(s); stream.wait_event(ev)
+
+    def traffic():
+        return sum(x.traffic()[0] for x in xds if x)
+
+    n0 = sum(c.launch_count() for c in d_ctx)
+    order = sched.wave_order() if args.dag_wave else None
+    ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 0, 32 * W, order)
+    join(); barrier()
+    oracle_checked = 0
+    if rank == 0 and W <= 3 and not os.environ.get("BENCH_SKIP_ORACLE_CHECK"):
+        # the stream's first picture (POC 32 predicted from POC 0, owner rank 0, commands of picture 0) against the CPU oracle chain on
+        # the same references: the graph plumbing (slots, reference lists, events) delivers what the oracle computes.  Untimed.
+        import helpers_chain
+        from oracle import pyoracle as po_chk
+        p0 = wl["refs"][0][0]
+        want = helpers_chain.oracle_picture(po_chk, dict(wl, refs=[[p0, p0], [p0, p0]], pocs=[[0, 0], [0, 0]]), pics[0])
+        helpers.assert_planes_equal(slots[32 % nb_slots].download(), want, "bench.py: first picture of the GOP stream vs the oracle chain")
+        oracle_checked = 1
+    barrier()
+    sent0 = traffic()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in list(d_streams[1:]) + xstreams:
+        s.wait_event(e0)
+    ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 32 * W, 32 * (W + K), order)
+    join()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sent = traffic() - sent0
+    # every copy of a picture of the last GOP (owner and consumers) must be the same picture, and the stream's first picture
+    # (POC 32 from POC 0, owner rank 0) must equal the CPU oracle chain on the same references
+    last = [poc for poc, _ in sched.pictures[-32:] if sched.owner[poc] == rank or sched.needs(rank, poc)]
+    md5 = {poc: helpers.md5(*slots[poc % nb_slots].download()) for poc in last}
+    info = {"gops": K, "warmup_gops": W, "pictures": 32 * K, "nvlink_bytes_per_step": None, "copies_identical": None, "oracle_checked": oracle_checked,
+            "lanes": L, "launches": sum(c.launch_count() for c in d_ctx) - n0}
+    if world > 1:
+        allmd5 = [None] * world
+        dist.all_gather_object(allmd5, md5)
+        t = torch.tensor([float(sent)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        info["nvlink_bytes_per_step"] = float(t[0]) / K
+        if rank == 0:
+            merged = {}
+            for m in allmd5:
+                for poc, dg in m.items():
+                    merged.setdefault(poc, set()).add(dg)
+            bad = [poc for poc, s_ in merged.items() if len(s_) != 1]
+            if bad:
+                raise SystemExit("bench.py: copies of pictures %s differ between ranks" % bad)
+            info["copies_identical"] = len(merged)
+    else:
+        info["nvlink_bytes_per_step"] = 0.0
+    return ms, info
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -303,6 +435,11 @@ def main():
     ap.add_argument("--e2e-share", type=int, default=1, help="e2e contexts (host threads) that share one stream")
     ap.add_argument("--e2e-sets", type=int, default=2, help="picture sets in flight in the e2e leg (1 or 2)")
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
+    ap.add_argument("--dag", type=int, default=1, help="1: `value` = a random-access GOP32 stream reconstructed as a dependency graph, picture k on rank "
+                    "k mod N, references handed to the ranks that need them (ovgpu_picture_publish / consume); 0: independent pictures per step")
+    ap.add_argument("--dag-lanes", type=int, default=1, help="communicators / exchange streams the GOPs of the --dag stream alternate over "
+                    "(measured on 8 GPUs: 4 lanes = 56 pictures/s, concurrent communicators starve each other; kept for the record)")
+    ap.add_argument("--dag-wave", type=int, default=1, help="1: pictures are issued in wave order (a new GOP every two hierarchy levels) instead of decoding order")
     ap.add_argument("--e2e-dl-streams", type=int, default=0, help="1: the output copy of a picture runs on a stream of its own (measured: no gain)")
     args = ap.parse_args()
     w, h = SIZES[args.size]
@@ -413,14 +550,20 @@ def main():
     # ---- value: device-resident throughput, CUDA events on the launching stream
     n0 = sum(c.launch_count() for c in d_ctx)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = sum(c.launch_count() for c in d_ctx) - n0
+    dag_info = None
+    if args.dag:
+        ms, dag_info = run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl, lmcs, d_streams, d_ctx, barrier)
+        pics_per_step = 32
+    else:
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        pics_per_step = P
+    launches = dag_info["launches"] if dag_info else sum(c.launch_count() for c in d_ctx) - n0
 
     # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
     stage_names = ("mc", "residual", "intra", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
@@ -577,9 +720,12 @@ def main():
         t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
+        t = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        launches = int(t[0])
 
     if rank == 0:
-        fps = world * P * args.steps / (ms * 1e-3)
+        fps = (pics_per_step * args.steps if args.dag else world * P * args.steps) / (ms * 1e-3)
         e2e_fps = world * P * e2e_steps / e2e_s
         peak, peak_src = peaks()
         dirs = float(np.mean([mc_dirs_per_sample(p["cmds"]) for p in pics]))
@@ -602,8 +748,8 @@ def main():
         h2d = sum(p["cmds"].nbytes + p["prof"].nbytes + p["tus"].nbytes + 3 * 8 * len(p["tus"]) + p["coeffs"].nbytes + p["icmds"].nbytes + 8 * len(p["icmds"]) + p["isp_words"].nbytes + p["anchors"].nbytes + p["dbf"]["ver"].nbytes + p["dbf"]["hor"].nbytes + p["dbf"]["qp"].nbytes + p["sao"].nbytes + 24 * 100 * 36 * 4 + 8 * len(p["alf_ctu"]) for p in pics)
         line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",
-                "config": workload_config(w, h, P, n_ds),
+                "scaling": "strong" if args.dag else "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",
+                "config": workload_config(w, h, pics_per_step, n_ds, args.dag),
                 "gpu_launches": launches,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": len(real_streams), "host_threads": n_ctx, "pictures_in_flight": n_sets * P,
@@ -615,6 +761,8 @@ def main():
                              "avg_launch_ms": stages[top]["avg_launch_ms"]},
                 "stages": stages, "mc_dirs_per_sample": dirs,
                 "clocks": clocks}
+        if dag_info:
+            line["dag"] = {k: v for k, v in dag_info.items() if k != "launches"}
         # CPU baseline on the box's host cores (N=1 only): the compiled reference on a bounded sample
         if world == 1:
             from oracle import pyoracle as po

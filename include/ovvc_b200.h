@@ -68,6 +68,26 @@ int  ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const 
 int  ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pitch_bytes[3]);
 int  ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src);
 
+/* ---- Reference hand-off between the GPUs of one node  (the device-side form of ovdpb_synchro_ref_decoded_ctus /
+ *      rcn_inter_synchronization, dpb.c:1242-1269, rcn_inter.c:131-146: a picture that later pictures reference must
+ *      be complete where they are reconstructed).  Pictures are sharded over the ranks (one process per GPU, picture k
+ *      of the decoding order on rank k mod G, like the reference's frame threads, ovdec.c:189-248); when a reference
+ *      picture is finished its owner PUBLISHES it to the ranks whose reference picture lists name it, and those ranks
+ *      CONSUME it into their copy: grouped ncclSend / ncclRecv of the three planes over NVLink, queued on the calling
+ *      context's stream (no host wait).  Every rank must issue its publish / consume calls in the same picture order.
+ *      NCCL is loaded with dlopen on the first ovgpu_dist_* call. --------------------------------------------------- */
+typedef struct OVGPUDist OVGPUDist;
+#define OVGPU_DIST_ID_BYTES 128
+/* rank 0: a fresh communicator id, to be handed to every rank by whatever means the host has */
+int  ovgpu_dist_unique_id(void *id, size_t bytes);
+/* collective over the nb_ranks processes (ncclCommInitRank) on the context's device */
+int  ovgpu_dist_create(OVGPUCtx *ctx, int nb_ranks, int rank, const void *id, OVGPUDist **dist);
+void ovgpu_dist_destroy(OVGPUDist *dist);
+int  ovgpu_picture_publish(OVGPUCtx *ctx, OVGPUDist *dist, const OVGPUPicture *pic, const int *consumers, int nb_consumers);
+int  ovgpu_picture_consume(OVGPUCtx *ctx, OVGPUDist *dist, OVGPUPicture *pic, int owner);
+/* bytes this rank has queued for sending / receiving so far */
+int  ovgpu_dist_traffic(const OVGPUDist *dist, uint64_t *bytes_sent, uint64_t *bytes_received);
+
 /* ---- ALF / CC-ALF  (replaces alf.rcn_alf_filter_line, rcn_alf.c:1285, for all CTU lines of a picture,
  *                     and alf.rcn_alf_reconstruct_coeff_APS, rcn_alf.c:264) ------------------------------ */
 #define OVGPU_ALF_NUM_SETS 24

@@ -300,6 +300,44 @@ class Lmcs:
             self.p = vp()
 
 
+class Dist:
+    """ovgpu_dist_*: the reference hand-off between the ranks of one node (NCCL send / receive behind the C ABI)"""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * Dist.ID_BYTES)()
+        ret = lib().ovgpu_dist_unique_id(buf, Dist.ID_BYTES)
+        if ret:
+            raise OVGPUError("ovgpu_dist_unique_id failed: %d" % ret)
+        return bytes(buf)
+
+    def __init__(self, ctx, nb_ranks, rank, uid):
+        self.ctx = ctx
+        self.p = vp()
+        buf = (C.c_uint8 * Dist.ID_BYTES).from_buffer_copy(uid)
+        _check(ctx.h, lib().ovgpu_dist_create(ctx.h, int(nb_ranks), int(rank), buf, C.byref(self.p)), "dist_create")
+
+    def publish(self, pic, consumers, ctx=None):
+        arr = (C.c_int * len(consumers))(*consumers)
+        _check((ctx or self.ctx).h, lib().ovgpu_picture_publish((ctx or self.ctx).h, self.p, pic.p, arr, len(consumers)), "picture_publish")
+
+    def consume(self, pic, owner, ctx=None):
+        _check((ctx or self.ctx).h, lib().ovgpu_picture_consume((ctx or self.ctx).h, self.p, pic.p, int(owner)), "picture_consume")
+
+    def traffic(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        lib().ovgpu_dist_traffic(self.p, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_dist_destroy.restype = None
+            lib().ovgpu_dist_destroy(self.p)
+            self.p = vp()
+
+
 class McBatch:
     """One picture's PU list on the device (ovgpu_mc_batch_*)."""
 
