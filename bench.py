@@ -76,17 +76,28 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_workload(w, h, n_pics, seed0=5000, all_intra=False):
+def make_workload(w, h, n_pics, seed0=5000, all_intra=False, tables="product"):
     """Shared reference pictures + n_pics synthetic inter pictures: PU list, SAO and ALF decoder state
-    (SURVEY.md §8(d) generators).  all_intra: every coding unit is intra and there is no PU list (an I picture)."""
+    (SURVEY.md §8(d) generators).  all_intra: every coding unit is intra and there is no PU list (an I picture).
+    tables: who builds the LMCS LUTs and the ALF coefficient tables from the APS data -- "product" = the C ABI's host-side
+    builders (our arm), "oracle" = the compiled reference / its port (the reference arm: that process never loads the product
+    library; the two builders are checked against each other by the tests)."""
     from openvvc_b200 import api, synth, synth_tu, synth_dbf, synth_recon
     refs = [[synth.planes(w, h, seed0 + 900 + i) for i in range(2)], [synth.planes(w, h, seed0 + 950 + i) for i in range(2)]]
     pocs = [[8, 16], [16, 24]]
-    lmcs = api.lmcs_build_luts(synth.lmcs_data(seed0))
+    if tables == "oracle":
+        from oracle import pyoracle as po_t
+        impl_t = "ref" if po_t.ref_available() else "port"
+        lmcs = po_t.lmcs_build_luts(synth.lmcs_data(seed0), impl=impl_t)
+    else:
+        lmcs = api.lmcs_build_luts(synth.lmcs_data(seed0))
     pics = []
     for i in range(n_pics):
         ap = synth.alf_params(w, h, seed0 + 100 + i, 7)
-        tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
+        if tables == "oracle":
+            tab = po_t.alf_build_tables(ap["luma_aps"], ap["chroma_aps"], impl=impl_t)
+        else:
+            tab = api.alf_tables_from_aps(ap["luma_aps"], ap["chroma_aps"])
         tab.np("cc_coeff")[:] = ap["cc_coeff"]
         sao = synth.sao_params(w, h, seed0 + 200 + i, 7, api.SAO_CTU)
         cmds, prof = synth.mc_commands_tools(w, h, seed0 + 300 + i, 7, p_bdof=0.25, p_affine=0.15, p_dmvr=0.15, p_gpm=0.1)
@@ -240,7 +251,7 @@ def reference_step(po, wl, threads):
         # same blocks through the reference's own slots in CU order (intra_pred*, mip, recon_isp_subtree_*); the ISP partitions'
         # transform blocks are part of that call, so they are left out of the residual pass above
         pi.intra_picture_isp(rec, p["icmds"].copy(), pi.isp_info_array(p["isp_words"], p["isp_tus"]), p["coeffs"], 7, impl=impl, simd=1)
-        po.port().ovo_lmcs_reshape_plane(rec[0].ctypes.data_as(po.u16p), w, w, h, luts.np("bwd_lut").ctypes.data_as(po.u16p), 10)
+        po.lmcs_reshape_backward(rec[0], luts, 7, impl=impl)           # the reference's own lmcs_reshape_backward slot, CTU by CTU
         if impl == "ref":
             pdf.dbf_picture_ref(rec, p["dbf_blks"], 7, simd=1)
         else:
@@ -263,7 +274,7 @@ def run_reference(args, w, h):
         return
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    wl = make_workload(w, h, min(cores, 8))
+    wl = make_workload(w, h, min(cores, 8), tables="oracle")
     threads = cores                      # every host thread the box has: one picture per thread (the reference's frame threads)
     for _ in range(max(1, min(args.warmup, 1))):
         reference_step(po, wl, threads)
@@ -280,6 +291,8 @@ def run_reference(args, w, h):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind,
                              "sample": "%d pictures per step, one per host thread, %d steps" % (threads, args.steps)},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    # this arm is the reference alone: the product library must not even be mapped into the process
+    line["product_library_loaded"] = "libovvc_b200" in open("/proc/self/maps").read()
     print(json.dumps(line))
 
 

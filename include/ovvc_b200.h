@@ -68,6 +68,23 @@ int  ovgpu_picture_download(OVGPUCtx *ctx, const OVGPUPicture *pic, void *const 
 int  ovgpu_picture_planes(const OVGPUPicture *pic, void *dev_planes[3], size_t pitch_bytes[3]);
 int  ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src);
 
+/* ---- Output stage  (examples/dectest.c:376-406 write_decoded_frame_to_file: the output window of a frame as Y, Cb, Cr rows of
+ *      16-bit samples; CI/ovnreg:82-85 hashes that file) --------------------------------------------------------------------- */
+typedef struct OVGPUWindow {        /* struct Window (ovframe.h): offsets in CHROMA sample units, luma = offset << 1 */
+    int32_t offset_lft, offset_rgt, offset_abv, offset_blw;
+} OVGPUWindow;
+/* the rows dectest would write, copied to host planes (win == NULL: the whole picture) */
+int  ovgpu_picture_download_window(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUWindow *win, void *const data[3], const size_t linesize[3]);
+/* running MD5 (RFC 1321) of those rows, computed on the device: ovgpu_md5_picture appends one picture (asynchronous, one GPU
+ * thread: a serial hash, ~0.2 s per 4K picture -- a checking aid, not part of the timed path); ovgpu_md5_final returns the digest
+ * of everything appended so far (blocking) without ending the hash */
+typedef struct OVGPUMd5 OVGPUMd5;
+int  ovgpu_md5_create(OVGPUCtx *ctx, OVGPUMd5 **md5);
+void ovgpu_md5_destroy(OVGPUMd5 *md5);
+int  ovgpu_md5_reset(OVGPUCtx *ctx, OVGPUMd5 *md5);
+int  ovgpu_md5_picture(OVGPUCtx *ctx, OVGPUMd5 *md5, const OVGPUPicture *pic, const OVGPUWindow *win);
+int  ovgpu_md5_final(OVGPUCtx *ctx, OVGPUMd5 *md5, uint8_t digest[16]);
+
 /* ---- Reference hand-off between the GPUs of one node  (the device-side form of ovdpb_synchro_ref_decoded_ctus /
  *      rcn_inter_synchronization, dpb.c:1242-1269, rcn_inter.c:131-146: a picture that later pictures reference must
  *      be complete where they are reconstructed).  Pictures are sharded over the ranks (one process per GPU, picture k

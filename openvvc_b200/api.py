@@ -300,6 +300,48 @@ class Lmcs:
             self.p = vp()
 
 
+class Window(C.Structure):
+    _fields_ = [("offset_lft", C.c_int32), ("offset_rgt", C.c_int32), ("offset_abv", C.c_int32), ("offset_blw", C.c_int32)]
+
+
+class Md5:
+    """ovgpu_md5_*: running MD5 of the output byte stream (dectest's YUV file), computed on the device"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_md5_create(ctx.h, C.byref(self.p)), "md5_create")
+
+    def reset(self):
+        _check(self.ctx.h, lib().ovgpu_md5_reset(self.ctx.h, self.p), "md5_reset")
+
+    def picture(self, pic, window=None, ctx=None):
+        win = Window(*window) if window is not None else None
+        _check((ctx or self.ctx).h, lib().ovgpu_md5_picture((ctx or self.ctx).h, self.p, pic.p, C.byref(win) if win is not None else None), "md5_picture")
+
+    def hexdigest(self, ctx=None):
+        out = (C.c_uint8 * 16)()
+        _check((ctx or self.ctx).h, lib().ovgpu_md5_final((ctx or self.ctx).h, self.p, out), "md5_final")
+        return bytes(out).hex()
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_md5_destroy.restype = None
+            lib().ovgpu_md5_destroy(self.p)
+            self.p = vp()
+
+
+def download_window(ctx, pic, window, w, h):
+    """ovgpu_picture_download_window: the planes dectest would write for output window (lft, rgt, abv, blw) in chroma units"""
+    l, r, a, b = window
+    out = [np.zeros((h - 2 * (a + b), w - 2 * (l + r)), np.uint16), np.zeros((h // 2 - (a + b), w // 2 - (l + r)), np.uint16),
+           np.zeros((h // 2 - (a + b), w // 2 - (l + r)), np.uint16)]
+    win = Window(l, r, a, b)
+    _check(ctx.h, lib().ovgpu_picture_download_window(ctx.h, pic.p, C.byref(win), *_host_planes(out)), "download_window")
+    ctx.sync()
+    return out
+
+
 class Dist:
     """ovgpu_dist_*: the reference hand-off between the ranks of one node (NCCL send / receive behind the C ABI)"""
 

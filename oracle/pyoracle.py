@@ -209,6 +209,18 @@ def lmcs_build_luts(d, bitdepth=10, impl="port"):
     return luts
 
 
+def lmcs_reshape_backward(luma, luts, log2_ctu=7, bitdepth=10, impl="port"):
+    """in-place backward reshape of a luma plane: impl="ref" = the compiled reference's own lmcs_reshape_backward slot, CTU by CTU
+    (oracle/ref_harness.c); "port" = the C restatement"""
+    h, w = luma.shape
+    if impl == "ref":
+        f = ref().ovref_lmcs_reshape_backward_plane
+        f.restype = None
+        f(luma.ctypes.data_as(u16p), luma.strides[0] // 2, w, h, C.byref(luts), log2_ctu, bitdepth)
+    else:
+        port().ovo_lmcs_reshape_plane(luma.ctypes.data_as(u16p), luma.strides[0] // 2, w, h, luts.np("bwd_lut").ctypes.data_as(u16p), bitdepth)
+
+
 def make_mc_refs(ref_lists, pocs):
     """ref_lists: [list0, list1], each a list of pictures (3 uint16 planes); pocs likewise."""
     r = McRefs()

@@ -276,6 +276,22 @@ ovref_lmcs_chroma_scale(const uint16_t *src, int stride, unsigned abv_mask, unsi
     return ret;
 }
 
+/* the reference's own lmcs_reshape_backward slot (rcn_lmcs.c:295; called per CTU by slicedec.c:745-750) over a whole luma plane:
+ * CTU by CTU like the decoder does, with the caller's LUTs in the slot's private struct LMCSLUTs layout */
+void
+ovref_lmcs_reshape_backward_plane(uint16_t *plane, int stride, int w, int h, const OVOLmcsLuts *luts, int log2_ctu, int bitdepth)
+{
+    OVCTUDec *c;
+    const int ctu = 1 << log2_ctu;
+    ctudec_init(&c);
+    rcn_init_functions(&c->rcn_funcs, 0, 1, 0, 1, bitdepth);
+    for (int y = 0; y < h; y += ctu)
+        for (int x = 0; x < w; x += ctu)
+            c->rcn_funcs.lmcs_reshape_backward(plane + (size_t)y * stride + x, stride, (const struct LMCSLUTs *)luts,
+                                               x + ctu <= w ? ctu : w - x, y + ctu <= h ? ctu : h - y);
+    free(c);
+}
+
 void
 ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
 {

@@ -97,3 +97,16 @@ def test_alf_disabled_is_identity(oracle):
     ctu = dict(ctu); ctu["flag"] = np.zeros_like(ctu["flag"]); ctu["cc_cb_enabled"] = 0; ctu["cc_cr_enabled"] = 0
     out = po.alf_picture(planes, tab, ctu, 7, impl="port")
     helpers.assert_planes_equal(out, planes, "ALF off")
+
+
+def test_lmcs_reshape_backward_ref_slot_matches_port(oracle):
+    """the reference's own lmcs_reshape_backward slot, CTU by CTU (what bench.py's reference arm times), against the port's plane pass"""
+    from openvvc_b200 import synth
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built")
+    luts = oracle.lmcs_build_luts(synth.lmcs_data(41), impl="ref")
+    a = synth.planes(416, 240, 9)[0]
+    b = a.copy()
+    oracle.lmcs_reshape_backward(a, luts, 7, impl="ref")
+    oracle.lmcs_reshape_backward(b, luts, 7, impl="port")
+    assert (a == b).all() and not (a == synth.planes(416, 240, 9)[0]).all()
