@@ -183,26 +183,38 @@ def commit_picture(api, c, d, p, w, h, tt=None):
     if tt is not None: tt.append(time.perf_counter())
 
 
-STAGE_KERNELS = {"mc": ("McK", "BdofK", "DmvrK", "ProfK", "McSmallCK"), "residual": ("TrK",), "intra": ("ovd_recon_kernel", "ReconPrepK"),
+STAGE_LAUNCHES = {"TrK": 4, "Lmcs": 2, "ovd_recon_kernel": 2, "ReconPrepK": 2}      # launches per picture of kernels that run once per plane
+STAGE_KERNELS = {"mc": ("McK", "McBigK", "BdofK", "DmvrK", "ProfK", "McSmallCK", "McPrep", "McGuardK"), "residual": ("TrK",), "intra": ("ovd_recon_kernel", "ReconPrepK"),
                  "lmcs": ("Lmcs",), "dbf_v": ("DbfK<0>",), "dbf_h": ("DbfK<1>",), "sao": ("SaoK",), "alf_luma": ("AlfLumaK",),
                  "alf_chroma": ("AlfChromaK",)}
 
 
 def ncu_traffic(stage):
     """DRAM bytes (read + write) per picture of a stage's kernels, from the newest committed `ncu --set full` summary under
-    profiles/ (tools/ncu_summary.py; a capture of the same command with --pics 1).  None when there is no summary."""
+    profiles/ (tools/ncu_summary.py over a capture of tools/ncu_picture.py: exactly ONE picture between cudaProfilerStart / Stop,
+    L2 flushed before it; older summaries without a `pictures` field are normalised per kernel by its own launch count).
+    None when there is no summary."""
     import glob
     import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_ncu_full_all_stages_v*.json")),
-                   key=lambda f: int(re.search(r"_v(\d+)", f).group(1)))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0[0-9]_ncu_full_all_stages_v*.json")),
+                   key=lambda f: (int(re.search(r"r(\d+)_", os.path.basename(f)).group(1)), int(re.search(r"_v(\d+)", f).group(1))))
     if not files:
         return None, None
-    launches = json.load(open(files[-1]))["launches"]
-    pics = max(1, sum("AlfLumaK" in l["kernel"] for l in launches))
-    sel = [l for l in launches if any(k in l["kernel"] for k in STAGE_KERNELS[stage])]
-    if not sel:
+    doc = json.load(open(files[-1]))
+    launches = doc["launches"]
+    total, found = 0.0, False
+    for k in STAGE_KERNELS[stage]:
+        sel = [l for l in launches if k in l["kernel"]]
+        if not sel:
+            continue
+        found = True
+        # pictures this kernel's launches stand for: the capture's picture count, or (older captures whose window straddled
+        # pictures) the kernel's OWN launch count over its launches per picture
+        n_pics = doc.get("pictures") or max(1.0, len(sel) / STAGE_LAUNCHES.get(k, 1))
+        total += sum(l.get("dram_read_MB", 0.0) + l.get("dram_write_MB", 0.0) for l in sel) / n_pics
+    if not found:
         return None, os.path.basename(files[-1])
-    return 1e6 * sum(l.get("dram_read_MB", 0.0) + l.get("dram_write_MB", 0.0) for l in sel) / pics, os.path.basename(files[-1])
+    return 1e6 * total, os.path.basename(files[-1])
 
 
 def residual_bytes(tus):
@@ -317,8 +329,8 @@ def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl
     import helpers
     n_ds = len(d_streams)
     nb_slots = 168                                  # DPB copies: the issue order keeps 3-4 GOPs in flight, a slot is reused 5 GOPs later
-    W, K = max(1, args.warmup), args.steps
-    sched = ovdist.GopSchedule(W + K, world)
+    W, K, R = max(1, args.warmup), args.steps, max(1, args.repeats)
+    sched = ovdist.GopSchedule(W + R * K, world)
     pics = wl["pics"]
     mk_ctx = d_ctx[0]
     slots = [mk_ctx.picture(w, h) for _ in range(nb_slots)]
@@ -399,21 +411,24 @@ def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl
         oracle_checked = 1
     barrier()
     sent0 = traffic()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for s in list(d_streams[1:]) + xstreams:
-        s.wait_event(e0)
-    ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 32 * W, 32 * (W + K), order)
-    join()
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    sent = traffic() - sent0
+    ms_all = []
+    for r_ in range(R):                             # R timed runs of exactly K steps (GOPs) each, back to back
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for s in list(d_streams[1:]) + xstreams:
+            s.wait_event(e0)
+        ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 32 * (W + r_ * K), 32 * (W + (r_ + 1) * K), order)
+        join()
+        e1.record(stream)
+        barrier()
+        ms_all.append(e0.elapsed_time(e1))
+    ms = ms_all
+    sent = (traffic() - sent0) / R
     # every copy of a picture of the last GOP (owner and consumers) must be the same picture, and the stream's first picture
     # (POC 32 from POC 0, owner rank 0) must equal the CPU oracle chain on the same references
     last = [poc for poc, _ in sched.pictures[-32:] if sched.owner[poc] == rank or sched.needs(rank, poc)]
     md5 = {poc: helpers.md5(*slots[poc % nb_slots].download()) for poc in last}
-    info = {"gops": K, "warmup_gops": W, "pictures": 32 * K, "nvlink_bytes_per_step": None, "copies_identical": None, "oracle_checked": oracle_checked,
+    info = {"gops": K, "warmup_gops": W, "pictures": 32 * K, "repeats": R, "nvlink_bytes_per_step": None, "copies_identical": None, "oracle_checked": oracle_checked,
             "lanes": L, "launches": sum(c.launch_count() for c in d_ctx) - n0}
     if world > 1:
         allmd5 = [None] * world
@@ -450,6 +465,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=8, help="independent contexts (streams) the e2e leg spreads pictures over")
     ap.add_argument("--dag", type=int, default=1, help="1: `value` = a random-access GOP32 stream reconstructed as a dependency graph, picture k on rank "
                     "k mod N, references handed to the ranks that need them (ovgpu_picture_publish / consume); 0: independent pictures per step")
+    ap.add_argument("--repeats", type=int, default=3, help="timed runs of exactly --steps steps each; the median run is reported, all are listed")
     ap.add_argument("--dag-lanes", type=int, default=1, help="communicators / exchange streams the GOPs of the --dag stream alternate over "
                     "(measured on 8 GPUs: 4 lanes = 56 pictures/s, concurrent communicators starve each other; kept for the record)")
     ap.add_argument("--dag-wave", type=int, default=1, help="1: pictures are issued in wave order (a new GOP every two hierarchy levels) instead of decoding order")
@@ -565,18 +581,20 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dag_info = None
     if args.dag:
-        ms, dag_info = run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl, lmcs, d_streams, d_ctx, barrier)
+        ms_runs, dag_info = run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl, lmcs, d_streams, d_ctx, barrier)
         pics_per_step = 32
     else:
-        barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_device()
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
+        ms_runs = []
+        for _ in range(max(1, args.repeats)):
+            barrier()
+            e0.record(stream)
+            for _ in range(args.steps):
+                step_device()
+            e1.record(stream)
+            barrier()
+            ms_runs.append(e0.elapsed_time(e1))
         pics_per_step = P
-    launches = dag_info["launches"] if dag_info else sum(c.launch_count() for c in d_ctx) - n0
+    launches = (dag_info["launches"] if dag_info else sum(c.launch_count() for c in d_ctx) - n0) // max(1, args.repeats)
 
     # ---- per-kernel device time (CUDA events around each launch, same stream), separate pass
     stage_names = ("mc", "residual", "intra", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
@@ -686,12 +704,15 @@ def main():
 
     step_e2e(); step_e2e()
     e2e_steps = max(2, args.steps)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_runs = []
+    for _ in range(max(1, args.repeats)):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_runs.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(e2e_runs))
     clocks = sampler.stop()
 
     # ---- verification of the end-to-end leg (untimed): one more end-to-end step and one device-resident step with NO reference
@@ -729,10 +750,13 @@ def main():
             sys.stderr.write("timeline step %d pic %d %-5s gpu %8.3f ms host %8.3f ms\n" % (stp, i, name, base[3].elapsed_time(e), 1e3 * (th - base[4])))
 
     # ---- max over ranks
+    # every run: max over ranks; the reported number is the MEDIAN run (all runs are listed beside it)
     if world > 1:
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor(ms_runs + e2e_runs, device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        ms_runs, e2e_runs = [float(v) for v in t[:len(ms_runs)]], [float(v) for v in t[len(ms_runs):]]
+    ms, e2e_s = float(np.median(ms_runs)), float(np.median(e2e_runs))
+    if world > 1:
         t = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(t)
         launches = int(t[0])
@@ -764,6 +788,8 @@ def main():
                 "scaling": "strong" if args.dag else "weak", "vs_baseline": None, "dtype": "u16/int32", "data": "synthetic",
                 "config": workload_config(w, h, pics_per_step, n_ds, args.dag),
                 "gpu_launches": launches,
+                "repeats": {"runs": len(ms_runs), "reported": "median", "value_runs": [(pics_per_step * args.steps if args.dag else world * P * args.steps) / (m * 1e-3) for m in ms_runs],
+                            "e2e_runs": [world * P * e2e_steps / s_ for s_ in e2e_runs]},
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": P * pbytes, "steps": e2e_steps, "streams": len(real_streams), "host_threads": n_ctx, "pictures_in_flight": n_sets * P,
                         "check": e2e_check},

@@ -1,5 +1,5 @@
 """Summarises an .ncu-rep (ncu --set full) into a small JSON for profiles/: per launch duration, DRAM bytes, registers,
-occupancy, instruction count, IPC and the main stall reasons.  Usage: python tools/ncu_summary.py in.ncu-rep out.json"""
+occupancy, instruction count, IPC and the main stall reasons.  Usage: python tools/ncu_summary.py in.ncu-rep out.json [pictures in the capture]"""
 import csv
 import io
 import json
@@ -49,8 +49,11 @@ def main(rep, out):
                 if name.endswith("_MB") and units[idx[k]].lower() == "byte":
                     d[name] = v / 1e6
         res.append(d)
-    json.dump({"source": rep, "command": "ncu --set full --clock-control none --import-source on (see DESIGN.md section 6)",
-               "launches": res}, open(out, "w"), indent=1)
+    doc = {"source": rep, "command": "ncu --profile-from-start off --set full --clock-control none --import-source on python tools/ncu_picture.py "
+                                     "(one benchmark picture, L2 flushed before it; DESIGN.md section 6)", "launches": res}
+    if len(sys.argv) > 3:
+        doc["pictures"] = int(sys.argv[3])      # pictures inside the capture window (tools/ncu_picture.py: 1)
+    json.dump(doc, open(out, "w"), indent=1)
     print("wrote", out, len(res), "launches")
 
 
