@@ -51,7 +51,9 @@ struct IntraK {
     static const int WARPS = 4;
     static const int REF_OFF = 72, REF_LEN = 256;                    // 64 + 2 negative-extension slots (MRL: two more), then 2 * 64 + 1 +
                                                                      // (m + 1) samples + up to 16 * (m + 1) of wide-angle padding
-    static const int SM_WARP = 4 * REF_LEN * 2;                      // abv, lft, filtered abv, filtered lft (uint16)
+    static const int SM_REFS = 4 * REF_LEN * 2;                      // abv, lft, filtered abv, filtered lft (uint16)
+    static const int SM_BLK = 256;                                   // the block's derived parameters (Blk), shared by the phases
+    static const int SM_WARP = SM_REFS + SM_BLK;
     static const int SMEM_BYTES = WARPS * SM_WARP;
 
     struct Args {
@@ -353,7 +355,15 @@ struct IntraK {
         const int nl = a.warp_comps ? THREADS / a.warp_comps : 32;
         const int warp = tid / nl, lane = tid - warp * nl;
         const int comp = a.warp_comps ? a.comp0 + warp : a.comp0 + by;
-        const Blk b = load(a, a.warp_comps ? bx : bx * WARPS + warp, comp);
+        // The parameters every phase needs are derived from the command ONCE, in phase 0, and left in shared memory for the others:
+        // the derivation is a few hundred dependent scalar instructions, and in the dataflow kernel it sat four times on every
+        // block's critical path (measured: 7.9 k of the 12 k cycles a block adds to the dependency chain).
+        Blk *const sblk = (Blk *)(smem + warp * SM_WARP + SM_REFS);
+        Blk b;
+        if (P == 0) {
+            b = load(a, a.warp_comps ? bx : bx * WARPS + warp, comp);
+            if (lane == 0) { if (b.valid) *sblk = b; else sblk->valid = 0; }
+        } else b = *sblk;
         if (!b.valid) return;
         uint16_t *plane = comp == 0 ? a.plane[0] : (comp == 1 ? a.plane[1] : a.plane[2]);
         const int pitch = comp == 0 ? a.pitch[0] : (comp == 1 ? a.pitch[1] : a.pitch[2]);

@@ -297,3 +297,6 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
 #endif
 
 static const int RECON_SMEM_BYTES = RECON_TR_SMEM_BYTES + IntraK::SMEM_BYTES;
+static_assert(sizeof(IntraK::Blk) <= IntraK::SM_BLK, "IntraK::Blk must fit its shared-memory slot");
+static_assert(sizeof(TrK<32>::Tb) <= TrK<32>::SM_TB && sizeof(TrK<128>::Tb) <= TrK<128>::SM_TB, "TrK::Tb must fit its shared-memory slot");
+static_assert((((TrK<32>::SM_CT + TrK<32>::SM_T2 + TrK<32>::SM_RES) * 2) & 7) == 0 && (((TrK<128>::SM_CT + TrK<128>::SM_T2 + TrK<128>::SM_RES) * 2) & 7) == 0, "Tb slot alignment");

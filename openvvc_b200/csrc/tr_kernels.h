@@ -56,7 +56,8 @@ struct TrK {
     static const int SM_CT = GROUP == 32 ? 320 : 32 * 34;     // dequantised block, transposed: [x][k = y], line stride kv4 + 2
     static const int SM_T2 = GROUP == 32 ? 384 : 64 * 34;     // after the vertical pass: [y][k = x], line stride kh4 + 2
     static const int SM_RES = GROUP == 32 ? 256 : 64 * 64;    // residual block, raster
-    static const int SM_GROUP = (SM_CT + SM_T2 + SM_RES) * 2;
+    static const int SM_TB = 256;                             // bytes: the block's derived parameters (Tb), shared by the phases
+    static const int SM_GROUP = (SM_CT + SM_T2 + SM_RES) * 2 + SM_TB;
     static const int SMEM_BYTES = GROUPS * SM_GROUP;
 
     struct Args {
@@ -274,7 +275,13 @@ struct TrK {
     {
         (void)st; (void)by; (void)bz;
         const int grp = tid / GROUP, gt = tid % GROUP;
-        const Tb t = load_tb(a, bx * GROUPS + grp);
+        // derived once (phase 0) and shared through shared memory: in the dataflow kernel phase 3 runs on a block's critical path
+        Tb *const stb = (Tb *)(smem + grp * SM_GROUP + (SM_CT + SM_T2 + SM_RES) * 2);
+        Tb t;
+        if (P == 0) {
+            t = load_tb(a, bx * GROUPS + grp);
+            if (gt == 0) { if (t.valid) *stb = t; else stb->valid = 0; }
+        } else t = *stb;
         if (!t.valid) return;
         int16_t *ct = (int16_t *)(smem + grp * SM_GROUP);
         int16_t *t2 = ct + SM_CT;
