@@ -209,7 +209,14 @@ static int recon_plane(OVGPUCtx *ctx, OVGPUPicture *pic, OVGPUIntraBatch *b, con
     ovgpu_tu_recon_args(tu, p, &a);
     a.pend = b->d_pend + (size_t)p * b->dev_units; a.serial = b->epoch; a.w_u = pic->width >> 2; a.h_u = pic->height >> 2;
     a.counter = b->d_counter + p;
-    const int max_ctas = ctx->num_sms * blocks_per_sm;
+    // Resident workers: what the dependency graph can keep busy, not what fits.  A plane of n commands on L dependency levels
+    // has n / L commands runnable at a time on average; workers beyond a few times that only spin on their neighbours' flags and
+    // hold the shared memory and issue slots that the kernels of other pictures could use.  Measured on an all-intra 4K picture
+    // (12.8 k commands, 1311 levels per plane): the same 16-19 ms per picture with 1 or 8 workers per SM, but 158 against 45
+    // pictures/s with eight pictures in flight.  (The queue order keeps ANY number of workers >= 1 deadlock-free.)
+    int max_ctas = ctx->num_sms * blocks_per_sm;
+    const int levels = b->lv.nb[p] > 0 ? b->lv.nb[p] : 1, want = 4 * (nb_items / levels + 1);
+    if (want < max_ctas) max_ctas = want > ctx->num_sms ? want : ctx->num_sms;
     StageScope scope(ctx, OVGPU_STAGE_INTRA, 1);
     ovd_recon_kernel<<<nb_items < max_ctas ? nb_items : max_ctas, 128, RECON_SMEM_BYTES, ctx->stream>>>(a);
     OVGPU_CUDA_CHECK(ctx, cudaGetLastError());

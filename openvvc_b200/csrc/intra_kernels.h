@@ -69,6 +69,7 @@ struct IntraK {
         uint64_t isp_cols, isp_rows;
         int warp_comps;             // 0, or (dataflow kernel, recon_kernels.h) the CTA owns ONE command: its threads split into warp_comps groups,
                                     // group k predicts component comp0 + k (1: luma, 2: Cb and Cr)
+        int predecoded;             // the block parameters are already in shared memory (predecode(), dataflow kernel): phase 0 does not derive them
     };
     struct State { int dummy; };
 
@@ -346,6 +347,20 @@ struct IntraK {
         return v;
     }
 
+    // The derivation alone, for callers that can run it ahead of time: the dataflow kernel derives a command's parameters BEFORE it
+    // waits for the command's neighbours (they depend on the command only), which takes the derivation off the dependency chain.
+    // Followed by a barrier, then the phases with Args::predecoded set.
+    OVD void predecode(const Args &a, unsigned char *smem, int tid, int bx, int by)
+    {
+        const int nl = a.warp_comps ? THREADS / a.warp_comps : 32;
+        const int warp = tid / nl, lane = tid - warp * nl;
+        if (lane) return;
+        const int comp = a.warp_comps ? a.comp0 + warp : a.comp0 + by;
+        Blk *const sblk = (Blk *)(smem + warp * SM_WARP + SM_REFS);
+        const Blk b = load(a, a.warp_comps ? bx : bx * WARPS + warp, comp);
+        if (b.valid) *sblk = b; else sblk->valid = 0;
+    }
+
     template <int P>
     OVD void phase(const Args &a, unsigned char *smem, State &st, int tid, int bx, int by, int bz)
     {
@@ -360,7 +375,7 @@ struct IntraK {
         // block's critical path (measured: 7.9 k of the 12 k cycles a block adds to the dependency chain).
         Blk *const sblk = (Blk *)(smem + warp * SM_WARP + SM_REFS);
         Blk b;
-        if (P == 0) {
+        if (P == 0 && !a.predecoded) {
             b = load(a, a.warp_comps ? bx : bx * WARPS + warp, comp);
             if (lane == 0) { if (b.valid) *sblk = b; else sblk->valid = 0; }
         } else b = *sblk;

@@ -88,6 +88,7 @@ OVD IntraK::Args recon_intra_args(const ReconArgs &a, const uint32_t *one_cmd)
     ia.log2_ctu = a.log2_ctu; ia.bitdepth = a.bitdepth; ia.cmds = a.cmds; ia.order = one_cmd; ia.nb = 1;
     ia.comp0 = a.plane_id; ia.warp_comps = a.plane_id ? 2 : 1;
     ia.isp_ox = ia.isp_oy = ia.isp_lpw = ia.isp_lph = 0; ia.isp_cols = ia.isp_rows = 0;
+    ia.predecoded = 0;
     return ia;
 }
 
@@ -216,6 +217,10 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
             if (it.large) { TrK<128>::Args ta = recon_tr_args<128>(a, sg.tb, 1); ta.cmds = sg.tu; RECON_TR_PHASES(128, tl, ta, 0, 2); }
             else          { TrK<32>::Args ta = recon_tr_args<32>(a, sg.tb, nk0); ta.cmds = sg.tu; RECON_TR_PHASES(32, ts, ta, 0, 2); }
         }
+        // ... and neither do the parameters the prediction derives from the command (plain blocks: an ISP command derives them per partition)
+        IntraK::Args ia = recon_intra_args(a, &sg.zero);
+        ia.cmds = &sg.cmd;
+        if (!ibc && !isp) { IntraK::predecode(ia, sm_intra, tid, 0, 0); ia.predecoded = 1; }
         if (ibc) {  // intra block copy: the units of the source block
             int ux0, uy0, ux1, uy1;
             ibc_source_units(c, &ux0, &uy0, &ux1, &uy1);
@@ -240,8 +245,6 @@ __global__ void __launch_bounds__(128, 8) ovd_recon_kernel(const ReconArgs a)
         }
         __threadfence();                                    // acquire side of the units' release stores (fence.acq_rel.gpu)
         __syncthreads();
-        IntraK::Args ia = recon_intra_args(a, &sg.zero);
-        ia.cmds = &sg.cmd;
         if (ibc) {
             ibc_copy(a.plane, a.pitch, a.plane_id, c, tid, 128);
             __syncthreads();

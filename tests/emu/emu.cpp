@@ -427,7 +427,12 @@ int emu_recon_picture(uint16_t *const planes[3], const int stride[3], int w, int
                 if (ibc) {
                     uint16_t *pl[3] = { planes[0], planes[1], planes[2] };
                     ibc_copy(pl, stride, p, *(const IntraCmdDev *)&c, 0, 1);
-                } else emu_phases<IntraK>(ia, sm + RECON_TR_SMEM_BYTES, 0, 3);
+                } else {
+                    // the parameters are derived ahead of the phases, as the kernel does before it waits for the neighbours
+                    for (int t = 0; t < IntraK::THREADS; t++) IntraK::predecode(ia, sm + RECON_TR_SMEM_BYTES, t, 0, 0);
+                    ia.predecoded = 1;
+                    emu_phases<IntraK>(ia, sm + RECON_TR_SMEM_BYTES, 0, 3);
+                }
                 if (nk0 && it.large) emu_phases<TrK<128> >(tl, sm, 3, 3);
                 else if (nk0) emu_phases<TrK<32> >(ts, sm, 3, 3);
                 if (it.large) for (int k = 1; k < it.nb_tb; k++) emu_tr_launch<128>(planes, stride, bitdepth, tus, items.data() + it.tb_start + k, 1, arena, &sl);
