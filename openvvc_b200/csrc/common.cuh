@@ -27,7 +27,25 @@ struct OVGPUCtx {
     // scratch used to flush L2 between timed iterations
     void *flush_buf;
     size_t flush_bytes;
+    // side streams for kernels of ONE stage that do not depend on each other (the six MC kernels work on disjoint blocks of the
+    // picture): forked from / joined to `stream` with events, so that one kernel's tail overlaps the others instead of idling
+    static const int NB_AUX = 5;
+    cudaStream_t aux[NB_AUX];
+    cudaEvent_t ev_fork, ev_join[NB_AUX];
+    int aux_init;
 };
+
+// creates the side streams on first use; 0 on success
+static inline int ovgpu_ctx_aux(OVGPUCtx *ctx)
+{
+    if (ctx->aux_init) return 0;
+    for (int i = 0; i < OVGPUCtx::NB_AUX; i++)
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) return -1;
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) return -1;
+    ctx->aux_init = 1;
+    return 0;
+}
 
 struct OVGPUPicture {
     int width, height, bitdepth;

@@ -88,6 +88,11 @@ void ovgpu_ctx_destroy(OVGPUCtx *ctx)
     if (ctx->ev_pool_init)
         for (int i = 0; i < 2 * OVGPUCtx::MAX_PENDING; i++) cudaEventDestroy(ctx->ev_pool[i]);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    for (int i = 0; i < OVGPUCtx::NB_AUX; i++) {
+        if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     free(ctx);
 }

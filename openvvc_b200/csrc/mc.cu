@@ -286,34 +286,50 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
     OVGPU_CUDA_CHECK(ctx, ovd_launch<McGuardK>(ga, dim3(1, 1, 1), 0, ctx->stream));
     ctx->launches += 1;
     StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0) + (b->nb_small_c > 0) + (b->nb_big > 0));
-    if (b->nb_big) {
-        McK::Args t = a;
-        t.items = d_items + 5 * b->max_items; t.nb_items = b->nb_big; t.limit = a.limit + 5;
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<McBigK>(t, dim3(OVGPU_CEIL_DIV(b->nb_big, McBigK::WARPS), 1, 1), McBigK::SMEM_BYTES, ctx->stream));
+    // The kernels work on disjoint blocks of the picture: they run side by side on the context's side streams (fork / join with
+    // events), the longest first, so that the tail of one fills with the others' CTAs instead of leaving SMs idle between launches.
+    static const int lanes = getenv("OVGPU_MC_LANES") ? atoi(getenv("OVGPU_MC_LANES")) : 2;      // streams the kernels are dealt over (1: serial)
+    const int par = lanes > 1 && ovgpu_ctx_aux(ctx) == 0;
+    int lane = 0, nb_used = 0;
+    cudaStream_t used[OVGPUCtx::NB_AUX];
+    if (par) OVGPU_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    auto next_stream = [&]() -> cudaStream_t {
+        const int l = par ? lane++ % (lanes < 1 + OVGPUCtx::NB_AUX ? lanes : 1 + OVGPUCtx::NB_AUX) : 0;
+        if (l == 0) return ctx->stream;
+        cudaStream_t s = ctx->aux[l - 1];
+        if (l > nb_used) { used[nb_used++] = s; cudaStreamWaitEvent(s, ctx->ev_fork, 0); }
+        return s;
+    };
+    if (b->nb_dmvr) {
+        DmvrK::Args t;
+        t.mc = a; t.mc.items = d_items + 3 * b->max_items; t.mc.nb_items = b->nb_dmvr; t.mc.limit = a.limit + 3; t.out = b->d_dmvr;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<DmvrK>(t, dim3(OVGPU_CEIL_DIV(b->nb_dmvr, DmvrK::WARPS), 1, 1), DmvrK::SMEM_BYTES, next_stream()));
     }
-    if (b->nb_items)
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, ctx->stream));
     if (b->nb_bdof) {
         McK::Args t = a;
         t.items = d_items + b->max_items; t.nb_items = b->nb_bdof; t.limit = a.limit + 1;
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, next_stream()));
+    }
+    if (b->nb_big) {
+        McK::Args t = a;
+        t.items = d_items + 5 * b->max_items; t.nb_items = b->nb_big; t.limit = a.limit + 5;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McBigK>(t, dim3(OVGPU_CEIL_DIV(b->nb_big, McBigK::WARPS), 1, 1), McBigK::SMEM_BYTES, next_stream()));
+    }
+    if (b->nb_items)
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McK>(a, dim3(OVGPU_CEIL_DIV(b->nb_items, McK::WARPS), 1, 1), McK::SMEM_BYTES, next_stream()));
+    if (b->nb_prof_items) {
+        ProfK::Args t;
+        t.mc = a; t.mc.items = d_items + 2 * b->max_items; t.mc.nb_items = b->nb_prof_items; t.mc.limit = a.limit + 2; t.prof = b->d_prof;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<ProfK>(t, dim3(OVGPU_CEIL_DIV(b->nb_prof_items, ProfK::WARPS * ProfK::SBS), 1, 1), ProfK::SMEM_BYTES, next_stream()));
     }
     if (b->nb_small_c) {
         McK::Args t = a;
         t.items = d_items + 4 * b->max_items; t.nb_items = b->nb_small_c; t.limit = a.limit + 4;
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<McSmallCK>(t, dim3(OVGPU_CEIL_DIV(b->nb_small_c, McSmallCK::WARPS * McSmallCK::SBS), 1, 1),
-                                                    McSmallCK::SMEM_BYTES, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McSmallCK>(t, dim3(OVGPU_CEIL_DIV(b->nb_small_c, McSmallCK::WARPS * McSmallCK::SBS), 1, 1), McSmallCK::SMEM_BYTES, next_stream()));
     }
-    if (b->nb_dmvr) {
-        DmvrK::Args t;
-        t.mc = a; t.mc.items = d_items + 3 * b->max_items; t.mc.nb_items = b->nb_dmvr; t.mc.limit = a.limit + 3; t.out = b->d_dmvr;
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<DmvrK>(t, dim3(OVGPU_CEIL_DIV(b->nb_dmvr, DmvrK::WARPS), 1, 1), DmvrK::SMEM_BYTES, ctx->stream));
-    }
-    if (b->nb_prof_items) {
-        ProfK::Args t;
-        t.mc = a; t.mc.items = d_items + 2 * b->max_items; t.mc.nb_items = b->nb_prof_items; t.mc.limit = a.limit + 2; t.prof = b->d_prof;
-        OVGPU_CUDA_CHECK(ctx, ovd_launch<ProfK>(t, dim3(OVGPU_CEIL_DIV(b->nb_prof_items, ProfK::WARPS * ProfK::SBS), 1, 1),
-                                                ProfK::SMEM_BYTES, ctx->stream));
+    for (int i = 0; i < nb_used; i++) {
+        OVGPU_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_join[i], used[i]));
+        OVGPU_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
     }
     OVGPU_CUDA_CHECK(ctx, cudaEventRecord(b->ev_status, ctx->stream));       // (McGuardK has stored the verdict in h_info)
     b->status_pending = 1; b->nb_cmds_run = b->nb_cmds; b->ran = 1;

@@ -34,7 +34,7 @@ struct OVGPUTuBatch {
 static_assert(sizeof(LmcsAnchorDev) == sizeof(OVGPULmcsAnchor) && sizeof(LmcsAnchorDev) == 8, "LMCS anchor layout");
 
 template <int GROUP>
-static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, const TbItemDev *items, int n)
+static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, const TbItemDev *items, int n, cudaStream_t stream)
 {
     typedef TrK<GROUP> K;
     typename K::Args a;
@@ -44,7 +44,7 @@ static cudaError_t launch_tr(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatc
     a.cmds = b->d_cmds; a.items = items; a.nb_items = n; a.arena = b->d_coeffs;
     a.dep_quant = b->slice.dep_quant; a.sh_ts_disabled = b->slice.sh_ts_disabled; a.ict_type = b->slice.ict_type;
     a.scales = b->nb_anchors ? b->d_scales : NULL;
-    return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, ctx->stream);
+    return ovd_launch<K>(a, dim3(OVGPU_CEIL_DIV(n, K::GROUPS), 1, 1), K::SMEM_BYTES, stream);
 }
 
 extern "C" {
@@ -196,8 +196,8 @@ int ovgpu_residual_picture(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch 
     const int nk = (b->nb_small > 0) + (b->nb_large > 0);
     if (!nk) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, nk);
-    if (b->nb_small) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items, b->nb_small));
-    if (b->nb_large) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->nb_small, b->nb_large));
+    if (b->nb_small) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items, b->nb_small, ctx->stream));
+    if (b->nb_large) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->nb_small, b->nb_large, ctx->stream));
     return 0;
 }
 
@@ -247,8 +247,19 @@ int ovgpu_tu_run_inter(OVGPUCtx *ctx, OVGPUPicture *pic, const OVGPUTuBatch *b, 
     const int ns = b->lists.n_small[p], nl = b->lists.n_large[p];
     if (!(ns + nl)) return 0;
     StageScope scope(ctx, OVGPU_STAGE_RESIDUAL, (ns > 0) + (nl > 0));
-    if (ns) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items + b->lists.start_small[p], ns));
-    if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->lists.start_large[p], nl));
+    // the two kernels work on different transform blocks: side by side (fork / join on a side stream of the context)
+    static const int tr_par = getenv("OVGPU_TR_PARALLEL") ? atoi(getenv("OVGPU_TR_PARALLEL")) : 1;
+    const int par = tr_par && ns && nl && ovgpu_ctx_aux(ctx) == 0;
+    if (par) {
+        OVGPU_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        OVGPU_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+    }
+    if (nl) OVGPU_CUDA_CHECK(ctx, launch_tr<128>(ctx, pic, b, b->d_items + b->lists.start_large[p], nl, ctx->stream));
+    if (ns) OVGPU_CUDA_CHECK(ctx, launch_tr<32>(ctx, pic, b, b->d_items + b->lists.start_small[p], ns, par ? ctx->aux[0] : ctx->stream));
+    if (par) {
+        OVGPU_CUDA_CHECK(ctx, cudaEventRecord(ctx->ev_join[0], ctx->aux[0]));
+        OVGPU_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+    }
     return 0;
 }
 
