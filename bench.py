@@ -400,7 +400,7 @@ def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl
         return sum(x.traffic()[0] for x in xds if x)
 
     n0 = sum(c.launch_count() for c in d_ctx)
-    order = sched.wave_order() if args.dag_wave else None
+    order = sched.wave_order(args.dag_wave) if args.dag_wave else None
     ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 0, 32 * W, order)
     join(); barrier()
     oracle_checked = 0
@@ -472,7 +472,7 @@ def main():
     ap.add_argument("--repeats", type=int, default=3, help="timed runs of exactly --steps steps each; the median run is reported, all are listed")
     ap.add_argument("--dag-lanes", type=int, default=1, help="communicators / exchange streams the GOPs of the --dag stream alternate over "
                     "(measured on 8 GPUs: 4 lanes = 56 pictures/s, concurrent communicators starve each other; kept for the record)")
-    ap.add_argument("--dag-wave", type=int, default=1, help="1: pictures are issued in wave order (a new GOP every two hierarchy levels) instead of decoding order")
+    ap.add_argument("--dag-wave", type=int, default=1, help="0: pictures are issued in decoding order; n: in wave order, a new GOP every n hierarchy levels (dist.py)")
     ap.add_argument("--e2e-dl-streams", type=int, default=0, help="1: the output copy of a picture runs on a stream of its own (measured: no gain)")
     args = ap.parse_args()
     w, h = SIZES[args.size]
