@@ -137,6 +137,19 @@ void ovo_mc_picture3(uint16_t *const dst[3], const int dst_stride[3], int pic_w,
                      const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd_lut,
                      const OVOProfInfo *prof_tab, OVODmvrMv *dmvr_out);
 
+/* Reference picture resampling (rcn_inter.c:1990-2747): per reference the scale factors the slice derived
+ * (inter_ctx->scale_fact_rpl0/1[ref_idx][hor, ver], ctudec.c:40-84; 1 << 14 = same size) and the reference's own size;
+ * the two chroma siting flags are the SPS's (dpb.c:1167-1168).  PLAIN, GPM and PROF commands may name scaled references
+ * (BDOF / DMVR are switched off by the decoder when a reference is scaled). */
+typedef struct OVOMcScaling {
+    uint16_t scale[2][16][2];
+    int32_t ref_w[2][16], ref_h[2][16];
+    uint8_t chroma_hor_col, chroma_ver_col;
+} OVOMcScaling;
+void ovo_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                        const OVOMcRefs *refs, const OVOMcScaling *sc, const OVOMcCmd *cmds, int nb_cmds,
+                        const uint16_t *lmcs_fwd_lut, const OVOProfInfo *prof_tab);
+
 /* ---- LMCS ------------------------------------------------------------------------------------------- */
 typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */
     uint8_t lmcs_min_bin_idx;

@@ -571,6 +571,192 @@ void ovo_mc_picture3(uint16_t *const dst[3], const int dst_stride[3], int pic_w,
 }
 
 /* ---------------------------------------------------------------------------------------------------
+ * Reference picture resampling: rcn_mcp_rpr_l / _bi_l / _c / _bi_c (rcn_inter.c:2025-2513), their combination
+ * rcn_mc_rpr_b_l / _b_c (:2524-2731, also the GPM path :3118-3146), rcn_mc_rpr_prof_b_l (:2594-2649), the dispatch on
+ * the slice's scale factors in rcn_mcp / rcn_mcp_b / _b_l / _b_c / rcn_prof_mcp_b_l (:2749-2966) and the filter
+ * kernels put_vvc_*_rpr_* (rcn_mc.c:535-785).
+ *
+ * A scaled reference is sampled on a grid of its own: output column c reads reference position
+ * (ref_pos_x + c * step) in 1/16 (chroma 1/32) sample units scaled by 2^14, one separable pass per direction with the
+ * 14-bit intermediate kept as int16.  The reference position is clipped so that the window stays within four samples
+ * of the reference picture (clip_rpr_position), the window border is replicated (emulate_block_border).
+ * ------------------------------------------------------------------------------------------------- */
+#include "mc_rpr_tables.h"
+
+static int rpr_filter_idx(int scale, int flag_4x4)
+{   /* compute_rpr_filter_idx, rcn_inter.c:1990-2006: thresholds 1.25 and 1.75 in 2^14 units */
+    int idx = flag_4x4 ? 3 : 0;
+    if (scale > (1 << 14) * 7 / 4) idx += 2;
+    else if (scale > (1 << 14) * 5 / 4) idx += 1;
+    return idx;
+}
+
+/* One component of one PU from one SCALED reference.  uni != 0: final clipped samples (rpr_v_uni); else the 14-bit
+ * prediction as int16 (rpr_v_bi).  Output stride 128.  pos / pu sizes in samples of the component. */
+static void rpr_pred(int16_t *out, const RefPlane *r, int chroma, int pos_x, int pos_y, int pu_w, int pu_h, int flag_4x4,
+                     MV mv, int scale_h, int scale_v, int hor_col, int ver_col, int bitdepth, int uni)
+{
+    const int shift_mv = chroma ? 5 : 4, shift_pos = 14 + shift_mv, offset = 1 << 13, fmask = (1 << shift_mv) - 1;
+    const int nt = chroma ? 4 : 8, before = chroma ? 1 : 3;
+    int fih = rpr_filter_idx(scale_h, flag_4x4), fiv = rpr_filter_idx(scale_v, flag_4x4);
+    /* chroma (rcn_inter.c:2300-2301) looks the same index up in a table of three sets: the 4x4 flag would read past it,
+     * a 4x4 luma block has 2x2 chroma blocks that no conforming stream predicts on their own */
+    if (chroma) { fih %= 3; fiv %= 3; }
+    const int stepX = ((scale_h + 8) >> 4) << 4, stepY = ((scale_v + 8) >> 4) << 4;
+    /* 32-bit products as the reference computes them (they wrap beyond 2^31 for 8K positions at 2x) */
+    int32_t ref_pos_x = (int32_t)((uint32_t)((pos_x << shift_mv) + mv.x) * (uint32_t)scale_h);
+    int32_t ref_pos_y = (int32_t)((uint32_t)((pos_y << shift_mv) + mv.y) * (uint32_t)scale_v);
+    if (chroma) {
+        ref_pos_x += (1 - hor_col) * 8 * (scale_h - (1 << 14)) + (1 << 8);
+        ref_pos_y += (1 - ver_col) * 8 * (scale_v - (1 << 14)) + (1 << 8);
+    } else { ref_pos_x += 1 << 7; ref_pos_y += 1 << 7; }
+    int ref_x = (ref_pos_x + offset) >> shift_pos, ref_y = (ref_pos_y + offset) >> shift_pos;
+    int ref_pu_w = ((ref_pos_x + (((pu_w - 1) * stepX) << shift_mv) + offset) >> shift_pos) - ref_x + 1;
+    int ref_pu_h = ((ref_pos_y + (((pu_h - 1) * stepY) << shift_mv) + offset) >> shift_pos) - ref_y + 1;
+    if (ref_pu_h < 1) ref_pu_h = 1;
+    {   /* clip_rpr_position, rcn_inter.c:2009-2022 */
+        int prec_x = ref_pos_x & ((1 << shift_pos) - 1), prec_y = ref_pos_y & ((1 << shift_pos) - 1);
+        int x_max = (r->w + 3) << shift_pos, y_max = (r->h + 3) << shift_pos;
+        int x_min = -((ref_pu_w + 4) << shift_pos), y_min = -((ref_pu_h + 4) << shift_pos);
+        ref_pos_x = clipi(ref_pos_x, x_min + prec_x, x_max + prec_x);
+        ref_pos_y = clipi(ref_pos_y, y_min + prec_y, y_max + prec_y);
+    }
+    ref_x = (ref_pos_x + offset) >> shift_pos; ref_y = (ref_pos_y + offset) >> shift_pos;
+    const int rows = ref_pu_h + nt;                       /* the rows the vertical pass can reach: ref_y - before .. */
+    int16_t *tmp = malloc((size_t)rows * pu_w * sizeof(int16_t));
+    for (int col = 0; col < pu_w; col++) {
+        int pos_mv_x = (ref_pos_x + ((col * stepX) << shift_mv) + offset) >> 14;
+        int prec_x = pos_mv_x & fmask, xi = pos_mv_x >> shift_mv;
+        const int8_t *f = chroma ? mc_rpr_c[fih][prec_x] : mc_rpr_l[fih][prec_x];
+        for (int rr = 0; rr < rows; rr++) {
+            int y = ref_y - before + rr, v;
+            if (!fih && !prec_x) v = rpx(r, xi, y) << (14 - bitdepth);                      /* put_vvc_pel_rpr */
+            else {
+                int sacc = 0;
+                for (int k = 0; k < nt; k++) sacc += f[k] * rpx(r, xi + k - before, y);
+                v = sacc >> (bitdepth - 8);                                                  /* put_vvc_{q,e}pel_rpr_h */
+            }
+            tmp[rr * pu_w + col] = (int16_t)v;
+        }
+    }
+    const int shift = 14 - bitdepth, off = 1 << (shift - 1), maxv = (1 << bitdepth) - 1;
+    for (int row = 0; row < pu_h; row++) {
+        int pos_mv_y = (ref_pos_y + ((row * stepY) << shift_mv) + offset) >> 14;
+        int prec_y = pos_mv_y & fmask, rb = (pos_mv_y >> shift_mv) - ref_y;
+        const int8_t *f = chroma ? mc_rpr_c[fiv][prec_y] : mc_rpr_l[fiv][prec_y];
+        for (int x = 0; x < pu_w; x++) {
+            int v;
+            if (!fiv && !prec_y) {
+                /* put_vvc_pel_rpr_clip reads the intermediate as UNSIGNED 16 bit (rcn_mc.c:623-642): a negative one saturates high */
+                if (uni) v = clipi(((uint16_t)tmp[(rb + before) * pu_w + x] + off) >> shift, 0, maxv);
+                else     v = tmp[(rb + before) * pu_w + x];                                  /* put_vvc_pel_rpr_bi */
+            } else {
+                int sacc = 0;
+                for (int k = 0; k < nt; k++) sacc += f[k] * tmp[(rb + k) * pu_w + x];
+                if (uni) v = clipi(((sacc >> 6) + off) >> shift, 0, maxv);                   /* put_vvc_*_rpr_clip_v */
+                else     v = (int16_t)(sacc >> 6);                                           /* put_vvc_*_rpr_bi_v */
+            }
+            out[row * 128 + x] = (int16_t)v;
+        }
+    }
+    free(tmp);
+}
+
+static int rpr_scaled(const OVOMcScaling *sc, int list, int idx) { return sc->scale[list][idx][0] != (1 << 14) || sc->scale[list][idx][1] != (1 << 14); }
+
+/* 14-bit prediction (or, uni, final samples) of one component from either kind of reference */
+static void rpr_any_pred(int16_t *out, const OVOMcRefs *refs, const OVOMcScaling *sc, int list, int ref_idx, int comp,
+                         int pic_w, int pic_h, const OVOMcCmd *c, MV mv, int bitdepth, int uni)
+{
+    if (!rpr_scaled(sc, list, ref_idx)) {                 /* rcn_mcp_bidir0_l / _c; uni: the caller rounds */
+        pu_pred14(out, refs, list, ref_idx, comp, pic_w, pic_h, c, mv, bitdepth);
+        return;
+    }
+    const int sh = comp ? 1 : 0;
+    RefPlane r = { refs->plane[list][ref_idx][comp], refs->stride[list][ref_idx][comp], sc->ref_w[list][ref_idx] >> sh, sc->ref_h[list][ref_idx] >> sh };
+    rpr_pred(out, &r, comp != 0, c->x0 >> sh, c->y0 >> sh, (1 << c->log2_w) >> sh, (1 << c->log2_h) >> sh,
+             c->log2_w == 2 && c->log2_h == 2, mv, sc->scale[list][ref_idx][0], sc->scale[list][ref_idx][1],
+             sc->chroma_hor_col, sc->chroma_ver_col, bitdepth, uni);
+}
+
+void ovo_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int bitdepth,
+                        const OVOMcRefs *refs, const OVOMcScaling *sc, const OVOMcCmd *cmds, int nb_cmds,
+                        const uint16_t *lmcs_fwd_lut, const OVOProfInfo *prof_tab)
+{
+    int16_t *p0 = malloc(2 * 128 * 128 * sizeof(int16_t)), *p1 = p0 + 128 * 128;
+    const int maxv = (1 << bitdepth) - 1;
+    for (int i = 0; i < nb_cmds; i++) {
+        const OVOMcCmd *c = &cmds[i];
+        const int gpm = c->tool == OVO_MC_TOOL_GPM;
+        MV mv0 = { c->mv0_x, c->mv0_y }, mv1 = { c->mv1_x, c->mv1_y };
+        int l0 = 0, l1 = 1;
+        if (gpm) { l0 = (c->aux >> 8) & 1; l1 = (c->aux >> 9) & 1; }
+        const int identical = c->tool == OVO_MC_TOOL_PLAIN && c->inter_dir == 3 &&
+                              (uint16_t)refs->poc[0][c->ref_idx0] == (uint16_t)refs->poc[1][c->ref_idx1] && mv0.x == mv1.x && mv0.y == mv1.y;
+        const int bi = gpm || (c->inter_dir == 3 && !identical);
+        const int uni_list = (c->inter_dir & 2 || identical) ? 1 : 0;
+        const int s0 = (bi || !uni_list) && rpr_scaled(sc, l0, c->ref_idx0), s1 = (bi || uni_list) && rpr_scaled(sc, l1, c->ref_idx1);
+        if ((c->tool != OVO_MC_TOOL_PLAIN && c->tool != OVO_MC_TOOL_GPM && c->tool != OVO_MC_TOOL_PROF) || (!s0 && !s1)) {
+            ovo_mc_picture3(dst, dst_stride, pic_w, pic_h, bitdepth, refs, c, 1, lmcs_fwd_lut, prof_tab, NULL);
+            continue;
+        }
+        for (int comp = 0; comp < 3; comp++) {
+            if (comp == 0 && !(c->flags & OVO_MC_LUMA)) continue;
+            if (comp != 0 && !(c->flags & OVO_MC_CHROMA)) continue;
+            const int sh = comp ? 1 : 0, w = (1 << c->log2_w) >> sh, h = (1 << c->log2_h) >> sh;
+            uint16_t *d = dst[comp] + (size_t)(c->y0 >> sh) * dst_stride[comp] + (c->x0 >> sh);
+            if (!bi) {                                    /* rcn_mcp_rpr_l / _c; a PROF command of a scaled reference is plain (:2895-2917) */
+                rpr_any_pred(p0, refs, sc, uni_list, uni_list ? c->ref_idx1 : c->ref_idx0, comp, pic_w, pic_h, c, uni_list ? mv1 : mv0, bitdepth, 1);
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) d[(size_t)y * dst_stride[comp] + x] = (uint16_t)p0[y * 128 + x];
+            } else {
+                const int prof_dir = c->tool == OVO_MC_TOOL_PROF ? (int)(c->aux & 3) : 0;
+                for (int l = 0; l < 2; l++) {
+                    int16_t *pb = l ? p1 : p0;
+                    const int list = l ? l1 : l0, scaled = l ? s1 : s0, ridx = l ? c->ref_idx1 : c->ref_idx0;
+                    const MV mv = l ? mv1 : mv0;
+                    if (!scaled && ((prof_dir >> l) & 1)) {
+                        /* rcn_mc_rpr_prof_b_l (apply_prof, :2880): the one unscaled list of a mixed bi-prediction is refined by
+                         * rcn_prof_mcp_bi_l when its prof_dir bit is set; the scaled list never is */
+                        const OVOProfInfo *pi = &prof_tab[c->aux >> 8];
+                        int16_t P[PS * PS], gx[PS * PS], gy[PS * PS];
+                        padded_pred14(P, refs, list, ridx, pic_w, pic_h, c->x0, c->y0, 4, 4, mv, (c->flags & OVO_MC_HPEL_AMVR) != 0, bitdepth);
+                        pad_grad(gx, gy, P, 4, 4);
+                        const int16_t *dh = l ? pi->dmv_scale_h_1 : pi->dmv_scale_h_0, *dv = l ? pi->dmv_scale_v_1 : pi->dmv_scale_v_0;
+                        for (int y = 0; y < 4; y++)
+                            for (int x = 0; x < 4; x++) {
+                                int o = (y + 1) * PS + x + 1;
+                                pb[y * 128 + x] = (int16_t)(P[o] + clipi(dh[4 * y + x] * gx[o] + dv[4 * y + x] * gy[o], -8192, 8191));
+                            }
+                        continue;
+                    }
+                    rpr_any_pred(pb, refs, sc, list, ridx, comp, pic_w, pic_h, c, mv, bitdepth, 0);
+                }
+                const int def = gpm || c->bcw_idx_plus1 == 0 || c->bcw_idx_plus1 == 3;
+                const int w1 = def ? 0 : bcw_w[c->bcw_idx_plus1 - 1], w0 = 8 - w1;
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) {
+                        int a = p0[y * 128 + x], b = p1[y * 128 + x], v;
+                        if (gpm) {                        /* put_weighted_gpm_bi_pixels */
+                            int g0 = gpm_weight(c->aux & 63, c->log2_w, c->log2_h, x << sh, y << sh);
+                            v = (b * (8 - g0) + a * g0 + (1 << (16 - bitdepth))) >> (17 - bitdepth);
+                        } else if (def) v = (a + b + (1 << (14 - bitdepth))) >> (15 - bitdepth);              /* put_vvc_qpel_rpr_bi_sum */
+                        else            v = (a * w0 + b * w1 + (1 << (16 - bitdepth))) >> (17 - bitdepth);   /* put_vvc_qpel_rpr_weighted, denom 3 */
+                        d[(size_t)y * dst_stride[comp] + x] = (uint16_t)clipi(v, 0, maxv);
+                    }
+            }
+            if (comp == 0 && lmcs_fwd_lut)
+                for (int y = 0; y < h; y++)
+                    for (int x = 0; x < w; x++) {
+                        uint16_t *q = &d[(size_t)y * dst_stride[0] + x];
+                        *q = lmcs_fwd_lut[*q & maxv];
+                    }
+        }
+    }
+    free(p0);
+}
+
+/* ---------------------------------------------------------------------------------------------------
  * LMCS look-up tables (rcn_lmcs.c:84-187, 189-203)
  * ------------------------------------------------------------------------------------------------- */
 void ovo_lmcs_build_luts(OVOLmcsLuts *luts, const OVOLmcsData *data, int bitdepth)

@@ -235,6 +235,49 @@ def make_mc_refs(ref_lists, pocs):
     return r, keep
 
 
+class McScaling(C.Structure):
+    """OVOMcScaling (oracle.h): scale[list][ref_idx][hor, ver] in 2^-14 units, the references' own sizes, the SPS's chroma siting"""
+    _fields_ = [("scale", C.c_uint16 * 2 * 16 * 2), ("ref_w", C.c_int32 * 16 * 2), ("ref_h", C.c_int32 * 16 * 2),
+                ("chroma_hor_col", C.c_uint8), ("chroma_ver_col", C.c_uint8)]
+
+
+def make_mc_scaling(w, h, ref_lists, hor_col=1, ver_col=0):
+    """scale factors as ctudec_compute_refs_scaling derives them (ctudec.c:42-84), no scaling-window offsets"""
+    sc = McScaling()
+    for l in range(2):
+        for i in range(16):
+            sc.scale[l][i][0] = sc.scale[l][i][1] = 1 << 14
+            sc.ref_w[l][i] = w; sc.ref_h[l][i] = h
+        for i, pic in enumerate(ref_lists[l]):
+            rh, rw = pic[0].shape
+            sc.ref_w[l][i] = rw; sc.ref_h[l][i] = rh
+            sc.scale[l][i][0] = ((rw << 14) + (w >> 1)) // w
+            sc.scale[l][i][1] = ((rh << 14) + (h >> 1)) // h
+    sc.chroma_hor_col = hor_col; sc.chroma_ver_col = ver_col
+    return sc
+
+
+def mc_picture_rpr(dst_planes, ref_lists, pocs, cmds, sc, log2_ctu=7, bitdepth=10, impl="port", lmcs=None, prof=None, simd=0):
+    """mc_picture with references of their own sizes (reference picture resampling); sc = make_mc_scaling(...)"""
+    h, w = dst_planes[0].shape
+    cmds = np.ascontiguousarray(cmds, dtype=McCmd)
+    refs, keep = make_mc_refs(ref_lists, pocs)
+    dst, ds = _planes_arg(dst_planes)
+    prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
+    pp = prof.ctypes.data_as(C.c_void_p) if prof is not None else None
+    if impl == "port":
+        lut = lmcs.np("fwd_lut").ctypes.data_as(u16p) if lmcs is not None else None
+        f = port().ovo_mc_picture_rpr
+        f.restype = None
+        f(dst, ds, w, h, bitdepth, C.byref(refs), C.byref(sc), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut, pp)
+    else:
+        f = ref().ovref_mc_picture_rpr
+        f.restype = None
+        f(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(refs), C.byref(sc), cmds.ctypes.data_as(C.c_void_p), len(cmds), pp,
+          C.byref(lmcs) if lmcs is not None else None)
+    return dst_planes
+
+
 DmvrMv = np.dtype([("mv0_x", np.int32), ("mv0_y", np.int32), ("mv1_x", np.int32), ("mv1_y", np.int32)])
 
 

@@ -314,10 +314,12 @@ ovref_lmcs_build_luts(OVOLmcsLuts *out, const OVOLmcsData *d, int bitdepth)
     free(c);
 }
 
-void
-ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
-                 int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const OVOProfInfo *prof_tab,
-                 const OVOLmcsLuts *lmcs, OVODmvrMv *dmvr_out)
+/* sc != NULL: reference picture resampling -- the references have their own sizes and the slice's scale factors
+ * (inter_ctx->scale_fact_rpl0/1, ctudec.c:40-84) send the stock slots down their rcn_mcp_rpr_* paths (rcn_inter.c:1990-2747) */
+static void
+mc_picture_impl(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
+                int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcScaling *sc, const OVOMcCmd *cmds, int nb_cmds,
+                const OVOProfInfo *prof_tab, const OVOLmcsLuts *lmcs, OVODmvrMv *dmvr_out)
 {
     OVCTUDec *c;
     OVPartInfo part;
@@ -349,13 +351,19 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
     struct InterDRVCtx *ic = &c->drv_ctx.inter_ctx;
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
+            /* rcn_mcp_rpr_c reads rpl0[ref_idx]->scale_info whatever the list (rcn_inter.c:2305): every entry gets a picture */
+            if (sc) {
+                pics[l][i].scale_info.chroma_hor_col_flag = sc->chroma_hor_col;
+                pics[l][i].scale_info.chroma_ver_col_flag = sc->chroma_ver_col;
+                if (l == 0) ic->rpl0[i] = &pics[l][i]; else ic->rpl1[i] = &pics[l][i];
+            }
             if (!refs->plane[l][i][0]) continue;
             OVFrame *f = &frames[l][i];
             for (int k = 0; k < 3; k++) {
                 f->data[k] = (void *)refs->plane[l][i][k];
                 f->linesize[k] = (size_t)refs->stride[l][i][k] * sizeof(uint16_t);
             }
-            f->width = pic_w; f->height = pic_h;
+            f->width = sc ? sc->ref_w[l][i] : pic_w; f->height = sc ? sc->ref_h[l][i] : pic_h;
             pics[l][i].frame = f;
             pics[l][i].poc = refs->poc[l][i];
             atomic_init(&pics[l][i].idx_function, 0);
@@ -363,6 +371,11 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
             pics[l][i].ovdpb_frame_synchro[1] = harness_no_synchro;
             if (l == 0) { ic->rpl0[i] = &pics[l][i]; ic->scale_fact_rpl0[i][0] = ic->scale_fact_rpl0[i][1] = 1 << 14; }
             else        { ic->rpl1[i] = &pics[l][i]; ic->scale_fact_rpl1[i][0] = ic->scale_fact_rpl1[i][1] = 1 << 14; }
+            if (sc)
+                for (int k = 0; k < 2; k++) {
+                    if (l == 0) ic->scale_fact_rpl0[i][k] = sc->scale[l][i][k];
+                    else        ic->scale_fact_rpl1[i][k] = sc->scale[l][i][k];
+                }
         }
 
     for (int n = 0; n < nb_cmds; n++) {
@@ -416,4 +429,39 @@ ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int
     if (lmcs) free(c->lmcs_info.luts);
     free(c);
     free(pics); free(frames); free(scr);
+}
+
+void
+ovref_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
+                 int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcCmd *cmds, int nb_cmds, const OVOProfInfo *prof_tab,
+                 const OVOLmcsLuts *lmcs, OVODmvrMv *dmvr_out)
+{
+    mc_picture_impl(dst, dst_stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd, refs, NULL, cmds, nb_cmds, prof_tab, lmcs, dmvr_out);
+}
+
+void
+ovref_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int pic_w, int pic_h, int log2_ctu_s,
+                     int bitdepth, int simd, const OVOMcRefs *refs, const OVOMcScaling *sc, const OVOMcCmd *cmds, int nb_cmds,
+                     const OVOProfInfo *prof_tab, const OVOLmcsLuts *lmcs)
+{
+    mc_picture_impl(dst, dst_stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd, refs, sc, cmds, nb_cmds, prof_tab, lmcs, NULL);
+}
+
+/* Taps of the resampling filters (ov_mc_filters_rpr / ov_mc_filters_rpr_c, static in rcn_mc.c:165-379), read back through the
+ * scalar mc_l / mc_c .rpr_h[1][1] slots by impulse probing: a sample of value 4 at tap k gives taps[k] * 4 >> (10 - 8). */
+int
+ovref_rpr_taps(int chroma, int filter_idx, int frac, int16_t *taps)
+{
+    struct RCNFunctions f;
+    memset(&f, 0, sizeof(f));
+    rcn_init_mc_functions_10(&f);
+    const int nt = chroma ? 4 : 8, before = chroma ? 1 : 3;
+    if (filter_idx < 0 || filter_idx >= (chroma ? 3 : 6) || frac < 0 || frac >= (chroma ? 32 : 16)) return -1;
+    for (int k = 0; k < nt; k++) {
+        uint16_t src[16] = { 0 }, out[4] = { 0 };
+        src[4 - before + k] = 4;
+        (chroma ? f.mc_c.rpr_h[1][1] : f.mc_l.rpr_h[1][1])(out, 4, src + 4, 16, 1, frac, 0, 1, (uint8_t)filter_idx);
+        taps[k] = (int16_t)out[0];
+    }
+    return 0;
 }

@@ -82,3 +82,21 @@ def gpu_mc(ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=None, dmvr_out=None):
         for p in lst:
             p.destroy()
     return out
+
+
+# reference picture resampling: reference sizes as (num, den) of the picture size, per list -- 2x, 1.5x (the two ratios VTM's
+# RPR configurations use), same size, and small references that are up-sampled
+RPR_RATIOS = [[(2, 1), (1, 1), (3, 2)], [(1, 2), (1, 1), (1, 4)]]
+
+
+def rpr_case(po, w, h, seed, log2_ctu=7, lmcs=False, kind="natural", hor_col=1, ver_col=0, p_gpm=0.15, p_affine=0.2):
+    """PU list (plain uni / bi / BCW, affine 4x4 with PROF, GPM) over references of their own sizes.
+    Returns (refs0, refs1, pocs, cmds, luts, prof, scaling)."""
+    def size(r):
+        return (w * r[0] // r[1]) & ~7, (h * r[0] // r[1]) & ~7
+    refs0 = [synth.planes(*size(r), seed + 10 + i, kind) for i, r in enumerate(RPR_RATIOS[0])]
+    refs1 = [synth.planes(*size(r), seed + 20 + i, kind) for i, r in enumerate(RPR_RATIOS[1])]
+    pocs = [[8, 16, 24], [16, 24, 32]]
+    cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, n_refs=3, p_bdof=0.0, p_affine=p_affine, p_gpm=p_gpm)
+    luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
+    return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof, po.make_mc_scaling(w, h, [refs0, refs1], hor_col, ver_col)

@@ -346,3 +346,51 @@ def test_dmvr_gpu_full_size_4k_vs_reference(oracle, gpu_ctx):
     oracle.mc_picture(a, [refs0, refs1], pocs, cmds, 7, impl="ref" if oracle.ref_available() else "port", lmcs=luts, prof=prof, dmvr_out=ma)
     helpers.assert_planes_equal(helpers_mc.gpu_mc(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, prof=prof, dmvr_out=mb), a, "CUDA DMVR vs reference at 4K")
     assert helpers.md5(ma) == helpers.md5(mb)
+
+
+# ================================================================================================ reference picture resampling (a17)
+RPR_GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mc_rpr_golden.json")))
+RIDS = lambda c: "%dx%d_ctu%d_%s%s" % (c["w"], c["h"], 1 << c["log2_ctu"], c["kind"], "_lmcs" if c["lmcs"] else "")
+
+
+def _rpr_case(po, c):
+    case = helpers_mc.rpr_case(po, c["w"], c["h"], c["seed"], c["log2_ctu"], c["lmcs"], c["kind"], c["hor_col"], c["ver_col"])
+    refs0, refs1, pocs, cmds, luts, prof, sc = case
+    assert helpers.md5(cmds, prof, *refs0[0], *refs1[-1]) == c["input_md5"], "synthetic generator drifted; regenerate golden"
+    return case
+
+
+@pytest.mark.parametrize("c", RPR_GOLDEN, ids=RIDS)
+def test_rpr_port_matches_golden(oracle, c):
+    """rcn_mcp_rpr_* / rcn_mc_rpr_b_* / rcn_mc_rpr_prof_b_l (a17): plain uni / bi / BCW, GPM and affine 4x4 (PROF on the unscaled
+    list of a mixed bi-prediction) from references 2x, 1.5x, 1x, 1/2 and 1/4 the picture's size"""
+    refs0, refs1, pocs, cmds, luts, prof, sc = _rpr_case(oracle, c)
+    used = set()
+    for m in cmds:
+        if m["inter_dir"] & 1:
+            used.add((0, int(m["ref_idx0"])))
+        if m["inter_dir"] & 2:
+            used.add((1, int(m["ref_idx1"])))
+    assert len(used) == 6 and set(cmds["tool"].tolist()) >= {0, 2, 4}
+    dst = helpers_mc.blank(c["w"], c["h"])
+    oracle.mc_picture_rpr(dst, [refs0, refs1], pocs, cmds, sc, c["log2_ctu"], impl="port", lmcs=luts, prof=prof)
+    assert [helpers.md5(p) for p in dst] == c["md5"]
+
+
+@pytest.mark.parametrize("w,h,log2,lmcs,kind,hc,vc", [(416, 240, 7, False, "natural", 1, 0), (320, 192, 7, True, "noise", 0, 0),
+                                                      (264, 136, 6, True, "noise", 1, 1), (200, 120, 5, False, "natural", 0, 1)])
+def test_rpr_port_vs_compiled_reference(oracle, w, h, log2, lmcs, kind, hc, vc):
+    """scalar C templates (arithmetic of record) and the SSE4.1 / AVX2 table.  Noise planes reach the reference's unsigned read of
+    a negative intermediate in put_vvc_pel_rpr_clip (rcn_mc.c:623-642), which the port reproduces."""
+    po = oracle
+    if not po.ref_available():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    refs0, refs1, pocs, cmds, luts, prof, sc = helpers_mc.rpr_case(po, w, h, 5 * w + h + 1, log2, lmcs, kind, hc, vc)
+    a = helpers_mc.blank(w, h)
+    po.mc_picture_rpr(a, [refs0, refs1], pocs, cmds, sc, log2, impl="port", lmcs=luts, prof=prof)
+    # the SSE / AVX2 kernels read that intermediate as signed, so they agree with the C templates only where it is not negative
+    # (natural content); the C templates are the arithmetic of record (DESIGN.md section 2)
+    for simd in ((0, 1) if kind == "natural" else (0,)):
+        b = helpers_mc.blank(w, h)
+        po.mc_picture_rpr(b, [refs0, refs1], pocs, cmds, sc, log2, impl="ref", lmcs=luts, prof=prof, simd=simd)
+        helpers.assert_planes_equal(a, b, "RPR port vs reference (simd=%d)" % simd)
