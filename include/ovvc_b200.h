@@ -253,6 +253,15 @@ typedef struct OVGPUMcRefs {
     int32_t poc[2][16];
 } OVGPUMcRefs;
 
+/* Reference picture resampling (replaces the rcn_mcp_rpr_* / rcn_mc_rpr_b_* / rcn_mc_rpr_prof_b_l paths the stock slots take
+ * when a scale factor differs from 1, rcn_inter.c:1990-2747, 2749-2966): the slice's scale factors
+ * inter_ctx->scale_fact_rpl0 / 1 [ref_idx][hor, ver] (ctudec.h:351-352, derived in ctudec_compute_refs_scaling, ctudec.c:42-84;
+ * 1 << 14 = same size, 0 = entry not in use) and the SPS's chroma sample siting (OVPicture.scale_info, dpb.c:1167-1168). */
+typedef struct OVGPUMcScaling {
+    uint16_t scale[2][16][2];
+    uint8_t chroma_hor_col, chroma_ver_col, pad[2];
+} OVGPUMcScaling;
+
 typedef struct OVGPUMcBatch OVGPUMcBatch;   /* pinned staging + device copy of one picture's PU list */
 int  ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBatch **b);
 void ovgpu_mc_batch_destroy(OVGPUMcBatch *b);
@@ -261,6 +270,11 @@ int  ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmd
 /* same, with the PROF table that OVGPU_MC_TOOL_PROF commands index (may be NULL when nb_prof == 0) */
 int  ovgpu_mc_batch_upload2(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds,
                             const OVGPUProfInfo *prof, int nb_prof);
+/* The scale factors the batch's NEXT upload / commit is routed by (NULL: none scaled, the default): PLAIN, PROF and GPM commands
+ * that name a scaled reference go to the resampling kernel, BDOF / DMVR commands that do are malformed (the decoder switches
+ * both tools off for such CUs).  ovgpu_mc_picture then accepts references whose size differs from the picture's for exactly
+ * those entries.  Host-side state only; call it before the commit of every picture whose factors differ from the last one's. */
+int  ovgpu_mc_batch_set_scaling(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcScaling *scaling);
 /* Zero-copy staging: _staging returns the batch's PINNED command (and PROF table) buffers for the recorder to fill,
  * _commit validates, builds the work lists in one pass and issues the asynchronous H2D copies. */
 int  ovgpu_mc_batch_staging(OVGPUCtx *ctx, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof);

@@ -245,6 +245,11 @@ class McRefs(C.Structure):
     _fields_ = [("rpl", vp * 16 * 2), ("poc", C.c_int32 * 16 * 2)]
 
 
+class McScaling(C.Structure):
+    """OVGPUMcScaling: scale[list][ref_idx][hor, ver] (inter_ctx->scale_fact_rpl0 / 1, 1 << 14 = same size) + chroma siting flags"""
+    _fields_ = [("scale", C.c_uint16 * 2 * 16 * 2), ("chroma_hor_col", C.c_uint8), ("chroma_ver_col", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
 class LmcsData(C.Structure):
     _fields_ = [("lmcs_min_bin_idx", C.c_uint8), ("lmcs_delta_max_bin_idx", C.c_uint8),
                 ("lmcs_delta_cw_prec_minus1", C.c_uint8), ("lmcs_delta_abs_cw", C.c_uint16 * 16),
@@ -397,6 +402,18 @@ class McBatch:
         _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_upload2((ctx or self.ctx).h, self.p, vp(cmds.ctypes.data), len(cmds),
                                                                  vp(prof.ctypes.data) if prof is not None else None,
                                                                  len(prof) if prof is not None else 0), "mc_batch_upload2")
+
+    def set_scaling(self, scale=None, hor_col=1, ver_col=0, ctx=None):
+        """ovgpu_mc_batch_set_scaling: scale[list][ref_idx] = (hor, ver) factors of the NEXT upload / commit; None = no reference scaled"""
+        if scale is None:
+            _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_set_scaling((ctx or self.ctx).h, self.p, None), "mc_batch_set_scaling")
+            return
+        sc = McScaling()
+        for l in range(2):
+            for i, (sh, sv) in enumerate(scale[l]):
+                sc.scale[l][i][0] = int(sh); sc.scale[l][i][1] = int(sv)
+        sc.chroma_hor_col = int(hor_col); sc.chroma_ver_col = int(ver_col)
+        _check((ctx or self.ctx).h, lib().ovgpu_mc_batch_set_scaling((ctx or self.ctx).h, self.p, C.byref(sc)), "mc_batch_set_scaling")
 
     def staging(self, ctx=None):
         """numpy views of the batch's PINNED command and PROF-table buffers (ovgpu_mc_batch_staging)"""

@@ -10,10 +10,12 @@ static_assert(sizeof(McCmdDev) == sizeof(OVGPUMcCmd) && sizeof(McCmdDev) == 32, 
 struct OVGPUMcBatch {
     int max_cmds, max_items, nb_cmds, nb_items, device;
     int nb_bdof, nb_prof_items, nb_prof;      // BDOF / PROF work items (appended to the item list), PROF table entries
-    int nb_dmvr, nb_small_c, nb_big;
+    int nb_dmvr, nb_small_c, nb_big, nb_rpr;
+    OVGPUMcScaling scaling;                   // ovgpu_mc_batch_set_scaling: the slice's scale factors (all 1 << 14 by default)
+    uint32_t scaled[2];                       // ... and the reference indices whose factor is not 1, per list
     DmvrMvDev *d_dmvr, *h_dmvr;               // refined MVs, one per DMVR item (device result + pinned read-back)
     McCmdDev *h_cmds, *d_cmds;
-    McItemDev *d_items;                       // six regions of max_items entries: plain | BDOF | PROF | DMVR | small chroma | big tiles,
+    McItemDev *d_items;                       // seven regions of max_items entries: plain | BDOF | PROF | DMVR | small chroma | big tiles | scaled,
                                               // built on the device by McPrep*K (mc_host.h)
     int32_t *d_block_sum;                     // scratch of the device-side list construction: [region][block of 256 commands]
     McPrepInfo *d_info, *h_info;              // its result (item counts, extents, references, first malformed command) + pinned copy
@@ -140,6 +142,8 @@ int ovgpu_mc_batch_create(OVGPUCtx *ctx, int max_cmds, int max_items, OVGPUMcBat
     if (!b) return OVGPU_ENOMEM;
     b->max_cmds = max_cmds; b->max_items = max_items; b->device = ctx->device;
     b->max_prof = max_cmds / 16 + 1;
+    for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) b->scaling.scale[l][i][0] = b->scaling.scale[l][i][1] = 1 << 14;
+    b->scaling.chroma_hor_col = 1;
     if (cudaMallocHost(&b->h_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMalloc(&b->d_prof, sizeof(ProfInfoDev) * b->max_prof) != cudaSuccess ||
         cudaMallocHost(&b->h_cmds, sizeof(McCmdDev) * max_cmds) != cudaSuccess ||
@@ -180,6 +184,25 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
     free(b);
 }
 
+int ovgpu_mc_batch_set_scaling(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcScaling *s)
+{
+    if (!ctx || !b) return OVGPU_EINVAL;
+    b->scaled[0] = b->scaled[1] = 0;
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++) {
+            for (int k = 0; k < 2; k++) {
+                const int f = s ? s->scale[l][i][k] : 1 << 14;
+                // the standard bounds the ratio between 1/8 (a reference eight times smaller) and 2; a factor of 0 = entry not in use
+                if (f && (f < 2048 || f > 32768)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "scale factor %d of list %d, reference %d out of range", f, l, i);
+                b->scaling.scale[l][i][k] = (uint16_t)(f ? f : 1 << 14);
+            }
+            if (b->scaling.scale[l][i][0] != (1 << 14) || b->scaling.scale[l][i][1] != (1 << 14)) b->scaled[l] |= 1u << i;
+        }
+    b->scaling.chroma_hor_col = s ? s->chroma_hor_col != 0 : 1;
+    b->scaling.chroma_ver_col = s ? s->chroma_ver_col != 0 : 0;
+    return 0;
+}
+
 int ovgpu_mc_batch_upload(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcCmd *cmds, int nb_cmds)
 {
     OVGPU_DEVICE_GUARD(ctx);
@@ -209,8 +232,8 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     {
         HostSection hs_loop(HT_MC_LOOP);
         int cnt[MC_NB_REGIONS];
-        mc_count_regions((const OVGPUMcCmd *)b->h_cmds, nb_cmds, b->max_items, cnt);
-        b->nb_items = cnt[0]; b->nb_bdof = cnt[1]; b->nb_prof_items = cnt[2]; b->nb_dmvr = cnt[3]; b->nb_small_c = cnt[4]; b->nb_big = cnt[5];
+        mc_count_regions((const OVGPUMcCmd *)b->h_cmds, nb_cmds, b->max_items, cnt, b->scaled);
+        b->nb_items = cnt[0]; b->nb_bdof = cnt[1]; b->nb_prof_items = cnt[2]; b->nb_dmvr = cnt[3]; b->nb_small_c = cnt[4]; b->nb_big = cnt[5]; b->nb_rpr = cnt[6];
     }
     HostSection hs_copies(HT_MC_COPIES);
     if (nb_cmds) {
@@ -222,7 +245,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
         // the commands take the DMA path and the kernels read the device copy
         static const int zero_copy = getenv("OVGPU_MC_ZERO_COPY") != NULL;
         McPrepArgs pa = { zero_copy ? b->h_cmds : b->d_cmds, b->d_cmds, zero_copy ? (const uint32_t *)b->h_prof : (const uint32_t *)b->d_prof, (uint32_t *)b->d_prof,
-                          nb_cmds, nb_prof, OVGPU_CEIL_DIV(nb_cmds, McPrepCountK::THREADS), b->max_items, b->d_block_sum, b->d_items, b->d_info };
+                          nb_cmds, nb_prof, OVGPU_CEIL_DIV(nb_cmds, McPrepCountK::THREADS), b->max_items, { b->scaled[0], b->scaled[1] }, b->d_block_sum, b->d_items, b->d_info };
         if (!zero_copy) {
             OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_cmds, b->h_cmds, sizeof(McCmdDev) * nb_cmds, cudaMemcpyHostToDevice, ps));
             if (nb_prof) OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(b->d_prof, b->h_prof, sizeof(ProfInfoDev) * nb_prof, cudaMemcpyHostToDevice, ps));
@@ -260,7 +283,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
     if (!ctx || !dst || !refs || !cb) return OVGPU_EINVAL;
     OVGPUMcBatch *b = (OVGPUMcBatch *)cb;              // (the batch's CONTENT is not changed: launch bookkeeping only)
     { const int ret = mc_take_status(ctx, b, 0); if (ret) return ret; }        // a previous run's verdict, if it is in and unread (never waits)
-    if (!b->nb_cmds || !(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr + b->nb_small_c + b->nb_big)) return 0;
+    if (!b->nb_cmds || !(b->nb_items + b->nb_bdof + b->nb_prof_items + b->nb_dmvr + b->nb_small_c + b->nb_big + b->nb_rpr)) return 0;
     McK::Args a;
     memset(&a, 0, sizeof(a));
     for (int c = 0; c < 3; c++) { PlaneView v = plane_view(dst, c); a.dst[c] = v.p; a.dst_pitch[c] = v.pitch; }
@@ -275,8 +298,10 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
             const OVGPUPicture *p = refs->rpl[l][i];
             a.refs.poc[l][i] = refs->poc[l][i];
             if (!p) continue;
-            if (p->width != dst->width || p->height != dst->height)
-                return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture size differs (RPR is not supported)");
+            // a reference of another size needs its scale factor in the batch's table (ovgpu_mc_batch_set_scaling)
+            if (!((b->scaled[l] >> i) & 1) && (p->width != dst->width || p->height != dst->height))
+                return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture (list %d, index %d) differs in size and has no scale factor", l, i);
+            if (p->bitdepth != dst->bitdepth) return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture bit depth differs");
             ga.present[l] |= 1u << i;
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = p->plane[c]; a.refs.pitch[l][i][c] = (int)(p->pitch[c] / 2); }
         }
@@ -285,7 +310,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
     OVGPU_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->stream, b->ev_built, 0));
     OVGPU_CUDA_CHECK(ctx, ovd_launch<McGuardK>(ga, dim3(1, 1, 1), 0, ctx->stream));
     ctx->launches += 1;
-    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0) + (b->nb_small_c > 0) + (b->nb_big > 0));
+    StageScope scope(ctx, OVGPU_STAGE_MC, (b->nb_items > 0) + (b->nb_bdof > 0) + (b->nb_prof_items > 0) + (b->nb_dmvr > 0) + (b->nb_small_c > 0) + (b->nb_big > 0) + (b->nb_rpr > 0));
     // The kernels work on disjoint blocks of the picture: they run side by side on the context's side streams (fork / join with
     // events), the longest first, so that the tail of one fills with the others' CTAs instead of leaving SMs idle between launches.
     static const int lanes = getenv("OVGPU_MC_LANES") ? atoi(getenv("OVGPU_MC_LANES")) : 2;      // streams the kernels are dealt over (1: serial)
@@ -309,6 +334,18 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
         McK::Args t = a;
         t.items = d_items + b->max_items; t.nb_items = b->nb_bdof; t.limit = a.limit + 1;
         OVGPU_CUDA_CHECK(ctx, ovd_launch<BdofK>(t, dim3(OVGPU_CEIL_DIV(b->nb_bdof, BdofK::WARPS), 1, 1), BdofK::SMEM_BYTES, next_stream()));
+    }
+    if (b->nb_rpr) {
+        McRprK::Args t;
+        t.mc = a; t.mc.items = d_items + 6 * b->max_items; t.mc.nb_items = b->nb_rpr; t.mc.limit = a.limit + 6; t.prof = b->d_prof;
+        for (int l = 0; l < 2; l++)
+            for (int i = 0; i < 16; i++) {
+                const OVGPUPicture *p = refs->rpl[l][i];
+                t.ref_w[l][i] = p ? p->width : dst->width; t.ref_h[l][i] = p ? p->height : dst->height;
+                t.scale[l][i][0] = b->scaling.scale[l][i][0]; t.scale[l][i][1] = b->scaling.scale[l][i][1];
+            }
+        t.hor_col = b->scaling.chroma_hor_col; t.ver_col = b->scaling.chroma_ver_col;
+        OVGPU_CUDA_CHECK(ctx, ovd_launch<McRprK>(t, dim3(OVGPU_CEIL_DIV(b->nb_rpr, McRprK::WARPS), 1, 1), McRprK::SMEM_BYTES, next_stream()));
     }
     if (b->nb_big) {
         McK::Args t = a;

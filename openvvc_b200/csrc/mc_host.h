@@ -6,13 +6,25 @@
 #include "../../include/ovvc_b200.h"
 #include "mc_tools_kernels.h"
 #include "mc_big_kernels.h"
+#include "mc_rpr_kernels.h"
 
 #define MC_ROUTE_BIG 6
+#define MC_ROUTE_RPR 7
+
+// Reference picture resampling: `sm` = per list the reference indices whose scale factor is not 1 (from the batch's scaling
+// table, ovgpu_mc_batch_set_scaling; NULL: none).  A command that names such a reference takes the resampling kernel.
+OVHD int mc_uses_scaled(const OVGPUMcCmd *c, const uint32_t *sm)
+{
+    if (!sm || !(sm[0] | sm[1])) return 0;
+    if (c->tool == OVGPU_MC_TOOL_GPM) return (int)(((sm[(c->aux >> 8) & 1] >> (c->ref_idx0 & 15)) | (sm[(c->aux >> 9) & 1] >> (c->ref_idx1 & 15))) & 1);
+    return (int)((((c->inter_dir & 1) ? sm[0] >> (c->ref_idx0 & 15) : 0) | ((c->inter_dir & 2) ? sm[1] >> (c->ref_idx1 & 15) : 0)) & 1);
+}
 
 // Which kernel runs a command: plain 4x4 luma-only commands (affine sub-blocks without PROF) take the packed 4x4 path of
 // ProfK (four sub-blocks per warp, refinement off) instead of a whole McK warp each.
-OVHD int mc_route(const OVGPUMcCmd *c)
+OVHD int mc_route(const OVGPUMcCmd *c, const uint32_t *sm = NULL)
 {
+    if (mc_uses_scaled(c, sm)) return MC_ROUTE_RPR;
     if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 2 && c->log2_h == 2 && (c->flags & 3) == OVGPU_MC_LUMA) return OVGPU_MC_TOOL_PROF;
     // plain chroma-only commands of 8x8 luma samples (the chroma blocks of affine CUs): two per warp in McSmallCK
     if (c->tool == OVGPU_MC_TOOL_PLAIN && c->log2_w == 3 && c->log2_h == 3 && (c->flags & 3) == OVGPU_MC_CHROMA && !(c->x0 & 3)) return MC_ROUTE_SMALL_C;
@@ -22,11 +34,11 @@ OVHD int mc_route(const OVGPUMcCmd *c)
 }
 
 // number of <=16x16 work items of the plain (tool 0) commands of a PU list
-static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
+static inline int mc_count_items(const OVGPUMcCmd *cmds, int n, const uint32_t *sm = NULL, int route = OVGPU_MC_TOOL_PLAIN)
 {
     int total = 0;
     for (int i = 0; i < n; i++) {
-        if (mc_route(&cmds[i]) != OVGPU_MC_TOOL_PLAIN) continue;
+        if (mc_route(&cmds[i], sm) != route) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         total += ((w + 15) >> 4) * ((h + 15) >> 4);
     }
@@ -34,18 +46,18 @@ static inline int mc_count_items(const OVGPUMcCmd *cmds, int n)
 }
 
 // BDOF / PROF commands are one work item each (BdofK: one warp per item, ProfK: four items per warp)
-static inline int mc_count_tool_items(const OVGPUMcCmd *cmds, int n, int tool)
+static inline int mc_count_tool_items(const OVGPUMcCmd *cmds, int n, int tool, const uint32_t *sm = NULL)
 {
     int total = 0;
-    for (int i = 0; i < n; i++) total += mc_route(&cmds[i]) == tool;
+    for (int i = 0; i < n; i++) total += mc_route(&cmds[i], sm) == tool;
     return total;
 }
 
-static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, int n, int tool)
+static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, int n, int tool, const uint32_t *sm = NULL)
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (mc_route(&cmds[i]) != tool) continue;
+        if (mc_route(&cmds[i], sm) != tool) continue;
         items[k].cmd = (uint32_t)i; items[k].ox = items[k].oy = 0;
         items[k].w = (uint8_t)(1 << cmds[i].log2_w); items[k].h = (uint8_t)(1 << cmds[i].log2_h);
         k++;
@@ -54,11 +66,13 @@ static inline int mc_build_tool_items(McItemDev *items, const OVGPUMcCmd *cmds, 
 }
 
 // well-formedness of one command; nb_prof = entries of the PROF table
-OVHD int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
+OVHD int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof, const uint32_t *sm = NULL)
 {
     if (c->log2_w < 2 || c->log2_w > 7 || c->log2_h < 2 || c->log2_h > 7 || c->inter_dir < 1 || c->inter_dir > 3 ||
         c->ref_idx0 < 0 || c->ref_idx0 > 15 || c->ref_idx1 < 0 || c->ref_idx1 > 15 || c->bcw_idx_plus1 > 5 || c->x0 < 0 || c->y0 < 0)
         return -1;
+    // the decoder switches BDOF and DMVR off for CUs with a scaled reference (and the reference has no such path)
+    if ((c->tool == OVGPU_MC_TOOL_BDOF || c->tool == OVGPU_MC_TOOL_DMVR) && mc_uses_scaled(c, sm)) return -1;
     if (c->tool == OVGPU_MC_TOOL_PLAIN) return 0;
     if (c->tool == OVGPU_MC_TOOL_GPM)       /* rcn_gpm_b: CU of 8..64 samples a side, two uni-predictions, luma and chroma, default BCW */
         return (c->inter_dir == 3 && c->log2_w >= 3 && c->log2_w <= 6 && c->log2_h >= 3 && c->log2_h <= 6 && (c->flags & 3) == 3 &&
@@ -76,11 +90,11 @@ OVHD int mc_check_cmd(const OVGPUMcCmd *c, int nb_prof)
 }
 
 // 32 x 32 (32 x 16 for 16-row commands) tiles of the commands routed to McBigK
-static inline int mc_build_big_items(McItemDev *items, const OVGPUMcCmd *cmds, int n)
+static inline int mc_build_big_items(McItemDev *items, const OVGPUMcCmd *cmds, int n, const uint32_t *sm = NULL)
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (mc_route(&cmds[i]) != MC_ROUTE_BIG) continue;
+        if (mc_route(&cmds[i], sm) != MC_ROUTE_BIG) continue;
         const int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h, th = h >= 32 ? 32 : 16;
         for (int oy = 0; oy < h; oy += th)
             for (int ox = 0; ox < w; ox += 32) {
@@ -91,11 +105,11 @@ static inline int mc_build_big_items(McItemDev *items, const OVGPUMcCmd *cmds, i
     return k;
 }
 
-static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n)
+static inline int mc_build_items(McItemDev *items, const OVGPUMcCmd *cmds, int n, const uint32_t *sm = NULL, int route = OVGPU_MC_TOOL_PLAIN)
 {
     int k = 0;
     for (int i = 0; i < n; i++) {
-        if (mc_route(&cmds[i]) != OVGPU_MC_TOOL_PLAIN) continue;
+        if (mc_route(&cmds[i], sm) != route) continue;
         int w = 1 << cmds[i].log2_w, h = 1 << cmds[i].log2_h;
         for (int oy = 0; oy < h; oy += 16)
             for (int ox = 0; ox < w; ox += 16) {
@@ -175,13 +189,15 @@ struct LmcsReshapeK {
 //                   host reads back to size the launches), overflow of a region's capacity
 //   McPrepScatterK  one thread per command again: its items written at block offset + offset inside the block -- so every
 //                   region lists its items in COMMAND ORDER (the refined MVs of DMVR items are returned in that order)
-// Regions of the item array: 0 plain (<=16x16 blocks, GPM), 1 BDOF, 2 PROF / plain 4x4, 3 DMVR, 4 small chroma, 5 big tiles.
-#define MC_NB_REGIONS 6
+// Regions of the item array: 0 plain (<=16x16 blocks, GPM), 1 BDOF, 2 PROF / plain 4x4, 3 DMVR, 4 small chroma, 5 big tiles,
+// 6 commands with a scaled reference (<=16x16 blocks, McRprK).
+#define MC_NB_REGIONS 7
 // region and number of work items of a (well-formed) command
-OVHD int mc_region_items(const OVGPUMcCmd *c, int *nb)
+OVHD int mc_region_items(const OVGPUMcCmd *c, int *nb, const uint32_t *sm = NULL)
 {
-    const int route = mc_route(c), w = 1 << c->log2_w, h = 1 << c->log2_h;
+    const int route = mc_route(c, sm), w = 1 << c->log2_w, h = 1 << c->log2_h;
     *nb = 1;
+    if (route == MC_ROUTE_RPR) { *nb = ((w + 15) >> 4) * ((h + 15) >> 4); return 6; }
     if (route == OVGPU_MC_TOOL_PLAIN) { *nb = ((w + 15) >> 4) * ((h + 15) >> 4); return 0; }
     if (route == MC_ROUTE_BIG) { *nb = (w >> 5) * (h >= 32 ? h >> 5 : 1); return 5; }
     return route == OVGPU_MC_TOOL_BDOF ? 1 : route == OVGPU_MC_TOOL_DMVR ? 3 : route == MC_ROUTE_SMALL_C ? 4 : 2;
@@ -217,12 +233,14 @@ struct McCountLut {                  // (tool, log2_w, log2_h, flags & 3, x0 & 3
         }
     }
 };
-static inline void mc_count_regions(const OVGPUMcCmd *cmds, int n, int cap, int cnt[MC_NB_REGIONS])
+static inline void mc_count_regions(const OVGPUMcCmd *cmds, int n, int cap, int cnt[MC_NB_REGIONS], const uint32_t *sm = NULL)
 {
     static const McCountLut lut;
     long long c64[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    const int any_scaled = sm && (sm[0] | sm[1]);
     for (int i = 0; i < n; i++) {
         const OVGPUMcCmd *c = &cmds[i];
+        if (any_scaled && mc_uses_scaled(c, sm)) { c64[6] += (((1 << (c->log2_w & 7)) + 15) >> 4) * (((1 << (c->log2_h & 7)) + 15) >> 4); continue; }
         const unsigned key = ((c->tool & 7u) << 9) | ((c->log2_w & 7u) << 6) | ((c->log2_h & 7u) << 3) | ((c->flags & 3u) << 1) | ((c->x0 & 3) != 0);
         const unsigned e = lut.v[key];
         c64[e >> 8] += e & 0xff;
@@ -269,6 +287,7 @@ struct McPrepArgs {
     const uint32_t *prof_src;        // PROF table as recorded / its device copy, in 32-bit words
     uint32_t *prof;
     int nb_cmds, nb_prof, nb_blocks, max_items;
+    uint32_t scaled[2];              // reference indices with a scale factor other than 1, per list (0: no resampling)
     int32_t *block_sum;              // [region][block] item counts, then (after the scan) exclusive offsets
     McItemDev *items;                // MC_NB_REGIONS regions of max_items entries
     McPrepInfo *info;                // device
@@ -296,9 +315,9 @@ struct McPrepCountK {
                 const McCmdDev cd = a.src[i];
                 if (a.cmds != a.src) a.cmds[i] = cd;
                 const OVGPUMcCmd *c = (const OVGPUMcCmd *)&cd;
-                if (mc_check_cmd(c, a.nb_prof)) ovd_atomic_max(&a.info->bad_rev, a.nb_cmds - i);
+                if (mc_check_cmd(c, a.nb_prof, a.scaled)) ovd_atomic_max(&a.info->bad_rev, a.nb_cmds - i);
                 else {
-                    reg = mc_region_items(c, &cnt);
+                    reg = mc_region_items(c, &cnt, a.scaled);
                     mx = c->x0 + (1 << c->log2_w); my = c->y0 + (1 << c->log2_h);
                     if (c->tool == OVGPU_MC_TOOL_GPM) { if ((c->aux >> 8) & 1) u1 |= 1u << c->ref_idx0; else u0 |= 1u << c->ref_idx0;
                                                         if ((c->aux >> 9) & 1) u1 |= 1u << c->ref_idx1; else u0 |= 1u << c->ref_idx1; }
@@ -375,7 +394,7 @@ struct McPrepScatterK {
             if (i < a.nb_cmds) {
                 const McCmdDev cd = a.cmds[i];
                 const OVGPUMcCmd *c = (const OVGPUMcCmd *)&cd;
-                if (!mc_check_cmd(c, a.nb_prof)) reg = mc_region_items(c, &cnt);
+                if (!mc_check_cmd(c, a.nb_prof, a.scaled)) reg = mc_region_items(c, &cnt, a.scaled);
             }
             s_reg[tid] = reg; s_cnt[tid] = cnt;
             return;
@@ -392,8 +411,8 @@ struct McPrepScatterK {
         McItemDev *it = a.items + (size_t)reg * a.max_items + off;
         const McCmdDev cd = a.cmds[i];
         const int w = 1 << cd.log2_w, h = 1 << cd.log2_h;
-        if (reg == 0 || reg == 5) {
-            const int tw = reg ? 32 : 16, th = reg ? (h >= 32 ? 32 : 16) : 16;
+        if (reg == 0 || reg == 5 || reg == 6) {
+            const int tw = reg == 5 ? 32 : 16, th = reg == 5 ? (h >= 32 ? 32 : 16) : 16;
             int k = 0;
             for (int oy = 0; oy < h; oy += th)
                 for (int ox = 0; ox < w; ox += tw, k++) {

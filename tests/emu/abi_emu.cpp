@@ -9,7 +9,8 @@
 
 struct OVGPUCtx { char err[256]; };
 struct OVGPUPicture { int w, h; uint16_t *plane[3]; int stride[3]; };
-struct OVGPUMcBatch { std::vector<OVGPUMcCmd> cmds; std::vector<OVGPUProfInfo> prof; int nb, nb_prof; std::vector<OVGPUDmvrMv> dmvr; int nb_dmvr; };
+struct OVGPUMcBatch { std::vector<OVGPUMcCmd> cmds; std::vector<OVGPUProfInfo> prof; int nb, nb_prof; std::vector<OVGPUDmvrMv> dmvr; int nb_dmvr;
+                      OVGPUMcScaling sc; uint32_t scaled[2]; };
 struct OVGPUTuBatch { std::vector<OVGPUTuCmd> cmds; std::vector<int16_t> coeffs; int nb; size_t nb_coeffs; OVGPUTuSlice sl; std::vector<OVGPULmcsAnchor> anchors; };
 struct OVGPUIntraBatch { std::vector<OVGPUIntraCmd> cmds; std::vector<OVGPUIspInfo> isp; int w, h, log2_ctu, levels; };
 struct OVGPUDbfParams { int w, h, log2_ctu, beta, tc; std::vector<uint32_t> ver[OVGPU_DBF_NB_MAPS], hor[OVGPU_DBF_NB_MAPS]; std::vector<uint8_t> qp[3]; };
@@ -55,13 +56,24 @@ int ovgpu_picture_download(OVGPUCtx *, const OVGPUPicture *p, void *const data[3
     return 0;
 }
 
-int ovgpu_mc_batch_create(OVGPUCtx *, int max_cmds, int, OVGPUMcBatch **b) { *b = new OVGPUMcBatch(); (*b)->cmds.resize(max_cmds + 1); (*b)->prof.resize(65536); (*b)->nb = (*b)->nb_prof = (*b)->nb_dmvr = 0; return 0; }
+int ovgpu_mc_batch_create(OVGPUCtx *, int max_cmds, int, OVGPUMcBatch **b) { *b = new OVGPUMcBatch(); (*b)->cmds.resize(max_cmds + 1); (*b)->prof.resize(65536); (*b)->nb = (*b)->nb_prof = (*b)->nb_dmvr = 0; return ovgpu_mc_batch_set_scaling(NULL, *b, NULL); }
+int ovgpu_mc_batch_set_scaling(OVGPUCtx *, OVGPUMcBatch *b, const OVGPUMcScaling *s)
+{
+    b->scaled[0] = b->scaled[1] = 0;
+    for (int l = 0; l < 2; l++)
+        for (int i = 0; i < 16; i++) {
+            for (int k = 0; k < 2; k++) b->sc.scale[l][i][k] = s && s->scale[l][i][k] ? s->scale[l][i][k] : 1 << 14;
+            if (b->sc.scale[l][i][0] != (1 << 14) || b->sc.scale[l][i][1] != (1 << 14)) b->scaled[l] |= 1u << i;
+        }
+    b->sc.chroma_hor_col = s ? s->chroma_hor_col : 1; b->sc.chroma_ver_col = s ? s->chroma_ver_col : 0;
+    return 0;
+}
 void ovgpu_mc_batch_destroy(OVGPUMcBatch *b) { delete b; }
 int ovgpu_mc_batch_staging(OVGPUCtx *, OVGPUMcBatch *b, OVGPUMcCmd **cmds, OVGPUProfInfo **prof) { *cmds = b->cmds.data(); *prof = b->prof.data(); return 0; }
 int ovgpu_mc_batch_commit(OVGPUCtx *c, OVGPUMcBatch *b, int nb, int nb_prof)
 {
     if (nb > (int)b->cmds.size() || nb_prof > (int)b->prof.size()) return fail(c, OVGPU_EINVAL, "MC batch overflow");
-    for (int i = 0; i < nb; i++) if (mc_check_cmd(&b->cmds[i], nb_prof)) return fail(c, OVGPU_EINVAL, "MC command %d malformed", i);
+    for (int i = 0; i < nb; i++) if (mc_check_cmd(&b->cmds[i], nb_prof, b->scaled)) return fail(c, OVGPU_EINVAL, "MC command %d malformed", i);
     b->nb = nb; b->nb_prof = nb_prof;
     return 0;
 }
@@ -155,15 +167,21 @@ int ovgpu_recon_picture(OVGPUCtx *c, OVGPUPicture *pic, const OVGPUMcRefs *refs,
     OVGPUMcBatch *mc = (OVGPUMcBatch *)mcb;
     if (mc && mc->nb) {
         EmuMcRefs er;
+        EmuMcScaling es;
         memset(&er, 0, sizeof(er));
+        memset(&es, 0, sizeof(es));
+        es.chroma_hor_col = mc->sc.chroma_hor_col; es.chroma_ver_col = mc->sc.chroma_ver_col;
         for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) {
             const OVGPUPicture *rp = refs->rpl[l][i];
             er.poc[l][i] = refs->poc[l][i];
+            es.scale[l][i][0] = mc->sc.scale[l][i][0]; es.scale[l][i][1] = mc->sc.scale[l][i][1];
+            es.ref_w[l][i] = rp ? rp->w : pic->w; es.ref_h[l][i] = rp ? rp->h : pic->h;
+            if (rp && !((mc->scaled[l] >> i) & 1) && (rp->w != pic->w || rp->h != pic->h)) return fail(c, OVGPU_EINVAL, "reference picture differs in size and has no scale factor");
             if (rp) for (int k = 0; k < 3; k++) { er.plane[l][i][k] = rp->plane[k]; er.stride[l][i][k] = rp->stride[k]; }
         }
         mc->nb_dmvr = mc_count_tool_items(mc->cmds.data(), mc->nb, OVGPU_MC_TOOL_DMVR);
         mc->dmvr.resize(mc->nb_dmvr + 1);
-        int rc = emu_mc_picture(pic->plane, pic->stride, pic->w, pic->h, 10, &er, mc->cmds.data(), mc->nb, lmcs ? lmcs->luts.fwd_lut : NULL,
+        int rc = emu_mc_picture_rpr(pic->plane, pic->stride, pic->w, pic->h, 10, &er, &es, mc->cmds.data(), mc->nb, lmcs ? lmcs->luts.fwd_lut : NULL,
                                 mc->prof.data(), mc->nb_prof, mc->dmvr.data());
         if (rc < 0) return fail(c, OVGPU_EINVAL, "emulated MC: %d", rc);
     }

@@ -123,19 +123,41 @@ struct EmuMcRefs {
     int32_t poc[2][16];
 };
 
+// reference picture resampling: like OVOMcScaling (oracle.h)
+struct EmuMcScaling {
+    uint16_t scale[2][16][2];
+    int32_t ref_w[2][16], ref_h[2][16];
+    uint8_t chroma_hor_col, chroma_ver_col;
+};
+
+int emu_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int w, int h, int bitdepth,
+                       const EmuMcRefs *refs, const EmuMcScaling *sc, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd,
+                       const OVGPUProfInfo *prof, int nb_prof, OVGPUDmvrMv *dmvr_out);
+
 int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h, int bitdepth,
                    const EmuMcRefs *refs, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd,
                    const OVGPUProfInfo *prof, int nb_prof, OVGPUDmvrMv *dmvr_out)
 {
+    return emu_mc_picture_rpr(dst, dst_stride, w, h, bitdepth, refs, NULL, cmds, nb_cmds, lmcs_fwd, prof, nb_prof, dmvr_out);
+}
+
+int emu_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int w, int h, int bitdepth,
+                       const EmuMcRefs *refs, const EmuMcScaling *sc, const OVGPUMcCmd *cmds, int nb_cmds, const uint16_t *lmcs_fwd,
+                       const OVGPUProfInfo *prof, int nb_prof, OVGPUDmvrMv *dmvr_out)
+{
+    uint32_t sm[2] = { 0, 0 };
+    if (sc)
+        for (int l = 0; l < 2; l++)
+            for (int i = 0; i < 16; i++) if (sc->scale[l][i][0] != (1 << 14) || sc->scale[l][i][1] != (1 << 14)) sm[l] |= 1u << i;
     // the work lists come from the product's device-side construction (McPrep*K), checked here against the host restatement
-    const int max_items = mc_count_items(cmds, nb_cmds) + nb_cmds + 1;
+    const int max_items = mc_count_items(cmds, nb_cmds) + mc_count_items(cmds, nb_cmds, sm, MC_ROUTE_RPR) + nb_cmds + 1;
     std::vector<McItemDev> items((size_t)MC_NB_REGIONS * max_items);
     McPrepInfo info;
     memset(&info, 0, sizeof(info));
     {
         const int nblk = (nb_cmds + McPrepCountK::THREADS - 1) / McPrepCountK::THREADS;
         std::vector<int32_t> bsum((size_t)MC_NB_REGIONS * (nblk + 1));
-        McPrepArgs pa = { (const McCmdDev *)cmds, (McCmdDev *)cmds, NULL, NULL, nb_cmds, nb_prof, nblk, max_items, bsum.data(), items.data(), &info };
+        McPrepArgs pa = { (const McCmdDev *)cmds, (McCmdDev *)cmds, NULL, NULL, nb_cmds, nb_prof, nblk, max_items, { sm[0], sm[1] }, bsum.data(), items.data(), &info };
         if (nb_cmds) {
             ovd_emulate<McPrepCountK>(pa, ovd_dim3(nblk, 1, 1), McPrepCountK::SMEM_BYTES);
             ovd_emulate<McPrepScanK>(pa, ovd_dim3(1, 1, 1), McPrepScanK::SMEM_BYTES);
@@ -143,11 +165,11 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
         }
     }
     for (int i = 0; i < nb_cmds; i++)
-        if (mc_check_cmd(&cmds[i], nb_prof)) return info.bad_rev == nb_cmds - i ? -(i + 1) : -1000000;      // first malformed command, both ways
+        if (mc_check_cmd(&cmds[i], nb_prof, sm)) return info.bad_rev == nb_cmds - i ? -(i + 1) : -1000000;      // first malformed command, both ways
     if (info.bad_rev || info.overflow) return -1000001;
     {   // the host's cheap count sizes the launches; the guard kernel publishes the limits the MC kernels stop at
         int cnt[MC_NB_REGIONS];
-        mc_count_regions(cmds, nb_cmds, max_items, cnt);
+        mc_count_regions(cmds, nb_cmds, max_items, cnt, sm);
         for (int r = 0; r < MC_NB_REGIONS; r++) if (cnt[r] != info.count[r]) return -1000020 - r;
         McGuardArgs ga = { &info, w, h, { 0, 0 }, NULL };
         for (int l = 0; l < 2; l++) for (int i = 0; i < 16; i++) if (refs->plane[l][i][0]) ga.present[l] |= 1u << i;
@@ -157,10 +179,10 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
     const int n_items = info.count[0], n_bdof = info.count[1], n_prof = info.count[2], n_dmvr = info.count[3], n_sc = info.count[4], n_big = info.count[5];
     {
         std::vector<McItemDev> want(max_items);
-        const int routes[MC_NB_REGIONS] = { OVGPU_MC_TOOL_PLAIN, OVGPU_MC_TOOL_BDOF, OVGPU_MC_TOOL_PROF, OVGPU_MC_TOOL_DMVR, MC_ROUTE_SMALL_C, MC_ROUTE_BIG };
+        const int routes[MC_NB_REGIONS] = { OVGPU_MC_TOOL_PLAIN, OVGPU_MC_TOOL_BDOF, OVGPU_MC_TOOL_PROF, OVGPU_MC_TOOL_DMVR, MC_ROUTE_SMALL_C, MC_ROUTE_BIG, MC_ROUTE_RPR };
         for (int r = 0; r < MC_NB_REGIONS; r++) {
-            const int n = r == 0 ? mc_build_items(want.data(), cmds, nb_cmds) : r == 5 ? mc_build_big_items(want.data(), cmds, nb_cmds)
-                                                                               : mc_build_tool_items(want.data(), cmds, nb_cmds, routes[r]);
+            const int n = r == 0 || r == 6 ? mc_build_items(want.data(), cmds, nb_cmds, sm, routes[r]) : r == 5 ? mc_build_big_items(want.data(), cmds, nb_cmds, sm)
+                                                                               : mc_build_tool_items(want.data(), cmds, nb_cmds, routes[r], sm);
             if (n != info.count[r] || (n && memcmp(want.data(), items.data() + (size_t)r * max_items, sizeof(McItemDev) * n))) return -1000002 - r;
         }
         int mx = 0, my = 0;
@@ -183,6 +205,19 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
             for (int c = 0; c < 3; c++) { a.refs.plane[l][i][c] = refs->plane[l][i][c]; a.refs.pitch[l][i][c] = refs->stride[l][i][c]; }
         }
     if (n_items) ovd_emulate<McK>(a, ovd_dim3((n_items + McK::WARPS - 1) / McK::WARPS, 1, 1), McK::SMEM_BYTES);
+    const int n_rpr = info.count[6];
+    if (n_rpr) {
+        McRprK::Args t;
+        memset(&t, 0, sizeof(t));
+        t.mc = a; t.mc.items = items.data() + 6 * (size_t)max_items; t.mc.nb_items = n_rpr; t.mc.limit = info.limit + 6; t.prof = (const ProfInfoDev *)prof;
+        for (int l = 0; l < 2; l++)
+            for (int i = 0; i < 16; i++) {
+                t.ref_w[l][i] = sc->ref_w[l][i]; t.ref_h[l][i] = sc->ref_h[l][i];
+                t.scale[l][i][0] = sc->scale[l][i][0]; t.scale[l][i][1] = sc->scale[l][i][1];
+            }
+        t.hor_col = sc->chroma_hor_col; t.ver_col = sc->chroma_ver_col;
+        ovd_emulate<McRprK>(t, ovd_dim3((n_rpr + McRprK::WARPS - 1) / McRprK::WARPS, 1, 1), McRprK::SMEM_BYTES);
+    }
     if (n_big) {
         McK::Args t = a;
         t.items = it_big; t.nb_items = n_big; t.limit = info.limit + 5;
@@ -209,7 +244,7 @@ int emu_mc_picture(uint16_t *const dst[3], const int dst_stride[3], int w, int h
         ovd_emulate<DmvrK>(t, ovd_dim3((n_dmvr + DmvrK::WARPS - 1) / DmvrK::WARPS, 1, 1), DmvrK::SMEM_BYTES);
         if (dmvr_out) memcpy(dmvr_out, dm.data(), sizeof(DmvrMvDev) * n_dmvr);
     }
-    return n_items + n_bdof + n_prof + n_dmvr + n_sc + n_big;
+    return n_items + n_bdof + n_prof + n_dmvr + n_sc + n_big + n_rpr;
 }
 
 int emu_lmcs_build_luts(OVGPULmcsLuts *luts, const OVGPULmcsData *d, int bitdepth)

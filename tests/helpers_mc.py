@@ -100,3 +100,48 @@ def rpr_case(po, w, h, seed, log2_ctu=7, lmcs=False, kind="natural", hor_col=1, 
     cmds, prof = synth.mc_commands_tools(w, h, seed, log2_ctu, n_refs=3, p_bdof=0.0, p_affine=p_affine, p_gpm=p_gpm)
     luts = po.lmcs_build_luts(synth.lmcs_data(seed), impl="port") if lmcs else None
     return refs0, refs1, pocs, cmds.astype(po.McCmd), luts, prof, po.make_mc_scaling(w, h, [refs0, refs1], hor_col, ver_col)
+
+
+def emu_mc_rpr(emu, po, w, h, refs0, refs1, pocs, cmds, luts, sc, bitdepth=10, prof=None):
+    out = blank(w, h)
+    refs, keep = po.make_mc_refs([refs0, refs1], pocs)
+    dst, ds = po._planes_arg(out)
+    lut = luts.np("fwd_lut").ctypes.data_as(po.u16p) if luts is not None else None
+    prof = np.ascontiguousarray(prof, dtype=np.int16) if prof is not None else None
+    n = emu.emu_mc_picture_rpr(dst, ds, w, h, bitdepth, C.byref(refs), C.byref(sc), cmds.ctypes.data_as(C.c_void_p), len(cmds), lut,
+                               prof.ctypes.data_as(C.c_void_p) if prof is not None else None, len(prof) if prof is not None else 0, None)
+    assert n >= 0, "emu rejected the batch (%d)" % n
+    return out
+
+
+def gpu_mc_rpr(ctx, w, h, refs0, refs1, pocs, cmds, luts, sc, prof=None):
+    """the C ABI with references of their own sizes: ovgpu_mc_batch_set_scaling before the upload, then ovgpu_mc_picture"""
+    from openvvc_b200 import api
+    dst = ctx.picture(w, h)
+    dst.upload(blank(w, h))
+    pics = [[], []]
+    for l, lst in enumerate((refs0, refs1)):
+        for planes in lst:
+            rh, rw = planes[0].shape
+            p = ctx.picture(rw, rh); p.upload(planes); pics[l].append(p)
+    batch = api.McBatch(ctx, len(cmds), api.mc_nb_items(cmds))
+    batch.set_scaling([[(sc.scale[l][i][0], sc.scale[l][i][1]) for i in range(len(lst))] for l, lst in enumerate((refs0, refs1))],
+                      sc.chroma_hor_col, sc.chroma_ver_col)
+    batch.upload(cmds.astype(api.MC_CMD), prof=prof)
+    lm = None
+    if luts is not None:
+        gl = api.LmcsLuts()
+        C.memmove(C.byref(gl), C.byref(luts), C.sizeof(gl))
+        lm = api.Lmcs(ctx, gl)
+    try:
+        batch.run(dst, pics, pocs, lm)
+        batch.status()
+        out = dst.download()
+    finally:
+        batch.destroy(); dst.destroy()
+        if lm:
+            lm.destroy()
+        for lst in pics:
+            for p in lst:
+                p.destroy()
+    return out

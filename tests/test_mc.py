@@ -394,3 +394,48 @@ def test_rpr_port_vs_compiled_reference(oracle, w, h, log2, lmcs, kind, hc, vc):
         b = helpers_mc.blank(w, h)
         po.mc_picture_rpr(b, [refs0, refs1], pocs, cmds, sc, log2, impl="ref", lmcs=luts, prof=prof, simd=simd)
         helpers.assert_planes_equal(a, b, "RPR port vs reference (simd=%d)" % simd)
+
+
+@pytest.mark.parametrize("c", [c for c in RPR_GOLDEN if c["w"] <= 832], ids=RIDS)
+def test_rpr_emulated_kernel_matches_golden(oracle, emu, c):
+    """McRprK's source + the device-side routing of commands that name a scaled reference, emulated on the CPU"""
+    refs0, refs1, pocs, cmds, luts, prof, sc = _rpr_case(oracle, c)
+    out = helpers_mc.emu_mc_rpr(emu, oracle, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, sc, prof=prof)
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
+def test_rpr_bdof_dmvr_on_scaled_reference_rejected(oracle, emu):
+    """the decoder switches BDOF / DMVR off when a reference is scaled: such a command is malformed"""
+    refs0, refs1, pocs, cmds, luts, prof, sc = helpers_mc.rpr_case(oracle, 256, 128, 5)
+    i = int(np.nonzero((cmds["tool"] == 0) & (cmds["inter_dir"] == 3) & (cmds["log2_w"] >= 4) & (cmds["log2_h"] >= 4))[0][0])
+    cmds["log2_w"][i] = cmds["log2_h"][i] = 4; cmds["ref_idx0"][i] = 0
+    for tool, flags in ((1, 1), (3, 3)):
+        bad = cmds.copy()
+        bad["tool"][i] = tool; bad["flags"][i] = flags; bad["bcw_idx_plus1"][i] = 0
+        with pytest.raises(AssertionError):
+            helpers_mc.emu_mc_rpr(emu, oracle, 256, 128, refs0, refs1, pocs, bad, luts, sc, prof=prof)
+    ok = cmds.copy()
+    ok["tool"][i] = 1; ok["flags"][i] = 1; ok["bcw_idx_plus1"][i] = 0; ok["ref_idx0"][i] = 1; ok["ref_idx1"][i] = 1    # both unscaled: fine
+    helpers_mc.emu_mc_rpr(emu, oracle, 256, 128, refs0, refs1, pocs, ok, luts, sc, prof=prof)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", RPR_GOLDEN, ids=RIDS)
+def test_rpr_gpu_matches_golden(oracle, gpu_ctx, c):
+    refs0, refs1, pocs, cmds, luts, prof, sc = _rpr_case(oracle, c)
+    out = helpers_mc.gpu_mc_rpr(gpu_ctx, c["w"], c["h"], refs0, refs1, pocs, cmds, luts, sc, prof=prof)
+    assert [helpers.md5(p) for p in out] == c["md5"]
+
+
+@pytest.mark.gpu
+def test_rpr_gpu_matches_oracle_and_refuses_unscaled_size_mismatch(oracle, gpu_ctx):
+    from openvvc_b200 import api
+    w, h = 320, 192
+    refs0, refs1, pocs, cmds, luts, prof, sc = helpers_mc.rpr_case(oracle, w, h, 77, 7, True, "noise", 0, 0)
+    want = helpers_mc.blank(w, h)
+    oracle.mc_picture_rpr(want, [refs0, refs1], pocs, cmds, sc, 7, impl="port", lmcs=luts, prof=prof)
+    helpers.assert_planes_equal(helpers_mc.gpu_mc_rpr(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, sc, prof=prof), want, "CUDA RPR vs oracle")
+    # a reference of another size whose scale factor was not announced: refused, not read out of bounds
+    sc.scale[0][0][0] = sc.scale[0][0][1] = 1 << 14
+    with pytest.raises(api.OVGPUError):
+        helpers_mc.gpu_mc_rpr(gpu_ctx, w, h, refs0, refs1, pocs, cmds, luts, sc, prof=prof)
