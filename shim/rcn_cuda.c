@@ -20,8 +20,9 @@
  * stays the reference's: transform trees, TUs, ISP sub-trees and the deblocking pre-processing still run through the STOCK
  * control functions, with every sample-touching leaf slot replaced by a no-op or a recorder.
  *
- * One tile (rect entry) per picture, 10 bit, no RPR: what the reference's CI covers for random access.  Anything else is left
- * to the stock table (the wrapper does not install the recorders). */
+ * One tile (rect entry) per picture, 10 bit: what the reference's CI covers for random access.  Pictures may change size inside
+ * a sequence (reference picture resampling): the per-picture objects follow the picture's size and the slice's scale factors go
+ * with the MC commands.  Anything else is left to the stock table (the wrapper does not install the recorders). */
 #include <pthread.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -239,7 +240,7 @@ static void rec_begin_picture(ShimRec *r, const OVFrame *f, const struct RectEnt
     const int w = c->pic_w, h = c->pic_h, ctu = 1 << log2_ctu;
     const int ncw = (w + ctu - 1) >> log2_ctu, nch = (h + ctu - 1) >> log2_ctu;
     if (e->ctb_x || e->ctb_y || e->nb_ctu_w != ncw || e->nb_ctu_h != nch) shim_fatal("pictures with several tiles are not supported by the CUDA back end");
-    if ((int)f->width != w || (int)f->height != h) shim_fatal("frame size differs from the picture size (RPR)");
+    if ((int)f->width != w || (int)f->height != h) shim_fatal("frame size differs from the picture size");
     if (!r->ctx && ovgpu_ctx_create(&r->ctx, g.device, NULL) < 0) shim_fatal("no usable sm_100 device (ovgpu_ctx_create)");
     if (r->w != w || r->h != h || r->log2_ctu != log2_ctu) {
         if (r->rec) { ovgpu_ctx_sync(r->ctx); ovgpu_picture_destroy(r->rec); ovgpu_picture_destroy(r->mid); ovgpu_dbf_params_destroy(r->dbf);
@@ -817,7 +818,20 @@ static void rec_end_picture(ShimRec *r)
     }
     OVGPUTuSlice sl;
     sl.dep_quant = c->residual_coding_l == &residual_coding_dpq; sl.sh_ts_disabled = c->sh_ts_disabled; sl.ict_type = r->ict_type; sl.pad = 0;
-    if (r->nb_mc) SHIM_CHECK(r, ovgpu_mc_batch_commit(x, r->mc, r->nb_mc, r->nb_prof));
+    if (r->nb_mc) {
+        /* reference picture resampling: the slice's scale factors (ctudec_compute_refs_scaling, ctudec.c:42-84) route the commands
+         * that name a scaled reference to the resampling kernel -- what the stock slots decide call by call (rcn_inter.c:2749-2966) */
+        OVGPUMcScaling sc;
+        memset(&sc, 0, sizeof(sc));
+        sc.chroma_hor_col = 1; sc.chroma_ver_col = r->collocated;
+        for (int i = 0; i < ic->nb_active_ref0 && i < 16; i++) {
+            sc.scale[0][i][0] = ic->scale_fact_rpl0[i][0]; sc.scale[0][i][1] = ic->scale_fact_rpl0[i][1];
+            if (ic->rpl0[i]) { sc.chroma_hor_col = ic->rpl0[i]->scale_info.chroma_hor_col_flag; sc.chroma_ver_col = ic->rpl0[i]->scale_info.chroma_ver_col_flag; }
+        }
+        for (int i = 0; i < ic->nb_active_ref1 && i < 16; i++) { sc.scale[1][i][0] = ic->scale_fact_rpl1[i][0]; sc.scale[1][i][1] = ic->scale_fact_rpl1[i][1]; }
+        SHIM_CHECK(r, ovgpu_mc_batch_set_scaling(x, r->mc, &sc));
+        SHIM_CHECK(r, ovgpu_mc_batch_commit(x, r->mc, r->nb_mc, r->nb_prof));
+    }
     SHIM_CHECK(r, ovgpu_tu_batch_set_anchors(x, r->tu, r->anchors, c->lmcs_info.scale_c_flag ? r->nb_anchors : 0));
     SHIM_CHECK(r, ovgpu_tu_batch_commit(x, r->tu, r->nb_tu, r->nb_coeffs, &sl));
     if (!r->intra) SHIM_CHECK(r, ovgpu_intra_batch_create(x, (r->w >> 2) * (r->h >> 2) * 2 + 16, &r->intra));

@@ -41,8 +41,13 @@ STREAMS = {
     "ctc_ra":     ("ctc", {}, 416, 240, 17, 16, 29),
     "ctc_ra_480": ("ctc", {}, 832, 480, 9, 8, 30),
     "ctc_ld":     ("ctc", {}, 416, 240, 6, 1, 31),
+    # reference picture resampling (a17): three picture sizes in one sequence, every picture draws its own, so pictures are predicted
+    # from larger and smaller references (plain / BCW / GPM / affine + PROF commands over scaled references, TMVP, all in-loop filters)
+    "rpr":        ("rpr", {}, 416, 240, 9, 8, 34, [(208, 120), (320, 192)]),
+    "rpr_ld":     ("rpr", {}, 384, 256, 8, 1, 35, [(192, 128), (256, 176), (384, 128)]),
 }
-GPU_ONLY = {"ctc_ra_1080": ("ctc", {}, 1920, 1080, 9, 8, 32), "ctc_ra_4k": ("ctc", {}, 3840, 2160, 5, 4, 33)}
+GPU_ONLY = {"ctc_ra_1080": ("ctc", {}, 1920, 1080, 9, 8, 32), "ctc_ra_4k": ("ctc", {}, 3840, 2160, 5, 4, 33),
+            "rpr_1080": ("rpr", {}, 1920, 1080, 5, 4, 36, [(960, 544), (1280, 720)])}
 
 
 def md5_file(path):
@@ -59,10 +64,10 @@ def stream_dir(tmp_path_factory):
 
 
 def make(stream_dir, name, table=STREAMS):
-    preset, over, w, h, n, gop, seed = table[name]
+    preset, over, w, h, n, gop, seed = table[name][:7]
     path = os.path.join(str(stream_dir), name + ".266")
     if not os.path.exists(path):
-        vs.make_stream(path, w, h, n, gop=gop, seed=seed, preset=preset, tool_over=over, verify=True)
+        vs.make_stream(path, w, h, n, gop=gop, seed=seed, preset=preset, tool_over=over, verify=True, rpr_sizes=table[name][7] if len(table[name]) > 7 else None)
     return path
 
 
