@@ -73,6 +73,12 @@ int  ovgpu_picture_copy(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *sr
 typedef struct OVGPUWindow {        /* struct Window (ovframe.h): offsets in CHROMA sample units, luma = offset << 1 */
     int32_t offset_lft, offset_rgt, offset_abv, offset_blw;
 } OVGPUWindow;
+/* Up-scaling of an output picture to the sequence's maximum size (replaces pp_sample_rate_conv, pp_pic_scale.c:252-377, as
+ * pp_process_frame applies it under sei->upscale_flag, post_proc.c:117-128): struct ScalingInfo (ovdpb.h:85-93) of the picture --
+ * scaling window offsets in chroma sample units, chroma sample siting.  win == NULL: no offsets, horizontally collocated chroma.
+ * dst must not be smaller than src's scaling window (the reference's down-sampling branch is not reached from post_proc.c). */
+typedef struct OVGPUScalingWindow { uint16_t left, right, top, bottom; uint8_t chroma_hor_col, chroma_ver_col; } OVGPUScalingWindow;
+int  ovgpu_picture_upscale(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUScalingWindow *win);
 /* the rows dectest would write, copied to host planes (win == NULL: the whole picture) */
 int  ovgpu_picture_download_window(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUWindow *win, void *const data[3], const size_t linesize[3]);
 /* running MD5 (RFC 1321) of those rows, computed on the device: ovgpu_md5_picture appends one picture (asynchronous, one GPU

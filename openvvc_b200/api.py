@@ -347,6 +347,18 @@ def download_window(ctx, pic, window, w, h):
     return out
 
 
+class ScalingWindow(C.Structure):
+    """OVGPUScalingWindow: struct ScalingInfo (ovdpb.h:85-93)"""
+    _fields_ = [("left", C.c_uint16), ("right", C.c_uint16), ("top", C.c_uint16), ("bottom", C.c_uint16),
+                ("chroma_hor_col", C.c_uint8), ("chroma_ver_col", C.c_uint8)]
+
+
+def upscale(ctx, dst, src, window=(0, 0, 0, 0), hor_col=1, ver_col=0):
+    """ovgpu_picture_upscale: src resampled into dst (the sequence's maximum size), as pp_process_frame does for output frames"""
+    win = ScalingWindow(*[int(v) for v in window], int(hor_col), int(ver_col))
+    _check(ctx.h, lib().ovgpu_picture_upscale(ctx.h, dst.p, src.p, C.byref(win)), "picture_upscale")
+
+
 class Dist:
     """ovgpu_dist_*: the reference hand-off between the ranks of one node (NCCL send / receive behind the C ABI)"""
 

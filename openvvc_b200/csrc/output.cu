@@ -8,6 +8,7 @@
 // 64-byte block), so this is ONE thread per hash and about 0.2 s per 4K picture: a checking aid for the drop-in tests, on its own
 // stream beside the reconstruction, not part of the timed path.
 #include "common.cuh"
+#include "pp_kernels.h"
 #include <stdlib.h>
 
 struct OVGPUMd5 {
@@ -203,6 +204,31 @@ int ovgpu_md5_final(OVGPUCtx *ctx, OVGPUMd5 *m, uint8_t digest[16])
     OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(m->h_state + 24, m->d_state + 24, 16, cudaMemcpyDeviceToHost, ctx->stream));
     OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(digest, m->h_state + 24, 16);
+    return 0;
+}
+
+
+// Up-scaling of an output picture to the sequence's maximum size: what pp_process_frame does on the CPU for sequences with
+// reference picture resampling (post_proc.c:117-128 -> pp_sample_rate_conv, pp_pic_scale.c:252-377).  Asynchronous.
+int ovgpu_picture_upscale(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUScalingWindow *win)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !dst || !src || dst == src) return OVGPU_EINVAL;
+    if (dst->bitdepth != src->bitdepth) return ovgpu_set_error(ctx, OVGPU_EINVAL, "up-scaling: bit depths differ");
+    UpscaleK::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) {
+        PlaneView d = plane_view(dst, c), s = plane_view((OVGPUPicture *)src, c);
+        a.dst[c] = d.p; a.dst_pitch[c] = d.pitch; a.src[c] = s.p; a.src_pitch[c] = s.pitch;
+    }
+    a.dst_w = dst->width; a.dst_h = dst->height; a.src_w = src->width; a.src_h = src->height;
+    a.maxv = (1 << 10) - 1;                               // pp_pic_scale.c is compiled for 10 bit only (:40)
+    if (upscale_setup(&a, win ? win->left : 0, win ? win->right : 0, win ? win->top : 0, win ? win->bottom : 0,
+                      win ? win->chroma_hor_col != 0 : 1, win ? win->chroma_ver_col != 0 : 0))
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "up-scaling: the target (%d x %d) is smaller than the source window (%d x %d)", dst->width, dst->height, src->width, src->height);
+    dim3 grid(OVGPU_CEIL_DIV(a.dst_w, 32), OVGPU_CEIL_DIV(a.dst_h, 8), 3);
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<UpscaleK>(a, grid, 0, ctx->stream));
+    ctx->launches += 1;
     return 0;
 }
 

@@ -150,6 +150,12 @@ void ovo_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int pic
                         const OVOMcRefs *refs, const OVOMcScaling *sc, const OVOMcCmd *cmds, int nb_cmds,
                         const uint16_t *lmcs_fwd_lut, const OVOProfInfo *prof_tab);
 
+/* ---- Output stage: up-scaling of a decoded picture to the sequence's maximum size (pp_sample_rate_conv,
+ * pp_pic_scale.c:252-377; struct ScalingInfo, ovdpb.h:85-93: scaling window offsets in chroma sample units) -------- */
+typedef struct OVOScalingWindow { uint16_t left, right, top, bottom; uint8_t chroma_hor_col, chroma_ver_col; } OVOScalingWindow;
+int ovo_pp_upscale_plane(uint16_t *dst, int dst_stride, int dst_w, int dst_h, const uint16_t *src, int src_stride, int src_w, int src_h,
+                         const OVOScalingWindow *win, int luma, int bitdepth);
+
 /* ---- LMCS ------------------------------------------------------------------------------------------- */
 typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */
     uint8_t lmcs_min_bin_idx;

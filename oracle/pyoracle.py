@@ -299,3 +299,30 @@ def mc_picture(dst_planes, ref_lists, pocs, cmds, log2_ctu=7, bitdepth=10, impl=
         ref().ovref_mc_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(refs), cmds.ctypes.data_as(C.c_void_p),
                                len(cmds), pp, C.byref(lmcs) if lmcs is not None else None, po_)
     return dst_planes
+
+
+# ---- output stage: up-scaling ---------------------------------------------------------------------------------
+class ScalingWindow(C.Structure):
+    """OVOScalingWindow: struct ScalingInfo (ovdpb.h:85-93), offsets in chroma sample units"""
+    _fields_ = [("left", C.c_uint16), ("right", C.c_uint16), ("top", C.c_uint16), ("bottom", C.c_uint16),
+                ("chroma_hor_col", C.c_uint8), ("chroma_ver_col", C.c_uint8)]
+
+
+def pp_upscale(planes, dst_w, dst_h, window=(0, 0, 0, 0), hor_col=1, ver_col=0, impl="port", bitdepth=10):
+    """pp_sample_rate_conv on the three planes of a decoded picture -> planes of dst_w x dst_h (post_proc.c:117-128)"""
+    win = ScalingWindow(*[int(v) for v in window], int(hor_col), int(ver_col))
+    out = []
+    for c, p in enumerate(planes):
+        p = np.ascontiguousarray(p)
+        dw, dh = (dst_w >> 1, dst_h >> 1) if c else (dst_w, dst_h)
+        d = np.zeros((dh, dw), np.uint16)
+        sh, sw = p.shape
+        if impl == "port":
+            rc = port().ovo_pp_upscale_plane(d.ctypes.data_as(u16p), dw, dw, dh, p.ctypes.data_as(u16p), p.strides[0] // 2, sw, sh, C.byref(win), int(c == 0), bitdepth)
+            assert rc == 0, "down-sampling is not restated"
+        else:
+            f = ref().ovref_pp_upscale_plane
+            f.restype = None
+            f(d.ctypes.data_as(u16p), dw, dw, dh, p.ctypes.data_as(u16p), p.strides[0] // 2, sw, sh, C.byref(win), int(c == 0))
+        out.append(d)
+    return out

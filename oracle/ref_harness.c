@@ -465,3 +465,17 @@ ovref_rpr_taps(int chroma, int filter_idx, int frac, int16_t *taps)
     }
     return 0;
 }
+
+/* the reference's output-stage up-scaler on one plane (pp_sample_rate_conv is exported: post_proc.h:68) */
+void pp_sample_rate_conv(uint16_t *scaled_dst, uint16_t scaled_stride, int scaledWidth, int scaledHeight, uint16_t *orgSrc, uint16_t org_stride,
+                         int orgWidth, int orgHeight, const struct ScalingInfo *const scale_info, uint8_t luma_flag);
+void
+ovref_pp_upscale_plane(uint16_t *dst, int dst_stride, int dst_w, int dst_h, const uint16_t *src, int src_stride, int src_w, int src_h,
+                       const OVOScalingWindow *win, int luma)
+{
+    struct ScalingInfo si;
+    memset(&si, 0, sizeof(si));
+    si.scaling_win_left = win->left; si.scaling_win_right = win->right; si.scaling_win_top = win->top; si.scaling_win_bottom = win->bottom;
+    si.chroma_hor_col_flag = win->chroma_hor_col; si.chroma_ver_col_flag = win->chroma_ver_col;
+    pp_sample_rate_conv(dst, (uint16_t)dst_stride, dst_w, dst_h, (uint16_t *)src, (uint16_t)src_stride, src_w, src_h, &si, (uint8_t)luma);
+}

@@ -9,6 +9,7 @@
 #include "../../openvvc_b200/csrc/tr_host.h"
 #include "../../openvvc_b200/csrc/dbf_kernels.h"
 #include "../../openvvc_b200/csrc/intra_host.h"
+#include "../../openvvc_b200/csrc/pp_kernels.h"
 
 static const int16_t *emu_tr_scales = NULL;     // LMCS chroma scales of the running emu_recon_picture call
 
@@ -113,6 +114,19 @@ int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
     a.nb_ctu_w = (w + ctu_s - 1) >> log2_ctu; a.nb_ctu_h = (h + ctu_s - 1) >> log2_ctu;
     a.ctu = (const SaoCtuDev *)ctu;
     ovd_emulate<SaoK>(a, ovd_dim3((w + SaoK::BX * 8 - 1) / (SaoK::BX * 8), (h + SaoK::BY - 1) / SaoK::BY, 3), 0);
+    return 0;
+}
+
+// output stage: up-scaling (UpscaleK); win = left, right, top, bottom (chroma units), hor_col, ver_col
+int emu_pp_upscale(uint16_t *const dst[3], const int dst_stride[3], int dst_w, int dst_h,
+                   const uint16_t *const src[3], const int src_stride[3], int src_w, int src_h, const int win[6])
+{
+    UpscaleK::Args a;
+    memset(&a, 0, sizeof(a));
+    for (int c = 0; c < 3; c++) { a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; a.src[c] = src[c]; a.src_pitch[c] = src_stride[c]; }
+    a.dst_w = dst_w; a.dst_h = dst_h; a.src_w = src_w; a.src_h = src_h; a.maxv = 1023;
+    if (upscale_setup(&a, win[0], win[1], win[2], win[3], win[4], win[5])) return -1;
+    ovd_emulate<UpscaleK>(a, ovd_dim3((dst_w + 31) / 32, (dst_h + 7) / 8, 3), 0);
     return 0;
 }
 

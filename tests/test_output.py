@@ -61,3 +61,58 @@ def test_gpu_window_download_and_md5(gpu_ctx, w, h, window):
     m.picture(pic2, None)
     assert m.hexdigest() == hashlib.md5(dectest_bytes(pl2, (0, 0, 0, 0))).hexdigest()
     m.destroy(); pic.destroy(); pic2.destroy()
+
+
+# ---- up-scaling of output pictures (pp_sample_rate_conv: the post-processing step of sequences with reference picture resampling)
+UPSCALE_CASES = [(208, 120, 416, 240, (0, 0, 0, 0), 1, 0, "natural"), (320, 192, 416, 240, (0, 0, 0, 0), 0, 1, "noise"),
+                 (416, 240, 416, 240, (0, 0, 0, 0), 1, 1, "noise"), (272, 160, 416, 240, (4, 4, 2, 6), 0, 0, "noise"),
+                 (624, 360, 832, 480, (0, 8, 0, 0), 1, 0, "natural")]
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pyoracle
+    pyoracle.build(ref=True)
+    return pyoracle
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh,win,hc,vc,kind", UPSCALE_CASES)
+def test_upscale_port_vs_compiled_reference_and_emulated_kernel(po, sw, sh, dw, dh, win, hc, vc, kind):
+    """oracle port == the reference's own pp_sample_rate_conv; UpscaleK's source emulated on the CPU == port"""
+    import ctypes as C
+    import subprocess
+    from openvvc_b200 import synth
+    pl = synth.planes(sw, sh, 11, kind)
+    want = po.pp_upscale(pl, dw, dh, win, hc, vc, "port")
+    if po.ref_available():
+        got = po.pp_upscale(pl, dw, dh, win, hc, vc, "ref")
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+    d = os.path.join(ROOT, "tests", "emu")
+    subprocess.run(["make", "-s", "-C", d], check=True)
+    emu = C.CDLL(os.path.join(d, "libovvc_b200_emu.so"))
+    out = [np.zeros((dh, dw), np.uint16), np.zeros((dh // 2, dw // 2), np.uint16), np.zeros((dh // 2, dw // 2), np.uint16)]
+    dst, ds = po._planes_arg(out)
+    src, ss = po._planes_arg(pl)
+    assert emu.emu_pp_upscale(dst, ds, dw, dh, src, ss, sw, sh, (C.c_int * 6)(*win, hc, vc)) == 0
+    for a, b in zip(want, out):
+        assert np.array_equal(a, b)
+    # a target smaller than the source is the reference's down-sampling branch: refused
+    assert emu.emu_pp_upscale(src, ss, sw // 2, sh // 2, src, ss, sw, sh, (C.c_int * 6)(0, 0, 0, 0, 1, 0)) == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sw,sh,dw,dh,win,hc,vc,kind", UPSCALE_CASES + [(1920, 1088, 3840, 2160, (0, 0, 0, 2), 1, 0, "natural")])
+def test_gpu_upscale_matches_oracle(gpu_ctx, po, sw, sh, dw, dh, win, hc, vc, kind):
+    from openvvc_b200 import api, synth
+    pl = synth.planes(sw, sh, 11, kind)
+    want = po.pp_upscale(pl, dw, dh, win, hc, vc, "port")
+    src = gpu_ctx.picture(sw, sh); src.upload(pl)
+    dst = gpu_ctx.picture(dw, dh)
+    api.upscale(gpu_ctx, dst, src, win, hc, vc)
+    got = dst.download()
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    with pytest.raises(api.OVGPUError):
+        api.upscale(gpu_ctx, src, dst)
+    src.destroy(); dst.destroy()
