@@ -415,15 +415,17 @@ def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl
         oracle_checked = 1
     barrier()
     sent0 = traffic()
-    ms_all = []
+    ms_all, issue_ms = [], []
     for r_ in range(R):                             # R timed runs of exactly K steps (GOPs) each, back to back
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for s in list(d_streams[1:]) + xstreams:
             s.wait_event(e0)
+        t_issue = time.perf_counter()
         ovdist.run_gop_stream(sched, rank, reconstruct, publish, consume, 32 * (W + r_ * K), 32 * (W + (r_ + 1) * K), order)
         join()
         e1.record(stream)
+        issue_ms.append((time.perf_counter() - t_issue) * 1e3)      # host time to ISSUE the run (no wait in it): against the device time below
         barrier()
         ms_all.append(e0.elapsed_time(e1))
     ms = ms_all
@@ -433,7 +435,9 @@ def run_dag(api, ovdist, torch, dist, args, w, h, rank, world, local, stream, wl
     last = [poc for poc, _ in sched.pictures[-32:] if sched.owner[poc] == rank or sched.needs(rank, poc)]
     md5 = {poc: helpers.md5(*slots[poc % nb_slots].download()) for poc in last}
     info = {"gops": K, "warmup_gops": W, "pictures": 32 * K, "repeats": R, "nvlink_bytes_per_step": None, "copies_identical": None, "oracle_checked": oracle_checked,
-            "lanes": L, "launches": sum(c.launch_count() for c in d_ctx) - n0}
+            "lanes": L, "launches": sum(c.launch_count() for c in d_ctx) - n0,
+            # how long the one host thread of the rank takes to issue a timed run, per step: close to ms_per_step = the host, not the GPU, sets the pace
+            "host_issue_ms_per_step": sorted(issue_ms)[len(issue_ms) // 2] / K}
     if world > 1:
         allmd5 = [None] * world
         dist.all_gather_object(allmd5, md5)

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--lib", default=None)
     ap.add_argument("--md5", action="store_true")
     ap.add_argument("--all-intra", action="store_true")
+    ap.add_argument("--threads", default="", help="e.g. 1,2,4: also time the multi-stream run issued from that many host threads (is the one issuing thread the limit?)")
     args = ap.parse_args()
     import torch
     import bench
@@ -78,6 +79,30 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     fps1 = args.pics * args.reps / (e0.elapsed_time(e1) * 1e-3)
+    # host threads: thread t issues the pictures of the streams j with j % T == t, nothing else changes (wall clock around issue + sync)
+    fps_threads, issue_ms = {}, {}
+    for T in [int(v) for v in args.threads.split(",") if v]:
+        import threading
+        import time
+        torch.cuda.synchronize()
+        n_rounds = args.reps * 2
+
+        def worker(t, T=T):
+            for _ in range(n_rounds):
+                for i, d in enumerate(dev):
+                    if (i % n_ds) % T == t:
+                        bench.run_stages(api, ctxs[i % n_ds], d, refs, wl["pocs"], lmcs)
+        th = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+        t0 = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        fps_threads[T] = round(args.pics * n_rounds / (t2 - t0), 1)
+        issue_ms[T] = round((t1 - t0) * 1e3 / (args.pics * n_rounds), 4)        # host time per picture until everything is issued
     names = ("mc", "residual", "intra", "lmcs", "dbf_v", "dbf_h", "sao", "alf_luma", "alf_chroma")
     ctx.profile(True); ctx.profile_reset()
     for _ in range(args.reps):
@@ -87,6 +112,9 @@ def main():
     out = {"lib": args.lib or "default", "size": args.size, "fps_multi_stream": round(fps, 1), "fps_one_stream": round(fps1, 1),
            "us_per_picture": {s: round(1e3 * prof[s][0] / (args.reps * args.pics), 1) for s in names if prof[s][1]}}
     out["us_sum"] = round(sum(out["us_per_picture"].values()), 1)
+    if fps_threads:
+        out["fps_by_host_threads"] = fps_threads
+        out["host_issue_ms_per_picture"] = issue_ms
     if args.md5:
         import helpers
         out["md5"] = [helpers.md5(*d["dst"].download()) for d in dev]
