@@ -32,9 +32,13 @@ OVD uint32_t alf_odd_pair(uint32_t w0, uint32_t w1) { return ovd_byte_perm(w0, w
 // =========================================================================================================
 template <bool WIDE>
 struct AlfLumaK {
-    static const int THREADS = 256, MIN_BLOCKS = 3, PHASES = 3;          // 80 registers: 3 CTAs / SM (was 128 -> 2)
+#ifndef ALF_LUMA_MIN_BLOCKS
+#define ALF_LUMA_MIN_BLOCKS 3
+#endif
+    static const int THREADS = 256, MIN_BLOCKS = ALF_LUMA_MIN_BLOCKS, PHASES = 3;          // 80 registers: 3 CTAs / SM (was 128 -> 2)
     static const int TW = 128, TH = 32;
-    static const int PIX_STRIDE = TW + 8;            // samples; halo of 4 left/right keeps 8-byte alignment
+    static const int HALO_L = 8;                     // samples staged left of the tile: 16 bytes, the granularity of cp.async
+    static const int PIX_STRIDE = TW + 16;           // samples; 8 left / right of the tile
     static const int PIX_ROWS = TH + 6;
     static const int CELL_COLS = TW / 2 + 2, CELL_ROWS = TH / 2 + 2;
     static const int SMEM_PIX = PIX_ROWS * PIX_STRIDE * 2;
@@ -113,10 +117,21 @@ struct AlfLumaK {
             return;
         }
         const int nrows = t.th + 6;
-        const int nchunks = (t.tw + 8) >> 2;          // 4-sample (8-byte) chunks, <= 34
+        // tiles away from the picture's left / right border: the rows go to shared memory as 16-byte asynchronous copies (LDGSTS),
+        // one lane per chunk and one warp per row -- no register staging, no per-chunk border tests (rows are clamped per row)
+        const bool fast = t.x0 >= HALO_L && t.x0 + t.tw + 8 <= a.pic_w && !(t.tw & 7) && !(a.src_pitch & 7);
+        if (fast) {
+            const int cpr = (t.tw + 16) >> 3, lane = tid & 31;        // <= 18 chunks per row
+            if (lane < cpr)
+                for (int r = tid >> 5; r < nrows; r += THREADS / 32) {
+                    const int y = ovd_clamp(t.y0 - 3 + r, 0, a.pic_h - 1);
+                    ovd_cp_async16(pix + r * PIX_STRIDE + 8 * lane, a.src + (size_t)y * a.src_pitch + t.x0 - HALO_L + 8 * lane);
+                }
+        }
+        const int nchunks = (t.tw + 16) >> 2;         // 4-sample (8-byte) chunks, <= 36
         const int ch = tid & 63;
-        if (ch < nchunks) {
-            int x = t.x0 - 4 + 4 * ch;
+        if (!fast && ch < nchunks) {
+            int x = t.x0 - HALO_L + 4 * ch;
             for (int r = tid >> 6; r < nrows; r += 4) {
                 int y = ovd_clamp(t.y0 - 3 + r, 0, a.pic_h - 1);
                 const uint16_t *row = a.src + (size_t)y * a.src_pitch;
@@ -129,6 +144,7 @@ struct AlfLumaK {
         }
         const ovd_u4 *g = (const ovd_u4 *)(a.tab + (size_t)t.set * ALF_TAB_SET_WORDS);
         for (int i = tid; i < ALF_TAB_SET_WORDS / 4; i += THREADS) ((ovd_u4 *)tab)[i] = g[i];
+        if (fast) ovd_cp_async_wait_all();
     }
 
     // ---- phase 1: 1-D Laplacians summed per 2x2 cell (rcn_alf.c:602-657 / :366-509) -------------------------
@@ -143,7 +159,7 @@ struct AlfLumaK {
             if (m >= ncc) continue;
             // cell rows: tile rows r0 = 2k-2, r0+1; shared-memory row index = tile row + 3
             int y_r0 = t.y0 + 2 * k - 2;
-            const uint32_t *rb = pw + (2 * k + 1) * ws + m;
+            const uint32_t *rb = pw + (2 * k + 1) * ws + m + (HALO_L - 4) / 2;
             const uint32_t *ra = (y_r0 == vb_abs) ? rb : rb - ws;              // "src0 = src1", rcn_alf.c:466
             const uint32_t *rc = rb + ws;
             const uint32_t *rd = (y_r0 + 1 == vb_abs - 1) ? rc : rc + ws;      // "src3 = src2", rcn_alf.c:464
@@ -276,7 +292,7 @@ struct AlfLumaK {
         // ---- 10 rows x 12 samples around the block; row r is first needed by output row r - 6, so rows 7..9 are loaded
         // inside the row loop: seven rows (42 registers) are live at a time instead of ten
         uint32_t R[10][6];
-        const ovd_u2 *pp = (const ovd_u2 *)(pix + (4 * byi) * PIX_STRIDE + 4 * bxi);
+        const ovd_u2 *pp = (const ovd_u2 *)(pix + (4 * byi) * PIX_STRIDE + 4 * bxi + (HALO_L - 4));
 #define ALF_LOAD_ROW(r_)                                                                   \
         _Pragma("unroll")                                                                   \
         for (int q = 0; q < 3; q++) {                                                       \
