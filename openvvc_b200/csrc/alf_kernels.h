@@ -97,8 +97,16 @@ struct AlfLumaK {
         uint32_t *tab = (uint32_t *)(smem + SMEM_PIX + SMEM_CELL);
         if (P == 0) phase_load(a, t, pix, tab, tid);
         else if (!t.enabled) return;
+#ifdef ALF_EXP_NO_CELLS              /* timing experiments (tools/build_variant.sh), never part of the product build */
+        else if (P == 1) return;
+#else
         else if (P == 1) phase_cells(a, t, pix, cell, tid);
+#endif
+#ifdef ALF_EXP_NO_FILTER
+        else return;
+#else
         else phase_filter(a, t, pix, cell, tab, tid);
+#endif
         (void)st;
     }
 
@@ -142,6 +150,7 @@ struct AlfLumaK {
                 *(ovd_u2 *)(pix + r * PIX_STRIDE + 4 * ch) = v;
             }
         }
+        // (reading each thread's table entry straight from global memory instead of staging the set was measured: no gain)
         const ovd_u4 *g = (const ovd_u4 *)(a.tab + (size_t)t.set * ALF_TAB_SET_WORDS);
         for (int i = tid; i < ALF_TAB_SET_WORDS / 4; i += THREADS) ((ovd_u4 *)tab)[i] = g[i];
         if (fast) ovd_cp_async_wait_all();
@@ -340,7 +349,8 @@ struct AlfLumaK {
 struct AlfChromaK {
     static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 2;
     static const int TW = 64, TH = 32;
-    static const int PIX_STRIDE = TW + 8, PIX_ROWS = TH + 4;
+    static const int HALO_L = 8;                     // samples staged left of the tile (16 bytes: cp.async granularity)
+    static const int PIX_STRIDE = TW + 16, PIX_ROWS = TH + 4;
     static const int SMEM_BYTES = PIX_ROWS * PIX_STRIDE * 2;
 
     struct Args {
@@ -393,11 +403,22 @@ struct AlfChromaK {
         const int w = a.pic_w >> 1, h = a.pic_h >> 1;
         const uint16_t *src = a.src[comp];
         if (P == 0) {
-            // stage tile + halo 2 (4 horizontally for alignment)
-            const int nrows = t.th + 4, nchunks = (t.tw + 8) >> 2;   // <= 18
+            // stage tile + halo 2 (8 horizontally for alignment): tiles away from the left / right border as 16-byte asynchronous
+            // copies (LDGSTS), one lane per chunk and one warp per row; border tiles through the clamped 8-byte path
+            const int nrows = t.th + 4, nchunks = (t.tw + 16) >> 2;   // <= 20
+            const bool fast = t.x0 >= HALO_L && t.x0 + t.tw + 8 <= w && !(t.tw & 7) && !(a.src_pitch & 7);
             const int ch = tid & 31;
+            if (fast) {
+                if (ch < ((t.tw + 16) >> 3))
+                    for (int r = tid >> 5; r < nrows; r += 8) {
+                        const int y = ovd_clamp(t.y0 - 2 + r, 0, h - 1);
+                        ovd_cp_async16(pix + r * PIX_STRIDE + 8 * ch, src + (size_t)y * a.src_pitch + t.x0 - HALO_L + 8 * ch);
+                    }
+                ovd_cp_async_wait_all();
+                return;
+            }
             if (ch < nchunks) {
-                int x = t.x0 - 4 + 4 * ch;
+                int x = t.x0 - HALO_L + 4 * ch;
                 for (int r = tid >> 5; r < nrows; r += 8) {
                     int y = ovd_clamp(t.y0 - 2 + r, 0, h - 1);
                     const uint16_t *row = src + (size_t)y * a.src_pitch;
@@ -437,7 +458,7 @@ struct AlfChromaK {
             else if (y_vb >= vb && y_vb <= vb + 1) reach = y_vb - vb;
             const int coarse = (y_vb == vb - 1) || (y_vb == vb);
             const int d1 = ovd_min(1, reach), d2 = ovd_min(2, reach);
-            const uint16_t *c0 = pix + (ly + 2) * PIX_STRIDE + 4 * tx + 4;
+            const uint16_t *c0 = pix + (ly + 2) * PIX_STRIDE + 4 * tx + HALO_L;
             const uint16_t *u1 = c0 - d1 * PIX_STRIDE, *u2 = c0 - d2 * PIX_STRIDE;
             const uint16_t *e1 = c0 + d1 * PIX_STRIDE, *e2 = c0 + d2 * PIX_STRIDE;
             // CC-ALF row offsets (rcn_alf.c:831-839)

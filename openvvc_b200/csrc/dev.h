@@ -40,6 +40,9 @@ static inline int ovd__mx(int a, int b) { return a > b ? a : b; }
 // per half: min((int16)(a+b), c)   (the add wraps to 16 bit like the hardware)
 OVD uint32_t ovd_viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c)
 { return ovd__pk(ovd__mn((int16_t)(ovd__lo(a) + ovd__lo(b)), ovd__lo(c)), ovd__mn((int16_t)(ovd__hi(a) + ovd__hi(b)), ovd__hi(c))); }
+// per half: max(min((int16)(a+b), c), 0)
+OVD uint32_t ovd_viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c)
+{ return ovd__pk(ovd__mx(ovd__mn((int16_t)(ovd__lo(a) + ovd__lo(b)), ovd__lo(c)), 0), ovd__mx(ovd__mn((int16_t)(ovd__hi(a) + ovd__hi(b)), ovd__hi(c)), 0)); }
 OVD uint32_t ovd_vmax_s16x2(uint32_t a, uint32_t b)
 { return ovd__pk(ovd__mx(ovd__lo(a), ovd__lo(b)), ovd__mx(ovd__hi(a), ovd__hi(b))); }
 OVD uint32_t ovd_vmin_s16x2(uint32_t a, uint32_t b)
@@ -76,6 +79,7 @@ OVD int ovd_max(int a, int b) { return a > b ? a : b; }
 OVD uint32_t ovd_umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
 #else
 OVD uint32_t ovd_viaddmin_s16x2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2(a, b, c); }
+OVD uint32_t ovd_viaddmin_s16x2_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_s16x2_relu(a, b, c); }
 OVD uint32_t ovd_vmax_s16x2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 OVD uint32_t ovd_vmin_s16x2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 OVD uint32_t ovd_vadd_16x2(uint32_t a, uint32_t b) { return __vadd2(a, b); }

@@ -26,18 +26,30 @@ def main():
     ap.add_argument("--md5", action="store_true")
     ap.add_argument("--all-intra", action="store_true")
     ap.add_argument("--threads", default="", help="e.g. 1,2,4: also time the multi-stream run issued from that many host threads (is the one issuing thread the limit?)")
+    ap.add_argument("--libs", default="", help="comma list of library variants (\"default\" = the product build) timed one after the other on ONE workload, one JSON line each")
     args = ap.parse_args()
+    import bench
+    from openvvc_b200 import api
+    w, h = bench.SIZES[args.size]
+    wl = bench.make_workload(w, h, args.pics, seed0=5000, all_intra=args.all_intra)
+    default_path, default_build = api.LIB_PATH, api._build.build
+    for lib in ([v for v in args.libs.split(",") if v] or [args.lib]):
+        args.lib = None if lib in (None, "default") else lib
+        api._lib = None
+        api.LIB_PATH, api._build.build = default_path, default_build
+        run_one(args, wl, w, h)
+
+
+def run_one(args, wl, w, h):
     import torch
     import bench
     from openvvc_b200 import api
     if args.lib:
         api.LIB_PATH = os.path.abspath(args.lib)
         api._build.build = lambda *a, **k: api.LIB_PATH
-    w, h = bench.SIZES[args.size]
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx = api.Ctx(0, stream.cuda_stream)
-    wl = bench.make_workload(w, h, args.pics, seed0=5000, all_intra=args.all_intra)
     refs = [[ctx.picture(w, h) for _ in lst] for lst in wl["refs"]]
     for lst, src in zip(refs, wl["refs"]):
         for pic, planes in zip(lst, src):
@@ -118,7 +130,7 @@ def main():
     if args.md5:
         import helpers
         out["md5"] = [helpers.md5(*d["dst"].download()) for d in dev]
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
