@@ -20,8 +20,11 @@
 #pragma once
 #include "mc_kernels.h"
 
+#ifndef MCBIG_MIN_BLOCKS
+#define MCBIG_MIN_BLOCKS 4
+#endif
 struct McBigK {
-    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 3;
+    static const int THREADS = 128, MIN_BLOCKS = MCBIG_MIN_BLOCKS, PHASES = 3;
     static const int WARPS = 4;
     static const int WY_STRIDE = 24, WY_WORDS = 39 * 24 + 2 * 16;       // 48 samples x (32 + 7) rows per list
     static const int WC_STRIDE = 16, WC_COMP = 336;                     // 32 samples x (16 + 3) rows per list and component

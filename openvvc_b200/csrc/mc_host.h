@@ -157,8 +157,11 @@ static inline void lmcs_build_luts_host(OVGPULmcsLuts *luts, const OVGPULmcsData
 }
 
 // whole-plane LUT pass (lmcs_reshape_backward on every CTU, slicedec.c:745-750): 8 samples per thread
+#ifndef LMCS_MIN_BLOCKS
+#define LMCS_MIN_BLOCKS 4
+#endif
 struct LmcsReshapeK {
-    static const int THREADS = 256, MIN_BLOCKS = 4, PHASES = 1;
+    static const int THREADS = 256, MIN_BLOCKS = LMCS_MIN_BLOCKS, PHASES = 1;
     struct Args { uint16_t *plane; int pitch, w, h, bitdepth; const uint16_t *lut; };
     struct State { int dummy; };
     template <int P>

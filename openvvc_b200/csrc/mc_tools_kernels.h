@@ -230,8 +230,11 @@ struct BdofK {
 };
 
 // =================================================================================================================
+#ifndef PROF_MIN_BLOCKS
+#define PROF_MIN_BLOCKS 4
+#endif
 struct ProfK {
-    static const int THREADS = 128, MIN_BLOCKS = 4, PHASES = 4;
+    static const int THREADS = 128, MIN_BLOCKS = PROF_MIN_BLOCKS, PHASES = 4;
     static const int WARPS = 4, SBS = 4;                     // 4 sub-blocks (commands) per warp
     static const int WW = 8, WR = 11;                        // 16 samples x 11 rows per sub-block and list
     static const int SM_ITEM = SBS * 16, SM_WIN = SBS * 2 * WR * WW, SM_EX = SBS * 2 * 16 / 2;

@@ -48,9 +48,12 @@ OVD_CONST uint8_t tr_iq_scale[2][6] = { { 40, 45, 51, 57, 64, 72 }, { 57, 64, 72
 OVD_CONST uint8_t tr_lfnst_scan[16] = { 0, 4, 1, 8, 5, 2, 12, 9, 6, 3, 13, 10, 7, 14, 11, 15 };   // rcn_lfnst.c:47
 OVD_CONST uint8_t tr_wide_shift[6] = { 0, 6, 10, 12, 14, 15 };                                    // drv_lfnst.c:53
 
+#ifndef TR_MIN_BLOCKS
+#define TR_MIN_BLOCKS 8
+#endif
 template <int GROUP>
 struct TrK {
-    static const int THREADS = 128, MIN_BLOCKS = 8, PHASES = 4;       // <= 64 registers: the line-tiled passes would otherwise take 80+
+    static const int THREADS = 128, MIN_BLOCKS = TR_MIN_BLOCKS, PHASES = 4;       // <= 64 registers: the line-tiled passes would otherwise take 80+
     static const int GROUPS = THREADS / GROUP;
     // shared memory per group, int16 units (see the size derivation in DESIGN.md "Residual")
     static const int SM_CT = GROUP == 32 ? 320 : 32 * 34;     // dequantised block, transposed: [x][k = y], line stride kv4 + 2
