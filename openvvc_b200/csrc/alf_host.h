@@ -8,7 +8,7 @@
 
 // Expand the RCNALF-format luma tables into kernel operands.  Returns 1 when some coefficient does not
 // fit the int8 operand of IDP.2A (then the WIDE kernel variant must be used).
-static inline int alf_pack_luma_tab(uint32_t *dst /*[24][100][36]*/, const OVGPUAlfTables *t)
+static inline int alf_pack_luma_tab(uint32_t *dst /*[24][100][24]*/, const OVGPUAlfTables *t)
 {
     int wide = 0;
     for (int s = 0; s < OVGPU_ALF_NUM_SETS; s++)
@@ -28,7 +28,6 @@ static inline int alf_pack_luma_tab(uint32_t *dst /*[24][100][36]*/, const OVGPU
                 // a clip of 1<<bitdepth never binds; keep it inside int16 (32767) so 8- and 10-bit share the path
                 int clv = cl > 32767 ? 32767 : cl;
                 w[12 + k] = (uint32_t)(uint16_t)clv * 0x10001u;
-                w[24 + k] = (uint32_t)(uint16_t)(-clv) * 0x10001u;
             }
         }
     return wide;

@@ -12,7 +12,7 @@
 #include "dev.h"
 
 // ---- device-side parameter formats -----------------------------------------------------------------------
-#define ALF_TAB_ENTRY_WORDS 36          // per (transpose, class): 12 coef operands, 12 clip, 12 -clip
+#define ALF_TAB_ENTRY_WORDS 24          // per (transpose, class): 12 coef operands, 12 clips (the kernel negates the clip itself)
 #define ALF_TAB_SET_WORDS   (100 * ALF_TAB_ENTRY_WORDS)
 
 struct AlfCtuDev {                      // 8 bytes per CTU
@@ -53,7 +53,7 @@ struct AlfLumaK {
         int pic_w, pic_h, log2_ctu, bitdepth;
         int tw, th;                      // tile size = min(TW/TH, ctu size)
         int tiles_x_per_ctu, tiles_y_per_ctu, nb_ctu_w;
-        const uint32_t *tab;             // [24][100][36]
+        const uint32_t *tab;             // [24][100][24]
         const AlfCtuDev *ctu;
     };
     struct State { int active; };
