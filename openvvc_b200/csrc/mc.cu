@@ -13,6 +13,8 @@ struct OVGPUMcBatch {
     int nb_dmvr, nb_small_c, nb_big, nb_rpr;
     OVGPUMcScaling scaling;                   // ovgpu_mc_batch_set_scaling: the slice's scale factors (all 1 << 14 by default)
     uint32_t scaled[2];                       // ... and the reference indices whose factor is not 1, per list
+    OVGPUMcScaling run_scaling;               // the table the LAST COMMIT was routed by: what ovgpu_mc_picture runs with, whatever
+    uint32_t run_scaled[2];                   // set_scaling has been told since (the next picture's factors may already be in)
     DmvrMvDev *d_dmvr, *h_dmvr;               // refined MVs, one per DMVR item (device result + pinned read-back)
     McCmdDev *h_cmds, *d_cmds;
     McItemDev *d_items;                       // seven regions of max_items entries: plain | BDOF | PROF | DMVR | small chroma | big tiles | scaled,
@@ -187,13 +189,19 @@ void ovgpu_mc_batch_destroy(OVGPUMcBatch *b)
 int ovgpu_mc_batch_set_scaling(OVGPUCtx *ctx, OVGPUMcBatch *b, const OVGPUMcScaling *s)
 {
     if (!ctx || !b) return OVGPU_EINVAL;
+    // the standard bounds the ratio between 1/8 (a reference eight times smaller) and 2; a factor of 0 = entry not in use.
+    // Checked before anything is changed: a refused table leaves the batch as it was.
+    for (int l = 0; s && l < 2; l++)
+        for (int i = 0; i < 16; i++)
+            for (int k = 0; k < 2; k++) {
+                const int f = s->scale[l][i][k];
+                if (f && (f < 2048 || f > 32768)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "scale factor %d of list %d, reference %d out of range", f, l, i);
+            }
     b->scaled[0] = b->scaled[1] = 0;
     for (int l = 0; l < 2; l++)
         for (int i = 0; i < 16; i++) {
             for (int k = 0; k < 2; k++) {
                 const int f = s ? s->scale[l][i][k] : 1 << 14;
-                // the standard bounds the ratio between 1/8 (a reference eight times smaller) and 2; a factor of 0 = entry not in use
-                if (f && (f < 2048 || f > 32768)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "scale factor %d of list %d, reference %d out of range", f, l, i);
                 b->scaling.scale[l][i][k] = (uint16_t)(f ? f : 1 << 14);
             }
             if (b->scaling.scale[l][i][0] != (1 << 14) || b->scaling.scale[l][i][1] != (1 << 14)) b->scaled[l] |= 1u << i;
@@ -229,6 +237,7 @@ int ovgpu_mc_batch_commit(OVGPUCtx *ctx, OVGPUMcBatch *b, int nb_cmds, int nb_pr
     // The commands go to the device as they are: validation, routing and the work-item lists are built there (mc_host.h).  The
     // host only counts the items per kernel to size the launches (no validation, no lists: a quarter of the old walk).
     b->nb_cmds = nb_cmds; b->nb_prof = nb_prof;
+    b->run_scaling = b->scaling; b->run_scaled[0] = b->scaled[0]; b->run_scaled[1] = b->scaled[1];
     {
         HostSection hs_loop(HT_MC_LOOP);
         int cnt[MC_NB_REGIONS];
@@ -299,7 +308,7 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
             a.refs.poc[l][i] = refs->poc[l][i];
             if (!p) continue;
             // a reference of another size needs its scale factor in the batch's table (ovgpu_mc_batch_set_scaling)
-            if (!((b->scaled[l] >> i) & 1) && (p->width != dst->width || p->height != dst->height))
+            if (!((b->run_scaled[l] >> i) & 1) && (p->width != dst->width || p->height != dst->height))
                 return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture (list %d, index %d) differs in size and has no scale factor", l, i);
             if (p->bitdepth != dst->bitdepth) return ovgpu_set_error(ctx, OVGPU_EINVAL, "reference picture bit depth differs");
             ga.present[l] |= 1u << i;
@@ -342,9 +351,9 @@ int ovgpu_mc_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUMcRefs *refs, 
             for (int i = 0; i < 16; i++) {
                 const OVGPUPicture *p = refs->rpl[l][i];
                 t.ref_w[l][i] = p ? p->width : dst->width; t.ref_h[l][i] = p ? p->height : dst->height;
-                t.scale[l][i][0] = b->scaling.scale[l][i][0]; t.scale[l][i][1] = b->scaling.scale[l][i][1];
+                t.scale[l][i][0] = b->run_scaling.scale[l][i][0]; t.scale[l][i][1] = b->run_scaling.scale[l][i][1];
             }
-        t.hor_col = b->scaling.chroma_hor_col; t.ver_col = b->scaling.chroma_ver_col;
+        t.hor_col = b->run_scaling.chroma_hor_col; t.ver_col = b->run_scaling.chroma_ver_col;
         OVGPU_CUDA_CHECK(ctx, ovd_launch<McRprK>(t, dim3(OVGPU_CEIL_DIV(b->nb_rpr, McRprK::WARPS), 1, 1), McRprK::SMEM_BYTES, next_stream()));
     }
     if (b->nb_big) {
