@@ -79,6 +79,23 @@ typedef struct OVGPUWindow {        /* struct Window (ovframe.h): offsets in CHR
  * dst must not be smaller than src's scaling window (the reference's down-sampling branch is not reached from post_proc.c). */
 typedef struct OVGPUScalingWindow { uint16_t left, right, top, bottom; uint8_t chroma_hor_col, chroma_ver_col; } OVGPUScalingWindow;
 int  ovgpu_picture_upscale(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUScalingWindow *win);
+/* Film grain synthesis on an output picture (replaces fg_grain_apply_pic, pp_film_grain.c:814-977, as pp_process_frame runs it when
+ * the stream carries a film grain characteristics SEI, post_proc.c:50-57, 100-103: de-blocking on, 10 bit): the fields of struct
+ * OVSEIFGrain (nvcl_structures.h:115-140) the synthesis reads, as the SEI carries them.  Pictures whose luma or chroma size leaves a
+ * block row / column of fewer than 8 samples (size % 16 in 1..7) are refused: the reference reads out of its planes there. */
+typedef struct OVGPUFilmGrain {
+    uint8_t log2_scale_factor;
+    uint8_t comp_model_present_flag[3];
+    uint8_t num_model_values_minus1[3];
+    uint8_t intensity_interval_lower_bound[3][8], intensity_interval_upper_bound[3][8];
+    int16_t comp_model_value[3][8][3];
+} OVGPUFilmGrain;
+typedef struct OVGPUFilmGrainSynth OVGPUFilmGrainSynth;   /* the 13 x 13 grain patterns in HBM + the per-picture generator states */
+int  ovgpu_film_grain_create(OVGPUCtx *ctx, OVGPUFilmGrainSynth **synth);
+void ovgpu_film_grain_destroy(OVGPUFilmGrainSynth *synth);
+/* dst = src + grain; poc = the frame's POC (the generator's seed, pp_film_grain.c:869-872).  Asynchronous. */
+int  ovgpu_film_grain_picture(OVGPUCtx *ctx, OVGPUFilmGrainSynth *synth, OVGPUPicture *dst, const OVGPUPicture *src,
+                              const OVGPUFilmGrain *fg, int32_t poc);
 /* the rows dectest would write, copied to host planes (win == NULL: the whole picture) */
 int  ovgpu_picture_download_window(OVGPUCtx *ctx, const OVGPUPicture *pic, const OVGPUWindow *win, void *const data[3], const size_t linesize[3]);
 /* running MD5 (RFC 1321) of those rows, computed on the device: ovgpu_md5_picture appends one picture (asynchronous, one GPU

@@ -359,6 +359,32 @@ def upscale(ctx, dst, src, window=(0, 0, 0, 0), hor_col=1, ver_col=0):
     _check(ctx.h, lib().ovgpu_picture_upscale(ctx.h, dst.p, src.p, C.byref(win)), "picture_upscale")
 
 
+class FilmGrainSei(C.Structure):
+    """OVGPUFilmGrain: the fields of the film grain characteristics SEI the synthesis reads"""
+    _fields_ = [("log2_scale_factor", C.c_uint8), ("comp_model_present_flag", C.c_uint8 * 3), ("num_model_values_minus1", C.c_uint8 * 3),
+                ("intensity_interval_lower_bound", C.c_uint8 * 8 * 3), ("intensity_interval_upper_bound", C.c_uint8 * 8 * 3),
+                ("comp_model_value", C.c_int16 * 3 * 8 * 3)]
+
+
+class FilmGrainSynth:
+    """ovgpu_film_grain_*: the grain patterns in HBM; picture(dst, src, sei, poc) = dst <- src + grain"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.p = vp()
+        _check(ctx.h, lib().ovgpu_film_grain_create(ctx.h, C.byref(self.p)), "film_grain_create")
+
+    def picture(self, dst, src, sei, poc):
+        g = FilmGrainSei()
+        C.memmove(C.byref(g), C.byref(sei), C.sizeof(g))
+        _check(self.ctx.h, lib().ovgpu_film_grain_picture(self.ctx.h, self.p, dst.p, src.p, C.byref(g), int(poc)), "film_grain_picture")
+
+    def destroy(self):
+        if self.p:
+            lib().ovgpu_film_grain_destroy(self.p)
+            self.p = vp()
+
+
 class Dist:
     """ovgpu_dist_*: the reference hand-off between the ranks of one node (NCCL send / receive behind the C ABI)"""
 

@@ -9,6 +9,7 @@
 // stream beside the reconstruction, not part of the timed path.
 #include "common.cuh"
 #include "pp_kernels.h"
+#include "fg_kernels.h"
 #include <stdlib.h>
 
 struct OVGPUMd5 {
@@ -229,6 +230,91 @@ int ovgpu_picture_upscale(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *
     dim3 grid(OVGPU_CEIL_DIV(a.dst_w, 32), OVGPU_CEIL_DIV(a.dst_h, 8), 3);
     OVGPU_CUDA_CHECK(ctx, ovd_launch<UpscaleK>(a, grid, 0, ctx->stream));
     ctx->launches += 1;
+    return 0;
+}
+
+
+// Film grain synthesis on an output picture: what pp_process_frame does on the CPU for streams with a film grain characteristics
+// SEI (post_proc.c:50-57, 100-103 -> fg_grain_apply_pic, pp_film_grain.c:814-977).  The synthesiser object owns the pattern data
+// base (built once on the host, 676 KB in HBM) and the per-picture generator states.
+struct OVGPUFilmGrainSynth {
+    int device;
+    int8_t *d_db;
+    uint32_t *d_seeds;
+    size_t seeds_cap;            // entries
+};
+
+int ovgpu_film_grain_create(OVGPUCtx *ctx, OVGPUFilmGrainSynth **out)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !out) return OVGPU_EINVAL;
+    OVGPUFilmGrainSynth *s = (OVGPUFilmGrainSynth *)calloc(1, sizeof(*s));
+    int8_t *db = (int8_t *)malloc(FG_DB_BYTES);
+    if (!s || !db) { free(s); free(db); return OVGPU_ENOMEM; }
+    s->device = ctx->device;
+    fg_build_database(db);
+    if (cudaMalloc(&s->d_db, FG_DB_BYTES) != cudaSuccess ||
+        cudaMemcpyAsync(s->d_db, db, FG_DB_BYTES, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        free(db); ovgpu_film_grain_destroy(s);
+        return ovgpu_set_error(ctx, OVGPU_ENOMEM, "film grain data base: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    free(db);
+    *out = s;
+    return 0;
+}
+
+void ovgpu_film_grain_destroy(OVGPUFilmGrainSynth *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->d_db) cudaFree(s->d_db);
+    if (s->d_seeds) cudaFree(s->d_seeds);
+    free(s);
+}
+
+int ovgpu_film_grain_picture(OVGPUCtx *ctx, OVGPUFilmGrainSynth *s, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUFilmGrain *fg, int32_t poc)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !s || !dst || !src || !fg || dst == src) return OVGPU_EINVAL;
+    if (dst->width != src->width || dst->height != src->height) return ovgpu_set_error(ctx, OVGPU_EINVAL, "film grain: picture sizes differ");
+    if (src->bitdepth != 10 || dst->bitdepth != 10) return ovgpu_set_error(ctx, OVGPU_EINVAL, "film grain: the reference synthesises at 10 bit only (pp_film_grain.c:836)");
+    if (fg->log2_scale_factor > 15) return ovgpu_set_error(ctx, OVGPU_EINVAL, "film grain: log2_scale_factor %d", fg->log2_scale_factor);
+    if (!fg_size_ok(src->width, src->height))
+        return ovgpu_set_error(ctx, OVGPU_EINVAL, "film grain: %d x %d leaves a block row / column of fewer than 8 samples, which the reference reads out of bounds", src->width, src->height);
+    static const uint8_t colour_offset[3] = { 0, 85, 170 };          // COLOUR_OFFSET_LUMA / _CR / _CB in component order (:56-58, 834-836)
+    FilmGrainK::Args a;
+    memset(&a, 0, sizeof(a));
+    FgSeedK::Args sa;
+    memset(&sa, 0, sizeof(sa));
+    size_t need = 0;
+    for (int c = 0; c < 3; c++) {
+        const int cw = src->width >> (c != 0), chh = src->height >> (c != 0);
+        sa.nb16w[c] = (cw + 15) >> 4; sa.nb16h[c] = (chh + 15) >> 4;
+        need += (size_t)sa.nb16w[c] * sa.nb16h[c];
+    }
+    if (need > s->seeds_cap) {
+        // (the buffer of a smaller picture may still be read by a kernel of the previous call on this stream)
+        OVGPU_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (s->d_seeds) cudaFree(s->d_seeds);
+        s->d_seeds = NULL; s->seeds_cap = 0;
+        if (cudaMalloc(&s->d_seeds, need * sizeof(uint32_t)) != cudaSuccess) return ovgpu_set_error(ctx, OVGPU_ENOMEM, "film grain generator states");
+        s->seeds_cap = need;
+    }
+    size_t off = 0;
+    for (int c = 0; c < 3; c++) {
+        PlaneView d = plane_view(dst, c), sv = plane_view((OVGPUPicture *)src, c);
+        a.dst[c] = d.p; a.dst_pitch[c] = d.pitch; a.src[c] = sv.p; a.src_pitch[c] = sv.pitch;
+        sa.seeds[c] = s->d_seeds + off; a.seeds[c] = sa.seeds[c];
+        off += (size_t)sa.nb16w[c] * sa.nb16h[c];
+        sa.seed0[c] = fg_seeds[((uint32_t)poc + colour_offset[c]) % 256];
+    }
+    a.w = src->width; a.h = src->height; a.db = s->d_db;
+    fg_make_params(&a.p, fg);
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<FgSeedK>(sa, dim3(1, 1, 3), 0, ctx->stream));
+    dim3 grid(OVGPU_CEIL_DIV(a.w, FilmGrainK::COLS), OVGPU_CEIL_DIV(a.h, 16), 3);
+    OVGPU_CUDA_CHECK(ctx, ovd_launch<FilmGrainK>(a, grid, FilmGrainK::SMEM_BYTES, ctx->stream));
+    ctx->launches += 2;
     return 0;
 }
 

@@ -156,6 +156,20 @@ typedef struct OVOScalingWindow { uint16_t left, right, top, bottom; uint8_t chr
 int ovo_pp_upscale_plane(uint16_t *dst, int dst_stride, int dst_w, int dst_h, const uint16_t *src, int src_stride, int src_w, int src_h,
                          const OVOScalingWindow *win, int luma, int bitdepth);
 
+/* ---- Output stage: film grain synthesis (fg_grain_apply_pic, pp_film_grain.c:814-977).  The fields of struct OVSEIFGrain
+ * (nvcl_structures.h:115-140) the synthesis reads, as the SEI carries them (the chroma conversion of the model values is part
+ * of the synthesis). ------------------------------------------------------------------------------------------------- */
+typedef struct OVOFilmGrain {
+    uint8_t log2_scale_factor;
+    uint8_t comp_model_present_flag[3];
+    uint8_t num_model_values_minus1[3];
+    uint8_t intensity_interval_lower_bound[3][8], intensity_interval_upper_bound[3][8];
+    int16_t comp_model_value[3][8][3];
+} OVOFilmGrain;
+void ovo_fg_database(int8_t *db /* [13][13][64][64] */, int deblock);
+int  ovo_fg_size_ok(int w, int h);
+int  ovo_fg_apply(uint16_t *const dst[3], const uint16_t *const src[3], int w, int h, const OVOFilmGrain *fg, int32_t poc, const int8_t *db);
+
 /* ---- LMCS ------------------------------------------------------------------------------------------- */
 typedef struct OVOLmcsData {          /* OVLMCSData, nvcl_structures.h:671-680 */
     uint8_t lmcs_min_bin_idx;

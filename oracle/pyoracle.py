@@ -326,3 +326,56 @@ def pp_upscale(planes, dst_w, dst_h, window=(0, 0, 0, 0), hor_col=1, ver_col=0, 
             f(d.ctypes.data_as(u16p), dw, dw, dh, p.ctypes.data_as(u16p), p.strides[0] // 2, sw, sh, C.byref(win), int(c == 0))
         out.append(d)
     return out
+
+
+# ---- output stage: film grain synthesis --------------------------------------------------------------------------
+class FilmGrain(C.Structure):
+    """OVOFilmGrain: the fields of the film grain characteristics SEI the synthesis reads (struct OVSEIFGrain)"""
+    _fields_ = [("log2_scale_factor", C.c_uint8), ("comp_model_present_flag", C.c_uint8 * 3), ("num_model_values_minus1", C.c_uint8 * 3),
+                ("intensity_interval_lower_bound", C.c_uint8 * 8 * 3), ("intensity_interval_upper_bound", C.c_uint8 * 8 * 3),
+                ("comp_model_value", C.c_int16 * 3 * 8 * 3)]
+
+
+def make_film_grain(seed, present=(1, 1, 1)):
+    """a random but well-formed SEI: log2 scale 2..7, up to 8 disjoint intensity intervals per component, 1..3 model values
+    (standard deviation 0..255, cut-off frequencies 2..14)"""
+    rng = np.random.default_rng(seed)
+    fg = FilmGrain()
+    fg.log2_scale_factor = int(rng.integers(2, 8))
+    for c in range(3):
+        fg.comp_model_present_flag[c] = int(present[c])
+        fg.num_model_values_minus1[c] = int(rng.integers(0, 3))
+        n = int(rng.integers(1, 9))
+        cuts = np.sort(rng.choice(np.arange(1, 255), size=2 * n, replace=False))
+        for i in range(n):
+            fg.intensity_interval_lower_bound[c][i] = int(cuts[2 * i]); fg.intensity_interval_upper_bound[c][i] = int(cuts[2 * i + 1])
+            fg.comp_model_value[c][i][0] = int(rng.integers(0, 256))
+            fg.comp_model_value[c][i][1] = int(rng.integers(2, 15)); fg.comp_model_value[c][i][2] = int(rng.integers(2, 15))
+    return fg
+
+
+_fg_db = {}
+
+
+def fg_database(impl="port"):
+    if impl not in _fg_db:
+        db = np.zeros(13 * 13 * 64 * 64, np.int8)
+        (port().ovo_fg_database if impl == "port" else ref().ovref_fg_database)(db.ctypes.data_as(C.c_void_p), 1)
+        _fg_db[impl] = db
+    return _fg_db[impl]
+
+
+def fg_apply(planes, fg, poc, impl="port"):
+    """fg_grain_apply_pic on the three planes of a decoded picture"""
+    src = [np.ascontiguousarray(p) for p in planes]
+    h, w = src[0].shape
+    out = [np.zeros_like(p) for p in src]
+    d3 = (u16p * 3)(*[p.ctypes.data_as(u16p) for p in out]); s3 = (u16p * 3)(*[p.ctypes.data_as(u16p) for p in src])
+    if impl == "port":
+        rc = port().ovo_fg_apply(d3, s3, w, h, C.byref(fg), int(poc), fg_database("port").ctypes.data_as(C.c_void_p))
+        assert rc == 0, "picture size the reference's block loops do not handle"
+    else:
+        f = ref().ovref_fg_apply
+        f.restype = None
+        f(d3, s3, w, h, C.byref(fg), int(poc))
+    return out

@@ -479,3 +479,44 @@ ovref_pp_upscale_plane(uint16_t *dst, int dst_stride, int dst_w, int dst_h, cons
     si.chroma_hor_col_flag = win->chroma_hor_col; si.chroma_ver_col_flag = win->chroma_ver_col;
     pp_sample_rate_conv(dst, (uint16_t)dst_stride, dst_w, dst_h, (uint16_t *)src, (uint16_t)src_stride, src_w, src_h, &si, (uint8_t)luma);
 }
+
+/* the reference's film grain synthesis (pp_film_grain.c; both functions are exported, post_proc.h) */
+void fg_data_base_generation(uint8_t enableDeblocking);
+void fg_simulate_grain_blk8x8(int32_t *grainStripe, uint32_t grainStripeOffsetBlk8, uint32_t width, uint8_t log2ScaleFactor, int16_t scaleFactor,
+                              uint32_t kOffset, uint32_t lOffset, uint8_t h, uint8_t v, uint32_t xSize);
+void fg_grain_apply_pic(int16_t **dstComp, int16_t **srcComp, struct OVSEIFGrain *fgrain, int pic_w, int pic_h, int poc, uint8_t isIdrPic, uint8_t enableDeblocking);
+
+/* its pattern data base (a static array), read back 8x8 window by window through fg_simulate_grain_blk8x8 with a unit scale */
+void
+ovref_fg_database(int8_t *db, int deblock)
+{
+    fg_data_base_generation((uint8_t)deblock);
+    for (int h = 0; h < 13; h++)
+        for (int v = 0; v < 13; v++)
+            for (int lo = 0; lo < 64; lo += 8)
+                for (int ko = 0; ko < 64; ko += 8) {
+                    int32_t blk[64];
+                    fg_simulate_grain_blk8x8(blk, 0, 8, 0, 64, ko, lo, (uint8_t)h, (uint8_t)v, 8);
+                    for (int l = 0; l < 8; l++)
+                        for (int k = 0; k < 8; k++) db[(size_t)(h * 13 + v) * 4096 + (lo + l) * 64 + ko + k] = (int8_t)blk[l * 8 + k];
+                }
+}
+
+void
+ovref_fg_apply(uint16_t *const dst[3], const uint16_t *const src[3], int w, int h, const OVOFilmGrain *fg, int32_t poc)
+{
+    struct OVSEIFGrain sei;
+    memset(&sei, 0, sizeof(sei));
+    sei.fg_log2_scale_factor = fg->log2_scale_factor;
+    for (int c = 0; c < 3; c++) {
+        sei.fg_comp_model_present_flag[c] = fg->comp_model_present_flag[c];
+        sei.fg_num_model_values_minus1[c] = fg->num_model_values_minus1[c];
+        for (int i = 0; i < 8; i++) {
+            sei.fg_intensity_interval_lower_bound[c][i] = fg->intensity_interval_lower_bound[c][i];
+            sei.fg_intensity_interval_upper_bound[c][i] = fg->intensity_interval_upper_bound[c][i];
+            for (int k = 0; k < 3; k++) sei.fg_comp_model_value[c][i][k] = fg->comp_model_value[c][i][k];
+        }
+    }
+    int16_t *d[3] = { (int16_t *)dst[0], (int16_t *)dst[1], (int16_t *)dst[2] }, *s_[3] = { (int16_t *)src[0], (int16_t *)src[1], (int16_t *)src[2] };
+    fg_grain_apply_pic(d, s_, &sei, w, h, poc, 0, 1);
+}

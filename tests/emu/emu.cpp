@@ -10,6 +10,7 @@
 #include "../../openvvc_b200/csrc/dbf_kernels.h"
 #include "../../openvvc_b200/csrc/intra_host.h"
 #include "../../openvvc_b200/csrc/pp_kernels.h"
+#include "../../openvvc_b200/csrc/fg_kernels.h"
 
 static const int16_t *emu_tr_scales = NULL;     // LMCS chroma scales of the running emu_recon_picture call
 
@@ -127,6 +128,34 @@ int emu_pp_upscale(uint16_t *const dst[3], const int dst_stride[3], int dst_w, i
     a.dst_w = dst_w; a.dst_h = dst_h; a.src_w = src_w; a.src_h = src_h; a.maxv = 1023;
     if (upscale_setup(&a, win[0], win[1], win[2], win[3], win[4], win[5])) return -1;
     ovd_emulate<UpscaleK>(a, ovd_dim3((dst_w + 31) / 32, (dst_h + 7) / 8, 3), 0);
+    return 0;
+}
+
+// output stage: film grain synthesis (FgSeedK + FilmGrainK)
+int emu_film_grain(uint16_t *const dst[3], const int dst_stride[3], const uint16_t *const src[3], const int src_stride[3], int w, int h,
+                   const OVGPUFilmGrain *fg, int32_t poc)
+{
+    static std::vector<int8_t> db;
+    if (db.empty()) { db.resize(FG_DB_BYTES); fg_build_database(db.data()); }
+    if (!fg_size_ok(w, h)) return -1;
+    static const uint8_t colour_offset[3] = { 0, 85, 170 };
+    FilmGrainK::Args a;
+    memset(&a, 0, sizeof(a));
+    FgSeedK::Args sa;
+    memset(&sa, 0, sizeof(sa));
+    std::vector<uint32_t> seeds[3];
+    for (int c = 0; c < 3; c++) {
+        const int cw = w >> (c != 0), chh = h >> (c != 0);
+        sa.nb16w[c] = (cw + 15) >> 4; sa.nb16h[c] = (chh + 15) >> 4;
+        seeds[c].resize((size_t)sa.nb16w[c] * sa.nb16h[c]);
+        sa.seeds[c] = seeds[c].data(); a.seeds[c] = seeds[c].data();
+        sa.seed0[c] = fg_seeds[((uint32_t)poc + colour_offset[c]) % 256];
+        a.dst[c] = dst[c]; a.dst_pitch[c] = dst_stride[c]; a.src[c] = src[c]; a.src_pitch[c] = src_stride[c];
+    }
+    a.w = w; a.h = h; a.db = db.data();
+    fg_make_params(&a.p, fg);
+    ovd_emulate<FgSeedK>(sa, ovd_dim3(1, 1, 3), 0);
+    ovd_emulate<FilmGrainK>(a, ovd_dim3((w + FilmGrainK::COLS - 1) / FilmGrainK::COLS, (h + 15) / 16, 3), FilmGrainK::SMEM_BYTES);
     return 0;
 }
 
