@@ -51,5 +51,25 @@ def test_results_do_not_depend_on_cta_order(oracle, emu):
         helpers.assert_planes_equal(helpers_df.emu_dbf(emu, planes, maps), want, "DBF, reversed CTA order")
         planes, sao = helpers.sao_case(oracle, w, h, 45, 7)
         helpers.assert_planes_equal(helpers.emu_sao(emu, planes, sao, 7), oracle.sao_picture(planes, sao, 7, impl="port"), "SAO, reversed CTA order")
+        # the kernels added last: motion compensation from scaled references, the up-scaler and the film grain synthesis
+        import ctypes as C
+        from openvvc_b200 import synth
+        refs0, refs1, pocs, cmds, luts, prof, sc = helpers_mc.rpr_case(oracle, w, h, 46, 7, True, "noise")
+        a = helpers_mc.blank(w, h)
+        oracle.mc_picture_rpr(a, [refs0, refs1], pocs, cmds, sc, 7, impl="port", lmcs=luts, prof=prof)
+        helpers.assert_planes_equal(helpers_mc.emu_mc_rpr(emu, oracle, w, h, refs0, refs1, pocs, cmds, luts, sc, prof=prof), a, "RPR MC, reversed CTA order")
+        pl = synth.planes(272, 160, 47, "noise")
+        want = oracle.pp_upscale(pl, w, h, (4, 4, 2, 6), 0, 0, "port")
+        out = helpers_mc.blank(w, h)
+        dst, ds = oracle._planes_arg(out); src, ss = oracle._planes_arg(pl)
+        assert emu.emu_pp_upscale(dst, ds, w, h, src, ss, 272, 160, (C.c_int * 6)(4, 4, 2, 6, 0, 0)) == 0
+        helpers.assert_planes_equal(out, want, "up-scaler, reversed CTA order")
+        pl = synth.planes(w, h, 48, "noise")
+        fg = oracle.make_film_grain(48)
+        want = oracle.fg_apply(pl, fg, 5, "port")
+        out = helpers_mc.blank(w, h)
+        dst, ds = oracle._planes_arg(out); src, ss = oracle._planes_arg(pl)
+        assert emu.emu_film_grain(dst, ds, src, ss, w, h, C.byref(fg), 5) == 0
+        helpers.assert_planes_equal(out, want, "film grain, reversed CTA order")
     finally:
         emu.emu_set_reverse_block_order(0)
