@@ -15,6 +15,10 @@
  *                               the CTU lines be reported decoded (dpb.c:1309; slicedec.c is compiled with
  *                               ovdpb_report_decoded_ctu_line redirected here), which is what TMVP of later pictures waits on
  *                               (drv_mvp.c:292).
+ *   pp_process_frame()          the output stage (post_proc.c:76, called from ovdec_receive_picture / _drain_picture): post_proc.c
+ *                               is compiled with -Dpp_process_frame=pp_process_frame_stock and this file's wrapper runs the
+ *                               up-scaling of resampled sequences (-u 1) and the film grain synthesis on the GPU from the
+ *                               frame's device mirror; anything it does not take goes to the stock function.
  *
  * The decoder-side bookkeeping that later CPU stages depend on (deblocking edge / bs / QP maps, progress bit fields, MV maps)
  * stays the reference's: transform trees, TUs, ISP sub-trees and the deblocking pre-processing still run through the STOCK
@@ -47,6 +51,9 @@
 #include "rcn_alf.h"
 #include "dbf_utils.h"
 #include "ovdec_internal.h"
+#include "ovframepool.h"
+#include "post_proc.h"
+#include "overror.h"
 #include "bitdepth.h"
 
 #include "ovvc_b200.h"
@@ -961,6 +968,86 @@ void rcn_init_functions_cuda(struct RCNFunctions *f)
     f->rcn_write_ctu_to_frame = &nop_ctx_u8; f->rcn_write_ctu_to_frame_border = &nop_ctx_int_int;
     f->rcn_ctu_to_intra_line = &nop_ctx_int_u8; f->rcn_intra_line_to_ctu = &nop_ctx_int_u8; f->rcn_update_ctu_border = &nop_ctx_u8_m;
     f->rcn_attach_frame_buff = &rec_attach_frame_buff;
+}
+
+/* ------------------------------------------------------------------------------------------------ output stage */
+int pp_process_frame_stock(const OVSEI *sei, OVFrame **frame_p);
+
+static struct {
+    pthread_mutex_t mtx;
+    OVGPUCtx *ctx;
+    OVGPUFilmGrainSynth *fg;
+    OVGPUPicture *out; int out_w, out_h;
+} pp = { PTHREAD_MUTEX_INITIALIZER, NULL, NULL, NULL, 0, 0 };
+
+/* Takes the place of pp_process_frame (post_proc.c:76-139).  What the stock function does to an output frame -- a second frame
+ * from the same pool, film grain into it (fg_grain_apply_pic) and / or the decoded frame resampled into it at the pool's size
+ * (pp_sample_rate_conv, which overwrites the grain: post_proc.c:100-128) -- is done from the frame's device mirror, and only the
+ * result crosses PCIe.  Frames without a mirror, cancelled film grain, film grain on a frame whose rows are not contiguous (the
+ * stock function walks such a frame with the wrong stride) or whose size it reads out of bounds: the stock function. */
+int pp_process_frame(const OVSEI *sei, OVFrame **frame_p)
+{
+    if (!ovshim_backend_enabled() || !sei || !frame_p || !*frame_p || (!sei->sei_fg && !sei->upscale_flag)) return pp_process_frame_stock(sei, frame_p);
+    OVFrame *frame = *frame_p;
+    const int up = sei->upscale_flag != 0, w = (int)frame->width, h = (int)frame->height;
+    if (!up) {
+        int ok = !sei->sei_fg->fg_characteristics_cancel_flag && frame->linesize[0] == frame->width * sizeof(uint16_t) &&
+                 frame->linesize[1] == (frame->width >> 1) * sizeof(uint16_t) && sei->sei_fg->fg_log2_scale_factor <= 15;
+        for (int c = 0; c < 2 && ok; c++) {
+            const int cw = w >> c, ch = h >> c;
+            if ((cw % 16 && cw % 16 < 8) || (ch % 16 && ch % 16 < 8)) ok = 0;
+        }
+        if (!ok) return pp_process_frame_stock(sei, frame_p);
+    }
+    pthread_mutex_lock(&g.mtx);
+    ShimFrame *sf = frame_lookup(frame, 0, NULL);
+    OVGPUPicture *dev = sf && sf->state == FRAME_DONE ? sf->dev : NULL;
+    pthread_mutex_unlock(&g.mtx);
+    if (!dev) return pp_process_frame_stock(sei, frame_p);
+    OVFrame *post = ovframepool_request_frame(frame->internal.frame_pool);
+    if (!post) { ov_log(NULL, OVLOG_ERROR, "Could not get a writable picture for post processing\n"); ovframe_unref(frame_p); return OVVC_ENOMEM; }
+    const int ow = up ? (int)post->width : w, oh = up ? (int)post->height : h;
+    int rc = 0;
+    pthread_mutex_lock(&pp.mtx);
+    if (!pp.ctx && ovgpu_ctx_create(&pp.ctx, g.device, NULL) < 0) rc = -1;
+    if (!rc && (!pp.out || pp.out_w != ow || pp.out_h != oh)) {
+        if (pp.out) { ovgpu_ctx_sync(pp.ctx); ovgpu_picture_destroy(pp.out); pp.out = NULL; }
+        if (ovgpu_picture_create(pp.ctx, ow, oh, 10, &pp.out) < 0) rc = -1;
+        pp.out_w = ow; pp.out_h = oh;
+    }
+    if (!rc && up) {
+        OVGPUScalingWindow win = { sei->scaling_info.scaling_win_left, sei->scaling_info.scaling_win_right, sei->scaling_info.scaling_win_top,
+                                   sei->scaling_info.scaling_win_bottom, sei->scaling_info.chroma_hor_col_flag, sei->scaling_info.chroma_ver_col_flag };
+        rc = ovgpu_picture_upscale(pp.ctx, pp.out, dev, &win);
+    } else if (!rc) {
+        const struct OVSEIFGrain *s = sei->sei_fg;
+        OVGPUFilmGrain fg;
+        memset(&fg, 0, sizeof(fg));
+        fg.log2_scale_factor = s->fg_log2_scale_factor;
+        for (int c = 0; c < 3; c++) {
+            fg.comp_model_present_flag[c] = s->fg_comp_model_present_flag[c]; fg.num_model_values_minus1[c] = s->fg_num_model_values_minus1[c];
+            for (int i = 0; i < 8; i++) {
+                fg.intensity_interval_lower_bound[c][i] = s->fg_intensity_interval_lower_bound[c][i];
+                fg.intensity_interval_upper_bound[c][i] = s->fg_intensity_interval_upper_bound[c][i];
+                for (int k = 0; k < 3; k++) fg.comp_model_value[c][i][k] = s->fg_comp_model_value[c][i][k];
+            }
+        }
+        if (!pp.fg && ovgpu_film_grain_create(pp.ctx, &pp.fg) < 0) rc = -1;
+        if (!rc) rc = ovgpu_film_grain_picture(pp.ctx, pp.fg, pp.out, dev, &fg, (int32_t)frame->poc);
+    }
+    post->width = ow; post->height = oh;
+    if (!rc) rc = ovgpu_picture_download(pp.ctx, pp.out, (void *const *)post->data, post->linesize);
+    if (!rc) rc = ovgpu_ctx_sync(pp.ctx);
+    if (rc < 0) ov_log(NULL, OVLOG_ERROR, "rcn cuda back end: output stage failed (%d): %s\n", rc, pp.ctx ? ovgpu_last_error(pp.ctx) : "no context");
+    pthread_mutex_unlock(&pp.mtx);
+    if (g.verbose) fprintf(stderr, "rcn cuda: output stage of POC %d on the GPU: %s -> %d x %d%s\n", (int)frame->poc, up ? "up-scaling" : "film grain", ow, oh, rc < 0 ? "  FAILED" : "");
+    if (rc < 0) {                        /* the decoded frame is intact in host memory: let the stock function produce the output */
+        ovframe_unref(&post);
+        return pp_process_frame_stock(sei, frame_p);
+    }
+    ovframe_unref(frame_p);
+    *frame_p = post;
+    return 0;
 }
 
 /* Takes the place of the reference's rcn_init_functions (rcn.c:148; slicedec.c:1462 calls it per entry job). */

@@ -56,6 +56,22 @@ int ovgpu_picture_download(OVGPUCtx *, const OVGPUPicture *p, void *const data[3
     return 0;
 }
 
+// output stage (shim: pp_process_frame)
+int ovgpu_picture_upscale(OVGPUCtx *c, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUScalingWindow *win)
+{
+    const int w6[6] = { win ? win->left : 0, win ? win->right : 0, win ? win->top : 0, win ? win->bottom : 0, win ? win->chroma_hor_col != 0 : 1, win ? win->chroma_ver_col != 0 : 0 };
+    if (emu_pp_upscale(dst->plane, dst->stride, dst->w, dst->h, src->plane, src->stride, src->w, src->h, w6)) return fail(c, OVGPU_EINVAL, "emulated up-scaling refused");
+    return 0;
+}
+struct OVGPUFilmGrainSynth { int dummy; };
+int ovgpu_film_grain_create(OVGPUCtx *, OVGPUFilmGrainSynth **s) { *s = new OVGPUFilmGrainSynth(); return 0; }
+void ovgpu_film_grain_destroy(OVGPUFilmGrainSynth *s) { delete s; }
+int ovgpu_film_grain_picture(OVGPUCtx *c, OVGPUFilmGrainSynth *, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUFilmGrain *fg, int32_t poc)
+{
+    if (dst->w != src->w || dst->h != src->h || emu_film_grain(dst->plane, dst->stride, src->plane, src->stride, src->w, src->h, fg, poc)) return fail(c, OVGPU_EINVAL, "emulated film grain refused");
+    return 0;
+}
+
 int ovgpu_mc_batch_create(OVGPUCtx *, int max_cmds, int, OVGPUMcBatch **b) { *b = new OVGPUMcBatch(); (*b)->cmds.resize(max_cmds + 1); (*b)->prof.resize(65536); (*b)->nb = (*b)->nb_prof = (*b)->nb_dmvr = 0; return ovgpu_mc_batch_set_scaling(NULL, *b, NULL); }
 int ovgpu_mc_batch_set_scaling(OVGPUCtx *, OVGPUMcBatch *b, const OVGPUMcScaling *s)
 {

@@ -71,12 +71,14 @@ def make(stream_dir, name, table=STREAMS):
     return path
 
 
-def decode(binary, stream, out, threads=1, backend=None):
+def decode(binary, stream, out, threads=1, backend=None, extra=(), verbose=False):
     env = dict(os.environ)
     env.pop("OVVC_RCN_BACKEND", None)
     if backend:
         env["OVVC_RCN_BACKEND"] = backend
-    r = subprocess.run([binary, "-i", stream, "-o", out, "-t", str(threads), "-e", "1", "-l", "2"], env=env, capture_output=True, text=True, timeout=1800)
+    if verbose:
+        env["OVVC_RCN_VERBOSE"] = "1"
+    r = vs.run_decoder([binary, "-i", stream, "-o", out, "-t", str(threads), "-e", "1", "-l", "2"] + list(extra), env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "rcn cuda back end:" not in r.stderr or "failed" not in r.stderr, r.stderr[-2000:]
     return md5_file(out), r.stderr

@@ -96,3 +96,66 @@ def test_gpu_matches_oracle(po, w, h, seed, poc, kind, present):
         synth_.destroy(); src.destroy(); dst.destroy(); small.destroy()
     finally:
         ctx.close()
+
+
+# ---- the output stage inside the drop-in: pp_process_frame (post_proc.c:76) taken over by shim/rcn_cuda.c ------------------------
+import test_dropin as td  # noqa: E402
+
+pp_streams = pytest.mark.skipif(not os.path.exists(os.path.join(td.REF, "dectest_gen")), reason="oracle/_ref (compiled reference + generative decoder) was not built")
+
+
+def _pp_stream(stream_dir, name):
+    path = os.path.join(str(stream_dir), name + ".266")
+    if not os.path.exists(path):
+        if name == "fg":          # the CTC toolset + a film grain characteristics SEI in front of the first picture
+            td.vs.make_stream(path, 416, 240, 9, gop=8, seed=41, preset="ctc", verify=True, film_grain=True)
+        else:                     # pictures of three sizes, decoded with -u 1: every output frame is brought to 416 x 240
+            td.vs.make_stream(path, 416, 240, 9, gop=8, seed=42, preset="rpr", verify=True, rpr_sizes=[(208, 120), (320, 192)])
+    return path
+
+
+def _check_output_stage(stream_dir, binary, name, extra, what, threads):
+    stream = _pp_stream(stream_dir, name)
+    base = os.path.join(str(stream_dir), name)
+    want, _ = td.decode(os.path.join(td.REF, "dectest_c"), stream, base + "_c.yuv", extra=extra)
+    got, err = td.decode(binary, stream, base + "_%s_t%d.yuv" % (os.path.basename(binary), threads), threads=threads, backend="cuda", extra=extra, verbose=True)
+    assert err.count("output stage of POC") == 9 and what in err and "FAILED" not in err, err[-1500:]      # taken by the back end, not the stock path
+    assert got == want, "%s: %s decodes to %s, the stock decoder to %s" % (name, os.path.basename(binary), got, want)
+    return want
+
+
+@pp_streams
+@pytest.mark.parametrize("name,extra,what", [("fg", (), "film grain"), ("rpr_up", ("-u", "1"), "up-scaling")])
+def test_output_stage_in_the_dropin_emulated(stream_dir, name, extra, what):
+    """film grain SEI / dectest -u 1 through build/dectest_emu: the frames come from the (emulated) device mirrors"""
+    binary = os.path.join(td.BUILD, "dectest_emu")
+    if not os.path.exists(binary):
+        pytest.skip("build/dectest_emu not built (python __graft_entry__.py)")
+    for threads in (1, 4):
+        _check_output_stage(stream_dir, binary, name, extra, what, threads)
+    if name == "fg":              # the SEI really changes the output: the same stream without its SEI NAL decodes differently
+        stream = _pp_stream(stream_dir, name)
+        data = open(stream, "rb").read()
+        i = data.find(b"\x00\x00\x01\x00\xb9")            # NAL header of the prefix SEI (type 23, temporal id 0)
+        j = data.find(b"\x00\x00\x01", i + 3)
+        assert i > 0 and j > i
+        bare = os.path.join(str(stream_dir), "fg_bare.266")
+        open(bare, "wb").write(data[:i] + data[j:])
+        a, _ = td.decode(os.path.join(td.REF, "dectest_c"), bare, bare + ".yuv")
+        b, _ = td.decode(os.path.join(td.REF, "dectest_c"), stream, bare + ".fg.yuv")
+        assert a != b
+
+
+@pytest.fixture(scope="module")
+def stream_dir(tmp_path_factory):
+    return tmp_path_factory.mktemp("pp_streams")
+
+
+@pp_streams
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra,what", [("fg", (), "film grain"), ("rpr_up", ("-u", "1"), "up-scaling")])
+def test_output_stage_in_the_dropin_gpu(stream_dir, name, extra, what):
+    binary = os.path.join(td.BUILD, "dectest")
+    assert os.path.exists(binary), "build/dectest missing: run python __graft_entry__.py where /root/reference exists"
+    for threads in (1, 4):
+        _check_output_stage(stream_dir, binary, name, extra, what, threads)
