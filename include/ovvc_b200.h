@@ -199,6 +199,13 @@ int  ovgpu_sao_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_
 void ovgpu_sao_params_destroy(OVGPUSaoParams *p);
 int  ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu *ctu);
 /* dst = SAO(src): src is the deblocked picture; dst must be a different picture. Asynchronous. */
+/* Tiles (rect entries, struct RectEntryInfo): the reference runs its in-loop filters entry by entry and treats an entry's edges like
+ * picture borders -- SAO leaves their samples alone for the edge classes that would look across them (rcn_sao.c:164-177, 211-214,
+ * 241-245; the single-CTU-row quirk of rcn_sao_first_pix_rows applies per entry).  Boundaries in CTUs: col_bd[0] = 0 ...
+ * col_bd[nb_cols] = the picture's width in CTUs, rows likewise; at most 20 x 20 tiles.  NULL or one tile: none (the default). */
+typedef struct OVGPUTileGrid { int32_t nb_cols, nb_rows; uint16_t col_bd[22], row_bd[22]; } OVGPUTileGrid;
+int  ovgpu_tile_grid_check(const OVGPUTileGrid *tiles, int nb_ctu_w, int nb_ctu_h);
+int  ovgpu_sao_params_set_tiles(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUTileGrid *tiles);
 int  ovgpu_sao_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUSaoParams *p);
 int  ovgpu_sao_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t dst_linesize[3],
                           const void *const src_data[3], const size_t src_linesize[3],

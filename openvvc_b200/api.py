@@ -652,6 +652,11 @@ def mc_nb_items(cmds):
     return int(np.where((cmds["tool"] == 0) | (cmds["tool"] == 4), n, 1).sum())
 
 
+class TileGrid(C.Structure):
+    """OVGPUTileGrid: tile boundaries in CTUs"""
+    _fields_ = [("nb_cols", C.c_int32), ("nb_rows", C.c_int32), ("col_bd", C.c_uint16 * 22), ("row_bd", C.c_uint16 * 22)]
+
+
 class SaoParams:
     def __init__(self, ctx, w, h, log2_ctu=7):
         self.ctx = ctx
@@ -662,6 +667,16 @@ class SaoParams:
         sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SAO_CTU)
         self._keep = sao_ctu
         _check((ctx or self.ctx).h, lib().ovgpu_sao_params_upload((ctx or self.ctx).h, self.p, vp(sao_ctu.ctypes.data)), "sao_params_upload")
+
+    def set_tiles(self, col_bd=None, row_bd=None, ctx=None):
+        """ovgpu_sao_params_set_tiles: tile boundaries in CTUs (None: one tile)"""
+        tg = None
+        if col_bd is not None:
+            tg = TileGrid()
+            tg.nb_cols, tg.nb_rows = len(col_bd) - 1, len(row_bd) - 1
+            tg.col_bd[:len(col_bd)] = [int(v) for v in col_bd]
+            tg.row_bd[:len(row_bd)] = [int(v) for v in row_bd]
+        _check((ctx or self.ctx).h, lib().ovgpu_sao_params_set_tiles((ctx or self.ctx).h, self.p, C.byref(tg) if tg is not None else None), "sao_params_set_tiles")
 
     def run(self, dst, src, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_sao_picture((ctx or self.ctx).h, dst.p, src.p, self.p), "sao_picture")

@@ -7,11 +7,14 @@
 struct OVGPUSaoParams {
     int width, height, log2_ctu, nb_ctu_w, nb_ctu_h, nb_ctu;
     SaoCtuDev *h_ctu, *d_ctu;
+    TileGridDev *h_tiles, *d_tiles;      // ovgpu_sao_params_set_tiles
+    int has_tiles;
     int device;
     StagingFence fence;
 };
 
 static_assert(sizeof(SaoCtuDev) == sizeof(OVGPUSaoCtu), "SAO CTU parameter layout");
+static_assert(sizeof(TileGridDev) == sizeof(OVGPUTileGrid), "tile grid layout");
 
 extern "C" {
 
@@ -28,6 +31,7 @@ int ovgpu_sao_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s
     p->nb_ctu_h = (height + ctu_s - 1) >> log2_ctu_s;
     p->nb_ctu = p->nb_ctu_w * p->nb_ctu_h;
     if (cudaMallocHost(&p->h_ctu, sizeof(SaoCtuDev) * p->nb_ctu) != cudaSuccess ||
+        cudaMallocHost(&p->h_tiles, sizeof(TileGridDev)) != cudaSuccess || cudaMalloc(&p->d_tiles, sizeof(TileGridDev)) != cudaSuccess ||
         cudaMalloc(&p->d_ctu, sizeof(SaoCtuDev) * p->nb_ctu) != cudaSuccess) {
         ovgpu_sao_params_destroy(p);
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "SAO parameter buffers: %s", cudaGetErrorString(cudaGetLastError()));
@@ -42,6 +46,8 @@ void ovgpu_sao_params_destroy(OVGPUSaoParams *p)
     cudaSetDevice(p->device);
     if (p->h_ctu) cudaFreeHost(p->h_ctu);
     if (p->d_ctu) cudaFree(p->d_ctu);
+    if (p->h_tiles) cudaFreeHost(p->h_tiles);
+    if (p->d_tiles) cudaFree(p->d_tiles);
     fence_destroy(&p->fence);
     free(p);
 }
@@ -64,6 +70,30 @@ int ovgpu_sao_params_upload(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUSaoCtu 
     return 0;
 }
 
+// boundaries must start at 0, increase and end at the picture's size in CTUs
+int ovgpu_tile_grid_check(const OVGPUTileGrid *t, int nb_ctu_w, int nb_ctu_h)
+{
+    if (!t || t->nb_cols < 1 || t->nb_cols > 20 || t->nb_rows < 1 || t->nb_rows > 20) return -1;
+    if (t->col_bd[0] != 0 || t->row_bd[0] != 0 || t->col_bd[t->nb_cols] != nb_ctu_w || t->row_bd[t->nb_rows] != nb_ctu_h) return -1;
+    for (int i = 0; i < t->nb_cols; i++) if (t->col_bd[i + 1] <= t->col_bd[i]) return -1;
+    for (int i = 0; i < t->nb_rows; i++) if (t->row_bd[i + 1] <= t->row_bd[i]) return -1;
+    return 0;
+}
+
+int ovgpu_sao_params_set_tiles(OVGPUCtx *ctx, OVGPUSaoParams *p, const OVGPUTileGrid *tiles)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !p) return OVGPU_EINVAL;
+    if (!tiles || tiles->nb_cols * tiles->nb_rows <= 1) { p->has_tiles = 0; return 0; }
+    if (ovgpu_tile_grid_check(tiles, p->nb_ctu_w, p->nb_ctu_h)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "tile grid does not cover the picture's %d x %d CTUs", p->nb_ctu_w, p->nb_ctu_h);
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
+    memcpy(p->h_tiles, tiles, sizeof(TileGridDev));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_tiles, p->h_tiles, sizeof(TileGridDev), cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&p->fence, ctx->stream));
+    p->has_tiles = 1;
+    return 0;
+}
+
 int ovgpu_sao_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUSaoParams *p)
 {
     OVGPU_DEVICE_GUARD(ctx);
@@ -80,6 +110,7 @@ int ovgpu_sao_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src,
     a.pic_w = p->width; a.pic_h = p->height; a.log2_ctu = p->log2_ctu; a.bitdepth = src->bitdepth;
     a.nb_ctu_w = p->nb_ctu_w; a.nb_ctu_h = p->nb_ctu_h;
     a.ctu = p->d_ctu;
+    a.tiles = p->has_tiles ? p->d_tiles : NULL;
     dim3 grid(OVGPU_CEIL_DIV(p->width, SaoK::BX * 8), OVGPU_CEIL_DIV(p->height, SaoK::BY), 3);
     OVGPU_CUDA_CHECK(ctx, ovd_launch<SaoK>(a, grid, 0, ctx->stream));
     return 0;

@@ -15,6 +15,17 @@ struct SaoCtuDev {                // == OVGPUSaoCtu (40 bytes)
     uint8_t pad;
 };
 
+// Tile grid of the picture (rect entries): the reference filters entry by entry and treats an entry's edges like picture borders
+// (rcn_sao.c:211-214, 241-245).  Boundaries in CTUs.  Kernels get a POINTER to it in device memory (NULL: one tile, the lookup is
+// skipped): a run-time index into a by-value kernel argument would move the whole argument block to local memory.
+struct TileGridDev { int nb_cols, nb_rows; uint16_t col_bd[22], row_bd[22]; };
+// first / one-past-last CTU of the tile holding CTU c along one axis
+OVD void tile_span(const uint16_t *bd, int nb, int c, int nb_ctu, int &c0, int &c1)
+{
+    c0 = 0; c1 = nb_ctu;
+    for (int i = 0; i < nb; i++) if (c >= bd[i] && c < bd[i + 1]) { c0 = bd[i]; c1 = bd[i + 1]; }
+}
+
 struct SaoK {
 #ifndef SAO_MIN_BLOCKS
 #define SAO_MIN_BLOCKS 6             /* 40 registers: the kernel waits on memory, not on the issue slots (4: 24.8 us, 6: 22.8 us per 4K picture) */
@@ -28,6 +39,7 @@ struct SaoK {
         int src_pitch[3], dst_pitch[3];    // samples
         int pic_w, pic_h, log2_ctu, bitdepth, nb_ctu_w, nb_ctu_h;
         const SaoCtuDev *ctu;
+        const TileGridDev *tiles;          // device memory, or NULL
     };
     struct State { int dummy; };
 
@@ -53,7 +65,7 @@ struct SaoK {
     // neighbour a = (XA, DYA), b = (-XA, -DYA)
     template <int XA, int DYA>
     OVD void edge(const uint16_t *src, int sp, int x, int y, int w, bool full, const uint32_t *c, uint32_t *o,
-                  uint32_t lut_lo, uint32_t lut_hi, uint32_t maxv2)
+                  uint32_t lut_lo, uint32_t lut_hi, uint32_t maxv2, int x_in_tile, int tile_w)
     {
         const uint16_t *ra = src + (size_t)(y + DYA) * sp, *rb = src + (size_t)(y - DYA) * sp;
         uint32_t wa[4], wb[4];
@@ -92,13 +104,14 @@ struct SaoK {
             const uint32_t idx = ovd_vsub_16x2(0x00020002u, ovd_vadd_16x2(sa, sb));                              // 2 + sign(c - a) + sign(c - b)
             o[i] = ovd_viaddmin_s16x2_relu(c[i], ovd_prmt(lut_lo, lut_hi, sel2(idx)), maxv2);
         }
-        if (XA != 0) {                     // first / last column of the picture keeps its value
-            if (x == 0) o[0] = (o[0] & 0xffff0000u) | (c[0] & 0xffffu);
-            const int il = w - 1 - x;
-            if (il < 8) {
-                const uint32_t m = (il & 1) ? 0xffff0000u : 0x0000ffffu;
+        if (XA != 0) {                     // first / last column of the picture (of the tile) keeps its value
+            const int il = tile_w - 1 - x_in_tile;             // position of the tile's last column among the thread's 8 samples
+            const uint32_t m = (il & 1) ? 0xffff0000u : 0x0000ffffu;
 #pragma unroll
-                for (int i = 0; i < 4; i++) if ((il >> 1) == i) o[i] = (o[i] & ~m) | (c[i] & m);
+            for (int i = 0; i < 4; i++) {                       // (selects on registers: no run-time index into o[] / c[])
+                uint32_t keep = il == 2 * i || il == 2 * i + 1 ? m : 0u;
+                if (i == 0 && x_in_tile == 0) keep |= 0x0000ffffu;
+                o[i] = (o[i] & ~keep) | (c[i] & keep);
             }
         }
     }
@@ -120,6 +133,15 @@ struct SaoK {
         const int type = p->type_idx[c];
         const int maxv = (1 << a.bitdepth) - 1;
 
+        // the tile of the thread's samples (8 samples never straddle a CTU): its edges count as picture borders
+        int tx0 = 0, tx1 = w, ty0 = 0, ty1 = h, tile_rows = a.nb_ctu_h;
+        if (a.tiles) {
+            int c0, c1;
+            tile_span(a.tiles->col_bd, a.tiles->nb_cols, x >> lc, a.nb_ctu_w, c0, c1);
+            tx0 = c0 << lc; tx1 = ovd_min(c1 << lc, w);
+            tile_span(a.tiles->row_bd, a.tiles->nb_rows, y >> lc, a.nb_ctu_h, c0, c1);
+            ty0 = c0 << lc; ty1 = ovd_min(c1 << lc, h); tile_rows = c1 - c0;
+        }
         const bool full = (x + 8 <= w);                       // chroma widths are only multiples of 4
         ovd_u4 v = ld_vec(src + (size_t)y * sp + x, full);
         const uint32_t in[4] = { v.x, v.y, v.z, v.w };
@@ -146,15 +168,15 @@ struct SaoK {
             // (rcn_sao.c:162-177); single-CTU-row quirk of rcn_sao_first_pix_rows (rcn_sao.c:259-272)
             bool row_ok = true;
             if (eo != 0) {
-                if (y == 0 || y == h - 1) row_ok = false;
-                if (a.nb_ctu_h == 1 && y == (6 >> sh) - 1) row_ok = false;
+                if (y == ty0 || y == ty1 - 1) row_ok = false;
+                if (tile_rows == 1 && y == ty0 + (6 >> sh) - 1) row_ok = false;
             }
             if (row_ok) {
-                // one specialised instance per edge class
-                if (eo == 0)      edge<-1, 0>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2);
-                else if (eo == 1) edge<0, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2);
-                else if (eo == 2) edge<-1, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2);
-                else              edge<1, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2);
+                // one specialised instance per edge class; columns relative to the tile: its first / last one keep their samples
+                if (eo == 0)      edge<-1, 0>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2, x - tx0, tx1 - tx0);
+                else if (eo == 1) edge<0, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2, x - tx0, tx1 - tx0);
+                else if (eo == 2) edge<-1, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2, x - tx0, tx1 - tx0);
+                else              edge<1, -1>(src, sp, x, y, w, full, in, o, lut_lo, lut_hi, maxv2, x - tx0, tx1 - tx0);
             }
         }
         ovd_u4 r;

@@ -85,6 +85,13 @@ typedef struct OVOSaoCtu {
     uint8_t pad;
 } OVOSaoCtu;
 
+/* Tiles (rect entries): the reference runs its in-loop filters entry by entry and treats the edges of an entry like picture
+ * borders -- SAO leaves their samples alone for the edge classes that would look across (rcn_sao.c:164-177, 211-214), ALF pads by
+ * replication (rcn_extend_filter_region, rcn_ctu.c:316-510).  Boundaries in CTUs: col_bd[0] = 0 ... col_bd[nb_cols] = picture width in
+ * CTUs, rows likewise.  NULL = one tile. */
+typedef struct OVOTileGrid { int32_t nb_cols, nb_rows; uint16_t col_bd[22], row_bd[22]; } OVOTileGrid;
+void ovo_sao_picture_tiles(uint16_t *const dst[3], const int dst_stride[3], const uint16_t *const src[3], const int src_stride[3],
+                           int pic_w, int pic_h, int log2_ctu_s, int bitdepth, const OVOSaoCtu *ctu, const OVOTileGrid *tiles);
 void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                      const uint16_t *const src[3], const int src_stride[3],
                      int pic_w, int pic_h, int log2_ctu_s, int bitdepth,

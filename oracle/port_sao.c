@@ -16,6 +16,21 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                      int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                      const OVOSaoCtu *ctu)
 {
+    ovo_sao_picture_tiles(dst, dst_stride, src, src_stride, pic_w, pic_h, log2_ctu_s, bitdepth, ctu, NULL);
+}
+
+/* first / one-past-last CTU of the tile that holds CTU `c` along one axis */
+static void tile_span(const uint16_t *bd, int nb, int c, int nb_ctu, int *c0, int *c1)
+{
+    *c0 = 0; *c1 = nb_ctu;
+    for (int i = 0; bd && i < nb; i++) if (c >= bd[i] && c < bd[i + 1]) { *c0 = bd[i]; *c1 = bd[i + 1]; }
+}
+
+void ovo_sao_picture_tiles(uint16_t *const dst[3], const int dst_stride[3],
+                           const uint16_t *const src[3], const int src_stride[3],
+                           int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                           const OVOSaoCtu *ctu, const OVOTileGrid *tiles)
+{
     /* neighbour offsets per eo_class: horizontal, vertical, 45, 135 (rcn_sao.c:86-91) */
     static const int8_t pos[4][2][2] = {
         { { -1, 0 }, { 1, 0 } }, { { 0, -1 }, { 0, 1 } }, { { -1, -1 }, { 1, 1 } }, { { 1, -1 }, { -1, 1 } } };
@@ -40,6 +55,11 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                 int x0 = cx * cs, y0 = cy * cs;
                 int x1 = x0 + cs < w ? x0 + cs : w;
                 int y1 = y0 + cs < h ? y0 + cs : h;
+                /* the rect entry (tile) of this CTU: its edges are borders (rcn_sao.c:211-214, 241-245) */
+                int tcx0, tcx1, tcy0, tcy1;
+                tile_span(tiles ? tiles->col_bd : NULL, tiles ? tiles->nb_cols : 0, cx, nb_w, &tcx0, &tcx1);
+                tile_span(tiles ? tiles->row_bd : NULL, tiles ? tiles->nb_rows : 0, cy, nb_h, &tcy0, &tcy1);
+                const int tx0 = tcx0 * cs, tx1 = tcx1 * cs < w ? tcx1 * cs : w, ty0 = tcy0 * cs, ty1 = tcy1 * cs < h ? tcy1 * cs : h;
 
                 if (p->type_idx[c] == 1) {            /* band, rcn_sao.c:46-76 */
                     int table[32] = { 0 };
@@ -53,12 +73,12 @@ void ovo_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
                 } else if (p->type_idx[c] == 2) {     /* edge, rcn_sao.c:79-117 + border rules :162-177 */
                     int eo = p->eo_class[c];
                     int xs = x0, xe = x1, ys = y0, ye = y1;
-                    if (eo != 1) { if (xs == 0) xs = 1; if (xe == w) xe = w - 1; }
-                    if (eo != 0) { if (ys == 0) ys = 1; if (ye == h) ye = h - 1; }
+                    if (eo != 1) { if (xs == tx0) xs = tx0 + 1; if (xe == tx1) xe = tx1 - 1; }
+                    if (eo != 0) { if (ys == ty0) ys = ty0 + 1; if (ye == ty1) ye = ty1 - 1; }
                     for (int y = ys; y < ye; y++) {
-                        /* reference quirk: with a single CTU row, rcn_sao_first_pix_rows (rcn_sao.c:259-272)
+                        /* reference quirk: in an entry of a single CTU row, rcn_sao_first_pix_rows (rcn_sao.c:259-272)
                          * carries the BOTTOM border flag, so the last of its 6 (3 chroma) rows is dropped */
-                        if (nb_h == 1 && eo != 0 && y == (6 >> sh) - 1) continue;
+                        if (tcy1 - tcy0 == 1 && eo != 0 && y == ty0 + (6 >> sh) - 1) continue;
                         for (int x = xs; x < xe; x++) {
                             int v = s[(size_t)y * ss + x];
                             int a = s[(size_t)(y + pos[eo][0][1]) * ss + x + pos[eo][0][0]];

@@ -149,18 +149,39 @@ def alf_classify(luma, log2_ctu=7, bitdepth=10):
     return cls
 
 
-def sao_picture(planes, sao_ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1):
+class TileGrid(C.Structure):
+    """OVOTileGrid / OVGPUTileGrid: tile boundaries in CTUs (col_bd[0] = 0 ... col_bd[nb_cols] = picture width in CTUs)"""
+    _fields_ = [("nb_cols", C.c_int32), ("nb_rows", C.c_int32), ("col_bd", C.c_uint16 * 22), ("row_bd", C.c_uint16 * 22)]
+
+
+def make_tile_grid(col_bd, row_bd):
+    tg = TileGrid()
+    tg.nb_cols, tg.nb_rows = len(col_bd) - 1, len(row_bd) - 1
+    tg.col_bd[:len(col_bd)] = [int(v) for v in col_bd]
+    tg.row_bd[:len(row_bd)] = [int(v) for v in row_bd]
+    return tg
+
+
+def sao_picture(planes, sao_ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1, tiles=None):
+    """tiles: TileGrid or None (one tile).  The reference is driven one rect entry per tile."""
     h, w = planes[0].shape
     sao_ctu = np.ascontiguousarray(sao_ctu, dtype=SaoCtu)
     if impl == "port":
         out = [np.empty_like(pl) for pl in planes]
         src, ss = _planes_arg(planes)
         dst, ds = _planes_arg(out)
-        port().ovo_sao_picture(dst, ds, src, ss, w, h, log2_ctu, bitdepth, sao_ctu.ctypes.data_as(C.c_void_p))
+        f = port().ovo_sao_picture_tiles
+        f.restype = None
+        f(dst, ds, src, ss, w, h, log2_ctu, bitdepth, sao_ctu.ctypes.data_as(C.c_void_p), C.byref(tiles) if tiles is not None else None)
         return out
     out = [pl.copy() for pl in planes]
     dst, ds = _planes_arg(out)
-    ref().ovref_sao_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, sao_ctu.ctypes.data_as(C.c_void_p))
+    if tiles is not None:
+        f = ref().ovref_sao_picture_tiles
+        f.restype = None
+        f(dst, ds, w, h, log2_ctu, bitdepth, simd, sao_ctu.ctypes.data_as(C.c_void_p), C.byref(tiles))
+    else:
+        ref().ovref_sao_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, sao_ctu.ctypes.data_as(C.c_void_p))
     return out
 
 

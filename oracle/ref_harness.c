@@ -520,3 +520,50 @@ ovref_fg_apply(uint16_t *const dst[3], const uint16_t *const src[3], int w, int 
     int16_t *d[3] = { (int16_t *)dst[0], (int16_t *)dst[1], (int16_t *)dst[2] }, *s_[3] = { (int16_t *)src[0], (int16_t *)src[1], (int16_t *)src[2] };
     fg_grain_apply_pic(d, s_, &sei, w, h, poc, 0, 1);
 }
+
+/* SAO of a picture cut into tiles: one rect entry per tile, each driven like a picture of its own (slicedec.c runs entries this
+ * way, one OVCTUDec per entry job; parameters are indexed relative to the entry, rcn_sao.c:217) */
+void
+ovref_sao_picture_tiles(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h,
+                        int log2_ctu_s, int bitdepth, int simd, const OVOSaoCtu *p, const OVOTileGrid *tg)
+{
+    int ctu_s = 1 << log2_ctu_s;
+    int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s;
+    for (int tr = 0; tr < tg->nb_rows; tr++)
+        for (int tc = 0; tc < tg->nb_cols; tc++) {
+            HarnessCtx *h = harness_open(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd);
+            OVCTUDec *c = h->ctudec;
+            struct RectEntryInfo e;
+            memset(&e, 0, sizeof(e));
+            e.ctb_x = tg->col_bd[tc]; e.ctb_y = tg->row_bd[tr];
+            e.nb_ctu_w = tg->col_bd[tc + 1] - tg->col_bd[tc]; e.nb_ctu_h = tg->row_bd[tr + 1] - tg->row_bd[tr];
+            e.nb_ctu_rect = e.nb_ctu_w * e.nb_ctu_h;
+            e.nb_ctb_pic_w = nb_w;
+            SAOParamsCtu *params = calloc(e.nb_ctu_rect, sizeof(*params));
+            for (int y = 0; y < e.nb_ctu_h; y++)
+                for (int x = 0; x < e.nb_ctu_w; x++) {
+                    const OVOSaoCtu *q = &p[(e.ctb_y + y) * nb_w + e.ctb_x + x];
+                    SAOParamsCtu *d = &params[y * e.nb_ctu_w + x];
+                    for (int k = 0; k < 3; k++) {
+                        memcpy(d->offset_val[k], q->offset_val[k], sizeof(d->offset_val[k]));
+                        d->band_position[k] = q->band_position[k]; d->eo_class[k] = q->eo_class[k]; d->type_idx[k] = q->type_idx[k];
+                    }
+                }
+            c->sao_info.sao_luma_flag = 1; c->sao_info.sao_chroma_flag = 1; c->sao_info.chroma_format_idc = 1;
+            c->sao_info.sao_params = params;
+            const struct SAOFunctions *sao = &c->rcn_funcs.sao;
+            for (int row = 0; row < e.nb_ctu_h; row++) {
+                if (row == 0) {
+                    sao->rcn_sao_first_pix_rows(c, &e, 0);
+                    if (e.nb_ctu_h == 1) sao->rcn_sao_filter_line(c, &e, 0);
+                } else if (row == e.nb_ctu_h - 1) {
+                    sao->rcn_sao_filter_line(c, &e, row - 1);
+                    sao->rcn_sao_filter_line(c, &e, row);
+                } else {
+                    sao->rcn_sao_filter_line(c, &e, row - 1);
+                }
+            }
+            harness_close(h);
+            free(params);
+        }
+}

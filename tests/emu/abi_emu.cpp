@@ -72,6 +72,10 @@ int ovgpu_film_grain_picture(OVGPUCtx *c, OVGPUFilmGrainSynth *, OVGPUPicture *d
     return 0;
 }
 
+int ovgpu_tile_grid_check(const OVGPUTileGrid *, int, int) { return 0; }
+int ovgpu_sao_params_set_tiles(OVGPUCtx *c, OVGPUSaoParams *, const OVGPUTileGrid *t)
+{ return t && t->nb_cols * t->nb_rows > 1 ? fail(c, OVGPU_EINVAL, "tiles are not part of the ABI emulation") : 0; }
+
 int ovgpu_mc_batch_create(OVGPUCtx *, int max_cmds, int, OVGPUMcBatch **b) { *b = new OVGPUMcBatch(); (*b)->cmds.resize(max_cmds + 1); (*b)->prof.resize(65536); (*b)->nb = (*b)->nb_prof = (*b)->nb_dmvr = 0; return ovgpu_mc_batch_set_scaling(NULL, *b, NULL); }
 int ovgpu_mc_batch_set_scaling(OVGPUCtx *, OVGPUMcBatch *b, const OVGPUMcScaling *s)
 {

@@ -102,9 +102,9 @@ int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
     return wide;
 }
 
-int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
-                    const uint16_t *const src[3], const int src_stride[3],
-                    int w, int h, int log2_ctu, int bitdepth, const OVGPUSaoCtu *ctu)
+int emu_sao_picture_tiles(uint16_t *const dst[3], const int dst_stride[3],
+                          const uint16_t *const src[3], const int src_stride[3],
+                          int w, int h, int log2_ctu, int bitdepth, const OVGPUSaoCtu *ctu, const OVGPUTileGrid *tiles)
 {
     SaoK::Args a;
     int ctu_s = 1 << log2_ctu;
@@ -114,8 +114,16 @@ int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
     a.pic_w = w; a.pic_h = h; a.log2_ctu = log2_ctu; a.bitdepth = bitdepth;
     a.nb_ctu_w = (w + ctu_s - 1) >> log2_ctu; a.nb_ctu_h = (h + ctu_s - 1) >> log2_ctu;
     a.ctu = (const SaoCtuDev *)ctu;
+    a.tiles = tiles && tiles->nb_cols * tiles->nb_rows > 1 ? (const TileGridDev *)tiles : NULL;
     ovd_emulate<SaoK>(a, ovd_dim3((w + SaoK::BX * 8 - 1) / (SaoK::BX * 8), (h + SaoK::BY - 1) / SaoK::BY, 3), 0);
     return 0;
+}
+
+int emu_sao_picture(uint16_t *const dst[3], const int dst_stride[3],
+                    const uint16_t *const src[3], const int src_stride[3],
+                    int w, int h, int log2_ctu, int bitdepth, const OVGPUSaoCtu *ctu)
+{
+    return emu_sao_picture_tiles(dst, dst_stride, src, src_stride, w, h, log2_ctu, bitdepth, ctu, NULL);
 }
 
 // output stage: up-scaling (UpscaleK); win = left, right, top, bottom (chroma units), hor_col, ver_col

@@ -159,3 +159,62 @@ def test_output_stage_in_the_dropin_gpu(stream_dir, name, extra, what):
     assert os.path.exists(binary), "build/dectest missing: run python __graft_entry__.py where /root/reference exists"
     for threads in (1, 4):
         _check_output_stage(stream_dir, binary, name, extra, what, threads)
+
+
+# ---- tile edges as filter borders: SAO --------------------------------------------------------------------
+# (w, h, log2_ctu, tile column boundaries, tile row boundaries in CTUs, seed); the third grid has tiles of a single CTU row
+TILE_CASES = [(416, 240, 6, [0, 3, 7], [0, 2, 4], 1), (832, 480, 7, [0, 2, 5, 7], [0, 1, 4], 2), (416, 240, 5, [0, 5, 13], [0, 1, 2, 8], 3),
+              (1920, 1080, 7, [0, 4, 9, 15], [0, 3, 9], 4)]
+
+
+@pytest.mark.parametrize("w,h,log2,cols,rows,seed", TILE_CASES)
+def test_sao_tile_edges_port_vs_compiled_reference_and_emulated_kernel(po, emu, w, h, log2, cols, rows, seed):
+    """the reference driven one rect entry per tile (rcn_sao_first_pix_rows / rcn_sao_filter_line) == the oracle with a tile grid ==
+    SaoK's source with the grid; and the grid matters (the result differs from the one-tile picture)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    planes, sao = helpers.sao_case(po, w, h, seed, log2)
+    tg = po.make_tile_grid(cols, rows)
+    want = po.sao_picture(planes, sao, log2, impl="port", tiles=tg)
+    assert any(not np.array_equal(a, b) for a, b in zip(want, po.sao_picture(planes, sao, log2, impl="port")))
+    if po.ref_available():
+        for simd in (0, 1):
+            got = po.sao_picture(planes, sao, log2, impl="ref", simd=simd, tiles=tg)
+            if simd == 0 or log2 == 7:            # (the SIMD chroma SAO differs from the C code on non-CTC geometries, DESIGN.md section 2)
+                for a, b in zip(want, got):
+                    assert np.array_equal(a, b), "simd=%d" % simd
+    out = [np.zeros_like(p) for p in planes]
+    dst, ds = po._planes_arg(out)
+    src, ss = po._planes_arg(planes)
+    emu.emu_sao_picture_tiles(dst, ds, src, ss, w, h, log2, 10, C.c_void_p(sao.ctypes.data), C.byref(tg))
+    for a, b in zip(want, out):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,cols,rows,seed", TILE_CASES)
+def test_gpu_sao_tile_edges(po, w, h, log2, cols, rows, seed):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from openvvc_b200 import api
+    ctx = api.Ctx(0)
+    try:
+        planes, sao = helpers.sao_case(po, w, h, seed, log2)
+        want = po.sao_picture(planes, sao, log2, impl="port", tiles=po.make_tile_grid(cols, rows))
+        src = ctx.picture(w, h); src.upload(planes)
+        dst = ctx.picture(w, h)
+        prm = api.SaoParams(ctx, w, h, log2)
+        prm.upload(sao.astype(api.SAO_CTU))
+        prm.set_tiles(cols, rows)
+        prm.run(dst, src)
+        for a, b in zip(want, dst.download()):
+            assert np.array_equal(a, b)
+        with pytest.raises(api.OVGPUError):           # a grid that does not end at the picture's last CTU
+            prm.set_tiles(cols[:-1] + [cols[-1] + 1], rows)
+        prm.set_tiles(None)                           # back to one tile
+        prm.run(dst, src)
+        for a, b in zip(po.sao_picture(planes, sao, log2, impl="port"), dst.download()):
+            assert np.array_equal(a, b)
+        prm.destroy(); src.destroy(); dst.destroy()
+    finally:
+        ctx.close()
