@@ -176,6 +176,11 @@ int  ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTab
                              const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
                              int cc_cb_enabled, int cc_cr_enabled);
 /* dst = ALF(src): src is the post-SAO picture; dst must be a different picture. Asynchronous. */
+/* tile (rect entry) edges padded like picture borders (the is_border flags of rcn_alf_filter_line -> rcn_extend_filter_region,
+ * rcn_alf.c:1311-1330, rcn_ctu.c:316-510): classification, luma / chroma filters and CC-ALF fetch their samples clamped to the
+ * CTU's tile; OVGPUTileGrid is declared with the SAO entry points below */
+struct OVGPUTileGrid;
+int  ovgpu_alf_params_set_tiles(OVGPUCtx *ctx, OVGPUAlfParams *p, const struct OVGPUTileGrid *tiles);
 int  ovgpu_alf_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUAlfParams *p);
 /* Whole call with HOST buffers: H2D of planes + params, ALF, D2H into dst planes, then stream sync. */
 int  ovgpu_alf_frame_host(OVGPUCtx *ctx, void *const dst_data[3], const size_t dst_linesize[3],

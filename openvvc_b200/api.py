@@ -221,6 +221,16 @@ class AlfParams:
         _check((ctx or self.ctx).h, lib().ovgpu_alf_params_upload((ctx or self.ctx).h, self.p, C.byref(tables), vp(ctu.ctypes.data), cc,
                                                          int(cc_en[0]), int(cc_en[1])), "alf_params_upload")
 
+    def set_tiles(self, col_bd=None, row_bd=None, ctx=None):
+        """ovgpu_alf_params_set_tiles: tile boundaries in CTUs (None: one tile)"""
+        tg = None
+        if col_bd is not None:
+            tg = TileGrid()
+            tg.nb_cols, tg.nb_rows = len(col_bd) - 1, len(row_bd) - 1
+            tg.col_bd[:len(col_bd)] = [int(v) for v in col_bd]
+            tg.row_bd[:len(row_bd)] = [int(v) for v in row_bd]
+        _check((ctx or self.ctx).h, lib().ovgpu_alf_params_set_tiles((ctx or self.ctx).h, self.p, C.byref(tg) if tg is not None else None), "alf_params_set_tiles")
+
     def run(self, dst, src, ctx=None):
         _check((ctx or self.ctx).h, lib().ovgpu_alf_picture((ctx or self.ctx).h, dst.p, src.p, self.p), "alf_picture")
 

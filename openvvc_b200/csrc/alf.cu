@@ -17,6 +17,8 @@ struct OVGPUAlfParams {
     AlfCtuDev *d_ctu;
     AlfChromaTab chroma;
     int wide, cc_enabled[2];
+    TileGridDev *h_tiles, *d_tiles;      // ovgpu_alf_params_set_tiles
+    int has_tiles;
     int device;
     StagingFence fence;
 };
@@ -140,6 +142,7 @@ int ovgpu_alf_params_create(OVGPUCtx *ctx, int width, int height, int log2_ctu_s
     if (cudaMallocHost(&p->h_tab, tab_bytes) != cudaSuccess ||
         cudaMallocHost(&p->h_ctu, sizeof(AlfCtuDev) * p->nb_ctu) != cudaSuccess ||
         cudaMalloc(&p->d_tab, tab_bytes) != cudaSuccess ||
+        cudaMallocHost(&p->h_tiles, sizeof(TileGridDev)) != cudaSuccess || cudaMalloc(&p->d_tiles, sizeof(TileGridDev)) != cudaSuccess ||
         cudaMalloc(&p->d_ctu, sizeof(AlfCtuDev) * p->nb_ctu) != cudaSuccess) {
         ovgpu_alf_params_destroy(p);
         return ovgpu_set_error(ctx, OVGPU_ENOMEM, "ALF parameter buffers: %s", cudaGetErrorString(cudaGetLastError()));
@@ -156,8 +159,24 @@ void ovgpu_alf_params_destroy(OVGPUAlfParams *p)
     if (p->h_ctu) cudaFreeHost(p->h_ctu);
     if (p->d_tab) cudaFree(p->d_tab);
     if (p->d_ctu) cudaFree(p->d_ctu);
+    if (p->h_tiles) cudaFreeHost(p->h_tiles);
+    if (p->d_tiles) cudaFree(p->d_tiles);
     fence_destroy(&p->fence);
     free(p);
+}
+
+int ovgpu_alf_params_set_tiles(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUTileGrid *tiles)
+{
+    OVGPU_DEVICE_GUARD(ctx);
+    if (!ctx || !p) return OVGPU_EINVAL;
+    if (!tiles || tiles->nb_cols * tiles->nb_rows <= 1) { p->has_tiles = 0; return 0; }
+    if (ovgpu_tile_grid_check(tiles, p->g.nb_ctu_w, p->g.nb_ctu_h)) return ovgpu_set_error(ctx, OVGPU_EINVAL, "tile grid does not cover the picture's %d x %d CTUs", p->g.nb_ctu_w, p->g.nb_ctu_h);
+    OVGPU_CUDA_CHECK(ctx, fence_wait(&p->fence));
+    memcpy(p->h_tiles, tiles, sizeof(TileGridDev));
+    OVGPU_CUDA_CHECK(ctx, cudaMemcpyAsync(p->d_tiles, p->h_tiles, sizeof(TileGridDev), cudaMemcpyHostToDevice, ctx->stream));
+    OVGPU_CUDA_CHECK(ctx, fence_mark(&p->fence, ctx->stream));
+    p->has_tiles = 1;
+    return 0;
 }
 
 int ovgpu_alf_params_upload(OVGPUCtx *ctx, OVGPUAlfParams *p, const OVGPUAlfTables *tab,
@@ -196,12 +215,12 @@ int ovgpu_alf_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src,
         if (p->wide) {
             typedef AlfLumaK<true> K;
             K::Args a = { sl.p, dl.p, sl.pitch, dl.pitch, p->width, p->height, p->log2_ctu, src->bitdepth,
-                          g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, p->d_tab, p->d_ctu };
+                          g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, p->d_tab, p->d_ctu, p->has_tiles ? p->d_tiles : NULL };
             OVGPU_CUDA_CHECK(ctx, ovd_launch<K>(a, grid, K::SMEM_BYTES, ctx->stream));
         } else {
             typedef AlfLumaK<false> K;
             K::Args a = { sl.p, dl.p, sl.pitch, dl.pitch, p->width, p->height, p->log2_ctu, src->bitdepth,
-                          g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, p->d_tab, p->d_ctu };
+                          g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, p->d_tab, p->d_ctu, p->has_tiles ? p->d_tiles : NULL };
             OVGPU_CUDA_CHECK(ctx, ovd_launch<K>(a, grid, K::SMEM_BYTES, ctx->stream));
         }
     }
@@ -220,6 +239,7 @@ int ovgpu_alf_picture(OVGPUCtx *ctx, OVGPUPicture *dst, const OVGPUPicture *src,
         a.cc_enabled[0] = p->cc_enabled[0]; a.cc_enabled[1] = p->cc_enabled[1];
         a.ctu = p->d_ctu;
         a.tab = p->chroma;
+        a.tiles = p->has_tiles ? p->d_tiles : NULL;
         dim3 grid(g.nb_ctu_w * g.c_tx, g.nb_ctu_h * g.c_ty, 2);
         OVGPU_CUDA_CHECK(ctx, ovd_launch<K>(a, grid, K::SMEM_BYTES, ctx->stream));
     }

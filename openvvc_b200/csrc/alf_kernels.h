@@ -10,6 +10,7 @@
 // differences of two horizontally adjacent samples per instruction and IDP.2A does the two multiply-adds.
 #pragma once
 #include "dev.h"
+#include "tile_grid.h"
 
 // ---- device-side parameter formats -----------------------------------------------------------------------
 #define ALF_TAB_ENTRY_WORDS 24          // per (transpose, class): 12 coef operands, 12 clips (the kernel negates the clip itself)
@@ -55,11 +56,13 @@ struct AlfLumaK {
         int tiles_x_per_ctu, tiles_y_per_ctu, nb_ctu_w;
         const uint32_t *tab;             // [24][100][24]
         const AlfCtuDev *ctu;
+        const TileGridDev *tiles;        // device memory, or NULL (one tile): tile edges are padded like picture borders
     };
     struct State { int active; };
 
     struct Tile {
         int x0, y0, tw, th, ctu_y0, ctu_h, vb, enabled, set;
+        int bx0, bx1, by0, by1;          // the rectangle samples are fetched from: the CTU's tile (the picture without tiles)
     };
 
     OVD Tile tile_of(const Args &a, int bx, int by)
@@ -78,10 +81,18 @@ struct AlfLumaK {
         // virtual boundary, CTU relative (rcn_alf.c:724 and :1353)
         t.vb = (t.ctu_h < ctu_s) ? a.pic_h : t.ctu_h - 4;
         t.enabled = 0; t.set = 0;
+        t.bx0 = 0; t.bx1 = a.pic_w; t.by0 = 0; t.by1 = a.pic_h;
         if (t.tw > 0 && t.th > 0) {
             AlfCtuDev c = a.ctu[cy * a.nb_ctu_w + cx];
             t.enabled = (c.flag >> 2) & 1;
             t.set = c.idx;
+            if (a.tiles) {
+                int c0, c1;
+                tile_span(a.tiles->col_bd, a.tiles->nb_cols, cx, a.nb_ctu_w, c0, c1);
+                t.bx0 = c0 << a.log2_ctu; t.bx1 = ovd_min(c1 << a.log2_ctu, a.pic_w);
+                tile_span(a.tiles->row_bd, a.tiles->nb_rows, cy, (a.pic_h + ctu_s - 1) >> a.log2_ctu, c0, c1);
+                t.by0 = c0 << a.log2_ctu; t.by1 = ovd_min(c1 << a.log2_ctu, a.pic_h);
+            }
         }
         return t;
     }
@@ -127,12 +138,12 @@ struct AlfLumaK {
         const int nrows = t.th + 6;
         // tiles away from the picture's left / right border: the rows go to shared memory as 16-byte asynchronous copies (LDGSTS),
         // one lane per chunk and one warp per row -- no register staging, no per-chunk border tests (rows are clamped per row)
-        const bool fast = t.x0 >= HALO_L && t.x0 + t.tw + 8 <= a.pic_w && !(t.tw & 7) && !(a.src_pitch & 7);
+        const bool fast = t.x0 >= t.bx0 + HALO_L && t.x0 + t.tw + 8 <= t.bx1 && !(t.tw & 7) && !(a.src_pitch & 7);
         if (fast) {
             const int cpr = (t.tw + 16) >> 3, lane = tid & 31;        // <= 18 chunks per row
             if (lane < cpr)
                 for (int r = tid >> 5; r < nrows; r += THREADS / 32) {
-                    const int y = ovd_clamp(t.y0 - 3 + r, 0, a.pic_h - 1);
+                    const int y = ovd_clamp(t.y0 - 3 + r, t.by0, t.by1 - 1);
                     ovd_cp_async16(pix + r * PIX_STRIDE + 8 * lane, a.src + (size_t)y * a.src_pitch + t.x0 - HALO_L + 8 * lane);
                 }
         }
@@ -141,11 +152,11 @@ struct AlfLumaK {
         if (!fast && ch < nchunks) {
             int x = t.x0 - HALO_L + 4 * ch;
             for (int r = tid >> 6; r < nrows; r += 4) {
-                int y = ovd_clamp(t.y0 - 3 + r, 0, a.pic_h - 1);
+                int y = ovd_clamp(t.y0 - 3 + r, t.by0, t.by1 - 1);
                 const uint16_t *row = a.src + (size_t)y * a.src_pitch;
                 ovd_u2 v;
-                if (x < 0)              { uint32_t e = row[0];           v.x = v.y = e * 0x10001u; }
-                else if (x >= a.pic_w)  { uint32_t e = row[a.pic_w - 1]; v.x = v.y = e * 0x10001u; }
+                if (x < t.bx0)          { uint32_t e = row[t.bx0];     v.x = v.y = e * 0x10001u; }
+                else if (x >= t.bx1)    { uint32_t e = row[t.bx1 - 1]; v.x = v.y = e * 0x10001u; }
                 else v = ovd_ld8(row + x);
                 *(ovd_u2 *)(pix + r * PIX_STRIDE + 4 * ch) = v;
             }
@@ -367,10 +378,12 @@ struct AlfChromaK {
         int cc_enabled[2];
         const AlfCtuDev *ctu;
         AlfChromaTab tab;
+        const TileGridDev *tiles;        // device memory, or NULL (one tile)
     };
     struct State { int dummy; };
 
-    struct Tile { int x0, y0, tw, th, partial_v, do_alf, alt, cc_idx; };
+    // bx0 .. by1: the rectangle samples are fetched from, in CHROMA samples (luma: twice that): the CTU's tile, or the picture
+    struct Tile { int x0, y0, tw, th, partial_v, do_alf, alt, cc_idx, bx0, bx1, by0, by1; };
 
     OVD Tile tile_of(const Args &a, int bx, int by, int comp)
     {
@@ -386,6 +399,14 @@ struct AlfChromaK {
         t.th = ovd_min(a.th, cy * ctu_c + ctu_h - t.y0);
         t.partial_v = ((cy + 1) << a.log2_ctu) > a.pic_h;
         t.do_alf = 0; t.alt = 0; t.cc_idx = 0;
+        t.bx0 = 0; t.bx1 = w; t.by0 = 0; t.by1 = h;
+        if (t.tw > 0 && t.th > 0 && a.tiles) {
+            int c0, c1;
+            tile_span(a.tiles->col_bd, a.tiles->nb_cols, cx, a.nb_ctu_w, c0, c1);
+            t.bx0 = c0 * ctu_c; t.bx1 = ovd_min(c1 * ctu_c, w);
+            tile_span(a.tiles->row_bd, a.tiles->nb_rows, cy, (h + ctu_c - 1) / ctu_c, c0, c1);
+            t.by0 = c0 * ctu_c; t.by1 = ovd_min(c1 * ctu_c, h);
+        }
         if (t.tw > 0 && t.th > 0) {
             AlfCtuDev c = a.ctu[cy * a.nb_ctu_w + cx];
             t.do_alf = comp == 0 ? (c.flag >> 1) & 1 : c.flag & 1;
@@ -404,17 +425,18 @@ struct AlfChromaK {
         if (t.tw <= 0 || t.th <= 0) return;
         uint16_t *pix = (uint16_t *)smem;
         const int w = a.pic_w >> 1, h = a.pic_h >> 1;
+        (void)w; (void)h;
         const uint16_t *src = a.src[comp];
         if (P == 0) {
             // stage tile + halo 2 (8 horizontally for alignment): tiles away from the left / right border as 16-byte asynchronous
             // copies (LDGSTS), one lane per chunk and one warp per row; border tiles through the clamped 8-byte path
             const int nrows = t.th + 4, nchunks = (t.tw + 16) >> 2;   // <= 20
-            const bool fast = t.x0 >= HALO_L && t.x0 + t.tw + 8 <= w && !(t.tw & 7) && !(a.src_pitch & 7);
+            const bool fast = t.x0 >= t.bx0 + HALO_L && t.x0 + t.tw + 8 <= t.bx1 && !(t.tw & 7) && !(a.src_pitch & 7);
             const int ch = tid & 31;
             if (fast) {
                 if (ch < ((t.tw + 16) >> 3))
                     for (int r = tid >> 5; r < nrows; r += 8) {
-                        const int y = ovd_clamp(t.y0 - 2 + r, 0, h - 1);
+                        const int y = ovd_clamp(t.y0 - 2 + r, t.by0, t.by1 - 1);
                         ovd_cp_async16(pix + r * PIX_STRIDE + 8 * ch, src + (size_t)y * a.src_pitch + t.x0 - HALO_L + 8 * ch);
                     }
                 ovd_cp_async_wait_all();
@@ -423,11 +445,11 @@ struct AlfChromaK {
             if (ch < nchunks) {
                 int x = t.x0 - HALO_L + 4 * ch;
                 for (int r = tid >> 5; r < nrows; r += 8) {
-                    int y = ovd_clamp(t.y0 - 2 + r, 0, h - 1);
+                    int y = ovd_clamp(t.y0 - 2 + r, t.by0, t.by1 - 1);
                     const uint16_t *row = src + (size_t)y * a.src_pitch;
                     ovd_u2 v;
-                    if (x < 0)        { uint32_t e = row[0];     v.x = v.y = e * 0x10001u; }
-                    else if (x >= w)  { uint32_t e = row[w - 1]; v.x = v.y = e * 0x10001u; }
+                    if (x < t.bx0)        { uint32_t e = row[t.bx0];     v.x = v.y = e * 0x10001u; }
+                    else if (x >= t.bx1)  { uint32_t e = row[t.bx1 - 1]; v.x = v.y = e * 0x10001u; }
                     else v = ovd_ld8(row + x);
                     *(ovd_u2 *)(pix + r * PIX_STRIDE + 4 * ch) = v;
                 }
@@ -471,9 +493,11 @@ struct AlfChromaK {
             else if (pos == vb_cc - 1 || pos == vb_cc) o1 = o2 = o3 = 0;
             const int ly2 = y << 1;
             const uint16_t *l0 = a.luma + (size_t)ly2 * a.luma_pitch;
-            const uint16_t *l1 = a.luma + (size_t)ovd_clamp(ly2 + o1, 0, a.pic_h - 1) * a.luma_pitch;
-            const uint16_t *l2 = a.luma + (size_t)ovd_clamp(ly2 + o2, 0, a.pic_h - 1) * a.luma_pitch;
-            const uint16_t *l3 = a.luma + (size_t)ovd_clamp(ly2 + o3, 0, a.pic_h - 1) * a.luma_pitch;
+            // (luma rows / columns of CC-ALF are clamped to the luma rectangle of the tile, like the padded filter region)
+            const int ly_lo = 2 * t.by0, ly_hi = ovd_min(2 * t.by1, a.pic_h) - 1, lx_lo = 2 * t.bx0, lx_hi = ovd_min(2 * t.bx1, a.pic_w) - 1;
+            const uint16_t *l1 = a.luma + (size_t)ovd_clamp(ly2 + o1, ly_lo, ly_hi) * a.luma_pitch;
+            const uint16_t *l2 = a.luma + (size_t)ovd_clamp(ly2 + o2, ly_lo, ly_hi) * a.luma_pitch;
+            const uint16_t *l3 = a.luma + (size_t)ovd_clamp(ly2 + o3, ly_lo, ly_hi) * a.luma_pitch;
             uint32_t outv[4];
             int alfv[4] = { c0[0], c0[1], c0[2], c0[3] };
             if (t.do_alf && !wide) {
@@ -515,7 +539,7 @@ struct AlfChromaK {
                 // CC-ALF (rcn_alf.c:826-870) for the four chroma samples at once: their eight luma columns come in as four 8-byte
                 // loads per row (+ the column to the left), the seven differences to the collocated luma sample are formed on
                 // packed pairs (even / odd luma columns picked with PRMT) and accumulated with IDP.2A
-                const int lx0 = (t.x0 + 4 * tx) << 1, lxm = ovd_max(lx0 - 1, 0);
+                const int lx0 = (t.x0 + 4 * tx) << 1, lxm = ovd_max(lx0 - 1, lx_lo);
                 const ovd_u2 r0a = ovd_ld8(l0 + lx0), r0b = ovd_ld8(l0 + lx0 + 4), r1a = ovd_ld8(l1 + lx0), r1b = ovd_ld8(l1 + lx0 + 4);
                 const ovd_u2 r2a = ovd_ld8(l2 + lx0), r2b = ovd_ld8(l2 + lx0 + 4), r3a = ovd_ld8(l3 + lx0), r3b = ovd_ld8(l3 + lx0 + 4);
                 const uint32_t w0[5] = { (uint32_t)l0[lxm] << 16, r0a.x, r0a.y, r0b.x, r0b.y };
@@ -562,7 +586,7 @@ struct AlfChromaK {
                     int sum = ccv[i];
                     if (cc_wide) {
                         const int lx = (t.x0 + 4 * tx + i) << 1;
-                        const int lxm = ovd_max(lx - 1, 0), lxp = ovd_min(lx + 1, a.pic_w - 1);
+                        const int lxm = ovd_max(lx - 1, lx_lo), lxp = ovd_min(lx + 1, lx_hi);
                         const int lc = l0[lx];
                         sum = cc[0] * (l2[lx] - lc) + cc[1] * (l0[lxm] - lc) + cc[2] * (l0[lxp] - lc)
                             + cc[3] * (l1[lxm] - lc) + cc[4] * (l1[lx] - lc) + cc[5] * (l1[lxp] - lc)

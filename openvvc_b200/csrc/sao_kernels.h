@@ -6,6 +6,7 @@
 // (the reference needs its padded filter-region copy for that).
 #pragma once
 #include "dev.h"
+#include "tile_grid.h"
 
 struct SaoCtuDev {                // == OVGPUSaoCtu (40 bytes)
     int16_t offset_val[3][5];
@@ -14,17 +15,6 @@ struct SaoCtuDev {                // == OVGPUSaoCtu (40 bytes)
     uint8_t type_idx[3];
     uint8_t pad;
 };
-
-// Tile grid of the picture (rect entries): the reference filters entry by entry and treats an entry's edges like picture borders
-// (rcn_sao.c:211-214, 241-245).  Boundaries in CTUs.  Kernels get a POINTER to it in device memory (NULL: one tile, the lookup is
-// skipped): a run-time index into a by-value kernel argument would move the whole argument block to local memory.
-struct TileGridDev { int nb_cols, nb_rows; uint16_t col_bd[22], row_bd[22]; };
-// first / one-past-last CTU of the tile holding CTU c along one axis
-OVD void tile_span(const uint16_t *bd, int nb, int c, int nb_ctu, int &c0, int &c1)
-{
-    c0 = 0; c1 = nb_ctu;
-    for (int i = 0; i < nb; i++) if (c >= bd[i] && c < bd[i + 1]) { c0 = bd[i]; c1 = bd[i + 1]; }
-}
 
 struct SaoK {
 #ifndef SAO_MIN_BLOCKS

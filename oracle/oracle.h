@@ -70,6 +70,11 @@ void ovo_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
                      const uint16_t *const src[3], const int src_stride[3],
                      int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                      const OVOAlfTables *tab, const OVOAlfCtuParams *ctu);
+/* same with a tile grid (OVOTileGrid below; NULL = one tile): tile edges are padded like picture borders */
+struct OVOTileGrid;
+void ovo_alf_picture_tiles(uint16_t *const dst[3], const int dst_stride[3], const uint16_t *const src[3], const int src_stride[3],
+                           int pic_w, int pic_h, int log2_ctu_s, int bitdepth, const OVOAlfTables *tab, const OVOAlfCtuParams *ctu,
+                           const struct OVOTileGrid *tg);
 
 /* Classification only (class | transpose<<5 per 4x4 block, raster over the picture's 4x4 grid). */
 void ovo_alf_classify_picture(uint8_t *cls, const uint16_t *src, int stride,

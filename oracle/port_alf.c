@@ -143,13 +143,33 @@ void ovo_alf_build_tables(OVOAlfTables *t, const OVOAlfAps *luma_aps, int nb_lum
 /* ---------------------------------------------------------------------------------------------------
  * Classification  (rcn_alf.c:283-738)
  * ------------------------------------------------------------------------------------------------- */
-typedef struct { const uint16_t *p; int stride, w, h; } Plane;
+/* (x0, y0) .. (x1, y1): the rect entry (tile) the samples are read for -- the whole plane without tiles */
+typedef struct { const uint16_t *p; int stride, w, h, x0, y0, x1, y1; } Plane;
 
 static inline int px(const Plane *pl, int x, int y)
-{   /* replicate padding == the filter-region margins at picture borders, rcn_ctu.c:363-508 */
-    x = clipi(x, 0, pl->w - 1);
-    y = clipi(y, 0, pl->h - 1);
+{   /* replicate padding == the filter-region margins at the borders of the picture / rect entry, rcn_ctu.c:363-508 */
+    x = clipi(x, pl->x0, pl->x1 - 1);
+    y = clipi(y, pl->y0, pl->y1 - 1);
     return pl->p[(size_t)y * pl->stride + x];
+}
+
+/* first / one-past-last CTU of the tile that holds CTU `c` along one axis */
+static void alf_tile_span(const uint16_t *bd, int nb, int c, int nb_ctu, int *c0, int *c1)
+{
+    *c0 = 0; *c1 = nb_ctu;
+    for (int i = 0; bd && i < nb; i++) if (c >= bd[i] && c < bd[i + 1]) { *c0 = bd[i]; *c1 = bd[i + 1]; }
+}
+/* the plane restricted to the tile of luma CTU (cx, cy); sh = 1 for the chroma planes */
+static Plane alf_tile_plane(Plane pl, const OVOTileGrid *tg, int cx, int cy, int nb_w, int nb_h, int log2_ctu_s, int sh)
+{
+    int c0, c1, r0, r1;
+    alf_tile_span(tg ? tg->col_bd : NULL, tg ? tg->nb_cols : 0, cx, nb_w, &c0, &c1);
+    alf_tile_span(tg ? tg->row_bd : NULL, tg ? tg->nb_rows : 0, cy, nb_h, &r0, &r1);
+    pl.x0 = (c0 << log2_ctu_s) >> sh; pl.y0 = (r0 << log2_ctu_s) >> sh;
+    pl.x1 = (c1 << log2_ctu_s) >> sh; pl.y1 = (r1 << log2_ctu_s) >> sh;
+    if (pl.x1 > pl.w) pl.x1 = pl.w;
+    if (pl.y1 > pl.h) pl.y1 = pl.h;
+    return pl;
 }
 
 /* The four 1-D Laplacians at one sample.  y_up / y_dn are the rows used as vertical neighbours: normally
@@ -229,18 +249,27 @@ static uint8_t alf_classify_4x4(const Plane *pl, int bx, int by, int ctu_y0, int
                                bitdepth + 4, near_vb);
 }
 
-void ovo_alf_classify_picture(uint8_t *cls, const uint16_t *src, int stride,
-                              int pic_w, int pic_h, int log2_ctu_s, int bitdepth)
+static void alf_classify_picture_tiles(uint8_t *cls, const uint16_t *src, int stride,
+                                       int pic_w, int pic_h, int log2_ctu_s, int bitdepth, const OVOTileGrid *tg)
 {
-    Plane pl = { src, stride, pic_w, pic_h };
+    Plane pl = { src, stride, pic_w, pic_h, 0, 0, pic_w, pic_h };
     int ctu_s = 1 << log2_ctu_s;
     int w4 = pic_w >> 2;
+    int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s, nb_h = (pic_h + ctu_s - 1) >> log2_ctu_s;
     for (int by = 0; by < pic_h; by += 4) {
         int ctu_y0 = by & ~(ctu_s - 1);
         int ctu_h = (ctu_y0 + ctu_s > pic_h) ? pic_h - ctu_y0 : ctu_s;
-        for (int bx = 0; bx < pic_w; bx += 4)
-            cls[(by >> 2) * w4 + (bx >> 2)] = alf_classify_4x4(&pl, bx, by, ctu_y0, ctu_h, ctu_s, bitdepth);
+        for (int bx = 0; bx < pic_w; bx += 4) {
+            Plane tp = tg ? alf_tile_plane(pl, tg, bx >> log2_ctu_s, by >> log2_ctu_s, nb_w, nb_h, log2_ctu_s, 0) : pl;
+            cls[(by >> 2) * w4 + (bx >> 2)] = alf_classify_4x4(&tp, bx, by, ctu_y0, ctu_h, ctu_s, bitdepth);
+        }
     }
+}
+
+void ovo_alf_classify_picture(uint8_t *cls, const uint16_t *src, int stride,
+                              int pic_w, int pic_h, int log2_ctu_s, int bitdepth)
+{
+    alf_classify_picture_tiles(cls, src, stride, pic_w, pic_h, log2_ctu_s, bitdepth, NULL);
 }
 
 /* ---------------------------------------------------------------------------------------------------
@@ -361,12 +390,23 @@ void ovo_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
                      int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
                      const OVOAlfTables *tab, const OVOAlfCtuParams *ctu)
 {
+    ovo_alf_picture_tiles(dst, dst_stride, src, src_stride, pic_w, pic_h, log2_ctu_s, bitdepth, tab, ctu, NULL);
+}
+
+/* tg != NULL: the edges of a tile (rect entry) are padded like picture borders (rcn_alf_filter_line's is_border flags ->
+ * rcn_extend_filter_region, rcn_alf.c:1316-1330, rcn_ctu.c:316-510): samples are fetched clamped to the CTU's tile */
+void ovo_alf_picture_tiles(uint16_t *const dst[3], const int dst_stride[3],
+                           const uint16_t *const src[3], const int src_stride[3],
+                           int pic_w, int pic_h, int log2_ctu_s, int bitdepth,
+                           const OVOAlfTables *tab, const OVOAlfCtuParams *ctu, const OVOTileGrid *tg)
+{
     int ctu_s = 1 << log2_ctu_s;
     int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s;
     int nb_h = (pic_h + ctu_s - 1) >> log2_ctu_s;
-    Plane pl[3] = { { src[0], src_stride[0], pic_w, pic_h },
-                    { src[1], src_stride[1], pic_w >> 1, pic_h >> 1 },
-                    { src[2], src_stride[2], pic_w >> 1, pic_h >> 1 } };
+    Plane pl_pic[3] = { { src[0], src_stride[0], pic_w, pic_h, 0, 0, pic_w, pic_h },
+                        { src[1], src_stride[1], pic_w >> 1, pic_h >> 1, 0, 0, pic_w >> 1, pic_h >> 1 },
+                        { src[2], src_stride[2], pic_w >> 1, pic_h >> 1, 0, 0, pic_w >> 1, pic_h >> 1 } };
+    Plane pl[3] = { pl_pic[0], pl_pic[1], pl_pic[2] };
     int w4 = pic_w >> 2;
     uint8_t *cls = malloc((size_t)w4 * (pic_h >> 2));
 
@@ -374,11 +414,12 @@ void ovo_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
         for (int y = 0; y < pl[c].h; y++)
             memcpy(dst[c] + (size_t)y * dst_stride[c], src[c] + (size_t)y * src_stride[c], pl[c].w * sizeof(uint16_t));
 
-    ovo_alf_classify_picture(cls, src[0], src_stride[0], pic_w, pic_h, log2_ctu_s, bitdepth);
+    alf_classify_picture_tiles(cls, src[0], src_stride[0], pic_w, pic_h, log2_ctu_s, bitdepth, tg);
 
     for (int cy = 0; cy < nb_h; cy++) {
         for (int cx = 0; cx < nb_w; cx++) {
             int rs = cy * nb_w + cx;
+            if (tg) for (int c = 0; c < 3; c++) pl[c] = alf_tile_plane(pl_pic[c], tg, cx, cy, nb_w, nb_h, log2_ctu_s, c != 0);
             int x0 = cx << log2_ctu_s, y0 = cy << log2_ctu_s;
             int w = (x0 + ctu_s > pic_w) ? pic_w - x0 : ctu_s;
             int h = (y0 + ctu_s > pic_h) ? pic_h - y0 : ctu_s;

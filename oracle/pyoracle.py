@@ -125,19 +125,27 @@ def alf_build_tables(luma_aps, chroma_aps, bitdepth=10, impl="port"):
     return t
 
 
-def alf_picture(planes, tables, ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1):
-    """planes: 3 contiguous uint16 arrays (post-SAO). Returns the 3 filtered planes."""
+def alf_picture(planes, tables, ctu, log2_ctu=7, bitdepth=10, impl="port", simd=1, tiles=None):
+    """planes: 3 contiguous uint16 arrays (post-SAO). Returns the 3 filtered planes.  tiles: TileGrid or None (one tile)."""
     h, w = planes[0].shape
     p, keep = _ctu_params(ctu)
+    tg = C.byref(tiles) if tiles is not None else None
     if impl == "port":
         out = [np.empty_like(pl) for pl in planes]
         src, ss = _planes_arg(planes)
         dst, ds = _planes_arg(out)
-        port().ovo_alf_picture(dst, ds, src, ss, w, h, log2_ctu, bitdepth, C.byref(tables), C.byref(p))
+        f = port().ovo_alf_picture_tiles
+        f.restype = None
+        f(dst, ds, src, ss, w, h, log2_ctu, bitdepth, C.byref(tables), C.byref(p), tg)
         return out
     out = [pl.copy() for pl in planes]
     dst, ds = _planes_arg(out)
-    ref().ovref_alf_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(tables), C.byref(p))
+    if tiles is not None:
+        f = ref().ovref_alf_picture_tiles
+        f.restype = None
+        f(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(tables), C.byref(p), tg)
+    else:
+        ref().ovref_alf_picture(dst, ds, w, h, log2_ctu, bitdepth, simd, C.byref(tables), C.byref(p))
     return out
 
 

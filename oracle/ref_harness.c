@@ -567,3 +567,52 @@ ovref_sao_picture_tiles(uint16_t *const planes[3], const int stride[3], int pic_
             free(params);
         }
 }
+
+/* ALF of a picture cut into tiles: one rect entry per tile (parameters and CC-ALF indices relative to the entry, rcn_alf.c:1319-1321, 1399) */
+void
+ovref_alf_picture_tiles(uint16_t *const planes[3], const int stride[3], int pic_w, int pic_h,
+                        int log2_ctu_s, int bitdepth, int simd,
+                        const OVOAlfTables *tab, const OVOAlfCtuParams *p, const OVOTileGrid *tg)
+{
+    int ctu_s = 1 << log2_ctu_s;
+    int nb_w = (pic_w + ctu_s - 1) >> log2_ctu_s;
+    /* in place like the decoder: an entry pads its own edges and never reads another entry's samples, so the order is free */
+    for (int tr = 0; tr < tg->nb_rows; tr++)
+        for (int tc = 0; tc < tg->nb_cols; tc++) {
+            HarnessCtx *h = harness_open(planes, stride, pic_w, pic_h, log2_ctu_s, bitdepth, simd);
+            OVCTUDec *c = h->ctudec;
+            struct ALFInfo *ai = &c->alf_info;
+            struct RectEntryInfo e;
+            memset(&e, 0, sizeof(e));
+            e.ctb_x = tg->col_bd[tc]; e.ctb_y = tg->row_bd[tr];
+            e.nb_ctu_w = tg->col_bd[tc + 1] - tg->col_bd[tc]; e.nb_ctu_h = tg->row_bd[tr + 1] - tg->row_bd[tr];
+            e.nb_ctu_rect = e.nb_ctu_w * e.nb_ctu_h;
+            e.nb_ctb_pic_w = nb_w;
+            ALFParamsCtu *params = calloc(e.nb_ctu_rect, sizeof(*params));
+            uint8_t *ccb = calloc(e.nb_ctu_rect, 1), *ccr = calloc(e.nb_ctu_rect, 1);
+            OVALFData cc[2];
+            memset(cc, 0, sizeof(cc));
+            memcpy(ai->rcn_alf.filter_coeff_dec, tab->luma_coeff, sizeof(tab->luma_coeff));
+            memcpy(ai->rcn_alf.filter_clip_dec,  tab->luma_clip,  sizeof(tab->luma_clip));
+            memcpy(ai->rcn_alf.chroma_coeff_final, tab->chroma_coeff, sizeof(tab->chroma_coeff));
+            memcpy(ai->rcn_alf.chroma_clip_final,  tab->chroma_clip,  sizeof(tab->chroma_clip));
+            memcpy(cc[0].alf_cc_mapped_coeff[0], tab->cc_coeff[0], sizeof(tab->cc_coeff[0]));
+            memcpy(cc[1].alf_cc_mapped_coeff[1], tab->cc_coeff[1], sizeof(tab->cc_coeff[1]));
+            for (int y = 0; y < e.nb_ctu_h; y++)
+                for (int x = 0; x < e.nb_ctu_w; x++) {
+                    const int i = (e.ctb_y + y) * nb_w + e.ctb_x + x, k = y * e.nb_ctu_w + x;
+                    params[k].ctb_alf_flag = p->ctb_alf_flag[i]; params[k].ctb_alf_idx = p->ctb_alf_idx[i];
+                    params[k].cb_alternative = p->cb_alternative[i]; params[k].cr_alternative = p->cr_alternative[i];
+                    ccb[k] = p->cc_idx_cb[i]; ccr[k] = p->cc_idx_cr[i];
+                }
+            ai->alf_luma_enabled_flag = 1; ai->alf_cb_enabled_flag = 1; ai->alf_cr_enabled_flag = 1;
+            ai->cc_alf_cb_enabled_flag = p->cc_cb_enabled; ai->cc_alf_cr_enabled_flag = p->cc_cr_enabled;
+            ai->aps_cc_alf_data_cb = &cc[0]; ai->aps_cc_alf_data_cr = &cc[1];
+            ai->ctb_alf_params = params;
+            ai->ctb_cc_alf_filter_idx[0] = ccb; ai->ctb_cc_alf_filter_idx[1] = ccr;
+            for (int row = 0; row < e.nb_ctu_h; row++)
+                c->rcn_funcs.alf.rcn_alf_filter_line(c, &e, row);
+            harness_close(h);
+            free(params); free(ccb); free(ccr);
+        }
+}

@@ -73,6 +73,8 @@ int ovgpu_film_grain_picture(OVGPUCtx *c, OVGPUFilmGrainSynth *, OVGPUPicture *d
 }
 
 int ovgpu_tile_grid_check(const OVGPUTileGrid *, int, int) { return 0; }
+int ovgpu_alf_params_set_tiles(OVGPUCtx *c, OVGPUAlfParams *, const OVGPUTileGrid *t)
+{ return t && t->nb_cols * t->nb_rows > 1 ? fail(c, OVGPU_EINVAL, "tiles are not part of the ABI emulation") : 0; }
 int ovgpu_sao_params_set_tiles(OVGPUCtx *c, OVGPUSaoParams *, const OVGPUTileGrid *t)
 { return t && t->nb_cols * t->nb_rows > 1 ? fail(c, OVGPU_EINVAL, "tiles are not part of the ABI emulation") : 0; }
 

@@ -58,12 +58,28 @@ extern "C" {
 
 void emu_set_reverse_block_order(int on) { ovd_emu_reverse_blocks = on; }
 
+int emu_alf_picture_tiles(uint16_t *const dst[3], const int dst_stride[3],
+                          const uint16_t *const src[3], const int src_stride[3],
+                          int w, int h, int log2_ctu, int bitdepth,
+                          const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
+                          int cc_cb_enabled, int cc_cr_enabled, const OVGPUTileGrid *tiles);
+
 int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
                     const uint16_t *const src[3], const int src_stride[3],
                     int w, int h, int log2_ctu, int bitdepth,
                     const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
                     int cc_cb_enabled, int cc_cr_enabled)
 {
+    return emu_alf_picture_tiles(dst, dst_stride, src, src_stride, w, h, log2_ctu, bitdepth, tab, ctu, cc_idx, cc_cb_enabled, cc_cr_enabled, NULL);
+}
+
+int emu_alf_picture_tiles(uint16_t *const dst[3], const int dst_stride[3],
+                          const uint16_t *const src[3], const int src_stride[3],
+                          int w, int h, int log2_ctu, int bitdepth,
+                          const OVGPUAlfTables *tab, const OVGPUAlfCtu *ctu, const uint8_t *const cc_idx[2],
+                          int cc_cb_enabled, int cc_cr_enabled, const OVGPUTileGrid *tiles)
+{
+    const TileGridDev *tgd = tiles && tiles->nb_cols * tiles->nb_rows > 1 ? (const TileGridDev *)tiles : NULL;
     AlfGeom g = alf_geom(w, h, log2_ctu);
     int n = g.nb_ctu_w * g.nb_ctu_h;
     std::vector<uint32_t> ltab((size_t)OVGPU_ALF_NUM_SETS * ALF_TAB_SET_WORDS + 4);
@@ -77,12 +93,12 @@ int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
     if (wide) {
         typedef AlfLumaK<true> K;
         K::Args a = { src[0], dst[0], src_stride[0], dst_stride[0], w, h, log2_ctu, bitdepth,
-                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data() };
+                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data(), tgd };
         ovd_emulate<K>(a, grid, K::SMEM_BYTES);
     } else {
         typedef AlfLumaK<false> K;
         K::Args a = { src[0], dst[0], src_stride[0], dst_stride[0], w, h, log2_ctu, bitdepth,
-                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data() };
+                      g.l_tw, g.l_th, g.l_tx, g.l_ty, g.nb_ctu_w, lt, dctu.data(), tgd };
         ovd_emulate<K>(a, grid, K::SMEM_BYTES);
     }
     {
@@ -96,6 +112,7 @@ int emu_alf_picture(uint16_t *const dst[3], const int dst_stride[3],
         a.cc_enabled[0] = cc_cb_enabled && cc_idx && cc_idx[0];
         a.cc_enabled[1] = cc_cr_enabled && cc_idx && cc_idx[1];
         a.ctu = dctu.data();
+        a.tiles = tgd;
         alf_pack_chroma_tab(&a.tab, tab);
         ovd_emulate<K>(a, ovd_dim3(g.nb_ctu_w * g.c_tx, g.nb_ctu_h * g.c_ty, 2), K::SMEM_BYTES);
     }

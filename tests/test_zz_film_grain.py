@@ -218,3 +218,61 @@ def test_gpu_sao_tile_edges(po, w, h, log2, cols, rows, seed):
         prm.destroy(); src.destroy(); dst.destroy()
     finally:
         ctx.close()
+
+
+# ---- tile edges as filter borders: ALF (classification, luma 7x7, chroma 5x5, CC-ALF) -----------------------------------------------
+ALF_TILE_CASES = [(416, 240, 6, [0, 3, 7], [0, 2, 4], 1, "natural"), (832, 480, 7, [0, 2, 5, 7], [0, 1, 4], 2, "noise"),
+                  (416, 240, 5, [0, 5, 13], [0, 1, 2, 8], 3, "noise"), (1920, 1080, 7, [0, 4, 9, 15], [0, 3, 9], 4, "natural")]
+
+
+@pytest.mark.parametrize("w,h,log2,cols,rows,seed,kind", ALF_TILE_CASES)
+def test_alf_tile_edges_port_vs_compiled_reference_and_emulated_kernels(po, emu, w, h, log2, cols, rows, seed, kind):
+    """the reference driven one rect entry per tile (rcn_alf_filter_line pads an entry's edges by replication) == the oracle with a
+    tile grid == the ALF kernels' source with the grid"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    planes, tab, ctu, _ = helpers.alf_case(po, w, h, seed, log2, kind)
+    tg = po.make_tile_grid(cols, rows)
+    want = po.alf_picture(planes, tab, ctu, log2, impl="port", tiles=tg)
+    assert all(not np.array_equal(a, b) for a, b in zip(want, po.alf_picture(planes, tab, ctu, log2, impl="port")))
+    if po.ref_available():
+        got = po.alf_picture(planes, tab, ctu, log2, impl="ref", simd=0, tiles=tg)
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+    out = [np.zeros_like(p) for p in planes]
+    src, ss = helpers.planes_arg(planes); dst, ds = helpers.planes_arg(out)
+    rows_ = helpers.alf_ctu_rows(ctu)
+    u8p = C.POINTER(C.c_uint8)
+    cc0 = np.ascontiguousarray(ctu["cc_cb"], dtype=np.uint8); cc1 = np.ascontiguousarray(ctu["cc_cr"], dtype=np.uint8)
+    cc = (u8p * 2)(cc0.ctypes.data_as(u8p), cc1.ctypes.data_as(u8p))
+    emu.emu_alf_picture_tiles(dst, ds, src, ss, w, h, log2, 10, C.byref(tab), C.c_void_p(rows_.ctypes.data), cc,
+                              int(ctu["cc_cb_enabled"]), int(ctu["cc_cr_enabled"]), C.byref(tg))
+    for a, b in zip(want, out):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,log2,cols,rows,seed,kind", ALF_TILE_CASES)
+def test_gpu_alf_tile_edges(po, w, h, log2, cols, rows, seed, kind):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from openvvc_b200 import api
+    ctx = api.Ctx(0)
+    try:
+        planes, tab, ctu, _ = helpers.alf_case(po, w, h, seed, log2, kind)
+        want = po.alf_picture(planes, tab, ctu, log2, impl="port", tiles=po.make_tile_grid(cols, rows))
+        src = ctx.picture(w, h); src.upload(planes)
+        dst = ctx.picture(w, h)
+        prm = api.AlfParams(ctx, w, h, log2)
+        prm.upload(helpers.gpu_tables(tab), api.alf_ctu_array(ctu), (ctu["cc_cb"], ctu["cc_cr"]), (ctu["cc_cb_enabled"], ctu["cc_cr_enabled"]))
+        prm.set_tiles(cols, rows)
+        prm.run(dst, src)
+        for a, b in zip(want, dst.download()):
+            assert np.array_equal(a, b)
+        prm.set_tiles(None)
+        prm.run(dst, src)
+        for a, b in zip(po.alf_picture(planes, tab, ctu, log2, impl="port"), dst.download()):
+            assert np.array_equal(a, b)
+        prm.destroy(); src.destroy(); dst.destroy()
+    finally:
+        ctx.close()
