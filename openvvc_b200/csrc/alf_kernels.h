@@ -358,7 +358,7 @@ struct AlfLumaK {
 // Chroma 5x5 + CC-ALF (one CTA = one 64x32 chroma tile of one component)
 // =========================================================================================================
 #ifndef ALF_CHROMA_MIN_BLOCKS
-#define ALF_CHROMA_MIN_BLOCKS 6            /* measured 4 / 5 / 6: 30.0 / 29.1 / 28.8 us per 4K picture */
+#define ALF_CHROMA_MIN_BLOCKS 5            /* measured 4 / 5 / 6: 30.0 / 29.1 / 28.8 us per 4K picture; 6 (40 registers) spills since the tile rectangle joined the CTA state */
 #endif
 struct AlfChromaK {
     static const int THREADS = 256, MIN_BLOCKS = ALF_CHROMA_MIN_BLOCKS, PHASES = 2;
