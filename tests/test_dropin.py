@@ -115,6 +115,26 @@ def test_recorder_gpu(stream_dir, name):
     check_dropin(stream_dir, name, binary, 4, table)
 
 
+def test_pictures_of_several_tiles_are_fabricated_and_refused(stream_dir):
+    """tools/vvc_stream.py writes pictures of 2 x 2 tiles (one slice, four CABAC sub-streams with entry point offsets) that the
+    stock decoder takes; the back end's recorders are per entry decoder and refuse such a picture loudly instead of producing a
+    wrong one (limits) -- the tile-edge arithmetic of SAO / ALF itself is pinned in tests/test_zz_film_grain.py"""
+    binary = os.path.join(BUILD, "dectest_emu")
+    if not os.path.exists(binary):
+        pytest.skip("build/dectest_emu not built")
+    path = os.path.join(str(stream_dir), "tiles.266")
+    md5, n = vs.make_stream(path, 416, 240, 3, gop=1, seed=37, preset="ctc", tiles=([2, 2], [1, 1]), verify=True)
+    assert n == 3
+    base = os.path.join(str(stream_dir), "tiles")
+    # what the generative run (SIMD table) reconstructed is what the stream decodes to, whatever the number of entry threads
+    for threads in (1, 4):
+        assert decode(os.path.join(REF, "dectest"), path, base + "_simd.yuv", threads=threads)[0] == md5
+    assert decode(os.path.join(REF, "dectest_c"), path, base + "_c1.yuv")[0] == decode(os.path.join(REF, "dectest_c"), path, base + "_c4.yuv", threads=4)[0]
+    env = dict(os.environ, OVVC_RCN_BACKEND="cuda")
+    r = subprocess.run([binary, "-i", path, "-o", base + "_emu.yuv", "-t", "1", "-e", "1"], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "pictures with several tiles are not supported" in r.stderr, r.stderr[-1500:]
+
+
 def test_backend_off_is_the_stock_decoder(stream_dir):
     """without OVVC_RCN_BACKEND=cuda the library is the reference: same output as oracle/_ref/dectest (SIMD table)"""
     binary = os.path.join(BUILD, "dectest_emu")
