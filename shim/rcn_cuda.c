@@ -24,9 +24,11 @@
  * stays the reference's: transform trees, TUs, ISP sub-trees and the deblocking pre-processing still run through the STOCK
  * control functions, with every sample-touching leaf slot replaced by a no-op or a recorder.
  *
- * One tile (rect entry) per picture, 10 bit: what the reference's CI covers for random access.  Pictures may change size inside
- * a sequence (reference picture resampling): the per-picture objects follow the picture's size and the slice's scale factors go
- * with the MC commands.  Anything else is left to the stock table (the wrapper does not install the recorders). */
+ * 10 bit.  Pictures may change size inside a sequence (reference picture resampling): the per-picture objects follow the picture's
+ * size and the slice's scale factors go with the MC commands.  Pictures of several tiles (rect entries; one slice per picture): an
+ * entry decoder hands what it recorded to the picture's accumulator when its entry ends (entry threads move on to other pictures), and
+ * the one that completes the picture issues it from the accumulated lists -- with the tile grid, since the reference's SAO and ALF
+ * treat an entry's edges as picture borders.  Anything else is left to the stock table (the wrapper does not install the recorders). */
 #include <pthread.h>
 #include <stddef.h>
 #include <stdio.h>
@@ -75,6 +77,21 @@ struct ISPTUInfo { uint8_t cbf_mask, tr_skip_mask, cu_mts_flag, cu_mts_idx, lfns
 
 enum { FRAME_IDLE = 0, FRAME_IN_FLIGHT = 1, FRAME_DONE = 2 };
 
+typedef struct DmvrPatch { uint16_t ctb_x, ctb_y; uint8_t x0, y0, log2_w, log2_h; OVMV mv0, mv1; } DmvrPatch;
+
+/* what the entries of a picture of several tiles have recorded so far (host memory; copied into the staging buffers of the entry
+ * decoder that completes the picture) */
+typedef struct ShimAcc {
+    const OVFrame *frame;           /* the picture being accumulated, NULL when idle */
+    int w, h, ctus_done, nb_col, nb_row, dbf_used, failed;
+    uint16_t col[24], row[24];      /* where the entries begin (CTUs) */
+    OVGPUMcCmd *mc; int nb_mc, cap_mc; OVGPUProfInfo *prof; int nb_prof, cap_prof; DmvrPatch *dmvr; int nb_dmvr, cap_dmvr;
+    OVGPUTuCmd *tu; int nb_tu, cap_tu; int16_t *coeffs; int nb_coeffs, cap_coeffs; OVGPULmcsAnchor *anchors; int nb_anchors, cap_anchors;
+    OVGPUIntraCmd *icmds; int nb_i, cap_i; OVGPUIspInfo *isp; int nb_isp, cap_isp;
+    uint32_t *ver[OVGPU_DBF_NB_MAPS], *hor[OVGPU_DBF_NB_MAPS]; uint8_t *qp[3];
+    OVGPUSaoCtu *sao_ctu; OVGPUAlfCtu *alf_ctu; uint8_t *cc_idx[2];
+} ShimAcc;
+
 typedef struct ShimFrame {
     void *key;                      /* frame->data[0]: stable for the life of the pool element */
     int w, h;
@@ -82,16 +99,17 @@ typedef struct ShimFrame {
     int state;
     OVPicture *pic;                 /* from the first deferred line report */
     unsigned long stamp;
+    ShimAcc acc;
 } ShimFrame;
-
-typedef struct DmvrPatch { uint16_t ctb_x, ctb_y; uint8_t x0, y0, log2_w, log2_h; OVMV mv0, mv1; } DmvrPatch;
 
 typedef struct ShimRec {
     OVCTUDec *ctudec;
     struct RCNFunctions stock;      /* the table rcn_init_functions_stock produced for this slice */
     OVGPUCtx *ctx;
     int w, h, log2_ctu, nb_ctu_w, nb_ctu_h;
-    uint8_t ict_type, collocated, active, failed;
+    uint8_t ict_type, collocated, active, failed, multi;
+    const OVGPUSaoCtu *use_sao; const OVGPUAlfCtu *use_alf; const uint8_t *use_cc[2];      /* per-CTU parameters the picture is issued with */
+    OVGPUAlfCtu *alf_ctu; uint8_t *cc_idx[2];
     const OVFrame *frame;
     ShimFrame *sf;
     const struct OVLMCSData *lmcs_data;
@@ -113,14 +131,14 @@ typedef struct ShimRec {
 } ShimRec;
 
 static struct {
-    pthread_mutex_t mtx;
+    pthread_mutex_t mtx, acc_mtx;
     pthread_cond_t cnd;
     ShimRec *recs[SHIM_MAX_RECS];
     int nb_recs;
     ShimFrame frames[SHIM_MAX_FRAMES];
     unsigned long stamp;
     int enabled, device, verbose;
-} g = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, { 0 }, 0, { { 0 } }, 0, -1, 0, 0 };
+} g = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, { 0 }, 0, { { 0 } }, 0, -1, 0, 0 };
 
 static __thread ShimRec *tls_rec;
 
@@ -241,12 +259,31 @@ static void rec_grow_tu(ShimRec *r, int need_cmds, size_t need_coeffs)
         }                                                                              \
     } while (0)
 
+static void acc_begin(ShimAcc *a, const OVFrame *f, int w, int h, int ncw, int nch)
+{
+    const int w_u = w >> 2, h_u = h >> 2;
+    if (a->w != w || a->h != h) {
+        for (int k = 0; k < OVGPU_DBF_NB_MAPS; k++) {
+            a->ver[k] = realloc(a->ver[k], sizeof(uint32_t) * nch * (w_u + 1)); a->hor[k] = realloc(a->hor[k], sizeof(uint32_t) * ncw * (h_u + 1));
+            if (!a->ver[k] || !a->hor[k]) shim_fatal("out of memory");
+        }
+        for (int k = 0; k < 3; k++) { a->qp[k] = realloc(a->qp[k], (size_t)w_u * h_u); if (!a->qp[k]) shim_fatal("out of memory"); }
+        a->sao_ctu = realloc(a->sao_ctu, sizeof(*a->sao_ctu) * ncw * nch); a->alf_ctu = realloc(a->alf_ctu, sizeof(*a->alf_ctu) * ncw * nch);
+        a->cc_idx[0] = realloc(a->cc_idx[0], (size_t)ncw * nch); a->cc_idx[1] = realloc(a->cc_idx[1], (size_t)ncw * nch);
+        if (!a->sao_ctu || !a->alf_ctu || !a->cc_idx[0] || !a->cc_idx[1]) shim_fatal("out of memory");
+        a->w = w; a->h = h;
+    }
+    a->frame = f;
+    a->ctus_done = a->nb_col = a->nb_row = a->dbf_used = a->failed = 0;
+    a->nb_mc = a->nb_prof = a->nb_dmvr = a->nb_tu = a->nb_coeffs = a->nb_anchors = a->nb_i = a->nb_isp = 0;
+}
+
 static void rec_begin_picture(ShimRec *r, const OVFrame *f, const struct RectEntryInfo *e, int log2_ctu)
 {
     OVCTUDec *c = r->ctudec;
     const int w = c->pic_w, h = c->pic_h, ctu = 1 << log2_ctu;
     const int ncw = (w + ctu - 1) >> log2_ctu, nch = (h + ctu - 1) >> log2_ctu;
-    if (e->ctb_x || e->ctb_y || e->nb_ctu_w != ncw || e->nb_ctu_h != nch) shim_fatal("pictures with several tiles are not supported by the CUDA back end");
+    r->multi = e->ctb_x || e->ctb_y || e->nb_ctu_w != ncw || e->nb_ctu_h != nch;
     if ((int)f->width != w || (int)f->height != h) shim_fatal("frame size differs from the picture size");
     if (!r->ctx && ovgpu_ctx_create(&r->ctx, g.device, NULL) < 0) shim_fatal("no usable sm_100 device (ovgpu_ctx_create)");
     if (r->w != w || r->h != h || r->log2_ctu != log2_ctu) {
@@ -257,6 +294,9 @@ static void rec_begin_picture(ShimRec *r, const OVFrame *f, const struct RectEnt
             ovgpu_alf_params_create(r->ctx, w, h, log2_ctu, &r->alf) < 0) shim_fatal("device allocation for a picture failed");
         if (!r->lmcs && ovgpu_lmcs_create(r->ctx, &r->lmcs) < 0) shim_fatal("LMCS object");
         r->sao_ctu = realloc(r->sao_ctu, sizeof(*r->sao_ctu) * ncw * nch);
+        r->alf_ctu = realloc(r->alf_ctu, sizeof(*r->alf_ctu) * ncw * nch);
+        r->cc_idx[0] = realloc(r->cc_idx[0], (size_t)ncw * nch); r->cc_idx[1] = realloc(r->cc_idx[1], (size_t)ncw * nch);
+        if (!r->sao_ctu || !r->alf_ctu || !r->cc_idx[0] || !r->cc_idx[1]) shim_fatal("out of memory");
         r->w = w; r->h = h; r->log2_ctu = log2_ctu;
     }
     r->nb_ctu_w = ncw; r->nb_ctu_h = nch;
@@ -270,8 +310,11 @@ static void rec_begin_picture(ShimRec *r, const OVFrame *f, const struct RectEnt
     r->frame = f;
     pthread_mutex_lock(&g.mtx);
     r->sf = frame_lookup(f, 1, r->ctx);
-    r->sf->state = FRAME_IN_FLIGHT;
-    r->sf->pic = NULL;
+    if (!(r->multi && r->sf->state == FRAME_IN_FLIGHT && r->sf->acc.frame == f)) {         /* else: a later entry of a picture under way */
+        r->sf->state = FRAME_IN_FLIGHT;
+        r->sf->pic = NULL;
+        if (r->multi) acc_begin(&r->sf->acc, f, w, h, ncw, nch);
+    }
     pthread_mutex_unlock(&g.mtx);
     r->active = 1;
 }
@@ -794,7 +837,130 @@ static void rec_dump(ShimRec *r)
     }
 }
 
-static void rec_end_picture(ShimRec *r)
+/* the entry's per-CTU SAO / ALF parameters (arrays of the entry decoder, indexed inside the entry: rcn_sao.c:221, rcn_alf.c:1319) ->
+ * picture-level arrays in raster order */
+static void entry_ctu_params(ShimRec *r, const struct RectEntryInfo *e, OVGPUSaoCtu *sao, OVGPUAlfCtu *alf, uint8_t *const cc[2])
+{
+    OVCTUDec *c = r->ctudec;
+    const struct ALFInfo *ai = &c->alf_info;
+    const int ncw = r->nb_ctu_w;
+    const int sao_on = c->sao_info.sao_luma_flag || c->sao_info.sao_chroma_flag;
+    const int alf_on = ai->alf_luma_enabled_flag || ai->alf_cb_enabled_flag || ai->alf_cr_enabled_flag;
+    const uint8_t en = (uint8_t)((ai->alf_luma_enabled_flag ? 4 : 0) | (ai->alf_cb_enabled_flag ? 2 : 0) | (ai->alf_cr_enabled_flag ? 1 : 0));
+    for (int y = 0; y < e->nb_ctu_h; y++) for (int x = 0; x < e->nb_ctu_w; x++) {
+        const int i = y * e->nb_ctu_w + x, o = (e->ctb_y + y) * ncw + e->ctb_x + x;
+        if (sao_on && c->sao_info.sao_params) {
+            const SAOParamsCtu *s = &c->sao_info.sao_params[i];
+            OVGPUSaoCtu *d = &sao[o];
+            memcpy(d->offset_val, s->offset_val, sizeof(d->offset_val));
+            for (int k = 0; k < 3; k++) {
+                const int on = k ? c->sao_info.sao_chroma_flag : c->sao_info.sao_luma_flag;
+                d->band_position[k] = s->band_position[k]; d->eo_class[k] = s->eo_class[k]; d->type_idx[k] = on ? s->type_idx[k] : 0;
+            }
+            d->pad = 0;
+        }
+        if (alf_on && ai->ctb_alf_params) {
+            const ALFParamsCtu *s = &ai->ctb_alf_params[i];
+            alf[o].ctb_alf_flag = s->ctb_alf_flag & en; alf[o].ctb_alf_idx = s->ctb_alf_idx;
+            alf[o].cb_alternative = s->cb_alternative; alf[o].cr_alternative = s->cr_alternative;
+            if (ai->cc_alf_cb_enabled_flag && ai->ctb_cc_alf_filter_idx[0]) cc[0][o] = ai->ctb_cc_alf_filter_idx[0][i];
+            if (ai->cc_alf_cr_enabled_flag && ai->ctb_cc_alf_filter_idx[1]) cc[1][o] = ai->ctb_cc_alf_filter_idx[1][i];
+        }
+    }
+}
+
+#define ACC_APPEND(dst, nb, cap, src, n, type)                            \
+    do {                                                                  \
+        GROW(dst, cap, (nb) + (n) + 1, type);                             \
+        if (n) memcpy((dst) + (nb), (src), sizeof(type) * (size_t)(n));   \
+    } while (0)
+
+/* an entry of a picture of several tiles is over: its lists go to the picture's accumulator (indices into the lists re-based), its
+ * CTUs' deblocking maps and filter parameters to the picture-level planes.  Returns 1 when the picture is complete.  g.mtx held. */
+static int acc_take_entry(ShimAcc *a, ShimRec *r, const struct RectEntryInfo *e)
+{
+    const int n_u = (1 << r->log2_ctu) >> 2, w_u = r->w >> 2, h_u = r->h >> 2, ncw = r->nb_ctu_w, nch = r->nb_ctu_h;
+    ACC_APPEND(a->mc, a->nb_mc, a->cap_mc, r->mc_cmds, r->nb_mc, OVGPUMcCmd);
+    for (int i = 0; i < r->nb_mc; i++) if (a->mc[a->nb_mc + i].tool == OVGPU_MC_TOOL_PROF) a->mc[a->nb_mc + i].aux += (uint32_t)a->nb_prof << 8;
+    ACC_APPEND(a->prof, a->nb_prof, a->cap_prof, r->prof, r->nb_prof, OVGPUProfInfo);
+    ACC_APPEND(a->dmvr, a->nb_dmvr, a->cap_dmvr, r->dmvr, r->nb_dmvr, DmvrPatch);
+    ACC_APPEND(a->tu, a->nb_tu, a->cap_tu, r->tu_cmds, r->nb_tu, OVGPUTuCmd);
+    for (int i = 0; i < r->nb_tu; i++) {
+        OVGPUTuCmd *m = &a->tu[a->nb_tu + i];
+        for (int k = 0; k < 3; k++) m->coeff_off[k] += (uint32_t)a->nb_coeffs;
+        if (m->flags & OVGPU_TU_SCALE_ANCHOR) m->scale_anchor = (uint16_t)(m->scale_anchor + a->nb_anchors);
+    }
+    ACC_APPEND(a->coeffs, a->nb_coeffs, a->cap_coeffs, r->coeffs, (int)r->nb_coeffs, int16_t);
+    ACC_APPEND(a->anchors, a->nb_anchors, a->cap_anchors, r->anchors, r->nb_anchors, OVGPULmcsAnchor);
+    ACC_APPEND(a->icmds, a->nb_i, a->cap_i, r->icmds, r->nb_i, OVGPUIntraCmd);
+    for (int i = 0; i < r->nb_i; i++) {
+        OVGPUIntraCmd *m = &a->icmds[a->nb_i + i];
+        if (m->flags & OVGPU_INTRA_ISP) { const int idx = (m->pad[0] | (m->pad[1] << 8)) + a->nb_isp; m->pad[0] = (uint8_t)(idx & 0xff); m->pad[1] = (uint8_t)(idx >> 8); }
+    }
+    ACC_APPEND(a->isp, a->nb_isp, a->cap_isp, r->isp, r->nb_isp, OVGPUIspInfo);
+    a->nb_mc += r->nb_mc; a->nb_prof += r->nb_prof; a->nb_dmvr += r->nb_dmvr; a->nb_tu += r->nb_tu; a->nb_coeffs += (int)r->nb_coeffs;
+    a->nb_anchors += r->nb_anchors; a->nb_i += r->nb_i; a->nb_isp += r->nb_isp;
+    a->dbf_used |= r->dbf_used; a->failed |= r->failed;
+    /* deblocking: the words of the entry's CTUs (dbf_record_ctu's layout; the far border column / row only at the picture's border) */
+    const int cx0 = e->ctb_x, cx1 = e->ctb_x + e->nb_ctu_w, cy0 = e->ctb_y, cy1 = e->ctb_y + e->nb_ctu_h;
+    const int nv = cx1 == ncw ? w_u + 1 - cx0 * n_u : (cx1 - cx0) * n_u, nh = cy1 == nch ? h_u + 1 - cy0 * n_u : (cy1 - cy0) * n_u;
+    for (int k = 0; k < OVGPU_DBF_NB_MAPS; k++) {
+        for (int cy = cy0; cy < cy1; cy++) { const size_t o = (size_t)cy * (w_u + 1) + cx0 * n_u; memcpy(a->ver[k] + o, r->maps.ver[k] + o, sizeof(uint32_t) * nv); }
+        for (int cx = cx0; cx < cx1; cx++) { const size_t o = (size_t)cx * (h_u + 1) + cy0 * n_u; memcpy(a->hor[k] + o, r->maps.hor[k] + o, sizeof(uint32_t) * nh); }
+    }
+    /* the reference deblocks entry by entry with the neighbour flags of the entry (ctu_lft / ctu_abv in rcn_dbf_ctu, rcn_df.c:2176-
+     * 2177): the edges that lie on an entry's left and upper border are never filtered, whatever the maps say.  Their boundary
+     * strength goes to 0; the edge bits stay, the filter lengths of the neighbouring edges are derived from them */
+    for (int k = 0; k < OVGPU_DBF_NB_MAPS; k++) {
+        if (k != OVGPU_DBF_BS1 && k != OVGPU_DBF_BS2 && k != OVGPU_DBF_BS1_CB && k != OVGPU_DBF_BS1_CR && k != OVGPU_DBF_BS2_C) continue;
+        if (cx0) for (int cy = cy0; cy < cy1; cy++) a->ver[k][(size_t)cy * (w_u + 1) + cx0 * n_u] = 0;
+        if (cy0) for (int cx = cx0; cx < cx1; cx++) a->hor[k][(size_t)cx * (h_u + 1) + cy0 * n_u] = 0;
+    }
+    const int x_u0 = cx0 * n_u, x_u1 = cx1 * n_u < w_u ? cx1 * n_u : w_u, y_u1 = cy1 * n_u < h_u ? cy1 * n_u : h_u;
+    for (int k = 0; k < 3; k++) for (int y = cy0 * n_u; y < y_u1; y++) memcpy(a->qp[k] + (size_t)y * w_u + x_u0, r->maps.qp[k] + (size_t)y * w_u + x_u0, x_u1 - x_u0);
+    entry_ctu_params(r, e, a->sao_ctu, a->alf_ctu, a->cc_idx);
+    /* the tile grid, from where the entries begin */
+    int i;
+    for (i = 0; i < a->nb_col && a->col[i] != cx0; i++) ;
+    if (i == a->nb_col && a->nb_col < 21) a->col[a->nb_col++] = (uint16_t)cx0;
+    for (i = 0; i < a->nb_row && a->row[i] != cy0; i++) ;
+    if (i == a->nb_row && a->nb_row < 21) a->row[a->nb_row++] = (uint16_t)cy0;
+    a->ctus_done += e->nb_ctu_w * e->nb_ctu_h;
+    return a->ctus_done == ncw * nch;
+}
+
+static int cmp_u16(const void *a, const void *b) { return (int)*(const uint16_t *)a - (int)*(const uint16_t *)b; }
+
+/* the accumulated picture -> the staging buffers of the entry decoder that completed it */
+static void acc_load(ShimAcc *a, ShimRec *r, OVGPUTileGrid *grid)
+{
+    const int w_u = r->w >> 2, h_u = r->h >> 2, ncw = r->nb_ctu_w, nch = r->nb_ctu_h;
+    r->nb_mc = r->nb_prof = r->nb_tu = 0; r->nb_coeffs = 0;
+    rec_grow_mc(r, a->nb_mc + 1, a->nb_prof + 1);
+    rec_grow_tu(r, a->nb_tu + 1, (size_t)a->nb_coeffs + 1);
+    memcpy(r->mc_cmds, a->mc, sizeof(OVGPUMcCmd) * a->nb_mc); memcpy(r->prof, a->prof, sizeof(OVGPUProfInfo) * a->nb_prof);
+    memcpy(r->tu_cmds, a->tu, sizeof(OVGPUTuCmd) * a->nb_tu); memcpy(r->coeffs, a->coeffs, sizeof(int16_t) * (size_t)a->nb_coeffs);
+    GROW(r->dmvr, r->cap_dmvr, a->nb_dmvr + 1, DmvrPatch); memcpy(r->dmvr, a->dmvr, sizeof(DmvrPatch) * a->nb_dmvr);
+    GROW(r->anchors, r->cap_anchors, a->nb_anchors + 1, OVGPULmcsAnchor); memcpy(r->anchors, a->anchors, sizeof(OVGPULmcsAnchor) * a->nb_anchors);
+    GROW(r->icmds, r->cap_i, a->nb_i + 1, OVGPUIntraCmd); memcpy(r->icmds, a->icmds, sizeof(OVGPUIntraCmd) * a->nb_i);
+    GROW(r->isp, r->cap_isp, a->nb_isp + 1, OVGPUIspInfo); memcpy(r->isp, a->isp, sizeof(OVGPUIspInfo) * a->nb_isp);
+    r->nb_mc = a->nb_mc; r->nb_prof = a->nb_prof; r->nb_dmvr = a->nb_dmvr; r->nb_tu = a->nb_tu; r->nb_coeffs = (size_t)a->nb_coeffs;
+    r->nb_anchors = a->nb_anchors; r->nb_i = a->nb_i; r->nb_isp = a->nb_isp; r->dbf_used = a->dbf_used; r->failed |= a->failed;
+    for (int k = 0; k < OVGPU_DBF_NB_MAPS; k++) {
+        memcpy((uint32_t *)r->maps.ver[k], a->ver[k], sizeof(uint32_t) * nch * (w_u + 1));
+        memcpy((uint32_t *)r->maps.hor[k], a->hor[k], sizeof(uint32_t) * ncw * (h_u + 1));
+    }
+    for (int k = 0; k < 3; k++) memcpy((uint8_t *)r->maps.qp[k], a->qp[k], (size_t)w_u * h_u);
+    r->use_sao = a->sao_ctu; r->use_alf = a->alf_ctu; r->use_cc[0] = a->cc_idx[0]; r->use_cc[1] = a->cc_idx[1];
+    qsort(a->col, a->nb_col, sizeof(uint16_t), cmp_u16); qsort(a->row, a->nb_row, sizeof(uint16_t), cmp_u16);
+    memset(grid, 0, sizeof(*grid));
+    grid->nb_cols = a->nb_col; grid->nb_rows = a->nb_row;
+    for (int i = 0; i < a->nb_col; i++) grid->col_bd[i] = a->col[i];
+    for (int i = 0; i < a->nb_row; i++) grid->row_bd[i] = a->row[i];
+    grid->col_bd[a->nb_col] = (uint16_t)ncw; grid->row_bd[a->nb_row] = (uint16_t)nch;
+}
+
+static void rec_end_picture(ShimRec *r, const OVGPUTileGrid *grid)
 {
     OVCTUDec *c = r->ctudec;
     struct InterDRVCtx *ic = &c->drv_ctx.inter_ctx;
@@ -857,24 +1023,14 @@ static void rec_end_picture(ShimRec *r)
     }
     OVGPUPicture *cur = rec;
     if (sao_on && !r->failed) {
-        for (int i = 0; i < nctu; i++) {
-            const SAOParamsCtu *s = &c->sao_info.sao_params[i];
-            OVGPUSaoCtu *d = &r->sao_ctu[i];
-            memcpy(d->offset_val, s->offset_val, sizeof(d->offset_val));
-            for (int k = 0; k < 3; k++) {
-                const int on = k ? c->sao_info.sao_chroma_flag : c->sao_info.sao_luma_flag;
-                d->band_position[k] = s->band_position[k]; d->eo_class[k] = s->eo_class[k]; d->type_idx[k] = on ? s->type_idx[k] : 0;
-            }
-            d->pad = 0;
-        }
         OVGPUPicture *dst = alf_on ? r->mid : final;
-        SHIM_CHECK(r, ovgpu_sao_params_upload(x, r->sao, r->sao_ctu));
+        SHIM_CHECK(r, ovgpu_sao_params_set_tiles(x, r->sao, grid));
+        SHIM_CHECK(r, ovgpu_sao_params_upload(x, r->sao, r->use_sao));
         SHIM_CHECK(r, ovgpu_sao_picture(x, dst, cur, r->sao));
         cur = dst;
     }
     if (alf_on && !r->failed) {
         static __thread OVGPUAlfTables tab;
-        static __thread OVGPUAlfCtu *actu; static __thread int actu_cap;
         memset(&tab, 0, sizeof(tab));
         /* RCNALF (rcn_alf.h:60-66) == the first four members of OVGPUAlfTables */
         memcpy(tab.luma_coeff, ai->rcn_alf.filter_coeff_dec, sizeof(tab.luma_coeff));
@@ -883,15 +1039,10 @@ static void rec_end_picture(ShimRec *r)
         memcpy(tab.chroma_clip, ai->rcn_alf.chroma_clip_final, sizeof(tab.chroma_clip));
         if (ai->cc_alf_cb_enabled_flag && ai->aps_cc_alf_data_cb) memcpy(tab.cc_coeff[0], ai->aps_cc_alf_data_cb->alf_cc_mapped_coeff[0], sizeof(tab.cc_coeff[0]));
         if (ai->cc_alf_cr_enabled_flag && ai->aps_cc_alf_data_cr) memcpy(tab.cc_coeff[1], ai->aps_cc_alf_data_cr->alf_cc_mapped_coeff[1], sizeof(tab.cc_coeff[1]));
-        if (actu_cap < nctu) { actu = realloc(actu, sizeof(*actu) * nctu); actu_cap = nctu; }
-        const uint8_t en = (uint8_t)((ai->alf_luma_enabled_flag ? 4 : 0) | (ai->alf_cb_enabled_flag ? 2 : 0) | (ai->alf_cr_enabled_flag ? 1 : 0));
-        for (int i = 0; i < nctu; i++) {
-            const ALFParamsCtu *s = &ai->ctb_alf_params[i];
-            actu[i].ctb_alf_flag = s->ctb_alf_flag & en; actu[i].ctb_alf_idx = s->ctb_alf_idx;
-            actu[i].cb_alternative = s->cb_alternative; actu[i].cr_alternative = s->cr_alternative;
-        }
-        const uint8_t *cc[2] = { ai->cc_alf_cb_enabled_flag ? ai->ctb_cc_alf_filter_idx[0] : NULL, ai->cc_alf_cr_enabled_flag ? ai->ctb_cc_alf_filter_idx[1] : NULL };
-        SHIM_CHECK(r, ovgpu_alf_params_upload(x, r->alf, &tab, actu, cc, ai->cc_alf_cb_enabled_flag && cc[0], ai->cc_alf_cr_enabled_flag && cc[1]));
+        const uint8_t *cc[2] = { ai->cc_alf_cb_enabled_flag && ai->ctb_cc_alf_filter_idx[0] ? r->use_cc[0] : NULL,
+                                 ai->cc_alf_cr_enabled_flag && ai->ctb_cc_alf_filter_idx[1] ? r->use_cc[1] : NULL };
+        SHIM_CHECK(r, ovgpu_alf_params_set_tiles(x, r->alf, grid));
+        SHIM_CHECK(r, ovgpu_alf_params_upload(x, r->alf, &tab, r->use_alf, cc, ai->cc_alf_cb_enabled_flag && cc[0], ai->cc_alf_cr_enabled_flag && cc[1]));
         SHIM_CHECK(r, ovgpu_alf_picture(x, final, cur, r->alf));
         cur = final;
     }
@@ -902,12 +1053,14 @@ static void rec_end_picture(ShimRec *r)
     patch_dmvr(r);
     OVPicture *pic;
     pthread_mutex_lock(&g.mtx);
+    r->sf->acc.frame = NULL;
     r->sf->state = FRAME_DONE;
     pic = r->sf->pic;
     pthread_cond_broadcast(&g.cnd);
     pthread_mutex_unlock(&g.mtx);
     /* now the lines may be seen as decoded: TMVP of later pictures (drv_mvp.c:292) reads the patched MV plane */
-    if (pic) for (int y = 0; y < nch - 1; y++) ovdpb_report_decoded_ctu_line(pic, y, 0, ncw - 1);
+    /* (several tiles: the reports of the last CTU line of the other bottom entries were deferred too) */
+    if (pic) for (int y = 0; y < nch - (grid ? 0 : 1); y++) ovdpb_report_decoded_ctu_line(pic, y, 0, ncw - 1);
     r->active = 0;
     r->pictures++;
     if (g.verbose) fprintf(stderr, "rcn cuda: picture %lu of entry decoder %p: %d PU, %d TU (%zu coeffs), %d intra (%d ISP), %d anchors, %d DMVR, dbf %d sao %d alf %d lmcs %d%s\n",
@@ -918,7 +1071,24 @@ static void rec_end_picture(ShimRec *r)
 static void rec_alf_filter_line(OVCTUDec *const c, const struct RectEntryInfo *const e, uint16_t ctb_y)
 {
     ShimRec *r = rec_of(c);
-    if (r->active && ctb_y == e->nb_ctu_h - 1) rec_end_picture(r);
+    if (!r->active || ctb_y != e->nb_ctu_h - 1) return;
+    if (!r->multi) {
+        entry_ctu_params(r, e, r->sao_ctu, r->alf_ctu, r->cc_idx);
+        r->use_sao = r->sao_ctu; r->use_alf = r->alf_ctu; r->use_cc[0] = r->cc_idx[0]; r->use_cc[1] = r->cc_idx[1];
+        rec_end_picture(r, NULL);
+        return;
+    }
+    ShimAcc *a = &r->sf->acc;
+    pthread_mutex_lock(&g.acc_mtx);
+    if (g.verbose) fprintf(stderr, "rcn cuda: POC %d entry at CTU (%d, %d) recorded by %p: %d PU, %d TU, %d intra\n", (int)r->frame->poc, e->ctb_x, e->ctb_y, (void *)r->ctudec, r->nb_mc, r->nb_tu, r->nb_i);
+    const int complete = acc_take_entry(a, r, e);
+    OVGPUTileGrid grid;
+    if (complete) acc_load(a, r, &grid);
+    pthread_mutex_unlock(&g.acc_mtx);
+    if (complete) {
+        /* all the picture's entries have handed over, nobody else touches the accumulator until the next picture on this frame */
+        rec_end_picture(r, &grid);
+    } else r->active = 0;
 }
 
 /* slicedec.c is compiled with ovdpb_report_decoded_ctu_line redirected here: a CTU line of a picture the GPU has not produced yet

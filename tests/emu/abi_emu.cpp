@@ -14,8 +14,8 @@ struct OVGPUMcBatch { std::vector<OVGPUMcCmd> cmds; std::vector<OVGPUProfInfo> p
 struct OVGPUTuBatch { std::vector<OVGPUTuCmd> cmds; std::vector<int16_t> coeffs; int nb; size_t nb_coeffs; OVGPUTuSlice sl; std::vector<OVGPULmcsAnchor> anchors; };
 struct OVGPUIntraBatch { std::vector<OVGPUIntraCmd> cmds; std::vector<OVGPUIspInfo> isp; int w, h, log2_ctu, levels; };
 struct OVGPUDbfParams { int w, h, log2_ctu, beta, tc; std::vector<uint32_t> ver[OVGPU_DBF_NB_MAPS], hor[OVGPU_DBF_NB_MAPS]; std::vector<uint8_t> qp[3]; };
-struct OVGPUSaoParams { int w, h, log2_ctu; std::vector<OVGPUSaoCtu> ctu; };
-struct OVGPUAlfParams { int w, h, log2_ctu, en[2]; OVGPUAlfTables tab; std::vector<OVGPUAlfCtu> ctu; std::vector<uint8_t> cc[2]; };
+struct OVGPUSaoParams { int w, h, log2_ctu; std::vector<OVGPUSaoCtu> ctu; OVGPUTileGrid tiles; };
+struct OVGPUAlfParams { int w, h, log2_ctu, en[2]; OVGPUAlfTables tab; std::vector<OVGPUAlfCtu> ctu; std::vector<uint8_t> cc[2]; OVGPUTileGrid tiles; };
 struct OVGPULmcs { OVGPULmcsLuts luts; OVGPULmcsData data; int has_data; };
 
 static int fail(OVGPUCtx *c, int code, const char *fmt, ...)
@@ -72,11 +72,26 @@ int ovgpu_film_grain_picture(OVGPUCtx *c, OVGPUFilmGrainSynth *, OVGPUPicture *d
     return 0;
 }
 
-int ovgpu_tile_grid_check(const OVGPUTileGrid *, int, int) { return 0; }
-int ovgpu_alf_params_set_tiles(OVGPUCtx *c, OVGPUAlfParams *, const OVGPUTileGrid *t)
-{ return t && t->nb_cols * t->nb_rows > 1 ? fail(c, OVGPU_EINVAL, "tiles are not part of the ABI emulation") : 0; }
-int ovgpu_sao_params_set_tiles(OVGPUCtx *c, OVGPUSaoParams *, const OVGPUTileGrid *t)
-{ return t && t->nb_cols * t->nb_rows > 1 ? fail(c, OVGPU_EINVAL, "tiles are not part of the ABI emulation") : 0; }
+/* same checks as the product's (sao.cu): boundaries ascending from 0 to the picture's size in CTUs, at most 20 x 20 tiles */
+int ovgpu_tile_grid_check(const OVGPUTileGrid *t, int ncw, int nch)
+{
+    if (!t) return -1;
+    if (t->nb_cols < 1 || t->nb_rows < 1 || t->nb_cols > 20 || t->nb_rows > 20 || t->col_bd[0] || t->row_bd[0] ||
+        t->col_bd[t->nb_cols] != ncw || t->row_bd[t->nb_rows] != nch) return OVGPU_EINVAL;
+    for (int i = 0; i < t->nb_cols; i++) if (t->col_bd[i + 1] <= t->col_bd[i]) return OVGPU_EINVAL;
+    for (int i = 0; i < t->nb_rows; i++) if (t->row_bd[i + 1] <= t->row_bd[i]) return OVGPU_EINVAL;
+    return 0;
+}
+static int set_tiles(OVGPUCtx *c, OVGPUTileGrid *dst, const OVGPUTileGrid *t, int w, int h, int l)
+{
+    const int s = 1 << l;
+    if (!t || t->nb_cols * t->nb_rows <= 1) { memset(dst, 0, sizeof(*dst)); return 0; }
+    if (ovgpu_tile_grid_check(t, (w + s - 1) >> l, (h + s - 1) >> l) < 0) return fail(c, OVGPU_EINVAL, "tile grid does not cover the picture");
+    *dst = *t;
+    return 0;
+}
+int ovgpu_alf_params_set_tiles(OVGPUCtx *c, OVGPUAlfParams *p, const OVGPUTileGrid *t) { return set_tiles(c, &p->tiles, t, p->w, p->h, p->log2_ctu); }
+int ovgpu_sao_params_set_tiles(OVGPUCtx *c, OVGPUSaoParams *p, const OVGPUTileGrid *t) { return set_tiles(c, &p->tiles, t, p->w, p->h, p->log2_ctu); }
 
 int ovgpu_mc_batch_create(OVGPUCtx *, int max_cmds, int, OVGPUMcBatch **b) { *b = new OVGPUMcBatch(); (*b)->cmds.resize(max_cmds + 1); (*b)->prof.resize(65536); (*b)->nb = (*b)->nb_prof = (*b)->nb_dmvr = 0; return ovgpu_mc_batch_set_scaling(NULL, *b, NULL); }
 int ovgpu_mc_batch_set_scaling(OVGPUCtx *, OVGPUMcBatch *b, const OVGPUMcScaling *s)
@@ -158,7 +173,7 @@ int ovgpu_sao_params_create(OVGPUCtx *, int w, int h, int l, OVGPUSaoParams **p)
 void ovgpu_sao_params_destroy(OVGPUSaoParams *p) { delete p; }
 int ovgpu_sao_params_upload(OVGPUCtx *, OVGPUSaoParams *p, const OVGPUSaoCtu *ctu) { p->ctu.assign(ctu, ctu + nctu(p->w, p->h, p->log2_ctu)); return 0; }
 int ovgpu_sao_picture(OVGPUCtx *, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUSaoParams *p)
-{ return emu_sao_picture(dst->plane, dst->stride, src->plane, src->stride, p->w, p->h, p->log2_ctu, 10, p->ctu.data()); }
+{ return emu_sao_picture_tiles(dst->plane, dst->stride, src->plane, src->stride, p->w, p->h, p->log2_ctu, 10, p->ctu.data(), p->tiles.nb_cols * p->tiles.nb_rows > 1 ? &p->tiles : NULL); }
 
 int ovgpu_alf_params_create(OVGPUCtx *, int w, int h, int l, OVGPUAlfParams **p) { *p = new OVGPUAlfParams(); (*p)->w = w; (*p)->h = h; (*p)->log2_ctu = l; return 0; }
 void ovgpu_alf_params_destroy(OVGPUAlfParams *p) { delete p; }
@@ -172,7 +187,7 @@ int ovgpu_alf_params_upload(OVGPUCtx *, OVGPUAlfParams *p, const OVGPUAlfTables 
 int ovgpu_alf_picture(OVGPUCtx *, OVGPUPicture *dst, const OVGPUPicture *src, const OVGPUAlfParams *p)
 {
     const uint8_t *cc[2] = { p->cc[0].data(), p->cc[1].data() };
-    emu_alf_picture(dst->plane, dst->stride, src->plane, src->stride, p->w, p->h, p->log2_ctu, 10, &p->tab, p->ctu.data(), cc, p->en[0], p->en[1]);
+    emu_alf_picture_tiles(dst->plane, dst->stride, src->plane, src->stride, p->w, p->h, p->log2_ctu, 10, &p->tab, p->ctu.data(), cc, p->en[0], p->en[1], p->tiles.nb_cols * p->tiles.nb_rows > 1 ? &p->tiles : NULL);
     return 0;
 }
 

@@ -12,7 +12,7 @@
 #include "../../openvvc_b200/csrc/pp_kernels.h"
 #include "../../openvvc_b200/csrc/fg_kernels.h"
 
-static const int16_t *emu_tr_scales = NULL;     // LMCS chroma scales of the running emu_recon_picture call
+static thread_local const int16_t *emu_tr_scales = NULL;     // LMCS chroma scales of the running emu_recon_picture call
 
 template <int GROUP>
 static void emu_tr_launch(uint16_t *const dst[3], const int dst_stride[3], int bitdepth, const OVGPUTuCmd *cmds,

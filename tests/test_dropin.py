@@ -71,14 +71,14 @@ def make(stream_dir, name, table=STREAMS):
     return path
 
 
-def decode(binary, stream, out, threads=1, backend=None, extra=(), verbose=False):
+def decode(binary, stream, out, threads=1, backend=None, extra=(), verbose=False, entries=1):
     env = dict(os.environ)
     env.pop("OVVC_RCN_BACKEND", None)
     if backend:
         env["OVVC_RCN_BACKEND"] = backend
     if verbose:
         env["OVVC_RCN_VERBOSE"] = "1"
-    r = vs.run_decoder([binary, "-i", stream, "-o", out, "-t", str(threads), "-e", "1", "-l", "2"] + list(extra), env=env)
+    r = vs.run_decoder([binary, "-i", stream, "-o", out, "-t", str(threads), "-e", str(entries), "-l", "2"] + list(extra), env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "rcn cuda back end:" not in r.stderr or "failed" not in r.stderr, r.stderr[-2000:]
     return md5_file(out), r.stderr
@@ -115,24 +115,41 @@ def test_recorder_gpu(stream_dir, name):
     check_dropin(stream_dir, name, binary, 4, table)
 
 
-def test_pictures_of_several_tiles_are_fabricated_and_refused(stream_dir):
-    """tools/vvc_stream.py writes pictures of 2 x 2 tiles (one slice, four CABAC sub-streams with entry point offsets) that the
-    stock decoder takes; the back end's recorders are per entry decoder and refuse such a picture loudly instead of producing a
-    wrong one (limits) -- the tile-edge arithmetic of SAO / ALF itself is pinned in tests/test_zz_film_grain.py"""
+# pictures of several tiles (f4): name -> (preset, overrides, width, height, frames, gop, seed, (tile column widths, tile row heights) in CTUs).
+# One slice per picture, one CABAC sub-stream (rect entry) per tile; the entries are decoded by several entry threads (-e) and
+# their recordings merged into one picture on the back end's side
+TILE_STREAMS = {
+    "tiles_2x2":    ("ctc", {}, 416, 240, 9, 8, 37, ([2, 2], [1, 1])),
+    "tiles_1x2":    ("ctc", {}, 416, 240, 5, 4, 38, ([4], [1, 1])),
+    "tiles_ld_4x3": ("ctc", {}, 832, 480, 4, 1, 39, ([1, 2, 1, 3], [1, 1, 2])),
+}
+TILE_STREAMS_GPU = {"tiles_1080_4x3": ("ctc", {}, 1920, 1080, 5, 4, 40, ([4, 4, 4, 3], [3, 3, 3]))}
+
+
+def check_tiles(stream_dir, name, binary, table=TILE_STREAMS, configs=((1, 1), (4, 4), (2, 3))):
+    preset, over, w, h, n, gop, seed, tiles = table[name]
+    path = os.path.join(str(stream_dir), name + ".266")
+    if not os.path.exists(path):
+        md5, nb = vs.make_stream(path, w, h, n, gop=gop, seed=seed, preset=preset, tool_over=over, tiles=tiles, verify=True)
+        assert nb == n
+    base = os.path.join(str(stream_dir), name)
+    want, _ = decode(os.path.join(REF, "dectest_c"), path, base + "_c.yuv")
+    assert decode(os.path.join(REF, "dectest_c"), path, base + "_c44.yuv", threads=4, entries=4)[0] == want      # the reference agrees with itself
+    for threads, entries in configs:
+        got, err = decode(binary, path, base + "_%s_t%de%d.yuv" % (os.path.basename(binary), threads, entries), threads=threads, entries=entries,
+                          backend="cuda", verbose=True)
+        assert "entry at CTU" in err                                      # the entries were handed over one by one, not refused
+        assert got == want, "%s at %d frame / %d entry threads: %s, the stock decoder %s" % (name, threads, entries, got, want)
+
+
+@pytest.mark.parametrize("name", sorted(TILE_STREAMS))
+def test_tiles_emulated(stream_dir, name):
+    """pictures of several tiles through the recorders over the emulated kernels == stock decoder: lists merged across entry decoders,
+    no deblocking across entry borders, SAO / ALF with the tile grid (the reference filters entry by entry)"""
     binary = os.path.join(BUILD, "dectest_emu")
     if not os.path.exists(binary):
         pytest.skip("build/dectest_emu not built")
-    path = os.path.join(str(stream_dir), "tiles.266")
-    md5, n = vs.make_stream(path, 416, 240, 3, gop=1, seed=37, preset="ctc", tiles=([2, 2], [1, 1]), verify=True)
-    assert n == 3
-    base = os.path.join(str(stream_dir), "tiles")
-    # what the generative run (SIMD table) reconstructed is what the stream decodes to, whatever the number of entry threads
-    for threads in (1, 4):
-        assert decode(os.path.join(REF, "dectest"), path, base + "_simd.yuv", threads=threads)[0] == md5
-    assert decode(os.path.join(REF, "dectest_c"), path, base + "_c1.yuv")[0] == decode(os.path.join(REF, "dectest_c"), path, base + "_c4.yuv", threads=4)[0]
-    env = dict(os.environ, OVVC_RCN_BACKEND="cuda")
-    r = subprocess.run([binary, "-i", path, "-o", base + "_emu.yuv", "-t", "1", "-e", "1"], env=env, capture_output=True, text=True, timeout=300)
-    assert r.returncode != 0 and "pictures with several tiles are not supported" in r.stderr, r.stderr[-1500:]
+    check_tiles(stream_dir, name, binary)
 
 
 def test_backend_off_is_the_stock_decoder(stream_dir):

@@ -276,3 +276,14 @@ def test_gpu_alf_tile_edges(po, w, h, log2, cols, rows, seed, kind):
         prm.destroy(); src.destroy(); dst.destroy()
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ pictures of several tiles, drop-in
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(td.TILE_STREAMS) + sorted(td.TILE_STREAMS_GPU))
+def test_tiles_dropin_gpu(stream_dir, name):
+    """the product on pictures of several tiles: build/libovvc.so over libovvc_b200.so == stock decoder (tests/test_dropin.py has
+    the emulated form; kept in this file so that it runs after the single-tile drop-in tests)"""
+    binary = os.path.join(td.BUILD, "dectest")
+    assert os.path.exists(binary), "build/dectest missing: run python __graft_entry__.py where /root/reference exists"
+    td.check_tiles(stream_dir, name, binary, td.TILE_STREAMS if name in td.TILE_STREAMS else td.TILE_STREAMS_GPU, configs=((1, 1), (4, 4)))
