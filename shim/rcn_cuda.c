@@ -964,7 +964,7 @@ static void rec_end_picture(ShimRec *r, const OVGPUTileGrid *grid)
 {
     OVCTUDec *c = r->ctudec;
     struct InterDRVCtx *ic = &c->drv_ctx.inter_ctx;
-    const int ncw = r->nb_ctu_w, nch = r->nb_ctu_h, nctu = ncw * nch;
+    const int ncw = r->nb_ctu_w, nch = r->nb_ctu_h;
     OVGPUCtx *x = r->ctx;
     OVGPUMcRefs refs;
     memset(&refs, 0, sizeof(refs));
