@@ -122,6 +122,10 @@ TILE_STREAMS = {
     "tiles_2x2":    ("ctc", {}, 416, 240, 9, 8, 37, ([2, 2], [1, 1])),
     "tiles_1x2":    ("ctc", {}, 416, 240, 5, 4, 38, ([4], [1, 1])),
     "tiles_ld_4x3": ("ctc", {}, 832, 480, 4, 1, 39, ([1, 2, 1, 3], [1, 1, 2])),
+    # what the merge has to re-base: PROF tables and DMVR patches, ISP records, LMCS anchors
+    "tiles_mc":     ("minimal", dict(amvr=1, bcw=1, mmvd=1, smvd=1, tmvp=1, sbtmvp=1, affine=1, prof=1, bdof=1, dmvr=1, gpm=1, ciip=1), 416, 240, 9, 8, 124, ([2, 2], [1, 1])),
+    "tiles_isp":    ("minimal", dict(isp=1, mts=1, lfnst=1), 416, 240, 1, 1, 122, ([1, 3], [1, 1])),
+    "tiles_lmcs":   ("minimal", dict(lmcs=1, jcbcr=1, ciip=1, tmvp=1), 416, 240, 5, 4, 128, ([2, 2], [1, 1])),
 }
 TILE_STREAMS_GPU = {"tiles_1080_4x3": ("ctc", {}, 1920, 1080, 5, 4, 40, ([4, 4, 4, 3], [3, 3, 3]))}
 
