@@ -218,7 +218,9 @@ int emu_mc_picture_rpr(uint16_t *const dst[3], const int dst_stride[3], int w, i
         for (int l = 0; l < 2; l++)
             for (int i = 0; i < 16; i++) if (sc->scale[l][i][0] != (1 << 14) || sc->scale[l][i][1] != (1 << 14)) sm[l] |= 1u << i;
     // the work lists come from the product's device-side construction (McPrep*K), checked here against the host restatement
-    const int max_items = mc_count_items(cmds, nb_cmds) + mc_count_items(cmds, nb_cmds, sm, MC_ROUTE_RPR) + nb_cmds + 1;
+    // (a region's capacity: the <=16x16 items of the plain and resampling routes, one item per tool command, 16 tiles of 32x32 for a
+    // 128x128 command of the big route -- a picture of two such commands has no other commands to borrow room from)
+    const int max_items = mc_count_items(cmds, nb_cmds) + mc_count_items(cmds, nb_cmds, sm, MC_ROUTE_RPR) + 17 * nb_cmds + 1;
     std::vector<McItemDev> items((size_t)MC_NB_REGIONS * max_items);
     McPrepInfo info;
     memset(&info, 0, sizeof(info));

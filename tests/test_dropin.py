@@ -156,6 +156,24 @@ def test_tiles_emulated(stream_dir, name):
     check_tiles(stream_dir, name, binary)
 
 
+# pictures of one CTU row / a few CTUs: whole-CTU prediction units (the 32x32-tile route of the MC command walk with nothing else in
+# the picture), single-CTU-row SAO, truncated CTUs on both borders
+SMALL_STREAMS = {
+    "small_256x128": ("ctc", {}, 256, 128, 5, 8, 33975),
+    "small_416x128": ("ctc", {}, 416, 128, 3, 1, 22369),
+    "small_512x264": ("ctc", {}, 512, 264, 3, 8, 93605),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SMALL_STREAMS))
+def test_small_pictures_emulated(stream_dir, name):
+    binary = os.path.join(BUILD, "dectest_emu")
+    if not os.path.exists(binary):
+        pytest.skip("build/dectest_emu not built")
+    check_dropin(stream_dir, name, binary, 1, SMALL_STREAMS)
+    check_dropin(stream_dir, name, binary, 4, SMALL_STREAMS)
+
+
 def test_backend_off_is_the_stock_decoder(stream_dir):
     """without OVVC_RCN_BACKEND=cuda the library is the reference: same output as oracle/_ref/dectest (SIMD table)"""
     binary = os.path.join(BUILD, "dectest_emu")

@@ -287,3 +287,13 @@ def test_tiles_dropin_gpu(stream_dir, name):
     binary = os.path.join(td.BUILD, "dectest")
     assert os.path.exists(binary), "build/dectest missing: run python __graft_entry__.py where /root/reference exists"
     td.check_tiles(stream_dir, name, binary, td.TILE_STREAMS if name in td.TILE_STREAMS else td.TILE_STREAMS_GPU, configs=((1, 1), (4, 4)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(td.SMALL_STREAMS))
+def test_small_pictures_gpu(stream_dir, name):
+    """pictures of one CTU row / a few CTUs through the product (emulated form in tests/test_dropin.py)"""
+    binary = os.path.join(td.BUILD, "dectest")
+    assert os.path.exists(binary), "build/dectest missing: run python __graft_entry__.py where /root/reference exists"
+    td.check_dropin(stream_dir, name, binary, 1, td.SMALL_STREAMS)
+    td.check_dropin(stream_dir, name, binary, 4, td.SMALL_STREAMS)
