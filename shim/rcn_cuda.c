@@ -72,7 +72,7 @@ struct TBInfo { uint16_t last_pos; uint64_t sig_sb_map; };
 struct TUInfo { uint8_t is_sbt, cbf_mask; uint16_t pos_offset; uint8_t tr_skip_mask, cu_mts_flag, cu_mts_idx, lfnst_flag, lfnst_idx; struct TBInfo tb_info[3]; };
 struct ISPTUInfo { uint8_t cbf_mask, tr_skip_mask, cu_mts_flag, cu_mts_idx, lfnst_flag, lfnst_idx; struct TBInfo tb_info[4]; };
 
-#define SHIM_MAX_RECS   64
+#define SHIM_MAX_RECS   256
 #define SHIM_MAX_FRAMES 96
 
 enum { FRAME_IDLE = 0, FRAME_IN_FLIGHT = 1, FRAME_DONE = 2 };
