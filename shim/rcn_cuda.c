@@ -812,9 +812,10 @@ static void wait_reference(ShimRec *r, const OVPicture *p, const OVGPUPicture **
     *dev = NULL;
     if (!p || !p->frame) return;
     pthread_mutex_lock(&g.mtx);
-    ShimFrame *sf = frame_lookup(p->frame, 0, r->ctx);
-    /* picture-level form of rcn_inter_synchronization (rcn_inter.c:131-146): the reference must be complete in HBM */
-    while (sf && sf->state == FRAME_IN_FLIGHT) pthread_cond_wait(&g.cnd, &g.mtx);
+    ShimFrame *sf;
+    /* picture-level form of rcn_inter_synchronization (rcn_inter.c:131-146): the reference must be complete in HBM (looked up again
+     * after every wait: a table entry belongs to a frame only as long as its key says so) */
+    while ((sf = frame_lookup(p->frame, 0, r->ctx)) && sf->state == FRAME_IN_FLIGHT) pthread_cond_wait(&g.cnd, &g.mtx);
     if (sf && sf->state == FRAME_DONE) *dev = sf->dev;
     pthread_mutex_unlock(&g.mtx);
     if (!*dev && !r->failed) { r->failed = 1; ov_log(NULL, OVLOG_ERROR, "rcn cuda back end: reference picture POC %d is not resident on the device\n", p->poc); }
